@@ -1,0 +1,155 @@
+/* metad_b200.h -- C ABI of the B200-native (sm_100a) CV + bias-force hot path.
+ *
+ * Drop-in boundary for jglaser/metadynamics-plugin's GPU kernel drivers.  Each entry point names the
+ * reference interface it replaces (paths relative to the reference's metadynamics/ directory).  The
+ * reference drivers are C++-linkage free functions taking HOOMD types (BoxDim, Index2D, GPUPartition,
+ * CachedAllocator) and launching on the default stream; here everything is extern "C", plain pointers
+ * and sizes, an explicit stream, and an int status (0 = ok, <0 = error; text via metad_last_error()).
+ *
+ * Conventions
+ *   - d_* pointers are DEVICE pointers owned by the caller and valid for the duration of the call.
+ *   - postype / force arrays use HOOMD's single-precision layout: float4 {x,y,z,w}; postype.w holds
+ *     the integer type id as raw bits (__scalar_as_int), force.w the per-particle energy (always 0).
+ *   - Scalars that the reference reads back to the host every step (CV value, bias factor dV/ds) live in
+ *     device memory as double, so a whole step can be enqueued without a host round trip.
+ *   - All calls are asynchronous with respect to the host unless stated otherwise.
+ *   - There is no CPU fallback: without a CUDA device every call fails with METAD_ERR_CUDA.
+ */
+#ifndef METAD_B200_H
+#define METAD_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* metad_stream_t; /* == cudaStream_t */
+
+enum {
+    METAD_OK = 0,
+    METAD_ERR_INVALID = -1,     /* bad argument */
+    METAD_ERR_CUDA = -2,        /* CUDA runtime error (see metad_last_error) */
+    METAD_ERR_UNSUPPORTED = -3, /* valid in the reference, not implemented here (e.g. non power-of-two mesh) */
+    METAD_ERR_STATE = -4        /* call order violated (e.g. forces before cv) */
+};
+
+/* HOOMD BoxDim flattened to a POD (hoomd/BoxDim.h; call sites OrderParameterMesh.cc:543,570-573,
+ * LamellarOrderParameter.cc:151-159).  lo = -L/2.  Device code derives the single-precision members
+ * exactly as a SINGLE_PRECISION HOOMD build would: L=(float)L, hi=L/2, lo=-hi. */
+typedef struct metad_box {
+    double L[3];    /* box lengths Lx, Ly, Lz */
+    double tilt[3]; /* xy, xz, yz */
+} metad_box;
+
+int metad_version(void);
+const char* metad_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * LamellarOrderParameter
+ * replaces gpu_calculate_fourier_modes (LamellarOrderParameterGPU.cuh:21-29, .cu:104-147) + the host sum
+ * of LamellarOrderParameterGPU.cc:79-89, and gpu_compute_sq_forces (LamellarOrderParameterGPU.cuh:45-54).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct metad_lamellar metad_lamellar;
+
+/* lattice_vectors: 3*n_wave ints (Miller indices); mode: ntypes per-type coefficients a(type). */
+int metad_lamellar_create(metad_lamellar** out, int n_wave, const int* lattice_vectors, int ntypes,
+                          const double* mode);
+int metad_lamellar_destroy(metad_lamellar* p);
+
+/* Local partial Fourier modes F_k = sum_j a_j (cos q_k.r_j, sin q_k.r_j) over the N local particles ->
+ * d_modes[2*n_wave] (device, double).  If finalize != 0 also writes CV = (sum_k Re F_k)/N_global to
+ * *d_cv (single-GPU case).  Multi-GPU: call with finalize=0, all-reduce d_modes, then
+ * metad_lamellar_finalize (reference: MPI_Allreduce, LamellarOrderParameterGPU.cc:70-77). */
+int metad_lamellar_modes(metad_lamellar* p, const float* d_postype, unsigned N, unsigned N_global,
+                         const metad_box* global_box, double* d_modes, int finalize, double* d_cv,
+                         metad_stream_t stream);
+int metad_lamellar_finalize(metad_lamellar* p, const double* d_modes, unsigned N_global, double* d_cv,
+                            metad_stream_t stream);
+/* F_j = (bias/N_global) sum_k 2 a_j sin(q_k.r_j) q_k, force.w = 0; bias read from *d_bias (device). */
+int metad_lamellar_forces(metad_lamellar* p, const float* d_postype, float* d_force, unsigned N,
+                          unsigned N_global, const metad_box* global_box, const double* d_bias,
+                          metad_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * OrderParameterMesh
+ * one plan replaces the cuFFT plans + scratch of OrderParameterMeshGPU.cc:75-155; metad_mesh_cv replaces
+ * gpu_bin_particles + gpu_assign_binned_particles_to_mesh + gpu_compute_mode_sq + cufftExecC2C (x2) +
+ * gpu_update_meshes + gpu_compute_cv (OrderParameterMeshGPU.cuh:9-88; OrderParameterMeshGPU.cc:157-364,
+ * 454-506); metad_mesh_forces replaces gpu_compute_forces (OrderParameterMeshGPU.cuh:51-62).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct metad_mesh metad_mesh;
+
+/* nx,ny,nz: mesh points (powers of two, 8..1024 each); mode: ntypes per-type coefficients. */
+int metad_mesh_create(metad_mesh** out, unsigned nx, unsigned ny, unsigned nz, int ntypes, const double* mode);
+int metad_mesh_destroy(metad_mesh* p);
+
+/* getCurrentValue: assignParticles + updateMeshes + computeCV.  Writes the CV to *d_cv (device double).
+ * Keeps the inverse-transformed mesh and the particle cell order for a following metad_mesh_forces. */
+int metad_mesh_cv(metad_mesh* p, const float* d_postype, unsigned N, unsigned N_global, const metad_box* box,
+                  double* d_cv, metad_stream_t stream);
+/* interpolateForces for the positions last passed to metad_mesh_cv; bias read from *d_bias. */
+int metad_mesh_forces(metad_mesh* p, const float* d_postype, float* d_force, unsigned N, unsigned N_global,
+                      const metad_box* box, const double* d_bias, metad_stream_t stream);
+
+/* Multi-GPU (z-slab decomposition; reference: HOOMD domain decomposition + CommunicatorGrid + dfft,
+ * OrderParameterMesh.cc:263-315, 659-746).  See metad_mesh_slab_* below. */
+
+/* Introspection for parity tests (synchronous, copies to HOST buffers):
+ *   which = 0: cell coordinates (ix,iy,iz) per particle, int[3*N], input order
+ *           1: density mesh rho, float[nx*ny*nz], index x + nx*(y + ny*z)
+ *           2: Re(inverse mesh), float[nx*ny*nz]
+ *           3: sum of mode^2 (double[1])                                                        */
+int metad_mesh_get(metad_mesh* p, int which, void* h_out);
+/* knobs: key 0 = resort period (1 = rebuild the cell order every call, default) */
+int metad_mesh_set(metad_mesh* p, int key, long value);
+
+/* ------------------------------------------------------------------------------------------------
+ * IntegratorMetaDynamics grid bias
+ * metad_grid_step replaces, on the device and without host round trips, the root-rank body of
+ * IntegratorMetaDynamics::updateBiasPotential (IntegratorMetaDynamics.cc:363-451): updateHistogram,
+ * updateSigmaGrid, the well-tempered scale, gpu_update_grid (IntegratorMetaDynamics.cuh:1-11),
+ * updateReweightedEstimator, the delta merge, biasPotentialDerivative and interpolateGrid.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct metad_grid metad_grid;
+
+int metad_grid_create(metad_grid** out, int n_cv, const double* cv_min, const double* cv_max,
+                      const unsigned* num_points, const double* sigma, double W, double T_shift, double T,
+                      unsigned stride, int add_bias, int well_tempered);
+int metad_grid_destroy(metad_grid* g);
+/* d_cv_values: n_cv doubles (device); d_bias_out: n_cv doubles (device) = dV/ds_i. */
+int metad_grid_step(metad_grid* g, unsigned timestep, const double* d_cv_values, double* d_bias_out,
+                    metad_stream_t stream);
+int metad_grid_set_flags(metad_grid* g, int add_bias, int well_tempered, unsigned stride);
+int metad_grid_reset_histogram(metad_grid* g, metad_stream_t stream);
+/* Synchronous host access for dump/restart (writeGrid/readGrid, IntegratorMetaDynamics.cc:831-1000).
+ * which: 0 grid, 1 grid_reweighted, 2 grid_weight, 3 sigma_grid (double[G]); 4 hist, 5 hist_gauss (unsigned[G]) */
+int metad_grid_download(metad_grid* g, int which, void* h_out);
+int metad_grid_upload(metad_grid* g, int which, const void* h_in);
+/* h_out4: curr_bias_potential, curr_reweight, num_gaussians, out-of-bounds warning count */
+int metad_grid_scalars(metad_grid* g, double* h_out4);
+int metad_grid_set_num_gaussians(metad_grid* g, unsigned n);
+unsigned metad_grid_num_elements(const metad_grid* g);
+
+/* ------------------------------------------------------------------------------------------------
+ * CollectiveVariable umbrella (CollectiveVariable.cc:22-66, 68-106), evaluated on the device so the
+ * CV value never has to visit the host: *d_bias_out = *d_bias_in + umbrella'(cv); optional energy.
+ * kind: 0 none, 1 linear, 2 harmonic, 3 wall, 4 gaussian (CollectiveVariable.h:35-42)
+ * ---------------------------------------------------------------------------------------------- */
+int metad_umbrella_apply(int kind, double cv0, double kappa, double width_flat, double scale,
+                         const double* d_cv, const double* d_bias_in, double* d_bias_out,
+                         double* d_energy_out, metad_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * WellTemperedEnsemble
+ * replaces gpu_reduce_potential_energy and gpu_scale_netforce (WellTemperedEnsemble.cuh:3-19).
+ * ---------------------------------------------------------------------------------------------- */
+/* *d_pe = sum_i net_force[i].w + external_energy */
+int metad_wte_reduce(const float* d_net_force, unsigned N, double external_energy, double* d_pe,
+                     metad_stream_t stream);
+/* net_force.xyz, net_torque.xyz, six virial rows (pitch-strided) *= (1 + *d_bias) */
+int metad_wte_scale(float* d_net_force, float* d_net_torque, float* d_net_virial, unsigned pitch, unsigned N,
+                    const double* d_bias, metad_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* METAD_B200_H */

@@ -1,0 +1,359 @@
+// mesh.cu -- OrderParameterMesh plan object and C ABI (see include/metad_b200.h).
+//
+// Step structure of metad_mesh_cv (reference: OrderParameterMesh::getCurrentValue, OrderParameterMesh.cc:925-968):
+//   bin -> scan -> reorder            cell order of this step (tile-major counting sort; exact, rebuilt per call)
+//   spread -> merge                   assignParticles (:517-640); also sum a^2 (m_mode_sq) and sum a
+//   x fwd, y fwd, plane0 + z fused, y inv, x inv   updateMeshes (:642-747) + computeCV (:866-923)
+// metad_mesh_forces: gather           interpolateForces (:749-864)
+//
+// DC removal: the merge pass subtracts the mean density (sum a / M) before the transforms.  The k = 0 mode is
+// excluded from the CV (:892) and a constant offset of IFFT(G) cannot produce a force (the TSC derivative
+// weights of the 27 taps sum to zero), so results are unchanged -- but without it the fp32 transforms carry a
+// DC term ~sqrt(N) times larger than every other mode and the force mesh loses several digits.
+#include "mesh_kernels.cuh"
+#include "mesh_fft_kernels.cuh"
+
+#include <cmath>
+#include <vector>
+
+using namespace metad;
+using namespace metad::mesh;
+using namespace metad::fft;
+
+struct metad_mesh {
+    Geom g;
+    int ntypes = 0;
+    float* d_mode = nullptr;
+    // particle order
+    unsigned cap = 0;
+    unsigned *d_keys = nullptr, *d_ranks = nullptr, *d_perm = nullptr;
+    float4* d_sorted = nullptr;
+    unsigned *d_count = nullptr, *d_start = nullptr, *d_block_sums = nullptr;
+    // mesh
+    float* d_scratch = nullptr;     // padded tiles
+    float* d_buf = nullptr;         // M floats: rho -> packed half spectrum -> Re IFFT(G)
+    float* d_rho_keep = nullptr;    // optional copy of rho (introspection)
+    float2 *d_twx = nullptr, *d_twy = nullptr, *d_twz = nullptr;
+    double* d_sums = nullptr;       // [0] sum a^2  [1] sum a
+    double* d_partials = nullptr;
+    unsigned* d_ticket = nullptr;
+    unsigned n_partials = 0;
+    // state
+    bool have_cv = false;
+    unsigned last_N = 0;
+    bool keep_rho = false;
+    size_t M() const { return (size_t)g.nx * g.ny * g.nz; }
+};
+
+namespace {
+
+bool is_pow2(unsigned n) { return n && !(n & (n - 1)); }
+unsigned ilog2(unsigned n) { unsigned l = 0; while ((1u << l) < n) ++l; return l; }
+
+int upload_twiddles(float2** dst, unsigned n) {
+    std::vector<float2> t(n);
+    for (unsigned k = 0; k < n; ++k) {
+        const double ph = -2.0 * M_PI * (double)k / (double)n;
+        t[k] = make_float2((float)cos(ph), (float)sin(ph));
+    }
+    METAD_CUDA(cudaMalloc(dst, sizeof(float2) * n));
+    METAD_CUDA(cudaMemcpy(*dst, t.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+    return METAD_OK;
+}
+
+template <class K> int set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) METAD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return METAD_OK;
+}
+
+// ---- FFT launchers -----------------------------------------------------------------------------------
+template <int LC> int run_x(metad_mesh* p, bool inverse, cudaStream_t st) {
+    const size_t smem = sizeof(float2) * (LayoutRow::size(LC) + 2 * LC);
+    const unsigned rows = p->g.ny * p->g.nz;
+    float2* buf = reinterpret_cast<float2*>(p->d_buf);
+    if (!inverse) {
+        int rc = set_smem(fft_x_fwd_kernel<LC>, smem); if (rc) return rc;
+        fft_x_fwd_kernel<LC><<<rows / kLines, kLines * LC / kE, smem, st>>>(buf, p->d_twx);
+    } else {
+        int rc = set_smem(fft_x_inv_kernel<LC>, smem); if (rc) return rc;
+        fft_x_inv_kernel<LC><<<rows / kLines, kLines * LC / kE, smem, st>>>(buf, p->d_twx);
+    }
+    METAD_LAUNCH_CHECK();
+    return METAD_OK;
+}
+template <int L> int run_y(metad_mesh* p, bool inverse, cudaStream_t st) {
+    const size_t smem = sizeof(float2) * (LayoutCol::size(L) + L);
+    const unsigned nxh = p->g.nx / 2;
+    float2* buf = reinterpret_cast<float2*>(p->d_buf);
+    dim3 grid(nxh / kLines, p->g.nz);
+    if (!inverse) {
+        int rc = set_smem(fft_y_kernel<L, -1>, smem); if (rc) return rc;
+        fft_y_kernel<L, -1><<<grid, kLines * L / kE, smem, st>>>(buf, p->d_twy, nxh);
+    } else {
+        int rc = set_smem(fft_y_kernel<L, +1>, smem); if (rc) return rc;
+        fft_y_kernel<L, +1><<<grid, kLines * L / kE, smem, st>>>(buf, p->d_twy, nxh);
+    }
+    METAD_LAUNCH_CHECK();
+    return METAD_OK;
+}
+template <int L> int run_z(metad_mesh* p, unsigned N_global, double* d_cv, cudaStream_t st) {
+    const size_t smem = sizeof(float2) * (LayoutCol::size(L) + L);
+    const unsigned nxh = p->g.nx / 2, ny = p->g.ny;
+    float2* buf = reinterpret_cast<float2*>(p->d_buf);
+    ConvParams cp;
+    cp.nx = p->g.nx; cp.ny = ny; cp.nz = p->g.nz;
+    cp.inv_n = (float)(1.0 / (double)N_global);
+    cp.n_global = (double)N_global;
+    cp.d_mode_sq = p->d_sums;
+    cp.partials = p->d_partials;
+    cp.ticket = p->d_ticket;
+    cp.n_blocks_plane0 = (ny / 2 + 1 + kLines / 2 - 1) / (kLines / 2);
+    cp.d_cv = d_cv;
+    int rc = set_smem(fft_z_plane0_kernel<L>, smem); if (rc) return rc;
+    rc = set_smem(fft_z_fused_kernel<L>, smem); if (rc) return rc;
+    fft_z_plane0_kernel<L><<<cp.n_blocks_plane0, kLines * L / kE, smem, st>>>(buf, p->d_twz, cp);
+    METAD_LAUNCH_CHECK();
+    dim3 grid(nxh / kLines, ny);
+    fft_z_fused_kernel<L><<<grid, kLines * L / kE, smem, st>>>(buf, p->d_twz, cp);
+    METAD_LAUNCH_CHECK();
+    return METAD_OK;
+}
+
+#define METAD_DISPATCH_LEN(n, EXPR)                                       \
+    switch (n) {                                                          \
+        case 16: { constexpr int LL = 16; rc = EXPR; } break;             \
+        case 32: { constexpr int LL = 32; rc = EXPR; } break;             \
+        case 64: { constexpr int LL = 64; rc = EXPR; } break;             \
+        case 128: { constexpr int LL = 128; rc = EXPR; } break;           \
+        case 256: { constexpr int LL = 256; rc = EXPR; } break;           \
+        case 512: { constexpr int LL = 512; rc = EXPR; } break;           \
+        default: set_error("cv.mesh: unsupported mesh dimension"); rc = METAD_ERR_UNSUPPORTED; \
+    }
+
+int fft_pipeline(metad_mesh* p, unsigned N_global, double* d_cv, cudaStream_t st) {
+    int rc = METAD_OK;
+    METAD_DISPATCH_LEN(p->g.nx / 2, (run_x<LL>(p, false, st))); if (rc) return rc;
+    METAD_DISPATCH_LEN(p->g.ny, (run_y<LL>(p, false, st))); if (rc) return rc;
+    METAD_DISPATCH_LEN(p->g.nz, (run_z<LL>(p, N_global, d_cv, st))); if (rc) return rc;
+    METAD_DISPATCH_LEN(p->g.ny, (run_y<LL>(p, true, st))); if (rc) return rc;
+    METAD_DISPATCH_LEN(p->g.nx / 2, (run_x<LL>(p, true, st))); if (rc) return rc;
+    return METAD_OK;
+}
+
+int ensure_capacity(metad_mesh* p, unsigned N) {
+    if (N <= p->cap) return METAD_OK;
+    cudaFree(p->d_keys); cudaFree(p->d_ranks); cudaFree(p->d_perm); cudaFree(p->d_sorted);
+    p->d_keys = p->d_ranks = p->d_perm = nullptr; p->d_sorted = nullptr; p->cap = 0;
+    const unsigned cap = N + N / 16 + 1024;
+    METAD_CUDA(cudaMalloc(&p->d_keys, sizeof(unsigned) * cap));
+    METAD_CUDA(cudaMalloc(&p->d_ranks, sizeof(unsigned) * cap));
+    METAD_CUDA(cudaMalloc(&p->d_perm, sizeof(unsigned) * cap));
+    METAD_CUDA(cudaMalloc(&p->d_sorted, sizeof(float4) * cap));
+    p->cap = cap;
+    return METAD_OK;
+}
+
+int set_box(metad_mesh* p, const metad_box* box) {
+    if (box->tilt[0] != 0.0 || box->tilt[1] != 0.0 || box->tilt[2] != 0.0) {
+        set_error("cv.mesh: triclinic boxes are not supported by the sm_100a mesh path yet");
+        return METAD_ERR_UNSUPPORTED;
+    }
+    Geom& g = p->g;
+    const unsigned n[3] = {g.nx, g.ny, g.nz};
+    for (int i = 0; i < 3; ++i) {
+        METAD_REQUIRE(box->L[i] > 0.0, "cv.mesh: box lengths must be positive");
+        g.L[i] = (float)box->L[i];
+        g.lo[i] = -(g.L[i] / 2.0f);
+        g.dlo[i] = -box->L[i] / 2.0;
+        g.dscale[i] = (double)n[i] / box->L[i];
+    }
+    return METAD_OK;
+}
+
+}  // namespace
+
+extern "C" int metad_mesh_create(metad_mesh** out, unsigned nx, unsigned ny, unsigned nz, int ntypes, const double* mode) {
+    METAD_REQUIRE(out && mode, "metad_mesh_create: null argument");
+    METAD_REQUIRE(ntypes > 0, "Number of modes unequal number of particle types.");
+    if (!is_pow2(nx) || !is_pow2(ny) || !is_pow2(nz)) {
+        set_error("cv.mesh: the number of mesh points along every direction must be a power of two");
+        return METAD_ERR_UNSUPPORTED;
+    }
+    if (nx < 32 || nx > 1024 || ny < 16 || ny > 512 || nz < 16 || nz > 512) {
+        set_error("cv.mesh: supported mesh sizes are 32 <= nx <= 1024, 16 <= ny,nz <= 512");
+        return METAD_ERR_UNSUPPORTED;
+    }
+    auto* p = new metad_mesh();
+    Geom& g = p->g;
+    memset(&g, 0, sizeof g);
+    g.nx = nx; g.ny = ny; g.nz = nz;
+    g.lgx = ilog2(nx); g.lgy = ilog2(ny); g.lgz = ilog2(nz);
+    const size_t M = (size_t)nx * ny * nz;
+    // 16^3 tiles once there are enough of them to fill the GPU twice, 8^3 otherwise
+    g.lgT = (M / 4096 >= (size_t)2 * device_sm_count()) ? 4 : 3;
+    g.ntx = nx >> g.lgT; g.nty = ny >> g.lgT; g.ntz = nz >> g.lgT;
+    p->ntypes = ntypes;
+    std::vector<float> m(ntypes);
+    for (int i = 0; i < ntypes; ++i) m[i] = (float)mode[i];
+    const unsigned P = padded_edge(g);
+    const unsigned nb_scan = (unsigned)(M / kScanBlockItems);
+    const unsigned nby = (ny / 2 + 1 + kLines / 2 - 1) / (kLines / 2);
+    p->n_partials = nby + (nx / 2 / kLines) * ny;
+    int rc = METAD_OK;
+    auto fail = [&](cudaError_t e, const char* what) { rc = cuda_fail(e, what, __FILE__, __LINE__); };
+    cudaError_t e;
+#define TRY(call) if (rc == METAD_OK && (e = (call)) != cudaSuccess) fail(e, #call)
+    TRY(cudaMalloc(&p->d_mode, sizeof(float) * ntypes));
+    TRY(cudaMemcpy(p->d_mode, m.data(), sizeof(float) * ntypes, cudaMemcpyHostToDevice));
+    TRY(cudaMalloc(&p->d_count, sizeof(unsigned) * M));
+    TRY(cudaMemset(p->d_count, 0, sizeof(unsigned) * M));
+    TRY(cudaMalloc(&p->d_start, sizeof(unsigned) * (M + 4)));
+    TRY(cudaMalloc(&p->d_block_sums, sizeof(unsigned) * (nb_scan + 1)));
+    TRY(cudaMalloc(&p->d_scratch, sizeof(float) * (size_t)num_tiles(g) * P * P * P));
+    TRY(cudaMalloc(&p->d_buf, sizeof(float) * M));
+    TRY(cudaMalloc(&p->d_sums, sizeof(double) * 2));
+    TRY(cudaMalloc(&p->d_partials, sizeof(double) * p->n_partials));
+    TRY(cudaMalloc(&p->d_ticket, sizeof(unsigned)));
+    TRY(cudaMemset(p->d_ticket, 0, sizeof(unsigned)));
+#undef TRY
+    if (rc == METAD_OK) rc = upload_twiddles(&p->d_twx, nx);
+    if (rc == METAD_OK) rc = upload_twiddles(&p->d_twy, ny);
+    if (rc == METAD_OK) rc = upload_twiddles(&p->d_twz, nz);
+    if (rc != METAD_OK) { metad_mesh_destroy(p); return rc; }
+    *out = p;
+    return METAD_OK;
+}
+
+extern "C" int metad_mesh_destroy(metad_mesh* p) {
+    if (!p) return METAD_OK;
+    cudaFree(p->d_mode); cudaFree(p->d_keys); cudaFree(p->d_ranks); cudaFree(p->d_perm); cudaFree(p->d_sorted);
+    cudaFree(p->d_count); cudaFree(p->d_start); cudaFree(p->d_block_sums); cudaFree(p->d_scratch); cudaFree(p->d_buf);
+    cudaFree(p->d_rho_keep); cudaFree(p->d_twx); cudaFree(p->d_twy); cudaFree(p->d_twz); cudaFree(p->d_sums);
+    cudaFree(p->d_partials); cudaFree(p->d_ticket);
+    delete p;
+    return METAD_OK;
+}
+
+extern "C" int metad_mesh_cv(metad_mesh* p, const float* d_postype, unsigned N, unsigned N_global, const metad_box* box,
+                             double* d_cv, metad_stream_t stream) {
+    METAD_REQUIRE(p && box && d_cv, "metad_mesh_cv: null argument");
+    METAD_REQUIRE(N == 0 || d_postype, "metad_mesh_cv: null positions");
+    METAD_REQUIRE(N_global > 0, "metad_mesh_cv: N_global must be positive");
+    int rc = set_box(p, box); if (rc) return rc;
+    rc = ensure_capacity(p, N); if (rc) return rc;
+    const Geom& g = p->g;
+    const size_t M = p->M();
+    const int sms = device_sm_count();
+    p->have_cv = false;
+
+    METAD_CUDA(cudaMemsetAsync(p->d_sums, 0, 2 * sizeof(double), stream));
+    if (N > 0) {
+        long nb = ((long)N + kBinThreads * 4L - 1) / (kBinThreads * 4L);
+        if (nb > sms * 16L) nb = sms * 16L;
+        mesh_bin_kernel<<<(int)nb, kBinThreads, 0, stream>>>((const float4*)d_postype, N, g, p->d_mode, p->d_keys, p->d_ranks,
+                                                            p->d_count, p->d_sums);
+        METAD_LAUNCH_CHECK();
+    }
+    const unsigned nb_scan = (unsigned)(M / kScanBlockItems);
+    scan_reduce_kernel<<<nb_scan, kScanThreads, 0, stream>>>((const uint4*)p->d_count, p->d_block_sums);
+    METAD_LAUNCH_CHECK();
+    scan_offsets_kernel<<<1, kScanThreads, 0, stream>>>(p->d_block_sums, nb_scan);
+    METAD_LAUNCH_CHECK();
+    scan_apply_kernel<<<nb_scan, kScanThreads, 0, stream>>>((uint4*)p->d_count, p->d_block_sums, p->d_start, (unsigned)M);
+    METAD_LAUNCH_CHECK();
+    if (N > 0) {
+        long nb = ((long)N + kBinThreads * 4L - 1) / (kBinThreads * 4L);
+        if (nb > sms * 16L) nb = sms * 16L;
+        mesh_reorder_kernel<<<(int)nb, kBinThreads, 0, stream>>>((const float4*)d_postype, N, p->d_mode, p->d_keys, p->d_ranks,
+                                                                p->d_start, p->d_sorted, p->d_perm);
+        METAD_LAUNCH_CHECK();
+    }
+    if (g.lgT == 4)
+        mesh_spread_kernel<4><<<num_tiles(g), kTileThreads, 0, stream>>>(p->d_sorted, p->d_perm, p->d_start, g, p->d_scratch);
+    else
+        mesh_spread_kernel<3><<<num_tiles(g), kTileThreads, 0, stream>>>(p->d_sorted, p->d_perm, p->d_start, g, p->d_scratch);
+    METAD_LAUNCH_CHECK();
+    if (p->keep_rho && !p->d_rho_keep) METAD_CUDA(cudaMalloc(&p->d_rho_keep, sizeof(float) * M));
+    {
+        long nb = (long)((M + 255) / 256);
+        if (nb > sms * 32L) nb = sms * 32L;
+        mesh_merge_kernel<<<(int)nb, 256, 0, stream>>>(p->d_scratch, g, p->d_sums, p->d_buf, p->keep_rho ? p->d_rho_keep : nullptr);
+        METAD_LAUNCH_CHECK();
+    }
+    rc = fft_pipeline(p, N_global, d_cv, stream);
+    if (rc) return rc;
+    p->have_cv = true;
+    p->last_N = N;
+    return METAD_OK;
+}
+
+extern "C" int metad_mesh_forces(metad_mesh* p, const float* d_postype, float* d_force, unsigned N, unsigned N_global,
+                                 const metad_box* box, const double* d_bias, metad_stream_t stream) {
+    METAD_REQUIRE(p && box && d_bias, "metad_mesh_forces: null argument");
+    METAD_REQUIRE(N_global > 0, "metad_mesh_forces: N_global must be positive");
+    if (!p->have_cv || p->last_N != N) {
+        set_error("metad_mesh_forces: call metad_mesh_cv for the same particles first");
+        return METAD_ERR_STATE;
+    }
+    if (N == 0) return METAD_OK;
+    METAD_REQUIRE(d_postype && d_force, "metad_mesh_forces: null particle arrays");
+    const Geom& g = p->g;
+    // reciprocal lattice vectors of the (orthorhombic) box without 2 pi, times the mesh dimensions (:761-769, :852-854)
+    ForceParams fp;
+    memset(&fp, 0, sizeof fp);
+    fp.nb1[0] = (float)((double)g.nx / box->L[0]);
+    fp.nb2[1] = (float)((double)g.ny / box->L[1]);
+    fp.nb3[2] = (float)((double)g.nz / box->L[2]);
+    fp.two_over_n = 2.0 / (double)N_global;
+    if (g.lgT == 4)
+        mesh_gather_kernel<4><<<num_tiles(g), kTileThreads, 0, stream>>>(p->d_sorted, p->d_perm, p->d_start, g, p->d_buf, fp, d_bias,
+                                                                       (float4*)d_force);
+    else
+        mesh_gather_kernel<3><<<num_tiles(g), kTileThreads, 0, stream>>>(p->d_sorted, p->d_perm, p->d_start, g, p->d_buf, fp, d_bias,
+                                                                       (float4*)d_force);
+    METAD_LAUNCH_CHECK();
+    return METAD_OK;
+}
+
+extern "C" int metad_mesh_get(metad_mesh* p, int which, void* h_out) {
+    METAD_REQUIRE(p && h_out, "metad_mesh_get: null argument");
+    METAD_CUDA(cudaDeviceSynchronize());
+    const size_t M = p->M();
+    switch (which) {
+        case 0: {
+            if (!p->have_cv) { set_error("metad_mesh_get: no cell order yet"); return METAD_ERR_STATE; }
+            std::vector<unsigned> keys(p->last_N);
+            METAD_CUDA(cudaMemcpy(keys.data(), p->d_keys, sizeof(unsigned) * p->last_N, cudaMemcpyDeviceToHost));
+            int* out = (int*)h_out;
+            for (unsigned i = 0; i < p->last_N; ++i) {
+                unsigned ix, iy, iz;
+                cell_of_key(keys[i], p->g, ix, iy, iz);
+                out[3 * (size_t)i] = (int)ix; out[3 * (size_t)i + 1] = (int)iy; out[3 * (size_t)i + 2] = (int)iz;
+            }
+            return METAD_OK;
+        }
+        case 1:
+            if (!p->d_rho_keep) { set_error("metad_mesh_get: enable metad_mesh_set(p, 1, 1) before metad_mesh_cv to keep rho"); return METAD_ERR_STATE; }
+            METAD_CUDA(cudaMemcpy(h_out, p->d_rho_keep, sizeof(float) * M, cudaMemcpyDeviceToHost));
+            return METAD_OK;
+        case 2:
+            if (!p->have_cv) { set_error("metad_mesh_get: no inverse mesh yet"); return METAD_ERR_STATE; }
+            METAD_CUDA(cudaMemcpy(h_out, p->d_buf, sizeof(float) * M, cudaMemcpyDeviceToHost));
+            return METAD_OK;
+        case 3:
+            METAD_CUDA(cudaMemcpy(h_out, p->d_sums, sizeof(double), cudaMemcpyDeviceToHost));
+            return METAD_OK;
+        default:
+            set_error("metad_mesh_get: unknown selector");
+            return METAD_ERR_INVALID;
+    }
+}
+
+extern "C" int metad_mesh_set(metad_mesh* p, int key, long value) {
+    METAD_REQUIRE(p, "metad_mesh_set: null plan");
+    switch (key) {
+        case 0: return METAD_OK;                       // resort period: the order is rebuilt every call in this version
+        case 1: p->keep_rho = value != 0; return METAD_OK;
+        default: set_error("metad_mesh_set: unknown key"); return METAD_ERR_INVALID;
+    }
+}

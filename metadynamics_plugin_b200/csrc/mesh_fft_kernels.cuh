@@ -1,0 +1,301 @@
+// mesh_fft_kernels.cuh -- the five FFT sweeps of the mesh CV (see mesh_fft.cuh for the engine).
+//
+// Buffer layout: one array of M = nx*ny*nz floats, reinterpreted as M/2 float2 "packed half spectrum"
+// [z][y][kx], kx < nx/2.  Slot kx = 0 holds X[0] + i X[nx/2] of the row (both real after the x pass); the y and
+// z passes treat it as an ordinary complex column, and the convolve step untangles it (plane0 kernel).
+//
+// Convolution restated from OrderParameterMesh.cc:689-708 (updateMeshes) and :887-905 (computeCV), folded onto
+// the half spectrum: with f = F/N, d = 0.5*mode_sq/N^2 and chi_k = [all Miller indices of k >= 0]
+// (= interp_k^2 of the reference, OrderParameterMesh.cc:448, SURVEY 8a note a4):
+//     reference   G_k = f_k (|f_k|^2 - d chi_k),  CV = 1/2 sum_{k != 0} (|f_k|^4 - 2 d chi_k |f_k|^2),
+//                 forces use Re(IFFT(G)).
+//     here        G^H_k = f_k (|f_k|^2 - d chis_k),  chis_k = (chi_k + chi_{-k})/2   (Hermitian part of G:
+//                 IFFT(G^H) = Re IFFT(G) because f_{-k} = conj f_k), and
+//                 CV = 1/2 sum_{stored k != 0} w_k (|f_k|^4 - 2 d chis_k |f_k|^2), w_k = 2 for 0 < kx < nx/2 else 1.
+#pragma once
+#include "common.cuh"
+#include "mesh_fft.cuh"
+
+namespace metad {
+namespace fft {
+
+struct ConvParams {
+    unsigned nx, ny, nz;
+    float inv_n;                  // 1 / N_global
+    double n_global;
+    const double* d_mode_sq;      // device: sum_j a_j^2 of this step
+    double* partials;             // per-block energy partial sums
+    unsigned* ticket;
+    unsigned n_blocks_plane0;     // plane0 blocks write partials[0 .. n_blocks_plane0)
+    double* d_cv;                 // device output: CV
+};
+
+// chi for one dimension: [k < ceil(n/2)] (non-negative Miller index), OrderParameterMesh.cc:417-422
+MHD bool nonneg(unsigned k, unsigned n) { return k < n / 2 + n % 2; }
+
+// pointwise convolution of one stored mode with 0 < kx < nx/2 (weight 2 in the CV sum):
+// chi_k = [ky>=0][kz>=0], chi_{-k} = 0 -> chis = chi_k/2.  Returns G^H, adds the CV summand to e.
+MHD float2 conv_general(float2 F, float inv_n, float d, bool chi_k, double& e) {
+    const float fr = F.x * inv_n, fi = F.y * inv_n;
+    const float val = fr * fr + fi * fi;
+    const float chis = chi_k ? 0.5f : 0.0f;
+    const float g = val - d * chis;
+    const double v = (double)val;
+    e += 2.0 * v * (v - 2.0 * (double)d * (double)chis);
+    return make_float2(fr * g, fi * g);
+}
+// pointwise convolution of the packed kx = 0 slot: z1 = Z(ky,kz), z2 = Z(-ky,-kz) (not yet conjugated).
+// A = (z1 + conj z2)/2 is the kx = 0 mode, B = (z1 - conj z2)/(2i) the kx = nx/2 mode; returns A' + i B'.
+MHD float2 conv_plane0(float2 z1, float2 z2raw, float inv_n, float d, unsigned ky, unsigned kz, unsigned ny,
+                       unsigned nz, bool counted, double& e) {
+    const float2 z2 = cconj(z2raw);
+    const float2 A = make_float2(0.5f * (z1.x + z2.x), 0.5f * (z1.y + z2.y));
+    const float2 Dm = make_float2(0.5f * (z1.x - z2.x), 0.5f * (z1.y - z2.y));
+    const float2 B = make_float2(Dm.y, -Dm.x);
+    // kx = 0: chi_k = [ky>=0][kz>=0], chi_{-k} = [-ky>=0][-kz>=0]
+    const float chis = 0.5f * ((nonneg(ky, ny) && nonneg(kz, nz) ? 1.0f : 0.0f) +
+                               (nonneg((ny - ky) % ny, ny) && nonneg((nz - kz) % nz, nz) ? 1.0f : 0.0f));
+    const float ar = A.x * inv_n, ai = A.y * inv_n;
+    const float va = ar * ar + ai * ai;
+    const float ga = va - d * chis;
+    const float2 GA = make_float2(ar * ga, ai * ga);
+    // kx = nx/2: negative Miller index in x for both k and -k -> chis = 0
+    const float br = B.x * inv_n, bi = B.y * inv_n;
+    const float vb = br * br + bi * bi;
+    const float2 GB = make_float2(br * vb, bi * vb);
+    if (counted) {
+        const double dva = (double)va, dvb = (double)vb;
+        if (!(ky == 0 && kz == 0)) e += dva * (dva - 2.0 * (double)d * (double)chis);   // flat index 0 excluded (:892)
+        e += dvb * dvb;
+    }
+    return make_float2(GA.x - GB.y, GA.y + GB.x);      // A' + i B'
+}
+
+// cooperative copy of the forward twiddle table exp(-2 pi i k/TWL) into shared memory
+template <int TWL> __device__ __forceinline__ void load_twiddles(float2* s_tw, const float2* __restrict__ g_tw) {
+    for (int i = threadIdx.x; i < TWL; i += blockDim.x) s_tw[i] = __ldg(g_tw + i);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// x pass, forward (R2C): 16 rows per CTA, row = y + ny*z
+// ---------------------------------------------------------------------------------------------------
+template <int LC>
+__global__ void __launch_bounds__(kLines * LC / kE)
+fft_x_fwd_kernel(float2* __restrict__ buf, const float2* __restrict__ g_tw /* length 2*LC */) {
+    extern __shared__ float2 smem[];
+    float2* tile = smem;
+    float2* s_tw = smem + LayoutRow::size(LC);
+    const int nthr = kLines * LC / kE;
+    const size_t row0 = (size_t)blockIdx.x * kLines;
+    load_twiddles<2 * LC>(s_tw, g_tw);
+    for (int idx = threadIdx.x; idx < kLines * LC; idx += nthr) {
+        const int w = idx / LC, l = idx % LC;
+        tile[LayoutRow::addr(w, l, LC)] = buf[(row0 + w) * LC + l];
+    }
+    __syncthreads();
+    const int w = threadIdx.x & (kLines - 1), t = threadIdx.x / kLines;
+    line_fft<LC, -1, 2 * LC, LayoutRow>(tile, w, t, s_tw);
+    for (int idx = threadIdx.x; idx < kLines * (LC / 2 + 1); idx += nthr) {
+        const int ww = idx & (kLines - 1), k = idx / kLines;
+        float2& zk = tile[LayoutRow::addr(ww, k, LC)];
+        float2& zp = tile[LayoutRow::addr(ww, (LC - k) % LC, LC)];
+        r2c_pair(zk, zp, k, LC, s_tw[k]);
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < kLines * LC; idx += nthr) {
+        const int ww = idx / LC, l = idx % LC;
+        buf[(row0 + ww) * LC + l] = tile[LayoutRow::addr(ww, l, LC)];
+    }
+}
+
+// x pass, inverse (C2R)
+template <int LC>
+__global__ void __launch_bounds__(kLines * LC / kE)
+fft_x_inv_kernel(float2* __restrict__ buf, const float2* __restrict__ g_tw) {
+    extern __shared__ float2 smem[];
+    float2* tile = smem;
+    float2* s_tw = smem + LayoutRow::size(LC);
+    const int nthr = kLines * LC / kE;
+    const size_t row0 = (size_t)blockIdx.x * kLines;
+    load_twiddles<2 * LC>(s_tw, g_tw);
+    for (int idx = threadIdx.x; idx < kLines * LC; idx += nthr) {
+        const int w = idx / LC, l = idx % LC;
+        tile[LayoutRow::addr(w, l, LC)] = buf[(row0 + w) * LC + l];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < kLines * (LC / 2 + 1); idx += nthr) {
+        const int ww = idx & (kLines - 1), k = idx / kLines;
+        float2& xk = tile[LayoutRow::addr(ww, k, LC)];
+        float2& xp = tile[LayoutRow::addr(ww, (LC - k) % LC, LC)];
+        c2r_pair(xk, xp, k, LC, s_tw[k]);
+    }
+    __syncthreads();
+    const int w = threadIdx.x & (kLines - 1), t = threadIdx.x / kLines;
+    line_fft<LC, +1, 2 * LC, LayoutRow>(tile, w, t, s_tw);
+    for (int idx = threadIdx.x; idx < kLines * LC; idx += nthr) {
+        const int ww = idx / LC, l = idx % LC;
+        buf[(row0 + ww) * LC + l] = tile[LayoutRow::addr(ww, l, LC)];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// y pass: tile = 16 consecutive kx  x  all y, fixed z.  grid = (nxh/16, nz)
+// ---------------------------------------------------------------------------------------------------
+template <int L, int SIGN>
+__global__ void __launch_bounds__(kLines * L / kE)
+fft_y_kernel(float2* __restrict__ buf, const float2* __restrict__ g_tw, unsigned nxh) {
+    extern __shared__ float2 smem[];
+    float2* tile = smem;
+    float2* s_tw = smem + LayoutCol::size(L);
+    const int nthr = kLines * L / kE;
+    const size_t base = (size_t)blockIdx.y * L * nxh + (size_t)blockIdx.x * kLines;
+    load_twiddles<L>(s_tw, g_tw);
+    for (int idx = threadIdx.x; idx < kLines * L; idx += nthr) {
+        const int w = idx & (kLines - 1), l = idx / kLines;
+        tile[idx] = buf[base + (size_t)l * nxh + w];
+    }
+    __syncthreads();
+    const int w = threadIdx.x & (kLines - 1), t = threadIdx.x / kLines;
+    line_fft<L, SIGN, L, LayoutCol>(tile, w, t, s_tw);
+    for (int idx = threadIdx.x; idx < kLines * L; idx += nthr) {
+        const int ww = idx & (kLines - 1), l = idx / kLines;
+        buf[base + (size_t)l * nxh + ww] = tile[idx];
+    }
+}
+
+// energy partial -> per-block slot; the last block of the LAST kernel (main z pass) sums all slots in order
+__device__ __forceinline__ void energy_block_finish(double e, const ConvParams& cp, unsigned slot, unsigned total_slots,
+                                                    bool finalize) {
+    __shared__ double red[32];
+    __shared__ bool is_last;
+    const double r = block_sum(e, red);
+    if (threadIdx.x == 0) cp.partials[slot] = r;
+    if (!finalize) return;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned nb = gridDim.x * gridDim.y;
+        is_last = (atomicAdd(cp.ticket, 1u) == nb - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double s = 0.0;
+    for (unsigned b = threadIdx.x; b < total_slots; b += blockDim.x) s += __ldcg(cp.partials + b);
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) {
+        *cp.d_cv = 0.5 * s;      // sum *= 1/2, OrderParameterMesh.cc:905
+        *cp.ticket = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// z pass fused with the convolution and the CV energy: forward z FFT -> G^H -> inverse z FFT.
+// tile = 16 consecutive kx  x  all z, fixed y.  grid = (nxh/16, ny).  Column kx = 0 is left to plane0.
+// ---------------------------------------------------------------------------------------------------
+template <int L>
+__global__ void __launch_bounds__(kLines * L / kE)
+fft_z_fused_kernel(float2* __restrict__ buf, const float2* __restrict__ g_tw, ConvParams cp) {
+    extern __shared__ float2 smem[];
+    float2* tile = smem;
+    float2* s_tw = smem + LayoutCol::size(L);
+    const int nthr = kLines * L / kE;
+    const unsigned nxh = cp.nx / 2, ny = cp.ny;
+    const unsigned kx0 = blockIdx.x * kLines, ky = blockIdx.y;
+    const size_t base = (size_t)ky * nxh + kx0;
+    const size_t zstride = (size_t)ny * nxh;
+    load_twiddles<L>(s_tw, g_tw);
+    for (int idx = threadIdx.x; idx < kLines * L; idx += nthr) {
+        const int w = idx & (kLines - 1), l = idx / kLines;
+        tile[idx] = buf[base + (size_t)l * zstride + w];
+    }
+    __syncthreads();
+    const int w = threadIdx.x & (kLines - 1), t = threadIdx.x / kLines;
+    line_fft<L, -1, L, LayoutCol>(tile, w, t, s_tw);
+
+    const double nd = cp.n_global;
+    const float d = (float)(0.5 * (*cp.d_mode_sq) / nd / nd);
+    const bool ky_nonneg = nonneg(ky, ny);
+    double e = 0.0;
+    for (int idx = threadIdx.x; idx < kLines * L; idx += nthr) {
+        const int ww = idx & (kLines - 1);
+        const unsigned kz = idx / kLines;
+        if (kx0 + ww == 0) continue;
+        tile[idx] = conv_general(tile[idx], cp.inv_n, d, ky_nonneg && nonneg(kz, L), e);
+    }
+    __syncthreads();
+    line_fft<L, +1, L, LayoutCol>(tile, w, t, s_tw);
+    for (int idx = threadIdx.x; idx < kLines * L; idx += nthr) {
+        const int ww = idx & (kLines - 1), l = idx / kLines;
+        if (kx0 + ww == 0) continue;
+        buf[base + (size_t)l * zstride + ww] = tile[idx];
+    }
+    const unsigned slot = cp.n_blocks_plane0 + blockIdx.y * gridDim.x + blockIdx.x;
+    energy_block_finish(e, cp, slot, cp.n_blocks_plane0 + gridDim.x * gridDim.y, true);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// plane kx = 0 (packed DC + Nyquist planes).  Each CTA handles 8 line pairs (ky, -ky): column 2p holds line ky,
+// column 2p+1 line (ny-ky)%ny.  After the z FFT:  A(ky,kz) = (Z(ky,kz) + conj Z(-ky,-kz))/2  is the kx = 0
+// spectrum, B = (Z(ky,kz) - conj Z(-ky,-kz))/(2i) the kx = nx/2 spectrum; both are convolved, re-packed as
+// A' + i B' and transformed back.  grid = ceil((ny/2+1)/8)
+// ---------------------------------------------------------------------------------------------------
+template <int L>
+__global__ void __launch_bounds__(kLines * L / kE)
+fft_z_plane0_kernel(float2* __restrict__ buf, const float2* __restrict__ g_tw, ConvParams cp) {
+    extern __shared__ float2 smem[];
+    float2* tile = smem;
+    float2* s_tw = smem + LayoutCol::size(L);
+    constexpr int nthr = kLines * L / kE;
+    constexpr int per_thread = kLines * L / nthr;   // = 8
+    const unsigned nxh = cp.nx / 2, ny = cp.ny;
+    const size_t zstride = (size_t)ny * nxh;
+    load_twiddles<L>(s_tw, g_tw);
+    for (int idx = threadIdx.x; idx < kLines * L; idx += nthr) {
+        const int w = idx & (kLines - 1), l = idx / kLines;
+        const unsigned kyp = blockIdx.x * (kLines / 2) + (w >> 1);
+        float2 v = make_float2(0.f, 0.f);
+        if (kyp <= ny / 2) {
+            const unsigned ky = (w & 1) ? (ny - kyp) % ny : kyp;
+            v = buf[(size_t)ky * nxh + (size_t)l * zstride];
+        }
+        tile[idx] = v;
+    }
+    __syncthreads();
+    const int w = threadIdx.x & (kLines - 1), t = threadIdx.x / kLines;
+    line_fft<L, -1, L, LayoutCol>(tile, w, t, s_tw);
+
+    const double nd = cp.n_global;
+    const float d = (float)(0.5 * (*cp.d_mode_sq) / nd / nd);
+    double e = 0.0;
+    float2 outv[per_thread];
+#pragma unroll
+    for (int it = 0; it < per_thread; ++it) {
+        const int idx = threadIdx.x + it * nthr;
+        const int ww = idx & (kLines - 1);
+        const unsigned kz = idx / kLines;
+        const unsigned kyp = blockIdx.x * (kLines / 2) + (ww >> 1);
+        const unsigned pky = (ny - kyp) % ny;
+        const unsigned ky = (ww & 1) ? pky : kyp;
+        const bool valid = kyp <= ny / 2;
+        const bool counted = valid && (!(ww & 1) || pky != kyp);
+        outv[it] = conv_plane0(tile[idx], tile[((L - kz) % L) * kLines + (ww ^ 1)], cp.inv_n, d, ky, kz, ny, L, counted, e);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < per_thread; ++it) tile[threadIdx.x + it * nthr] = outv[it];
+    __syncthreads();
+    line_fft<L, +1, L, LayoutCol>(tile, w, t, s_tw);
+    for (int idx = threadIdx.x; idx < kLines * L; idx += nthr) {
+        const int ww = idx & (kLines - 1), l = idx / kLines;
+        const unsigned kyp = blockIdx.x * (kLines / 2) + (ww >> 1);
+        const unsigned pky = (ny - kyp) % ny;
+        if (kyp > ny / 2) continue;
+        if ((ww & 1) && pky == kyp) continue;
+        const unsigned ky = (ww & 1) ? pky : kyp;
+        buf[(size_t)ky * nxh + (size_t)l * zstride] = tile[idx];
+    }
+    energy_block_finish(e, cp, blockIdx.x, 0, false);
+}
+
+}  // namespace fft
+}  // namespace metad

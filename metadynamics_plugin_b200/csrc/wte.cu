@@ -1,0 +1,143 @@
+// wte.cu -- WellTemperedEnsemble reduce/scale kernels and the device-side umbrella of CollectiveVariable.
+//
+// Reference behaviour restated (CPU path = parity target): WellTemperedEnsemble.cc:30-68 (pe = sum of
+// net_force.w + external energy), :135-188 (net force xyz, net torque xyzw, six virial rows *= 1+bias);
+// CollectiveVariable.cc:22-66 (umbrella bias increment), :68-106 (umbrella energy).
+// Reference GPU drivers replaced: gpu_reduce_potential_energy / gpu_scale_netforce
+// (WellTemperedEnsemble.cu:19-243; atomicCAS double add, autotuned block size, managed scratch).
+#include "common.cuh"
+
+namespace metad {
+
+constexpr int kWteThreads = 256;
+
+__global__ void __launch_bounds__(kWteThreads)
+wte_reduce_kernel(const float4* __restrict__ net_force, unsigned N, double external_energy, double* __restrict__ partials,
+                  unsigned* __restrict__ ticket, double* __restrict__ d_pe) {
+    double acc = 0.0;
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) acc += (double)ld_stream(net_force + i).w;
+    __shared__ double red[32];
+    __shared__ bool is_last;
+    const double r = block_sum(acc, red);
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = r;
+        __threadfence();
+        is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double s = 0.0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) s += __ldcg(partials + b);
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) { *d_pe = s + external_energy; *ticket = 0; }
+}
+
+__global__ void __launch_bounds__(kWteThreads)
+wte_scale_kernel(float4* __restrict__ net_force, float4* __restrict__ net_torque, float* __restrict__ net_virial,
+                 unsigned pitch, unsigned N, const double* __restrict__ d_bias) {
+    const float fac = (float)(1.0 + *d_bias);
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+        float4 f = net_force[i];
+        f.x *= fac; f.y *= fac; f.z *= fac;
+        net_force[i] = f;
+        if (net_torque) {
+            float4 t = net_torque[i];
+            t.x *= fac; t.y *= fac; t.z *= fac; t.w *= fac;
+            net_torque[i] = t;
+        }
+        if (net_virial) {
+#pragma unroll
+            for (int r = 0; r < 6; ++r) net_virial[i + (size_t)r * pitch] *= fac;
+        }
+    }
+}
+
+__global__ void umbrella_kernel(int kind, double cv0, double kappa, double width_flat, double scale,
+                                const double* __restrict__ d_cv, const double* __restrict__ d_bias_in,
+                                double* __restrict__ d_bias_out, double* __restrict__ d_energy_out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double val = *d_cv;
+    double bias = d_bias_in ? *d_bias_in : 0.0;
+    double energy = 0.0;
+    const bool flat = (val < cv0 + width_flat / 2.0) && (val > cv0 - width_flat / 2.0);
+    if (kind != 0 && !flat) {
+        double delta = 0.0;
+        if (val > cv0) delta = val - cv0 - width_flat / 2.0;
+        else delta = val - cv0 + width_flat / 2.0;
+        // energy uses delta = 0 when val == cv0 exactly (CollectiveVariable.cc:80-84)
+        const double edelta = (val > cv0 || val < cv0) ? delta : 0.0;
+        if (kind == 1) { bias += scale * 1.0; energy = scale * edelta; }
+        else if (kind == 2) { bias += kappa * delta; energy = 0.5 * edelta * edelta * kappa; }
+        else if (kind == 3) { bias += scale * 12.0 * pow(delta / kappa, 11.0) / kappa; energy = scale * pow(edelta / kappa, 12.0); }
+        else if (kind == 4) {
+            const double g = exp(-(val - cv0) * (val - cv0) / kappa / kappa / 2.0);
+            bias -= scale * (val - cv0) * g;
+            energy = scale * g - scale;
+        }
+    }
+    if (d_bias_out) *d_bias_out = bias;
+    if (d_energy_out) *d_energy_out = energy;
+}
+
+struct WteScratch {
+    double* partials = nullptr;
+    unsigned* ticket = nullptr;
+    int blocks = 0;
+};
+static WteScratch g_wte;   // per process (= per GPU)
+
+static int wte_scratch() {
+    if (g_wte.partials) return METAD_OK;
+    g_wte.blocks = device_sm_count() * 8;
+    METAD_CUDA(cudaMalloc(&g_wte.partials, sizeof(double) * g_wte.blocks));
+    METAD_CUDA(cudaMalloc(&g_wte.ticket, sizeof(unsigned)));
+    METAD_CUDA(cudaMemset(g_wte.ticket, 0, sizeof(unsigned)));
+    return METAD_OK;
+}
+
+}  // namespace metad
+
+using namespace metad;
+
+extern "C" int metad_wte_reduce(const float* d_net_force, unsigned N, double external_energy, double* d_pe,
+                                metad_stream_t stream) {
+    METAD_REQUIRE(d_pe, "metad_wte_reduce: null output");
+    METAD_REQUIRE(N == 0 || d_net_force, "metad_wte_reduce: null net force array");
+    int rc = wte_scratch();
+    if (rc) return rc;
+    long b = ((long)N + kWteThreads * 8L - 1) / (kWteThreads * 8L);
+    if (b < 1) b = 1;
+    if (b > g_wte.blocks) b = g_wte.blocks;
+    wte_reduce_kernel<<<(int)b, kWteThreads, 0, stream>>>((const float4*)d_net_force, N, external_energy, g_wte.partials,
+                                                         g_wte.ticket, d_pe);
+    METAD_LAUNCH_CHECK();
+    return METAD_OK;
+}
+
+extern "C" int metad_wte_scale(float* d_net_force, float* d_net_torque, float* d_net_virial, unsigned pitch, unsigned N,
+                               const double* d_bias, metad_stream_t stream) {
+    METAD_REQUIRE(d_bias, "metad_wte_scale: null bias");
+    if (N == 0) return METAD_OK;
+    METAD_REQUIRE(d_net_force, "metad_wte_scale: null net force array");
+    METAD_REQUIRE(!d_net_virial || pitch >= N, "metad_wte_scale: virial pitch smaller than N");
+    long b = ((long)N + kWteThreads * 4L - 1) / (kWteThreads * 4L);
+    const long cap = device_sm_count() * 8L;
+    if (b > cap) b = cap;
+    wte_scale_kernel<<<(int)b, kWteThreads, 0, stream>>>((float4*)d_net_force, (float4*)d_net_torque, d_net_virial, pitch, N,
+                                                        d_bias);
+    METAD_LAUNCH_CHECK();
+    return METAD_OK;
+}
+
+extern "C" int metad_umbrella_apply(int kind, double cv0, double kappa, double width_flat, double scale,
+                                    const double* d_cv, const double* d_bias_in, double* d_bias_out,
+                                    double* d_energy_out, metad_stream_t stream) {
+    METAD_REQUIRE(d_cv, "metad_umbrella_apply: null cv");
+    METAD_REQUIRE(kind >= 0 && kind <= 4, "cv: Invalid umbrella mode specified.");
+    umbrella_kernel<<<1, 32, 0, stream>>>(kind, cv0, kappa, width_flat, scale, d_cv, d_bias_in, d_bias_out, d_energy_out);
+    METAD_LAUNCH_CHECK();
+    return METAD_OK;
+}

@@ -2,7 +2,10 @@
 // TEST INFRASTRUCTURE ONLY; see the header of metad_oracle.hpp ("parity unpinned").
 // Every entry point exists twice: suffix _f32 (S=float) and _f64 (S=double).  Arrays cross the
 // boundary as double (outputs) / float (particle data, as HOOMD's fp32 position array).
+#include <iostream>
 #include "metad_oracle.hpp"
+
+static std::ios_base::Init g_iostream_init;   // the toolchain links libstdc++ statically: make sure locales exist
 
 using namespace oracle;
 
@@ -149,6 +152,7 @@ template <class S> void wte_scale_c(float* f4, float* t4, float* vir, unsigned p
         auto* m = (MeshCV<S>*)h; for (size_t i = 0; i < (size_t)3 * N; ++i) out[i] = m->cells[i];                     \
     }                                                                                                                 \
     double orc_mesh_mode_sq_##SFX(void* h) { return ((MeshCV<S>*)h)->mode_sq; }                                       \
+    void orc_mesh_set_literal_copysignf_##SFX(void* h, int on) { ((MeshCV<S>*)h)->literal_copysignf = on != 0; }      \
     void orc_mesh_qmax_##SFX(void* h, double* out4) {                                                                 \
         S o[4]; ((MeshCV<S>*)h)->qmax(o); for (int i = 0; i < 4; ++i) out4[i] = o[i];                                 \
     }                                                                                                                 \

@@ -227,10 +227,16 @@ template <class S> struct MeshCV {
         else if (xsq <= S(9.0 / 4.0)) return S(1.0 / 2.0) * (S(3.0 / 2.0) - xabs) * (S(3.0 / 2.0) - xabs);
         return S(0.0);
     }
-    // assignTSCderiv: OrderParameterMesh.cc:470-483 (copysignf even when S=double, note 3 of SURVEY 8a)
-    static S Wd(S x) {
+    // assignTSCderiv: OrderParameterMesh.cc:470-483.  The reference writes |x| as copysignf(x, 1) even when
+    // Scalar = double (SURVEY 8a note 3), i.e. a double build rounds |x| to float.  In a SINGLE_PRECISION build
+    // copysignf is exact.  `literal_copysignf` selects the literal restatement (default); with it switched off
+    // the double instance evaluates the single-precision build's formula (|x| exact) in double, which is the
+    // tolerance target for forces: the float-rounded |x| of the double build multiplies the DC term of the
+    // inverse mesh and perturbs ideal-gas-like forces at the 1e-2 level (tests/test_oracle.py demonstrates it).
+    bool literal_copysignf = true;
+    S Wd(S x) const {
         S xsq = x * x;
-        S xabs = (S)copysignf((float)x, 1.0f);
+        S xabs = literal_copysignf ? (S)copysignf((float)x, 1.0f) : std::fabs(x);
         S fac = (S(3.0 / 2.0) - xabs);
         S ret(0.0);
         if (xsq <= S(1.0 / 4.0)) ret = -S(2.0) * x;

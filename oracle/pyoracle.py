@@ -61,6 +61,7 @@ def lib():
             g("orc_mesh_mode_sq").restype = C.c_double
             g("orc_mesh_mode_sq").argtypes = [C.c_void_p]
             g("orc_mesh_qmax").argtypes = [C.c_void_p, _dp]
+            g("orc_mesh_set_literal_copysignf").argtypes = [C.c_void_p, C.c_int]
             g("orc_lamellar_cv").restype = C.c_double
             g("orc_lamellar_cv").argtypes = [_fp, C.c_uint, C.c_uint, _dp, C.c_int, _ip, C.c_int, _dp, _dp]
             g("orc_lamellar_forces").argtypes = [_fp, C.c_uint, C.c_uint, _dp, C.c_int, _ip, C.c_int, _dp, C.c_double, _dp]
@@ -123,13 +124,16 @@ def make_postype(pos, types=None):
 class Mesh:
     """OrderParameterMesh oracle (CPU path)."""
 
-    def __init__(self, nx, ny, nz, mode, L, n_global, prec="f64", tilt=(0, 0, 0)):
+    def __init__(self, nx, ny, nz, mode, L, n_global, prec="f64", tilt=(0, 0, 0), literal_copysignf=True):
+        """literal_copysignf=False: evaluate |x| exactly in assignTSCderiv (what a SINGLE_PRECISION build does);
+        the double instance with this switch off is the tolerance target for forces (see metad_oracle.hpp)."""
         self.prec = prec
         self.dims = (nx, ny, nz)
         self.M = nx * ny * nz
         mode = np.ascontiguousarray(mode, dtype=np.float64)
         self._box = box6(L, tilt)
         self.h = _fn("orc_mesh_create", prec)(nx, ny, nz, _d(mode), len(mode), _d(self._box), n_global)
+        _fn("orc_mesh_set_literal_copysignf", prec)(self.h, int(literal_copysignf))
 
     def __del__(self):
         try:

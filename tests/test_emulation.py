@@ -1,0 +1,111 @@
+"""CPU emulation of the device pipeline: tests/cpu_emul/*.cu run the SAME __host__ __device__ bodies the CUDA
+kernels are made of (csrc/mesh_fft.cuh, mesh_fft_kernels.cuh, mesh_kernels.cuh), thread by thread, with the
+kernels' tile and index mapping.  This pins the index logic (Stockham stages, R2C packing, the kx=0 plane
+untangling, tile-major keys, 27-round spreading, padded-tile merge, gather) without a GPU."""
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from conftest import build_emul
+
+
+def np_chi(dims):
+    nx, ny, nz = dims
+    nn = lambda n: np.arange(n) < (n // 2 + n % 2)
+    return nn(nz)[:, None, None] & nn(ny)[None, :, None] & nn(nx)[None, None, :]
+
+
+def run_fft(exe, rho, N, mode_sq, stage):
+    nz, ny, nx = rho.shape
+    with tempfile.TemporaryDirectory() as d:
+        fin, fout = os.path.join(d, "in.bin"), os.path.join(d, "out.bin")
+        rho.astype(np.float32).tofile(fin)
+        subprocess.check_call([exe, str(nx), str(ny), str(nz), repr(float(N)), repr(float(mode_sq)), str(stage), fin, fout])
+        raw = np.fromfile(fout, dtype=np.uint8)
+    M = rho.size
+    return raw[:4 * M].view(np.float32).reshape(nz, ny, nx), raw[4 * M:].view(np.float64)[0]
+
+
+@pytest.mark.parametrize("dims", [(32, 16, 16), (64, 32, 16), (32, 32, 64), (128, 16, 32), (256, 16, 16), (32, 128, 16),
+                                  (32, 16, 256), (512, 16, 16), (1024, 16, 16), (32, 512, 16), (32, 16, 512)])
+def test_fft_sweeps_match_numpy(dims):
+    exe = build_emul("fft_emul")
+    nx, ny, nz = dims
+    rng = np.random.default_rng(sum(dims))
+    rho = (rng.random((nz, ny, nx)) - 0.5).astype(np.float32)
+    # forward x and y sweeps: packed half spectrum
+    out, _ = run_fft(exe, rho, 1, 1, 0)
+    P = out.view(np.complex64).reshape(nz, ny, nx // 2)
+    Fxy = np.fft.fft(np.fft.rfft(rho.astype(np.float64), axis=2), axis=1)
+    exp = Fxy[:, :, :nx // 2].copy()
+    exp[:, :, 0] = Fxy[:, :, 0] + 1j * Fxy[:, :, nx // 2]          # packed slot: X0 + i X_{nx/2}
+    assert np.abs(P - exp).max() < 5e-7 * np.abs(exp).max()
+    # full pipeline: CV energy and inverse mesh
+    N = rho.size / 4.0
+    out, cv = run_fft(exe, rho, N, N, 1)
+    f = np.fft.fftn(rho.astype(np.float64)) / N
+    a2 = np.abs(f) ** 2
+    d = 0.5 * N / N / N
+    chi = np_chi(dims)
+    s = a2 ** 2 - 2 * d * chi * a2
+    s[0, 0, 0] = 0
+    assert cv == pytest.approx(0.5 * s.sum(), rel=1e-6)
+    inv = (np.fft.ifftn(f * (a2 - d * chi)) * rho.size).real
+    assert np.abs(out - inv).max() < 2e-6 * np.abs(inv).max()
+
+
+def run_mesh(exe, pt, dims, L, n_global, bias, lgT, modes):
+    nx, ny, nz = dims
+    N = pt.shape[0]
+    with tempfile.TemporaryDirectory() as d:
+        fin, fout = os.path.join(d, "in.bin"), os.path.join(d, "out.bin")
+        pt.tofile(fin)
+        subprocess.check_call([exe, str(nx), str(ny), str(nz)] + [repr(float(x)) for x in L] + [str(n_global), repr(bias), str(lgT),
+                              str(len(modes))] + [repr(float(m)) for m in modes] + [fin, fout])
+        raw = np.fromfile(fout, dtype=np.uint8)
+    M = nx * ny * nz
+    cv, msq = raw[:16].view(np.float64)
+    o = 16
+    rho = raw[o:o + 4 * M].view(np.float32).reshape(nz, ny, nx); o += 4 * M
+    inv = raw[o:o + 4 * M].view(np.float32).reshape(nz, ny, nx); o += 4 * M
+    force = raw[o:o + 16 * N].view(np.float32).reshape(N, 4); o += 16 * N
+    cells = raw[o:o + 12 * N].view(np.int32).reshape(N, 3)
+    return cv, msq, rho, inv, force, cells
+
+
+@pytest.mark.parametrize("N,dims,L,lgT,modes,edge", [
+    (1000, (32, 32, 32), (10.0, 10.0, 10.0), 3, (1.0,), False),
+    (1000, (32, 32, 32), (10.0, 10.0, 10.0), 4, (1.0,), True),
+    (5000, (32, 16, 64), (10.0, 7.3, 21.1), 3, (1.0, -1.0), True),
+    (5000, (64, 32, 16), (10.0, 7.3, 21.1), 4, (1.0, -0.5, 2.0), True),
+    (30000, (32, 32, 32), (31.0, 31.0, 31.0), 3, (1.0,), False),
+])
+def test_mesh_pipeline_matches_oracle(oracle, N, dims, L, lgT, modes, edge):
+    exe = build_emul("mesh_emul")
+    rng = np.random.default_rng(N + lgT)
+    Lf = np.asarray(L, dtype=np.float64)
+    pos = ((rng.random((N, 3)) - 0.5) * Lf).astype(np.float32)
+    if edge:      # particles on the upper faces, on the lower corner and one ulp inside
+        pos[0] = [np.float32(Lf[0]) / 2, 0, 0]
+        pos[1] = [-np.float32(Lf[0]) / 2, np.float32(Lf[1]) / 2, -np.float32(Lf[2]) / 2]
+        pos[2] = np.nextafter((Lf / 2).astype(np.float32), np.float32(0))
+    pt = oracle.make_postype(pos, rng.integers(0, len(modes), N))
+    bias = 0.7
+    cv, msq, rho, inv, force, cells = run_mesh(exe, pt, dims, L, N, bias, lgT, modes)
+    m = oracle.Mesh(*dims, modes, L, N, "f64", literal_copysignf=False)
+    cvo = m.current_value(pt)
+    fo = m.forces(pt, bias)
+    m32 = oracle.Mesh(*dims, modes, L, N, "f32")
+    m32.assign(pt)
+    assert np.array_equal(cells, m32.cells())                       # bit-exact against the single-precision build
+    assert msq == m.mode_sq()
+    assert cv == pytest.approx(cvo, rel=1e-6)                       # north-star tolerance for CVs
+    assert np.abs(rho - m.mesh).max() < 2e-6 * max(1.0, np.abs(m.mesh).max())
+    dinv = inv - m.inv_re
+    dinv -= dinv.mean()                                             # DC removal shifts the inverse mesh by a constant
+    assert np.abs(dinv).max() < 5e-6 * np.abs(m.inv_re - m.inv_re.mean()).max()
+    assert np.abs(force - fo).max() < 1e-5 * np.abs(fo).max()       # north-star tolerance for forces
+    assert np.all(force[:, 3] == 0)
