@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- CV + bias-force step benchmark (BASELINE.json metric), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C4|C3|C2|C5|C1] [--impl ours|reference]
+
+A "step" = one pass of the hot path over one batch of synthetic particles:
+    mesh workloads      metad_mesh_cv -> metad_grid_step (1-D grid bias, deposit every `stride`) -> metad_mesh_forces
+    lamellar workloads  metad_lamellar_modes -> metad_grid_step -> metad_lamellar_forces
+Rank 0 prints ONE JSON line (see DESIGN.md "Measurement" for every field).  `value` is measured with the inputs
+resident in HBM; `e2e` repeats the step through the same calls with HOST (pinned) buffers, host->device copy of the
+positions and device->host copy of the forces and the CV inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+STAGE_BYTES_DOC = "algorithmic bytes per launch: see DESIGN.md 'Kernels and rooflines'"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(name, shard=None):
+    from metadynamics_plugin_b200 import workloads
+    return {"C1": workloads.c1, "C2": workloads.c2, "C3": workloads.c3, "C4": workloads.c4, "C5": workloads.c5}[name]()
+
+
+# ---------------------------------------------------------------------------------------------------- ours
+class MeshStep:
+    """mesh CV -> 1-D grid bias -> forces, everything device-resident."""
+    launches_per_step = 15      # bin, 3 scan, reorder, spread, merge, x/y fwd, plane0, z fused, y/x inv, grid step, gather
+
+    def __init__(self, w, ops, torch, calibrate=True):
+        self.ops, self.torch, self.w = ops, torch, w
+        self.N = w["postype"].shape[0]
+        self.box = ops.Box.make(w["L"])
+        self.mesh = ops.Mesh(*w["mesh"], w["mode"])
+        self.d_pt = torch.from_numpy(w["postype"]).cuda()
+        self.d_force = torch.empty_like(self.d_pt)
+        self.t = 0
+        # 1-D grid spanning the observed CV +-50 %, 400 points
+        cv = self.mesh.compute_cv(self.d_pt, self.N, self.box).cpu().item()
+        self.cv0 = cv
+        lo, hi = (0.5 * cv, 1.5 * cv) if cv > 0 else (1.5 * cv, 0.5 * cv)
+        self.grid = ops.BiasGrid([lo], [hi], [400], [0.05 * abs(cv)], W=1e-3 * abs(cv), T_shift=7.0, T=1.0,
+                                 stride=w.get("stride", 100), well_tempered=True)
+
+    def step(self):
+        cv = self.mesh.compute_cv(self.d_pt, self.N, self.box)
+        bias = self.grid.step(self.t, cv)
+        self.mesh.forces(self.d_pt, self.N, self.box, bias, out=self.d_force)
+        self.t += 1
+
+    def algorithmic_bytes(self):
+        M = int(np.prod(self.w["mesh"]))
+        return 48 * self.N + 48 * M
+
+    def stage_bytes(self):
+        N, M = self.N, int(np.prod(self.w["mesh"]))
+        return {"bin": 16 * N, "scan": 0, "reorder": 0, "spread": 16 * N + 4 * M, "merge": 0, "fft_x_fwd": 8 * M, "fft_y_fwd": 8 * M,
+                "fft_z_fused": 8 * M, "fft_y_inv": 8 * M, "fft_x_inv": 8 * M, "gather": 32 * N + 4 * M}
+
+
+class LamellarStep:
+    launches_per_step = 3
+
+    def __init__(self, w, ops, torch):
+        self.ops, self.torch, self.w = ops, torch, w
+        self.N = w["postype"].shape[0]
+        self.box = ops.Box.make(w["L"])
+        self.lam = ops.Lamellar(w["mode"], w["lattice_vectors"])
+        self.d_pt = torch.from_numpy(w["postype"]).cuda()
+        self.d_force = torch.empty_like(self.d_pt)
+        g = w["grid"]
+        self.ncv = len(g["num_points"])
+        self.grid = ops.BiasGrid(g["cv_min"], g["cv_max"], g["num_points"], g["sigma"], W=w["W"], T_shift=w["deltaT"], T=w["T"],
+                                 stride=w["stride"], well_tempered=True)
+        self.cvs = torch.zeros(self.ncv, dtype=torch.float64, device="cuda")
+        if self.ncv == 2:       # second CV = aspect ratio Lx/Ly of the (cubic) box: host scalar
+            self.cvs[1] = 1.0
+        self.t = 0
+
+    def step(self):
+        cv = self.lam.compute_modes(self.d_pt, self.N, self.box)
+        self.cvs[0:1].copy_(cv)
+        bias = self.grid.step(self.t, self.cvs)
+        self.lam.forces(self.d_pt, self.N, self.box, bias[0:1], out=self.d_force)
+        self.t += 1
+
+    def algorithmic_bytes(self):
+        return 48 * self.N
+
+
+def run_ours(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    from metadynamics_plugin_b200 import ops
+
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    peak, peak_src = load_peaks()
+    w = make_workload(args.workload)
+    if world > 1:
+        # replicas: every rank evaluates the full configuration (the sharded mesh path is not wired in yet)
+        pass
+    runner = MeshStep(w, ops, torch) if w["kind"] == "mesh" else LamellarStep(w, ops, torch)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        runner.step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        runner.step()
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    ms_per_step = ms / args.steps
+
+    # per-kernel timing of the dominant kernel (CUDA events inside the library, on the launching stream)
+    roofline = None
+    if w["kind"] == "mesh":
+        runner.mesh.set(2, 1)
+        acc = {}
+        nprof = min(args.steps, 10)
+        for _ in range(nprof):
+            runner.step()
+            torch.cuda.synchronize()
+            for k, v in runner.mesh.timings().items():
+                acc[k] = acc.get(k, 0.0) + v / nprof
+        runner.mesh.set(2, 0)
+        sb = runner.stage_bytes()
+        top = max((k for k in acc if sb[k] > 0), key=lambda k: acc[k])
+        achieved = sb[top] / (acc[top] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": peak_src, "stage_ms": {k: round(v, 4) for k, v in acc.items()},
+                    "step_frac": runner.algorithmic_bytes() / (ms_per_step * 1e-3) / 1e9 / peak}
+    else:
+        achieved = runner.algorithmic_bytes() / (ms_per_step * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "lamellar_modes+grid_step+lamellar_force (whole step)", "achieved": achieved, "peak": peak,
+                    "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src}
+
+    # end to end through the same calls with host buffers
+    h_pt = torch.from_numpy(w["postype"]).pin_memory()
+    h_force = torch.empty_like(h_pt).pin_memory()
+    h_cv = torch.zeros(1, dtype=torch.float64).pin_memory()
+    cv_t = runner.mesh.cv if w["kind"] == "mesh" else runner.lam.cv
+    e2e_steps = max(1, min(args.steps, 20))
+
+    def e2e_step():
+        runner.d_pt.copy_(h_pt, non_blocking=True)
+        runner.step()
+        h_force.copy_(runner.d_force, non_blocking=True)
+        h_cv.copy_(cv_t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    sync_all()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = t.item()
+
+    out = {
+        "metric": "cv_bias_force_steps_per_sec", "value": world * 1e3 / ms_per_step, "unit": "steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (fp64 accumulation)", "data": "synthetic",
+        "ns_per_particle_step": ms_per_step * 1e6 / runner.N,
+        "config": {"workload": "%s: %s" % (w["name"], describe(w)), "N": runner.N, "l2": "inputs larger than L2 (no flush)",
+                   "parallelism": "1 GPU" if world == 1 else "%d independent replicas" % world},
+        "roofline": roofline,
+        "e2e": {"value": world * 1e3 / e2e_ms, "unit": "steps/s", "h2d_bytes_per_step": int(h_pt.numel() * 4),
+                "d2h_bytes_per_step": int(h_force.numel() * 4 + 8), "steps": e2e_steps},
+        "gpu_launches": runner.launches_per_step * args.steps,
+        "clocks": clocks,
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(w, budget_s=args.cpu_budget)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def describe(w):
+    if w["kind"] == "mesh":
+        return "OrderParameterMesh CV + 1-D well-tempered grid bias, N=%d, mesh %dx%dx%d, L=%.3f" % (
+            w["postype"].shape[0], *w["mesh"], w["L"])
+    return "LamellarOrderParameter %d wave vectors + %d-D well-tempered grid bias, N=%d, L=%.3f" % (
+        len(w["lattice_vectors"]), len(w["grid"]["num_points"]), w["postype"].shape[0], w["L"])
+
+
+# ---------------------------------------------------------------------------------------------------- CPU side
+def cpu_step_fn(w, prec="f32"):
+    """One full CV + bias-force step of the reference's CPU path (oracle port, single-threaded like the reference)."""
+    from oracle import pyoracle as po
+    N = w["postype"].shape[0]
+    if w["kind"] == "mesh":
+        m = po.Mesh(*w["mesh"], w["mode"], w["L"], N, prec)
+        phases = {}
+
+        def step():
+            t0 = time.perf_counter(); m.assign(w["postype"])
+            t1 = time.perf_counter(); m.update()
+            t2 = time.perf_counter(); cv = m.cv()
+            t3 = time.perf_counter(); m.forces(w["postype"], 1.0)
+            t4 = time.perf_counter()
+            for k, v in (("assign", t1 - t0), ("fft+convolve", t2 - t1), ("cv_sum", t3 - t2), ("forces", t4 - t3)):
+                phases[k] = phases.get(k, 0.0) + v
+            return cv
+        return step, phases
+    g = w["grid"]
+    grid = po.Grid(g["cv_min"], g["cv_max"], g["num_points"], g["sigma"], W=w["W"], T_shift=w["deltaT"], T=w["T"], stride=w["stride"],
+                   well_tempered=True, prec=prec)
+    state = {"t": 0}
+    phases = {}
+
+    def step():
+        t0 = time.perf_counter()
+        cv, _ = po.lamellar_cv(w["postype"], N, w["mode"], w["lattice_vectors"], w["L"], prec)
+        t1 = time.perf_counter()
+        vals = [cv] + ([1.0] if len(g["num_points"]) == 2 else [])
+        b = grid.update(state["t"], vals)
+        t2 = time.perf_counter()
+        po.lamellar_forces(w["postype"], N, w["mode"], w["lattice_vectors"], w["L"], b[0], prec)
+        t3 = time.perf_counter()
+        state["t"] += 1
+        for k, v in (("cv", t1 - t0), ("grid", t2 - t1), ("forces", t3 - t2)):
+            phases[k] = phases.get(k, 0.0) + v
+        return cv
+    return step, phases
+
+
+def cpu_baseline(w, budget_s=25.0):
+    step, phases = cpu_step_fn(w)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        step()
+        n += 1
+        if time.perf_counter() - t0 > budget_s or n >= 50:
+            break
+    dt = (time.perf_counter() - t0) / n
+    return {"value": 1.0 / dt, "unit": "steps/s", "cores": 1, "kind": "port",
+            "sample": "%d full step(s) of the same workload, oracle port of the reference CPU path (float instance), "
+                      "single thread as the reference is serial per rank; host has %d cores" % (n, os.cpu_count()),
+            "phases_s_per_step": {k: v / n for k, v in phases.items()}}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (HOOMD cannot be built here -> oracle port)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = make_workload(args.workload)
+    step, phases = cpu_step_fn(w)
+    budget = 150.0
+    t_start = time.perf_counter()
+    done_w = 0
+    for _ in range(args.warmup):
+        if done_w >= 1 and time.perf_counter() - t_start > 0.25 * budget:
+            break
+        step(); done_w += 1
+    phases.clear()
+    n, t0 = 0, time.perf_counter()
+    for _ in range(args.steps):
+        step(); n += 1
+        if time.perf_counter() - t_start > budget:
+            break
+    dt = (time.perf_counter() - t0) / n
+    N = w["postype"].shape[0]
+    sample = ("%d of %d requested full step(s) (time-bounded), %d warm-up; oracle port of the reference CPU path, float instance, "
+              "1 thread (reference CPU path is serial per MPI rank); host has %d cores" % (n, args.steps, done_w, os.cpu_count()))
+    out = {"impl": "reference", "metric": "cv_bias_force_steps_per_sec", "value": 1.0 / dt, "unit": "steps/s",
+           "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": n, "warmup": done_w, "ms_per_step": dt * 1e3,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "ns_per_particle_step": dt * 1e9 / N,
+           "config": {"workload": "%s: %s" % (w["name"], describe(w)), "N": N},
+           "cpu_baseline": {"value": 1.0 / dt, "unit": "steps/s", "cores": 1, "kind": "port", "sample": sample,
+                            "phases_s_per_step": {k: v / n for k, v in phases.items()}},
+           "e2e": {"value": 1.0 / dt, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="C4", choices=["C1", "C2", "C3", "C4", "C5"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=25.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

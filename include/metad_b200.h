@@ -97,9 +97,12 @@ int metad_mesh_forces(metad_mesh* p, const float* d_postype, float* d_force, uns
  *   which = 0: cell coordinates (ix,iy,iz) per particle, int[3*N], input order
  *           1: density mesh rho, float[nx*ny*nz], index x + nx*(y + ny*z)
  *           2: Re(inverse mesh), float[nx*ny*nz]
- *           3: sum of mode^2 (double[1])                                                        */
+ *           3: sum of mode^2 (double[1])
+ *           4: per-stage milliseconds of the last cv + forces pair, float[11] (needs key 2): bin, scan, reorder,
+ *              spread, merge, fft x fwd, fft y fwd, fft z fused, fft y inv, fft x inv, gather                    */
 int metad_mesh_get(metad_mesh* p, int which, void* h_out);
-/* knobs: key 0 = resort period (1 = rebuild the cell order every call, default) */
+/* knobs: key 0 = resort period (1 = rebuild the cell order every call, default)
+ *        key 1 = keep a copy of rho for metad_mesh_get(1)      key 2 = record per-stage CUDA events (profiling) */
 int metad_mesh_set(metad_mesh* p, int key, long value);
 
 /* ------------------------------------------------------------------------------------------------

@@ -20,6 +20,10 @@ using namespace metad;
 using namespace metad::mesh;
 using namespace metad::fft;
 
+// stages timed when profiling is on: 0 bin, 1 scan, 2 reorder, 3 spread, 4 merge, 5 fft x fwd, 6 fft y fwd,
+// 7 fft z fused (+plane0), 8 fft y inv, 9 fft x inv, 10 gather
+constexpr int kNumStages = 11;
+
 struct metad_mesh {
     Geom g;
     int ntypes = 0;
@@ -42,6 +46,9 @@ struct metad_mesh {
     bool have_cv = false;
     unsigned last_N = 0;
     bool keep_rho = false;
+    // optional per-stage timing (CUDA events on the caller's stream): boundaries between the stages below
+    bool profile = false;
+    cudaEvent_t ev[kNumStages + 2] = {};      // 0..10 stage starts of the cv pipeline (10 = its end), 11/12 gather start/end
     size_t M() const { return (size_t)g.nx * g.ny * g.nz; }
 };
 
@@ -130,13 +137,27 @@ template <int L> int run_z(metad_mesh* p, unsigned N_global, double* d_cv, cudaS
         default: set_error("cv.mesh: unsupported mesh dimension"); rc = METAD_ERR_UNSUPPORTED; \
     }
 
+// event i marks the START of stage i (event kNumStages the end of the cv pipeline, kNumStages+1 the end of gather)
+int mark(metad_mesh* p, int i, cudaStream_t st) {
+    if (!p->profile) return METAD_OK;
+    if (!p->ev[i]) METAD_CUDA(cudaEventCreate(&p->ev[i]));
+    METAD_CUDA(cudaEventRecord(p->ev[i], st));
+    return METAD_OK;
+}
+
 int fft_pipeline(metad_mesh* p, unsigned N_global, double* d_cv, cudaStream_t st) {
     int rc = METAD_OK;
+    rc = mark(p, 5, st); if (rc) return rc;
     METAD_DISPATCH_LEN(p->g.nx / 2, (run_x<LL>(p, false, st))); if (rc) return rc;
+    rc = mark(p, 6, st); if (rc) return rc;
     METAD_DISPATCH_LEN(p->g.ny, (run_y<LL>(p, false, st))); if (rc) return rc;
+    rc = mark(p, 7, st); if (rc) return rc;
     METAD_DISPATCH_LEN(p->g.nz, (run_z<LL>(p, N_global, d_cv, st))); if (rc) return rc;
+    rc = mark(p, 8, st); if (rc) return rc;
     METAD_DISPATCH_LEN(p->g.ny, (run_y<LL>(p, true, st))); if (rc) return rc;
+    rc = mark(p, 9, st); if (rc) return rc;
     METAD_DISPATCH_LEN(p->g.nx / 2, (run_x<LL>(p, true, st))); if (rc) return rc;
+    rc = mark(p, 10, st); if (rc) return rc;        // end of the cv pipeline (re-recorded as start of gather by forces)
     return METAD_OK;
 }
 
@@ -230,6 +251,7 @@ extern "C" int metad_mesh_destroy(metad_mesh* p) {
     cudaFree(p->d_count); cudaFree(p->d_start); cudaFree(p->d_block_sums); cudaFree(p->d_scratch); cudaFree(p->d_buf);
     cudaFree(p->d_rho_keep); cudaFree(p->d_twx); cudaFree(p->d_twy); cudaFree(p->d_twz); cudaFree(p->d_sums);
     cudaFree(p->d_partials); cudaFree(p->d_ticket);
+    for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     delete p;
     return METAD_OK;
 }
@@ -247,6 +269,7 @@ extern "C" int metad_mesh_cv(metad_mesh* p, const float* d_postype, unsigned N, 
     p->have_cv = false;
 
     METAD_CUDA(cudaMemsetAsync(p->d_sums, 0, 2 * sizeof(double), stream));
+    rc = mark(p, 0, stream); if (rc) return rc;
     if (N > 0) {
         long nb = ((long)N + kBinThreads * 4L - 1) / (kBinThreads * 4L);
         if (nb > sms * 16L) nb = sms * 16L;
@@ -254,6 +277,7 @@ extern "C" int metad_mesh_cv(metad_mesh* p, const float* d_postype, unsigned N, 
                                                             p->d_count, p->d_sums);
         METAD_LAUNCH_CHECK();
     }
+    rc = mark(p, 1, stream); if (rc) return rc;
     const unsigned nb_scan = (unsigned)(M / kScanBlockItems);
     scan_reduce_kernel<<<nb_scan, kScanThreads, 0, stream>>>((const uint4*)p->d_count, p->d_block_sums);
     METAD_LAUNCH_CHECK();
@@ -261,6 +285,7 @@ extern "C" int metad_mesh_cv(metad_mesh* p, const float* d_postype, unsigned N, 
     METAD_LAUNCH_CHECK();
     scan_apply_kernel<<<nb_scan, kScanThreads, 0, stream>>>((uint4*)p->d_count, p->d_block_sums, p->d_start, (unsigned)M);
     METAD_LAUNCH_CHECK();
+    rc = mark(p, 2, stream); if (rc) return rc;
     if (N > 0) {
         long nb = ((long)N + kBinThreads * 4L - 1) / (kBinThreads * 4L);
         if (nb > sms * 16L) nb = sms * 16L;
@@ -268,12 +293,14 @@ extern "C" int metad_mesh_cv(metad_mesh* p, const float* d_postype, unsigned N, 
                                                                 p->d_start, p->d_sorted, p->d_perm);
         METAD_LAUNCH_CHECK();
     }
+    rc = mark(p, 3, stream); if (rc) return rc;
     if (g.lgT == 4)
         mesh_spread_kernel<4><<<num_tiles(g), kTileThreads, 0, stream>>>(p->d_sorted, p->d_perm, p->d_start, g, p->d_scratch);
     else
         mesh_spread_kernel<3><<<num_tiles(g), kTileThreads, 0, stream>>>(p->d_sorted, p->d_perm, p->d_start, g, p->d_scratch);
     METAD_LAUNCH_CHECK();
     if (p->keep_rho && !p->d_rho_keep) METAD_CUDA(cudaMalloc(&p->d_rho_keep, sizeof(float) * M));
+    rc = mark(p, 4, stream); if (rc) return rc;
     {
         long nb = (long)((M + 255) / 256);
         if (nb > sms * 32L) nb = sms * 32L;
@@ -305,6 +332,7 @@ extern "C" int metad_mesh_forces(metad_mesh* p, const float* d_postype, float* d
     fp.nb2[1] = (float)((double)g.ny / box->L[1]);
     fp.nb3[2] = (float)((double)g.nz / box->L[2]);
     fp.two_over_n = 2.0 / (double)N_global;
+    { int rc = mark(p, 11, stream); if (rc) return rc; }
     if (g.lgT == 4)
         mesh_gather_kernel<4><<<num_tiles(g), kTileThreads, 0, stream>>>(p->d_sorted, p->d_perm, p->d_start, g, p->d_buf, fp, d_bias,
                                                                        (float4*)d_force);
@@ -312,6 +340,7 @@ extern "C" int metad_mesh_forces(metad_mesh* p, const float* d_postype, float* d
         mesh_gather_kernel<3><<<num_tiles(g), kTileThreads, 0, stream>>>(p->d_sorted, p->d_perm, p->d_start, g, p->d_buf, fp, d_bias,
                                                                        (float4*)d_force);
     METAD_LAUNCH_CHECK();
+    { int rc = mark(p, 12, stream); if (rc) return rc; }
     return METAD_OK;
 }
 
@@ -343,6 +372,14 @@ extern "C" int metad_mesh_get(metad_mesh* p, int which, void* h_out) {
         case 3:
             METAD_CUDA(cudaMemcpy(h_out, p->d_sums, sizeof(double), cudaMemcpyDeviceToHost));
             return METAD_OK;
+        case 4: {
+            // per-stage milliseconds of the last metad_mesh_cv + metad_mesh_forces pair (float[kNumStages])
+            if (!p->profile || !p->ev[0] || !p->ev[12]) { set_error("metad_mesh_get: profiling is off (metad_mesh_set(p, 2, 1))"); return METAD_ERR_STATE; }
+            float* out = (float*)h_out;
+            for (int i = 0; i < 10; ++i) METAD_CUDA(cudaEventElapsedTime(out + i, p->ev[i], p->ev[i + 1]));
+            METAD_CUDA(cudaEventElapsedTime(out + 10, p->ev[11], p->ev[12]));
+            return METAD_OK;
+        }
         default:
             set_error("metad_mesh_get: unknown selector");
             return METAD_ERR_INVALID;
@@ -354,6 +391,7 @@ extern "C" int metad_mesh_set(metad_mesh* p, int key, long value) {
     switch (key) {
         case 0: return METAD_OK;                       // resort period: the order is rebuilt every call in this version
         case 1: p->keep_rho = value != 0; return METAD_OK;
+        case 2: p->profile = value != 0; return METAD_OK;
         default: set_error("metad_mesh_set: unknown key"); return METAD_ERR_INVALID;
     }
 }

@@ -127,6 +127,15 @@ class Mesh:
     def inv(self):
         return self._mesh(2)
 
+    STAGES = ("bin", "scan", "reorder", "spread", "merge", "fft_x_fwd", "fft_y_fwd", "fft_z_fused", "fft_y_inv", "fft_x_inv",
+              "gather")
+
+    def timings(self):
+        """Per-stage milliseconds of the last compute_cv + forces pair (profiling knob 2 must be on)."""
+        out = np.empty(len(self.STAGES), dtype=np.float32)
+        check(lib.metad_mesh_get(self.h, 4, out.ctypes.data_as(C.c_void_p)))
+        return dict(zip(self.STAGES, out.tolist()))
+
     def mode_sq(self):
         out = np.empty(1, dtype=np.float64)
         check(lib.metad_mesh_get(self.h, 3, out.ctypes.data_as(C.c_void_p)))

@@ -1,0 +1,290 @@
+"""GPU parity tests: the sm_100a path (through the C ABI, include/metad_b200.h) against the CPU oracle.
+
+Tolerances are the north star's (BASELINE.json): CV values 1e-6 relative, forces 1e-5 (relative to max |F|),
+cell / bin / grid indices bit-exact against the single-precision CPU build.  Oracle truth = the double
+instance (for the mesh forces with |x| evaluated exactly, see oracle/metad_oracle.hpp on copysignf).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from metadynamics_plugin_b200 import ops, _abi       # raises if libmetad_b200.so is missing: no fallback
+    return ops
+
+
+def rand_pt(N, L, ntypes, seed):
+    rng = np.random.default_rng(seed)
+    L = np.broadcast_to(np.asarray(L, float), (3,))
+    pos = ((rng.random((N, 3)) - 0.5) * L).astype(np.float32)
+    return pos, rng.integers(0, ntypes, N).astype(np.int32)
+
+
+def to_dev(gpu, pos, types):
+    return gpu.make_postype(pos, types)
+
+
+def host_pt(oracle, pos, types):
+    return oracle.make_postype(pos, types)
+
+
+# ------------------------------------------------------------------------------------------------ lamellar
+@pytest.mark.parametrize("N,L,tilt,lv,modes", [
+    (4096, 16.0, (0, 0, 0), [(0, 0, 3), (0, 3, 0), (3, 0, 0)], [1.0, -1.0]),
+    (100003, (20.0, 24.0, 18.0), (0, 0, 0), [(0, 0, 5)], [1.0, -1.0, 0.5]),
+    (50000, (20.0, 24.0, 18.0), (0.1, -0.2, 0.05), [(1, 2, 0), (2, -1, 1)], [1.0, -1.0]),
+    (20000, 12.0, (0, 0, 0), [(i % 3, (i + 1) % 4, i % 5 + 1) for i in range(11)], [1.0, -1.0]),      # > 8 modes: two passes
+    (1, 5.0, (0, 0, 0), [(0, 0, 1)], [2.0]),
+])
+def test_lamellar_cv_and_forces(gpu, oracle, N, L, tilt, lv, modes):
+    import torch
+    pos, types = rand_pt(N, L, len(modes), 7)
+    d_pt = to_dev(gpu, pos, types)
+    box = gpu.Box.make(np.broadcast_to(np.asarray(L, float), (3,)), tilt)
+    lam = gpu.Lamellar(modes, lv)
+    cv = lam.compute_modes(d_pt, N, box).cpu().item()
+    fm = lam.modes.cpu().numpy().reshape(-1, 2)
+    h_pt = host_pt(oracle, pos, types)
+    cvo, fmo = oracle.lamellar_cv(h_pt, N, modes, lv, L, "f64", tilt)
+    scale = np.sqrt(N) * max(abs(m) for m in modes)
+    assert np.abs(fm - fmo).max() < 2e-6 * scale
+    assert abs(cv - cvo) < max(1e-6 * abs(cvo), 2e-6 * scale * len(lv) / N)
+    bias = torch.tensor([0.83], dtype=torch.float64, device="cuda")
+    f = lam.forces(d_pt, N, box, bias).cpu().numpy()
+    fo = oracle.lamellar_forces(h_pt, N, modes, lv, L, 0.83, "f64", tilt)
+    assert np.abs(f - fo).max() < 1e-5 * np.abs(fo).max()
+    assert np.all(f[:, 3] == 0)
+
+
+def test_lamellar_ordered_cv_relative(gpu, oracle):
+    """Lamellar-ordered melt (config C2 at reduced N): CV is O(0.1), 1e-6 relative."""
+    from metadynamics_plugin_b200 import workloads
+    w = workloads.c2(N=65536)
+    N = w["postype"].shape[0]
+    import torch
+    d_pt = torch.from_numpy(w["postype"]).cuda()
+    lam = gpu.Lamellar(w["mode"], w["lattice_vectors"])
+    cv = lam.compute_modes(d_pt, N, gpu.Box.make(w["L"])).cpu().item()
+    cvo, _ = oracle.lamellar_cv(w["postype"], N, w["mode"], w["lattice_vectors"], w["L"])
+    assert abs(cvo) > 0.05
+    assert cv == pytest.approx(cvo, rel=1e-6)
+
+
+def test_lamellar_sharded_modes_allreduce_equivalence(gpu, oracle):
+    """Particle-sharded evaluation (the multi-GPU decomposition): partial modes of the shards add up to the
+    single-shard modes; finalize after the (emulated) all-reduce gives the same CV."""
+    pos, types = rand_pt(30000, 14.0, 2, 3)
+    lv, modes = [(0, 0, 3), (2, 1, 0)], [1.0, -1.0]
+    box = gpu.Box.make(14.0)
+    full = gpu.Lamellar(modes, lv)
+    cv_full = full.compute_modes(to_dev(gpu, pos, types), 30000, box).cpu().item()
+    acc = None
+    for lo, hi in ((0, 7000), (7000, 7001), (7001, 30000)):
+        part = gpu.Lamellar(modes, lv)
+        part.compute_modes(to_dev(gpu, pos[lo:hi], types[lo:hi]), 30000, box, finalize=False)
+        acc = part.modes.clone() if acc is None else acc + part.modes
+    full.modes.copy_(acc)
+    assert full.finalize(30000).cpu().item() == pytest.approx(cv_full, rel=1e-12, abs=1e-15)
+
+
+# ------------------------------------------------------------------------------------------------ mesh
+MESH_CASES = [
+    (1000, (32, 32, 32), 10.0, (1.0,), True),
+    (5000, (32, 16, 64), (10.0, 7.3, 21.1), (1.0, -1.0), True),
+    (5000, (64, 32, 16), (10.0, 7.3, 21.1), (1.0, -0.5, 2.0), True),
+    (131072, (64, 64, 64), 50.8, (1.0,), False),
+    (300000, (128, 64, 128), (70.0, 35.0, 70.0), (1.0,), False),        # 16^3 tiles
+    (3, (32, 32, 32), 6.0, (1.0,), False),
+]
+
+
+@pytest.mark.parametrize("N,dims,L,modes,edge", MESH_CASES)
+def test_mesh_cv_forces_cells(gpu, oracle, N, dims, L, modes, edge):
+    import torch
+    Lf = np.broadcast_to(np.asarray(L, float), (3,))
+    pos, types = rand_pt(N, Lf, len(modes), N % 1000 + 1)
+    if edge:
+        pos[0] = [np.float32(Lf[0]) / 2, 0, 0]
+        pos[1] = [-np.float32(Lf[0]) / 2, np.float32(Lf[1]) / 2, -np.float32(Lf[2]) / 2]
+        pos[2] = np.nextafter((Lf / 2).astype(np.float32), np.float32(0))
+    d_pt = to_dev(gpu, pos, types)
+    h_pt = host_pt(oracle, pos, types)
+    box = gpu.Box.make(Lf)
+    mesh = gpu.Mesh(*dims, modes)
+    mesh.set(1, 1)                                               # keep rho for inspection
+    cv = mesh.compute_cv(d_pt, N, box).cpu().item()
+    m = oracle.Mesh(*dims, modes, Lf, N, "f64", literal_copysignf=False)
+    cvo = m.current_value(h_pt)
+    m32 = oracle.Mesh(*dims, modes, Lf, N, "f32")
+    m32.assign(h_pt)
+    assert np.array_equal(mesh.cells(), m32.cells())             # bit-exact cell indices
+    assert mesh.mode_sq() == m.mode_sq()
+    assert np.abs(mesh.rho() - m.mesh).max() < 2e-6 * max(1.0, np.abs(m.mesh).max())
+    assert cv == pytest.approx(cvo, rel=1e-6)
+    bias = torch.tensor([0.61], dtype=torch.float64, device="cuda")
+    f = mesh.forces(d_pt, N, box, bias).cpu().numpy()
+    fo = m.forces(h_pt, 0.61)
+    assert np.abs(f - fo).max() < 1e-5 * np.abs(fo).max()
+    assert np.all(f[:, 3] == 0)
+    # determinism: a second evaluation is bitwise identical (no float atomics, fixed summation orders)
+    cv2 = mesh.compute_cv(d_pt, N, box).cpu().item()
+    f2 = mesh.forces(d_pt, N, box, bias).cpu().numpy()
+    assert cv2 == cv and np.array_equal(f, f2)
+
+
+def test_mesh_order_independence(gpu):
+    """Shuffling the particle array permutes the forces and leaves CV / forces bitwise unchanged."""
+    import torch
+    N, dims, L = 40000, (64, 64, 64), 30.0
+    pos, types = rand_pt(N, L, 1, 5)
+    box = gpu.Box.make(L)
+    mesh = gpu.Mesh(*dims, [1.0])
+    bias = torch.tensor([1.0], dtype=torch.float64, device="cuda")
+    cv = mesh.compute_cv(to_dev(gpu, pos, types), N, box).cpu().item()
+    f = mesh.forces(to_dev(gpu, pos, types), N, box, bias).cpu().numpy()
+    perm = np.random.default_rng(0).permutation(N)
+    d2 = to_dev(gpu, pos[perm], types[perm])
+    cv2 = mesh.compute_cv(d2, N, box).cpu().item()
+    f2 = mesh.forces(d2, N, box, bias).cpu().numpy()
+    assert cv2 == pytest.approx(cv, rel=1e-6)
+    assert np.abs(f2 - f[perm]).max() < 1e-5 * np.abs(f).max()
+
+
+def test_mesh_c1_golden_with_umbrella(gpu, oracle):
+    """Config C1 (the reference's test/test_mesh.py geometry): CV, device-side harmonic umbrella, forces."""
+    import json, os, torch
+    from metadynamics_plugin_b200 import workloads
+    here = os.path.dirname(os.path.abspath(__file__))
+    gold = json.load(open(os.path.join(here, "golden", "golden.json")))
+    data = np.load(os.path.join(here, "golden", "golden.npz"))
+    w = workloads.c1()
+    d_pt = torch.from_numpy(w["postype"]).cuda()
+    box = gpu.Box.make(w["L"])
+    mesh = gpu.Mesh(*w["mesh"], w["mode"])
+    cv = mesh.compute_cv(d_pt, 1000, box)
+    assert cv.cpu().item() == pytest.approx(gold["c1_cv"], rel=1e-6)
+    u = w["umbrella"]
+    energy = torch.zeros(1, dtype=torch.float64, device="cuda")
+    bias = gpu.umbrella_apply("harmonic", cv, None, cv0=u["cv0"], kappa=u["kappa"], energy_out=energy)
+    assert bias.cpu().item() == pytest.approx(gold["c1_bias"], rel=1e-4)       # kappa*(cv-cv0): cancellation amplifies 1e-6
+    assert energy.cpu().item() == pytest.approx(gold["c1_umbrella_energy"], rel=2e-4)
+    # forces with the oracle's bias (isolates the force kernel from the umbrella's cancellation)
+    b = torch.tensor([gold["c1_bias"]], dtype=torch.float64, device="cuda")
+    f = mesh.forces(d_pt, 1000, box, b).cpu().numpy()
+    assert np.abs(f - data["c1_forces"]).max() < 1e-5 * np.abs(data["c1_forces"]).max()
+    assert np.array_equal(mesh.cells(), data["c1_cells"])
+
+
+def test_mesh_rejects_unsupported(gpu):
+    from metadynamics_plugin_b200._abi import MetadError
+    with pytest.raises(MetadError, match="power of two"):
+        gpu.Mesh(48, 32, 32, [1.0])
+    mesh = gpu.Mesh(32, 32, 32, [1.0])
+    import torch
+    pt = gpu.make_postype(np.zeros((4, 3), np.float32))
+    with pytest.raises(MetadError, match="triclinic"):
+        mesh.compute_cv(pt, 4, gpu.Box.make(5.0, (0.1, 0, 0)))
+    with pytest.raises(MetadError, match="metad_mesh_cv"):
+        mesh.forces(pt, 4, gpu.Box.make(5.0), torch.zeros(1, dtype=torch.float64, device="cuda"))
+
+
+# ------------------------------------------------------------------------------------------------ bias grid
+@pytest.mark.parametrize("dims_cfg", [
+    dict(cv_min=[-2.0], cv_max=[2.0], num_points=[400], sigma=[0.05]),
+    dict(cv_min=[0.0, 0.0], cv_max=[1.0, 2.0], num_points=[20, 30], sigma=[0.25, 0.1]),
+    dict(cv_min=[-2.0, 0.0], cv_max=[2.0, 2.0], num_points=[256, 256], sigma=[0.05, 0.1]),
+    dict(cv_min=[0.0, -1.0, 2.0], cv_max=[1.0, 1.0, 3.0], num_points=[12, 9, 7], sigma=[0.2, 0.3, 0.25]),
+])
+@pytest.mark.parametrize("well_tempered", [False, True])
+def test_bias_grid_sequence(gpu, oracle, dims_cfg, well_tempered):
+    import torch
+    d = len(dims_cfg["num_points"])
+    kw = dict(W=0.8, T_shift=7.0, T=1.3, stride=3, well_tempered=well_tempered)
+    g = gpu.BiasGrid(**dims_cfg, **kw)
+    o = oracle.Grid(**dims_cfg, **kw)
+    rng = np.random.default_rng(d)
+    lo, hi = np.array(dims_cfg["cv_min"]), np.array(dims_cfg["cv_max"])
+    s = lo + (hi - lo) * rng.random(d)
+    for t in range(14):
+        s = np.clip(s + 0.04 * (hi - lo) * rng.normal(size=d), lo - 0.02 * (hi - lo), hi + 0.02 * (hi - lo))   # occasionally off-grid
+        if t == 5:
+            s = lo + 0.3 * (hi - lo) / (np.array(dims_cfg["num_points"]) - 1)       # forward-difference branch
+        if t == 9:
+            s = hi - 0.3 * (hi - lo) / (np.array(dims_cfg["num_points"]) - 1)       # backward-difference branch
+        b = g.step(t, torch.tensor(s, dtype=torch.float64, device="cuda")).cpu().numpy()
+        bo = o.update(t, s)
+        np.testing.assert_allclose(b, bo, rtol=1e-9, atol=1e-12)
+    for name in ("grid", "reweighted", "weight", "sigma_grid"):
+        np.testing.assert_allclose(g.get(name), o.get(name), rtol=1e-10, atol=1e-300, err_msg=name)
+    for name in ("hist", "hist_gauss", "hist_delta"):                               # integer grids: bit-exact
+        assert np.array_equal(g.get(name), o.get(name).astype(np.uint32)), name
+    gs, os_ = g.scalars(), o.scalars()
+    assert gs["num_gaussians"] == os_["num_gaussians"] == 5
+    assert gs["bias_potential"] == pytest.approx(os_["bias_potential"], rel=1e-10, abs=1e-14)
+    assert gs["reweight"] == pytest.approx(os_["reweight"], rel=1e-10)
+    assert gs["out_of_bounds"] == os_["out_of_bounds"]
+
+
+def test_bias_grid_restart_and_flags(gpu, oracle):
+    import torch
+    cfg = dict(cv_min=[0.0, 0.0], cv_max=[1.0, 2.0], num_points=[20, 30], sigma=[0.25, 0.1])
+    g = gpu.BiasGrid(**cfg, stride=1, well_tempered=True)
+    o = oracle.Grid(**cfg, stride=1, well_tempered=True)
+    dev = lambda v: torch.tensor(v, dtype=torch.float64, device="cuda")
+    for t, s in enumerate(([0.1, 1.0], [0.8, 1.0])):
+        g.step(t, dev(s)); o.update(t, s)
+    r = gpu.BiasGrid(**cfg, stride=1, well_tempered=True)                            # restart from the arrays
+    for name in ("grid", "reweighted", "weight", "sigma_grid", "hist", "hist_gauss"):
+        r.put(name, g.get(name))
+    r.set_num_gaussians(g.scalars()["num_gaussians"])
+    b1 = r.step(2, dev([0.4, 1.4])).cpu().numpy()
+    b2 = g.step(2, dev([0.4, 1.4])).cpu().numpy()
+    np.testing.assert_array_equal(b1, b2)
+    np.testing.assert_array_equal(r.get("grid"), g.get("grid"))
+    np.testing.assert_allclose(g.get("grid"), (o.update(2, [0.4, 1.4]), o.get("grid"))[1], rtol=1e-10)
+    g.set_flags(False, True, 1)                                                     # add_hills = False: no deposit
+    before = g.get("grid")
+    g.step(3, dev([0.5, 1.0]))
+    np.testing.assert_array_equal(g.get("grid"), before)
+    assert g.get("hist_delta").sum() == 1
+    g.reset_histogram()
+    assert g.get("hist").sum() == 0 and g.get("hist_delta").sum() == 0
+
+
+# ------------------------------------------------------------------------------------------------ umbrella / WTE
+def test_umbrella_kinds(gpu, oracle):
+    import torch
+    for kind, kw in (("harmonic", dict(cv0=0.025, kappa=1.6e7)), ("harmonic", dict(cv0=0.025, kappa=1.6e7, width_flat=0.02)),
+                     ("linear", dict(cv0=0.1, scale=3.0)), ("wall", dict(kappa=1.5, scale=0.1)),
+                     ("gaussian", dict(cv0=0.1, kappa=0.5, scale=2.0)), ("no_umbrella", {})):
+        for val in (0.03, 0.0249, 0.4, -0.2):
+            cv = torch.tensor([val], dtype=torch.float64, device="cuda")
+            bin_ = torch.tensor([0.37], dtype=torch.float64, device="cuda")
+            en = torch.zeros(1, dtype=torch.float64, device="cuda")
+            b = gpu.umbrella_apply(kind, cv, bin_, energy_out=en, **kw).cpu().item()
+            assert b == pytest.approx(oracle.umbrella_bias(kind, val, 0.37, **kw), rel=1e-12, abs=1e-300)
+            assert en.cpu().item() == pytest.approx(oracle.umbrella_potential(kind, val, **kw), rel=1e-12, abs=1e-300)
+
+
+@pytest.mark.parametrize("N", [1, 1000, 250007])
+def test_wte_reduce_and_scale(gpu, oracle, N):
+    import torch
+    rng = np.random.default_rng(N)
+    nf = rng.normal(size=(N, 4)).astype(np.float32)
+    tq = rng.normal(size=(N, 4)).astype(np.float32)
+    pitch = (N + 15) // 16 * 16
+    vir = rng.normal(size=(6 * pitch,)).astype(np.float32)
+    d_nf, d_tq, d_vir = (torch.from_numpy(a).cuda() for a in (nf, tq, vir))
+    pe = gpu.wte_reduce(d_nf, 1.25).cpu().item()
+    assert pe == pytest.approx(oracle.wte_pe(nf, 1.25), rel=1e-12)
+    bias = torch.tensor([0.5], dtype=torch.float64, device="cuda")
+    gpu.wte_scale(d_nf, d_tq, d_vir, pitch, bias)
+    f, t, v, _ = oracle.wte_scale(nf, tq, vir, pitch, 0.5, np.zeros(6))
+    np.testing.assert_allclose(d_nf.cpu().numpy(), f, rtol=1e-6)
+    np.testing.assert_allclose(d_tq.cpu().numpy(), t, rtol=1e-6)
+    np.testing.assert_allclose(d_vir.cpu().numpy(), v, rtol=1e-6)
