@@ -291,7 +291,7 @@ extern "C" int metad_grid_step(metad_grid* g, unsigned timestep, const double* d
                                metad_stream_t stream) {
     METAD_REQUIRE(g && d_cv_values && d_bias_out, "metad_grid_step: null argument");
     const int deposit = (g->add_bias && (timestep % g->stride == 0)) ? 1 : 0;
-    grid_step_kernel<<<1, kGridThreads, 0, stream>>>(g->P, g->A, d_cv_values, d_bias_out, deposit);
+    grid_step_kernel<<<1, deposit ? kGridThreads : 32, 0, stream>>>(g->P, g->A, d_cv_values, d_bias_out, deposit);
     METAD_LAUNCH_CHECK();
     return METAD_OK;
 }

@@ -30,7 +30,7 @@ struct metad_mesh {
     float* d_mode = nullptr;
     // particle order
     unsigned cap = 0;
-    unsigned *d_keys = nullptr, *d_ranks = nullptr, *d_perm = nullptr;
+    unsigned *d_keys = nullptr, *d_ranks = nullptr, *d_perm = nullptr, *d_skey = nullptr, *d_slot = nullptr;
     float4* d_sorted = nullptr;
     unsigned *d_count = nullptr, *d_start = nullptr, *d_block_sums = nullptr;
     // mesh
@@ -116,12 +116,9 @@ template <int L> int run_z(metad_mesh* p, unsigned N_global, double* d_cv, cudaS
     cp.ticket = p->d_ticket;
     cp.n_blocks_plane0 = (ny / 2 + 1 + kLines / 2 - 1) / (kLines / 2);
     cp.d_cv = d_cv;
-    int rc = set_smem(fft_z_plane0_kernel<L>, smem); if (rc) return rc;
-    rc = set_smem(fft_z_fused_kernel<L>, smem); if (rc) return rc;
-    fft_z_plane0_kernel<L><<<cp.n_blocks_plane0, kLines * L / kE, smem, st>>>(buf, p->d_twz, cp);
-    METAD_LAUNCH_CHECK();
-    dim3 grid(nxh / kLines, ny);
-    fft_z_fused_kernel<L><<<grid, kLines * L / kE, smem, st>>>(buf, p->d_twz, cp);
+    int rc = set_smem(fft_z_fused_kernel<L>, smem); if (rc) return rc;
+    const unsigned nblocks = cp.n_blocks_plane0 + (nxh / kLines) * ny;
+    fft_z_fused_kernel<L><<<nblocks, kLines * L / kE, smem, st>>>(buf, p->d_twz, cp);
     METAD_LAUNCH_CHECK();
     return METAD_OK;
 }
@@ -163,12 +160,14 @@ int fft_pipeline(metad_mesh* p, unsigned N_global, double* d_cv, cudaStream_t st
 
 int ensure_capacity(metad_mesh* p, unsigned N) {
     if (N <= p->cap) return METAD_OK;
-    cudaFree(p->d_keys); cudaFree(p->d_ranks); cudaFree(p->d_perm); cudaFree(p->d_sorted);
-    p->d_keys = p->d_ranks = p->d_perm = nullptr; p->d_sorted = nullptr; p->cap = 0;
+    cudaFree(p->d_keys); cudaFree(p->d_ranks); cudaFree(p->d_perm); cudaFree(p->d_sorted); cudaFree(p->d_skey); cudaFree(p->d_slot);
+    p->d_keys = p->d_ranks = p->d_perm = p->d_skey = p->d_slot = nullptr; p->d_sorted = nullptr; p->cap = 0;
     const unsigned cap = N + N / 16 + 1024;
     METAD_CUDA(cudaMalloc(&p->d_keys, sizeof(unsigned) * cap));
     METAD_CUDA(cudaMalloc(&p->d_ranks, sizeof(unsigned) * cap));
     METAD_CUDA(cudaMalloc(&p->d_perm, sizeof(unsigned) * cap));
+    METAD_CUDA(cudaMalloc(&p->d_skey, sizeof(unsigned) * cap));
+    METAD_CUDA(cudaMalloc(&p->d_slot, sizeof(unsigned) * cap));
     METAD_CUDA(cudaMalloc(&p->d_sorted, sizeof(float4) * cap));
     p->cap = cap;
     return METAD_OK;
@@ -207,17 +206,14 @@ extern "C" int metad_mesh_create(metad_mesh** out, unsigned nx, unsigned ny, uns
     auto* p = new metad_mesh();
     Geom& g = p->g;
     memset(&g, 0, sizeof g);
-    g.nx = nx; g.ny = ny; g.nz = nz;
-    g.lgx = ilog2(nx); g.lgy = ilog2(ny); g.lgz = ilog2(nz);
     const size_t M = (size_t)nx * ny * nz;
     // 16^3 tiles once there are enough of them to fill the GPU twice, 8^3 otherwise
-    g.lgT = (M / 4096 >= (size_t)2 * device_sm_count()) ? 4 : 3;
-    g.ntx = nx >> g.lgT; g.nty = ny >> g.lgT; g.ntz = nz >> g.lgT;
+    geom_set_dims(g, nx, ny, nz, (M / 4096 >= (size_t)2 * device_sm_count()) ? 4 : 3);
     p->ntypes = ntypes;
     std::vector<float> m(ntypes);
     for (int i = 0; i < ntypes; ++i) m[i] = (float)mode[i];
     const unsigned P = padded_edge(g);
-    const unsigned nb_scan = (unsigned)(M / kScanBlockItems);
+    const unsigned nb_scan = (unsigned)(M / (4 * kScanThreads));
     const unsigned nby = (ny / 2 + 1 + kLines / 2 - 1) / (kLines / 2);
     p->n_partials = nby + (nx / 2 / kLines) * ny;
     int rc = METAD_OK;
@@ -247,7 +243,7 @@ extern "C" int metad_mesh_create(metad_mesh** out, unsigned nx, unsigned ny, uns
 
 extern "C" int metad_mesh_destroy(metad_mesh* p) {
     if (!p) return METAD_OK;
-    cudaFree(p->d_mode); cudaFree(p->d_keys); cudaFree(p->d_ranks); cudaFree(p->d_perm); cudaFree(p->d_sorted);
+    cudaFree(p->d_mode); cudaFree(p->d_keys); cudaFree(p->d_ranks); cudaFree(p->d_perm); cudaFree(p->d_sorted); cudaFree(p->d_skey); cudaFree(p->d_slot);
     cudaFree(p->d_count); cudaFree(p->d_start); cudaFree(p->d_block_sums); cudaFree(p->d_scratch); cudaFree(p->d_buf);
     cudaFree(p->d_rho_keep); cudaFree(p->d_twx); cudaFree(p->d_twy); cudaFree(p->d_twz); cudaFree(p->d_sums);
     cudaFree(p->d_partials); cudaFree(p->d_ticket);
@@ -278,26 +274,38 @@ extern "C" int metad_mesh_cv(metad_mesh* p, const float* d_postype, unsigned N, 
         METAD_LAUNCH_CHECK();
     }
     rc = mark(p, 1, stream); if (rc) return rc;
-    const unsigned nb_scan = (unsigned)(M / kScanBlockItems);
-    scan_reduce_kernel<<<nb_scan, kScanThreads, 0, stream>>>((const uint4*)p->d_count, p->d_block_sums);
-    METAD_LAUNCH_CHECK();
-    scan_offsets_kernel<<<1, kScanThreads, 0, stream>>>(p->d_block_sums, nb_scan);
-    METAD_LAUNCH_CHECK();
-    scan_apply_kernel<<<nb_scan, kScanThreads, 0, stream>>>((uint4*)p->d_count, p->d_block_sums, p->d_start, (unsigned)M);
-    METAD_LAUNCH_CHECK();
+    if (M % (16 * kScanThreads) == 0) {
+        const unsigned nb_scan = (unsigned)(M / (16 * kScanThreads));
+        scan_reduce_kernel<4><<<nb_scan, kScanThreads, 0, stream>>>((const uint4*)p->d_count, p->d_block_sums);
+        METAD_LAUNCH_CHECK();
+        scan_offsets_kernel<<<1, kScanThreads, 0, stream>>>(p->d_block_sums, nb_scan);
+        METAD_LAUNCH_CHECK();
+        scan_apply_kernel<4><<<nb_scan, kScanThreads, 0, stream>>>((uint4*)p->d_count, p->d_block_sums, p->d_start, (unsigned)M);
+        METAD_LAUNCH_CHECK();
+    } else {
+        const unsigned nb_scan = (unsigned)(M / (4 * kScanThreads));
+        scan_reduce_kernel<1><<<nb_scan, kScanThreads, 0, stream>>>((const uint4*)p->d_count, p->d_block_sums);
+        METAD_LAUNCH_CHECK();
+        scan_offsets_kernel<<<1, kScanThreads, 0, stream>>>(p->d_block_sums, nb_scan);
+        METAD_LAUNCH_CHECK();
+        scan_apply_kernel<1><<<nb_scan, kScanThreads, 0, stream>>>((uint4*)p->d_count, p->d_block_sums, p->d_start, (unsigned)M);
+        METAD_LAUNCH_CHECK();
+    }
     rc = mark(p, 2, stream); if (rc) return rc;
     if (N > 0) {
         long nb = ((long)N + kBinThreads * 4L - 1) / (kBinThreads * 4L);
         if (nb > sms * 16L) nb = sms * 16L;
-        mesh_reorder_kernel<<<(int)nb, kBinThreads, 0, stream>>>((const float4*)d_postype, N, p->d_mode, p->d_keys, p->d_ranks,
-                                                                p->d_start, p->d_sorted, p->d_perm);
+        mesh_place_kernel<<<(int)nb, kBinThreads, 0, stream>>>(N, p->d_keys, p->d_ranks, p->d_start, p->d_slot);
+        METAD_LAUNCH_CHECK();
+        mesh_reorder_kernel<<<(int)nb, kBinThreads, 0, stream>>>((const float4*)d_postype, N, p->d_mode, p->d_keys, p->d_start,
+                                                                p->d_slot, p->d_sorted, p->d_perm, p->d_skey);
         METAD_LAUNCH_CHECK();
     }
     rc = mark(p, 3, stream); if (rc) return rc;
     if (g.lgT == 4)
-        mesh_spread_kernel<4><<<num_tiles(g), kTileThreads, 0, stream>>>(p->d_sorted, p->d_perm, p->d_start, g, p->d_scratch);
+        mesh_spread_kernel<4><<<num_tiles(g), 256, 0, stream>>>(p->d_sorted, p->d_skey, p->d_start, g, p->d_scratch);
     else
-        mesh_spread_kernel<3><<<num_tiles(g), kTileThreads, 0, stream>>>(p->d_sorted, p->d_perm, p->d_start, g, p->d_scratch);
+        mesh_spread_kernel<3><<<num_tiles(g), 64, 0, stream>>>(p->d_sorted, p->d_skey, p->d_start, g, p->d_scratch);
     METAD_LAUNCH_CHECK();
     if (p->keep_rho && !p->d_rho_keep) METAD_CUDA(cudaMalloc(&p->d_rho_keep, sizeof(float) * M));
     rc = mark(p, 4, stream); if (rc) return rc;
@@ -334,11 +342,11 @@ extern "C" int metad_mesh_forces(metad_mesh* p, const float* d_postype, float* d
     fp.two_over_n = 2.0 / (double)N_global;
     { int rc = mark(p, 11, stream); if (rc) return rc; }
     if (g.lgT == 4)
-        mesh_gather_kernel<4><<<num_tiles(g), kTileThreads, 0, stream>>>(p->d_sorted, p->d_perm, p->d_start, g, p->d_buf, fp, d_bias,
-                                                                       (float4*)d_force);
+        mesh_gather_kernel<4><<<num_tiles(g), kGatherThreads, 0, stream>>>(p->d_sorted, p->d_perm, p->d_skey, p->d_start, g, p->d_buf, fp,
+                                                                         d_bias, (float4*)d_force);
     else
-        mesh_gather_kernel<3><<<num_tiles(g), kTileThreads, 0, stream>>>(p->d_sorted, p->d_perm, p->d_start, g, p->d_buf, fp, d_bias,
-                                                                       (float4*)d_force);
+        mesh_gather_kernel<3><<<num_tiles(g), kGatherThreads, 0, stream>>>(p->d_sorted, p->d_perm, p->d_skey, p->d_start, g, p->d_buf, fp,
+                                                                         d_bias, (float4*)d_force);
     METAD_LAUNCH_CHECK();
     { int rc = mark(p, 12, stream); if (rc) return rc; }
     return METAD_OK;

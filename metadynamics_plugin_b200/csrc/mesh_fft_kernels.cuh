@@ -164,17 +164,15 @@ fft_y_kernel(float2* __restrict__ buf, const float2* __restrict__ g_tw, unsigned
 }
 
 // energy partial -> per-block slot; the last block of the LAST kernel (main z pass) sums all slots in order
-__device__ __forceinline__ void energy_block_finish(double e, const ConvParams& cp, unsigned slot, unsigned total_slots,
-                                                    bool finalize) {
+__device__ __forceinline__ void energy_block_finish(double e, const ConvParams& cp) {
     __shared__ double red[32];
     __shared__ bool is_last;
+    const unsigned slot = blockIdx.x, total_slots = gridDim.x;
     const double r = block_sum(e, red);
     if (threadIdx.x == 0) cp.partials[slot] = r;
-    if (!finalize) return;
     if (threadIdx.x == 0) {
         __threadfence();
-        const unsigned nb = gridDim.x * gridDim.y;
-        is_last = (atomicAdd(cp.ticket, 1u) == nb - 1);
+        is_last = (atomicAdd(cp.ticket, 1u) == gridDim.x - 1);
     }
     __syncthreads();
     if (!is_last) return;
@@ -190,17 +188,16 @@ __device__ __forceinline__ void energy_block_finish(double e, const ConvParams& 
 
 // ---------------------------------------------------------------------------------------------------
 // z pass fused with the convolution and the CV energy: forward z FFT -> G^H -> inverse z FFT.
-// tile = 16 consecutive kx  x  all z, fixed y.  grid = (nxh/16, ny).  Column kx = 0 is left to plane0.
+// tile = 16 consecutive kx  x  all z, fixed y.  Column kx = 0 is left to the plane0 blocks of the same launch.
 // ---------------------------------------------------------------------------------------------------
 template <int L>
-__global__ void __launch_bounds__(kLines * L / kE)
-fft_z_fused_kernel(float2* __restrict__ buf, const float2* __restrict__ g_tw, ConvParams cp) {
-    extern __shared__ float2 smem[];
+__device__ __forceinline__ void z_general_body(float2* __restrict__ buf, const float2* __restrict__ g_tw, const ConvParams& cp,
+                                               unsigned bx, unsigned by, float2* smem) {
     float2* tile = smem;
     float2* s_tw = smem + LayoutCol::size(L);
     const int nthr = kLines * L / kE;
     const unsigned nxh = cp.nx / 2, ny = cp.ny;
-    const unsigned kx0 = blockIdx.x * kLines, ky = blockIdx.y;
+    const unsigned kx0 = bx * kLines, ky = by;
     const size_t base = (size_t)ky * nxh + kx0;
     const size_t zstride = (size_t)ny * nxh;
     load_twiddles<L>(s_tw, g_tw);
@@ -229,8 +226,7 @@ fft_z_fused_kernel(float2* __restrict__ buf, const float2* __restrict__ g_tw, Co
         if (kx0 + ww == 0) continue;
         buf[base + (size_t)l * zstride + ww] = tile[idx];
     }
-    const unsigned slot = cp.n_blocks_plane0 + blockIdx.y * gridDim.x + blockIdx.x;
-    energy_block_finish(e, cp, slot, cp.n_blocks_plane0 + gridDim.x * gridDim.y, true);
+    energy_block_finish(e, cp);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -240,9 +236,8 @@ fft_z_fused_kernel(float2* __restrict__ buf, const float2* __restrict__ g_tw, Co
 // A' + i B' and transformed back.  grid = ceil((ny/2+1)/8)
 // ---------------------------------------------------------------------------------------------------
 template <int L>
-__global__ void __launch_bounds__(kLines * L / kE)
-fft_z_plane0_kernel(float2* __restrict__ buf, const float2* __restrict__ g_tw, ConvParams cp) {
-    extern __shared__ float2 smem[];
+__device__ __forceinline__ void z_plane0_body(float2* __restrict__ buf, const float2* __restrict__ g_tw, const ConvParams& cp,
+                                              unsigned blk, float2* smem) {
     float2* tile = smem;
     float2* s_tw = smem + LayoutCol::size(L);
     constexpr int nthr = kLines * L / kE;
@@ -252,7 +247,7 @@ fft_z_plane0_kernel(float2* __restrict__ buf, const float2* __restrict__ g_tw, C
     load_twiddles<L>(s_tw, g_tw);
     for (int idx = threadIdx.x; idx < kLines * L; idx += nthr) {
         const int w = idx & (kLines - 1), l = idx / kLines;
-        const unsigned kyp = blockIdx.x * (kLines / 2) + (w >> 1);
+        const unsigned kyp = blk * (kLines / 2) + (w >> 1);
         float2 v = make_float2(0.f, 0.f);
         if (kyp <= ny / 2) {
             const unsigned ky = (w & 1) ? (ny - kyp) % ny : kyp;
@@ -273,7 +268,7 @@ fft_z_plane0_kernel(float2* __restrict__ buf, const float2* __restrict__ g_tw, C
         const int idx = threadIdx.x + it * nthr;
         const int ww = idx & (kLines - 1);
         const unsigned kz = idx / kLines;
-        const unsigned kyp = blockIdx.x * (kLines / 2) + (ww >> 1);
+        const unsigned kyp = blk * (kLines / 2) + (ww >> 1);
         const unsigned pky = (ny - kyp) % ny;
         const unsigned ky = (ww & 1) ? pky : kyp;
         const bool valid = kyp <= ny / 2;
@@ -287,14 +282,27 @@ fft_z_plane0_kernel(float2* __restrict__ buf, const float2* __restrict__ g_tw, C
     line_fft<L, +1, L, LayoutCol>(tile, w, t, s_tw);
     for (int idx = threadIdx.x; idx < kLines * L; idx += nthr) {
         const int ww = idx & (kLines - 1), l = idx / kLines;
-        const unsigned kyp = blockIdx.x * (kLines / 2) + (ww >> 1);
+        const unsigned kyp = blk * (kLines / 2) + (ww >> 1);
         const unsigned pky = (ny - kyp) % ny;
         if (kyp > ny / 2) continue;
         if ((ww & 1) && pky == kyp) continue;
         const unsigned ky = (ww & 1) ? pky : kyp;
         buf[(size_t)ky * nxh + (size_t)l * zstride] = tile[idx];
     }
-    energy_block_finish(e, cp, blockIdx.x, 0, false);
+    energy_block_finish(e, cp);
+}
+
+// one launch: blocks [0, n_blocks_plane0) untangle the kx = 0 slot, the rest are (kx tile, ky) blocks of the general case
+template <int L>
+__global__ void __launch_bounds__(kLines * L / kE)
+fft_z_fused_kernel(float2* __restrict__ buf, const float2* __restrict__ g_tw, ConvParams cp) {
+    extern __shared__ float2 smem[];
+    if (blockIdx.x < cp.n_blocks_plane0) {
+        z_plane0_body<L>(buf, g_tw, cp, blockIdx.x, smem);
+    } else {
+        const unsigned b = blockIdx.x - cp.n_blocks_plane0, ntx = cp.nx / 2 / kLines;
+        z_general_body<L>(buf, g_tw, cp, b % ntx, b / ntx, smem);
+    }
 }
 
 }  // namespace fft

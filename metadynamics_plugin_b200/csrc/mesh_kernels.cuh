@@ -6,10 +6,13 @@
 // gpu_compute_forces_kernel (OrderParameterMeshGPU.cu:90-364, 566-769): non-deterministic atomicInc binning with
 // an overflow-retry loop, a 27x scratch mesh, texture gathers.
 //
-// Here: particles are counting-sorted by a TILE-MAJOR cell key (tile of T^3 cells, T = 8 or 16), so that
-//   * spreading is a thread-per-cell, atomics-free accumulation into a shared-memory tile with a one-cell halo
-//     (27 conflict-free "shift" rounds), flushed as one contiguous padded tile; a merge pass sums the <= 8
-//     overlapping padded tiles per cell in a fixed order (deterministic, no float atomics anywhere);
+// Here: particles are counting-sorted (stable: ties keep the input order) by a TILE-MAJOR cell key (tile of T^3
+// cells, T = 8 or 16), so that
+//   * spreading is atomics-free: one thread per cell COLUMN of a tile walks the column in z with the 3x9 partial
+//     sums of three planes in registers; columns exchange their x,y taps through nine write-once "replica" planes
+//     in shared memory (no read-modify-write, one barrier per plane); every tile is flushed as one contiguous
+//     padded tile and a merge pass sums the <= 8 overlapping padded tiles per cell in a fixed order.  Summation
+//     orders are fixed, so results are bitwise reproducible;
 //   * force interpolation is thread-per-particle over a contiguous particle range per tile, reading a
 //     shared-memory tile of Re(IFFT(G)) with halo.
 // Cell indices are computed with non-contracted IEEE fp32 operations and are bit-exact against the reference's
@@ -28,15 +31,31 @@ struct Geom {
     unsigned nx, ny, nz;        // mesh points (powers of two)
     unsigned lgx, lgy, lgz;     // log2 of the above
     unsigned lgT;               // log2 of the tile edge T (3 or 4)
-    unsigned ntx, nty, ntz;     // tiles per dimension
+    unsigned ntx, nty, ntz;     // tiles per dimension (powers of two)
+    unsigned lgtx, lgty, lgtz;  // log2 of the above
     float lo[3], L[3];          // single-precision box (HOOMD SINGLE_PRECISION BoxDim)
     double dlo[3], dscale[3];   // fp64: lo and n/L for the in-cell offset
 };
 
+MHD void geom_set_dims(Geom& g, unsigned nx, unsigned ny, unsigned nz, unsigned lgT) {
+    auto lg = [](unsigned n) { unsigned l = 0; while ((1u << l) < n) ++l; return l; };
+    g.nx = nx; g.ny = ny; g.nz = nz;
+    g.lgx = lg(nx); g.lgy = lg(ny); g.lgz = lg(nz);
+    g.lgT = lgT;
+    g.lgtx = g.lgx - lgT; g.lgty = g.lgy - lgT; g.lgtz = g.lgz - lgT;
+    g.ntx = 1u << g.lgtx; g.nty = 1u << g.lgty; g.ntz = 1u << g.lgtz;
+}
+
 MHD unsigned tile_edge(const Geom& g) { return 1u << g.lgT; }
 MHD unsigned cells_per_tile(const Geom& g) { return 1u << (3 * g.lgT); }
 MHD unsigned padded_edge(const Geom& g) { return (1u << g.lgT) + 2; }
-MHD unsigned num_tiles(const Geom& g) { return g.ntx * g.nty * g.ntz; }
+MHD unsigned num_tiles(const Geom& g) { return 1u << (g.lgtx + g.lgty + g.lgtz); }
+MHD unsigned tile_index(unsigned tx, unsigned ty, unsigned tz, const Geom& g) { return (((tz << g.lgty) + ty) << g.lgtx) + tx; }
+MHD void tile_coords(unsigned tile, const Geom& g, unsigned& tx, unsigned& ty, unsigned& tz) {
+    tx = tile & (g.ntx - 1);
+    ty = (tile >> g.lgtx) & (g.nty - 1);
+    tz = tile >> (g.lgtx + g.lgty);
+}
 
 // non-contracted IEEE single-precision helpers (host: plain ops, the emulation is built without FMA contraction)
 MHD float f_sub(float a, float b) {
@@ -79,15 +98,15 @@ MHD int cell_coord(float x, float lo, float L, unsigned n) {
 // tile-major key: tile index * T^3 + local cell index (x fastest inside the tile)
 MHD unsigned key_of(unsigned ix, unsigned iy, unsigned iz, const Geom& g) {
     const unsigned T1 = (1u << g.lgT) - 1;
-    const unsigned tx = ix >> g.lgT, ty = iy >> g.lgT, tz = iz >> g.lgT;
-    const unsigned tile = (tz * g.nty + ty) * g.ntx + tx;
+    const unsigned tile = tile_index(ix >> g.lgT, iy >> g.lgT, iz >> g.lgT, g);
     const unsigned local = ((((iz & T1) << g.lgT) + (iy & T1)) << g.lgT) + (ix & T1);
     return (tile << (3 * g.lgT)) + local;
 }
 MHD void cell_of_key(unsigned key, const Geom& g, unsigned& ix, unsigned& iy, unsigned& iz) {
     const unsigned T1 = (1u << g.lgT) - 1;
-    const unsigned local = key & ((1u << (3 * g.lgT)) - 1), tile = key >> (3 * g.lgT);
-    const unsigned tx = tile % g.ntx, ty = (tile / g.ntx) % g.nty, tz = tile / (g.ntx * g.nty);
+    const unsigned local = key & ((1u << (3 * g.lgT)) - 1);
+    unsigned tx, ty, tz;
+    tile_coords(key >> (3 * g.lgT), g, tx, ty, tz);
     ix = (tx << g.lgT) + (local & T1);
     iy = (ty << g.lgT) + ((local >> g.lgT) & T1);
     iz = (tz << g.lgT) + (local >> (2 * g.lgT));
@@ -123,27 +142,46 @@ MHD void tsc_deriv(float s, float (&w)[3]) {
 // per-thread bodies shared by the kernels and the CPU emulation (tests/cpu_emul/mesh_emul.cu)
 // ---------------------------------------------------------------------------------------------------
 
-// accumulate one particle into the 27 per-cell partial sums; acc index = (i*3 + j)*3 + k with i the x tap
-MHD void spread_accumulate(float4 p /* x,y,z,a */, unsigned ix, unsigned iy, unsigned iz, const Geom& g, float (&acc)[27]) {
+// index inside the padded tile (edge P = T+2) of tap (i,j,k) in {0,1,2}^3 of local cell (lx,ly,lz)
+MHD unsigned padded_index(unsigned lx, unsigned ly, unsigned lz, int i, int j, int k, unsigned P) {
+    return ((lz + k) * P + (ly + j)) * P + (lx + i);
+}
+
+// Separable TSC weights of one particle relative to its cell: w[0..2] = a*Wx(tap -1,0,+1), w[3..5] = Wy, w[6..8] = Wz
+MHD void spread_weights(float4 p /* x,y,z,a */, unsigned ix, unsigned iy, unsigned iz, const Geom& g, float (&w)[9]) {
     float wx[3], wy[3], wz[3];
     tsc(cell_shift(p.x, ix, 0, g), wx);
     tsc(cell_shift(p.y, iy, 1, g), wy);
     tsc(cell_shift(p.z, iz, 2, g), wz);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const float ax = p.w * wx[i];
+    for (int i = 0; i < 3; ++i) { w[i] = p.w * wx[i]; w[3 + i] = wy[i]; w[6 + i] = wz[i]; }
+}
+// Rolling accumulators of a cell column: acc[k*9 + i*3 + j], k = z tap (plane lz-1+k), i = x tap, j = y tap
+MHD void spread_accumulate9(const float (&w)[9], float (&acc)[27]) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-            const float axy = ax * wy[j];
+            const float axy = w[i] * w[3 + j];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) acc[(i * 3 + j) * 3 + k] += axy * wz[k];
+            for (int k = 0; k < 3; ++k) acc[k * 9 + i * 3 + j] = fmaf(axy, w[6 + k], acc[k * 9 + i * 3 + j]);
         }
-    }
 }
-
-// index inside the padded tile (edge P = T+2) of tap (i,j,k) in {0,1,2}^3 of local cell (lx,ly,lz)
-MHD unsigned padded_index(unsigned lx, unsigned ly, unsigned lz, int i, int j, int k, unsigned P) {
-    return ((lz + k) * P + (ly + j)) * P + (lx + i);
+// Exchange in x,y without atomics or read-modify-write: column (lx,ly) stores its nine (i,j) partial sums of a finished
+// plane into nine "replica" planes at padded position (lx+i, ly+j); replica r = i*3+j is written at most once per
+// position.  The value of padded position (px,py) is the sum over the replicas whose source column exists.
+MHD unsigned replica_index(int r, unsigned px, unsigned py, unsigned P) { return (r * P + py) * P + px; }
+MHD float reduce_replicas(const float* rep, unsigned px, unsigned py, unsigned T) {
+    const unsigned P = T + 2;
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            // source column (px - i, py - j) must lie inside the tile
+            if (px >= (unsigned)i && px - i < T && py >= (unsigned)j && py - j < T) sum += rep[replica_index(i * 3 + j, px, py, P)];
+        }
+    return sum;
 }
 
 // merge: value of mesh cell (x,y,z) = sum over the <= 8 padded tiles that cover it, in fixed (z,y,x) order
@@ -155,19 +193,19 @@ MHD float merge_cell(const float* __restrict__ scratch, unsigned x, unsigned y, 
     unsigned ctx[2], cpx[2], cty[2], cpy[2], ctz[2], cpz[2];
     int nxc = 1, nyc = 1, nzc = 1;
     ctx[0] = tx; cpx[0] = lx + 1;
-    if (lx == 0) { ctx[1] = (tx + g.ntx - 1) % g.ntx; cpx[1] = T + 1; nxc = 2; }
-    else if (lx == T - 1) { ctx[1] = (tx + 1) % g.ntx; cpx[1] = 0; nxc = 2; }
+    if (lx == 0) { ctx[1] = (tx + g.ntx - 1) & (g.ntx - 1); cpx[1] = T + 1; nxc = 2; }
+    else if (lx == T - 1) { ctx[1] = (tx + 1) & (g.ntx - 1); cpx[1] = 0; nxc = 2; }
     cty[0] = ty; cpy[0] = ly + 1;
-    if (ly == 0) { cty[1] = (ty + g.nty - 1) % g.nty; cpy[1] = T + 1; nyc = 2; }
-    else if (ly == T - 1) { cty[1] = (ty + 1) % g.nty; cpy[1] = 0; nyc = 2; }
+    if (ly == 0) { cty[1] = (ty + g.nty - 1) & (g.nty - 1); cpy[1] = T + 1; nyc = 2; }
+    else if (ly == T - 1) { cty[1] = (ty + 1) & (g.nty - 1); cpy[1] = 0; nyc = 2; }
     ctz[0] = tz; cpz[0] = lz + 1;
-    if (lz == 0) { ctz[1] = (tz + g.ntz - 1) % g.ntz; cpz[1] = T + 1; nzc = 2; }
-    else if (lz == T - 1) { ctz[1] = (tz + 1) % g.ntz; cpz[1] = 0; nzc = 2; }
+    if (lz == 0) { ctz[1] = (tz + g.ntz - 1) & (g.ntz - 1); cpz[1] = T + 1; nzc = 2; }
+    else if (lz == T - 1) { ctz[1] = (tz + 1) & (g.ntz - 1); cpz[1] = 0; nzc = 2; }
     float sum = 0.f;
     for (int c = 0; c < nzc; ++c)
         for (int b = 0; b < nyc; ++b)
             for (int a = 0; a < nxc; ++a) {
-                const unsigned tile = (ctz[c] * g.nty + cty[b]) * g.ntx + ctx[a];
+                const unsigned tile = tile_index(ctx[a], cty[b], ctz[c], g);
                 sum += scratch[(size_t)tile * P3 + (cpz[c] * P + cpy[b]) * P + cpx[a]];
             }
     return sum;
@@ -180,6 +218,7 @@ MHD void gather_sums(const float* tile, unsigned lx, unsigned ly, unsigned lz, u
                      const float (&wy)[3], const float (&wz)[3], const float (&dx)[3], const float (&dy)[3],
                      const float (&dz)[3], float& Sx, float& Sy, float& Sz) {
     Sx = 0.f; Sy = 0.f; Sz = 0.f;
+    const float* base = tile + (lz * P + ly) * P + lx;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         float tw = 0.f, td = 0.f, tz = 0.f;   // sum_j {Wy, W'y, Wy} * sum_k {Wz, Wz, W'z} inv
@@ -188,7 +227,7 @@ MHD void gather_sums(const float* tile, unsigned lx, unsigned ly, unsigned lz, u
             float u = 0.f, v = 0.f;
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const float val = tile[padded_index(lx, ly, lz, i, j, k, P)];
+                const float val = base[(k * P + j) * P + i];
                 u = fmaf(wz[k], val, u);
                 v = fmaf(dz[k], val, v);
             }
@@ -207,20 +246,19 @@ struct ForceParams {
     double two_over_n;              // 2 / N_global  (:858)
 };
 
-MHD float4 gather_force(float4 p /* x,y,z,a */, unsigned ix, unsigned iy, unsigned iz, const float* tile, const Geom& g,
-                        const ForceParams& fp, double bias) {
-    const unsigned T1 = (1u << g.lgT) - 1, P = (1u << g.lgT) + 2;
+// (lx,ly,lz): local cell inside the tile; (ix,iy,iz): global cell; scale = (2/N) * bias rounded to float
+MHD float4 gather_force(float4 p /* x,y,z,a */, unsigned ix, unsigned iy, unsigned iz, unsigned lx, unsigned ly, unsigned lz,
+                        const float* tile, const Geom& g, const ForceParams& fp, float scale) {
+    const unsigned P = (1u << g.lgT) + 2;
     const float sx = cell_shift(p.x, ix, 0, g), sy = cell_shift(p.y, iy, 1, g), sz = cell_shift(p.z, iz, 2, g);
     float wx[3], wy[3], wz[3], dx[3], dy[3], dz[3];
     tsc(sx, wx); tsc(sy, wy); tsc(sz, wz);
     tsc_deriv(sx, dx); tsc_deriv(sy, dy); tsc_deriv(sz, dz);
     float Sx, Sy, Sz;
-    gather_sums(tile, ix & T1, iy & T1, iz & T1, P, wx, wy, wz, dx, dy, dz, Sx, Sy, Sz);
-    const float fx = -p.w * (fp.nb1[0] * Sx + fp.nb2[0] * Sy + fp.nb3[0] * Sz);
-    const float fy = -p.w * (fp.nb1[1] * Sx + fp.nb2[1] * Sy + fp.nb3[1] * Sz);
-    const float fz = -p.w * (fp.nb1[2] * Sx + fp.nb2[2] * Sy + fp.nb3[2] * Sz);
-    const double sc = fp.two_over_n * bias;
-    return make_float4((float)((double)fx * sc), (float)((double)fy * sc), (float)((double)fz * sc), 0.f);
+    gather_sums(tile, lx, ly, lz, P, wx, wy, wz, dx, dy, dz, Sx, Sy, Sz);
+    const float m = -p.w * scale;
+    return make_float4(m * (fp.nb1[0] * Sx + fp.nb2[0] * Sy + fp.nb3[0] * Sz), m * (fp.nb1[1] * Sx + fp.nb2[1] * Sy + fp.nb3[1] * Sz),
+                       m * (fp.nb1[2] * Sx + fp.nb2[2] * Sy + fp.nb3[2] * Sz), 0.f);
 }
 
 #ifdef __CUDACC__
@@ -228,9 +266,8 @@ MHD float4 gather_force(float4 p /* x,y,z,a */, unsigned ix, unsigned iy, unsign
 // kernels
 // ---------------------------------------------------------------------------------------------------
 constexpr int kBinThreads = 256;
-constexpr int kTileThreads = 512;
 
-// bin: key + rank (slot inside the cell) per particle, per-cell counts, sum a^2 and sum a
+// bin: key + rank (arrival order inside the cell) per particle, per-cell counts, sum a^2 and sum a
 __global__ void __launch_bounds__(kBinThreads)
 mesh_bin_kernel(const float4* __restrict__ postype, unsigned N, Geom g, const float* __restrict__ mode,
                 unsigned* __restrict__ keys, unsigned* __restrict__ ranks, unsigned* __restrict__ count,
@@ -255,10 +292,10 @@ mesh_bin_kernel(const float4* __restrict__ postype, unsigned N, Geom g, const fl
     if (threadIdx.x == 0) { atomicAdd(sums, tsq); atomicAdd(sums + 1, ts1); }
 }
 
-// ---- exclusive scan of count[0..n) -> start[0..n]; n is a multiple of 4096.  Three launches: per-block sums,
-// scan of the block sums (single block), apply.  The apply pass also clears count[] for the next step.
+// ---- exclusive scan of count[0..n) -> start[0..n].  Three launches: per-block sums, scan of the block sums (single
+// block), apply.  Each thread owns V consecutive uint4 (n must be a multiple of 4096*V).  The apply pass also
+// clears count[] for the next step.
 constexpr int kScanThreads = 1024;
-constexpr int kScanBlockItems = 4 * kScanThreads;
 
 // block-wide exclusive scan of one value per thread (blockDim.x == 1024); total returned to every thread
 __device__ __forceinline__ unsigned block_excl_scan(unsigned v, unsigned* sm /* >= 33 */, unsigned& total) {
@@ -289,12 +326,19 @@ __device__ __forceinline__ unsigned block_excl_scan(unsigned v, unsigned* sm /* 
     return excl;
 }
 
+template <int V>
 __global__ void __launch_bounds__(kScanThreads)
 scan_reduce_kernel(const uint4* __restrict__ count4, unsigned* __restrict__ block_sums) {
     __shared__ unsigned sm[33];
-    const uint4 v = count4[(size_t)blockIdx.x * kScanThreads + threadIdx.x];
+    const uint4* src = count4 + ((size_t)blockIdx.x * kScanThreads + threadIdx.x) * V;
+    uint4 v[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) v[k] = src[k];
+    unsigned s = 0;
+#pragma unroll
+    for (int k = 0; k < V; ++k) s += v[k].x + v[k].y + v[k].z + v[k].w;
     unsigned total;
-    block_excl_scan(v.x + v.y + v.z + v.w, sm, total);
+    block_excl_scan(s, sm, total);
     if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
 }
 
@@ -313,86 +357,121 @@ scan_offsets_kernel(unsigned* __restrict__ block_sums, unsigned nb) {
     if (threadIdx.x == 0) block_sums[nb] = carry;
 }
 
+template <int V>
 __global__ void __launch_bounds__(kScanThreads)
 scan_apply_kernel(uint4* __restrict__ count4, const unsigned* __restrict__ block_sums, unsigned* __restrict__ start,
                   unsigned n) {
     __shared__ unsigned sm[33];
-    const size_t i4 = (size_t)blockIdx.x * kScanThreads + threadIdx.x;
-    const uint4 v = count4[i4];
-    count4[i4] = make_uint4(0u, 0u, 0u, 0u);
+    const size_t i4 = ((size_t)blockIdx.x * kScanThreads + threadIdx.x) * V;
+    uint4 v[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) v[k] = count4[i4 + k];
+#pragma unroll
+    for (int k = 0; k < V; ++k) count4[i4 + k] = make_uint4(0u, 0u, 0u, 0u);
+    unsigned s = 0;
+#pragma unroll
+    for (int k = 0; k < V; ++k) s += v[k].x + v[k].y + v[k].z + v[k].w;
     unsigned total;
-    const unsigned excl = block_excl_scan(v.x + v.y + v.z + v.w, sm, total) + block_sums[blockIdx.x];
-    uint4 o;
-    o.x = excl; o.y = o.x + v.x; o.z = o.y + v.y; o.w = o.z + v.z;
-    reinterpret_cast<uint4*>(start)[i4] = o;
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) start[n] = o.w + v.w;
+    unsigned run = block_excl_scan(s, sm, total) + block_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        uint4 o;
+        o.x = run; o.y = o.x + v[k].x; o.z = o.y + v[k].y; o.w = o.z + v[k].z;
+        run = o.w + v[k].w;
+        reinterpret_cast<uint4*>(start)[i4 + k] = o;
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) start[n] = run;
 }
 
-// reorder: sorted[start[key] + rank] = {x, y, z, a(type)}, perm[...] = original index
+// place: slot[start[key] + arrival rank] = particle index.  The arrival rank comes from atomics and is not
+// reproducible; the reorder pass below turns it into the stable rank (ascending particle index inside a cell).
+__global__ void __launch_bounds__(kBinThreads)
+mesh_place_kernel(unsigned N, const unsigned* __restrict__ keys, const unsigned* __restrict__ ranks,
+                  const unsigned* __restrict__ start, unsigned* __restrict__ slot) {
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) slot[__ldg(start + keys[i]) + ranks[i]] = i;
+}
+
+// reorder (one thread per slot): stable position inside the cell = number of cell mates with a smaller particle
+// index; sorted[...] = {x, y, z, a(type)}, perm[...] = particle index, skey[...] = key.
 __global__ void __launch_bounds__(kBinThreads)
 mesh_reorder_kernel(const float4* __restrict__ postype, unsigned N, const float* __restrict__ mode,
-                    const unsigned* __restrict__ keys, const unsigned* __restrict__ ranks,
-                    const unsigned* __restrict__ start, float4* __restrict__ sorted, unsigned* __restrict__ perm) {
+                    const unsigned* __restrict__ keys, const unsigned* __restrict__ start, const unsigned* __restrict__ slot,
+                    float4* __restrict__ sorted, unsigned* __restrict__ perm, unsigned* __restrict__ skey) {
     const unsigned stride = gridDim.x * blockDim.x;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
-        float4 p = ld_stream(postype + i);
+    for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += stride) {
+        const unsigned i = slot[j];
+        const unsigned key = __ldg(keys + i);
+        const unsigned s = __ldg(start + key), e = __ldg(start + key + 1);
+        unsigned dst = s;
+        for (unsigned m = s; m < e; ++m) dst += (__ldg(slot + m) < i) ? 1u : 0u;
+        float4 p = __ldg(postype + i);
         p.w = __ldg(mode + __float_as_int(p.w));
-        const unsigned dst = __ldg(start + keys[i]) + ranks[i];
         sorted[dst] = p;
         perm[dst] = i;
+        skey[dst] = key;
     }
 }
 
-// spread: one CTA per tile, one thread per cell (batches of kTileThreads cells), atomics-free.
-// Particles of a cell are visited in ascending original index so the fp32 sum order is reproducible.
+// spread: one CTA per tile, one thread per cell COLUMN (lx,ly); the thread walks its column in z keeping the
+// 3x9 partial sums of the planes lz-1, lz, lz+1 in registers.  Per plane:
+//   phase 1  (thread per particle, balanced): separable weights of the plane's particles -> shared memory
+//   phase 2  (thread per cell): accumulate the cell's particles in slot order (= ascending particle index)
+//   flush    the finished plane lz-1: nine replica stores per column, one barrier, replica reduction -> padded tile
+// No atomics, no shared-memory read-modify-write.
+constexpr int kSpreadCap = 512;     // particles per phase-1 chunk
 template <int LGT>
-__global__ void __launch_bounds__(kTileThreads)
-mesh_spread_kernel(const float4* __restrict__ sorted, const unsigned* __restrict__ perm,
-                   const unsigned* __restrict__ start, Geom g, float* __restrict__ scratch) {
-    constexpr unsigned T = 1u << LGT, P = T + 2, P3 = P * P * P, NC = T * T * T;
-    __shared__ float tile[P3];
-    for (unsigned i = threadIdx.x; i < P3; i += kTileThreads) tile[i] = 0.f;
-    __syncthreads();
+__global__ void __launch_bounds__(1 << (2 * LGT), LGT == 4 ? 3 : 8)
+mesh_spread_kernel(const float4* __restrict__ sorted, const unsigned* __restrict__ skey, const unsigned* __restrict__ start,
+                   Geom g, float* __restrict__ scratch) {
+    constexpr unsigned T = 1u << LGT, P = T + 2, PP = P * P, NT = T * T;
+    __shared__ float wbuf[9 * kSpreadCap];
+    __shared__ float rep[2][9 * PP];
+    const unsigned tid = threadIdx.x, lx = tid & (T - 1), ly = tid >> LGT;
     const unsigned tile_id = blockIdx.x;
-    for (unsigned lc0 = 0; lc0 < NC; lc0 += kTileThreads) {
-        const unsigned lc = lc0 + threadIdx.x;          // NC is a multiple of kTileThreads
-        const unsigned key = (tile_id << (3 * LGT)) + lc;
-        unsigned ix, iy, iz;
-        cell_of_key(key, g, ix, iy, iz);
-        const unsigned lx = lc & (T - 1), ly = (lc >> LGT) & (T - 1), lz = lc >> (2 * LGT);
-        const unsigned s = __ldg(start + key), e = __ldg(start + key + 1);
-        float acc[27];
+    unsigned tx, ty, tz;
+    tile_coords(tile_id, g, tx, ty, tz);
+    float* out = scratch + (size_t)tile_id * PP * P;
+    float acc[27];
 #pragma unroll
-        for (int r = 0; r < 27; ++r) acc[r] = 0.f;
-        if (e - s == 1) {
-            spread_accumulate(sorted[s], ix, iy, iz, g, acc);
-        } else if (e > s) {
-            // selection by ascending original index (cells hold few particles)
-            long long last = -1;
-            for (unsigned it = s; it < e; ++it) {
-                unsigned best = 0xffffffffu, bj = s;
-                for (unsigned j = s; j < e; ++j) {
-                    const unsigned pj = __ldg(perm + j);
-                    if ((long long)pj > last && pj < best) { best = pj; bj = j; }
+    for (int r = 0; r < 27; ++r) acc[r] = 0.f;
+    int buf = 0;
+    for (unsigned lz = 0; lz < T + 2; ++lz) {
+        if (lz < T) {
+            const unsigned key0 = (tile_id << (3 * LGT)) + lz * NT;
+            const unsigned s_plane = __ldg(start + key0), e_plane = __ldg(start + key0 + NT);
+            const unsigned s = __ldg(start + key0 + tid), e = __ldg(start + key0 + tid + 1);
+            for (unsigned c0 = s_plane; c0 < e_plane; c0 += kSpreadCap) {
+                const unsigned c1 = min(c0 + (unsigned)kSpreadCap, e_plane);
+                for (unsigned j = c0 + tid; j < c1; j += NT) {
+                    const unsigned local = __ldg(skey + j) & (NT - 1);     // cell inside the plane
+                    float w[9];
+                    spread_weights(sorted[j], (tx << LGT) + (local & (T - 1)), (ty << LGT) + (local >> LGT), (tz << LGT) + lz, g, w);
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) wbuf[c * kSpreadCap + (j - c0)] = w[c];
                 }
-                last = (long long)best;
-                spread_accumulate(sorted[bj], ix, iy, iz, g, acc);
+                __syncthreads();
+                const unsigned a = max(s, c0), b = min(e, c1);
+                for (unsigned j = a; j < b; ++j) {
+                    float w[9];
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) w[c] = wbuf[c * kSpreadCap + (j - c0)];
+                    spread_accumulate9(w, acc);
+                }
+                __syncthreads();
             }
         }
-        const bool any = e > s;
+        // flush the finished plane: padded z index lz (= tile plane lz - 1)
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
-            for (int j = 0; j < 3; ++j)
+            for (int j = 0; j < 3; ++j) rep[buf][replica_index(i * 3 + j, lx + i, ly + j, P)] = acc[i * 3 + j];
+        __syncthreads();
+        for (unsigned idx = tid; idx < PP; idx += NT) out[(size_t)lz * PP + idx] = reduce_replicas(rep[buf], idx % P, idx / P, T);
+        buf ^= 1;
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    // in one round every thread targets a distinct address (its cell shifted by the same offset)
-                    if (any) tile[padded_index(lx, ly, lz, i, j, k, P)] += acc[(i * 3 + j) * 3 + k];
-                    __syncthreads();
-                }
+        for (int r = 0; r < 9; ++r) { acc[r] = acc[9 + r]; acc[9 + r] = acc[18 + r]; acc[18 + r] = 0.f; }
     }
-    float* out = scratch + (size_t)tile_id * P3;
-    for (unsigned i = threadIdx.x; i < P3; i += kTileThreads) out[i] = tile[i];
 }
 
 // merge: mesh[x + nx (y + ny z)] = sum of covering padded tiles - mean (DC removal, see mesh.cu)
@@ -401,41 +480,55 @@ mesh_merge_kernel(const float* __restrict__ scratch, Geom g, const double* __res
                   float* __restrict__ rho_keep) {
     const size_t M = (size_t)g.nx * g.ny * g.nz;
     const float mean = (float)(sums[1] / (double)M);
+    const unsigned T = 1u << g.lgT, P = T + 2;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < M; c += stride) {
         const unsigned x = (unsigned)(c & (g.nx - 1)), y = (unsigned)((c >> g.lgx) & (g.ny - 1)), z = (unsigned)(c >> (g.lgx + g.lgy));
-        const float v = merge_cell(scratch, x, y, z, g);
+        const unsigned lx = x & (T - 1), ly = y & (T - 1), lz = z & (T - 1);
+        float v;
+        if (lx != 0 && lx != T - 1 && ly != 0 && ly != T - 1 && lz != 0 && lz != T - 1) {
+            // interior cell of its tile: a single contribution
+            const unsigned tile = tile_index(x >> g.lgT, y >> g.lgT, z >> g.lgT, g);
+            v = __ldg(scratch + (size_t)tile * (P * P * P) + ((lz + 1) * P + (ly + 1)) * P + (lx + 1));
+        } else {
+            v = merge_cell(scratch, x, y, z, g);
+        }
         if (rho_keep) rho_keep[c] = v;
         rho[c] = v - mean;
     }
 }
 
 // gather: one CTA per tile; shared tile of Re(IFFT(G)) with halo; one thread per particle of the tile
+constexpr int kGatherThreads = 256;
 template <int LGT>
-__global__ void __launch_bounds__(kTileThreads)
-mesh_gather_kernel(const float4* __restrict__ sorted, const unsigned* __restrict__ perm,
+__global__ void __launch_bounds__(kGatherThreads)
+mesh_gather_kernel(const float4* __restrict__ sorted, const unsigned* __restrict__ perm, const unsigned* __restrict__ skey,
                    const unsigned* __restrict__ start, Geom g, const float* __restrict__ inv, ForceParams fp,
                    const double* __restrict__ d_bias, float4* __restrict__ force) {
     constexpr unsigned T = 1u << LGT, P = T + 2, P3 = P * P * P;
     __shared__ float tile[P3];
     const unsigned tile_id = blockIdx.x;
-    const unsigned tx = tile_id % g.ntx, ty = (tile_id / g.ntx) % g.nty, tz = tile_id / (g.ntx * g.nty);
-    for (unsigned i = threadIdx.x; i < P3; i += kTileThreads) {
-        const unsigned px = i % P, py = (i / P) % P, pz = i / (P * P);
-        const unsigned x = ((tx << LGT) + px + g.nx - 1) & (g.nx - 1);
+    const unsigned s = __ldg(start + (tile_id << (3 * LGT))), e = __ldg(start + ((tile_id + 1) << (3 * LGT)));
+    if (e == s) return;                                   // empty tile: nothing to interpolate
+    unsigned tx, ty, tz;
+    tile_coords(tile_id, g, tx, ty, tz);
+    // padded tile, one row (P floats along x) per warp iteration
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (unsigned row = warp; row < P * P; row += kGatherThreads / 32) {
+        const unsigned py = row % P, pz = row / P;
         const unsigned y = ((ty << LGT) + py + g.ny - 1) & (g.ny - 1);
         const unsigned z = ((tz << LGT) + pz + g.nz - 1) & (g.nz - 1);
-        tile[i] = __ldg(inv + (size_t)x + (size_t)g.nx * (y + (size_t)g.ny * z));
+        if (lane < P) {
+            const unsigned x = ((tx << LGT) + lane + g.nx - 1) & (g.nx - 1);
+            tile[row * P + lane] = __ldg(inv + (size_t)x + (size_t)g.nx * (y + (size_t)g.ny * z));
+        }
     }
     __syncthreads();
-    const double bias = *d_bias;
-    const unsigned s = __ldg(start + (tile_id << (3 * LGT))), e = __ldg(start + ((tile_id + 1) << (3 * LGT)));
-    for (unsigned j = s + threadIdx.x; j < e; j += kTileThreads) {
-        const float4 p = sorted[j];
-        const unsigned ix = cell_coord(p.x, g.lo[0], g.L[0], g.nx);
-        const unsigned iy = cell_coord(p.y, g.lo[1], g.L[1], g.ny);
-        const unsigned iz = cell_coord(p.z, g.lo[2], g.L[2], g.nz);
-        force[__ldg(perm + j)] = gather_force(p, ix, iy, iz, tile, g, fp, bias);
+    const float scale = (float)(fp.two_over_n * *d_bias);
+    for (unsigned j = s + threadIdx.x; j < e; j += kGatherThreads) {
+        const unsigned local = __ldg(skey + j) & ((1u << (3 * LGT)) - 1);
+        const unsigned lx = local & (T - 1), ly = (local >> LGT) & (T - 1), lz = local >> (2 * LGT);
+        force[__ldg(perm + j)] = gather_force(sorted[j], (tx << LGT) + lx, (ty << LGT) + ly, (tz << LGT) + lz, lx, ly, lz, tile, g, fp, scale);
     }
 }
 #endif  // __CUDACC__
