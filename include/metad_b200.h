@@ -152,6 +152,11 @@ int metad_wte_reduce(const float* d_net_force, unsigned N, double external_energ
 int metad_wte_scale(float* d_net_force, float* d_net_torque, float* d_net_virial, unsigned pitch, unsigned N,
                     const double* d_bias, metad_stream_t stream);
 
+/* Stand-in for HOOMD's net-force summation (Integrator::computeNetForceGPU, not part of the plugin): the shim
+ * integrator of the host layer uses it to build the net force the WellTemperedEnsemble CV reads.
+ * net[i] = (init ? 0 : net[i]) + f[i] for all four components. */
+int metad_accumulate_force(float* d_net_force, const float* d_force, unsigned N, int init, metad_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,6 +74,7 @@ SIGNATURES = {
     "metad_umbrella_apply": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, _vp, _vp, _vp, _vp, _vp]),
     "metad_wte_reduce": (C.c_int, [_vp, C.c_uint, C.c_double, _vp, _vp]),
     "metad_wte_scale": (C.c_int, [_vp, _vp, _vp, C.c_uint, C.c_uint, _vp, _vp]),
+    "metad_accumulate_force": (C.c_int, [_vp, _vp, C.c_uint, C.c_int, _vp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -82,6 +82,16 @@ __global__ void umbrella_kernel(int kind, double cv0, double kappa, double width
     if (d_energy_out) *d_energy_out = energy;
 }
 
+__global__ void __launch_bounds__(kWteThreads)
+accumulate_force_kernel(float4* __restrict__ net, const float4* __restrict__ f, unsigned N, int init) {
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+        float4 a = f[i];
+        if (!init) { const float4 b = net[i]; a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+        net[i] = a;
+    }
+}
+
 struct WteScratch {
     double* partials = nullptr;
     unsigned* ticket = nullptr;
@@ -128,6 +138,17 @@ extern "C" int metad_wte_scale(float* d_net_force, float* d_net_torque, float* d
     if (b > cap) b = cap;
     wte_scale_kernel<<<(int)b, kWteThreads, 0, stream>>>((float4*)d_net_force, (float4*)d_net_torque, d_net_virial, pitch, N,
                                                         d_bias);
+    METAD_LAUNCH_CHECK();
+    return METAD_OK;
+}
+
+extern "C" int metad_accumulate_force(float* d_net_force, const float* d_force, unsigned N, int init, metad_stream_t stream) {
+    if (N == 0) return METAD_OK;
+    METAD_REQUIRE(d_net_force && d_force, "metad_accumulate_force: null array");
+    long b = ((long)N + kWteThreads * 4L - 1) / (kWteThreads * 4L);
+    const long cap = device_sm_count() * 8L;
+    if (b > cap) b = cap;
+    accumulate_force_kernel<<<(int)b, kWteThreads, 0, stream>>>((float4*)d_net_force, (const float4*)d_force, N, init);
     METAD_LAUNCH_CHECK();
     return METAD_OK;
 }

@@ -1,0 +1,176 @@
+"""GPU tests of the reference-facing surface: the pybind `_metadynamics` classes and the cv.py / integrate.py API,
+driven the way the reference's own scripts (test/test_mesh.py, test/test_2d.py) drive the plugin, checked against
+the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def api():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from metadynamics_plugin_b200 import cv, integrate, hoomd_shim
+    hoomd_shim.context.initialize()
+    return cv, integrate, hoomd_shim
+
+
+def test_reference_test_mesh_scenario(api, oracle):
+    """reference test/test_mesh.py: N=1000, L=10, cv.mesh(nx=32, mode={'A':1}) under a harmonic umbrella with
+    md.integrate.mode_standard; checks cv_mesh, umbrella_energy_mesh and the forces of one step."""
+    cv, integrate, hoomd = api
+    from metadynamics_plugin_b200 import workloads
+    w = workloads.c1()
+    pos = w["postype"][:, :3]
+    hoomd.init.from_arrays(pos, np.zeros(1000, np.int32), ["A"], 10.0)
+    integrate.mode_standard(dt=0.001)
+    mesh = cv.mesh(nx=32, mode={'A': 1})
+    cv0 = 0.025
+    mesh.set_params(umbrella='harmonic', cv0=cv0, kappa=10000 / cv0 ** 2)
+    hoomd.run(1)
+    o = oracle.Mesh(32, 32, 32, [1.0], 10.0, 1000, "f64", literal_copysignf=False)
+    cvo = o.current_value(w["postype"])
+    val = mesh.cpp_force.getLogValue("cv_mesh", 1)
+    assert val == pytest.approx(cvo, rel=2e-6)                     # float return value of the reference API
+    bias = oracle.umbrella_bias("harmonic", float(np.float64(val)), 0.0, cv0=cv0, kappa=10000 / cv0 ** 2)
+    f = mesh.get_forces()
+    # the device evaluates the umbrella from its fp64 CV; compare force direction/magnitude with the oracle at that bias
+    fo = o.forces(w["postype"], bias)
+    assert np.abs(f - fo).max() < 2e-4 * np.abs(fo).max()          # kappa (cv - cv0): cancellation amplifies the CV's 1e-6
+    e = mesh.cpp_force.getLogValue("umbrella_energy_mesh", 1)
+    assert e == pytest.approx(oracle.umbrella_potential("harmonic", float(val), cv0=cv0, kappa=10000 / cv0 ** 2), rel=1e-3)
+    assert mesh.cpp_force.getBiasFactor() == 0.0                   # computeForces resets the bias (CollectiveVariable.cc:65)
+    assert "cv_mesh" in mesh.cpp_force.getProvidedLogQuantities()
+    with pytest.raises(RuntimeError):
+        mesh.cpp_force.getLogValue("no_such_quantity", 1)
+
+
+def test_reference_test_2d_scenario(api, oracle, tmp_path):
+    """reference test/test_2d.py: one particle, density + aspect-ratio CVs on a 20x30 grid, well-tempered, stride 1,
+    grid dumped every step, box rescaled between two run(1) calls; a restart from bias.dat_1 must reproduce
+    bias.dat_2 ("identical up to rounding errors")."""
+    cv, integrate, hoomd = api
+    from metadynamics_plugin_b200 import _metadynamics
+    L0 = 10 ** (1. / 3.)
+    s = 0.125 ** (1. / 3.)
+
+    def setup():
+        hoomd.context.initialize()
+        hoomd.init.from_arrays(np.zeros((1, 3), np.float32), [0], ["A"], L0)
+        meta = integrate.mode_metadynamics(dt=0.005, mode='well_tempered', stride=1, deltaT=1, W=1)
+        density = cv.density(sigma=0.25)
+        density.set_grid(cv_min=0, cv_max=1, num_points=20)
+        aspect = cv.aspect_ratio(sigma=0.1, dir1=0, dir2=1)
+        aspect.set_grid(cv_min=0, cv_max=2, num_points=30)
+        return meta
+
+    def rescale():
+        pd = hoomd.context.current.system_definition.getParticleData()
+        pd.setGlobalBox(_metadynamics.BoxDim(L0 * s, L0 * s, L0 * s))
+
+    meta = setup()
+    meta.dump_grid(str(tmp_path / 'bias.dat'), period=1)
+    meta.set_params(multiple_walkers=True)
+    hoomd.run(1)
+    rescale()
+    hoomd.run(1)
+    grid_final = np.array(meta.cpp_integrator.getGridArray("grid"))
+    assert meta.cpp_integrator.getNumGaussians() == 4
+
+    meta2 = setup()
+    meta2.restart_from_grid(str(tmp_path / 'bias.dat_1'))
+    meta2.dump_grid(str(tmp_path / 'bias_restart.dat'), period=1)
+    meta2.set_params(multiple_walkers=True)
+    rescale()
+    hoomd.run(1)
+
+    a = np.loadtxt(tmp_path / 'bias.dat_2', skiprows=4)
+    b = np.loadtxt(tmp_path / 'bias_restart.dat_0', skiprows=4)
+    assert a.shape == (600, 8)
+    np.testing.assert_allclose(b, a, rtol=2e-9, atol=1e-300)
+    hdr = open(tmp_path / 'bias.dat_2').read().splitlines()[:4]
+    assert hdr[0] == "#n_cv: 2" and hdr[1] == "#dim:  20 30" and hdr[2] == "#num_gaussians: 4"
+    assert hdr[3].split("\t") == ["cv_density", "cv_aspect_ratio", "grid_value", "det_sigma", "num_gaussians", "hist", "hist_reweight", "weight"]
+
+    # the same CV sequence through the oracle: rho = 1/V = 0.1 then 0.8, aspect = 1
+    o = oracle.Grid([0.0, 0.0], [1.0, 2.0], [20, 30], [0.25, 0.1], W=1.0, T_shift=1.0, T=1.0, stride=1, well_tempered=True)
+    seq =[(0, 1.0 / L0 ** 3), (1, 1.0 / L0 ** 3), (1, 1.0 / (L0 * s) ** 3), (2, 1.0 / (L0 * s) ** 3)]
+    for t, rho in seq:
+        o.update(t, [float(np.float32(rho)), 1.0])
+    np.testing.assert_allclose(grid_final, o.get("grid"), rtol=1e-5, atol=1e-12)      # CV values are float in the API
+    assert abs(a[:, 2] - o.get("grid")).max() < 1e-5 * o.get("grid").max()
+
+
+def test_lamellar_metadynamics_steps(api, oracle):
+    """cv.lamellar + integrate.mode_metadynamics over a few steps: CV log value, bias factor hand-off, forces, grid."""
+    cv, integrate, hoomd = api
+    from metadynamics_plugin_b200 import workloads
+    w = workloads.c2(N=32768)
+    pt = w["postype"]
+    types = pt[:, 3].view(np.int32)
+    hoomd.init.from_arrays(pt[:, :3], types, ["A", "B"], w["L"])
+    meta = integrate.mode_metadynamics(dt=0.005, mode='well_tempered', stride=2, deltaT=7.0, W=1.0)
+    lam = cv.lamellar(sigma=0.05, mode=dict(A=1.0, B=-1.0), lattice_vectors=w["lattice_vectors"])
+    lam.set_grid(cv_min=-2.0, cv_max=2.0, num_points=400)
+    hoomd.run(3)
+    cvo, _ = oracle.lamellar_cv(pt, 32768, [1.0, -1.0], w["lattice_vectors"], w["L"])
+    assert lam.cpp_force.getLogValue("cv_lamellar", 3) == pytest.approx(cvo, rel=2e-6)
+    o = oracle.Grid([-2.0], [2.0], [400], [0.05], W=1.0, T_shift=7.0, T=1.0, stride=2, well_tempered=True)
+    for t in (0, 1, 2, 3):                                # prepRun(0) + update(0..2) -> timesteps 0,1,2,3
+        bo = o.update(t, [cvo])
+    assert meta.cpp_integrator.getNumGaussians() == 2
+    np.testing.assert_allclose(np.array(meta.cpp_integrator.getGridArray("grid")), o.get("grid"), rtol=1e-5, atol=1e-12)
+    f = lam.get_forces()
+    fo = oracle.lamellar_forces(pt, 32768, [1.0, -1.0], w["lattice_vectors"], w["L"], bo[0])
+    assert np.abs(f - fo).max() < 1e-3 * np.abs(fo).max() + 1e-12      # dV/ds near a hill centre is ill-conditioned in s
+    assert meta.cpp_integrator.getLogValue("bias", 3) == pytest.approx(o.scalars()["bias_potential"], rel=1e-5)
+    with pytest.raises(RuntimeError):                     # the set of CVs may not change between runs
+        cv.lamellar(sigma=0.05, mode=dict(A=1.0, B=-1.0), lattice_vectors=[(0, 0, 1)], name="x").set_grid(-1, 1, 10)
+        hoomd.run(1)
+
+
+def test_api_error_behaviour(api):
+    cv, integrate, hoomd = api
+    hoomd.init.from_arrays(np.zeros((8, 3), np.float32), np.zeros(8, np.int32), ["A", "B"], 5.0)
+    with pytest.raises(RuntimeError):
+        cv.lamellar(mode=dict(A=1.0), lattice_vectors=[(0, 0, 1)])           # missing mode amplitude for type B
+    with pytest.raises(RuntimeError):
+        cv.lamellar(mode=dict(A=1.0, B=1.0), lattice_vectors=[])
+    with pytest.raises(RuntimeError):
+        cv.mesh(mode=[1.0, 1.0], nx=32)                                       # modes must be a dict
+    with pytest.raises(RuntimeError, match="power of two"):
+        cv.mesh(mode=dict(A=1.0, B=1.0), nx=48)
+    with pytest.raises(RuntimeError):
+        cv.aspect_ratio(dir1=1, dir2=1)
+    with pytest.raises(RuntimeError):
+        integrate.mode_metadynamics(dt=0.005, stride=1, mode="flux_tempered")
+    m = cv.mesh(mode=dict(A=1.0, B=-1.0), nx=32)
+    with pytest.raises(RuntimeError):
+        m.set_params(umbrella="parabolic")
+    meta = integrate.mode_metadynamics(dt=0.005, stride=1)
+    m.set_grid(0.5, 0.1, 10)                                                   # max < min
+    with pytest.raises(RuntimeError):
+        hoomd.run(1)
+
+
+def test_potential_energy_cv(api, oracle):
+    """cv.potential_energy (well-tempered ensemble): CV = sum of net_force.w; forces = net force scaled by 1+bias."""
+    cv, integrate, hoomd = api
+    N = 5000
+    rng = np.random.default_rng(3)
+    sd = hoomd.init.from_arrays(rng.random((N, 3)) - 0.5, np.zeros(N, np.int32), ["A"], 4.0)
+    pe = cv.potential_energy(sigma=2.0)
+    nf = rng.normal(size=(N, 4)).astype(np.float32)
+    pd = sd.getParticleData()
+    pd.setNetForce(nf)
+    pd.setExternalEnergy(0.5)
+    assert pe.cpp_force.requiresNetForce() and not pe.cpp_force.canComputeDerivatives()
+    val = pe.cpp_force.getCurrentValue(0)
+    assert val == pytest.approx(oracle.wte_pe(nf, 0.5), rel=1e-6)
+    pe.cpp_force.setBiasFactor(0.25)
+    pe.cpp_force.compute(1)
+    np.testing.assert_allclose(pd.getNetForce()[:, :3], nf[:, :3] * 1.25, rtol=1e-6)
+    np.testing.assert_array_equal(pd.getNetForce()[:, 3], nf[:, 3])
