@@ -90,8 +90,36 @@ int metad_mesh_cv(metad_mesh* p, const float* d_postype, unsigned N, unsigned N_
 int metad_mesh_forces(metad_mesh* p, const float* d_postype, float* d_force, unsigned N, unsigned N_global,
                       const metad_box* box, const double* d_bias, metad_stream_t stream);
 
-/* Multi-GPU (z-slab decomposition; reference: HOOMD domain decomposition + CommunicatorGrid + dfft,
- * OrderParameterMesh.cc:263-315, 659-746).  See metad_mesh_slab_* below. */
+/* Multi-GPU: z-slab decomposition (reference: HOOMD domain decomposition + CommunicatorGrid ghost exchange + dfft,
+ * OrderParameterMesh.cc:231-315, 659-746).  Rank r of n_ranks owns the planes [r nz/P, (r+1) nz/P) and the particles
+ * inside them.  The library provides the five compute stages of a step; the caller issues the collectives between
+ * them (ops.MeshSlab does it with NCCL through torch.distributed):
+ *
+ *   metad_mesh_slab_spread      local density; d_sums[3] = local {sum a^2, sum a, #particles outside the slab};
+ *                               d_ghost_send[2][ny][nx] = halo planes z0-1 (for rank r-1) and z0+nz/P (for rank r+1)
+ *      -> all-reduce(d_sums), neighbour exchange of the two planes
+ *   metad_mesh_slab_fft_x       adds d_ghost_recv[2][ny][nx] ([0] from rank r-1, [1] from rank r+1), removes the global
+ *                               mean, x FFT; d_send = M/P/2 complex, already packed [dest rank][plane][y][kx in pencil]
+ *      -> all-to-all (equal splits): d_pencil = [nz][ny][nx/2/P] complex, planes in rank order = global z order
+ *   metad_mesh_slab_fft_yz      y FFT, fused z FFT + convolution + inverse z FFT, inverse y FFT on the pencil, in
+ *                               place; *d_cv_partial = this rank's share of the CV
+ *      -> all-reduce(d_cv_partial), all-to-all back (the pencil buffer is contiguous per destination rank)
+ *   metad_mesh_slab_fft_x_inv   unpacks d_recv while transforming; copies the first and the last local plane of
+ *                               Re IFFT(G) to d_planes_out[0], [1] (to send to rank r-1 / r+1)
+ *      -> neighbour exchange: d_ghost_inv[0] = last plane of rank r-1, d_ghost_inv[1] = first plane of rank r+1
+ *   metad_mesh_slab_forces      interpolateForces for the local particles
+ * Requirements: n_ranks a power of two, nz/n_ranks >= 8, nx/2/n_ranks >= 16.  `global_box` is the global box. */
+int metad_mesh_slab_create(metad_mesh** out, unsigned nx, unsigned ny, unsigned nz, unsigned n_ranks, unsigned rank, int ntypes,
+                           const double* mode);
+int metad_mesh_slab_spread(metad_mesh* p, const float* d_postype, unsigned N_local, const metad_box* global_box, double* d_sums,
+                           float* d_ghost_send, metad_stream_t stream);
+int metad_mesh_slab_fft_x(metad_mesh* p, const float* d_ghost_recv, const double* d_sums_global, float* d_send,
+                          metad_stream_t stream);
+int metad_mesh_slab_fft_yz(metad_mesh* p, float* d_pencil, const double* d_sums_global, unsigned N_global, double* d_cv_partial,
+                           metad_stream_t stream);
+int metad_mesh_slab_fft_x_inv(metad_mesh* p, const float* d_recv, float* d_planes_out /* [2][ny][nx] */, metad_stream_t stream);
+int metad_mesh_slab_forces(metad_mesh* p, const float* d_ghost_inv, const float* d_postype, float* d_force, unsigned N_local,
+                           unsigned N_global, const metad_box* global_box, const double* d_bias, metad_stream_t stream);
 
 /* Introspection for parity tests (synchronous, copies to HOST buffers):
  *   which = 0: cell coordinates (ix,iy,iz) per particle, int[3*N], input order

@@ -1,15 +1,23 @@
 // mesh.cu -- OrderParameterMesh plan object and C ABI (see include/metad_b200.h).
 //
 // Step structure of metad_mesh_cv (reference: OrderParameterMesh::getCurrentValue, OrderParameterMesh.cc:925-968):
-//   bin -> scan -> reorder            cell order of this step (tile-major counting sort; exact, rebuilt per call)
+//   bin -> scan -> place -> reorder   cell order of this step (tile-major stable counting sort; exact, rebuilt per call)
 //   spread -> merge                   assignParticles (:517-640); also sum a^2 (m_mode_sq) and sum a
-//   x fwd, y fwd, plane0 + z fused, y inv, x inv   updateMeshes (:642-747) + computeCV (:866-923)
+//   x fwd, y fwd, z fused (+plane0), y inv, x inv   updateMeshes (:642-747) + computeCV (:866-923)
 // metad_mesh_forces: gather           interpolateForces (:749-864)
 //
 // DC removal: the merge pass subtracts the mean density (sum a / M) before the transforms.  The k = 0 mode is
 // excluded from the CV (:892) and a constant offset of IFFT(G) cannot produce a force (the TSC derivative
 // weights of the 27 taps sum to zero), so results are unchanged -- but without it the fp32 transforms carry a
 // DC term ~sqrt(N) times larger than every other mode and the force mesh loses several digits.
+//
+// z-slab sharding (metad_mesh_slab_*): rank r owns the planes [r nz/P, (r+1) nz/P) and the particles inside them
+// (reference: HOOMD domain decomposition + CommunicatorGrid ghost exchange + dfft, OrderParameterMesh.cc:263-315,
+// 659-746).  Per step: local spread, halo-add of one plane per side, x FFT written directly in the layout of the
+// slab -> kx-pencil all-to-all, y and fused z passes on the pencil (the packed kx = 0 column lives entirely on rank
+// 0), all-to-all back, x inverse, halo-fill of one plane per side, local gather.  The collectives themselves
+// (2 all-to-alls, 2 neighbour exchanges, 2 tiny all-reduces) are issued by the caller (NCCL via torch.distributed in
+// ops.MeshSlab); this file provides the five compute stages between them.
 #include "mesh_kernels.cuh"
 #include "mesh_fft_kernels.cuh"
 
@@ -25,7 +33,10 @@ using namespace metad::fft;
 constexpr int kNumStages = 11;
 
 struct metad_mesh {
-    Geom g;
+    Geom g;                         // LOCAL geometry (slab: nz = planes of this rank)
+    unsigned n_ranks = 1, rank = 0; // z-slab sharding
+    unsigned nzg = 0;               // global planes
+    unsigned kxl = 0;               // kx pencil width (complex) = nx/2/n_ranks
     int ntypes = 0;
     float* d_mode = nullptr;
     // particle order
@@ -35,10 +46,10 @@ struct metad_mesh {
     unsigned *d_count = nullptr, *d_start = nullptr, *d_block_sums = nullptr;
     // mesh
     float* d_scratch = nullptr;     // padded tiles
-    float* d_buf = nullptr;         // M floats: rho -> packed half spectrum -> Re IFFT(G)
+    float* d_buf = nullptr;         // M_local floats: rho -> packed half spectrum -> Re IFFT(G)
     float* d_rho_keep = nullptr;    // optional copy of rho (introspection)
     float2 *d_twx = nullptr, *d_twy = nullptr, *d_twz = nullptr;
-    double* d_sums = nullptr;       // [0] sum a^2  [1] sum a
+    double* d_sums = nullptr;       // [0] sum a^2  [1] sum a  [2] particles outside the slab
     double* d_partials = nullptr;
     unsigned* d_ticket = nullptr;
     unsigned n_partials = 0;
@@ -74,50 +85,54 @@ template <class K> int set_smem(K kernel, size_t bytes) {
 }
 
 // ---- FFT launchers -----------------------------------------------------------------------------------
-template <int LC> int run_x(metad_mesh* p, bool inverse, cudaStream_t st) {
+// x pass over the local rows.  io: nullptr = in place; otherwise the packed all-to-all buffer (output of the
+// forward pass / input of the inverse pass), [part][row][kx in part] with parts of width kxl.
+template <int LC> int run_x(metad_mesh* p, bool inverse, float2* io, cudaStream_t st) {
     const size_t smem = sizeof(float2) * (LayoutRow::size(LC) + 2 * LC);
     const unsigned rows = p->g.ny * p->g.nz;
     float2* buf = reinterpret_cast<float2*>(p->d_buf);
+    const unsigned lg_part = io ? ilog2(p->kxl) : ilog2(LC);
     if (!inverse) {
         int rc = set_smem(fft_x_fwd_kernel<LC>, smem); if (rc) return rc;
-        fft_x_fwd_kernel<LC><<<rows / kLines, kLines * LC / kE, smem, st>>>(buf, p->d_twx);
+        fft_x_fwd_kernel<LC><<<rows / kLines, kLines * LC / kE, smem, st>>>(buf, p->d_twx, io ? io : buf, lg_part, rows);
     } else {
         int rc = set_smem(fft_x_inv_kernel<LC>, smem); if (rc) return rc;
-        fft_x_inv_kernel<LC><<<rows / kLines, kLines * LC / kE, smem, st>>>(buf, p->d_twx);
+        fft_x_inv_kernel<LC><<<rows / kLines, kLines * LC / kE, smem, st>>>(buf, p->d_twx, io ? io : buf, lg_part, rows);
     }
     METAD_LAUNCH_CHECK();
     return METAD_OK;
 }
-template <int L> int run_y(metad_mesh* p, bool inverse, cudaStream_t st) {
+// y pass on buf = [nz_rows][ny][row_len]
+template <int L> int run_y(metad_mesh* p, bool inverse, float2* buf, unsigned row_len, unsigned nz_rows, cudaStream_t st) {
     const size_t smem = sizeof(float2) * (LayoutCol::size(L) + L);
-    const unsigned nxh = p->g.nx / 2;
-    float2* buf = reinterpret_cast<float2*>(p->d_buf);
-    dim3 grid(nxh / kLines, p->g.nz);
+    dim3 grid(row_len / kLines, nz_rows);
     if (!inverse) {
         int rc = set_smem(fft_y_kernel<L, -1>, smem); if (rc) return rc;
-        fft_y_kernel<L, -1><<<grid, kLines * L / kE, smem, st>>>(buf, p->d_twy, nxh);
+        fft_y_kernel<L, -1><<<grid, kLines * L / kE, smem, st>>>(buf, p->d_twy, row_len);
     } else {
         int rc = set_smem(fft_y_kernel<L, +1>, smem); if (rc) return rc;
-        fft_y_kernel<L, +1><<<grid, kLines * L / kE, smem, st>>>(buf, p->d_twy, nxh);
+        fft_y_kernel<L, +1><<<grid, kLines * L / kE, smem, st>>>(buf, p->d_twy, row_len);
     }
     METAD_LAUNCH_CHECK();
     return METAD_OK;
 }
-template <int L> int run_z(metad_mesh* p, unsigned N_global, double* d_cv, cudaStream_t st) {
+// fused z pass on buf = [nzg][ny][row_len]; d_sums: (global) sum a^2; d_cv receives 0.5 * (local) energy sum
+template <int L> int run_z(metad_mesh* p, float2* buf, unsigned row_len, unsigned kx_off, const double* d_sums, unsigned N_global,
+                           double* d_cv, cudaStream_t st) {
     const size_t smem = sizeof(float2) * (LayoutCol::size(L) + L);
-    const unsigned nxh = p->g.nx / 2, ny = p->g.ny;
-    float2* buf = reinterpret_cast<float2*>(p->d_buf);
+    const unsigned ny = p->g.ny;
     ConvParams cp;
-    cp.nx = p->g.nx; cp.ny = ny; cp.nz = p->g.nz;
+    cp.nx = p->g.nx; cp.ny = ny; cp.nz = p->nzg;
+    cp.row_len = row_len; cp.kx_off = kx_off;
     cp.inv_n = (float)(1.0 / (double)N_global);
     cp.n_global = (double)N_global;
-    cp.d_mode_sq = p->d_sums;
+    cp.d_mode_sq = d_sums;
     cp.partials = p->d_partials;
     cp.ticket = p->d_ticket;
-    cp.n_blocks_plane0 = (ny / 2 + 1 + kLines / 2 - 1) / (kLines / 2);
+    cp.n_blocks_plane0 = kx_off == 0 ? (ny / 2 + 1 + kLines / 2 - 1) / (kLines / 2) : 0;
     cp.d_cv = d_cv;
     int rc = set_smem(fft_z_fused_kernel<L>, smem); if (rc) return rc;
-    const unsigned nblocks = cp.n_blocks_plane0 + (nxh / kLines) * ny;
+    const unsigned nblocks = cp.n_blocks_plane0 + (row_len / kLines) * ny;
     fft_z_fused_kernel<L><<<nblocks, kLines * L / kE, smem, st>>>(buf, p->d_twz, cp);
     METAD_LAUNCH_CHECK();
     return METAD_OK;
@@ -134,7 +149,7 @@ template <int L> int run_z(metad_mesh* p, unsigned N_global, double* d_cv, cudaS
         default: set_error("cv.mesh: unsupported mesh dimension"); rc = METAD_ERR_UNSUPPORTED; \
     }
 
-// event i marks the START of stage i (event kNumStages the end of the cv pipeline, kNumStages+1 the end of gather)
+// event i marks the START of stage i (10 = end of the cv pipeline, 11/12 = start/end of the gather)
 int mark(metad_mesh* p, int i, cudaStream_t st) {
     if (!p->profile) return METAD_OK;
     if (!p->ev[i]) METAD_CUDA(cudaEventCreate(&p->ev[i]));
@@ -144,17 +159,19 @@ int mark(metad_mesh* p, int i, cudaStream_t st) {
 
 int fft_pipeline(metad_mesh* p, unsigned N_global, double* d_cv, cudaStream_t st) {
     int rc = METAD_OK;
+    float2* buf = reinterpret_cast<float2*>(p->d_buf);
+    const unsigned nxh = p->g.nx / 2;
     rc = mark(p, 5, st); if (rc) return rc;
-    METAD_DISPATCH_LEN(p->g.nx / 2, (run_x<LL>(p, false, st))); if (rc) return rc;
+    METAD_DISPATCH_LEN(nxh, (run_x<LL>(p, false, nullptr, st))); if (rc) return rc;
     rc = mark(p, 6, st); if (rc) return rc;
-    METAD_DISPATCH_LEN(p->g.ny, (run_y<LL>(p, false, st))); if (rc) return rc;
+    METAD_DISPATCH_LEN(p->g.ny, (run_y<LL>(p, false, buf, nxh, p->g.nz, st))); if (rc) return rc;
     rc = mark(p, 7, st); if (rc) return rc;
-    METAD_DISPATCH_LEN(p->g.nz, (run_z<LL>(p, N_global, d_cv, st))); if (rc) return rc;
+    METAD_DISPATCH_LEN(p->g.nz, (run_z<LL>(p, buf, nxh, 0, p->d_sums, N_global, d_cv, st))); if (rc) return rc;
     rc = mark(p, 8, st); if (rc) return rc;
-    METAD_DISPATCH_LEN(p->g.ny, (run_y<LL>(p, true, st))); if (rc) return rc;
+    METAD_DISPATCH_LEN(p->g.ny, (run_y<LL>(p, true, buf, nxh, p->g.nz, st))); if (rc) return rc;
     rc = mark(p, 9, st); if (rc) return rc;
-    METAD_DISPATCH_LEN(p->g.nx / 2, (run_x<LL>(p, true, st))); if (rc) return rc;
-    rc = mark(p, 10, st); if (rc) return rc;        // end of the cv pipeline (re-recorded as start of gather by forces)
+    METAD_DISPATCH_LEN(nxh, (run_x<LL>(p, true, nullptr, st))); if (rc) return rc;
+    rc = mark(p, 10, st); if (rc) return rc;
     return METAD_OK;
 }
 
@@ -179,7 +196,7 @@ int set_box(metad_mesh* p, const metad_box* box) {
         return METAD_ERR_UNSUPPORTED;
     }
     Geom& g = p->g;
-    const unsigned n[3] = {g.nx, g.ny, g.nz};
+    const unsigned n[3] = {g.nx, g.ny, g.nzg};       // the box is the GLOBAL box
     for (int i = 0; i < 3; ++i) {
         METAD_REQUIRE(box->L[i] > 0.0, "cv.mesh: box lengths must be positive");
         g.L[i] = (float)box->L[i];
@@ -190,87 +207,19 @@ int set_box(metad_mesh* p, const metad_box* box) {
     return METAD_OK;
 }
 
-}  // namespace
-
-extern "C" int metad_mesh_create(metad_mesh** out, unsigned nx, unsigned ny, unsigned nz, int ntypes, const double* mode) {
-    METAD_REQUIRE(out && mode, "metad_mesh_create: null argument");
-    METAD_REQUIRE(ntypes > 0, "Number of modes unequal number of particle types.");
-    if (!is_pow2(nx) || !is_pow2(ny) || !is_pow2(nz)) {
-        set_error("cv.mesh: the number of mesh points along every direction must be a power of two");
-        return METAD_ERR_UNSUPPORTED;
-    }
-    if (nx < 32 || nx > 1024 || ny < 16 || ny > 512 || nz < 16 || nz > 512) {
-        set_error("cv.mesh: supported mesh sizes are 32 <= nx <= 1024, 16 <= ny,nz <= 512");
-        return METAD_ERR_UNSUPPORTED;
-    }
-    auto* p = new metad_mesh();
-    Geom& g = p->g;
-    memset(&g, 0, sizeof g);
-    const size_t M = (size_t)nx * ny * nz;
-    // 16^3 tiles once there are enough of them to fill the GPU twice, 8^3 otherwise
-    geom_set_dims(g, nx, ny, nz, (M / 4096 >= (size_t)2 * device_sm_count()) ? 4 : 3);
-    p->ntypes = ntypes;
-    std::vector<float> m(ntypes);
-    for (int i = 0; i < ntypes; ++i) m[i] = (float)mode[i];
-    const unsigned P = padded_edge(g);
-    const unsigned nb_scan = (unsigned)(M / (4 * kScanThreads));
-    const unsigned nby = (ny / 2 + 1 + kLines / 2 - 1) / (kLines / 2);
-    p->n_partials = nby + (nx / 2 / kLines) * ny;
-    int rc = METAD_OK;
-    auto fail = [&](cudaError_t e, const char* what) { rc = cuda_fail(e, what, __FILE__, __LINE__); };
-    cudaError_t e;
-#define TRY(call) if (rc == METAD_OK && (e = (call)) != cudaSuccess) fail(e, #call)
-    TRY(cudaMalloc(&p->d_mode, sizeof(float) * ntypes));
-    TRY(cudaMemcpy(p->d_mode, m.data(), sizeof(float) * ntypes, cudaMemcpyHostToDevice));
-    TRY(cudaMalloc(&p->d_count, sizeof(unsigned) * M));
-    TRY(cudaMemset(p->d_count, 0, sizeof(unsigned) * M));
-    TRY(cudaMalloc(&p->d_start, sizeof(unsigned) * (M + 4)));
-    TRY(cudaMalloc(&p->d_block_sums, sizeof(unsigned) * (nb_scan + 1)));
-    TRY(cudaMalloc(&p->d_scratch, sizeof(float) * (size_t)num_tiles(g) * P * P * P));
-    TRY(cudaMalloc(&p->d_buf, sizeof(float) * M));
-    TRY(cudaMalloc(&p->d_sums, sizeof(double) * 2));
-    TRY(cudaMalloc(&p->d_partials, sizeof(double) * p->n_partials));
-    TRY(cudaMalloc(&p->d_ticket, sizeof(unsigned)));
-    TRY(cudaMemset(p->d_ticket, 0, sizeof(unsigned)));
-#undef TRY
-    if (rc == METAD_OK) rc = upload_twiddles(&p->d_twx, nx);
-    if (rc == METAD_OK) rc = upload_twiddles(&p->d_twy, ny);
-    if (rc == METAD_OK) rc = upload_twiddles(&p->d_twz, nz);
-    if (rc != METAD_OK) { metad_mesh_destroy(p); return rc; }
-    *out = p;
-    return METAD_OK;
-}
-
-extern "C" int metad_mesh_destroy(metad_mesh* p) {
-    if (!p) return METAD_OK;
-    cudaFree(p->d_mode); cudaFree(p->d_keys); cudaFree(p->d_ranks); cudaFree(p->d_perm); cudaFree(p->d_sorted); cudaFree(p->d_skey); cudaFree(p->d_slot);
-    cudaFree(p->d_count); cudaFree(p->d_start); cudaFree(p->d_block_sums); cudaFree(p->d_scratch); cudaFree(p->d_buf);
-    cudaFree(p->d_rho_keep); cudaFree(p->d_twx); cudaFree(p->d_twy); cudaFree(p->d_twz); cudaFree(p->d_sums);
-    cudaFree(p->d_partials); cudaFree(p->d_ticket);
-    for (auto& e : p->ev) if (e) cudaEventDestroy(e);
-    delete p;
-    return METAD_OK;
-}
-
-extern "C" int metad_mesh_cv(metad_mesh* p, const float* d_postype, unsigned N, unsigned N_global, const metad_box* box,
-                             double* d_cv, metad_stream_t stream) {
-    METAD_REQUIRE(p && box && d_cv, "metad_mesh_cv: null argument");
-    METAD_REQUIRE(N == 0 || d_postype, "metad_mesh_cv: null positions");
-    METAD_REQUIRE(N_global > 0, "metad_mesh_cv: N_global must be positive");
-    int rc = set_box(p, box); if (rc) return rc;
-    rc = ensure_capacity(p, N); if (rc) return rc;
+// cell order of this step + spread into padded tiles (d_scratch); sums -> p->d_sums
+int order_and_spread(metad_mesh* p, const float* d_postype, unsigned N, cudaStream_t stream) {
     const Geom& g = p->g;
     const size_t M = p->M();
     const int sms = device_sm_count();
-    p->have_cv = false;
-
-    METAD_CUDA(cudaMemsetAsync(p->d_sums, 0, 2 * sizeof(double), stream));
+    int rc = ensure_capacity(p, N); if (rc) return rc;
+    METAD_CUDA(cudaMemsetAsync(p->d_sums, 0, 4 * sizeof(double), stream));
     rc = mark(p, 0, stream); if (rc) return rc;
+    long nbp = ((long)N + kBinThreads * 4L - 1) / (kBinThreads * 4L);
+    if (nbp > sms * 16L) nbp = sms * 16L;
     if (N > 0) {
-        long nb = ((long)N + kBinThreads * 4L - 1) / (kBinThreads * 4L);
-        if (nb > sms * 16L) nb = sms * 16L;
-        mesh_bin_kernel<<<(int)nb, kBinThreads, 0, stream>>>((const float4*)d_postype, N, g, p->d_mode, p->d_keys, p->d_ranks,
-                                                            p->d_count, p->d_sums);
+        mesh_bin_kernel<<<(int)nbp, kBinThreads, 0, stream>>>((const float4*)d_postype, N, g, p->d_mode, p->d_keys, p->d_ranks, p->d_count,
+                                                             p->d_sums);
         METAD_LAUNCH_CHECK();
     }
     rc = mark(p, 1, stream); if (rc) return rc;
@@ -293,12 +242,10 @@ extern "C" int metad_mesh_cv(metad_mesh* p, const float* d_postype, unsigned N, 
     }
     rc = mark(p, 2, stream); if (rc) return rc;
     if (N > 0) {
-        long nb = ((long)N + kBinThreads * 4L - 1) / (kBinThreads * 4L);
-        if (nb > sms * 16L) nb = sms * 16L;
-        mesh_place_kernel<<<(int)nb, kBinThreads, 0, stream>>>(N, p->d_keys, p->d_ranks, p->d_start, p->d_slot);
+        mesh_place_kernel<<<(int)nbp, kBinThreads, 0, stream>>>(N, p->d_keys, p->d_ranks, p->d_start, p->d_slot);
         METAD_LAUNCH_CHECK();
-        mesh_reorder_kernel<<<(int)nb, kBinThreads, 0, stream>>>((const float4*)d_postype, N, p->d_mode, p->d_keys, p->d_start,
-                                                                p->d_slot, p->d_sorted, p->d_perm, p->d_skey);
+        mesh_reorder_kernel<<<(int)nbp, kBinThreads, 0, stream>>>((const float4*)d_postype, N, p->d_mode, p->d_keys, p->d_start, p->d_slot,
+                                                                 p->d_sorted, p->d_perm, p->d_skey);
         METAD_LAUNCH_CHECK();
     }
     rc = mark(p, 3, stream); if (rc) return rc;
@@ -309,14 +256,128 @@ extern "C" int metad_mesh_cv(metad_mesh* p, const float* d_postype, unsigned N, 
     METAD_LAUNCH_CHECK();
     if (p->keep_rho && !p->d_rho_keep) METAD_CUDA(cudaMalloc(&p->d_rho_keep, sizeof(float) * M));
     rc = mark(p, 4, stream); if (rc) return rc;
-    {
-        long nb = (long)((M + 255) / 256);
-        if (nb > sms * 32L) nb = sms * 32L;
-        mesh_merge_kernel<<<(int)nb, 256, 0, stream>>>(p->d_scratch, g, p->d_sums, p->d_buf, p->keep_rho ? p->d_rho_keep : nullptr);
-        METAD_LAUNCH_CHECK();
+    long nb = (long)((M + 255) / 256);
+    if (nb > sms * 32L) nb = sms * 32L;
+    mesh_merge_kernel<<<(int)nb, 256, 0, stream>>>(p->d_scratch, g, p->d_sums, p->d_buf, (p->keep_rho && !g.slab) ? p->d_rho_keep : nullptr);
+    METAD_LAUNCH_CHECK();
+    return METAD_OK;
+}
+
+int launch_gather(metad_mesh* p, const float* d_ghost, float* d_force, unsigned N_global, const metad_box* box, const double* d_bias,
+                  cudaStream_t stream) {
+    const Geom& g = p->g;
+    // reciprocal lattice vectors of the (orthorhombic) box without 2 pi, times the mesh dimensions (:761-769, :852-854)
+    ForceParams fp;
+    memset(&fp, 0, sizeof fp);
+    fp.nb1[0] = (float)((double)g.nx / box->L[0]);
+    fp.nb2[1] = (float)((double)g.ny / box->L[1]);
+    fp.nb3[2] = (float)((double)g.nzg / box->L[2]);
+    fp.two_over_n = 2.0 / (double)N_global;
+    int rc = mark(p, 11, stream); if (rc) return rc;
+    if (g.lgT == 4)
+        mesh_gather_kernel<4><<<num_tiles(g), kGatherThreads, 0, stream>>>(p->d_sorted, p->d_perm, p->d_skey, p->d_start, g, p->d_buf, d_ghost,
+                                                                         fp, d_bias, (float4*)d_force);
+    else
+        mesh_gather_kernel<3><<<num_tiles(g), kGatherThreads, 0, stream>>>(p->d_sorted, p->d_perm, p->d_skey, p->d_start, g, p->d_buf, d_ghost,
+                                                                         fp, d_bias, (float4*)d_force);
+    METAD_LAUNCH_CHECK();
+    return mark(p, 12, stream);
+}
+
+int create_common(metad_mesh** out, unsigned nx, unsigned ny, unsigned nzg, unsigned n_ranks, unsigned rank, int ntypes,
+                  const double* mode) {
+    METAD_REQUIRE(out && mode, "metad_mesh_create: null argument");
+    METAD_REQUIRE(ntypes > 0, "Number of modes unequal number of particle types.");
+    if (!is_pow2(nx) || !is_pow2(ny) || !is_pow2(nzg)) {
+        set_error("cv.mesh: the number of mesh points along every direction must be a power of two");
+        return METAD_ERR_UNSUPPORTED;
     }
-    rc = fft_pipeline(p, N_global, d_cv, stream);
-    if (rc) return rc;
+    if (nx < 32 || nx > 1024 || ny < 16 || ny > 512 || nzg < 16 || nzg > 512) {
+        set_error("cv.mesh: supported mesh sizes are 32 <= nx <= 1024, 16 <= ny,nz <= 512");
+        return METAD_ERR_UNSUPPORTED;
+    }
+    METAD_REQUIRE(n_ranks >= 1 && rank < n_ranks && is_pow2(n_ranks), "cv.mesh: the number of ranks must be a power of two");
+    const bool slab = n_ranks > 1;
+    if (slab && (nzg / n_ranks < 8 || nx / 2 / n_ranks < (unsigned)kLines)) {
+        set_error("cv.mesh: z-slab sharding needs nz/ranks >= 8 and nx/2/ranks >= 16");
+        return METAD_ERR_UNSUPPORTED;
+    }
+    auto* p = new metad_mesh();
+    Geom& g = p->g;
+    memset(&g, 0, sizeof g);
+    const unsigned nzl = nzg / n_ranks;
+    const size_t M = (size_t)nx * ny * nzl;
+    // 16^3 tiles once there are enough of them to fill the GPU twice, 8^3 otherwise
+    unsigned lgT = (M / 4096 >= (size_t)2 * device_sm_count()) ? 4 : 3;
+    if (nzl < 16) lgT = 3;
+    geom_set_dims(g, nx, ny, nzl, lgT);
+    g.nzg = nzg; g.z0 = rank * nzl; g.slab = slab ? 1 : 0;
+    p->n_ranks = n_ranks; p->rank = rank; p->nzg = nzg; p->kxl = nx / 2 / n_ranks;
+    p->ntypes = ntypes;
+    std::vector<float> m(ntypes);
+    for (int i = 0; i < ntypes; ++i) m[i] = (float)mode[i];
+    const unsigned P = padded_edge(g);
+    const unsigned nb_scan = (unsigned)(M / (4 * kScanThreads));
+    const unsigned nby = (ny / 2 + 1 + kLines / 2 - 1) / (kLines / 2);
+    p->n_partials = nby + (p->kxl / kLines) * ny;
+    int rc = METAD_OK;
+    auto fail = [&](cudaError_t e, const char* what) { rc = cuda_fail(e, what, __FILE__, __LINE__); };
+    cudaError_t e;
+#define TRY(call) if (rc == METAD_OK && (e = (call)) != cudaSuccess) fail(e, #call)
+    TRY(cudaMalloc(&p->d_mode, sizeof(float) * ntypes));
+    TRY(cudaMemcpy(p->d_mode, m.data(), sizeof(float) * ntypes, cudaMemcpyHostToDevice));
+    TRY(cudaMalloc(&p->d_count, sizeof(unsigned) * M));
+    TRY(cudaMemset(p->d_count, 0, sizeof(unsigned) * M));
+    TRY(cudaMalloc(&p->d_start, sizeof(unsigned) * (M + 4)));
+    TRY(cudaMalloc(&p->d_block_sums, sizeof(unsigned) * (nb_scan + 1)));
+    TRY(cudaMalloc(&p->d_scratch, sizeof(float) * (size_t)num_tiles(g) * P * P * P));
+    TRY(cudaMalloc(&p->d_buf, sizeof(float) * M));
+    TRY(cudaMalloc(&p->d_sums, sizeof(double) * 4));
+    TRY(cudaMalloc(&p->d_partials, sizeof(double) * p->n_partials));
+    TRY(cudaMalloc(&p->d_ticket, sizeof(unsigned)));
+    TRY(cudaMemset(p->d_ticket, 0, sizeof(unsigned)));
+#undef TRY
+    if (rc == METAD_OK) rc = upload_twiddles(&p->d_twx, nx);
+    if (rc == METAD_OK) rc = upload_twiddles(&p->d_twy, ny);
+    if (rc == METAD_OK) rc = upload_twiddles(&p->d_twz, nzg);
+    if (rc != METAD_OK) { metad_mesh_destroy(p); return rc; }
+    *out = p;
+    return METAD_OK;
+}
+
+}  // namespace
+
+extern "C" int metad_mesh_create(metad_mesh** out, unsigned nx, unsigned ny, unsigned nz, int ntypes, const double* mode) {
+    return create_common(out, nx, ny, nz, 1, 0, ntypes, mode);
+}
+
+extern "C" int metad_mesh_slab_create(metad_mesh** out, unsigned nx, unsigned ny, unsigned nz, unsigned n_ranks, unsigned rank, int ntypes,
+                                      const double* mode) {
+    METAD_REQUIRE(n_ranks >= 2, "metad_mesh_slab_create: use metad_mesh_create for a single rank");
+    return create_common(out, nx, ny, nz, n_ranks, rank, ntypes, mode);
+}
+
+extern "C" int metad_mesh_destroy(metad_mesh* p) {
+    if (!p) return METAD_OK;
+    cudaFree(p->d_mode); cudaFree(p->d_keys); cudaFree(p->d_ranks); cudaFree(p->d_perm); cudaFree(p->d_sorted); cudaFree(p->d_skey); cudaFree(p->d_slot);
+    cudaFree(p->d_count); cudaFree(p->d_start); cudaFree(p->d_block_sums); cudaFree(p->d_scratch); cudaFree(p->d_buf);
+    cudaFree(p->d_rho_keep); cudaFree(p->d_twx); cudaFree(p->d_twy); cudaFree(p->d_twz); cudaFree(p->d_sums);
+    cudaFree(p->d_partials); cudaFree(p->d_ticket);
+    for (auto& e : p->ev) if (e) cudaEventDestroy(e);
+    delete p;
+    return METAD_OK;
+}
+
+extern "C" int metad_mesh_cv(metad_mesh* p, const float* d_postype, unsigned N, unsigned N_global, const metad_box* box,
+                             double* d_cv, metad_stream_t stream) {
+    METAD_REQUIRE(p && box && d_cv, "metad_mesh_cv: null argument");
+    METAD_REQUIRE(!p->g.slab, "metad_mesh_cv: this plan is a z-slab shard, use the metad_mesh_slab_* stages");
+    METAD_REQUIRE(N == 0 || d_postype, "metad_mesh_cv: null positions");
+    METAD_REQUIRE(N_global > 0, "metad_mesh_cv: N_global must be positive");
+    int rc = set_box(p, box); if (rc) return rc;
+    p->have_cv = false;
+    rc = order_and_spread(p, d_postype, N, stream); if (rc) return rc;
+    rc = fft_pipeline(p, N_global, d_cv, stream); if (rc) return rc;
     p->have_cv = true;
     p->last_N = N;
     return METAD_OK;
@@ -325,6 +386,7 @@ extern "C" int metad_mesh_cv(metad_mesh* p, const float* d_postype, unsigned N, 
 extern "C" int metad_mesh_forces(metad_mesh* p, const float* d_postype, float* d_force, unsigned N, unsigned N_global,
                                  const metad_box* box, const double* d_bias, metad_stream_t stream) {
     METAD_REQUIRE(p && box && d_bias, "metad_mesh_forces: null argument");
+    METAD_REQUIRE(!p->g.slab, "metad_mesh_forces: this plan is a z-slab shard, use metad_mesh_slab_forces");
     METAD_REQUIRE(N_global > 0, "metad_mesh_forces: N_global must be positive");
     if (!p->have_cv || p->last_N != N) {
         set_error("metad_mesh_forces: call metad_mesh_cv for the same particles first");
@@ -332,24 +394,81 @@ extern "C" int metad_mesh_forces(metad_mesh* p, const float* d_postype, float* d
     }
     if (N == 0) return METAD_OK;
     METAD_REQUIRE(d_postype && d_force, "metad_mesh_forces: null particle arrays");
-    const Geom& g = p->g;
-    // reciprocal lattice vectors of the (orthorhombic) box without 2 pi, times the mesh dimensions (:761-769, :852-854)
-    ForceParams fp;
-    memset(&fp, 0, sizeof fp);
-    fp.nb1[0] = (float)((double)g.nx / box->L[0]);
-    fp.nb2[1] = (float)((double)g.ny / box->L[1]);
-    fp.nb3[2] = (float)((double)g.nz / box->L[2]);
-    fp.two_over_n = 2.0 / (double)N_global;
-    { int rc = mark(p, 11, stream); if (rc) return rc; }
-    if (g.lgT == 4)
-        mesh_gather_kernel<4><<<num_tiles(g), kGatherThreads, 0, stream>>>(p->d_sorted, p->d_perm, p->d_skey, p->d_start, g, p->d_buf, fp,
-                                                                         d_bias, (float4*)d_force);
-    else
-        mesh_gather_kernel<3><<<num_tiles(g), kGatherThreads, 0, stream>>>(p->d_sorted, p->d_perm, p->d_skey, p->d_start, g, p->d_buf, fp,
-                                                                         d_bias, (float4*)d_force);
+    return launch_gather(p, nullptr, d_force, N_global, box, d_bias, stream);
+}
+
+// ---- z-slab stages ------------------------------------------------------------------------------------
+extern "C" int metad_mesh_slab_spread(metad_mesh* p, const float* d_postype, unsigned N_local, const metad_box* global_box,
+                                      double* d_sums, float* d_ghost_send, metad_stream_t stream) {
+    METAD_REQUIRE(p && global_box && d_sums && d_ghost_send, "metad_mesh_slab_spread: null argument");
+    METAD_REQUIRE(p->g.slab, "metad_mesh_slab_spread: not a slab plan");
+    METAD_REQUIRE(N_local == 0 || d_postype, "metad_mesh_slab_spread: null positions");
+    int rc = set_box(p, global_box); if (rc) return rc;
+    p->have_cv = false;
+    rc = order_and_spread(p, d_postype, N_local, stream); if (rc) return rc;
+    const unsigned plane = p->g.nx * p->g.ny;
+    mesh_ghost_extract_kernel<<<(2 * plane + 255) / 256, 256, 0, stream>>>(p->d_scratch, p->g, d_ghost_send);
     METAD_LAUNCH_CHECK();
-    { int rc = mark(p, 12, stream); if (rc) return rc; }
+    METAD_CUDA(cudaMemcpyAsync(d_sums, p->d_sums, 3 * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    p->last_N = N_local;
     return METAD_OK;
+}
+
+extern "C" int metad_mesh_slab_fft_x(metad_mesh* p, const float* d_ghost_recv, const double* d_sums_global, float* d_send,
+                                     metad_stream_t stream) {
+    METAD_REQUIRE(p && d_ghost_recv && d_sums_global && d_send, "metad_mesh_slab_fft_x: null argument");
+    METAD_REQUIRE(p->g.slab, "metad_mesh_slab_fft_x: not a slab plan");
+    const size_t M = p->M();
+    if (p->keep_rho && !p->d_rho_keep) METAD_CUDA(cudaMalloc(&p->d_rho_keep, sizeof(float) * M));
+    long nb = (long)((M + 255) / 256);
+    if (nb > device_sm_count() * 32L) nb = device_sm_count() * 32L;
+    mesh_add_ghost_kernel<<<(int)nb, 256, 0, stream>>>(p->d_buf, p->g, d_ghost_recv, d_sums_global, p->keep_rho ? p->d_rho_keep : nullptr);
+    METAD_LAUNCH_CHECK();
+    int rc = METAD_OK;
+    METAD_DISPATCH_LEN(p->g.nx / 2, (run_x<LL>(p, false, reinterpret_cast<float2*>(d_send), stream)));
+    return rc;
+}
+
+extern "C" int metad_mesh_slab_fft_yz(metad_mesh* p, float* d_pencil, const double* d_sums_global, unsigned N_global,
+                                      double* d_cv_partial, metad_stream_t stream) {
+    METAD_REQUIRE(p && d_pencil && d_sums_global && d_cv_partial, "metad_mesh_slab_fft_yz: null argument");
+    METAD_REQUIRE(p->g.slab, "metad_mesh_slab_fft_yz: not a slab plan");
+    METAD_REQUIRE(N_global > 0, "metad_mesh_slab_fft_yz: N_global must be positive");
+    float2* buf = reinterpret_cast<float2*>(d_pencil);
+    int rc = METAD_OK;
+    METAD_DISPATCH_LEN(p->g.ny, (run_y<LL>(p, false, buf, p->kxl, p->nzg, stream))); if (rc) return rc;
+    METAD_DISPATCH_LEN(p->nzg, (run_z<LL>(p, buf, p->kxl, p->rank * p->kxl, d_sums_global, N_global, d_cv_partial, stream))); if (rc) return rc;
+    METAD_DISPATCH_LEN(p->g.ny, (run_y<LL>(p, true, buf, p->kxl, p->nzg, stream)));
+    return rc;
+}
+
+extern "C" int metad_mesh_slab_fft_x_inv(metad_mesh* p, const float* d_recv, float* d_planes_out, metad_stream_t stream) {
+    METAD_REQUIRE(p && d_recv, "metad_mesh_slab_fft_x_inv: null argument");
+    METAD_REQUIRE(p->g.slab, "metad_mesh_slab_fft_x_inv: not a slab plan");
+    int rc = METAD_OK;
+    METAD_DISPATCH_LEN(p->g.nx / 2, (run_x<LL>(p, true, reinterpret_cast<float2*>(const_cast<float*>(d_recv)), stream)));
+    if (rc) return rc;
+    const size_t plane = (size_t)p->g.nx * p->g.ny;
+    if (d_planes_out) {     // first and last local plane of Re IFFT(G): the neighbours' halo planes
+        METAD_CUDA(cudaMemcpyAsync(d_planes_out, p->d_buf, plane * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+        METAD_CUDA(cudaMemcpyAsync(d_planes_out + plane, p->d_buf + plane * (p->g.nz - 1), plane * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    }
+    p->have_cv = true;
+    return METAD_OK;
+}
+
+extern "C" int metad_mesh_slab_forces(metad_mesh* p, const float* d_ghost_inv, const float* d_postype, float* d_force, unsigned N_local,
+                                      unsigned N_global, const metad_box* global_box, const double* d_bias, metad_stream_t stream) {
+    METAD_REQUIRE(p && d_ghost_inv && global_box && d_bias, "metad_mesh_slab_forces: null argument");
+    METAD_REQUIRE(p->g.slab, "metad_mesh_slab_forces: not a slab plan");
+    METAD_REQUIRE(N_global > 0, "metad_mesh_slab_forces: N_global must be positive");
+    if (!p->have_cv || p->last_N != N_local) {
+        set_error("metad_mesh_slab_forces: run the spread/fft stages for the same particles first");
+        return METAD_ERR_STATE;
+    }
+    if (N_local == 0) return METAD_OK;
+    METAD_REQUIRE(d_postype && d_force, "metad_mesh_slab_forces: null particle arrays");
+    return launch_gather(p, d_ghost_inv, d_force, N_global, global_box, d_bias, stream);
 }
 
 extern "C" int metad_mesh_get(metad_mesh* p, int which, void* h_out) {
@@ -358,19 +477,19 @@ extern "C" int metad_mesh_get(metad_mesh* p, int which, void* h_out) {
     const size_t M = p->M();
     switch (which) {
         case 0: {
-            if (!p->have_cv) { set_error("metad_mesh_get: no cell order yet"); return METAD_ERR_STATE; }
+            if (p->last_N == 0) return METAD_OK;
             std::vector<unsigned> keys(p->last_N);
             METAD_CUDA(cudaMemcpy(keys.data(), p->d_keys, sizeof(unsigned) * p->last_N, cudaMemcpyDeviceToHost));
             int* out = (int*)h_out;
             for (unsigned i = 0; i < p->last_N; ++i) {
                 unsigned ix, iy, iz;
                 cell_of_key(keys[i], p->g, ix, iy, iz);
-                out[3 * (size_t)i] = (int)ix; out[3 * (size_t)i + 1] = (int)iy; out[3 * (size_t)i + 2] = (int)iz;
+                out[3 * (size_t)i] = (int)ix; out[3 * (size_t)i + 1] = (int)iy; out[3 * (size_t)i + 2] = (int)(iz + p->g.z0);
             }
             return METAD_OK;
         }
         case 1:
-            if (!p->d_rho_keep) { set_error("metad_mesh_get: enable metad_mesh_set(p, 1, 1) before metad_mesh_cv to keep rho"); return METAD_ERR_STATE; }
+            if (!p->d_rho_keep) { set_error("metad_mesh_get: enable metad_mesh_set(p, 1, 1) before the spread to keep rho"); return METAD_ERR_STATE; }
             METAD_CUDA(cudaMemcpy(h_out, p->d_rho_keep, sizeof(float) * M, cudaMemcpyDeviceToHost));
             return METAD_OK;
         case 2:
@@ -382,7 +501,7 @@ extern "C" int metad_mesh_get(metad_mesh* p, int which, void* h_out) {
             return METAD_OK;
         case 4: {
             // per-stage milliseconds of the last metad_mesh_cv + metad_mesh_forces pair (float[kNumStages])
-            if (!p->profile || !p->ev[0] || !p->ev[12]) { set_error("metad_mesh_get: profiling is off (metad_mesh_set(p, 2, 1))"); return METAD_ERR_STATE; }
+            if (!p->profile || !p->ev[0] || !p->ev[10] || !p->ev[12]) { set_error("metad_mesh_get: profiling is off (metad_mesh_set(p, 2, 1))"); return METAD_ERR_STATE; }
             float* out = (float*)h_out;
             for (int i = 0; i < 10; ++i) METAD_CUDA(cudaEventElapsedTime(out + i, p->ev[i], p->ev[i + 1]));
             METAD_CUDA(cudaEventElapsedTime(out + 10, p->ev[11], p->ev[12]));

@@ -20,7 +20,9 @@ namespace metad {
 namespace fft {
 
 struct ConvParams {
-    unsigned nx, ny, nz;
+    unsigned nx, ny, nz;          // GLOBAL mesh dimensions
+    unsigned row_len;             // complex elements per (z,y) row of the buffer: nx/2, or the kx pencil width when sharded
+    unsigned kx_off;              // global kx of local column 0 (0 unless sharded)
     float inv_n;                  // 1 / N_global
     double n_global;
     const double* d_mode_sq;      // device: sum_j a_j^2 of this step
@@ -81,7 +83,10 @@ template <int TWL> __device__ __forceinline__ void load_twiddles(float2* s_tw, c
 // ---------------------------------------------------------------------------------------------------
 template <int LC>
 __global__ void __launch_bounds__(kLines * LC / kE)
-fft_x_fwd_kernel(float2* __restrict__ buf, const float2* __restrict__ g_tw /* length 2*LC */) {
+fft_x_fwd_kernel(float2* buf, const float2* __restrict__ g_tw /* length 2*LC */, float2* out,
+                 unsigned lg_part /* log2 of the kx pencil width */, unsigned rows_total) {
+    // out == buf, lg_part = log2(LC): plain in-place transform.  Sharded: out = send buffer laid out [part][row][kx in part],
+    // i.e. already packed for the slab -> pencil all-to-all.
     extern __shared__ float2 smem[];
     float2* tile = smem;
     float2* s_tw = smem + LayoutRow::size(LC);
@@ -102,25 +107,32 @@ fft_x_fwd_kernel(float2* __restrict__ buf, const float2* __restrict__ g_tw /* le
         r2c_pair(zk, zp, k, LC, s_tw[k]);
     }
     __syncthreads();
+    const unsigned part_len = 1u << lg_part;
     for (int idx = threadIdx.x; idx < kLines * LC; idx += nthr) {
         const int ww = idx / LC, l = idx % LC;
-        buf[(row0 + ww) * LC + l] = tile[LayoutRow::addr(ww, l, LC)];
+        const size_t dst = ((size_t)(l >> lg_part) * rows_total + (row0 + ww)) * part_len + (l & (part_len - 1));
+        out[dst] = tile[LayoutRow::addr(ww, l, LC)];
     }
 }
 
 // x pass, inverse (C2R)
 template <int LC>
 __global__ void __launch_bounds__(kLines * LC / kE)
-fft_x_inv_kernel(float2* __restrict__ buf, const float2* __restrict__ g_tw) {
+fft_x_inv_kernel(float2* buf, const float2* __restrict__ g_tw, const float2* in, unsigned lg_part,
+                 unsigned rows_total) {
+    // in == buf, lg_part = log2(LC): plain in-place transform.  Sharded: in = receive buffer of the pencil -> slab
+    // all-to-all, laid out [part][row][kx in part].
     extern __shared__ float2 smem[];
     float2* tile = smem;
     float2* s_tw = smem + LayoutRow::size(LC);
     const int nthr = kLines * LC / kE;
     const size_t row0 = (size_t)blockIdx.x * kLines;
     load_twiddles<2 * LC>(s_tw, g_tw);
+    const unsigned part_len = 1u << lg_part;
     for (int idx = threadIdx.x; idx < kLines * LC; idx += nthr) {
         const int w = idx / LC, l = idx % LC;
-        tile[LayoutRow::addr(w, l, LC)] = buf[(row0 + w) * LC + l];
+        const size_t src = ((size_t)(l >> lg_part) * rows_total + (row0 + w)) * part_len + (l & (part_len - 1));
+        tile[LayoutRow::addr(w, l, LC)] = in[src];
     }
     __syncthreads();
     for (int idx = threadIdx.x; idx < kLines * (LC / 2 + 1); idx += nthr) {
@@ -196,7 +208,7 @@ __device__ __forceinline__ void z_general_body(float2* __restrict__ buf, const f
     float2* tile = smem;
     float2* s_tw = smem + LayoutCol::size(L);
     const int nthr = kLines * L / kE;
-    const unsigned nxh = cp.nx / 2, ny = cp.ny;
+    const unsigned nxh = cp.row_len, ny = cp.ny;
     const unsigned kx0 = bx * kLines, ky = by;
     const size_t base = (size_t)ky * nxh + kx0;
     const size_t zstride = (size_t)ny * nxh;
@@ -216,14 +228,14 @@ __device__ __forceinline__ void z_general_body(float2* __restrict__ buf, const f
     for (int idx = threadIdx.x; idx < kLines * L; idx += nthr) {
         const int ww = idx & (kLines - 1);
         const unsigned kz = idx / kLines;
-        if (kx0 + ww == 0) continue;
+        if (cp.kx_off + kx0 + ww == 0) continue;
         tile[idx] = conv_general(tile[idx], cp.inv_n, d, ky_nonneg && nonneg(kz, L), e);
     }
     __syncthreads();
     line_fft<L, +1, L, LayoutCol>(tile, w, t, s_tw);
     for (int idx = threadIdx.x; idx < kLines * L; idx += nthr) {
         const int ww = idx & (kLines - 1), l = idx / kLines;
-        if (kx0 + ww == 0) continue;
+        if (cp.kx_off + kx0 + ww == 0) continue;
         buf[base + (size_t)l * zstride + ww] = tile[idx];
     }
     energy_block_finish(e, cp);
@@ -242,7 +254,7 @@ __device__ __forceinline__ void z_plane0_body(float2* __restrict__ buf, const fl
     float2* s_tw = smem + LayoutCol::size(L);
     constexpr int nthr = kLines * L / kE;
     constexpr int per_thread = kLines * L / nthr;   // = 8
-    const unsigned nxh = cp.nx / 2, ny = cp.ny;
+    const unsigned nxh = cp.row_len, ny = cp.ny;
     const size_t zstride = (size_t)ny * nxh;
     load_twiddles<L>(s_tw, g_tw);
     for (int idx = threadIdx.x; idx < kLines * L; idx += nthr) {
@@ -300,7 +312,7 @@ fft_z_fused_kernel(float2* __restrict__ buf, const float2* __restrict__ g_tw, Co
     if (blockIdx.x < cp.n_blocks_plane0) {
         z_plane0_body<L>(buf, g_tw, cp, blockIdx.x, smem);
     } else {
-        const unsigned b = blockIdx.x - cp.n_blocks_plane0, ntx = cp.nx / 2 / kLines;
+        const unsigned b = blockIdx.x - cp.n_blocks_plane0, ntx = cp.row_len / kLines;
         z_general_body<L>(buf, g_tw, cp, b % ntx, b / ntx, smem);
     }
 }

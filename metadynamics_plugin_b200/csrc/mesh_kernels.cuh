@@ -28,8 +28,10 @@ namespace metad {
 namespace mesh {
 
 struct Geom {
-    unsigned nx, ny, nz;        // mesh points (powers of two)
+    unsigned nx, ny, nz;        // mesh points of the LOCAL mesh (powers of two); nz = planes of this z slab
     unsigned lgx, lgy, lgz;     // log2 of the above
+    unsigned nzg, z0;           // global number of z planes and first global plane of this slab (nzg = nz, z0 = 0 if unsharded)
+    unsigned slab;              // 1: z is not periodic locally, the planes z0-1 and z0+nz belong to the neighbour ranks
     unsigned lgT;               // log2 of the tile edge T (3 or 4)
     unsigned ntx, nty, ntz;     // tiles per dimension (powers of two)
     unsigned lgtx, lgty, lgtz;  // log2 of the above
@@ -41,6 +43,7 @@ MHD void geom_set_dims(Geom& g, unsigned nx, unsigned ny, unsigned nz, unsigned 
     auto lg = [](unsigned n) { unsigned l = 0; while ((1u << l) < n) ++l; return l; };
     g.nx = nx; g.ny = ny; g.nz = nz;
     g.lgx = lg(nx); g.lgy = lg(ny); g.lgz = lg(nz);
+    g.nzg = nz; g.z0 = 0; g.slab = 0;
     g.lgT = lgT;
     g.lgtx = g.lgx - lgT; g.lgty = g.lgy - lgT; g.lgtz = g.lgz - lgT;
     g.ntx = 1u << g.lgtx; g.nty = 1u << g.lgty; g.ntz = 1u << g.lgtz;
@@ -115,7 +118,8 @@ MHD void cell_of_key(unsigned key, const Geom& g, unsigned& ix, unsigned& iy, un
 // in-cell offset in cell units, s in [-1/2, 1/2] (OrderParameterMesh.cc:565-573: minimum-image distance to the
 // cell centre through makeCoordinates/minImage/makeFraction; evaluated here directly in fp64)
 MHD float cell_shift(float x, unsigned i, int axis, const Geom& g) {
-    const unsigned n = axis == 0 ? g.nx : (axis == 1 ? g.ny : g.nz);
+    // i is the GLOBAL cell coordinate (for z: z0 + local plane)
+    const unsigned n = axis == 0 ? g.nx : (axis == 1 ? g.ny : g.nzg);
     double s = ((double)x - g.dlo[axis]) * g.dscale[axis] - ((double)i + 0.5);
     const double half = 0.5 * (double)n;
     if (s > half) s -= (double)n;
@@ -184,30 +188,36 @@ MHD float reduce_replicas(const float* rep, unsigned px, unsigned py, unsigned T
     return sum;
 }
 
-// merge: value of mesh cell (x,y,z) = sum over the <= 8 padded tiles that cover it, in fixed (z,y,x) order
-MHD float merge_cell(const float* __restrict__ scratch, unsigned x, unsigned y, unsigned z, const Geom& g) {
+// merge: value of mesh cell (x,y,z) = sum over the <= 8 padded tiles that cover it, in fixed (z,y,x) order.
+// merge_plane sums the x,y candidates of padded plane pz of tile row tz.
+MHD float merge_plane(const float* __restrict__ scratch, unsigned x, unsigned y, unsigned tz, unsigned pz, const Geom& g) {
     const unsigned T = 1u << g.lgT, P = T + 2, P3 = P * P * P;
-    const unsigned tx = x >> g.lgT, ty = y >> g.lgT, tz = z >> g.lgT;
-    const unsigned lx = x & (T - 1), ly = y & (T - 1), lz = z & (T - 1);
-    // candidates per axis: (tile, padded coordinate)
-    unsigned ctx[2], cpx[2], cty[2], cpy[2], ctz[2], cpz[2];
-    int nxc = 1, nyc = 1, nzc = 1;
+    const unsigned tx = x >> g.lgT, ty = y >> g.lgT;
+    const unsigned lx = x & (T - 1), ly = y & (T - 1);
+    unsigned ctx[2], cpx[2], cty[2], cpy[2];
+    int nxc = 1, nyc = 1;
     ctx[0] = tx; cpx[0] = lx + 1;
     if (lx == 0) { ctx[1] = (tx + g.ntx - 1) & (g.ntx - 1); cpx[1] = T + 1; nxc = 2; }
     else if (lx == T - 1) { ctx[1] = (tx + 1) & (g.ntx - 1); cpx[1] = 0; nxc = 2; }
     cty[0] = ty; cpy[0] = ly + 1;
     if (ly == 0) { cty[1] = (ty + g.nty - 1) & (g.nty - 1); cpy[1] = T + 1; nyc = 2; }
     else if (ly == T - 1) { cty[1] = (ty + 1) & (g.nty - 1); cpy[1] = 0; nyc = 2; }
-    ctz[0] = tz; cpz[0] = lz + 1;
-    if (lz == 0) { ctz[1] = (tz + g.ntz - 1) & (g.ntz - 1); cpz[1] = T + 1; nzc = 2; }
-    else if (lz == T - 1) { ctz[1] = (tz + 1) & (g.ntz - 1); cpz[1] = 0; nzc = 2; }
     float sum = 0.f;
-    for (int c = 0; c < nzc; ++c)
-        for (int b = 0; b < nyc; ++b)
-            for (int a = 0; a < nxc; ++a) {
-                const unsigned tile = tile_index(ctx[a], cty[b], ctz[c], g);
-                sum += scratch[(size_t)tile * P3 + (cpz[c] * P + cpy[b]) * P + cpx[a]];
-            }
+    for (int b = 0; b < nyc; ++b)
+        for (int a = 0; a < nxc; ++a) {
+            const unsigned tile = tile_index(ctx[a], cty[b], tz, g);
+            sum += scratch[(size_t)tile * P3 + (pz * P + cpy[b]) * P + cpx[a]];
+        }
+    return sum;
+}
+// In slab mode the halo planes below the first / above the last local tile row are NOT wrapped around: they are
+// extracted by merge_plane(..., tz = 0, pz = 0) / (tz = ntz-1, pz = T+1) and added by the neighbour rank.
+MHD float merge_cell(const float* __restrict__ scratch, unsigned x, unsigned y, unsigned z, const Geom& g) {
+    const unsigned T = 1u << g.lgT;
+    const unsigned tz = z >> g.lgT, lz = z & (T - 1);
+    float sum = merge_plane(scratch, x, y, tz, lz + 1, g);
+    if (lz == 0 && !(g.slab && tz == 0)) sum += merge_plane(scratch, x, y, (tz + g.ntz - 1) & (g.ntz - 1), T + 1, g);
+    else if (lz == T - 1 && !(g.slab && tz == g.ntz - 1)) sum += merge_plane(scratch, x, y, (tz + 1) & (g.ntz - 1), 0, g);
     return sum;
 }
 
@@ -271,14 +281,17 @@ constexpr int kBinThreads = 256;
 __global__ void __launch_bounds__(kBinThreads)
 mesh_bin_kernel(const float4* __restrict__ postype, unsigned N, Geom g, const float* __restrict__ mode,
                 unsigned* __restrict__ keys, unsigned* __restrict__ ranks, unsigned* __restrict__ count,
-                double* __restrict__ sums /* [0] sum a^2, [1] sum a */) {
+                double* __restrict__ sums /* [0] sum a^2, [1] sum a, [2] misplaced particles */) {
     double sq = 0.0, s1 = 0.0;
     const unsigned stride = gridDim.x * blockDim.x;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
         const float4 p = ld_stream(postype + i);
         const unsigned ix = cell_coord(p.x, g.lo[0], g.L[0], g.nx);
         const unsigned iy = cell_coord(p.y, g.lo[1], g.L[1], g.ny);
-        const unsigned iz = cell_coord(p.z, g.lo[2], g.L[2], g.nz);
+        // global plane -> local plane of this slab; a particle outside the slab is a caller error: it is folded into
+        // the slab (keeps memory safe) and counted in sums[2]
+        unsigned iz = (unsigned)cell_coord(p.z, g.lo[2], g.L[2], g.nzg) - g.z0;
+        if (iz >= g.nz) { iz &= (g.nz - 1); atomicAdd(sums + 2, 1.0); }
         const unsigned key = key_of(ix, iy, iz, g);
         keys[i] = key;
         ranks[i] = atomicAdd(count + key, 1u);
@@ -446,7 +459,7 @@ mesh_spread_kernel(const float4* __restrict__ sorted, const unsigned* __restrict
                 for (unsigned j = c0 + tid; j < c1; j += NT) {
                     const unsigned local = __ldg(skey + j) & (NT - 1);     // cell inside the plane
                     float w[9];
-                    spread_weights(sorted[j], (tx << LGT) + (local & (T - 1)), (ty << LGT) + (local >> LGT), (tz << LGT) + lz, g, w);
+                    spread_weights(sorted[j], (tx << LGT) + (local & (T - 1)), (ty << LGT) + (local >> LGT), g.z0 + (tz << LGT) + lz, g, w);
 #pragma unroll
                     for (int c = 0; c < 9; ++c) wbuf[c * kSpreadCap + (j - c0)] = w[c];
                 }
@@ -479,7 +492,8 @@ __global__ void __launch_bounds__(256)
 mesh_merge_kernel(const float* __restrict__ scratch, Geom g, const double* __restrict__ sums, float* __restrict__ rho,
                   float* __restrict__ rho_keep) {
     const size_t M = (size_t)g.nx * g.ny * g.nz;
-    const float mean = (float)(sums[1] / (double)M);
+    // slab mode: the mean needs the GLOBAL sum, it is subtracted later (mesh_add_ghost_kernel)
+    const float mean = g.slab ? 0.f : (float)(sums[1] / (double)M);
     const unsigned T = 1u << g.lgT, P = T + 2;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < M; c += stride) {
@@ -498,12 +512,40 @@ mesh_merge_kernel(const float* __restrict__ scratch, Geom g, const double* __res
     }
 }
 
+// slab mode: the two halo planes that belong to the neighbour ranks: ghost[0] = plane z0-1, ghost[1] = plane z0+nz
+__global__ void __launch_bounds__(256)
+mesh_ghost_extract_kernel(const float* __restrict__ scratch, Geom g, float* __restrict__ ghost) {
+    const unsigned plane = g.nx * g.ny, T = 1u << g.lgT;
+    for (unsigned c = blockIdx.x * blockDim.x + threadIdx.x; c < 2 * plane; c += gridDim.x * blockDim.x) {
+        const unsigned which = c >= plane, cc = which ? c - plane : c;
+        const unsigned x = cc & (g.nx - 1), y = cc >> g.lgx;
+        ghost[c] = which ? merge_plane(scratch, x, y, g.ntz - 1, T + 1, g) : merge_plane(scratch, x, y, 0, 0, g);
+    }
+}
+// slab mode: add the planes received from the neighbours (recv[0] -> first local plane, recv[1] -> last local plane)
+// and subtract the global mean density (DC removal)
+__global__ void __launch_bounds__(256)
+mesh_add_ghost_kernel(float* __restrict__ rho, Geom g, const float* __restrict__ recv, const double* __restrict__ sums_global,
+                      float* __restrict__ rho_keep) {
+    const size_t M = (size_t)g.nx * g.ny * g.nz, plane = (size_t)g.nx * g.ny;
+    const float mean = (float)(sums_global[1] / ((double)plane * (double)g.nzg));
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < M; c += stride) {
+        float v = rho[c];
+        if (c < plane) v += recv[c];
+        if (c >= M - plane) v += recv[plane + (c - (M - plane))];
+        if (rho_keep) rho_keep[c] = v;
+        rho[c] = v - mean;
+    }
+}
+
 // gather: one CTA per tile; shared tile of Re(IFFT(G)) with halo; one thread per particle of the tile
 constexpr int kGatherThreads = 256;
 template <int LGT>
 __global__ void __launch_bounds__(kGatherThreads)
 mesh_gather_kernel(const float4* __restrict__ sorted, const unsigned* __restrict__ perm, const unsigned* __restrict__ skey,
-                   const unsigned* __restrict__ start, Geom g, const float* __restrict__ inv, ForceParams fp,
+                   const unsigned* __restrict__ start, Geom g, const float* __restrict__ inv,
+                   const float* __restrict__ ghost /* slab mode: planes z0-1 and z0+nz of Re IFFT(G) */, ForceParams fp,
                    const double* __restrict__ d_bias, float4* __restrict__ force) {
     constexpr unsigned T = 1u << LGT, P = T + 2, P3 = P * P * P;
     __shared__ float tile[P3];
@@ -517,10 +559,14 @@ mesh_gather_kernel(const float4* __restrict__ sorted, const unsigned* __restrict
     for (unsigned row = warp; row < P * P; row += kGatherThreads / 32) {
         const unsigned py = row % P, pz = row / P;
         const unsigned y = ((ty << LGT) + py + g.ny - 1) & (g.ny - 1);
-        const unsigned z = ((tz << LGT) + pz + g.nz - 1) & (g.nz - 1);
+        const int zl = (int)((tz << LGT) + pz) - 1;                  // local plane, -1 and nz are halo planes
+        const float* src;
+        if (g.slab && zl < 0) src = ghost + (size_t)g.nx * y;
+        else if (g.slab && zl >= (int)g.nz) src = ghost + (size_t)g.nx * (g.ny + y);
+        else src = inv + (size_t)g.nx * (y + (size_t)g.ny * ((unsigned)(zl + (int)g.nz) & (g.nz - 1)));
         if (lane < P) {
             const unsigned x = ((tx << LGT) + lane + g.nx - 1) & (g.nx - 1);
-            tile[row * P + lane] = __ldg(inv + (size_t)x + (size_t)g.nx * (y + (size_t)g.ny * z));
+            tile[row * P + lane] = __ldg(src + x);
         }
     }
     __syncthreads();
@@ -528,7 +574,7 @@ mesh_gather_kernel(const float4* __restrict__ sorted, const unsigned* __restrict
     for (unsigned j = s + threadIdx.x; j < e; j += kGatherThreads) {
         const unsigned local = __ldg(skey + j) & ((1u << (3 * LGT)) - 1);
         const unsigned lx = local & (T - 1), ly = (local >> LGT) & (T - 1), lz = local >> (2 * LGT);
-        force[__ldg(perm + j)] = gather_force(sorted[j], (tx << LGT) + lx, (ty << LGT) + ly, (tz << LGT) + lz, lx, ly, lz, tile, g, fp, scale);
+        force[__ldg(perm + j)] = gather_force(sorted[j], (tx << LGT) + lx, (ty << LGT) + ly, g.z0 + (tz << LGT) + lz, lx, ly, lz, tile, g, fp, scale);
     }
 }
 #endif  // __CUDACC__

@@ -1,0 +1,221 @@
+"""Multi-GPU drivers: one process per GPU, torch.distributed (NCCL) for the collectives, the C ABI for the compute.
+
+LamellarSharded   any particle partition; one all-reduce of 2*n_wave doubles per step
+                  (reference: MPI_Allreduce, LamellarOrderParameterGPU.cc:70-77).
+MeshSlab          z-slab decomposition of the particle mesh (reference: HOOMD domain decomposition + CommunicatorGrid
+                  ghost exchange + dfft, OrderParameterMesh.cc:231-315, 659-746): two neighbour plane exchanges,
+                  two all-to-all transposes (slab <-> kx pencil) and two tiny all-reduces per step.
+The bias grid is replicated: every rank applies the identical metad_grid_step after the CV all-reduce.
+
+The communication pattern is written against a small `Comm` interface so that the same driver code runs
+  * over NCCL (TorchComm, one process per GPU),
+  * over gloo on CPU tensors with a numpy stand-in for the local compute (tests/test_distributed_cpu.py), and
+  * over LocalComm: all ranks emulated in one process, bulk-synchronously, on one GPU (tests/test_gpu_sharded.py).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ._abi import Box, check, lib
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# ---------------------------------------------------------------------------------------------------- communicators
+class TorchComm:
+    """torch.distributed process group (NCCL on GPUs, gloo on CPU)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.rank, self.size = dist.get_rank(group), dist.get_world_size(group)
+
+    def all_reduce_sum(self, t):
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+
+    def all_to_all(self, out, inp):
+        self.dist.all_to_all_single(out, inp, group=self.group)
+
+    def neighbour_exchange(self, send_down, send_up, recv_from_down, recv_from_up):
+        """send_down -> rank-1, send_up -> rank+1 (periodic); receive the matching planes."""
+        d = self.dist
+        down, up = (self.rank - 1) % self.size, (self.rank + 1) % self.size
+        if self.size == 1:
+            recv_from_up.copy_(send_down)
+            recv_from_down.copy_(send_up)
+            return
+        ops = [d.P2POp(d.isend, send_down, down, self.group), d.P2POp(d.isend, send_up, up, self.group),
+               d.P2POp(d.irecv, recv_from_down, down, self.group), d.P2POp(d.irecv, recv_from_up, up, self.group)]
+        if self.size == 2:
+            # down == up: pair the two messages by tag order (both ranks post send_down first, then send_up):
+            # what rank r sends "down" is what rank 1-r must receive "from up"
+            ops = [d.P2POp(d.isend, send_down, down, self.group), d.P2POp(d.irecv, recv_from_up, up, self.group),
+                   d.P2POp(d.isend, send_up, up, self.group), d.P2POp(d.irecv, recv_from_down, down, self.group)]
+        for r in d.batch_isend_irecv(ops):
+            r.wait()
+
+
+class LocalComm:
+    """All ranks in one process (bulk-synchronous emulation): every collective takes the list of per-rank tensors."""
+
+    def __init__(self, size):
+        self.size = size
+
+    def all_reduce_sum(self, ts):
+        s = torch.stack(list(ts)).sum(0)
+        for t in ts:
+            t.copy_(s)
+
+    def all_to_all(self, outs, inps):
+        P = self.size
+        for r in range(P):
+            o = outs[r].view(P, -1)
+            for q in range(P):
+                o[q].copy_(inps[q].view(P, -1)[r])
+
+    def neighbour_exchange(self, send_down, send_up, recv_from_down, recv_from_up):
+        P = self.size
+        for r in range(P):
+            recv_from_up[(r - 1) % P].copy_(send_down[r])
+            recv_from_down[(r + 1) % P].copy_(send_up[r])
+
+
+# ---------------------------------------------------------------------------------------------------- lamellar
+class LamellarSharded:
+    def __init__(self, comm, mode, lattice_vectors):
+        from .ops import Lamellar
+        self.comm, self.lam = comm, Lamellar(mode, lattice_vectors)
+
+    def compute_cv(self, postype_local, n_global, box):
+        self.lam.compute_modes(postype_local, n_global, box, finalize=False)
+        self.comm.all_reduce_sum(self.lam.modes)
+        return self.lam.finalize(n_global)
+
+    def forces(self, postype_local, n_global, box, bias, out=None):
+        return self.lam.forces(postype_local, n_global, box, bias, out=out)
+
+
+# ---------------------------------------------------------------------------------------------------- mesh
+def slab_of(z, L, nz, n_ranks):
+    """Owner rank of a particle: the slab holding its global mesh plane (single-precision cell rule of the path)."""
+    Lf = np.float32(L)
+    f = (np.asarray(z, np.float32) - (-(Lf / np.float32(2)))) / Lf
+    iz = (f * np.float32(nz)).astype(np.int64)
+    iz[iz == nz] = 0
+    return iz // (nz // n_ranks)
+
+
+class MeshSlabRank:
+    """The five compute stages of one rank (thin wrappers of metad_mesh_slab_*) and its communication buffers."""
+
+    def __init__(self, nx, ny, nz, n_ranks, rank, mode, device="cuda"):
+        m = np.ascontiguousarray(mode, dtype=np.float64)
+        self.dims, self.P, self.rank = (nx, ny, nz), n_ranks, rank
+        self.nzl, self.kxl = nz // n_ranks, nx // 2 // n_ranks
+        self.h = C.c_void_p()
+        check(lib.metad_mesh_slab_create(C.byref(self.h), nx, ny, nz, n_ranks, rank, len(m), m.ctypes.data_as(C.POINTER(C.c_double))))
+        f32, f64 = dict(dtype=torch.float32, device=device), dict(dtype=torch.float64, device=device)
+        m_local = nx * ny * self.nzl
+        self.sums = torch.zeros(3, **f64)
+        self.ghost_send = torch.zeros(2, ny, nx, **f32)
+        self.ghost_recv = torch.zeros(2, ny, nx, **f32)
+        self.send = torch.empty(m_local, **f32)            # packed half spectrum of the slab: [dest][plane][y][kx]
+        self.pencil = torch.empty(m_local, **f32)          # [nz][ny][kxl] complex
+        self.cv = torch.zeros(1, **f64)
+        self.inv_send = torch.zeros(2, ny, nx, **f32)
+        self.inv_ghost = torch.zeros(2, ny, nx, **f32)
+        self._n = 0
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib.metad_mesh_destroy(self.h)
+            self.h = None
+
+    def set(self, key, value):
+        check(lib.metad_mesh_set(self.h, int(key), int(value)))
+
+    def stage_spread(self, postype, box):
+        self._n = postype.shape[0]
+        check(lib.metad_mesh_slab_spread(self.h, _ptr(postype), self._n, C.byref(box), _ptr(self.sums), _ptr(self.ghost_send), _stream()))
+
+    def stage_fft_x(self):
+        check(lib.metad_mesh_slab_fft_x(self.h, _ptr(self.ghost_recv), _ptr(self.sums), _ptr(self.send), _stream()))
+
+    def stage_fft_yz(self, n_global):
+        check(lib.metad_mesh_slab_fft_yz(self.h, _ptr(self.pencil), _ptr(self.sums), int(n_global), _ptr(self.cv), _stream()))
+
+    def stage_fft_x_inv(self):
+        check(lib.metad_mesh_slab_fft_x_inv(self.h, _ptr(self.send), _ptr(self.inv_send), _stream()))
+
+    def stage_forces(self, postype, n_global, box, bias, out=None):
+        if out is None:
+            out = torch.empty_like(postype)
+        check(lib.metad_mesh_slab_forces(self.h, _ptr(self.inv_ghost), _ptr(postype), _ptr(out), postype.shape[0], int(n_global),
+                                         C.byref(box), _ptr(bias), _stream()))
+        return out
+
+    def cells(self):
+        out = np.empty((self._n, 3), dtype=np.int32)
+        check(lib.metad_mesh_get(self.h, 0, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def local_mesh(self, which):
+        nx, ny, _ = self.dims
+        out = np.empty((self.nzl, ny, nx), dtype=np.float32)
+        check(lib.metad_mesh_get(self.h, which, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+
+class MeshSlab:
+    """One rank of the sharded mesh CV, driving the stages and the collectives of `comm` (TorchComm)."""
+
+    def __init__(self, comm, nx, ny, nz, mode):
+        self.comm = comm
+        self.r = MeshSlabRank(nx, ny, nz, comm.size, comm.rank, mode)
+
+    def compute_cv(self, postype_local, n_global, box):
+        r, c = self.r, self.comm
+        r.stage_spread(postype_local, box)
+        c.all_reduce_sum(r.sums)
+        c.neighbour_exchange(r.ghost_send[0], r.ghost_send[1], r.ghost_recv[0], r.ghost_recv[1])
+        r.stage_fft_x()
+        c.all_to_all(r.pencil, r.send)
+        r.stage_fft_yz(n_global)
+        c.all_reduce_sum(r.cv)
+        c.all_to_all(r.send, r.pencil)
+        r.stage_fft_x_inv()
+        # my first plane is rank-1's upper halo, my last plane rank+1's lower halo
+        c.neighbour_exchange(r.inv_send[0], r.inv_send[1], r.inv_ghost[0], r.inv_ghost[1])
+        return r.cv
+
+    def forces(self, postype_local, n_global, box, bias, out=None):
+        return self.r.stage_forces(postype_local, n_global, box, bias, out=out)
+
+
+def mesh_slab_step_local(ranks, comm, postypes, n_global, box, bias):
+    """Bulk-synchronous emulation of all ranks in one process (LocalComm): returns (cv tensors, forces per rank)."""
+    for r, pt in zip(ranks, postypes):
+        r.stage_spread(pt, box)
+    comm.all_reduce_sum([r.sums for r in ranks])
+    comm.neighbour_exchange([r.ghost_send[0] for r in ranks], [r.ghost_send[1] for r in ranks],
+                            [r.ghost_recv[0] for r in ranks], [r.ghost_recv[1] for r in ranks])
+    for r in ranks:
+        r.stage_fft_x()
+    comm.all_to_all([r.pencil for r in ranks], [r.send for r in ranks])
+    for r in ranks:
+        r.stage_fft_yz(n_global)
+    comm.all_reduce_sum([r.cv for r in ranks])
+    comm.all_to_all([r.send for r in ranks], [r.pencil for r in ranks])
+    for r in ranks:
+        r.stage_fft_x_inv()
+    comm.neighbour_exchange([r.inv_send[0] for r in ranks], [r.inv_send[1] for r in ranks],
+                            [r.inv_ghost[0] for r in ranks], [r.inv_ghost[1] for r in ranks])
+    forces = [r.stage_forces(pt, n_global, box, bias) for r, pt in zip(ranks, postypes)]
+    return [r.cv for r in ranks], forces

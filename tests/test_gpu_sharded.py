@@ -1,0 +1,114 @@
+"""GPU tests of the z-slab sharded mesh path: all ranks are emulated bulk-synchronously in ONE process on one GPU
+(sharded.LocalComm), which exercises every slab stage and the exact buffer layouts of the collectives; the result
+must match the single-plan path and the oracle.  (Real multi-process NCCL runs happen in bench.py --gpus N; the
+communication pattern itself is covered on CPU with gloo in tests/test_distributed_cpu.py.)"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from metadynamics_plugin_b200 import ops, sharded
+    return ops, sharded
+
+
+@pytest.mark.parametrize("N,dims,L,P,modes", [
+    (20000, (64, 32, 32), (20.0, 11.0, 13.0), 2, (1.0,)),
+    (60000, (128, 32, 64), (40.0, 10.0, 20.0), 4, (1.0, -1.0)),
+    (200000, (256, 64, 64), (64.0, 16.0, 16.0), 8, (1.0,)),
+    (3000, (64, 16, 16), (9.0, 5.0, 6.0), 2, (1.0, 0.5)),          # 8^3 tiles, one tile row per slab
+])
+def test_mesh_slab_matches_single_plan_and_oracle(gpu, oracle, N, dims, L, P, modes):
+    import torch
+    ops, sharded = gpu
+    nx, ny, nz = dims
+    rng = np.random.default_rng(N + P)
+    Lf = np.asarray(L, float)
+    pos = ((rng.random((N, 3)) - 0.5) * Lf).astype(np.float32)
+    pos[0] = [0.0, 0.0, np.float32(Lf[2]) / 2]                     # on the upper z face -> wraps to plane 0 (rank 0)
+    pos[1, 2] = np.nextafter(np.float32(-Lf[2] / 2 + Lf[2] / P), np.float32(-1e9))     # just below a slab boundary
+    types = rng.integers(0, len(modes), N).astype(np.int32)
+    owner = sharded.slab_of(pos[:, 2], Lf[2], nz, P)
+    box = ops.Box.make(Lf)
+    ranks = [sharded.MeshSlabRank(nx, ny, nz, P, r, modes) for r in range(P)]
+    for r in ranks:
+        r.set(1, 1)
+    idx = [np.nonzero(owner == r)[0] for r in range(P)]
+    pts = [ops.make_postype(pos[i], types[i]) for i in idx]
+    bias = torch.tensor([0.9], dtype=torch.float64, device="cuda")
+    comm = sharded.LocalComm(P)
+    cvs, forces = sharded.mesh_slab_step_local(ranks, comm, pts, N, box, bias)
+    cv = cvs[0].cpu().item()
+    assert all(c.cpu().item() == cv for c in cvs)
+    assert all(r.sums.cpu()[2].item() == 0 for r in ranks)        # no particle outside its slab
+    f = np.zeros((N, 4), np.float32)
+    for i, fr in zip(idx, forces):
+        f[i] = fr.cpu().numpy()
+
+    # single-plan path on the same GPU
+    single = ops.Mesh(nx, ny, nz, modes)
+    d_all = ops.make_postype(pos, types)
+    cv1 = single.compute_cv(d_all, N, box).cpu().item()
+    f1 = single.forces(d_all, N, box, bias).cpu().numpy()
+    assert cv == pytest.approx(cv1, rel=2e-7)
+    assert np.abs(f - f1).max() < 2e-6 * np.abs(f1).max()
+
+    # oracle
+    h_pt = oracle.make_postype(pos, types)
+    o = oracle.Mesh(nx, ny, nz, modes, Lf, N, "f64", literal_copysignf=False)
+    cvo = o.current_value(h_pt)
+    fo = o.forces(h_pt, 0.9)
+    assert cv == pytest.approx(cvo, rel=1e-6)
+    assert np.abs(f - fo).max() < 1e-5 * np.abs(fo).max()
+    o32 = oracle.Mesh(nx, ny, nz, modes, Lf, N, "f32")
+    o32.assign(h_pt)
+    cells = np.zeros((N, 3), np.int32)
+    for i, r in zip(idx, ranks):
+        cells[i] = r.cells()
+    assert np.array_equal(cells, o32.cells())                     # bit-exact global cell indices
+    rho = np.concatenate([r.local_mesh(1) for r in ranks], axis=0)
+    assert np.abs(rho - o.mesh).max() < 2e-6 * max(1.0, np.abs(o.mesh).max())
+
+
+def test_mesh_slab_counts_misplaced_particles(gpu):
+    import torch
+    ops, sharded = gpu
+    ranks = [sharded.MeshSlabRank(64, 16, 16, 2, r, [1.0]) for r in range(2)]
+    pos = np.zeros((10, 3), np.float32)
+    pos[:, 2] = -3.0                                               # all in slab 0
+    ranks[1].stage_spread(ops.make_postype(pos), ops.Box.make(8.0))
+    assert ranks[1].sums.cpu()[2].item() == 10                    # reported, not silently dropped
+
+
+def test_slab_rejects_bad_decompositions(gpu):
+    ops, sharded = gpu
+    from metadynamics_plugin_b200._abi import MetadError
+    with pytest.raises(MetadError):
+        sharded.MeshSlabRank(64, 16, 16, 4, 0, [1.0])             # nx/2/P = 8 < 16
+    with pytest.raises(MetadError):
+        sharded.MeshSlabRank(128, 16, 16, 3, 0, [1.0])            # not a power of two
+
+
+def test_lamellar_sharded_local(gpu, oracle):
+    import torch
+    ops, sharded = gpu
+    N, L, P = 50000, 17.0, 4
+    rng = np.random.default_rng(5)
+    pos = ((rng.random((N, 3)) - 0.5) * L).astype(np.float32)
+    types = rng.integers(0, 2, N).astype(np.int32)
+    lv, modes = [(0, 0, 3), (1, 1, 0)], [1.0, -1.0]
+    box = ops.Box.make(L)
+    parts = np.array_split(np.arange(N), P)
+    lams = [ops.Lamellar(modes, lv) for _ in range(P)]
+    pts = [ops.make_postype(pos[i], types[i]) for i in parts]
+    for lam, pt in zip(lams, pts):
+        lam.compute_modes(pt, N, box, finalize=False)
+    sharded.LocalComm(P).all_reduce_sum([lam.modes for lam in lams])
+    cvs = [lam.finalize(N).cpu().item() for lam in lams]
+    cvo, _ = oracle.lamellar_cv(oracle.make_postype(pos, types), N, modes, lv, L)
+    assert all(c == cvs[0] for c in cvs)
+    assert abs(cvs[0] - cvo) < 2e-6 * np.sqrt(N) * 2 / N
