@@ -83,7 +83,9 @@ int metad_mesh_create(metad_mesh** out, unsigned nx, unsigned ny, unsigned nz, i
 int metad_mesh_destroy(metad_mesh* p);
 
 /* getCurrentValue: assignParticles + updateMeshes + computeCV.  Writes the CV to *d_cv (device double).
- * Keeps the inverse-transformed mesh and the particle cell order for a following metad_mesh_forces. */
+ * Keeps the inverse-transformed mesh and the particle tile order for a following metad_mesh_forces.
+ * The density is accumulated in 32-bit fixed point (bitwise independent of the particle order); the tile order
+ * (a permutation of the particles, tile by tile) is rebuilt only every `period` calls or when particles drifted. */
 int metad_mesh_cv(metad_mesh* p, const float* d_postype, unsigned N, unsigned N_global, const metad_box* box,
                   double* d_cv, metad_stream_t stream);
 /* interpolateForces for the positions last passed to metad_mesh_cv; bias read from *d_bias. */
@@ -96,10 +98,14 @@ int metad_mesh_forces(metad_mesh* p, const float* d_postype, float* d_force, uns
  * them (ops.MeshSlab does it with NCCL through torch.distributed):
  *
  *   metad_mesh_slab_spread      local density; d_sums[3] = local {sum a^2, sum a, #particles outside the slab};
- *                               d_ghost_send[2][ny][nx] = halo planes z0-1 (for rank r-1) and z0+nz/P (for rank r+1)
- *      -> all-reduce(d_sums), neighbour exchange of the two planes
- *   metad_mesh_slab_fft_x       adds d_ghost_recv[2][ny][nx] ([0] from rank r-1, [1] from rank r+1), removes the global
- *                               mean, x FFT; d_send = M/P/2 complex, already packed [dest rank][plane][y][kx in pencil]
+ *                               d_ghost_send[2][ny*nx + 4] (int32) = two halo messages: the fixed-point density of plane
+ *                               z0-1 (for rank r-1) and of plane z0+nz/P (for rank r+1), each followed by 4 ints of which
+ *                               the first holds the bits of the sender's 1/scale
+ *      -> all-reduce(d_sums), neighbour exchange of the two messages
+ *   metad_mesh_slab_fft_x       adds d_ghost_recv[2][ny*nx + 4] ([0] from rank r-1, [1] from rank r+1; integer addition
+ *                               when the scales agree, so the density equals the single-GPU one bit for bit), removes the
+ *                               global mean, x FFT;
+ *                               d_send = M/P/2 complex, already packed [dest rank][plane][y][kx in pencil]
  *      -> all-to-all (equal splits): d_pencil = [nz][ny][nx/2/P] complex, planes in rank order = global z order
  *   metad_mesh_slab_fft_yz      y FFT, fused z FFT + convolution + inverse z FFT, inverse y FFT on the pencil, in
  *                               place; *d_cv_partial = this rank's share of the CV
@@ -112,8 +118,8 @@ int metad_mesh_forces(metad_mesh* p, const float* d_postype, float* d_force, uns
 int metad_mesh_slab_create(metad_mesh** out, unsigned nx, unsigned ny, unsigned nz, unsigned n_ranks, unsigned rank, int ntypes,
                            const double* mode);
 int metad_mesh_slab_spread(metad_mesh* p, const float* d_postype, unsigned N_local, const metad_box* global_box, double* d_sums,
-                           float* d_ghost_send, metad_stream_t stream);
-int metad_mesh_slab_fft_x(metad_mesh* p, const float* d_ghost_recv, const double* d_sums_global, float* d_send,
+                           int* d_ghost_send, metad_stream_t stream);
+int metad_mesh_slab_fft_x(metad_mesh* p, const int* d_ghost_recv, const double* d_sums_global, float* d_send,
                           metad_stream_t stream);
 int metad_mesh_slab_fft_yz(metad_mesh* p, float* d_pencil, const double* d_sums_global, unsigned N_global, double* d_cv_partial,
                            metad_stream_t stream);
@@ -122,15 +128,19 @@ int metad_mesh_slab_forces(metad_mesh* p, const float* d_ghost_inv, const float*
                            unsigned N_global, const metad_box* global_box, const double* d_bias, metad_stream_t stream);
 
 /* Introspection for parity tests (synchronous, copies to HOST buffers):
- *   which = 0: cell coordinates (ix,iy,iz) per particle, int[3*N], input order
- *           1: density mesh rho, float[nx*ny*nz], index x + nx*(y + ny*z)
+ *   which = 0: cell coordinates (ix,iy,iz) per particle as computed by the spread, int[3*N], input order (needs key 3)
+ *           1: density mesh rho, float[nx*ny*nz], index x + nx*(y + ny*z) (needs key 1)
  *           2: Re(inverse mesh), float[nx*ny*nz]
  *           3: sum of mode^2 (double[1])
- *           4: per-stage milliseconds of the last cv + forces pair, float[11] (needs key 2): bin, scan, reorder,
- *              spread, merge, fft x fwd, fft y fwd, fft z fused, fft y inv, fft x inv, gather                    */
+ *           4: per-stage milliseconds of the last cv + forces pair, float[8] (needs key 2): tile order (0 on calls that
+ *              reuse it), spread, fft x fwd, fft y fwd, fft z fused, fft y inv, fft x inv, gather
+ *           5: statistics, double[6]: rebuilds of the tile order so far; of the last spread: particles that took the
+ *              direct path (drifted out of their padded tile), particles outside the slab, padded-tile cells past 1/8 of
+ *              the fixed-point range; the fixed-point scale; calls since the last rebuild                              */
 int metad_mesh_get(metad_mesh* p, int which, void* h_out);
-/* knobs: key 0 = resort period (1 = rebuild the cell order every call, default)
- *        key 1 = keep a copy of rho for metad_mesh_get(1)      key 2 = record per-stage CUDA events (profiling) */
+/* knobs: key 0 = rebuild period of the tile order in calls (default 32; value 0 = rebuild at the next call)
+ *        key 1 = keep a copy of rho for metad_mesh_get(1)      key 2 = record per-stage CUDA events (profiling)
+ *        key 3 = record the cell index of every particle for metad_mesh_get(0)                                         */
 int metad_mesh_set(metad_mesh* p, int key, long value);
 
 /* ------------------------------------------------------------------------------------------------

@@ -1,23 +1,31 @@
 // mesh.cu -- OrderParameterMesh plan object and C ABI (see include/metad_b200.h).
 //
 // Step structure of metad_mesh_cv (reference: OrderParameterMesh::getCurrentValue, OrderParameterMesh.cc:925-968):
-//   bin -> scan -> place -> reorder   cell order of this step (tile-major stable counting sort; exact, rebuilt per call)
-//   spread -> merge                   assignParticles (:517-640); also sum a^2 (m_mode_sq) and sum a
-//   x fwd, y fwd, z fused (+plane0), y inv, x inv   updateMeshes (:642-747) + computeCV (:866-923)
-// metad_mesh_forces: gather           interpolateForces (:749-864)
+//   [tile order: bin -> scan -> place]   only every `period` calls, or when particles drifted (amortised; see below)
+//   spread                               assignParticles (:517-640) into the fixed-point mesh; also sum a^2 (m_mode_sq), sum a
+//   x fwd (+ int -> float, DC removal), y fwd, z fused (+plane0), y inv, x inv   updateMeshes (:642-747) + computeCV (:866-923)
+// metad_mesh_forces: gather              interpolateForces (:749-864)
 //
-// DC removal: the merge pass subtracts the mean density (sum a / M) before the transforms.  The k = 0 mode is
+// Tile order.  The spread and gather kernels visit the particles tile by tile through a permutation.  Because the
+// density is accumulated in integers and every particle's cell is recomputed from its current position, ANY permutation
+// gives bitwise the same result; the order only decides speed (particles that left their padded tile take a slow path).
+// It is therefore rebuilt lazily: on the first call, when N changes, every `period` calls (metad_mesh_set key 0,
+// default 32), and as soon as the device reports drifted particles or a cell near the fixed-point range (counters
+// copied asynchronously to pinned host memory after every spread; no host synchronisation anywhere in a step).
+//
+// DC removal: the x pass subtracts the mean density (sum a / M) before the transforms.  The k = 0 mode is
 // excluded from the CV (:892) and a constant offset of IFFT(G) cannot produce a force (the TSC derivative
 // weights of the 27 taps sum to zero), so results are unchanged -- but without it the fp32 transforms carry a
 // DC term ~sqrt(N) times larger than every other mode and the force mesh loses several digits.
 //
 // z-slab sharding (metad_mesh_slab_*): rank r owns the planes [r nz/P, (r+1) nz/P) and the particles inside them
 // (reference: HOOMD domain decomposition + CommunicatorGrid ghost exchange + dfft, OrderParameterMesh.cc:263-315,
-// 659-746).  Per step: local spread, halo-add of one plane per side, x FFT written directly in the layout of the
-// slab -> kx-pencil all-to-all, y and fused z passes on the pencil (the packed kx = 0 column lives entirely on rank
-// 0), all-to-all back, x inverse, halo-fill of one plane per side, local gather.  The collectives themselves
-// (2 all-to-alls, 2 neighbour exchanges, 2 tiny all-reduces) are issued by the caller (NCCL via torch.distributed in
-// ops.MeshSlab); this file provides the five compute stages between them.
+// 659-746).  Per step: local spread (the integer mesh carries one ghost plane per side), halo exchange of the two
+// integer ghost planes, x FFT written directly in the layout of the slab -> kx-pencil all-to-all, y and fused z passes
+// on the pencil (the packed kx = 0 column lives entirely on rank 0), all-to-all back, x inverse, halo-fill of one plane
+// per side, local gather.  The collectives themselves (2 all-to-alls, 2 neighbour exchanges, 2 tiny all-reduces) are
+// issued by the caller (NCCL via torch.distributed in sharded.MeshSlab); this file provides the five compute stages
+// between them.  Integer halo addition makes the sharded density bitwise equal to the single-GPU one.
 #include "mesh_kernels.cuh"
 #include "mesh_fft_kernels.cuh"
 
@@ -28,9 +36,9 @@ using namespace metad;
 using namespace metad::mesh;
 using namespace metad::fft;
 
-// stages timed when profiling is on: 0 bin, 1 scan, 2 reorder, 3 spread, 4 merge, 5 fft x fwd, 6 fft y fwd,
-// 7 fft z fused (+plane0), 8 fft y inv, 9 fft x inv, 10 gather
-constexpr int kNumStages = 11;
+// stages timed when profiling is on: 0 tile order (bin + scan + place; 0 ms on calls that reuse the order), 1 spread,
+// 2 fft x fwd, 3 fft y fwd, 4 fft z fused, 5 fft y inv, 6 fft x inv, 7 gather
+constexpr int kNumStages = 8;
 
 struct metad_mesh {
     Geom g;                         // LOCAL geometry (slab: nz = planes of this rank)
@@ -39,27 +47,36 @@ struct metad_mesh {
     unsigned kxl = 0;               // kx pencil width (complex) = nx/2/n_ranks
     int ntypes = 0;
     float* d_mode = nullptr;
-    // particle order
+    float amax = 0.f;               // largest |mode coefficient|
+    // tile order
     unsigned cap = 0;
-    unsigned *d_keys = nullptr, *d_ranks = nullptr, *d_perm = nullptr, *d_skey = nullptr, *d_slot = nullptr;
-    float4* d_sorted = nullptr;
-    unsigned *d_count = nullptr, *d_start = nullptr, *d_block_sums = nullptr;
+    unsigned *d_keys = nullptr, *d_ranks = nullptr, *d_perm = nullptr;
+    unsigned *d_count = nullptr, *d_start = nullptr, *d_block_sums = nullptr, *d_tstart = nullptr, *d_max_count = nullptr;
+    bool order_valid = false;
+    unsigned order_N = 0, calls_since_rebuild = 0, period = 32;
+    unsigned long long n_rebuilds = 0;
     // mesh
-    float* d_scratch = nullptr;     // padded tiles
-    float* d_buf = nullptr;         // M_local floats: rho -> packed half spectrum -> Re IFFT(G)
+    int* d_mesh_alloc = nullptr;    // integer density: nz planes (+ one ghost plane on each side in slab mode)
+    int* d_mesh_i = nullptr;        // local plane 0 inside d_mesh_alloc
+    float* d_buf = nullptr;         // M_local floats: packed half spectrum -> Re IFFT(G)
     float* d_rho_keep = nullptr;    // optional copy of rho (introspection)
     float2 *d_twx = nullptr, *d_twy = nullptr, *d_twz = nullptr;
+    float* d_fx = nullptr;          // {scale, 1/scale} of the fixed-point density
     double* d_sums = nullptr;       // [0] sum a^2  [1] sum a  [2] particles outside the slab
+    double* d_tile_sums = nullptr;
+    unsigned* d_counters = nullptr; // [0] ticket [1] drifted particles [2] particles outside the slab [3] cells near the range limit
+    unsigned* h_counters = nullptr; // pinned copy of d_counters, refreshed asynchronously after every spread
     double* d_partials = nullptr;
     unsigned* d_ticket = nullptr;
     unsigned n_partials = 0;
     // state
     bool have_cv = false;
     unsigned last_N = 0;
-    bool keep_rho = false;
-    // optional per-stage timing (CUDA events on the caller's stream): boundaries between the stages below
+    bool keep_rho = false, keep_cells = false;
+    // optional per-stage timing (CUDA events on the caller's stream): ev[i] = start of stage i for i < 7, ev[7] = end of the
+    // cv pipeline, ev[8]/ev[9] = start/end of the gather
     bool profile = false;
-    cudaEvent_t ev[kNumStages + 2] = {};      // 0..10 stage starts of the cv pipeline (10 = its end), 11/12 gather start/end
+    cudaEvent_t ev[kNumStages + 2] = {};
     size_t M() const { return (size_t)g.nx * g.ny * g.nz; }
 };
 
@@ -85,16 +102,25 @@ template <class K> int set_smem(K kernel, size_t bytes) {
 }
 
 // ---- FFT launchers -----------------------------------------------------------------------------------
-// x pass over the local rows.  io: nullptr = in place; otherwise the packed all-to-all buffer (output of the
-// forward pass / input of the inverse pass), [part][row][kx in part] with parts of width kxl.
-template <int LC> int run_x(metad_mesh* p, bool inverse, float2* io, cudaStream_t st) {
+// x pass over the local rows.  io: nullptr = the plan's own buffer; otherwise the packed all-to-all buffer (output of
+// the forward pass / input of the inverse pass), [part][row][kx in part] with parts of width kxl.
+// Forward: consumes (and clears) the integer density; d_sums = (global) sums, d_ghost = received halo planes (slab).
+template <int LC> int run_x(metad_mesh* p, bool inverse, float2* io, const double* d_sums, const int* d_ghost, cudaStream_t st) {
     const size_t smem = sizeof(float2) * (LayoutRow::size(LC) + 2 * LC);
     const unsigned rows = p->g.ny * p->g.nz;
     float2* buf = reinterpret_cast<float2*>(p->d_buf);
     const unsigned lg_part = io ? ilog2(p->kxl) : ilog2(LC);
     if (!inverse) {
         int rc = set_smem(fft_x_fwd_kernel<LC>, smem); if (rc) return rc;
-        fft_x_fwd_kernel<LC><<<rows / kLines, kLines * LC / kE, smem, st>>>(buf, p->d_twx, io ? io : buf, lg_part, rows);
+        DensityIn in;
+        in.mesh = reinterpret_cast<int2*>(p->d_mesh_i);
+        in.d_fx = p->d_fx;
+        in.d_sums = d_sums;
+        in.inv_cells = 1.0 / ((double)p->g.nx * (double)p->g.ny * (double)p->nzg);
+        in.ghost = reinterpret_cast<const int2*>(d_ghost);
+        in.lgy = p->g.lgy; in.nz = p->g.nz;
+        in.rho_keep = p->keep_rho ? reinterpret_cast<float2*>(p->d_rho_keep) : nullptr;
+        fft_x_fwd_kernel<LC><<<rows / kLines, kLines * LC / kE, smem, st>>>(in, p->d_twx, io ? io : buf, lg_part, rows);
     } else {
         int rc = set_smem(fft_x_inv_kernel<LC>, smem); if (rc) return rc;
         fft_x_inv_kernel<LC><<<rows / kLines, kLines * LC / kE, smem, st>>>(buf, p->d_twx, io ? io : buf, lg_part, rows);
@@ -149,7 +175,6 @@ template <int L> int run_z(metad_mesh* p, float2* buf, unsigned row_len, unsigne
         default: set_error("cv.mesh: unsupported mesh dimension"); rc = METAD_ERR_UNSUPPORTED; \
     }
 
-// event i marks the START of stage i (10 = end of the cv pipeline, 11/12 = start/end of the gather)
 int mark(metad_mesh* p, int i, cudaStream_t st) {
     if (!p->profile) return METAD_OK;
     if (!p->ev[i]) METAD_CUDA(cudaEventCreate(&p->ev[i]));
@@ -161,31 +186,30 @@ int fft_pipeline(metad_mesh* p, unsigned N_global, double* d_cv, cudaStream_t st
     int rc = METAD_OK;
     float2* buf = reinterpret_cast<float2*>(p->d_buf);
     const unsigned nxh = p->g.nx / 2;
-    rc = mark(p, 5, st); if (rc) return rc;
-    METAD_DISPATCH_LEN(nxh, (run_x<LL>(p, false, nullptr, st))); if (rc) return rc;
-    rc = mark(p, 6, st); if (rc) return rc;
+    if (p->keep_rho && !p->d_rho_keep) METAD_CUDA(cudaMalloc(&p->d_rho_keep, sizeof(float) * p->M()));
+    rc = mark(p, 2, st); if (rc) return rc;
+    METAD_DISPATCH_LEN(nxh, (run_x<LL>(p, false, nullptr, p->d_sums, nullptr, st))); if (rc) return rc;
+    rc = mark(p, 3, st); if (rc) return rc;
     METAD_DISPATCH_LEN(p->g.ny, (run_y<LL>(p, false, buf, nxh, p->g.nz, st))); if (rc) return rc;
-    rc = mark(p, 7, st); if (rc) return rc;
+    rc = mark(p, 4, st); if (rc) return rc;
     METAD_DISPATCH_LEN(p->g.nz, (run_z<LL>(p, buf, nxh, 0, p->d_sums, N_global, d_cv, st))); if (rc) return rc;
-    rc = mark(p, 8, st); if (rc) return rc;
+    rc = mark(p, 5, st); if (rc) return rc;
     METAD_DISPATCH_LEN(p->g.ny, (run_y<LL>(p, true, buf, nxh, p->g.nz, st))); if (rc) return rc;
-    rc = mark(p, 9, st); if (rc) return rc;
-    METAD_DISPATCH_LEN(nxh, (run_x<LL>(p, true, nullptr, st))); if (rc) return rc;
-    rc = mark(p, 10, st); if (rc) return rc;
+    rc = mark(p, 6, st); if (rc) return rc;
+    METAD_DISPATCH_LEN(nxh, (run_x<LL>(p, true, nullptr, nullptr, nullptr, st))); if (rc) return rc;
+    rc = mark(p, 7, st); if (rc) return rc;
     return METAD_OK;
 }
 
 int ensure_capacity(metad_mesh* p, unsigned N) {
     if (N <= p->cap) return METAD_OK;
-    cudaFree(p->d_keys); cudaFree(p->d_ranks); cudaFree(p->d_perm); cudaFree(p->d_sorted); cudaFree(p->d_skey); cudaFree(p->d_slot);
-    p->d_keys = p->d_ranks = p->d_perm = p->d_skey = p->d_slot = nullptr; p->d_sorted = nullptr; p->cap = 0;
+    cudaFree(p->d_keys); cudaFree(p->d_ranks); cudaFree(p->d_perm);
+    p->d_keys = p->d_ranks = p->d_perm = nullptr; p->cap = 0;
+    p->order_valid = false;
     const unsigned cap = N + N / 16 + 1024;
     METAD_CUDA(cudaMalloc(&p->d_keys, sizeof(unsigned) * cap));
     METAD_CUDA(cudaMalloc(&p->d_ranks, sizeof(unsigned) * cap));
     METAD_CUDA(cudaMalloc(&p->d_perm, sizeof(unsigned) * cap));
-    METAD_CUDA(cudaMalloc(&p->d_skey, sizeof(unsigned) * cap));
-    METAD_CUDA(cudaMalloc(&p->d_slot, sizeof(unsigned) * cap));
-    METAD_CUDA(cudaMalloc(&p->d_sorted, sizeof(float4) * cap));
     p->cap = cap;
     return METAD_OK;
 }
@@ -195,34 +219,23 @@ int set_box(metad_mesh* p, const metad_box* box) {
         set_error("cv.mesh: triclinic boxes are not supported by the sm_100a mesh path yet");
         return METAD_ERR_UNSUPPORTED;
     }
-    Geom& g = p->g;
-    const unsigned n[3] = {g.nx, g.ny, g.nzg};       // the box is the GLOBAL box
-    for (int i = 0; i < 3; ++i) {
-        METAD_REQUIRE(box->L[i] > 0.0, "cv.mesh: box lengths must be positive");
-        g.L[i] = (float)box->L[i];
-        g.lo[i] = -(g.L[i] / 2.0f);
-        g.dlo[i] = -box->L[i] / 2.0;
-        g.dscale[i] = (double)n[i] / box->L[i];
-    }
+    for (int i = 0; i < 3; ++i) METAD_REQUIRE(box->L[i] > 0.0, "cv.mesh: box lengths must be positive");
+    geom_set_box(p->g, box->L);          // the box is the GLOBAL box
     return METAD_OK;
 }
 
-// cell order of this step + spread into padded tiles (d_scratch); sums -> p->d_sums
-int order_and_spread(metad_mesh* p, const float* d_postype, unsigned N, cudaStream_t stream) {
+// counting sort of the particles by tile-major cell key -> perm, tstart; fixed-point scale for the following calls
+int rebuild_order(metad_mesh* p, const float* d_postype, unsigned N, cudaStream_t stream) {
     const Geom& g = p->g;
     const size_t M = p->M();
     const int sms = device_sm_count();
-    int rc = ensure_capacity(p, N); if (rc) return rc;
-    METAD_CUDA(cudaMemsetAsync(p->d_sums, 0, 4 * sizeof(double), stream));
-    rc = mark(p, 0, stream); if (rc) return rc;
+    METAD_CUDA(cudaMemsetAsync(p->d_max_count, 0, sizeof(unsigned), stream));
     long nbp = ((long)N + kBinThreads * 4L - 1) / (kBinThreads * 4L);
     if (nbp > sms * 16L) nbp = sms * 16L;
-    if (N > 0) {
-        mesh_bin_kernel<<<(int)nbp, kBinThreads, 0, stream>>>((const float4*)d_postype, N, g, p->d_mode, p->d_keys, p->d_ranks, p->d_count,
-                                                             p->d_sums);
-        METAD_LAUNCH_CHECK();
-    }
-    rc = mark(p, 1, stream); if (rc) return rc;
+    if (nbp < 1) nbp = 1;
+    mesh_bin_kernel<<<(int)nbp, kBinThreads, 0, stream>>>((const float4*)d_postype, N, g, p->d_mode, p->ntypes, p->d_keys, p->d_ranks,
+                                                         p->d_count, p->d_max_count);
+    METAD_LAUNCH_CHECK();
     if (M % (16 * kScanThreads) == 0) {
         const unsigned nb_scan = (unsigned)(M / (16 * kScanThreads));
         scan_reduce_kernel<4><<<nb_scan, kScanThreads, 0, stream>>>((const uint4*)p->d_count, p->d_block_sums);
@@ -240,31 +253,60 @@ int order_and_spread(metad_mesh* p, const float* d_postype, unsigned N, cudaStre
         scan_apply_kernel<1><<<nb_scan, kScanThreads, 0, stream>>>((uint4*)p->d_count, p->d_block_sums, p->d_start, (unsigned)M);
         METAD_LAUNCH_CHECK();
     }
-    rc = mark(p, 2, stream); if (rc) return rc;
-    if (N > 0) {
-        mesh_place_kernel<<<(int)nbp, kBinThreads, 0, stream>>>(N, p->d_keys, p->d_ranks, p->d_start, p->d_slot);
-        METAD_LAUNCH_CHECK();
-        mesh_reorder_kernel<<<(int)nbp, kBinThreads, 0, stream>>>((const float4*)d_postype, N, p->d_mode, p->d_keys, p->d_start, p->d_slot,
-                                                                 p->d_sorted, p->d_perm, p->d_skey);
-        METAD_LAUNCH_CHECK();
-    }
-    rc = mark(p, 3, stream); if (rc) return rc;
-    if (g.lgT == 4)
-        mesh_spread_kernel<4><<<num_tiles(g), 256, 0, stream>>>(p->d_sorted, p->d_skey, p->d_start, g, p->d_scratch);
-    else
-        mesh_spread_kernel<3><<<num_tiles(g), 64, 0, stream>>>(p->d_sorted, p->d_skey, p->d_start, g, p->d_scratch);
+    mesh_place_kernel<<<(int)nbp, kBinThreads, 0, stream>>>(N, p->d_keys, p->d_ranks, p->d_start, p->d_perm, num_tiles(g), 3 * g.lgT,
+                                                           p->d_tstart);
     METAD_LAUNCH_CHECK();
-    if (p->keep_rho && !p->d_rho_keep) METAD_CUDA(cudaMalloc(&p->d_rho_keep, sizeof(float) * M));
-    rc = mark(p, 4, stream); if (rc) return rc;
-    long nb = (long)((M + 255) / 256);
-    if (nb > sms * 32L) nb = sms * 32L;
-    mesh_merge_kernel<<<(int)nb, 256, 0, stream>>>(p->d_scratch, g, p->d_sums, p->d_buf, (p->keep_rho && !g.slab) ? p->d_rho_keep : nullptr);
+    mesh_fx_scale_kernel<<<1, 1, 0, stream>>>(p->d_max_count, p->amax, p->d_fx);
     METAD_LAUNCH_CHECK();
+    p->order_valid = true;
+    p->order_N = N;
+    p->calls_since_rebuild = 0;
+    ++p->n_rebuilds;
     return METAD_OK;
 }
 
-int launch_gather(metad_mesh* p, const float* d_ghost, float* d_force, unsigned N_global, const metad_box* box, const double* d_bias,
-                  cudaStream_t stream) {
+template <int LGT> size_t tile_smem_bytes() { return sizeof(int) * (size_t)((1 << LGT) + 2 * kHalo) * ((1 << LGT) + 2 * kHalo) * ((1 << LGT) + 2 * kHalo); }
+
+// tile order of this call (rebuilt if needed) + spread into the integer mesh; sums -> p->d_sums
+int order_and_spread(metad_mesh* p, const float* d_postype, unsigned N, cudaStream_t stream) {
+    const Geom& g = p->g;
+    int rc = ensure_capacity(p, N); if (rc) return rc;
+    rc = mark(p, 0, stream); if (rc) return rc;
+    if (N == 0) {
+        METAD_CUDA(cudaMemsetAsync(p->d_sums, 0, 4 * sizeof(double), stream));
+        rc = mark(p, 1, stream); if (rc) return rc;
+        return METAD_OK;
+    }
+    // drifted particles / range warnings reported by an earlier spread (asynchronous copy: may lag by a call)
+    const bool drift = p->h_counters[1] > N / 256u || p->h_counters[3] > 0;
+    if (!p->order_valid || p->order_N != N || p->calls_since_rebuild >= p->period || drift) {
+        rc = rebuild_order(p, d_postype, N, stream); if (rc) return rc;
+        p->h_counters[1] = p->h_counters[3] = 0;
+    }
+    ++p->calls_since_rebuild;
+    rc = mark(p, 1, stream); if (rc) return rc;
+    METAD_CUDA(cudaMemsetAsync(p->d_counters + 1, 0, 3 * sizeof(unsigned), stream));
+    SpreadOut out;
+    out.mesh = p->d_mesh_i;
+    out.tile_sums = p->d_tile_sums;
+    out.sums = p->d_sums;
+    out.counters = p->d_counters;
+    out.keys = p->keep_cells ? p->d_keys : nullptr;
+    if (g.lgT == 4) {
+        rc = set_smem(mesh_spread_kernel<4>, tile_smem_bytes<4>()); if (rc) return rc;
+        mesh_spread_kernel<4><<<num_tiles(g), kSpreadThreads, tile_smem_bytes<4>(), stream>>>((const float4*)d_postype, p->d_perm, p->d_tstart, g,
+                                                                                           p->d_mode, p->d_fx, out);
+    } else {
+        mesh_spread_kernel<3><<<num_tiles(g), kSpreadThreads, tile_smem_bytes<3>(), stream>>>((const float4*)d_postype, p->d_perm, p->d_tstart, g,
+                                                                                           p->d_mode, p->d_fx, out);
+    }
+    METAD_LAUNCH_CHECK();
+    METAD_CUDA(cudaMemcpyAsync(p->h_counters, p->d_counters, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+    return METAD_OK;
+}
+
+int launch_gather(metad_mesh* p, const float* d_postype, const float* d_ghost, float* d_force, unsigned N_global, const metad_box* box,
+                  const double* d_bias, cudaStream_t stream) {
     const Geom& g = p->g;
     // reciprocal lattice vectors of the (orthorhombic) box without 2 pi, times the mesh dimensions (:761-769, :852-854)
     ForceParams fp;
@@ -273,15 +315,17 @@ int launch_gather(metad_mesh* p, const float* d_ghost, float* d_force, unsigned 
     fp.nb2[1] = (float)((double)g.ny / box->L[1]);
     fp.nb3[2] = (float)((double)g.nzg / box->L[2]);
     fp.two_over_n = 2.0 / (double)N_global;
-    int rc = mark(p, 11, stream); if (rc) return rc;
-    if (g.lgT == 4)
-        mesh_gather_kernel<4><<<num_tiles(g), kGatherThreads, 0, stream>>>(p->d_sorted, p->d_perm, p->d_skey, p->d_start, g, p->d_buf, d_ghost,
-                                                                         fp, d_bias, (float4*)d_force);
-    else
-        mesh_gather_kernel<3><<<num_tiles(g), kGatherThreads, 0, stream>>>(p->d_sorted, p->d_perm, p->d_skey, p->d_start, g, p->d_buf, d_ghost,
-                                                                         fp, d_bias, (float4*)d_force);
+    int rc = mark(p, 8, stream); if (rc) return rc;
+    if (g.lgT == 4) {
+        rc = set_smem(mesh_gather_kernel<4>, tile_smem_bytes<4>()); if (rc) return rc;
+        mesh_gather_kernel<4><<<num_tiles(g), kGatherThreads, tile_smem_bytes<4>(), stream>>>((const float4*)d_postype, p->d_perm, p->d_tstart, g,
+                                                                                           p->d_mode, p->d_buf, d_ghost, fp, d_bias, (float4*)d_force);
+    } else {
+        mesh_gather_kernel<3><<<num_tiles(g), kGatherThreads, tile_smem_bytes<3>(), stream>>>((const float4*)d_postype, p->d_perm, p->d_tstart, g,
+                                                                                           p->d_mode, p->d_buf, d_ghost, fp, d_bias, (float4*)d_force);
+    }
     METAD_LAUNCH_CHECK();
-    return mark(p, 12, stream);
+    return mark(p, 9, stream);
 }
 
 int create_common(metad_mesh** out, unsigned nx, unsigned ny, unsigned nzg, unsigned n_ranks, unsigned rank, int ntypes,
@@ -316,10 +360,14 @@ int create_common(metad_mesh** out, unsigned nx, unsigned ny, unsigned nzg, unsi
     p->ntypes = ntypes;
     std::vector<float> m(ntypes);
     for (int i = 0; i < ntypes; ++i) m[i] = (float)mode[i];
-    const unsigned P = padded_edge(g);
+    p->amax = 0.f;
+    for (float v : m) p->amax = fmaxf(p->amax, fabsf(v));
     const unsigned nb_scan = (unsigned)(M / (4 * kScanThreads));
     const unsigned nby = (ny / 2 + 1 + kLines / 2 - 1) / (kLines / 2);
     p->n_partials = nby + (p->kxl / kLines) * ny;
+    const size_t plane = (size_t)nx * ny;
+    const size_t mesh_ints = M + (slab ? 2 * plane : 0);
+    const float fx_init[2] = {1.0f, 1.0f};
     int rc = METAD_OK;
     auto fail = [&](cudaError_t e, const char* what) { rc = cuda_fail(e, what, __FILE__, __LINE__); };
     cudaError_t e;
@@ -330,13 +378,28 @@ int create_common(metad_mesh** out, unsigned nx, unsigned ny, unsigned nzg, unsi
     TRY(cudaMemset(p->d_count, 0, sizeof(unsigned) * M));
     TRY(cudaMalloc(&p->d_start, sizeof(unsigned) * (M + 4)));
     TRY(cudaMalloc(&p->d_block_sums, sizeof(unsigned) * (nb_scan + 1)));
-    TRY(cudaMalloc(&p->d_scratch, sizeof(float) * (size_t)num_tiles(g) * P * P * P));
+    TRY(cudaMalloc(&p->d_tstart, sizeof(unsigned) * (num_tiles(g) + 1)));
+    TRY(cudaMemset(p->d_tstart, 0, sizeof(unsigned) * (num_tiles(g) + 1)));
+    TRY(cudaMalloc(&p->d_max_count, sizeof(unsigned)));
+    TRY(cudaMalloc(&p->d_mesh_alloc, sizeof(int) * mesh_ints));
+    TRY(cudaMemset(p->d_mesh_alloc, 0, sizeof(int) * mesh_ints));
     TRY(cudaMalloc(&p->d_buf, sizeof(float) * M));
+    TRY(cudaMalloc(&p->d_fx, sizeof(float) * 2));
+    TRY(cudaMemcpy(p->d_fx, fx_init, sizeof fx_init, cudaMemcpyHostToDevice));
     TRY(cudaMalloc(&p->d_sums, sizeof(double) * 4));
+    TRY(cudaMemset(p->d_sums, 0, sizeof(double) * 4));
+    TRY(cudaMalloc(&p->d_tile_sums, sizeof(double) * 2 * num_tiles(g)));
+    TRY(cudaMalloc(&p->d_counters, sizeof(unsigned) * 4));
+    TRY(cudaMemset(p->d_counters, 0, sizeof(unsigned) * 4));
+    TRY(cudaMallocHost(&p->h_counters, sizeof(unsigned) * 4));
     TRY(cudaMalloc(&p->d_partials, sizeof(double) * p->n_partials));
     TRY(cudaMalloc(&p->d_ticket, sizeof(unsigned)));
     TRY(cudaMemset(p->d_ticket, 0, sizeof(unsigned)));
 #undef TRY
+    if (rc == METAD_OK) {
+        memset(p->h_counters, 0, sizeof(unsigned) * 4);
+        p->d_mesh_i = p->d_mesh_alloc + (slab ? plane : 0);
+    }
     if (rc == METAD_OK) rc = upload_twiddles(&p->d_twx, nx);
     if (rc == METAD_OK) rc = upload_twiddles(&p->d_twy, ny);
     if (rc == METAD_OK) rc = upload_twiddles(&p->d_twz, nzg);
@@ -359,8 +422,10 @@ extern "C" int metad_mesh_slab_create(metad_mesh** out, unsigned nx, unsigned ny
 
 extern "C" int metad_mesh_destroy(metad_mesh* p) {
     if (!p) return METAD_OK;
-    cudaFree(p->d_mode); cudaFree(p->d_keys); cudaFree(p->d_ranks); cudaFree(p->d_perm); cudaFree(p->d_sorted); cudaFree(p->d_skey); cudaFree(p->d_slot);
-    cudaFree(p->d_count); cudaFree(p->d_start); cudaFree(p->d_block_sums); cudaFree(p->d_scratch); cudaFree(p->d_buf);
+    cudaFree(p->d_mode); cudaFree(p->d_keys); cudaFree(p->d_ranks); cudaFree(p->d_perm);
+    cudaFree(p->d_count); cudaFree(p->d_start); cudaFree(p->d_block_sums); cudaFree(p->d_tstart); cudaFree(p->d_max_count);
+    cudaFree(p->d_mesh_alloc); cudaFree(p->d_buf); cudaFree(p->d_fx); cudaFree(p->d_tile_sums); cudaFree(p->d_counters);
+    if (p->h_counters) cudaFreeHost(p->h_counters);
     cudaFree(p->d_rho_keep); cudaFree(p->d_twx); cudaFree(p->d_twy); cudaFree(p->d_twz); cudaFree(p->d_sums);
     cudaFree(p->d_partials); cudaFree(p->d_ticket);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
@@ -394,38 +459,41 @@ extern "C" int metad_mesh_forces(metad_mesh* p, const float* d_postype, float* d
     }
     if (N == 0) return METAD_OK;
     METAD_REQUIRE(d_postype && d_force, "metad_mesh_forces: null particle arrays");
-    return launch_gather(p, nullptr, d_force, N_global, box, d_bias, stream);
+    return launch_gather(p, d_postype, nullptr, d_force, N_global, box, d_bias, stream);
 }
 
 // ---- z-slab stages ------------------------------------------------------------------------------------
 extern "C" int metad_mesh_slab_spread(metad_mesh* p, const float* d_postype, unsigned N_local, const metad_box* global_box,
-                                      double* d_sums, float* d_ghost_send, metad_stream_t stream) {
+                                      double* d_sums, int* d_ghost_send, metad_stream_t stream) {
     METAD_REQUIRE(p && global_box && d_sums && d_ghost_send, "metad_mesh_slab_spread: null argument");
     METAD_REQUIRE(p->g.slab, "metad_mesh_slab_spread: not a slab plan");
     METAD_REQUIRE(N_local == 0 || d_postype, "metad_mesh_slab_spread: null positions");
     int rc = set_box(p, global_box); if (rc) return rc;
     p->have_cv = false;
     rc = order_and_spread(p, d_postype, N_local, stream); if (rc) return rc;
-    const unsigned plane = p->g.nx * p->g.ny;
-    mesh_ghost_extract_kernel<<<(2 * plane + 255) / 256, 256, 0, stream>>>(p->d_scratch, p->g, d_ghost_send);
-    METAD_LAUNCH_CHECK();
+    // the two ghost planes (global planes z0-1 and z0+nz) leave for the neighbours and are cleared for the next call
+    const size_t plane = (size_t)p->g.nx * p->g.ny;
+    int* below = p->d_mesh_alloc;
+    int* above = p->d_mesh_alloc + plane * (p->g.nz + 1);
+    const size_t msg = plane + 4;        // a halo message: the plane, then 4 ints of which the first carries the bits of 1/scale
+    METAD_CUDA(cudaMemcpyAsync(d_ghost_send, below, plane * sizeof(int), cudaMemcpyDeviceToDevice, stream));
+    METAD_CUDA(cudaMemcpyAsync(d_ghost_send + plane, p->d_fx + 1, sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    METAD_CUDA(cudaMemcpyAsync(d_ghost_send + msg, above, plane * sizeof(int), cudaMemcpyDeviceToDevice, stream));
+    METAD_CUDA(cudaMemcpyAsync(d_ghost_send + msg + plane, p->d_fx + 1, sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    METAD_CUDA(cudaMemsetAsync(below, 0, plane * sizeof(int), stream));
+    METAD_CUDA(cudaMemsetAsync(above, 0, plane * sizeof(int), stream));
     METAD_CUDA(cudaMemcpyAsync(d_sums, p->d_sums, 3 * sizeof(double), cudaMemcpyDeviceToDevice, stream));
     p->last_N = N_local;
     return METAD_OK;
 }
 
-extern "C" int metad_mesh_slab_fft_x(metad_mesh* p, const float* d_ghost_recv, const double* d_sums_global, float* d_send,
+extern "C" int metad_mesh_slab_fft_x(metad_mesh* p, const int* d_ghost_recv, const double* d_sums_global, float* d_send,
                                      metad_stream_t stream) {
     METAD_REQUIRE(p && d_ghost_recv && d_sums_global && d_send, "metad_mesh_slab_fft_x: null argument");
     METAD_REQUIRE(p->g.slab, "metad_mesh_slab_fft_x: not a slab plan");
-    const size_t M = p->M();
-    if (p->keep_rho && !p->d_rho_keep) METAD_CUDA(cudaMalloc(&p->d_rho_keep, sizeof(float) * M));
-    long nb = (long)((M + 255) / 256);
-    if (nb > device_sm_count() * 32L) nb = device_sm_count() * 32L;
-    mesh_add_ghost_kernel<<<(int)nb, 256, 0, stream>>>(p->d_buf, p->g, d_ghost_recv, d_sums_global, p->keep_rho ? p->d_rho_keep : nullptr);
-    METAD_LAUNCH_CHECK();
+    if (p->keep_rho && !p->d_rho_keep) METAD_CUDA(cudaMalloc(&p->d_rho_keep, sizeof(float) * p->M()));
     int rc = METAD_OK;
-    METAD_DISPATCH_LEN(p->g.nx / 2, (run_x<LL>(p, false, reinterpret_cast<float2*>(d_send), stream)));
+    METAD_DISPATCH_LEN(p->g.nx / 2, (run_x<LL>(p, false, reinterpret_cast<float2*>(d_send), d_sums_global, d_ghost_recv, stream)));
     return rc;
 }
 
@@ -446,7 +514,7 @@ extern "C" int metad_mesh_slab_fft_x_inv(metad_mesh* p, const float* d_recv, flo
     METAD_REQUIRE(p && d_recv, "metad_mesh_slab_fft_x_inv: null argument");
     METAD_REQUIRE(p->g.slab, "metad_mesh_slab_fft_x_inv: not a slab plan");
     int rc = METAD_OK;
-    METAD_DISPATCH_LEN(p->g.nx / 2, (run_x<LL>(p, true, reinterpret_cast<float2*>(const_cast<float*>(d_recv)), stream)));
+    METAD_DISPATCH_LEN(p->g.nx / 2, (run_x<LL>(p, true, reinterpret_cast<float2*>(const_cast<float*>(d_recv)), nullptr, nullptr, stream)));
     if (rc) return rc;
     const size_t plane = (size_t)p->g.nx * p->g.ny;
     if (d_planes_out) {     // first and last local plane of Re IFFT(G): the neighbours' halo planes
@@ -468,7 +536,7 @@ extern "C" int metad_mesh_slab_forces(metad_mesh* p, const float* d_ghost_inv, c
     }
     if (N_local == 0) return METAD_OK;
     METAD_REQUIRE(d_postype && d_force, "metad_mesh_slab_forces: null particle arrays");
-    return launch_gather(p, d_ghost_inv, d_force, N_global, global_box, d_bias, stream);
+    return launch_gather(p, d_postype, d_ghost_inv, d_force, N_global, global_box, d_bias, stream);
 }
 
 extern "C" int metad_mesh_get(metad_mesh* p, int which, void* h_out) {
@@ -478,6 +546,7 @@ extern "C" int metad_mesh_get(metad_mesh* p, int which, void* h_out) {
     switch (which) {
         case 0: {
             if (p->last_N == 0) return METAD_OK;
+            if (!p->keep_cells) { set_error("metad_mesh_get: enable metad_mesh_set(p, 3, 1) before the spread to keep the cell indices"); return METAD_ERR_STATE; }
             std::vector<unsigned> keys(p->last_N);
             METAD_CUDA(cudaMemcpy(keys.data(), p->d_keys, sizeof(unsigned) * p->last_N, cudaMemcpyDeviceToHost));
             int* out = (int*)h_out;
@@ -501,10 +570,21 @@ extern "C" int metad_mesh_get(metad_mesh* p, int which, void* h_out) {
             return METAD_OK;
         case 4: {
             // per-stage milliseconds of the last metad_mesh_cv + metad_mesh_forces pair (float[kNumStages])
-            if (!p->profile || !p->ev[0] || !p->ev[10] || !p->ev[12]) { set_error("metad_mesh_get: profiling is off (metad_mesh_set(p, 2, 1))"); return METAD_ERR_STATE; }
+            if (!p->profile || !p->ev[0] || !p->ev[7] || !p->ev[9]) { set_error("metad_mesh_get: profiling is off (metad_mesh_set(p, 2, 1))"); return METAD_ERR_STATE; }
             float* out = (float*)h_out;
-            for (int i = 0; i < 10; ++i) METAD_CUDA(cudaEventElapsedTime(out + i, p->ev[i], p->ev[i + 1]));
-            METAD_CUDA(cudaEventElapsedTime(out + 10, p->ev[11], p->ev[12]));
+            for (int i = 0; i < 7; ++i) METAD_CUDA(cudaEventElapsedTime(out + i, p->ev[i], p->ev[i + 1]));
+            METAD_CUDA(cudaEventElapsedTime(out + 7, p->ev[8], p->ev[9]));
+            return METAD_OK;
+        }
+        case 5: {
+            // statistics, double[6]: rebuilds of the tile order so far; of the LAST spread: particles that took the direct
+            // path, particles outside the slab, cells past half of the fixed-point range; fixed-point scale; calls since rebuild
+            double* out = (double*)h_out;
+            unsigned c[4];
+            float fx[2];
+            METAD_CUDA(cudaMemcpy(c, p->d_counters, sizeof c, cudaMemcpyDeviceToHost));
+            METAD_CUDA(cudaMemcpy(fx, p->d_fx, sizeof fx, cudaMemcpyDeviceToHost));
+            out[0] = (double)p->n_rebuilds; out[1] = c[1]; out[2] = c[2]; out[3] = c[3]; out[4] = fx[0]; out[5] = p->calls_since_rebuild;
             return METAD_OK;
         }
         default:
@@ -516,9 +596,13 @@ extern "C" int metad_mesh_get(metad_mesh* p, int which, void* h_out) {
 extern "C" int metad_mesh_set(metad_mesh* p, int key, long value) {
     METAD_REQUIRE(p, "metad_mesh_set: null plan");
     switch (key) {
-        case 0: return METAD_OK;                       // resort period: the order is rebuilt every call in this version
+        case 0:                                        // rebuild period of the tile order (calls); 0 = rebuild now
+            if (value <= 0) p->order_valid = false;
+            else p->period = (unsigned)value;
+            return METAD_OK;
         case 1: p->keep_rho = value != 0; return METAD_OK;
         case 2: p->profile = value != 0; return METAD_OK;
+        case 3: p->keep_cells = value != 0; return METAD_OK;
         default: set_error("metad_mesh_set: unknown key"); return METAD_ERR_INVALID;
     }
 }

@@ -79,13 +79,30 @@ template <int TWL> __device__ __forceinline__ void load_twiddles(float2* s_tw, c
 }
 
 // ---------------------------------------------------------------------------------------------------
-// x pass, forward (R2C): 16 rows per CTA, row = y + ny*z
+// x pass, forward (R2C): 16 rows per CTA, row = y + ny*z.  The input is the fixed-point density accumulated by the
+// spread (mesh_kernels.cuh): it is converted to float, the mean density is removed (DC removal, see mesh.cu) and the
+// accumulator is cleared for the next call, all inside this sweep.
 // ---------------------------------------------------------------------------------------------------
+struct DensityIn {
+    int2* mesh;             // integer density of the local planes, row-major [z][y][x] (read, then zeroed)
+    const float* d_fx;      // device: {scale, 1/scale} of the fixed-point density
+    const double* d_sums;   // device: [1] = (global) sum of the mode coefficients -> mean density
+    double inv_cells;       // 1 / (global number of mesh cells)
+    const int2* ghost;      // z slab: the two halo messages received from the neighbours, each ny*nx ints of fixed-point density
+                            // followed by 4 ints of which the first holds the bits of the sender's 1/scale; message [0] is
+                            // added to the first local plane, [1] to the last; nullptr if unsharded
+    unsigned lgy, nz;       // log2(ny), local planes
+    float2* rho_keep;       // optional: float copy of the density (before the mean is removed), or nullptr
+};
+
+// density of mesh cell pair `v` (+ ghost contribution) as float: value = v / scale
+MHD float2 density_to_float(int2 v, float inv_scale) { return make_float2((float)v.x * inv_scale, (float)v.y * inv_scale); }
+
 template <int LC>
 __global__ void __launch_bounds__(kLines * LC / kE)
-fft_x_fwd_kernel(float2* buf, const float2* __restrict__ g_tw /* length 2*LC */, float2* out,
+fft_x_fwd_kernel(DensityIn in, const float2* __restrict__ g_tw /* length 2*LC */, float2* out,
                  unsigned lg_part /* log2 of the kx pencil width */, unsigned rows_total) {
-    // out == buf, lg_part = log2(LC): plain in-place transform.  Sharded: out = send buffer laid out [part][row][kx in part],
+    // lg_part = log2(LC): out is the plain [row][kx] buffer.  Sharded: out = send buffer laid out [part][row][kx in part],
     // i.e. already packed for the slab -> pencil all-to-all.
     extern __shared__ float2 smem[];
     float2* tile = smem;
@@ -93,9 +110,52 @@ fft_x_fwd_kernel(float2* buf, const float2* __restrict__ g_tw /* length 2*LC */,
     const int nthr = kLines * LC / kE;
     const size_t row0 = (size_t)blockIdx.x * kLines;
     load_twiddles<2 * LC>(s_tw, g_tw);
-    for (int idx = threadIdx.x; idx < kLines * LC; idx += nthr) {
+    const float inv_scale = __ldg(in.d_fx + 1);
+    const float mean = (float)(in.d_sums[1] * in.inv_cells);
+    const unsigned ny = 1u << in.lgy;
+    // all kE loads of a thread are issued before the accumulator is cleared (the stores alias the loads)
+    int2 vin[kE];
+#pragma unroll
+    for (int q = 0; q < kE; ++q) {
+        const int idx = threadIdx.x + q * nthr;
+        vin[q] = in.mesh[(row0 + idx / LC) * LC + idx % LC];
+    }
+#pragma unroll
+    for (int q = 0; q < kE; ++q) {
+        const int idx = threadIdx.x + q * nthr;
+        in.mesh[(row0 + idx / LC) * LC + idx % LC] = make_int2(0, 0);
+    }
+#pragma unroll
+    for (int q = 0; q < kE; ++q) {
+        const int idx = threadIdx.x + q * nthr;
         const int w = idx / LC, l = idx % LC;
-        tile[LayoutRow::addr(w, l, LC)] = buf[(row0 + w) * LC + l];
+        const size_t row = row0 + w;
+        int2 v = vin[q];
+        float2 r;
+        if (in.ghost) {
+            // ranks choose their fixed-point scales independently: equal scales (the common case) add as integers, which
+            // reproduces the unsharded density bit for bit; different scales add as floats
+            const unsigned z = (unsigned)(row >> in.lgy), y = (unsigned)row & (ny - 1);
+            const size_t msg = (size_t)ny * LC + 2;          // int2 elements per message
+            float2 extra = make_float2(0.f, 0.f);
+            if (z == 0) {
+                const int2 a = __ldg(in.ghost + (size_t)y * LC + l);
+                const float gs = __int_as_float(__ldg(&in.ghost[(size_t)ny * LC].x));
+                if (gs == inv_scale) { v.x += a.x; v.y += a.y; } else { extra.x += (float)a.x * gs; extra.y += (float)a.y * gs; }
+            }
+            if (z == in.nz - 1) {
+                const int2 a = __ldg(in.ghost + msg + (size_t)y * LC + l);
+                const float gs = __int_as_float(__ldg(&in.ghost[msg + (size_t)ny * LC].x));
+                if (gs == inv_scale) { v.x += a.x; v.y += a.y; } else { extra.x += (float)a.x * gs; extra.y += (float)a.y * gs; }
+            }
+            r = density_to_float(v, inv_scale);
+            r.x += extra.x; r.y += extra.y;
+        } else {
+            r = density_to_float(v, inv_scale);
+        }
+        if (in.rho_keep) in.rho_keep[row * LC + l] = r;
+        r.x -= mean; r.y -= mean;
+        tile[LayoutRow::addr(w, l, LC)] = r;
     }
     __syncthreads();
     const int w = threadIdx.x & (kLines - 1), t = threadIdx.x / kLines;

@@ -3,20 +3,25 @@
 // Reference behaviour restated (CPU path = parity target): OrderParameterMesh.cc:517-640 (assignParticles),
 // :457-483 (TSC weights), :749-864 (interpolateForces).  Reference GPU kernels replaced:
 // gpu_bin_particles_kernel / gpu_assign_binned_particles_to_scratch_kernel / gpu_reduce_scratch_kernel /
-// gpu_compute_forces_kernel (OrderParameterMeshGPU.cu:90-364, 566-769): non-deterministic atomicInc binning with
-// an overflow-retry loop, a 27x scratch mesh, texture gathers.
+// gpu_compute_forces_kernel (OrderParameterMeshGPU.cu:90-364, 566-769): per-step atomicInc binning with an
+// overflow-retry loop, a 27x float scratch mesh, texture gathers.
 //
-// Here: particles are counting-sorted (stable: ties keep the input order) by a TILE-MAJOR cell key (tile of T^3
-// cells, T = 8 or 16), so that
-//   * spreading is atomics-free: one thread per cell COLUMN of a tile walks the column in z with the 3x9 partial
-//     sums of three planes in registers; columns exchange their x,y taps through nine write-once "replica" planes
-//     in shared memory (no read-modify-write, one barrier per plane); every tile is flushed as one contiguous
-//     padded tile and a merge pass sums the <= 8 overlapping padded tiles per cell in a fixed order.  Summation
-//     orders are fixed, so results are bitwise reproducible;
-//   * force interpolation is thread-per-particle over a contiguous particle range per tile, reading a
-//     shared-memory tile of Re(IFFT(G)) with halo.
+// Design (measured on B200, bench_micro/spread_bench.cu + profiles/):
+//   * The density is accumulated in 32-bit FIXED POINT.  Integer addition is associative, so the mesh is bitwise
+//     independent of the order in which particles are processed (any particle order, any tile assignment, any
+//     number of ranks) -- and sm_100a has a native shared-memory integer atomic (ATOMS.ADD), which costs nothing
+//     next to the per-particle arithmetic, whereas float atomics are CAS loops (3x slower for the whole kernel).
+//   * Particles are visited through a TILE ORDER: a permutation that lists the particles tile by tile (T^3 cells,
+//     T = 8 or 16).  The order is rebuilt only every few calls (counting sort, amortised): a CTA owns one tile plus a
+//     halo of H = 2 cells in shared memory, and every particle's cell is recomputed from its CURRENT position each
+//     call, so a stale order is still exact -- a particle that drifted out of its padded tile falls back to global
+//     atomics and is counted (the count triggers the next rebuild).
+//   * The padded tile is flushed with red.global.add.s32 into the integer mesh; the x FFT pass converts it to float,
+//     removes the mean density and clears it for the next call.
+//   * Force interpolation: one CTA per tile, shared-memory tile of Re IFFT(G) with halo, one thread per particle.
 // Cell indices are computed with non-contracted IEEE fp32 operations and are bit-exact against the reference's
-// single-precision arithmetic; in-cell offsets are evaluated in fp64 (they only need to be accurate).
+// single-precision arithmetic; in-cell offsets are evaluated in compensated fp32 (error < 1e-7 cell) against the
+// double-precision box.
 #pragma once
 #include "common.cuh"
 
@@ -27,6 +32,8 @@
 namespace metad {
 namespace mesh {
 
+constexpr int kHalo = 2;          // halo cells of a padded tile: 1 for the TSC stencil + 1 of drift tolerance
+
 struct Geom {
     unsigned nx, ny, nz;        // mesh points of the LOCAL mesh (powers of two); nz = planes of this z slab
     unsigned lgx, lgy, lgz;     // log2 of the above
@@ -36,7 +43,12 @@ struct Geom {
     unsigned ntx, nty, ntz;     // tiles per dimension (powers of two)
     unsigned lgtx, lgty, lgtz;  // log2 of the above
     float lo[3], L[3];          // single-precision box (HOOMD SINGLE_PRECISION BoxDim)
-    double dlo[3], dscale[3];   // fp64: lo and n/L for the in-cell offset
+    double dlo[3], dscale[3];   // fp64: lo and n/L of the double-precision box (reference form of the in-cell offset)
+    // the same two numbers as unevaluated float pairs: -lo = hl_hi + hl_lo, n/L = c_hi + c_lo
+    float hl_hi[3], hl_lo[3], c_hi[3], c_lo[3];
+    float fn[3];                // (float) global mesh dimensions
+    float rcpL[3];              // correctly rounded 1/L (single precision) for the exact constant division below
+    unsigned fast_div;          // 1: (x - lo)/L is evaluated as Markstein's FMA sequence (bit-identical to IEEE division)
 };
 
 MHD void geom_set_dims(Geom& g, unsigned nx, unsigned ny, unsigned nz, unsigned lgT) {
@@ -48,10 +60,41 @@ MHD void geom_set_dims(Geom& g, unsigned nx, unsigned ny, unsigned nz, unsigned 
     g.lgtx = g.lgx - lgT; g.lgty = g.lgy - lgT; g.lgtz = g.lgz - lgT;
     g.ntx = 1u << g.lgtx; g.nty = 1u << g.lgty; g.ntz = 1u << g.lgtz;
 }
+// box: L[] in double (the GLOBAL box); n[] = global mesh dimensions
+inline void geom_set_box(Geom& g, const double* Ld) {
+    const unsigned n[3] = {g.nx, g.ny, g.nzg};
+    for (int i = 0; i < 3; ++i) {
+        g.L[i] = (float)Ld[i];
+        g.lo[i] = -(g.L[i] / 2.0f);
+        g.dlo[i] = -Ld[i] / 2.0;
+        g.dscale[i] = (double)n[i] / Ld[i];
+        const double hl = Ld[i] / 2.0;
+        g.hl_hi[i] = (float)hl; g.hl_lo[i] = (float)(hl - (double)g.hl_hi[i]);
+        g.c_hi[i] = (float)g.dscale[i]; g.c_lo[i] = (float)(g.dscale[i] - (double)g.c_hi[i]);
+        g.fn[i] = (float)n[i];
+    }
+    // correctly rounded reciprocal of the single-precision box length: the candidate next to (float)(1/L) with the
+    // smallest exact residual |1 - r L| (the product of two floats is exact in double)
+    g.fast_div = 1;
+    for (int i = 0; i < 3; ++i) {
+        const float L = g.L[i];
+        float best = (float)(1.0 / (double)L);
+        double be = fabs(1.0 - (double)best * (double)L);
+        const float cand[2] = {nextafterf(best, 0.0f), nextafterf(best, 3.0e38f)};
+        for (float c : cand) {
+            const double e = fabs(1.0 - (double)c * (double)L);
+            if (e < be) { be = e; best = c; }
+        }
+        g.rcpL[i] = best;
+        // Markstein's theorem excludes divisors whose significand is all ones; also keep away from tiny / huge boxes
+        unsigned bits; memcpy(&bits, &L, 4);
+        if ((bits & 0x7fffffu) == 0x7fffffu || !(L > 1e-10f && L < 1e10f)) g.fast_div = 0;
+    }
+}
 
 MHD unsigned tile_edge(const Geom& g) { return 1u << g.lgT; }
 MHD unsigned cells_per_tile(const Geom& g) { return 1u << (3 * g.lgT); }
-MHD unsigned padded_edge(const Geom& g) { return (1u << g.lgT) + 2; }
+MHD unsigned padded_edge(const Geom& g) { return (1u << g.lgT) + 2 * kHalo; }
 MHD unsigned num_tiles(const Geom& g) { return 1u << (g.lgtx + g.lgty + g.lgtz); }
 MHD unsigned tile_index(unsigned tx, unsigned ty, unsigned tz, const Geom& g) { return (((tz << g.lgty) + ty) << g.lgtx) + tx; }
 MHD void tile_coords(unsigned tile, const Geom& g, unsigned& tx, unsigned& ty, unsigned& tz) {
@@ -60,12 +103,27 @@ MHD void tile_coords(unsigned tile, const Geom& g, unsigned& tx, unsigned& ty, u
     tz = tile >> (g.lgtx + g.lgty);
 }
 
+MHD int f2i_bits(float f) {
+#ifdef __CUDA_ARCH__
+    return __float_as_int(f);
+#else
+    int i; memcpy(&i, &f, 4); return i;
+#endif
+}
+
 // non-contracted IEEE single-precision helpers (host: plain ops, the emulation is built without FMA contraction)
 MHD float f_sub(float a, float b) {
 #ifdef __CUDA_ARCH__
     return __fsub_rn(a, b);
 #else
     volatile float r = a - b; return r;
+#endif
+}
+MHD float f_add(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fadd_rn(a, b);
+#else
+    volatile float r = a + b; return r;
 #endif
 }
 MHD float f_div(float a, float b) {
@@ -82,19 +140,47 @@ MHD float f_mul(float a, float b) {
     volatile float r = a * b; return r;
 #endif
 }
+MHD float f_fma(float a, float b, float c) {
+#ifdef __CUDA_ARCH__
+    return __fmaf_rn(a, b, c);
+#else
+    return fmaf(a, b, c);
+#endif
+}
 
 // cell coordinate along one axis: OrderParameterMesh.cc:543-561 with BoxDim::makeFraction = (x - lo)/L.
 //   f = (x - lo)/L ; r = f*n ; i = (int) r (truncation) ; i == n -> 0
-// Out-of-box input (which HOOMD never hands over) is folded back periodically instead of indexing out of range.
-MHD int cell_coord(float x, float lo, float L, unsigned n) {
+// Reference form (IEEE division, C truncation).  Out-of-box input (which HOOMD never hands over) is folded into the
+// mesh instead of indexing out of range.
+MHD int cell_coord_ref(float x, float lo, float L, unsigned n) {
     const float f = f_div(f_sub(x, lo), L);
     const float r = f_mul(f, (float)n);
-    int i = (int)r;
-    if (i == (int)n) i = 0;
-    if (i < 0 || i > (int)n) {
-        i %= (int)n;
-        if (i < 0) i += (int)n;
-    }
+    int i = (r >= 0.f && r < 4194304.f) ? (int)r : 0;
+    if (i >= (int)n) i = 0;
+    return i;
+}
+// a / L, correctly rounded, without the division unit: with y = RN(1/L), q = RN(a y), the residual r = a - q L is
+// exact in one FMA and RN(q + r y) = RN(a / L) (Markstein 1990; excluded divisors are filtered by geom_set_box;
+// tests/cpu_emul/mesh_emul.cu compares against IEEE division).
+MHD float div_by_const(float a, float L, float rcpL) {
+    const float q = f_mul(a, rcpL);
+    const float r = f_fma(-q, L, a);
+    return f_fma(r, rcpL, q);
+}
+// Hot form: same value as cell_coord_ref for every input, no division, no conversion-pipe instruction.
+MHD int cell_coord(float x, int axis, const Geom& g) {
+    const float a = f_sub(x, g.lo[axis]);
+    const float f = g.fast_div ? div_by_const(a, g.L[axis], g.rcpL[axis]) : f_div(a, g.L[axis]);
+    float r = f_mul(f, g.fn[axis]);
+    const int n = (int)(axis == 0 ? g.nx : (axis == 1 ? g.ny : g.nzg));
+#ifdef __CUDA_ARCH__
+    // truncation: for 0 <= r < 2^22, RZ(r + 2^23) = 2^23 + trunc(r) exactly; anything else (out-of-box input, NaN) -> 0
+    r = (r >= 0.f && r < 4194304.f) ? r : 0.f;
+    int i = __float_as_int(__fadd_rz(r, 8388608.f)) & 0x7fffff;
+#else
+    int i = (r >= 0.f && r < 4194304.f) ? (int)r : 0;
+#endif
+    if (i >= n) i = 0;
     return i;
 }
 
@@ -116,8 +202,8 @@ MHD void cell_of_key(unsigned key, const Geom& g, unsigned& ix, unsigned& iy, un
 }
 
 // in-cell offset in cell units, s in [-1/2, 1/2] (OrderParameterMesh.cc:565-573: minimum-image distance to the
-// cell centre through makeCoordinates/minImage/makeFraction; evaluated here directly in fp64)
-MHD float cell_shift(float x, unsigned i, int axis, const Geom& g) {
+// cell centre through makeCoordinates/minImage/makeFraction).  Reference form in fp64:
+MHD float cell_shift_f64(float x, unsigned i, int axis, const Geom& g) {
     // i is the GLOBAL cell coordinate (for z: z0 + local plane)
     const unsigned n = axis == 0 ? g.nx : (axis == 1 ? g.ny : g.nzg);
     double s = ((double)x - g.dlo[axis]) * g.dscale[axis] - ((double)i + 0.5);
@@ -125,6 +211,26 @@ MHD float cell_shift(float x, unsigned i, int axis, const Geom& g) {
     if (s > half) s -= (double)n;
     else if (s < -half) s += (double)n;
     return (float)s;
+}
+// The same quantity in compensated single precision (no conversion-pipe or fp64 instructions): with
+// -lo = hl_hi + hl_lo and n/L = c_hi + c_lo,  x - lo = d + e exactly (Fast2Sum, |x| <= L/2), (d + e)(c_hi + c_lo)
+// is evaluated as fma(d, c_hi, -(i + 1/2)) -- one rounding of a number of magnitude <= 1/2 -- plus the two small terms.
+// |cell_shift - cell_shift_f64| < 1e-7 for in-box particles (tests/cpu_emul/mesh_emul.cu checks it).
+MHD float cell_shift(float x, unsigned i, int axis, const Geom& g) {
+    const float hl = g.hl_hi[axis], ch = g.c_hi[axis];
+    const float d = f_add(hl, x);
+    const float e = f_add(f_sub(x, f_sub(d, hl)), g.hl_lo[axis]);
+    // (float)i + 0.5 without the conversion pipe: i < 2^22
+#ifdef __CUDA_ARCH__
+    const float ci = __int_as_float(0x4B000000 | (int)i) - 8388607.5f;
+#else
+    const float ci = (float)i + 0.5f;
+#endif
+    // d*ch - (i + 1/2) in ONE rounding (the product is exact inside the FMA; |result| <= 1/2 unless the cell wrapped)
+    float t = f_fma(d, ch, -ci);
+    // periodic image: only the upper-edge particle, whose cell wrapped to 0, is affected; redo the single rounding there
+    if (t > 0.5f * g.fn[axis]) t = f_fma(d, ch, -(ci + g.fn[axis]));
+    return f_add(t, f_fma(e, ch, f_mul(d, g.c_lo[axis])));
 }
 
 // TSC weights of the three taps i = -1, 0, +1 for offset s (assignTSC, OrderParameterMesh.cc:457-468, with
@@ -143,92 +249,92 @@ MHD void tsc_deriv(float s, float (&w)[3]) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// per-thread bodies shared by the kernels and the CPU emulation (tests/cpu_emul/mesh_emul.cu)
+// fixed point
 // ---------------------------------------------------------------------------------------------------
+// round(a*b) as an integer without the conversion pipe: fma(a, b, 1.5*2^23) has ulp 1, its mantissa bits are
+// 0x4B400000 + rint(a*b) for |a*b| < 2^22 (single rounding, round to nearest even).
+constexpr float kFxMagic = 12582912.0f;
+constexpr int kFxMagicBits = 0x4B400000;
+MHD int fx_round(float a, float b) { return f2i_bits(f_fma(a, b, kFxMagic)) - kFxMagicBits; }
 
-// index inside the padded tile (edge P = T+2) of tap (i,j,k) in {0,1,2}^3 of local cell (lx,ly,lz)
-MHD unsigned padded_index(unsigned lx, unsigned ly, unsigned lz, int i, int j, int k, unsigned P) {
-    return ((lz + k) * P + (ly + j)) * P + (lx + i);
+// Scale of the fixed-point density: a power of two such that (i) one tap, |a| W^3 <= 0.421875 |a|max, stays below
+// 2^22 (fx_round) and (ii) the total of a cell stays below 2^31 / 4: a cell collects at most
+// sum_offsets Wmax(offset) = (1/2 + 3/4 + 1/2)^3 = 5.36 times the largest per-cell load of its 27 neighbours.
+// max_cell_load = max over cells of sum |a| at the last rebuild of the tile order (the factor 4 is the headroom for
+// density changes until the next rebuild; the flush raises a flag once any cell passes 2^30).
+MHD float fx_scale_for(float amax, float max_cell_load) {
+    if (!(amax > 0.f)) return 1.0f;
+    const float tap = 4194304.0f / (0.421875f * amax);
+    const float load = max_cell_load > amax ? max_cell_load : amax;
+    const float tot = 2147483648.0f / (4.0f * 5.359375f * load);
+    const float lim = tap < tot ? tap : tot;
+    // largest power of two <= lim
+    int b = f2i_bits(lim);
+    b &= 0x7f800000;
+    float p;
+#ifdef __CUDA_ARCH__
+    p = __int_as_float(b);
+#else
+    memcpy(&p, &b, 4);
+#endif
+    return p;
 }
 
-// Separable TSC weights of one particle relative to its cell: w[0..2] = a*Wx(tap -1,0,+1), w[3..5] = Wy, w[6..8] = Wz
-MHD void spread_weights(float4 p /* x,y,z,a */, unsigned ix, unsigned iy, unsigned iz, const Geom& g, float (&w)[9]) {
+// ---------------------------------------------------------------------------------------------------
+// per-particle bodies shared by the kernels and the CPU emulation (tests/cpu_emul/mesh_emul.cu)
+// ---------------------------------------------------------------------------------------------------
+struct Cell {
+    int ix, iy, iz;      // global cell (bit-exact reference rule); iz is the GLOBAL plane
+    bool owned;          // slab mode: the plane belongs to this rank
+};
+MHD Cell particle_cell(float4 p, const Geom& g) {
+    Cell c;
+    c.ix = cell_coord(p.x, 0, g);
+    c.iy = cell_coord(p.y, 1, g);
+    c.iz = cell_coord(p.z, 2, g);
+    c.owned = (unsigned)(c.iz - (int)g.z0) < g.nz;
+    return c;
+}
+// coordinates of the cell inside the padded tile with origin (ox,oy,oz) = tile origin - halo (local planes in z);
+// returns true if all 27 taps lie inside the padded tile
+MHD bool padded_coords(const Cell& c, int ox, int oy, int oz, const Geom& g, int P, unsigned& lx, unsigned& ly, unsigned& lz) {
+    lx = (unsigned)(c.ix - ox) & (g.nx - 1);
+    ly = (unsigned)(c.iy - oy) & (g.ny - 1);
+    const int zl = c.iz - (int)g.z0;
+    lz = g.slab ? (unsigned)(zl - oz) : ((unsigned)(zl - oz) & (g.nz - 1));
+    return (lx - 1u) < (unsigned)(P - 2) && (ly - 1u) < (unsigned)(P - 2) && (lz - 1u) < (unsigned)(P - 2);
+}
+// separable weights: w[0..2] = Wx(tap -1,0,+1), w[3..5] = Wy, w[6..8] = amp * Wz
+MHD void spread_weights(float4 p, const Cell& c, float amp, const Geom& g, float (&w)[9]) {
     float wx[3], wy[3], wz[3];
-    tsc(cell_shift(p.x, ix, 0, g), wx);
-    tsc(cell_shift(p.y, iy, 1, g), wy);
-    tsc(cell_shift(p.z, iz, 2, g), wz);
+    tsc(cell_shift(p.x, c.ix, 0, g), wx);
+    tsc(cell_shift(p.y, c.iy, 1, g), wy);
+    tsc(cell_shift(p.z, c.iz, 2, g), wz);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) { w[i] = p.w * wx[i]; w[3 + i] = wy[i]; w[6 + i] = wz[i]; }
+    for (int i = 0; i < 3; ++i) { w[i] = wx[i]; w[3 + i] = wy[i]; w[6 + i] = amp * wz[i]; }
 }
-// Rolling accumulators of a cell column: acc[k*9 + i*3 + j], k = z tap (plane lz-1+k), i = x tap, j = y tap
-MHD void spread_accumulate9(const float (&w)[9], float (&acc)[27]) {
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const float axy = w[i] * w[3 + j];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) acc[k * 9 + i * 3 + j] = fmaf(axy, w[6 + k], acc[k * 9 + i * 3 + j]);
-        }
-}
-// Exchange in x,y without atomics or read-modify-write: column (lx,ly) stores its nine (i,j) partial sums of a finished
-// plane into nine "replica" planes at padded position (lx+i, ly+j); replica r = i*3+j is written at most once per
-// position.  The value of padded position (px,py) is the sum over the replicas whose source column exists.
-MHD unsigned replica_index(int r, unsigned px, unsigned py, unsigned P) { return (r * P + py) * P + px; }
-MHD float reduce_replicas(const float* rep, unsigned px, unsigned py, unsigned T) {
-    const unsigned P = T + 2;
-    float sum = 0.f;
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            // source column (px - i, py - j) must lie inside the tile
-            if (px >= (unsigned)i && px - i < T && py >= (unsigned)j && py - j < T) sum += rep[replica_index(i * 3 + j, px, py, P)];
-        }
-    return sum;
+// fixed-point value of tap (i,j,k) in {0,1,2}^3: the SAME expression on every path (tile, stray, emulation)
+MHD int tap_value(const float (&w)[9], int i, int j, int k) { return fx_round(w[i], f_mul(w[3 + j], w[6 + k])); }
+
+// mesh index of tap (i,j,k) of cell c for the direct (stray) path; returns false if the plane is outside the slab + ghosts.
+// `mesh` points at local plane 0; in slab mode the ghost planes are plane -1 and plane nz of the same allocation.
+MHD bool tap_index(const Cell& c, int i, int j, int k, const Geom& g, long long& idx) {
+    const unsigned x = (unsigned)(c.ix + i - 1) & (g.nx - 1), y = (unsigned)(c.iy + j - 1) & (g.ny - 1);
+    int z = c.iz - (int)g.z0 + k - 1;
+    if (g.slab) { if (z < -1 || z > (int)g.nz) return false; }
+    else z = (int)((unsigned)z & (g.nz - 1));
+    idx = (long long)x + (long long)g.nx * ((long long)y + (long long)g.ny * (long long)z);
+    return true;
 }
 
-// merge: value of mesh cell (x,y,z) = sum over the <= 8 padded tiles that cover it, in fixed (z,y,x) order.
-// merge_plane sums the x,y candidates of padded plane pz of tile row tz.
-MHD float merge_plane(const float* __restrict__ scratch, unsigned x, unsigned y, unsigned tz, unsigned pz, const Geom& g) {
-    const unsigned T = 1u << g.lgT, P = T + 2, P3 = P * P * P;
-    const unsigned tx = x >> g.lgT, ty = y >> g.lgT;
-    const unsigned lx = x & (T - 1), ly = y & (T - 1);
-    unsigned ctx[2], cpx[2], cty[2], cpy[2];
-    int nxc = 1, nyc = 1;
-    ctx[0] = tx; cpx[0] = lx + 1;
-    if (lx == 0) { ctx[1] = (tx + g.ntx - 1) & (g.ntx - 1); cpx[1] = T + 1; nxc = 2; }
-    else if (lx == T - 1) { ctx[1] = (tx + 1) & (g.ntx - 1); cpx[1] = 0; nxc = 2; }
-    cty[0] = ty; cpy[0] = ly + 1;
-    if (ly == 0) { cty[1] = (ty + g.nty - 1) & (g.nty - 1); cpy[1] = T + 1; nyc = 2; }
-    else if (ly == T - 1) { cty[1] = (ty + 1) & (g.nty - 1); cpy[1] = 0; nyc = 2; }
-    float sum = 0.f;
-    for (int b = 0; b < nyc; ++b)
-        for (int a = 0; a < nxc; ++a) {
-            const unsigned tile = tile_index(ctx[a], cty[b], tz, g);
-            sum += scratch[(size_t)tile * P3 + (pz * P + cpy[b]) * P + cpx[a]];
-        }
-    return sum;
-}
-// In slab mode the halo planes below the first / above the last local tile row are NOT wrapped around: they are
-// extracted by merge_plane(..., tz = 0, pz = 0) / (tz = ntz-1, pz = T+1) and added by the neighbour rank.
-MHD float merge_cell(const float* __restrict__ scratch, unsigned x, unsigned y, unsigned z, const Geom& g) {
-    const unsigned T = 1u << g.lgT;
-    const unsigned tz = z >> g.lgT, lz = z & (T - 1);
-    float sum = merge_plane(scratch, x, y, tz, lz + 1, g);
-    if (lz == 0 && !(g.slab && tz == 0)) sum += merge_plane(scratch, x, y, (tz + g.ntz - 1) & (g.ntz - 1), T + 1, g);
-    else if (lz == T - 1 && !(g.slab && tz == g.ntz - 1)) sum += merge_plane(scratch, x, y, (tz + 1) & (g.ntz - 1), 0, g);
-    return sum;
-}
-
-// force on one particle from the padded tile of Re(IFFT(G)) (interpolateForces, OrderParameterMesh.cc:812-860):
+// force on one particle from a tile of Re(IFFT(G)) (interpolateForces, OrderParameterMesh.cc:812-860):
 //   F = -(a) * sum_taps inv * [ nb1 W'x Wy Wz + nb2 Wx W'y Wz + nb3 Wx Wy W'z ],  nb_a = n_a * b_a (no 2 pi)
-// evaluated as three separable contractions; returns the three scalar sums (Sx,Sy,Sz).
-MHD void gather_sums(const float* tile, unsigned lx, unsigned ly, unsigned lz, unsigned P, const float (&wx)[3],
+// evaluated as three separable contractions; returns the three scalar sums (Sx,Sy,Sz).  base = address of tap
+// (0,0,0); sx/sy/sz = element strides.
+MHD void gather_sums(const float* base, long long sy_, long long sz_, const float (&wx)[3],
                      const float (&wy)[3], const float (&wz)[3], const float (&dx)[3], const float (&dy)[3],
                      const float (&dz)[3], float& Sx, float& Sy, float& Sz) {
     Sx = 0.f; Sy = 0.f; Sz = 0.f;
-    const float* base = tile + (lz * P + ly) * P + lx;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         float tw = 0.f, td = 0.f, tz = 0.f;   // sum_j {Wy, W'y, Wy} * sum_k {Wz, Wz, W'z} inv
@@ -237,7 +343,7 @@ MHD void gather_sums(const float* tile, unsigned lx, unsigned ly, unsigned lz, u
             float u = 0.f, v = 0.f;
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const float val = base[(k * P + j) * P + i];
+                const float val = base[k * sz_ + j * sy_ + i];
                 u = fmaf(wz[k], val, u);
                 v = fmaf(dz[k], val, v);
             }
@@ -256,58 +362,57 @@ struct ForceParams {
     double two_over_n;              // 2 / N_global  (:858)
 };
 
-// (lx,ly,lz): local cell inside the tile; (ix,iy,iz): global cell; scale = (2/N) * bias rounded to float
-MHD float4 gather_force(float4 p /* x,y,z,a */, unsigned ix, unsigned iy, unsigned iz, unsigned lx, unsigned ly, unsigned lz,
-                        const float* tile, const Geom& g, const ForceParams& fp, float scale) {
-    const unsigned P = (1u << g.lgT) + 2;
-    const float sx = cell_shift(p.x, ix, 0, g), sy = cell_shift(p.y, iy, 1, g), sz = cell_shift(p.z, iz, 2, g);
-    float wx[3], wy[3], wz[3], dx[3], dy[3], dz[3];
-    tsc(sx, wx); tsc(sy, wy); tsc(sz, wz);
-    tsc_deriv(sx, dx); tsc_deriv(sy, dy); tsc_deriv(sz, dz);
-    float Sx, Sy, Sz;
-    gather_sums(tile, lx, ly, lz, P, wx, wy, wz, dx, dy, dz, Sx, Sy, Sz);
-    const float m = -p.w * scale;
+struct GatherWeights { float wx[3], wy[3], wz[3], dx[3], dy[3], dz[3]; };
+MHD void gather_weights(float4 p, const Cell& c, const Geom& g, GatherWeights& w) {
+    const float sx = cell_shift(p.x, c.ix, 0, g), sy = cell_shift(p.y, c.iy, 1, g), sz = cell_shift(p.z, c.iz, 2, g);
+    tsc(sx, w.wx); tsc(sy, w.wy); tsc(sz, w.wz);
+    tsc_deriv(sx, w.dx); tsc_deriv(sy, w.dy); tsc_deriv(sz, w.dz);
+}
+// amp = a(type); scale = (2/N) * bias rounded to float
+MHD float4 force_from_sums(float Sx, float Sy, float Sz, float amp, const ForceParams& fp, float scale) {
+    const float m = -amp * scale;
     return make_float4(m * (fp.nb1[0] * Sx + fp.nb2[0] * Sy + fp.nb3[0] * Sz), m * (fp.nb1[1] * Sx + fp.nb2[1] * Sy + fp.nb3[1] * Sz),
                        m * (fp.nb1[2] * Sx + fp.nb2[2] * Sy + fp.nb3[2] * Sz), 0.f);
 }
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------------
-// kernels
+// kernels: tile order (rebuilt every few calls)
 // ---------------------------------------------------------------------------------------------------
 constexpr int kBinThreads = 256;
 
-// bin: key + rank (arrival order inside the cell) per particle, per-cell counts, sum a^2 and sum a
+// bin: key + arrival rank inside the cell per particle, per-cell counts, largest per-cell load sum |a|
 __global__ void __launch_bounds__(kBinThreads)
-mesh_bin_kernel(const float4* __restrict__ postype, unsigned N, Geom g, const float* __restrict__ mode,
+mesh_bin_kernel(const float4* __restrict__ postype, unsigned N, Geom g, const float* __restrict__ mode, int ntypes,
                 unsigned* __restrict__ keys, unsigned* __restrict__ ranks, unsigned* __restrict__ count,
-                double* __restrict__ sums /* [0] sum a^2, [1] sum a, [2] misplaced particles */) {
-    double sq = 0.0, s1 = 0.0;
+                unsigned* __restrict__ max_count) {
     const unsigned stride = gridDim.x * blockDim.x;
+    unsigned mx = 0;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
         const float4 p = ld_stream(postype + i);
-        const unsigned ix = cell_coord(p.x, g.lo[0], g.L[0], g.nx);
-        const unsigned iy = cell_coord(p.y, g.lo[1], g.L[1], g.ny);
-        // global plane -> local plane of this slab; a particle outside the slab is a caller error: it is folded into
-        // the slab (keeps memory safe) and counted in sums[2]
-        unsigned iz = (unsigned)cell_coord(p.z, g.lo[2], g.L[2], g.nzg) - g.z0;
-        if (iz >= g.nz) { iz &= (g.nz - 1); atomicAdd(sums + 2, 1.0); }
-        const unsigned key = key_of(ix, iy, iz, g);
+        const Cell c = particle_cell(p, g);
+        // a particle outside the slab is a caller error: it is listed in a tile of the slab (the spread skips and counts it)
+        const unsigned iz = (unsigned)(c.iz - (int)g.z0) & (g.nz - 1);
+        const unsigned key = key_of(c.ix, c.iy, iz, g);
         keys[i] = key;
-        ranks[i] = atomicAdd(count + key, 1u);
-        const float a = __ldg(mode + __float_as_int(p.w));
-        sq += (double)a * (double)a;        // m_mode_sq, OrderParameterMesh.cc:623
-        s1 += (double)a;
+        const unsigned r = atomicAdd(count + key, 1u);
+        ranks[i] = r;
+        mx = max(mx, r + 1);
     }
-    __shared__ double red[32];
-    const double tsq = block_sum(sq, red);
-    const double ts1 = block_sum(s1, red);
-    if (threadIdx.x == 0) { atomicAdd(sums, tsq); atomicAdd(sums + 1, ts1); }
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0) atomicMax(max_count, mx);
+}
+
+// fixed-point scale of the density for the calls until the next rebuild: d_fx = {scale, 1/scale}
+__global__ void mesh_fx_scale_kernel(const unsigned* __restrict__ max_count, float amax, float* __restrict__ d_fx) {
+    const float s = fx_scale_for(amax, amax * (float)*max_count);
+    d_fx[0] = s;
+    d_fx[1] = 1.0f / s;
 }
 
 // ---- exclusive scan of count[0..n) -> start[0..n].  Three launches: per-block sums, scan of the block sums (single
 // block), apply.  Each thread owns V consecutive uint4 (n must be a multiple of 4096*V).  The apply pass also
-// clears count[] for the next step.
+// clears count[] for the next rebuild.
 constexpr int kScanThreads = 1024;
 
 // block-wide exclusive scan of one value per thread (blockDim.x == 1024); total returned to every thread
@@ -396,185 +501,249 @@ scan_apply_kernel(uint4* __restrict__ count4, const unsigned* __restrict__ block
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) start[n] = run;
 }
 
-// place: slot[start[key] + arrival rank] = particle index.  The arrival rank comes from atomics and is not
-// reproducible; the reorder pass below turns it into the stable rank (ascending particle index inside a cell).
+// place: perm[start[key] + arrival rank] = particle index; tstart[tile] = first slot of the tile.  The order inside
+// a cell is arbitrary -- results do not depend on it (integer accumulation).
 __global__ void __launch_bounds__(kBinThreads)
 mesh_place_kernel(unsigned N, const unsigned* __restrict__ keys, const unsigned* __restrict__ ranks,
-                  const unsigned* __restrict__ start, unsigned* __restrict__ slot) {
+                  const unsigned* __restrict__ start, unsigned* __restrict__ perm, unsigned ntiles, unsigned lg_cells,
+                  unsigned* __restrict__ tstart) {
     const unsigned stride = gridDim.x * blockDim.x;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) slot[__ldg(start + keys[i]) + ranks[i]] = i;
+    const unsigned t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    for (unsigned i = t0; i < N; i += stride) perm[__ldg(start + keys[i]) + ranks[i]] = i;
+    for (unsigned t = t0; t <= ntiles; t += stride) tstart[t] = __ldg(start + ((size_t)t << lg_cells));
 }
 
-// reorder (one thread per slot): stable position inside the cell = number of cell mates with a smaller particle
-// index; sorted[...] = {x, y, z, a(type)}, perm[...] = particle index, skey[...] = key.
-__global__ void __launch_bounds__(kBinThreads)
-mesh_reorder_kernel(const float4* __restrict__ postype, unsigned N, const float* __restrict__ mode,
-                    const unsigned* __restrict__ keys, const unsigned* __restrict__ start, const unsigned* __restrict__ slot,
-                    float4* __restrict__ sorted, unsigned* __restrict__ perm, unsigned* __restrict__ skey) {
-    const unsigned stride = gridDim.x * blockDim.x;
-    for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += stride) {
-        const unsigned i = slot[j];
-        const unsigned key = __ldg(keys + i);
-        const unsigned s = __ldg(start + key), e = __ldg(start + key + 1);
-        unsigned dst = s;
-        for (unsigned m = s; m < e; ++m) dst += (__ldg(slot + m) < i) ? 1u : 0u;
-        float4 p = __ldg(postype + i);
-        p.w = __ldg(mode + __float_as_int(p.w));
-        sorted[dst] = p;
-        perm[dst] = i;
-        skey[dst] = key;
-    }
-}
+// ---------------------------------------------------------------------------------------------------
+// spread
+// ---------------------------------------------------------------------------------------------------
+constexpr int kSpreadThreads = 256;
+// counters[] (device, unsigned): [0] ticket, [1] particles handled by the direct path (drifted out of their padded
+// tile), [2] particles outside the slab (caller error), [3] cells past half of the fixed-point range
+struct SpreadOut {
+    int* mesh;               // integer density, local plane 0 (slab: ghost planes at -1 and nz)
+    double* tile_sums;       // [ntiles][2] partial sum a^2, sum a
+    double* sums;            // [0] sum a^2 (m_mode_sq, OrderParameterMesh.cc:623), [1] sum a, [2] particles outside the slab
+    unsigned* counters;
+    unsigned* keys;          // optional: tile-major cell key per particle (introspection), or nullptr
+};
 
-// spread: one CTA per tile, one thread per cell COLUMN (lx,ly); the thread walks its column in z keeping the
-// 3x9 partial sums of the planes lz-1, lz, lz+1 in registers.  Per plane:
-//   phase 1  (thread per particle, balanced): separable weights of the plane's particles -> shared memory
-//   phase 2  (thread per cell): accumulate the cell's particles in slot order (= ascending particle index)
-//   flush    the finished plane lz-1: nine replica stores per column, one barrier, replica reduction -> padded tile
-// No atomics, no shared-memory read-modify-write.
-constexpr int kSpreadCap = 512;     // particles per phase-1 chunk
 template <int LGT>
-__global__ void __launch_bounds__(1 << (2 * LGT), LGT == 4 ? 3 : 8)
-mesh_spread_kernel(const float4* __restrict__ sorted, const unsigned* __restrict__ skey, const unsigned* __restrict__ start,
-                   Geom g, float* __restrict__ scratch) {
-    constexpr unsigned T = 1u << LGT, P = T + 2, PP = P * P, NT = T * T;
-    __shared__ float wbuf[9 * kSpreadCap];
-    __shared__ float rep[2][9 * PP];
-    const unsigned tid = threadIdx.x, lx = tid & (T - 1), ly = tid >> LGT;
-    const unsigned tile_id = blockIdx.x;
+__global__ void __launch_bounds__(kSpreadThreads)
+mesh_spread_kernel(const float4* __restrict__ postype, const unsigned* __restrict__ perm, const unsigned* __restrict__ tstart,
+                   Geom g, const float* __restrict__ mode, const float* __restrict__ d_fx, SpreadOut out) {
+    constexpr int T = 1 << LGT, P = T + 2 * kHalo, P3 = P * P * P;
+    extern __shared__ int tile[];
+    __shared__ double red[32];
+    __shared__ bool is_last;
+    const unsigned s = __ldg(tstart + blockIdx.x), e = __ldg(tstart + blockIdx.x + 1);
     unsigned tx, ty, tz;
-    tile_coords(tile_id, g, tx, ty, tz);
-    float* out = scratch + (size_t)tile_id * PP * P;
-    float acc[27];
-#pragma unroll
-    for (int r = 0; r < 27; ++r) acc[r] = 0.f;
-    int buf = 0;
-    for (unsigned lz = 0; lz < T + 2; ++lz) {
-        if (lz < T) {
-            const unsigned key0 = (tile_id << (3 * LGT)) + lz * NT;
-            const unsigned s_plane = __ldg(start + key0), e_plane = __ldg(start + key0 + NT);
-            const unsigned s = __ldg(start + key0 + tid), e = __ldg(start + key0 + tid + 1);
-            for (unsigned c0 = s_plane; c0 < e_plane; c0 += kSpreadCap) {
-                const unsigned c1 = min(c0 + (unsigned)kSpreadCap, e_plane);
-                for (unsigned j = c0 + tid; j < c1; j += NT) {
-                    const unsigned local = __ldg(skey + j) & (NT - 1);     // cell inside the plane
-                    float w[9];
-                    spread_weights(sorted[j], (tx << LGT) + (local & (T - 1)), (ty << LGT) + (local >> LGT), g.z0 + (tz << LGT) + lz, g, w);
-#pragma unroll
-                    for (int c = 0; c < 9; ++c) wbuf[c * kSpreadCap + (j - c0)] = w[c];
-                }
-                __syncthreads();
-                const unsigned a = max(s, c0), b = min(e, c1);
-                for (unsigned j = a; j < b; ++j) {
-                    float w[9];
-#pragma unroll
-                    for (int c = 0; c < 9; ++c) w[c] = wbuf[c * kSpreadCap + (j - c0)];
-                    spread_accumulate9(w, acc);
-                }
-                __syncthreads();
-            }
-        }
-        // flush the finished plane: padded z index lz (= tile plane lz - 1)
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) rep[buf][replica_index(i * 3 + j, lx + i, ly + j, P)] = acc[i * 3 + j];
+    tile_coords(blockIdx.x, g, tx, ty, tz);
+    const int ox = (int)(tx << LGT) - kHalo, oy = (int)(ty << LGT) - kHalo, oz = (int)(tz << LGT) - kHalo;
+    double sq = 0.0, s1 = 0.0;
+    if (e > s) {
+        for (int i = threadIdx.x; i < P3; i += kSpreadThreads) tile[i] = 0;
         __syncthreads();
-        for (unsigned idx = tid; idx < PP; idx += NT) out[(size_t)lz * PP + idx] = reduce_replicas(rep[buf], idx % P, idx / P, T);
-        buf ^= 1;
+        const float scale = __ldg(d_fx);
+        unsigned strays = 0, foreign = 0;
+        // software pipeline: the index and the position of the next particle are in flight while this one is spread
+        unsigned j = s + threadIdx.x;
+        unsigned n = 0;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < e) { n = __ldg(perm + j); p = __ldg(postype + n); }
+        while (j < e) {
+            const unsigned jn = j + kSpreadThreads;
+            unsigned n_next = 0;
+            float4 p_next = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (jn < e) { n_next = __ldg(perm + jn); p_next = __ldg(postype + n_next); }
+            const float a = __ldg(mode + __float_as_int(p.w));
+            const Cell c = particle_cell(p, g);
+            if (out.keys) out.keys[n] = key_of(c.ix, c.iy, (unsigned)(c.iz - (int)g.z0) & (g.nz - 1), g);
+            if (c.owned) {
+                sq += (double)a * (double)a;
+                s1 += (double)a;
+                float w[9];
+                spread_weights(p, c, a * scale, g, w);
+                unsigned lx, ly, lz;
+                if (padded_coords(c, ox, oy, oz, g, P, lx, ly, lz)) {
+                    int* base = tile + ((lz - 1) * P + (ly - 1)) * P + (lx - 1);
 #pragma unroll
-        for (int r = 0; r < 9; ++r) { acc[r] = acc[9 + r]; acc[9 + r] = acc[18 + r]; acc[18 + r] = 0.f; }
-    }
-}
-
-// merge: mesh[x + nx (y + ny z)] = sum of covering padded tiles - mean (DC removal, see mesh.cu)
-__global__ void __launch_bounds__(256)
-mesh_merge_kernel(const float* __restrict__ scratch, Geom g, const double* __restrict__ sums, float* __restrict__ rho,
-                  float* __restrict__ rho_keep) {
-    const size_t M = (size_t)g.nx * g.ny * g.nz;
-    // slab mode: the mean needs the GLOBAL sum, it is subtracted later (mesh_add_ghost_kernel)
-    const float mean = g.slab ? 0.f : (float)(sums[1] / (double)M);
-    const unsigned T = 1u << g.lgT, P = T + 2;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < M; c += stride) {
-        const unsigned x = (unsigned)(c & (g.nx - 1)), y = (unsigned)((c >> g.lgx) & (g.ny - 1)), z = (unsigned)(c >> (g.lgx + g.lgy));
-        const unsigned lx = x & (T - 1), ly = y & (T - 1), lz = z & (T - 1);
-        float v;
-        if (lx != 0 && lx != T - 1 && ly != 0 && ly != T - 1 && lz != 0 && lz != T - 1) {
-            // interior cell of its tile: a single contribution
-            const unsigned tile = tile_index(x >> g.lgT, y >> g.lgT, z >> g.lgT, g);
-            v = __ldg(scratch + (size_t)tile * (P * P * P) + ((lz + 1) * P + (ly + 1)) * P + (lx + 1));
-        } else {
-            v = merge_cell(scratch, x, y, z, g);
+                    for (int k = 0; k < 3; ++k)
+#pragma unroll
+                        for (int jj = 0; jj < 3; ++jj) {
+                            const float wyz = f_mul(w[3 + jj], w[6 + k]);
+#pragma unroll
+                            for (int i = 0; i < 3; ++i) atomicAdd(base + (k * P + jj) * P + i, fx_round(w[i], wyz));
+                        }
+                } else {
+                    ++strays;
+                    for (int k = 0; k < 3; ++k)
+                        for (int jj = 0; jj < 3; ++jj)
+                            for (int i = 0; i < 3; ++i) {
+                                long long idx;
+                                if (tap_index(c, i, jj, k, g, idx)) atomicAdd(out.mesh + idx, tap_value(w, i, jj, k));
+                            }
+                }
+            } else {
+                ++foreign;
+            }
+            j = jn; n = n_next; p = p_next;
         }
-        if (rho_keep) rho_keep[c] = v;
-        rho[c] = v - mean;
+        if (strays) atomicAdd(out.counters + 1, strays);
+        if (foreign) atomicAdd(out.counters + 2, foreign);
+        __syncthreads();
+        // flush the padded tile: flat index walked incrementally (kSpreadThreads = 0*P*P + sy*P + sx)
+        constexpr int sx = kSpreadThreads % P, sy = (kSpreadThreads / P) % P, sz = kSpreadThreads / (P * P);
+        int px = threadIdx.x % P, py = (threadIdx.x / P) % P, pz = threadIdx.x / (P * P);
+        const unsigned mx = g.nx - 1, my = g.ny - 1, mz = g.slab ? 0xffffffffu : g.nz - 1;
+        const unsigned sh_y = g.lgx, sh_z = g.lgx + g.lgy;
+        int vmax = 0;
+        for (int idx = threadIdx.x; idx < P3; idx += kSpreadThreads) {
+            const int v = tile[idx];
+            if (v != 0) {
+                const unsigned x = (unsigned)(ox + px) & mx, y = (unsigned)(oy + py) & my;
+                const int z = (int)((unsigned)(oz + pz) & mz);
+                atomicAdd(out.mesh + (long long)z * (long long)(1u << sh_z) + (long long)((y << sh_y) | x), v);
+                vmax = max(vmax, abs(v));
+            }
+            px += sx; py += sy; pz += sz;
+            if (px >= P) { px -= P; ++py; }
+            if (py >= P) { py -= P; ++pz; }
+        }
+        // one eighth of the range: a cell sums at most 8 padded tiles, so no total has left the 32-bit range
+        if (__any_sync(0xffffffffu, vmax > (1 << 28)) && (threadIdx.x & 31) == 0) atomicAdd(out.counters + 3, 1u);
+    }
+    // deterministic sums: per-tile partials, the last CTA adds them in tile order
+    const double tsq = block_sum(sq, red);
+    const double ts1 = block_sum(s1, red);
+    if (threadIdx.x == 0) {
+        out.tile_sums[2 * blockIdx.x] = tsq;
+        out.tile_sums[2 * blockIdx.x + 1] = ts1;
+        __threadfence();
+        is_last = (atomicAdd(out.counters, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double a2 = 0.0, a1 = 0.0;
+    for (unsigned t = threadIdx.x; t < gridDim.x; t += kSpreadThreads) { a2 += __ldcg(out.tile_sums + 2 * t); a1 += __ldcg(out.tile_sums + 2 * t + 1); }
+    a2 = block_sum(a2, red);
+    a1 = block_sum(a1, red);
+    if (threadIdx.x == 0) {
+        out.sums[0] = a2;
+        out.sums[1] = a1;
+        out.sums[2] = (double)__ldcg(out.counters + 2);
+        out.counters[0] = 0;
     }
 }
 
-// slab mode: the two halo planes that belong to the neighbour ranks: ghost[0] = plane z0-1, ghost[1] = plane z0+nz
-__global__ void __launch_bounds__(256)
-mesh_ghost_extract_kernel(const float* __restrict__ scratch, Geom g, float* __restrict__ ghost) {
-    const unsigned plane = g.nx * g.ny, T = 1u << g.lgT;
-    for (unsigned c = blockIdx.x * blockDim.x + threadIdx.x; c < 2 * plane; c += gridDim.x * blockDim.x) {
-        const unsigned which = c >= plane, cc = which ? c - plane : c;
-        const unsigned x = cc & (g.nx - 1), y = cc >> g.lgx;
-        ghost[c] = which ? merge_plane(scratch, x, y, g.ntz - 1, T + 1, g) : merge_plane(scratch, x, y, 0, 0, g);
-    }
-}
-// slab mode: add the planes received from the neighbours (recv[0] -> first local plane, recv[1] -> last local plane)
-// and subtract the global mean density (DC removal)
-__global__ void __launch_bounds__(256)
-mesh_add_ghost_kernel(float* __restrict__ rho, Geom g, const float* __restrict__ recv, const double* __restrict__ sums_global,
-                      float* __restrict__ rho_keep) {
-    const size_t M = (size_t)g.nx * g.ny * g.nz, plane = (size_t)g.nx * g.ny;
-    const float mean = (float)(sums_global[1] / ((double)plane * (double)g.nzg));
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < M; c += stride) {
-        float v = rho[c];
-        if (c < plane) v += recv[c];
-        if (c >= M - plane) v += recv[plane + (c - (M - plane))];
-        if (rho_keep) rho_keep[c] = v;
-        rho[c] = v - mean;
-    }
-}
-
+// ---------------------------------------------------------------------------------------------------
 // gather: one CTA per tile; shared tile of Re(IFFT(G)) with halo; one thread per particle of the tile
+// ---------------------------------------------------------------------------------------------------
 constexpr int kGatherThreads = 256;
+
+// slow path of a particle that drifted out of its padded tile: the 27 taps come from global memory.  Not inlined and
+// fed by value, so that the fast path keeps its weights in registers; recomputes cell and weights from the position.
+struct GatherDirectArgs { const float* inv; const float* ghost; const Geom* g; };
+__device__ __noinline__ float3 gather_direct(float4 p, GatherDirectArgs a) {
+    const Geom g = *a.g;
+    const Cell c = particle_cell(p, g);
+    GatherWeights w;
+    gather_weights(p, c, g, w);
+    const size_t plane = (size_t)g.nx * g.ny;
+    float t27[27];
+    for (int k = 0; k < 3; ++k)
+        for (int jj = 0; jj < 3; ++jj)
+            for (int i = 0; i < 3; ++i) {
+                const unsigned x = (unsigned)(c.ix + i - 1) & (g.nx - 1), y = (unsigned)(c.iy + jj - 1) & (g.ny - 1);
+                const int z = c.iz - (int)g.z0 + k - 1;
+                float v;
+                if (g.slab) v = z == -1 ? a.ghost[(size_t)g.nx * y + x] : (z == (int)g.nz ? a.ghost[plane + (size_t)g.nx * y + x] : a.inv[(size_t)g.nx * y + x + plane * (size_t)z]);
+                else v = a.inv[(size_t)g.nx * y + x + plane * (size_t)((unsigned)z & (g.nz - 1))];
+                t27[(k * 3 + jj) * 3 + i] = v;
+            }
+    float3 S;
+    gather_sums(t27, 3, 9, w.wx, w.wy, w.wz, w.dx, w.dy, w.dz, S.x, S.y, S.z);
+    return S;
+}
+
 template <int LGT>
-__global__ void __launch_bounds__(kGatherThreads)
-mesh_gather_kernel(const float4* __restrict__ sorted, const unsigned* __restrict__ perm, const unsigned* __restrict__ skey,
-                   const unsigned* __restrict__ start, Geom g, const float* __restrict__ inv,
+__global__ void __launch_bounds__(kGatherThreads, 2)
+mesh_gather_kernel(const float4* __restrict__ postype, const unsigned* __restrict__ perm, const unsigned* __restrict__ tstart,
+                   const __grid_constant__ Geom g, const float* __restrict__ mode, const float* __restrict__ inv,
                    const float* __restrict__ ghost /* slab mode: planes z0-1 and z0+nz of Re IFFT(G) */, ForceParams fp,
                    const double* __restrict__ d_bias, float4* __restrict__ force) {
-    constexpr unsigned T = 1u << LGT, P = T + 2, P3 = P * P * P;
-    __shared__ float tile[P3];
-    const unsigned tile_id = blockIdx.x;
-    const unsigned s = __ldg(start + (tile_id << (3 * LGT))), e = __ldg(start + ((tile_id + 1) << (3 * LGT)));
+    constexpr int T = 1 << LGT, P = T + 2 * kHalo;
+    extern __shared__ float ftile[];
+    const unsigned s = __ldg(tstart + blockIdx.x), e = __ldg(tstart + blockIdx.x + 1);
     if (e == s) return;                                   // empty tile: nothing to interpolate
     unsigned tx, ty, tz;
-    tile_coords(tile_id, g, tx, ty, tz);
-    // padded tile, one row (P floats along x) per warp iteration
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (unsigned row = warp; row < P * P; row += kGatherThreads / 32) {
-        const unsigned py = row % P, pz = row / P;
-        const unsigned y = ((ty << LGT) + py + g.ny - 1) & (g.ny - 1);
-        const int zl = (int)((tz << LGT) + pz) - 1;                  // local plane, -1 and nz are halo planes
-        const float* src;
-        if (g.slab && zl < 0) src = ghost + (size_t)g.nx * y;
-        else if (g.slab && zl >= (int)g.nz) src = ghost + (size_t)g.nx * (g.ny + y);
-        else src = inv + (size_t)g.nx * (y + (size_t)g.ny * ((unsigned)(zl + (int)g.nz) & (g.nz - 1)));
-        if (lane < P) {
-            const unsigned x = ((tx << LGT) + lane + g.nx - 1) & (g.nx - 1);
-            tile[row * P + lane] = __ldg(src + x);
+    tile_coords(blockIdx.x, g, tx, ty, tz);
+    const int ox = (int)(tx << LGT) - kHalo, oy = (int)(ty << LGT) - kHalo, oz = (int)(tz << LGT) - kHalo;
+    const size_t plane = (size_t)g.nx * g.ny;
+    // padded tile: flat index walked incrementally, four independent loads in flight per thread
+    {
+        constexpr int sx = kGatherThreads % P, sy = (kGatherThreads / P) % P, sz = kGatherThreads / (P * P);
+        int px = threadIdx.x % P, py = (threadIdx.x / P) % P, pz = threadIdx.x / (P * P);
+        const unsigned mx = g.nx - 1, my = g.ny - 1;
+        constexpr int P3 = P * P * P, U = 4;
+        for (int idx0 = threadIdx.x; idx0 < P3; idx0 += U * kGatherThreads) {
+            float v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                v[u] = 0.f;
+                if (idx0 + u * kGatherThreads < P3) {
+                    const unsigned x = (unsigned)(ox + px) & mx, y = (unsigned)(oy + py) & my;
+                    int zl = oz + pz;                                    // local plane; -1 and nz are the ghost planes of a slab
+                    const float* src = nullptr;
+                    if (g.slab) {
+                        if (zl == -1) src = ghost;
+                        else if (zl == (int)g.nz) src = ghost + plane;
+                        else if (zl >= 0 && zl < (int)g.nz) src = inv + plane * (size_t)zl;
+                    } else {
+                        src = inv + plane * (size_t)((unsigned)zl & (g.nz - 1));
+                    }
+                    if (src) v[u] = __ldg(src + ((y << g.lgx) | x));
+                }
+                px += sx; py += sy; pz += sz;
+                if (px >= P) { px -= P; ++py; }
+                if (py >= P) { py -= P; ++pz; }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (idx0 + u * kGatherThreads < P3) ftile[idx0 + u * kGatherThreads] = v[u];
         }
     }
     __syncthreads();
     const float scale = (float)(fp.two_over_n * *d_bias);
-    for (unsigned j = s + threadIdx.x; j < e; j += kGatherThreads) {
-        const unsigned local = __ldg(skey + j) & ((1u << (3 * LGT)) - 1);
-        const unsigned lx = local & (T - 1), ly = (local >> LGT) & (T - 1), lz = local >> (2 * LGT);
-        force[__ldg(perm + j)] = gather_force(sorted[j], (tx << LGT) + lx, (ty << LGT) + ly, g.z0 + (tz << LGT) + lz, lx, ly, lz, tile, g, fp, scale);
+    unsigned j = s + threadIdx.x;
+    unsigned n = 0;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < e) { n = __ldg(perm + j); p = __ldg(postype + n); }
+    while (j < e) {
+        const unsigned jn = j + kGatherThreads;
+        unsigned n_next = 0;
+        float4 p_next = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (jn < e) { n_next = __ldg(perm + jn); p_next = __ldg(postype + n_next); }
+        const Cell c = particle_cell(p, g);
+        float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c.owned) {
+            const float a = __ldg(mode + __float_as_int(p.w));
+            GatherWeights w;
+            gather_weights(p, c, g, w);
+            unsigned lx, ly, lz;
+            float Sx, Sy, Sz;
+            if (padded_coords(c, ox, oy, oz, g, P, lx, ly, lz)) {
+                gather_sums(ftile + ((lz - 1) * P + (ly - 1)) * P + (lx - 1), P, P * P, w.wx, w.wy, w.wz, w.dx, w.dy, w.dz, Sx, Sy, Sz);
+            } else {
+                GatherDirectArgs da;
+                da.inv = inv; da.ghost = ghost; da.g = &g;
+                const float3 S = gather_direct(p, da);
+                Sx = S.x; Sy = S.y; Sz = S.z;
+            }
+            f = force_from_sums(Sx, Sy, Sz, a, fp, scale);
+        }
+        force[n] = f;
+        j = jn; n = n_next; p = p_next;
     }
 }
 #endif  // __CUDACC__

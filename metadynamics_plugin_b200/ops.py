@@ -127,8 +127,7 @@ class Mesh:
     def inv(self):
         return self._mesh(2)
 
-    STAGES = ("bin", "scan", "reorder", "spread", "merge", "fft_x_fwd", "fft_y_fwd", "fft_z_fused", "fft_y_inv", "fft_x_inv",
-              "gather")
+    STAGES = ("tile_order", "spread", "fft_x_fwd", "fft_y_fwd", "fft_z_fused", "fft_y_inv", "fft_x_inv", "gather")
 
     def timings(self):
         """Per-stage milliseconds of the last compute_cv + forces pair (profiling knob 2 must be on)."""
@@ -140,6 +139,13 @@ class Mesh:
         out = np.empty(1, dtype=np.float64)
         check(lib.metad_mesh_get(self.h, 3, out.ctypes.data_as(C.c_void_p)))
         return float(out[0])
+
+    def stats(self):
+        """Tile-order / fixed-point statistics of the last spread (synchronises)."""
+        out = np.empty(6, dtype=np.float64)
+        check(lib.metad_mesh_get(self.h, 5, out.ctypes.data_as(C.c_void_p)))
+        return dict(rebuilds=int(out[0]), drifted=int(out[1]), outside_slab=int(out[2]), range_warnings=int(out[3]),
+                    fx_scale=float(out[4]), calls_since_rebuild=int(out[5]))
 
 
 class BiasGrid:

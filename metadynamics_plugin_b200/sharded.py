@@ -122,10 +122,12 @@ class MeshSlabRank:
         self.h = C.c_void_p()
         check(lib.metad_mesh_slab_create(C.byref(self.h), nx, ny, nz, n_ranks, rank, len(m), m.ctypes.data_as(C.POINTER(C.c_double))))
         f32, f64 = dict(dtype=torch.float32, device=device), dict(dtype=torch.float64, device=device)
+        i32 = dict(dtype=torch.int32, device=device)
         m_local = nx * ny * self.nzl
         self.sums = torch.zeros(3, **f64)
-        self.ghost_send = torch.zeros(2, ny, nx, **f32)
-        self.ghost_recv = torch.zeros(2, ny, nx, **f32)
+        # fixed-point density halo messages: ny*nx ints + 4 trailing ints carrying the sender's scale
+        self.ghost_send = torch.zeros(2, ny * nx + 4, **i32)
+        self.ghost_recv = torch.zeros(2, ny * nx + 4, **i32)
         self.send = torch.empty(m_local, **f32)            # packed half spectrum of the slab: [dest][plane][y][kx]
         self.pencil = torch.empty(m_local, **f32)          # [nz][ny][kxl] complex
         self.cv = torch.zeros(1, **f64)
@@ -165,6 +167,12 @@ class MeshSlabRank:
         out = np.empty((self._n, 3), dtype=np.int32)
         check(lib.metad_mesh_get(self.h, 0, out.ctypes.data_as(C.c_void_p)))
         return out
+
+    def stats(self):
+        out = np.empty(6, dtype=np.float64)
+        check(lib.metad_mesh_get(self.h, 5, out.ctypes.data_as(C.c_void_p)))
+        return dict(rebuilds=int(out[0]), drifted=int(out[1]), outside_slab=int(out[2]), range_warnings=int(out[3]),
+                    fx_scale=float(out[4]), calls_since_rebuild=int(out[5]))
 
     def local_mesh(self, which):
         nx, ny, _ = self.dims

@@ -1,34 +1,37 @@
 // mesh_emul.cu -- CPU emulation of the whole OrderParameterMesh device pipeline (host-only program, built with
-// nvcc, runs without a GPU).  bin -> counting sort (place + stable reorder) -> spread (thread per cell column,
-// rolling accumulators, replica exchange) -> merge -> FFT sweeps -> gather, using the SAME __host__ __device__
-// bodies as the kernels in csrc/mesh_kernels.cuh and csrc/mesh_fft_kernels.cuh, with the kernels' loop structure.
-// tests/test_emulation.py compares the dump against the oracle.
+// nvcc, runs without a GPU).  tile order (bin -> scan -> place) -> fixed-point spread (CTA per tile, padded integer
+// tile, direct path for drifted particles, flush) -> int-to-float + mean removal -> FFT sweeps -> gather, using the
+// SAME __host__ __device__ bodies as the kernels in csrc/mesh_kernels.cuh and csrc/mesh_fft_kernels.cuh, with the
+// kernels' loop structure.  tests/test_emulation.py compares the dump against the oracle.
 #include <cstring>
+#include <cmath>
 #include <algorithm>
 #include "../../metadynamics_plugin_b200/csrc/mesh_kernels.cuh"
 #include "emul_fft.h"
 
 using namespace metad::mesh;
 
-// usage: mesh_emul nx ny nz Lx Ly Lz N_global bias lgT ntypes mode... in.bin out.bin
+// usage: mesh_emul nx ny nz Lx Ly Lz N_global bias lgT stale ntypes mode... in.bin out.bin
+//   stale: the tile order is built from positions displaced by up to `stale` cells (the real positions are then
+//   spread / gathered through that stale order; displacements > kHalo - 1 exercise the direct path)
+static unsigned hash32(unsigned x) { x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16; return x; }
+
 int main(int argc, char** argv) {
-    if (argc < 13) { fprintf(stderr, "usage\n"); return 2; }
+    if (argc < 14) { fprintf(stderr, "usage\n"); return 2; }
     Geom g; memset(&g, 0, sizeof g);
     const unsigned nx = atoi(argv[1]), ny = atoi(argv[2]), nz = atoi(argv[3]);
     const double Ld[3] = {atof(argv[4]), atof(argv[5]), atof(argv[6])};
     const unsigned N_global = (unsigned)atol(argv[7]);
     const double bias = atof(argv[8]);
     geom_set_dims(g, nx, ny, nz, atoi(argv[9]));
-    const int ntypes = atoi(argv[10]);
+    const double stale = atof(argv[10]);
+    const int ntypes = atoi(argv[11]);
     std::vector<float> mode(ntypes);
-    for (int i = 0; i < ntypes; ++i) mode[i] = (float)atof(argv[11 + i]);
-    const char* fin = argv[11 + ntypes];
-    const char* fout = argv[12 + ntypes];
-    const unsigned n3[3] = {g.nx, g.ny, g.nz};
-    for (int i = 0; i < 3; ++i) {
-        g.L[i] = (float)Ld[i]; g.lo[i] = -(g.L[i] / 2.0f);
-        g.dlo[i] = -Ld[i] / 2.0; g.dscale[i] = (double)n3[i] / Ld[i];
-    }
+    float amax = 0.f;
+    for (int i = 0; i < ntypes; ++i) { mode[i] = (float)atof(argv[12 + i]); amax = std::max(amax, std::fabs(mode[i])); }
+    const char* fin = argv[12 + ntypes];
+    const char* fout = argv[13 + ntypes];
+    geom_set_box(g, Ld);
     FILE* f = fopen(fin, "rb");
     fseek(f, 0, SEEK_END); const long bytes = ftell(f); fseek(f, 0, SEEK_SET);
     const unsigned N = (unsigned)(bytes / 16);
@@ -36,98 +39,120 @@ int main(int argc, char** argv) {
     if (fread(postype.data(), 16, N, f) != N) return 2;
     fclose(f);
     const size_t M = (size_t)g.nx * g.ny * g.nz;
+    const unsigned n3[3] = {g.nx, g.ny, g.nz};
 
-    // ---- bin (mesh_bin_kernel)
-    std::vector<unsigned> keys(N), ranks(N), count(M, 0), start(M + 1), perm(N), slot(N), skey(N);
-    double sums[2] = {0, 0};
-    for (unsigned i = 0; i < N; ++i) {
-        const float4 p = postype[i];
-        const unsigned ix = cell_coord(p.x, g.lo[0], g.L[0], g.nx), iy = cell_coord(p.y, g.lo[1], g.L[1], g.ny),
-                       iz = cell_coord(p.z, g.lo[2], g.L[2], g.nz);
-        keys[i] = key_of(ix, iy, iz, g);
-        unsigned cx, cy, cz; cell_of_key(keys[i], g, cx, cy, cz);
-        if (cx != ix || cy != iy || cz != iz) { fprintf(stderr, "key round trip failed\n"); return 3; }
-        ranks[i] = count[keys[i]]++;
-        int t; memcpy(&t, &p.w, 4);
-        sums[0] += (double)mode[t] * mode[t]; sums[1] += (double)mode[t];
+    // ---- hot cell rule (Markstein division, magic truncation) against its reference form (IEEE division, C cast):
+    // the input particles, positions within a few ulps of every cell boundary, and random positions
+    unsigned long long cell_mismatch = 0;
+    {
+        auto check = [&](float x, int axis) {
+            const unsigned nn = axis == 0 ? g.nx : (axis == 1 ? g.ny : g.nzg);
+            if (cell_coord(x, axis, g) != cell_coord_ref(x, g.lo[axis], g.L[axis], nn)) ++cell_mismatch;
+        };
+        for (unsigned i = 0; i < N; ++i) { check(postype[i].x, 0); check(postype[i].y, 1); check(postype[i].z, 2); }
+        for (int axis = 0; axis < 3; ++axis) {
+            const unsigned nn = axis == 0 ? g.nx : (axis == 1 ? g.ny : g.nzg);
+            for (unsigned k = 0; k <= nn; ++k) {
+                float x = (float)(-Ld[axis] / 2.0 + (double)k * Ld[axis] / (double)nn);
+                float lo_side = x, hi_side = x;
+                for (int u = 0; u < 24; ++u) {
+                    check(lo_side, axis); check(hi_side, axis);
+                    lo_side = nextafterf(lo_side, -1e30f); hi_side = nextafterf(hi_side, 1e30f);
+                }
+            }
+            for (unsigned k = 0; k < 200000; ++k) {
+                const float u = (hash32(k * 7u + axis + 1000u) >> 8) * (1.0f / 16777216.0f);
+                check((u - 0.5f) * g.L[axis], axis);
+            }
+        }
     }
-    // ---- scan
+    // ---- tile order (mesh_bin_kernel / scan / mesh_place_kernel) from the displaced positions
+    std::vector<unsigned> keys(N), ranks(N), count(M, 0), start(M + 1), perm(N);
+    unsigned max_count = 0;
+    for (unsigned i = 0; i < N; ++i) {
+        float4 p = postype[i];
+        float* c = &p.x;
+        for (int d = 0; d < 3; ++d) {
+            const float u = (hash32(i * 3u + d + 17u) >> 8) * (1.0f / 16777216.0f);
+            float v = c[d] + (u - 0.5f) * 2.f * (float)(stale * Ld[d] / n3[d]);
+            if (v >= g.L[d] / 2.0f) v -= g.L[d];
+            if (v < -(g.L[d] / 2.0f)) v += g.L[d];
+            c[d] = v;
+        }
+        const Cell cc = particle_cell(p, g);
+        keys[i] = key_of(cc.ix, cc.iy, cc.iz, g);
+        unsigned cx, cy, cz; cell_of_key(keys[i], g, cx, cy, cz);
+        if ((int)cx != cc.ix || (int)cy != cc.iy || (int)cz != cc.iz) { fprintf(stderr, "key round trip failed\n"); return 3; }
+        ranks[i] = count[keys[i]]++;
+        max_count = std::max(max_count, ranks[i] + 1);
+    }
     unsigned run = 0;
     for (size_t c = 0; c < M; ++c) { start[c] = run; run += count[c]; }
     start[M] = run;
-    // ---- place (mesh_place_kernel); the arrival rank of the device is arbitrary: emulate it reversed
-    for (unsigned i = 0; i < N; ++i) slot[start[keys[i]] + (count[keys[i]] - 1 - ranks[i])] = i;
-    // ---- stable reorder (mesh_reorder_kernel, one thread per slot)
-    std::vector<float4> sorted(N);
-    for (unsigned j = 0; j < N; ++j) {
-        const unsigned i = slot[j], key = keys[i], s = start[key], e = start[key + 1];
-        unsigned dst = s;
-        for (unsigned m = s; m < e; ++m) dst += slot[m] < i ? 1u : 0u;
-        float4 p = postype[i];
-        int t; memcpy(&t, &p.w, 4);
-        p.w = mode[t];
-        sorted[dst] = p; perm[dst] = i; skey[dst] = key;
-    }
-    for (unsigned j = 1; j < N; ++j)
-        if (skey[j] == skey[j - 1] && perm[j] < perm[j - 1]) { fprintf(stderr, "order inside a cell is not stable\n"); return 3; }
-    // ---- spread (mesh_spread_kernel): thread per column, rolling accumulators, replica exchange
-    const unsigned T = 1u << g.lgT, P = T + 2, PP = P * P, P3 = PP * P, NT = T * T, ntiles = num_tiles(g);
-    const unsigned CAP = 8;     // tiny chunk capacity: exercises the multi-chunk path
-    std::vector<float> scratch((size_t)ntiles * P3);
-    std::vector<float> tile(P3);
+    // the arrival rank of the device is arbitrary: emulate it reversed
+    for (unsigned i = 0; i < N; ++i) perm[start[keys[i]] + (count[keys[i]] - 1 - ranks[i])] = i;
+    const unsigned T = 1u << g.lgT, P = T + 2 * kHalo, P3 = P * P * P, ntiles = num_tiles(g);
+    std::vector<unsigned> tstart(ntiles + 1);
+    for (unsigned t = 0; t <= ntiles; ++t) tstart[t] = start[(size_t)t << (3 * g.lgT)];
+    const float scale = fx_scale_for(amax, amax * (float)max_count);
+    const float inv_scale = 1.0f / scale;
+
+    // ---- spread (mesh_spread_kernel): CTA per tile, integer padded tile, flush into the integer mesh
+    std::vector<int> mesh_i(M, 0), tile(P3);
+    std::vector<unsigned> cell_keys(N);
+    double sums[2] = {0, 0}, shift_err = 0.0;
+    unsigned strays = 0;
     for (unsigned tile_id = 0; tile_id < ntiles; ++tile_id) {
         unsigned tx, ty, tz; tile_coords(tile_id, g, tx, ty, tz);
-        std::vector<float> acc(NT * 27, 0.f);
-        std::vector<float> wbuf(9 * CAP), rep(9 * PP);
-        float* out = scratch.data() + (size_t)tile_id * P3;
-        for (unsigned lz = 0; lz < T + 2; ++lz) {
-            if (lz < T) {
-                const unsigned key0 = (tile_id << (3 * g.lgT)) + lz * NT;
-                const unsigned s_plane = start[key0], e_plane = start[key0 + NT];
-                for (unsigned c0 = s_plane; c0 < e_plane; c0 += CAP) {
-                    const unsigned c1 = std::min(c0 + CAP, e_plane);
-                    for (unsigned j = c0; j < c1; ++j) {                       // phase 1
-                        const unsigned local = skey[j] & (NT - 1);
-                        float w[9];
-                        spread_weights(sorted[j], (tx << g.lgT) + (local & (T - 1)), (ty << g.lgT) + (local >> g.lgT), (tz << g.lgT) + lz, g, w);
-                        for (int c = 0; c < 9; ++c) wbuf[c * CAP + (j - c0)] = w[c];
-                    }
-                    for (unsigned tid = 0; tid < NT; ++tid) {                  // phase 2
-                        const unsigned s = start[key0 + tid], e = start[key0 + tid + 1];
-                        const unsigned a = std::max(s, c0), b = std::min(e, c1);
-                        float (&ac)[27] = *reinterpret_cast<float (*)[27]>(&acc[tid * 27]);
-                        for (unsigned j = a; j < b; ++j) {
-                            float w[9]; for (int c = 0; c < 9; ++c) w[c] = wbuf[c * CAP + (j - c0)];
-                            spread_accumulate9(w, ac);
-                        }
-                    }
+        const int ox = (int)(tx << g.lgT) - kHalo, oy = (int)(ty << g.lgT) - kHalo, oz = (int)(tz << g.lgT) - kHalo;
+        std::fill(tile.begin(), tile.end(), 0);
+        double sq = 0.0, s1 = 0.0;
+        for (unsigned j = tstart[tile_id]; j < tstart[tile_id + 1]; ++j) {
+            const unsigned n = perm[j];
+            const float4 p = postype[n];
+            int t; memcpy(&t, &p.w, 4);
+            const float a = mode[t];
+            const Cell c = particle_cell(p, g);
+            cell_keys[n] = key_of(c.ix, c.iy, c.iz, g);
+            sq += (double)a * (double)a; s1 += (double)a;
+            float w[9];
+            spread_weights(p, c, a * scale, g, w);
+            const float xyz[3] = {p.x, p.y, p.z};
+            const int cxyz[3] = {c.ix, c.iy, c.iz};
+            for (int d = 0; d < 3; ++d)
+                shift_err = std::max(shift_err, (double)std::fabs(cell_shift(xyz[d], cxyz[d], d, g) - cell_shift_f64(xyz[d], cxyz[d], d, g)));
+            unsigned lx, ly, lz;
+            if (padded_coords(c, ox, oy, oz, g, P, lx, ly, lz)) {
+                int* base = tile.data() + ((lz - 1) * P + (ly - 1)) * P + (lx - 1);
+                for (int k = 0; k < 3; ++k) for (int jj = 0; jj < 3; ++jj) {
+                    const float wyz = f_mul(w[3 + jj], w[6 + k]);
+                    for (int i = 0; i < 3; ++i) base[(k * P + jj) * P + i] += fx_round(w[i], wyz);
+                }
+            } else {
+                ++strays;
+                for (int k = 0; k < 3; ++k) for (int jj = 0; jj < 3; ++jj) for (int i = 0; i < 3; ++i) {
+                    long long idx;
+                    if (tap_index(c, i, jj, k, g, idx)) mesh_i[idx] += tap_value(w, i, jj, k);
                 }
             }
-            std::fill(rep.begin(), rep.end(), 1e30f);                          // poison: unwritten replicas must not be read
-            for (unsigned tid = 0; tid < NT; ++tid) {
-                const unsigned lx = tid & (T - 1), ly = tid >> g.lgT;
-                for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) rep[replica_index(i * 3 + j, lx + i, ly + j, P)] = acc[tid * 27 + i * 3 + j];
+        }
+        sums[0] += sq; sums[1] += s1;
+        for (unsigned idx = 0; idx < P3; ++idx) {
+            const int v = tile[idx];
+            if (v != 0) {
+                const int px = idx % P, py = (idx / P) % P, pz = idx / (P * P);
+                const unsigned x = (unsigned)(ox + px) & (g.nx - 1), y = (unsigned)(oy + py) & (g.ny - 1), z = (unsigned)(oz + pz) & (g.nz - 1);
+                mesh_i[(size_t)x + (size_t)g.nx * (y + (size_t)g.ny * z)] += v;
             }
-            for (unsigned idx = 0; idx < PP; ++idx) out[(size_t)lz * PP + idx] = reduce_replicas(rep.data(), idx % P, idx / P, T);
-            for (unsigned tid = 0; tid < NT; ++tid)
-                for (int r = 0; r < 9; ++r) { acc[tid * 27 + r] = acc[tid * 27 + 9 + r]; acc[tid * 27 + 9 + r] = acc[tid * 27 + 18 + r]; acc[tid * 27 + 18 + r] = 0.f; }
         }
     }
-    // ---- merge (mesh_merge_kernel incl. its interior fast path)
+    // ---- x forward load phase (fft_x_fwd_kernel): int -> float, mean removal
     std::vector<float> rho(M), buf(M);
-    const float mean = (float)(sums[1] / (double)M);
-    for (size_t c = 0; c < M; ++c) {
-        const unsigned x = (unsigned)(c & (g.nx - 1)), y = (unsigned)((c >> g.lgx) & (g.ny - 1)), z = (unsigned)(c >> (g.lgx + g.lgy));
-        const unsigned lx = x & (T - 1), ly = y & (T - 1), lz = z & (T - 1);
-        float v;
-        if (lx != 0 && lx != T - 1 && ly != 0 && ly != T - 1 && lz != 0 && lz != T - 1) {
-            const unsigned t = tile_index(x >> g.lgT, y >> g.lgT, z >> g.lgT, g);
-            v = scratch[(size_t)t * P3 + ((lz + 1) * P + (ly + 1)) * P + (lx + 1)];
-        } else {
-            v = merge_cell(scratch.data(), x, y, z, g);
-        }
-        rho[c] = v;
-        buf[c] = v - mean;
+    const float mean = (float)(sums[1] * (1.0 / (double)M));
+    for (size_t c = 0; c < M; c += 2) {
+        const float2 r = density_to_float(make_int2(mesh_i[c], mesh_i[c + 1]), inv_scale);
+        rho[c] = r.x; rho[c + 1] = r.y;
+        buf[c] = r.x - mean; buf[c + 1] = r.y - mean;
     }
     // ---- FFT sweeps
     float2* b2 = reinterpret_cast<float2*>(buf.data());
@@ -146,31 +171,50 @@ int main(int argc, char** argv) {
     ForceParams fp; memset(&fp, 0, sizeof fp);
     fp.nb1[0] = (float)((double)g.nx / Ld[0]); fp.nb2[1] = (float)((double)g.ny / Ld[1]); fp.nb3[2] = (float)((double)g.nz / Ld[2]);
     fp.two_over_n = 2.0 / (double)N_global;
-    const float scale = (float)(fp.two_over_n * bias);
+    const float fscale = (float)(fp.two_over_n * bias);
     std::vector<float4> force(N);
+    std::vector<float> ftile(P3);
     for (unsigned tile_id = 0; tile_id < ntiles; ++tile_id) {
         unsigned tx, ty, tz; tile_coords(tile_id, g, tx, ty, tz);
-        for (unsigned row = 0; row < PP; ++row) {
+        const int ox = (int)(tx << g.lgT) - kHalo, oy = (int)(ty << g.lgT) - kHalo, oz = (int)(tz << g.lgT) - kHalo;
+        for (unsigned row = 0; row < P * P; ++row) {
             const unsigned py = row % P, pz = row / P;
-            const unsigned y = ((ty << g.lgT) + py + g.ny - 1) & (g.ny - 1), z = ((tz << g.lgT) + pz + g.nz - 1) & (g.nz - 1);
+            const unsigned y = (unsigned)(oy + (int)py) & (g.ny - 1), z = (unsigned)(oz + (int)pz) & (g.nz - 1);
             for (unsigned lane = 0; lane < P; ++lane) {
-                const unsigned x = ((tx << g.lgT) + lane + g.nx - 1) & (g.nx - 1);
-                tile[row * P + lane] = buf[(size_t)x + (size_t)g.nx * (y + (size_t)g.ny * z)];
+                const unsigned x = (unsigned)(ox + (int)lane) & (g.nx - 1);
+                ftile[row * P + lane] = buf[(size_t)x + (size_t)g.nx * (y + (size_t)g.ny * z)];
             }
         }
-        const unsigned s = start[tile_id << (3 * g.lgT)], en = start[(tile_id + 1) << (3 * g.lgT)];
-        for (unsigned j = s; j < en; ++j) {
-            const unsigned local = skey[j] & ((1u << (3 * g.lgT)) - 1);
-            const unsigned lx = local & (T - 1), ly = (local >> g.lgT) & (T - 1), lz = local >> (2 * g.lgT);
-            force[perm[j]] = gather_force(sorted[j], (tx << g.lgT) + lx, (ty << g.lgT) + ly, (tz << g.lgT) + lz, lx, ly, lz, tile.data(), g, fp, scale);
+        for (unsigned j = tstart[tile_id]; j < tstart[tile_id + 1]; ++j) {
+            const unsigned n = perm[j];
+            const float4 p = postype[n];
+            int t; memcpy(&t, &p.w, 4);
+            const Cell c = particle_cell(p, g);
+            GatherWeights w;
+            gather_weights(p, c, g, w);
+            unsigned lx, ly, lz;
+            float Sx, Sy, Sz;
+            if (padded_coords(c, ox, oy, oz, g, P, lx, ly, lz)) {
+                gather_sums(ftile.data() + ((lz - 1) * P + (ly - 1)) * P + (lx - 1), P, P * P, w.wx, w.wy, w.wz, w.dx, w.dy, w.dz, Sx, Sy, Sz);
+            } else {        // gather_direct
+                float t27[27];
+                for (int k = 0; k < 3; ++k) for (int jj = 0; jj < 3; ++jj) for (int i = 0; i < 3; ++i) {
+                    const unsigned x = (unsigned)(c.ix + i - 1) & (g.nx - 1), y = (unsigned)(c.iy + jj - 1) & (g.ny - 1), z = (unsigned)(c.iz + k - 1) & (g.nz - 1);
+                    t27[(k * 3 + jj) * 3 + i] = buf[(size_t)x + (size_t)g.nx * (y + (size_t)g.ny * z)];
+                }
+                gather_sums(t27, 3, 9, w.wx, w.wy, w.wz, w.dx, w.dy, w.dz, Sx, Sy, Sz);
+            }
+            force[n] = force_from_sums(Sx, Sy, Sz, mode[t], fp, fscale);
         }
     }
-    // ---- dump: cv, mode_sq, rho[M], inv[M], force[4N], cells[3N]
+    // ---- dump: cv, mode_sq, shift_err, strays, scale, cell rule mismatches, rho[M], inv[M], force[4N], cells[3N]
     f = fopen(fout, "wb");
-    fwrite(&cv, 8, 1, f); fwrite(&sums[0], 8, 1, f);
+    const double dstrays = strays, dscale = scale, dmis = (double)cell_mismatch;
+    fwrite(&cv, 8, 1, f); fwrite(&sums[0], 8, 1, f); fwrite(&shift_err, 8, 1, f); fwrite(&dstrays, 8, 1, f); fwrite(&dscale, 8, 1, f);
+    fwrite(&dmis, 8, 1, f);
     fwrite(rho.data(), 4, M, f); fwrite(buf.data(), 4, M, f); fwrite(force.data(), 16, N, f);
     std::vector<int> cells(3 * (size_t)N);
-    for (unsigned i = 0; i < N; ++i) { unsigned ix, iy, iz; cell_of_key(keys[i], g, ix, iy, iz); cells[3 * i] = ix; cells[3 * i + 1] = iy; cells[3 * i + 2] = iz; }
+    for (unsigned i = 0; i < N; ++i) { unsigned ix, iy, iz; cell_of_key(cell_keys[i], g, ix, iy, iz); cells[3 * i] = ix; cells[3 * i + 1] = iy; cells[3 * i + 2] = iz; }
     fwrite(cells.data(), 4, cells.size(), f);
     fclose(f);
     return 0;

@@ -57,55 +57,89 @@ def test_fft_sweeps_match_numpy(dims):
     assert np.abs(out - inv).max() < 2e-6 * np.abs(inv).max()
 
 
-def run_mesh(exe, pt, dims, L, n_global, bias, lgT, modes):
+def run_mesh(exe, pt, dims, L, n_global, bias, lgT, modes, stale=0.0):
     nx, ny, nz = dims
     N = pt.shape[0]
     with tempfile.TemporaryDirectory() as d:
         fin, fout = os.path.join(d, "in.bin"), os.path.join(d, "out.bin")
         pt.tofile(fin)
         subprocess.check_call([exe, str(nx), str(ny), str(nz)] + [repr(float(x)) for x in L] + [str(n_global), repr(bias), str(lgT),
-                              str(len(modes))] + [repr(float(m)) for m in modes] + [fin, fout])
+                              repr(float(stale)), str(len(modes))] + [repr(float(m)) for m in modes] + [fin, fout])
         raw = np.fromfile(fout, dtype=np.uint8)
     M = nx * ny * nz
-    cv, msq = raw[:16].view(np.float64)
-    o = 16
+    cv, msq, shift_err, strays, scale, mismatch = raw[:48].view(np.float64)
+    o = 48
     rho = raw[o:o + 4 * M].view(np.float32).reshape(nz, ny, nx); o += 4 * M
     inv = raw[o:o + 4 * M].view(np.float32).reshape(nz, ny, nx); o += 4 * M
     force = raw[o:o + 16 * N].view(np.float32).reshape(N, 4); o += 16 * N
     cells = raw[o:o + 12 * N].view(np.int32).reshape(N, 3)
-    return cv, msq, rho, inv, force, cells
+    return dict(cv=cv, msq=msq, shift_err=shift_err, strays=int(strays), scale=scale, cell_mismatch=int(mismatch), rho=rho, inv=inv,
+                force=force, cells=cells)
 
 
-@pytest.mark.parametrize("N,dims,L,lgT,modes,edge", [
-    (1000, (32, 32, 32), (10.0, 10.0, 10.0), 3, (1.0,), False),
-    (1000, (32, 32, 32), (10.0, 10.0, 10.0), 4, (1.0,), True),
-    (5000, (32, 16, 64), (10.0, 7.3, 21.1), 3, (1.0, -1.0), True),
-    (5000, (64, 32, 16), (10.0, 7.3, 21.1), 4, (1.0, -0.5, 2.0), True),
-    (30000, (32, 32, 32), (31.0, 31.0, 31.0), 3, (1.0,), False),
-])
-def test_mesh_pipeline_matches_oracle(oracle, N, dims, L, lgT, modes, edge):
-    exe = build_emul("mesh_emul")
-    rng = np.random.default_rng(N + lgT)
+def mesh_case(N, dims, L, modes, edge, seed):
+    rng = np.random.default_rng(seed)
     Lf = np.asarray(L, dtype=np.float64)
     pos = ((rng.random((N, 3)) - 0.5) * Lf).astype(np.float32)
     if edge:      # particles on the upper faces, on the lower corner and one ulp inside
         pos[0] = [np.float32(Lf[0]) / 2, 0, 0]
         pos[1] = [-np.float32(Lf[0]) / 2, np.float32(Lf[1]) / 2, -np.float32(Lf[2]) / 2]
         pos[2] = np.nextafter((Lf / 2).astype(np.float32), np.float32(0))
-    pt = oracle.make_postype(pos, rng.integers(0, len(modes), N))
+    return pos, rng.integers(0, len(modes), N)
+
+
+@pytest.mark.parametrize("N,dims,L,lgT,modes,edge,stale", [
+    (1000, (32, 32, 32), (10.0, 10.0, 10.0), 3, (1.0,), False, 0.0),
+    (1000, (32, 32, 32), (10.0, 10.0, 10.0), 4, (1.0,), True, 0.9),
+    (5000, (32, 16, 64), (10.0, 7.3, 21.1), 3, (1.0, -1.0), True, 0.9),
+    (5000, (64, 32, 16), (10.0, 7.3, 21.1), 4, (1.0, -0.5, 2.0), True, 3.5),      # stale order beyond the halo: direct path
+    (30000, (32, 32, 32), (31.0, 31.0, 31.0), 3, (1.0,), False, 2.5),
+])
+def test_mesh_pipeline_matches_oracle(oracle, N, dims, L, lgT, modes, edge, stale):
+    exe = build_emul("mesh_emul")
+    pos, types = mesh_case(N, dims, L, modes, edge, N + lgT)
+    pt = oracle.make_postype(pos, types)
     bias = 0.7
-    cv, msq, rho, inv, force, cells = run_mesh(exe, pt, dims, L, N, bias, lgT, modes)
+    r = run_mesh(exe, pt, dims, L, N, bias, lgT, modes, stale)
     m = oracle.Mesh(*dims, modes, L, N, "f64", literal_copysignf=False)
     cvo = m.current_value(pt)
     fo = m.forces(pt, bias)
     m32 = oracle.Mesh(*dims, modes, L, N, "f32")
     m32.assign(pt)
-    assert np.array_equal(cells, m32.cells())                       # bit-exact against the single-precision build
-    assert msq == m.mode_sq()
-    assert cv == pytest.approx(cvo, rel=1e-6)                       # north-star tolerance for CVs
-    assert np.abs(rho - m.mesh).max() < 2e-6 * max(1.0, np.abs(m.mesh).max())
-    dinv = inv - m.inv_re
+    assert np.array_equal(r["cells"], m32.cells())                  # bit-exact against the single-precision build
+    assert r["msq"] == m.mode_sq()
+    assert r["cell_mismatch"] == 0                                  # division-free cell rule == IEEE division + C truncation
+    assert r["shift_err"] < 1e-7                                    # compensated fp32 in-cell offset vs its fp64 form
+    assert (r["strays"] > 0) == (stale > 2.0)
+    assert r["cv"] == pytest.approx(cvo, rel=1e-6)                  # north-star tolerance for CVs
+    assert np.abs(r["rho"] - m.mesh).max() < 2e-6 * max(1.0, np.abs(m.mesh).max())
+    dinv = r["inv"] - m.inv_re
     dinv -= dinv.mean()                                             # DC removal shifts the inverse mesh by a constant
     assert np.abs(dinv).max() < 5e-6 * np.abs(m.inv_re - m.inv_re.mean()).max()
-    assert np.abs(force - fo).max() < 1e-5 * np.abs(fo).max()       # north-star tolerance for forces
-    assert np.all(force[:, 3] == 0)
+    assert np.abs(r["force"] - fo).max() < 1e-5 * np.abs(fo).max()  # north-star tolerance for forces
+    assert np.all(r["force"][:, 3] == 0)
+
+
+def test_mesh_density_is_order_independent(oracle):
+    """Integer accumulation: the density, the CV and the forces are bitwise independent of the tile order."""
+    exe = build_emul("mesh_emul")
+    dims, L, modes, N = (32, 32, 32), (12.0, 12.0, 12.0), (1.0, -0.7), 4000
+    pos, types = mesh_case(N, dims, L, modes, True, 99)
+    pt = oracle.make_postype(pos, types)
+    ref = run_mesh(exe, pt, dims, L, N, 0.3, 3, modes, 0.0)
+    for lgT, stale in ((3, 0.9), (3, 4.0), (4, 0.0), (4, 6.0)):
+        r = run_mesh(exe, pt, dims, L, N, 0.3, lgT, modes, stale)
+        assert np.array_equal(r["rho"], ref["rho"])
+        assert r["cv"] == ref["cv"]
+        assert np.array_equal(r["force"], ref["force"])
+
+
+def test_fixed_point_scale_bounds():
+    """fx_scale_for keeps one tap below 2^22 and a full cell below 2^31/4 (host copy of the rule in mesh_kernels.cuh)."""
+    for amax, load in ((1.0, 1.0), (1.0, 10.0), (1e-3, 5e-3), (250.0, 4000.0), (1.0, 1e6)):
+        tap = 2.0 ** 22 / (0.421875 * amax)
+        tot = 2.0 ** 31 / (4 * 5.359375 * max(load, amax))
+        lim = min(tap, tot)
+        s = 2.0 ** np.floor(np.log2(lim))
+        assert s <= lim < 2 * s
+        assert 0.421875 * amax * s < 2 ** 22 and 5.359375 * load * s <= 2 ** 29

@@ -117,6 +117,7 @@ def test_mesh_cv_forces_cells(gpu, oracle, N, dims, L, modes, edge):
     box = gpu.Box.make(Lf)
     mesh = gpu.Mesh(*dims, modes)
     mesh.set(1, 1)                                               # keep rho for inspection
+    mesh.set(3, 1)                                               # keep the cell indices computed by the spread
     cv = mesh.compute_cv(d_pt, N, box).cpu().item()
     m = oracle.Mesh(*dims, modes, Lf, N, "f64", literal_copysignf=False)
     cvo = m.current_value(h_pt)
@@ -131,28 +132,123 @@ def test_mesh_cv_forces_cells(gpu, oracle, N, dims, L, modes, edge):
     fo = m.forces(h_pt, 0.61)
     assert np.abs(f - fo).max() < 1e-5 * np.abs(fo).max()
     assert np.all(f[:, 3] == 0)
-    # determinism: a second evaluation is bitwise identical (no float atomics, fixed summation orders)
+    # determinism: a second evaluation is bitwise identical (integer density accumulation, fixed summation orders)
     cv2 = mesh.compute_cv(d_pt, N, box).cpu().item()
     f2 = mesh.forces(d_pt, N, box, bias).cpu().numpy()
     assert cv2 == cv and np.array_equal(f, f2)
+    st = mesh.stats()
+    assert st["rebuilds"] == 1 and st["drifted"] == 0 and st["outside_slab"] == 0 and st["range_warnings"] == 0
 
 
 def test_mesh_order_independence(gpu):
-    """Shuffling the particle array permutes the forces and leaves CV / forces bitwise unchanged."""
+    """Shuffling the particle array permutes the forces and leaves density / CV / forces BITWISE unchanged
+    (the density is accumulated in integers)."""
     import torch
     N, dims, L = 40000, (64, 64, 64), 30.0
-    pos, types = rand_pt(N, L, 1, 5)
+    pos, types = rand_pt(N, L, 2, 5)
     box = gpu.Box.make(L)
-    mesh = gpu.Mesh(*dims, [1.0])
+    mesh = gpu.Mesh(*dims, [1.0, -0.4])
+    mesh.set(1, 1)
     bias = torch.tensor([1.0], dtype=torch.float64, device="cuda")
-    cv = mesh.compute_cv(to_dev(gpu, pos, types), N, box).cpu().item()
-    f = mesh.forces(to_dev(gpu, pos, types), N, box, bias).cpu().numpy()
+    d1 = to_dev(gpu, pos, types)
+    cv = mesh.compute_cv(d1, N, box).cpu().item()
+    rho = mesh.rho()
+    f = mesh.forces(d1, N, box, bias).cpu().numpy()
     perm = np.random.default_rng(0).permutation(N)
     d2 = to_dev(gpu, pos[perm], types[perm])
-    cv2 = mesh.compute_cv(d2, N, box).cpu().item()
-    f2 = mesh.forces(d2, N, box, bias).cpu().numpy()
-    assert cv2 == pytest.approx(cv, rel=1e-6)
-    assert np.abs(f2 - f[perm]).max() < 1e-5 * np.abs(f).max()
+    mesh2 = gpu.Mesh(*dims, [1.0, -0.4])
+    mesh2.set(1, 1)
+    cv2 = mesh2.compute_cv(d2, N, box).cpu().item()
+    f2 = mesh2.forces(d2, N, box, bias).cpu().numpy()
+    assert np.array_equal(mesh2.rho(), rho)
+    assert cv2 == cv
+    assert np.array_equal(f2, f[perm])
+
+
+def test_mesh_stale_tile_order(gpu, oracle):
+    """The tile order is reused across calls while the particles move: every call is still exact (cells are recomputed
+    from the current positions), drifted particles take the direct path and trigger a rebuild; results are bitwise those
+    of a fresh plan."""
+    import torch
+    N, dims, L = 60000, (64, 64, 64), 40.0
+    rng = np.random.default_rng(11)
+    pos, types = rand_pt(N, L, 2, 3)
+    modes = [1.0, -1.0]
+    box = gpu.Box.make(L)
+    bias = torch.tensor([0.9], dtype=torch.float64, device="cuda")
+    mesh = gpu.Mesh(*dims, modes)
+    mesh.set(0, 1000)                                    # never rebuild on the period
+    mesh.set(3, 1)
+    h = L / dims[0]
+    rebuilds = []
+    for step, amp in enumerate((0.0, 0.3, 0.3, 0.3, 2.5, 0.0, 0.0)):      # displacement per step in cells
+        pos = pos + (rng.random((N, 3)).astype(np.float32) - 0.5) * np.float32(2 * amp * h)
+        pos = (((pos + L / 2) % L) - L / 2).astype(np.float32)
+        pos[pos >= np.float32(L / 2)] = -np.float32(L / 2)
+        d_pt = to_dev(gpu, pos, types)
+        cv = mesh.compute_cv(d_pt, N, box).cpu().item()
+        f = mesh.forces(d_pt, N, box, bias).cpu().numpy()
+        st = mesh.stats()
+        rebuilds.append(st["rebuilds"])
+        fresh = gpu.Mesh(*dims, modes)
+        cvf = fresh.compute_cv(d_pt, N, box).cpu().item()
+        ff = fresh.forces(d_pt, N, box, bias).cpu().numpy()
+        assert cv == cvf and np.array_equal(f, ff), step
+        if step in (0, 4):
+            h_pt = host_pt(oracle, pos, types)
+            m = oracle.Mesh(*dims, modes, [L] * 3, N, "f64", literal_copysignf=False)
+            assert cv == pytest.approx(m.current_value(h_pt), rel=1e-6)
+            fo = m.forces(h_pt, 0.9)
+            assert np.abs(f - fo).max() < 1e-5 * np.abs(fo).max()
+            m32 = oracle.Mesh(*dims, modes, [L] * 3, N, "f32")
+            m32.assign(h_pt)
+            assert np.array_equal(mesh.cells(), m32.cells())
+        if step == 4:
+            assert st["drifted"] > N // 256              # the big move left many particles outside their padded tile
+    assert rebuilds[0] == 1 and rebuilds[4] == 1         # small moves reuse the order ...
+    assert rebuilds[-1] == 2                             # ... the drift report triggers exactly one rebuild
+    mesh.set(0, 2)                                       # periodic rebuild
+    for _ in range(4):
+        mesh.compute_cv(d_pt, N, box)
+    assert mesh.stats()["rebuilds"] == 4
+
+
+@pytest.mark.parametrize("sigma,cv_tol", [(3.0, 1e-6), (0.8, None)])
+def test_mesh_dense_cells_fixed_point_range(gpu, oracle, sigma, cv_tol):
+    """Many particles per cell and large mode coefficients: the fixed-point scale adapts (no range warnings).  The 32-bit
+    range is shared between the per-particle resolution and the largest cell total, so the precision of the density is
+    ~1e-9 x (largest number of particles in a cell) relative to one particle (CV: < 2e-8 x that number): 1e-6 CV parity holds up to a few hundred
+    particles per cell (sigma = 3: ~6 per cell); the clustered case (sigma = 0.8: ~800 in the densest cell) documents the
+    limit."""
+    import torch
+    N, dims, L = 200000, (32, 32, 32), 8.0
+    rng = np.random.default_rng(5)
+    pos = (rng.normal(0.0, sigma, (N, 3))).astype(np.float32)
+    pos = (((pos + L / 2) % L) - L / 2).astype(np.float32)
+    pos[pos >= np.float32(L / 2)] = -np.float32(L / 2)
+    types = rng.integers(0, 2, N).astype(np.int32)
+    modes = [250.0, 100.0]
+    box = gpu.Box.make(L)
+    mesh = gpu.Mesh(*dims, modes)
+    mesh.set(1, 1)
+    d_pt = to_dev(gpu, pos, types)
+    cv = mesh.compute_cv(d_pt, N, box).cpu().item()
+    st = mesh.stats()
+    assert st["range_warnings"] == 0 and st["fx_scale"] < 2 ** 22 / (0.421875 * 250.0)
+    h_pt = host_pt(oracle, pos, types)
+    m = oracle.Mesh(*dims, modes, [L] * 3, N, "f64", literal_copysignf=False)
+    cvo = m.current_value(h_pt)
+    m32 = oracle.Mesh(*dims, modes, [L] * 3, N, "f32")
+    m32.assign(h_pt)
+    c = m32.cells()
+    max_count = np.bincount(c[:, 0] + 32 * (c[:, 1] + 32 * c[:, 2])).max()
+    # taps accumulate like fp32 sums: error ~ 1e-7 of the peak times sqrt(terms)
+    assert np.abs(mesh.rho() - m.mesh).max() < 1e-5 * np.abs(m.mesh).max()
+    assert abs(cv / cvo - 1) < (cv_tol if cv_tol else 2e-8 * max_count)
+    bias = torch.tensor([1.0], dtype=torch.float64, device="cuda")
+    f = mesh.forces(d_pt, N, box, bias).cpu().numpy()
+    fo = m.forces(h_pt, 1.0)
+    assert np.abs(f - fo).max() < 1e-5 * np.abs(fo).max()
 
 
 def test_mesh_c1_golden_with_umbrella(gpu, oracle):
@@ -166,6 +262,7 @@ def test_mesh_c1_golden_with_umbrella(gpu, oracle):
     d_pt = torch.from_numpy(w["postype"]).cuda()
     box = gpu.Box.make(w["L"])
     mesh = gpu.Mesh(*w["mesh"], w["mode"])
+    mesh.set(3, 1)
     cv = mesh.compute_cv(d_pt, 1000, box)
     assert cv.cpu().item() == pytest.approx(gold["c1_cv"], rel=1e-6)
     u = w["umbrella"]

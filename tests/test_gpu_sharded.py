@@ -37,6 +37,7 @@ def test_mesh_slab_matches_single_plan_and_oracle(gpu, oracle, N, dims, L, P, mo
     ranks = [sharded.MeshSlabRank(nx, ny, nz, P, r, modes) for r in range(P)]
     for r in ranks:
         r.set(1, 1)
+        r.set(3, 1)
     idx = [np.nonzero(owner == r)[0] for r in range(P)]
     pts = [ops.make_postype(pos[i], types[i]) for i in idx]
     bias = torch.tensor([0.9], dtype=torch.float64, device="cuda")
@@ -56,6 +57,12 @@ def test_mesh_slab_matches_single_plan_and_oracle(gpu, oracle, N, dims, L, P, mo
     f1 = single.forces(d_all, N, box, bias).cpu().numpy()
     assert cv == pytest.approx(cv1, rel=2e-7)
     assert np.abs(f - f1).max() < 2e-6 * np.abs(f1).max()
+    single.set(1, 1)
+    single.compute_cv(d_all, N, box)
+    rho = np.concatenate([r.local_mesh(1) for r in ranks], axis=0)
+    fx = {r.stats()["fx_scale"] for r in ranks} | {single.stats()["fx_scale"]}
+    if len(fx) == 1:                                              # equal fixed-point scales: the sharded density is bit-identical
+        assert np.array_equal(rho, single.rho())
 
     # oracle
     h_pt = oracle.make_postype(pos, types)
@@ -70,7 +77,6 @@ def test_mesh_slab_matches_single_plan_and_oracle(gpu, oracle, N, dims, L, P, mo
     for i, r in zip(idx, ranks):
         cells[i] = r.cells()
     assert np.array_equal(cells, o32.cells())                     # bit-exact global cell indices
-    rho = np.concatenate([r.local_mesh(1) for r in ranks], axis=0)
     assert np.abs(rho - o.mesh).max() < 2e-6 * max(1.0, np.abs(o.mesh).max())
 
 
