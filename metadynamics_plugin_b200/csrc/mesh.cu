@@ -113,7 +113,7 @@ template <int LC> int run_x(metad_mesh* p, bool inverse, float2* io, const doubl
     if (!inverse) {
         int rc = set_smem(fft_x_fwd_kernel<LC>, smem); if (rc) return rc;
         DensityIn in;
-        in.mesh = reinterpret_cast<int2*>(p->d_mesh_i);
+        in.mesh = reinterpret_cast<const int2*>(p->d_mesh_i);
         in.d_fx = p->d_fx;
         in.d_sums = d_sums;
         in.inv_cells = 1.0 / ((double)p->g.nx * (double)p->g.ny * (double)p->nzg);
@@ -121,6 +121,9 @@ template <int LC> int run_x(metad_mesh* p, bool inverse, float2* io, const doubl
         in.lgy = p->g.lgy; in.nz = p->g.nz;
         in.rho_keep = p->keep_rho ? reinterpret_cast<float2*>(p->d_rho_keep) : nullptr;
         fft_x_fwd_kernel<LC><<<rows / kLines, kLines * LC / kE, smem, st>>>(in, p->d_twx, io ? io : buf, lg_part, rows);
+        METAD_LAUNCH_CHECK();
+        // the accumulator is empty again for the next spread (a plain memset runs at the full write bandwidth)
+        METAD_CUDA(cudaMemsetAsync(p->d_mesh_i, 0, sizeof(int) * p->M(), st));
     } else {
         int rc = set_smem(fft_x_inv_kernel<LC>, smem); if (rc) return rc;
         fft_x_inv_kernel<LC><<<rows / kLines, kLines * LC / kE, smem, st>>>(buf, p->d_twx, io ? io : buf, lg_part, rows);

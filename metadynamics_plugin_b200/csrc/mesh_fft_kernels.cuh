@@ -80,11 +80,11 @@ template <int TWL> __device__ __forceinline__ void load_twiddles(float2* s_tw, c
 
 // ---------------------------------------------------------------------------------------------------
 // x pass, forward (R2C): 16 rows per CTA, row = y + ny*z.  The input is the fixed-point density accumulated by the
-// spread (mesh_kernels.cuh): it is converted to float, the mean density is removed (DC removal, see mesh.cu) and the
-// accumulator is cleared for the next call, all inside this sweep.
+// spread (mesh_kernels.cuh): it is converted to float and the mean density is removed (DC removal, see mesh.cu) inside
+// this sweep.
 // ---------------------------------------------------------------------------------------------------
 struct DensityIn {
-    int2* mesh;             // integer density of the local planes, row-major [z][y][x] (read, then zeroed)
+    const int2* mesh;       // integer density of the local planes, row-major [z][y][x] (the caller clears it afterwards)
     const float* d_fx;      // device: {scale, 1/scale} of the fixed-point density
     const double* d_sums;   // device: [1] = (global) sum of the mode coefficients -> mean density
     double inv_cells;       // 1 / (global number of mesh cells)
@@ -113,24 +113,19 @@ fft_x_fwd_kernel(DensityIn in, const float2* __restrict__ g_tw /* length 2*LC */
     const float inv_scale = __ldg(in.d_fx + 1);
     const float mean = (float)(in.d_sums[1] * in.inv_cells);
     const unsigned ny = 1u << in.lgy;
-    // all kE loads of a thread are issued before the accumulator is cleared (the stores alias the loads)
-    int2 vin[kE];
+    // 128-bit loads: kE/2 per thread, all issued before the first use
+    int4 vin[kE / 2];
 #pragma unroll
-    for (int q = 0; q < kE; ++q) {
-        const int idx = threadIdx.x + q * nthr;
-        vin[q] = in.mesh[(row0 + idx / LC) * LC + idx % LC];
+    for (int q = 0; q < kE / 2; ++q) {
+        const int idx = threadIdx.x + q * nthr;          // pair index: row w = idx / (LC/2), columns 2*(idx % (LC/2)) and +1
+        vin[q] = __ldcs(reinterpret_cast<const int4*>(in.mesh + (row0 + idx / (LC / 2)) * LC) + idx % (LC / 2));
     }
 #pragma unroll
-    for (int q = 0; q < kE; ++q) {
-        const int idx = threadIdx.x + q * nthr;
-        in.mesh[(row0 + idx / LC) * LC + idx % LC] = make_int2(0, 0);
-    }
-#pragma unroll
-    for (int q = 0; q < kE; ++q) {
-        const int idx = threadIdx.x + q * nthr;
-        const int w = idx / LC, l = idx % LC;
+    for (int q2 = 0; q2 < kE; ++q2) {
+        const int idx = threadIdx.x + (q2 >> 1) * nthr;
+        const int w = idx / (LC / 2), l = 2 * (idx % (LC / 2)) + (q2 & 1);
         const size_t row = row0 + w;
-        int2 v = vin[q];
+        int2 v = (q2 & 1) ? make_int2(vin[q2 >> 1].z, vin[q2 >> 1].w) : make_int2(vin[q2 >> 1].x, vin[q2 >> 1].y);
         float2 r;
         if (in.ghost) {
             // ranks choose their fixed-point scales independently: equal scales (the common case) add as integers, which

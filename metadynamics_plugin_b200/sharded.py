@@ -89,9 +89,11 @@ class LocalComm:
 
 # ---------------------------------------------------------------------------------------------------- lamellar
 class LamellarSharded:
-    def __init__(self, comm, mode, lattice_vectors):
-        from .ops import Lamellar
-        self.comm, self.lam = comm, Lamellar(mode, lattice_vectors)
+    def __init__(self, comm, mode, lattice_vectors, lamellar_factory=None):
+        """lamellar_factory: class with the interface of ops.Lamellar (tests substitute a CPU stand-in)."""
+        if lamellar_factory is None:
+            from .ops import Lamellar as lamellar_factory
+        self.comm, self.lam = comm, lamellar_factory(mode, lattice_vectors)
 
     def compute_cv(self, postype_local, n_global, box):
         self.lam.compute_modes(postype_local, n_global, box, finalize=False)
@@ -184,9 +186,10 @@ class MeshSlabRank:
 class MeshSlab:
     """One rank of the sharded mesh CV, driving the stages and the collectives of `comm` (TorchComm)."""
 
-    def __init__(self, comm, nx, ny, nz, mode):
+    def __init__(self, comm, nx, ny, nz, mode, rank_factory=None):
+        """rank_factory: class with the interface of MeshSlabRank (tests substitute a CPU stand-in)."""
         self.comm = comm
-        self.r = MeshSlabRank(nx, ny, nz, comm.size, comm.rank, mode)
+        self.r = (rank_factory or MeshSlabRank)(nx, ny, nz, comm.size, comm.rank, mode)
 
     def compute_cv(self, postype_local, n_global, box):
         r, c = self.r, self.comm
