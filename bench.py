@@ -87,9 +87,9 @@ def make_workload(name, shard=None):
 # ---------------------------------------------------------------------------------------------------- ours
 class MeshStep:
     """mesh CV -> 1-D grid bias -> forces, everything device-resident."""
-    # spread, x/y fwd, z fused (+plane0), y/x inv, grid step, gather; a rebuild of the tile order adds bin, 3 scan, place, scale
+    # spread, x/y fwd, z fused (+plane0), y/x inv, grid step, gather; a rebuild of the tile order adds bin, 3 scan, place, layer order, scale
     launches_per_step = 8
-    launches_per_rebuild = 6
+    launches_per_rebuild = 7
 
     def __init__(self, w, ops, torch, calibrate=True, period=32):
         self.ops, self.torch, self.w = ops, torch, w

@@ -50,7 +50,11 @@ struct metad_mesh {
     float amax = 0.f;               // largest |mode coefficient|
     // tile order
     unsigned cap = 0;
+    // d_keys: cell key per particle; d_ranks: arrival rank inside the cell during a rebuild, afterwards THE TILE ORDER
+    // (layer order, see mesh_layer_order_kernel); d_perm: cell-sorted permutation (intermediate)
     unsigned *d_keys = nullptr, *d_ranks = nullptr, *d_perm = nullptr;
+    float4* d_cache4 = nullptr;     // particle cache spread -> gather (tile order): offsets + amplitude
+    uint2* d_cache_code = nullptr;     // {code word, particle index}
     unsigned *d_count = nullptr, *d_start = nullptr, *d_block_sums = nullptr, *d_tstart = nullptr, *d_max_count = nullptr;
     bool order_valid = false;
     unsigned order_N = 0, calls_since_rebuild = 0, period = 32;
@@ -206,13 +210,15 @@ int fft_pipeline(metad_mesh* p, unsigned N_global, double* d_cv, cudaStream_t st
 
 int ensure_capacity(metad_mesh* p, unsigned N) {
     if (N <= p->cap) return METAD_OK;
-    cudaFree(p->d_keys); cudaFree(p->d_ranks); cudaFree(p->d_perm);
-    p->d_keys = p->d_ranks = p->d_perm = nullptr; p->cap = 0;
+    cudaFree(p->d_keys); cudaFree(p->d_ranks); cudaFree(p->d_perm); cudaFree(p->d_cache4); cudaFree(p->d_cache_code);
+    p->d_keys = p->d_ranks = p->d_perm = nullptr; p->d_cache_code = nullptr; p->d_cache4 = nullptr; p->cap = 0;
     p->order_valid = false;
     const unsigned cap = N + N / 16 + 1024;
     METAD_CUDA(cudaMalloc(&p->d_keys, sizeof(unsigned) * cap));
     METAD_CUDA(cudaMalloc(&p->d_ranks, sizeof(unsigned) * cap));
     METAD_CUDA(cudaMalloc(&p->d_perm, sizeof(unsigned) * cap));
+    METAD_CUDA(cudaMalloc(&p->d_cache4, sizeof(float4) * cap));
+    METAD_CUDA(cudaMalloc(&p->d_cache_code, sizeof(uint2) * cap));
     p->cap = cap;
     return METAD_OK;
 }
@@ -259,6 +265,10 @@ int rebuild_order(metad_mesh* p, const float* d_postype, unsigned N, cudaStream_
     mesh_place_kernel<<<(int)nbp, kBinThreads, 0, stream>>>(N, p->d_keys, p->d_ranks, p->d_start, p->d_perm, num_tiles(g), 3 * g.lgT,
                                                            p->d_tstart);
     METAD_LAUNCH_CHECK();
+    // layer order inside every tile; the arrival ranks are no longer needed, their buffer receives the final order
+    if (g.lgT == 4) mesh_layer_order_kernel<4><<<num_tiles(g), kLayerThreads, 0, stream>>>(p->d_start, p->d_perm, p->d_ranks);
+    else mesh_layer_order_kernel<3><<<num_tiles(g), kLayerThreads, 0, stream>>>(p->d_start, p->d_perm, p->d_ranks);
+    METAD_LAUNCH_CHECK();
     mesh_fx_scale_kernel<<<1, 1, 0, stream>>>(p->d_max_count, p->amax, p->d_fx);
     METAD_LAUNCH_CHECK();
     p->order_valid = true;
@@ -268,7 +278,11 @@ int rebuild_order(metad_mesh* p, const float* d_postype, unsigned N, cudaStream_
     return METAD_OK;
 }
 
-template <int LGT> size_t tile_smem_bytes() { return sizeof(int) * (size_t)((1 << LGT) + 2 * kHalo) * ((1 << LGT) + 2 * kHalo) * ((1 << LGT) + 2 * kHalo); }
+template <int LGT> size_t tile_smem_bytes() {
+    return sizeof(int) * (size_t)((1 << LGT) + 2 * kHaloX) * ((1 << LGT) + 2 * kHalo) * ((1 << LGT) + 2 * kHalo);
+}
+// gather: the tile plus two staging buffers of the particle cache (float4 + uint2 per thread)
+template <int LGT> size_t gather_smem_bytes() { return tile_smem_bytes<LGT>() + 2 * kGatherThreads * (sizeof(float4) + sizeof(uint2)); }
 
 // tile order of this call (rebuilt if needed) + spread into the integer mesh; sums -> p->d_sums
 int order_and_spread(metad_mesh* p, const float* d_postype, unsigned N, cudaStream_t stream) {
@@ -295,12 +309,14 @@ int order_and_spread(metad_mesh* p, const float* d_postype, unsigned N, cudaStre
     out.sums = p->d_sums;
     out.counters = p->d_counters;
     out.keys = p->keep_cells ? p->d_keys : nullptr;
+    out.cache4 = p->d_cache4;
+    out.cache_code = p->d_cache_code;
     if (g.lgT == 4) {
         rc = set_smem(mesh_spread_kernel<4>, tile_smem_bytes<4>()); if (rc) return rc;
-        mesh_spread_kernel<4><<<num_tiles(g), kSpreadThreads, tile_smem_bytes<4>(), stream>>>((const float4*)d_postype, p->d_perm, p->d_tstart, g,
+        mesh_spread_kernel<4><<<num_tiles(g), kSpreadThreads, tile_smem_bytes<4>(), stream>>>((const float4*)d_postype, p->d_ranks, p->d_tstart, g,
                                                                                            p->d_mode, p->d_fx, out);
     } else {
-        mesh_spread_kernel<3><<<num_tiles(g), kSpreadThreads, tile_smem_bytes<3>(), stream>>>((const float4*)d_postype, p->d_perm, p->d_tstart, g,
+        mesh_spread_kernel<3><<<num_tiles(g), kSpreadThreads, tile_smem_bytes<3>(), stream>>>((const float4*)d_postype, p->d_ranks, p->d_tstart, g,
                                                                                            p->d_mode, p->d_fx, out);
     }
     METAD_LAUNCH_CHECK();
@@ -320,12 +336,14 @@ int launch_gather(metad_mesh* p, const float* d_postype, const float* d_ghost, f
     fp.two_over_n = 2.0 / (double)N_global;
     int rc = mark(p, 8, stream); if (rc) return rc;
     if (g.lgT == 4) {
-        rc = set_smem(mesh_gather_kernel<4>, tile_smem_bytes<4>()); if (rc) return rc;
-        mesh_gather_kernel<4><<<num_tiles(g), kGatherThreads, tile_smem_bytes<4>(), stream>>>((const float4*)d_postype, p->d_perm, p->d_tstart, g,
-                                                                                           p->d_mode, p->d_buf, d_ghost, fp, d_bias, (float4*)d_force);
+        rc = set_smem(mesh_gather_kernel<4>, gather_smem_bytes<4>()); if (rc) return rc;
+        mesh_gather_kernel<4><<<num_tiles(g), kGatherThreads, gather_smem_bytes<4>(), stream>>>((const float4*)d_postype, p->d_tstart,
+                                                                                           p->d_cache4, p->d_cache_code, g, p->d_buf, d_ghost, fp, d_bias,
+                                                                                           (float4*)d_force);
     } else {
-        mesh_gather_kernel<3><<<num_tiles(g), kGatherThreads, tile_smem_bytes<3>(), stream>>>((const float4*)d_postype, p->d_perm, p->d_tstart, g,
-                                                                                           p->d_mode, p->d_buf, d_ghost, fp, d_bias, (float4*)d_force);
+        mesh_gather_kernel<3><<<num_tiles(g), kGatherThreads, gather_smem_bytes<3>(), stream>>>((const float4*)d_postype, p->d_tstart,
+                                                                                           p->d_cache4, p->d_cache_code, g, p->d_buf, d_ghost, fp, d_bias,
+                                                                                           (float4*)d_force);
     }
     METAD_LAUNCH_CHECK();
     return mark(p, 9, stream);
@@ -425,7 +443,7 @@ extern "C" int metad_mesh_slab_create(metad_mesh** out, unsigned nx, unsigned ny
 
 extern "C" int metad_mesh_destroy(metad_mesh* p) {
     if (!p) return METAD_OK;
-    cudaFree(p->d_mode); cudaFree(p->d_keys); cudaFree(p->d_ranks); cudaFree(p->d_perm);
+    cudaFree(p->d_mode); cudaFree(p->d_keys); cudaFree(p->d_ranks); cudaFree(p->d_perm); cudaFree(p->d_cache4); cudaFree(p->d_cache_code);
     cudaFree(p->d_count); cudaFree(p->d_start); cudaFree(p->d_block_sums); cudaFree(p->d_tstart); cudaFree(p->d_max_count);
     cudaFree(p->d_mesh_alloc); cudaFree(p->d_buf); cudaFree(p->d_fx); cudaFree(p->d_tile_sums); cudaFree(p->d_counters);
     if (p->h_counters) cudaFreeHost(p->h_counters);

@@ -24,6 +24,10 @@
 // double-precision box.
 #pragma once
 #include "common.cuh"
+#ifdef __CUDACC__
+#include <cuda_pipeline.h>
+#include <cuda/ptx>
+#endif
 
 #ifndef MHD
 #define MHD __host__ __device__ __forceinline__
@@ -32,7 +36,11 @@
 namespace metad {
 namespace mesh {
 
-constexpr int kHalo = 2;          // halo cells of a padded tile: 1 for the TSC stencil + 1 of drift tolerance
+// halo cells of a padded tile: 1 for the TSC stencil + drift tolerance.  The x halo is 4 cells so that every row of the
+// padded tile starts on a 16-byte boundary of the mesh: rows then move with one bulk asynchronous copy each (TMA engine:
+// cp.reduce.async.bulk for the spread flush, cp.async.bulk for the gather tile).
+constexpr int kHalo = 2;
+constexpr int kHaloX = 4;
 
 struct Geom {
     unsigned nx, ny, nz;        // mesh points of the LOCAL mesh (powers of two); nz = planes of this z slab
@@ -94,7 +102,7 @@ inline void geom_set_box(Geom& g, const double* Ld) {
 
 MHD unsigned tile_edge(const Geom& g) { return 1u << g.lgT; }
 MHD unsigned cells_per_tile(const Geom& g) { return 1u << (3 * g.lgT); }
-MHD unsigned padded_edge(const Geom& g) { return (1u << g.lgT) + 2 * kHalo; }
+MHD unsigned padded_cells(const Geom& g) { const unsigned T = 1u << g.lgT; return (T + 2 * kHaloX) * (T + 2 * kHalo) * (T + 2 * kHalo); }
 MHD unsigned num_tiles(const Geom& g) { return 1u << (g.lgtx + g.lgty + g.lgtz); }
 MHD unsigned tile_index(unsigned tx, unsigned ty, unsigned tz, const Geom& g) { return (((tz << g.lgty) + ty) << g.lgtx) + tx; }
 MHD void tile_coords(unsigned tile, const Geom& g, unsigned& tx, unsigned& ty, unsigned& tz) {
@@ -297,21 +305,46 @@ MHD Cell particle_cell(float4 p, const Geom& g) {
 }
 // coordinates of the cell inside the padded tile with origin (ox,oy,oz) = tile origin - halo (local planes in z);
 // returns true if all 27 taps lie inside the padded tile
-MHD bool padded_coords(const Cell& c, int ox, int oy, int oz, const Geom& g, int P, unsigned& lx, unsigned& ly, unsigned& lz) {
+MHD bool padded_coords(const Cell& c, int ox, int oy, int oz, const Geom& g, int PX, int PY, int PZ, unsigned& lx, unsigned& ly,
+                       unsigned& lz) {
     lx = (unsigned)(c.ix - ox) & (g.nx - 1);
     ly = (unsigned)(c.iy - oy) & (g.ny - 1);
     const int zl = c.iz - (int)g.z0;
     lz = g.slab ? (unsigned)(zl - oz) : ((unsigned)(zl - oz) & (g.nz - 1));
-    return (lx - 1u) < (unsigned)(P - 2) && (ly - 1u) < (unsigned)(P - 2) && (lz - 1u) < (unsigned)(P - 2);
+    return (lx - 1u) < (unsigned)(PX - 2) && (ly - 1u) < (unsigned)(PY - 2) && (lz - 1u) < (unsigned)(PZ - 2);
+}
+// Row (py, pz) of a padded tile in the mesh: plane (local; a slab also has planes -1 and nz) and row y; returns false if the
+// plane does not exist.  The x range [ox, ox + PX) wraps periodically: `first` cells lie before the wrap.
+struct TileRow { int z; unsigned y; unsigned x0; int first; };
+MHD bool tile_row(int ox, int oy, int oz, int py, int pz, int PX, const Geom& g, TileRow& r) {
+    r.y = (unsigned)(oy + py) & (g.ny - 1);
+    r.z = oz + pz;
+    if (g.slab) { if (r.z < -1 || r.z > (int)g.nz) return false; }
+    else r.z = (int)((unsigned)r.z & (g.nz - 1));
+    r.x0 = (unsigned)ox & (g.nx - 1);
+    const int room = (int)g.nx - (int)r.x0;
+    r.first = room < PX ? room : PX;
+    return true;
+}
+// in-cell offsets of a particle (cell units)
+MHD float3 particle_shift(float4 p, const Cell& c, const Geom& g) {
+    return make_float3(cell_shift(p.x, c.ix, 0, g), cell_shift(p.y, c.iy, 1, g), cell_shift(p.z, c.iz, 2, g));
 }
 // separable weights: w[0..2] = Wx(tap -1,0,+1), w[3..5] = Wy, w[6..8] = amp * Wz
-MHD void spread_weights(float4 p, const Cell& c, float amp, const Geom& g, float (&w)[9]) {
+MHD void spread_weights(float3 s, float amp, float (&w)[9]) {
     float wx[3], wy[3], wz[3];
-    tsc(cell_shift(p.x, c.ix, 0, g), wx);
-    tsc(cell_shift(p.y, c.iy, 1, g), wy);
-    tsc(cell_shift(p.z, c.iz, 2, g), wz);
+    tsc(s.x, wx);
+    tsc(s.y, wy);
+    tsc(s.z, wz);
 #pragma unroll
     for (int i = 0; i < 3; ++i) { w[i] = wx[i]; w[3 + i] = wy[i]; w[6 + i] = amp * wz[i]; }
+}
+// Particle cache written by the spread for the gather of the same call pair (tile order): {sx, sy, sz, a(type)} and a
+// code word: padded-tile coordinates of the cell (10 bits each) | kCacheInside (all taps inside the padded tile) |
+// kCacheOwned (the plane belongs to this rank).  The gather then needs neither the positions nor the cell arithmetic.
+constexpr unsigned kCacheInside = 1u << 30, kCacheOwned = 1u << 31;
+MHD unsigned cache_code(unsigned lx, unsigned ly, unsigned lz, bool inside, bool owned) {
+    return inside ? (lx | (ly << 10) | (lz << 20) | kCacheInside | kCacheOwned) : (owned ? kCacheOwned : 0u);
 }
 // fixed-point value of tap (i,j,k) in {0,1,2}^3: the SAME expression on every path (tile, stray, emulation)
 MHD int tap_value(const float (&w)[9], int i, int j, int k) { return fx_round(w[i], f_mul(w[3 + j], w[6 + k])); }
@@ -335,25 +368,23 @@ MHD void gather_sums(const float* base, long long sy_, long long sz_, const floa
                      const float (&wy)[3], const float (&wz)[3], const float (&dx)[3], const float (&dy)[3],
                      const float (&dz)[3], float& Sx, float& Sy, float& Sz) {
     Sx = 0.f; Sy = 0.f; Sz = 0.f;
+    // plane by plane (9 values live at a time): a_j = sum_i Wx_i v_ij, b_j = sum_i W'x_i v_ij, then the y and z contractions
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        float tw = 0.f, td = 0.f, tz = 0.f;   // sum_j {Wy, W'y, Wy} * sum_k {Wz, Wz, W'z} inv
+    for (int k = 0; k < 3; ++k) {
+        float pk = 0.f, qk = 0.f, rk = 0.f;
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-            float u = 0.f, v = 0.f;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const float val = base[k * sz_ + j * sy_ + i];
-                u = fmaf(wz[k], val, u);
-                v = fmaf(dz[k], val, v);
-            }
-            tw = fmaf(wy[j], u, tw);
-            td = fmaf(dy[j], u, td);
-            tz = fmaf(wy[j], v, tz);
+            const float* row = base + k * sz_ + j * sy_;
+            const float v0 = row[0], v1 = row[1], v2 = row[2];
+            const float a = fmaf(wx[2], v2, fmaf(wx[1], v1, wx[0] * v0));
+            const float b = fmaf(dx[2], v2, fmaf(dx[1], v1, dx[0] * v0));
+            pk = fmaf(wy[j], a, pk);
+            qk = fmaf(wy[j], b, qk);
+            rk = fmaf(dy[j], a, rk);
         }
-        Sx = fmaf(dx[i], tw, Sx);
-        Sy = fmaf(wx[i], td, Sy);
-        Sz = fmaf(wx[i], tz, Sz);
+        Sx = fmaf(wz[k], qk, Sx);
+        Sy = fmaf(wz[k], rk, Sy);
+        Sz = fmaf(dz[k], pk, Sz);
     }
 }
 
@@ -363,10 +394,9 @@ struct ForceParams {
 };
 
 struct GatherWeights { float wx[3], wy[3], wz[3], dx[3], dy[3], dz[3]; };
-MHD void gather_weights(float4 p, const Cell& c, const Geom& g, GatherWeights& w) {
-    const float sx = cell_shift(p.x, c.ix, 0, g), sy = cell_shift(p.y, c.iy, 1, g), sz = cell_shift(p.z, c.iz, 2, g);
-    tsc(sx, w.wx); tsc(sy, w.wy); tsc(sz, w.wz);
-    tsc_deriv(sx, w.dx); tsc_deriv(sy, w.dy); tsc_deriv(sz, w.dz);
+MHD void gather_weights(float3 s, GatherWeights& w) {
+    tsc(s.x, w.wx); tsc(s.y, w.wy); tsc(s.z, w.wz);
+    tsc_deriv(s.x, w.dx); tsc_deriv(s.y, w.dy); tsc_deriv(s.z, w.dz);
 }
 // amp = a(type); scale = (2/N) * bias rounded to float
 MHD float4 force_from_sums(float Sx, float Sy, float Sz, float amp, const ForceParams& fp, float scale) {
@@ -513,6 +543,71 @@ mesh_place_kernel(unsigned N, const unsigned* __restrict__ keys, const unsigned*
     for (unsigned t = t0; t <= ntiles; t += stride) tstart[t] = __ldg(start + ((size_t)t << lg_cells));
 }
 
+// layer order inside a tile: first one particle of every occupied cell (cells ascending, x fastest), then the second
+// particles, and so on.  Consecutive lanes of a warp then work on DIFFERENT, mostly x-adjacent cells, so the 27
+// shared-memory atomics of a warp hit distinct addresses in distinct banks (particles of one cell in neighbouring lanes
+// would serialise: measured 4.05 wavefronts per ATOMS with the plain cell order).  One CTA per tile; amortised.
+constexpr int kLayerThreads = 256;
+template <int LGT>
+__global__ void __launch_bounds__(kLayerThreads)
+mesh_layer_order_kernel(const unsigned* __restrict__ start, const unsigned* __restrict__ perm, unsigned* __restrict__ order) {
+    constexpr int CELLS = 1 << (3 * LGT), CPT = CELLS / kLayerThreads;      // cells per thread (16 or 2)
+    __shared__ unsigned s_start[CELLS + 1];
+    __shared__ unsigned s_scan[kLayerThreads / 32 + 1];
+    __shared__ unsigned s_max;
+    const size_t key0 = (size_t)blockIdx.x << (3 * LGT);
+    for (int i = threadIdx.x; i <= CELLS; i += kLayerThreads) s_start[i] = __ldg(start + key0 + i);
+    if (threadIdx.x == 0) s_max = 0;
+    __syncthreads();
+    const unsigned tile_begin = s_start[0];
+    if (s_start[CELLS] == tile_begin) return;
+    const int c0 = threadIdx.x * CPT;
+    unsigned mx = 0;
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) mx = max(mx, s_start[c0 + k + 1] - s_start[c0 + k]);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0) atomicMax(&s_max, mx);
+    __syncthreads();
+    const unsigned layers = s_max;
+    unsigned out = tile_begin;
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (unsigned r = 0; r < layers; ++r) {
+        unsigned cnt = 0;
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) cnt += (s_start[c0 + k + 1] - s_start[c0 + k] > r) ? 1u : 0u;
+        // block exclusive scan of cnt
+        unsigned incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (unsigned)o) incl += y;
+        }
+        if (lane == 31) s_scan[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            const unsigned w = lane < kLayerThreads / 32 ? s_scan[lane] : 0u;
+            unsigned wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned y = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= (unsigned)o) wi += y;
+            }
+            if (lane < kLayerThreads / 32) s_scan[lane] = wi - w;
+            if (lane == 31) s_scan[kLayerThreads / 32] = wi;
+        }
+        __syncthreads();
+        unsigned pos = out + s_scan[wid] + incl - cnt;
+        const unsigned total = s_scan[kLayerThreads / 32];
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+            const unsigned b = s_start[c0 + k];
+            if (s_start[c0 + k + 1] - b > r) order[pos++] = __ldg(perm + b + r);
+        }
+        out += total;
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // spread
 // ---------------------------------------------------------------------------------------------------
@@ -525,23 +620,25 @@ struct SpreadOut {
     double* sums;            // [0] sum a^2 (m_mode_sq, OrderParameterMesh.cc:623), [1] sum a, [2] particles outside the slab
     unsigned* counters;
     unsigned* keys;          // optional: tile-major cell key per particle (introspection), or nullptr
+    float4* cache4;          // particle cache for the gather, tile order: {sx, sy, sz, a}
+    uint2* cache_code;       //   ... and {code word (cache_code()), particle index}
 };
 
 template <int LGT>
 __global__ void __launch_bounds__(kSpreadThreads)
 mesh_spread_kernel(const float4* __restrict__ postype, const unsigned* __restrict__ perm, const unsigned* __restrict__ tstart,
                    Geom g, const float* __restrict__ mode, const float* __restrict__ d_fx, SpreadOut out) {
-    constexpr int T = 1 << LGT, P = T + 2 * kHalo, P3 = P * P * P;
-    extern __shared__ int tile[];
+    constexpr int T = 1 << LGT, PX = T + 2 * kHaloX, PY = T + 2 * kHalo, PZ = PY, P3 = PX * PY * PZ;
+    extern __shared__ __align__(16) int tile[];
     __shared__ double red[32];
     __shared__ bool is_last;
     const unsigned s = __ldg(tstart + blockIdx.x), e = __ldg(tstart + blockIdx.x + 1);
     unsigned tx, ty, tz;
     tile_coords(blockIdx.x, g, tx, ty, tz);
-    const int ox = (int)(tx << LGT) - kHalo, oy = (int)(ty << LGT) - kHalo, oz = (int)(tz << LGT) - kHalo;
+    const int ox = (int)(tx << LGT) - kHaloX, oy = (int)(ty << LGT) - kHalo, oz = (int)(tz << LGT) - kHalo;
     double sq = 0.0, s1 = 0.0;
     if (e > s) {
-        for (int i = threadIdx.x; i < P3; i += kSpreadThreads) tile[i] = 0;
+        for (int i = threadIdx.x; i < P3 / 4; i += kSpreadThreads) reinterpret_cast<int4*>(tile)[i] = make_int4(0, 0, 0, 0);
         __syncthreads();
         const float scale = __ldg(d_fx);
         unsigned strays = 0, foreign = 0;
@@ -558,21 +655,25 @@ mesh_spread_kernel(const float4* __restrict__ postype, const unsigned* __restric
             const float a = __ldg(mode + __float_as_int(p.w));
             const Cell c = particle_cell(p, g);
             if (out.keys) out.keys[n] = key_of(c.ix, c.iy, (unsigned)(c.iz - (int)g.z0) & (g.nz - 1), g);
+            const float3 sh = particle_shift(p, c, g);
+            unsigned lx = 0, ly = 0, lz = 0;
+            const bool inside = c.owned && padded_coords(c, ox, oy, oz, g, PX, PY, PZ, lx, ly, lz);
+            out.cache4[j] = make_float4(sh.x, sh.y, sh.z, a);
+            out.cache_code[j] = make_uint2(cache_code(lx, ly, lz, inside, c.owned), n);
             if (c.owned) {
                 sq += (double)a * (double)a;
                 s1 += (double)a;
                 float w[9];
-                spread_weights(p, c, a * scale, g, w);
-                unsigned lx, ly, lz;
-                if (padded_coords(c, ox, oy, oz, g, P, lx, ly, lz)) {
-                    int* base = tile + ((lz - 1) * P + (ly - 1)) * P + (lx - 1);
+                spread_weights(sh, a * scale, w);
+                if (inside) {
+                    int* base = tile + ((lz - 1) * PY + (ly - 1)) * PX + (lx - 1);
 #pragma unroll
                     for (int k = 0; k < 3; ++k)
 #pragma unroll
                         for (int jj = 0; jj < 3; ++jj) {
                             const float wyz = f_mul(w[3 + jj], w[6 + k]);
 #pragma unroll
-                            for (int i = 0; i < 3; ++i) atomicAdd(base + (k * P + jj) * P + i, fx_round(w[i], wyz));
+                            for (int i = 0; i < 3; ++i) atomicAdd(base + (k * PY + jj) * PX + i, fx_round(w[i], wyz));
                         }
                 } else {
                     ++strays;
@@ -591,26 +692,34 @@ mesh_spread_kernel(const float4* __restrict__ postype, const unsigned* __restric
         if (strays) atomicAdd(out.counters + 1, strays);
         if (foreign) atomicAdd(out.counters + 2, foreign);
         __syncthreads();
-        // flush the padded tile: flat index walked incrementally (kSpreadThreads = 0*P*P + sy*P + sx)
-        constexpr int sx = kSpreadThreads % P, sy = (kSpreadThreads / P) % P, sz = kSpreadThreads / (P * P);
-        int px = threadIdx.x % P, py = (threadIdx.x / P) % P, pz = threadIdx.x / (P * P);
-        const unsigned mx = g.nx - 1, my = g.ny - 1, mz = g.slab ? 0xffffffffu : g.nz - 1;
-        const unsigned sh_y = g.lgx, sh_z = g.lgx + g.lgy;
+        // flush: one thread per row of the padded tile; a row that received anything is added to the mesh by ONE bulk
+        // asynchronous reduction (cp.reduce.async.bulk .add.s32, executed by the TMA engine / L2), two if it wraps in x
+        cuda::ptx::fence_proxy_async(cuda::ptx::space_shared);      // the tile was written through the generic proxy
+        const size_t plane = (size_t)g.nx * g.ny;
         int vmax = 0;
-        for (int idx = threadIdx.x; idx < P3; idx += kSpreadThreads) {
-            const int v = tile[idx];
-            if (v != 0) {
-                const unsigned x = (unsigned)(ox + px) & mx, y = (unsigned)(oy + py) & my;
-                const int z = (int)((unsigned)(oz + pz) & mz);
-                atomicAdd(out.mesh + (long long)z * (long long)(1u << sh_z) + (long long)((y << sh_y) | x), v);
-                vmax = max(vmax, abs(v));
+        for (int row = threadIdx.x; row < PY * PZ; row += kSpreadThreads) {
+            const int4* r4 = reinterpret_cast<const int4*>(tile + row * PX);
+            int m = 0;
+#pragma unroll
+            for (int q = 0; q < PX / 4; ++q) {
+                const int4 v = r4[q];
+                m = max(m, max(max(abs(v.x), abs(v.y)), max(abs(v.z), abs(v.w))));
             }
-            px += sx; py += sy; pz += sz;
-            if (px >= P) { px -= P; ++py; }
-            if (py >= P) { py -= P; ++pz; }
+            TileRow r;
+            if (m != 0 && tile_row(ox, oy, oz, row % PY, row / PY, PX, g, r)) {
+                vmax = max(vmax, m);
+                int* dst = out.mesh + (long long)r.z * (long long)plane + (size_t)r.y * g.nx;
+                cuda::ptx::cp_reduce_async_bulk(cuda::ptx::space_global, cuda::ptx::space_shared, cuda::ptx::op_add, dst + r.x0,
+                                                tile + row * PX, (unsigned)(r.first * sizeof(int)));
+                if (r.first < PX)
+                    cuda::ptx::cp_reduce_async_bulk(cuda::ptx::space_global, cuda::ptx::space_shared, cuda::ptx::op_add, dst,
+                                                    tile + row * PX + r.first, (unsigned)((PX - r.first) * sizeof(int)));
+            }
         }
+        cuda::ptx::cp_async_bulk_commit_group();
         // one eighth of the range: a cell sums at most 8 padded tiles, so no total has left the 32-bit range
         if (__any_sync(0xffffffffu, vmax > (1 << 28)) && (threadIdx.x & 31) == 0) atomicAdd(out.counters + 3, 1u);
+        cuda::ptx::cp_async_bulk_wait_group_read(cuda::ptx::n32_t<0>());       // the tile must outlive the reads
     }
     // deterministic sums: per-tile partials, the last CTA adds them in tile order
     const double tsq = block_sum(sq, red);
@@ -648,7 +757,7 @@ __device__ __noinline__ float3 gather_direct(float4 p, GatherDirectArgs a) {
     const Geom g = *a.g;
     const Cell c = particle_cell(p, g);
     GatherWeights w;
-    gather_weights(p, c, g, w);
+    gather_weights(particle_shift(p, c, g), w);
     const size_t plane = (size_t)g.nx * g.ny;
     float t27[27];
     for (int k = 0; k < 3; ++k)
@@ -667,83 +776,91 @@ __device__ __noinline__ float3 gather_direct(float4 p, GatherDirectArgs a) {
 }
 
 template <int LGT>
-__global__ void __launch_bounds__(kGatherThreads, 2)
-mesh_gather_kernel(const float4* __restrict__ postype, const unsigned* __restrict__ perm, const unsigned* __restrict__ tstart,
-                   const __grid_constant__ Geom g, const float* __restrict__ mode, const float* __restrict__ inv,
+__global__ void __launch_bounds__(kGatherThreads, 3)
+mesh_gather_kernel(const float4* __restrict__ postype, const unsigned* __restrict__ tstart,
+                   const float4* __restrict__ cache4, const uint2* __restrict__ cache_code,
+                   const __grid_constant__ Geom g, const float* __restrict__ inv,
                    const float* __restrict__ ghost /* slab mode: planes z0-1 and z0+nz of Re IFFT(G) */, ForceParams fp,
                    const double* __restrict__ d_bias, float4* __restrict__ force) {
-    constexpr int T = 1 << LGT, P = T + 2 * kHalo;
-    extern __shared__ float ftile[];
+    constexpr int T = 1 << LGT, PX = T + 2 * kHaloX, PY = T + 2 * kHalo, PZ = PY, P3 = PX * PY * PZ;
+    extern __shared__ __align__(16) float ftile[];          // P3 floats, then the staging buffers of the particle cache
+    float4* s_q = reinterpret_cast<float4*>(ftile + P3);    // [2][kGatherThreads]
+    uint2* s_c = reinterpret_cast<uint2*>(s_q + 2 * kGatherThreads);
+    __shared__ uint64_t bar;
     const unsigned s = __ldg(tstart + blockIdx.x), e = __ldg(tstart + blockIdx.x + 1);
     if (e == s) return;                                   // empty tile: nothing to interpolate
     unsigned tx, ty, tz;
     tile_coords(blockIdx.x, g, tx, ty, tz);
-    const int ox = (int)(tx << LGT) - kHalo, oy = (int)(ty << LGT) - kHalo, oz = (int)(tz << LGT) - kHalo;
+    const int ox = (int)(tx << LGT) - kHaloX, oy = (int)(ty << LGT) - kHalo, oz = (int)(tz << LGT) - kHalo;
     const size_t plane = (size_t)g.nx * g.ny;
-    // padded tile: flat index walked incrementally, four independent loads in flight per thread
-    {
-        constexpr int sx = kGatherThreads % P, sy = (kGatherThreads / P) % P, sz = kGatherThreads / (P * P);
-        int px = threadIdx.x % P, py = (threadIdx.x / P) % P, pz = threadIdx.x / (P * P);
-        const unsigned mx = g.nx - 1, my = g.ny - 1;
-        constexpr int P3 = P * P * P, U = 4;
-        for (int idx0 = threadIdx.x; idx0 < P3; idx0 += U * kGatherThreads) {
-            float v[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                v[u] = 0.f;
-                if (idx0 + u * kGatherThreads < P3) {
-                    const unsigned x = (unsigned)(ox + px) & mx, y = (unsigned)(oy + py) & my;
-                    int zl = oz + pz;                                    // local plane; -1 and nz are the ghost planes of a slab
-                    const float* src = nullptr;
-                    if (g.slab) {
-                        if (zl == -1) src = ghost;
-                        else if (zl == (int)g.nz) src = ghost + plane;
-                        else if (zl >= 0 && zl < (int)g.nz) src = inv + plane * (size_t)zl;
-                    } else {
-                        src = inv + plane * (size_t)((unsigned)zl & (g.nz - 1));
-                    }
-                    if (src) v[u] = __ldg(src + ((y << g.lgx) | x));
-                }
-                px += sx; py += sy; pz += sz;
-                if (px >= P) { px -= P; ++py; }
-                if (py >= P) { py -= P; ++pz; }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (idx0 + u * kGatherThreads < P3) ftile[idx0 + u * kGatherThreads] = v[u];
-        }
-    }
+    if (threadIdx.x == 0) cuda::ptx::mbarrier_init(&bar, kGatherThreads);
     __syncthreads();
+    // padded tile of Re IFFT(G): one bulk asynchronous copy (cp.async.bulk, TMA engine) per row, two if the row wraps in x;
+    // completion is counted in bytes on an mbarrier
+    {
+        unsigned bytes = 0;
+        for (int row = threadIdx.x; row < PY * PZ; row += kGatherThreads) {
+            TileRow r;
+            float* dst = ftile + row * PX;
+            if (tile_row(ox, oy, oz, row % PY, row / PY, PX, g, r)) {
+                const float* src;
+                if (g.slab && r.z == -1) src = ghost;
+                else if (g.slab && r.z == (int)g.nz) src = ghost + plane;
+                else src = inv + plane * (size_t)r.z;
+                src += (size_t)r.y * g.nx;
+                cuda::ptx::cp_async_bulk(cuda::ptx::space_cluster, cuda::ptx::space_global, dst, src + r.x0,
+                                         (unsigned)(r.first * sizeof(float)), &bar);
+                if (r.first < PX)
+                    cuda::ptx::cp_async_bulk(cuda::ptx::space_cluster, cuda::ptx::space_global, dst + r.first, src,
+                                             (unsigned)((PX - r.first) * sizeof(float)), &bar);
+                bytes += PX * sizeof(float);
+            } else {
+                for (int i = 0; i < PX; ++i) dst[i] = 0.f;          // plane outside the slab and its ghosts: never read by owned particles
+            }
+        }
+        cuda::ptx::mbarrier_arrive_expect_tx(cuda::ptx::sem_release, cuda::ptx::scope_cta, cuda::ptx::space_shared, &bar, bytes);
+    }
     const float scale = (float)(fp.two_over_n * *d_bias);
+    // one thread per particle of the tile; offsets, amplitude, padded-tile cell and particle index come from the cache
+    // the spread wrote.  The entries are staged through shared memory with asynchronous copies, one iteration ahead.
     unsigned j = s + threadIdx.x;
-    unsigned n = 0;
-    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (j < e) { n = __ldg(perm + j); p = __ldg(postype + n); }
-    while (j < e) {
+    int buf = 0;
+    if (j < e) {
+        __pipeline_memcpy_async(s_q + threadIdx.x, cache4 + j, sizeof(float4));
+        __pipeline_memcpy_async(s_c + threadIdx.x, cache_code + j, sizeof(uint2));
+    }
+    __pipeline_commit();
+    while (!cuda::ptx::mbarrier_try_wait_parity(&bar, 0)) {}
+    __syncthreads();                                       // zero-filled rows (generic stores) are visible too
+    for (; j < e; j += kGatherThreads) {
         const unsigned jn = j + kGatherThreads;
-        unsigned n_next = 0;
-        float4 p_next = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (jn < e) { n_next = __ldg(perm + jn); p_next = __ldg(postype + n_next); }
-        const Cell c = particle_cell(p, g);
+        if (jn < e) {
+            __pipeline_memcpy_async(s_q + (buf ^ 1) * kGatherThreads + threadIdx.x, cache4 + jn, sizeof(float4));
+            __pipeline_memcpy_async(s_c + (buf ^ 1) * kGatherThreads + threadIdx.x, cache_code + jn, sizeof(uint2));
+        }
+        __pipeline_commit();
+        __pipeline_wait_prior(1);                          // everything but the copies just issued has landed
+        const float4 q = s_q[buf * kGatherThreads + threadIdx.x];
+        const uint2 cn = s_c[buf * kGatherThreads + threadIdx.x];
+        const unsigned code = cn.x, n = cn.y;
+        buf ^= 1;
         float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c.owned) {
-            const float a = __ldg(mode + __float_as_int(p.w));
-            GatherWeights w;
-            gather_weights(p, c, g, w);
-            unsigned lx, ly, lz;
+        if (code & kCacheOwned) {
             float Sx, Sy, Sz;
-            if (padded_coords(c, ox, oy, oz, g, P, lx, ly, lz)) {
-                gather_sums(ftile + ((lz - 1) * P + (ly - 1)) * P + (lx - 1), P, P * P, w.wx, w.wy, w.wz, w.dx, w.dy, w.dz, Sx, Sy, Sz);
+            if (code & kCacheInside) {
+                GatherWeights w;
+                gather_weights(make_float3(q.x, q.y, q.z), w);
+                const unsigned lx = code & 1023u, ly = (code >> 10) & 1023u, lz = (code >> 20) & 1023u;
+                gather_sums(ftile + ((lz - 1) * PY + (ly - 1)) * PX + (lx - 1), PX, PX * PY, w.wx, w.wy, w.wz, w.dx, w.dy, w.dz, Sx, Sy, Sz);
             } else {
                 GatherDirectArgs da;
                 da.inv = inv; da.ghost = ghost; da.g = &g;
-                const float3 S = gather_direct(p, da);
+                const float3 S = gather_direct(__ldg(postype + n), da);
                 Sx = S.x; Sy = S.y; Sz = S.z;
             }
-            f = force_from_sums(Sx, Sy, Sz, a, fp, scale);
+            f = force_from_sums(Sx, Sy, Sz, q.w, fp, scale);
         }
         force[n] = f;
-        j = jn; n = n_next; p = p_next;
     }
 }
 #endif  // __CUDACC__

@@ -91,20 +91,36 @@ int main(int argc, char** argv) {
     start[M] = run;
     // the arrival rank of the device is arbitrary: emulate it reversed
     for (unsigned i = 0; i < N; ++i) perm[start[keys[i]] + (count[keys[i]] - 1 - ranks[i])] = i;
-    const unsigned T = 1u << g.lgT, P = T + 2 * kHalo, P3 = P * P * P, ntiles = num_tiles(g);
+    const unsigned T = 1u << g.lgT, PX = T + 2 * kHaloX, PY = T + 2 * kHalo, PZ = PY, P3 = PX * PY * PZ, ntiles = num_tiles(g);
     std::vector<unsigned> tstart(ntiles + 1);
     for (unsigned t = 0; t <= ntiles; ++t) tstart[t] = start[(size_t)t << (3 * g.lgT)];
+    // layer order inside every tile (mesh_layer_order_kernel)
+    {
+        std::vector<unsigned> order(N);
+        const unsigned cells = 1u << (3 * g.lgT);
+        for (unsigned t = 0; t < ntiles; ++t) {
+            const size_t key0 = (size_t)t << (3 * g.lgT);
+            unsigned out = tstart[t], layers = 0;
+            for (unsigned c = 0; c < cells; ++c) layers = std::max(layers, start[key0 + c + 1] - start[key0 + c]);
+            for (unsigned r = 0; r < layers; ++r)
+                for (unsigned c = 0; c < cells; ++c)
+                    if (start[key0 + c + 1] - start[key0 + c] > r) order[out++] = perm[start[key0 + c] + r];
+            if (out != tstart[t + 1]) { fprintf(stderr, "layer order lost particles\n"); return 3; }
+        }
+        perm.swap(order);
+    }
     const float scale = fx_scale_for(amax, amax * (float)max_count);
     const float inv_scale = 1.0f / scale;
 
     // ---- spread (mesh_spread_kernel): CTA per tile, integer padded tile, flush into the integer mesh
     std::vector<int> mesh_i(M, 0), tile(P3);
-    std::vector<unsigned> cell_keys(N);
+    std::vector<unsigned> cell_keys(N), cache_code_v(N);
+    std::vector<float4> cache4(N);
     double sums[2] = {0, 0}, shift_err = 0.0;
     unsigned strays = 0;
     for (unsigned tile_id = 0; tile_id < ntiles; ++tile_id) {
         unsigned tx, ty, tz; tile_coords(tile_id, g, tx, ty, tz);
-        const int ox = (int)(tx << g.lgT) - kHalo, oy = (int)(ty << g.lgT) - kHalo, oz = (int)(tz << g.lgT) - kHalo;
+        const int ox = (int)(tx << g.lgT) - kHaloX, oy = (int)(ty << g.lgT) - kHalo, oz = (int)(tz << g.lgT) - kHalo;
         std::fill(tile.begin(), tile.end(), 0);
         double sq = 0.0, s1 = 0.0;
         for (unsigned j = tstart[tile_id]; j < tstart[tile_id + 1]; ++j) {
@@ -116,17 +132,21 @@ int main(int argc, char** argv) {
             cell_keys[n] = key_of(c.ix, c.iy, c.iz, g);
             sq += (double)a * (double)a; s1 += (double)a;
             float w[9];
-            spread_weights(p, c, a * scale, g, w);
+            const float3 sh = particle_shift(p, c, g);
+            spread_weights(sh, a * scale, w);
             const float xyz[3] = {p.x, p.y, p.z};
             const int cxyz[3] = {c.ix, c.iy, c.iz};
             for (int d = 0; d < 3; ++d)
                 shift_err = std::max(shift_err, (double)std::fabs(cell_shift(xyz[d], cxyz[d], d, g) - cell_shift_f64(xyz[d], cxyz[d], d, g)));
             unsigned lx, ly, lz;
-            if (padded_coords(c, ox, oy, oz, g, P, lx, ly, lz)) {
-                int* base = tile.data() + ((lz - 1) * P + (ly - 1)) * P + (lx - 1);
+            const bool inside = padded_coords(c, ox, oy, oz, g, PX, PY, PZ, lx, ly, lz);
+            cache4[j] = make_float4(sh.x, sh.y, sh.z, a);
+            cache_code_v[j] = cache_code(lx, ly, lz, inside, true);
+            if (inside) {
+                int* base = tile.data() + ((lz - 1) * PY + (ly - 1)) * PX + (lx - 1);
                 for (int k = 0; k < 3; ++k) for (int jj = 0; jj < 3; ++jj) {
                     const float wyz = f_mul(w[3 + jj], w[6 + k]);
-                    for (int i = 0; i < 3; ++i) base[(k * P + jj) * P + i] += fx_round(w[i], wyz);
+                    for (int i = 0; i < 3; ++i) base[(k * PY + jj) * PX + i] += fx_round(w[i], wyz);
                 }
             } else {
                 ++strays;
@@ -137,13 +157,13 @@ int main(int argc, char** argv) {
             }
         }
         sums[0] += sq; sums[1] += s1;
-        for (unsigned idx = 0; idx < P3; ++idx) {
-            const int v = tile[idx];
-            if (v != 0) {
-                const int px = idx % P, py = (idx / P) % P, pz = idx / (P * P);
-                const unsigned x = (unsigned)(ox + px) & (g.nx - 1), y = (unsigned)(oy + py) & (g.ny - 1), z = (unsigned)(oz + pz) & (g.nz - 1);
-                mesh_i[(size_t)x + (size_t)g.nx * (y + (size_t)g.ny * z)] += v;
-            }
+        // flush: row-wise bulk reductions (tile_row: start, wrap point)
+        for (unsigned row = 0; row < PY * PZ; ++row) {
+            TileRow r;
+            if (!tile_row(ox, oy, oz, row % PY, row / PY, PX, g, r)) continue;
+            int* dst = mesh_i.data() + ((size_t)r.z * g.ny + r.y) * g.nx;
+            for (int i = 0; i < r.first; ++i) dst[r.x0 + i] += tile[row * PX + i];
+            for (int i = r.first; i < (int)PX; ++i) dst[i - r.first] += tile[row * PX + i];
         }
     }
     // ---- x forward load phase (fft_x_fwd_kernel): int -> float, mean removal
@@ -176,26 +196,26 @@ int main(int argc, char** argv) {
     std::vector<float> ftile(P3);
     for (unsigned tile_id = 0; tile_id < ntiles; ++tile_id) {
         unsigned tx, ty, tz; tile_coords(tile_id, g, tx, ty, tz);
-        const int ox = (int)(tx << g.lgT) - kHalo, oy = (int)(ty << g.lgT) - kHalo, oz = (int)(tz << g.lgT) - kHalo;
-        for (unsigned row = 0; row < P * P; ++row) {
-            const unsigned py = row % P, pz = row / P;
-            const unsigned y = (unsigned)(oy + (int)py) & (g.ny - 1), z = (unsigned)(oz + (int)pz) & (g.nz - 1);
-            for (unsigned lane = 0; lane < P; ++lane) {
-                const unsigned x = (unsigned)(ox + (int)lane) & (g.nx - 1);
-                ftile[row * P + lane] = buf[(size_t)x + (size_t)g.nx * (y + (size_t)g.ny * z)];
-            }
+        const int ox = (int)(tx << g.lgT) - kHaloX, oy = (int)(ty << g.lgT) - kHalo, oz = (int)(tz << g.lgT) - kHalo;
+        for (unsigned row = 0; row < PY * PZ; ++row) {
+            TileRow r;
+            if (!tile_row(ox, oy, oz, row % PY, row / PY, PX, g, r)) continue;
+            const float* src = buf.data() + ((size_t)r.z * g.ny + r.y) * g.nx;
+            for (int i = 0; i < r.first; ++i) ftile[row * PX + i] = src[r.x0 + i];
+            for (int i = r.first; i < (int)PX; ++i) ftile[row * PX + i] = src[i - r.first];
         }
         for (unsigned j = tstart[tile_id]; j < tstart[tile_id + 1]; ++j) {
             const unsigned n = perm[j];
             const float4 p = postype[n];
-            int t; memcpy(&t, &p.w, 4);
+            const unsigned code = cache_code_v[j];
+            const float4 q = cache4[j];
             const Cell c = particle_cell(p, g);
             GatherWeights w;
-            gather_weights(p, c, g, w);
-            unsigned lx, ly, lz;
+            gather_weights(make_float3(q.x, q.y, q.z), w);
             float Sx, Sy, Sz;
-            if (padded_coords(c, ox, oy, oz, g, P, lx, ly, lz)) {
-                gather_sums(ftile.data() + ((lz - 1) * P + (ly - 1)) * P + (lx - 1), P, P * P, w.wx, w.wy, w.wz, w.dx, w.dy, w.dz, Sx, Sy, Sz);
+            if (code & kCacheInside) {
+                const unsigned lx = code & 1023u, ly = (code >> 10) & 1023u, lz = (code >> 20) & 1023u;
+                gather_sums(ftile.data() + ((lz - 1) * PY + (ly - 1)) * PX + (lx - 1), PX, PX * PY, w.wx, w.wy, w.wz, w.dx, w.dy, w.dz, Sx, Sy, Sz);
             } else {        // gather_direct
                 float t27[27];
                 for (int k = 0; k < 3; ++k) for (int jj = 0; jj < 3; ++jj) for (int i = 0; i < 3; ++i) {
@@ -204,7 +224,7 @@ int main(int argc, char** argv) {
                 }
                 gather_sums(t27, 3, 9, w.wx, w.wy, w.wz, w.dx, w.dy, w.dz, Sx, Sy, Sz);
             }
-            force[n] = force_from_sums(Sx, Sy, Sz, mode[t], fp, fscale);
+            force[n] = force_from_sums(Sx, Sy, Sz, q.w, fp, fscale);
         }
     }
     // ---- dump: cv, mode_sq, shift_err, strays, scale, cell rule mismatches, rho[M], inv[M], force[4N], cells[3N]
