@@ -127,6 +127,28 @@ int metad_mesh_slab_fft_x_inv(metad_mesh* p, const float* d_recv, float* d_plane
 int metad_mesh_slab_forces(metad_mesh* p, const float* d_ghost_inv, const float* d_postype, float* d_force, unsigned N_local,
                            unsigned N_global, const metad_box* global_box, const double* d_bias, metad_stream_t stream);
 
+/* The same decomposition over PEER MEMORY (NVLink, CUDA IPC) -- no library collective inside a step.  Every rank owns an
+ * arena (pencil, receive buffer, halo slots, per-rank scalar tables, barrier flags) that its peers map; the transposes of the
+ * distributed FFT are fused into the FFT sweeps (the x forward pass stores each kx pencil straight into the owner's
+ * arena, the inverse y pass each plane), halos and partial sums are pushed with plain P2P stores, and the ranks meet at
+ * four flag barriers per step which also perform the tiny all-reduces in rank order (identical result on every rank).
+ *   metad_mesh_slab_p2p_arena     allocate the arena, return its CUDA IPC handle (64 bytes) to be all-gathered by the caller
+ *   metad_mesh_slab_p2p_connect   map the peers: handles = n_ranks x 64 bytes in rank order (own slot ignored)
+ *   metad_mesh_slab_p2p_connect_local   same for "ranks" living in ONE process (tests): plans[] in rank order
+ *   metad_mesh_slab_p2p_cv        stage = -1: the whole step (spread ... CV, ready for forces); every rank must call it
+ *                                 the same number of times.  stage = 0..4: one stage without its barrier wait, for
+ *                                 bulk-synchronous emulation of all ranks in one process (stage k for every rank, then k+1).
+ *                                 *d_cv receives the global CV on every rank.
+ *   metad_mesh_slab_p2p_forces    interpolateForces for the local particles (halo planes are already in the arena)
+ * Up to 8 ranks (one NVSwitch domain).  metad_mesh_get(p, 6, unsigned[2]) reports a barrier time-out / misplaced particles. */
+int metad_mesh_slab_p2p_arena(metad_mesh* p, void* handle_out /* 64 bytes */, unsigned long long* bytes_out);
+int metad_mesh_slab_p2p_connect(metad_mesh* p, const void* handles);
+int metad_mesh_slab_p2p_connect_local(metad_mesh* p, metad_mesh* const* plans);
+int metad_mesh_slab_p2p_cv(metad_mesh* p, const float* d_postype, unsigned N_local, unsigned N_global, const metad_box* global_box,
+                           double* d_cv, int stage, metad_stream_t stream);
+int metad_mesh_slab_p2p_forces(metad_mesh* p, const float* d_postype, float* d_force, unsigned N_local, unsigned N_global,
+                               const metad_box* global_box, const double* d_bias, metad_stream_t stream);
+
 /* Introspection for parity tests (synchronous, copies to HOST buffers):
  *   which = 0: cell coordinates (ix,iy,iz) per particle as computed by the spread, int[3*N], input order (needs key 3)
  *           1: density mesh rho, float[nx*ny*nz], index x + nx*(y + ny*z) (needs key 1)
@@ -136,7 +158,8 @@ int metad_mesh_slab_forces(metad_mesh* p, const float* d_ghost_inv, const float*
  *              reuse it), spread, fft x fwd, fft y fwd, fft z fused, fft y inv, fft x inv, gather
  *           5: statistics, double[6]: rebuilds of the tile order so far; of the last spread: particles that took the
  *              direct path (drifted out of their padded tile), particles outside the slab, padded-tile cells past 1/8 of
- *              the fixed-point range; the fixed-point scale; calls since the last rebuild                              */
+ *              the fixed-point range; the fixed-point scale; calls since the last rebuild
+ *           6: peer-memory mode, unsigned[2]: {a barrier timed out, particles outside their slab summed over the ranks}    */
 int metad_mesh_get(metad_mesh* p, int which, void* h_out);
 /* knobs: key 0 = rebuild period of the tile order in calls (default 32; value 0 = rebuild at the next call)
  *        key 1 = keep a copy of rho for metad_mesh_get(1)      key 2 = record per-stage CUDA events (profiling)

@@ -64,6 +64,11 @@ SIGNATURES = {
     "metad_mesh_slab_fft_yz": (C.c_int, [_vp, _vp, _vp, C.c_uint, _vp, _vp]),
     "metad_mesh_slab_fft_x_inv": (C.c_int, [_vp, _vp, _vp, _vp]),
     "metad_mesh_slab_forces": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint, C.c_uint, _boxp, _vp, _vp]),
+    "metad_mesh_slab_p2p_arena": (C.c_int, [_vp, _vp, C.POINTER(C.c_ulonglong)]),
+    "metad_mesh_slab_p2p_connect": (C.c_int, [_vp, _vp]),
+    "metad_mesh_slab_p2p_connect_local": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "metad_mesh_slab_p2p_cv": (C.c_int, [_vp, _vp, C.c_uint, C.c_uint, _boxp, _vp, C.c_int, _vp]),
+    "metad_mesh_slab_p2p_forces": (C.c_int, [_vp, _vp, _vp, C.c_uint, C.c_uint, _boxp, _vp, _vp]),
     "metad_mesh_get": (C.c_int, [_vp, C.c_int, _vp]),
     "metad_mesh_set": (C.c_int, [_vp, C.c_int, C.c_long]),
     "metad_grid_create": (C.c_int, [C.POINTER(_vp), C.c_int, _dp, _dp, _up, _dp, C.c_double, C.c_double, C.c_double,

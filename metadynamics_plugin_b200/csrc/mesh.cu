@@ -28,6 +28,7 @@
 // between them.  Integer halo addition makes the sharded density bitwise equal to the single-GPU one.
 #include "mesh_kernels.cuh"
 #include "mesh_fft_kernels.cuh"
+#include "mesh_p2p.cuh"
 
 #include <cmath>
 #include <vector>
@@ -65,7 +66,7 @@ struct metad_mesh {
     float* d_buf = nullptr;         // M_local floats: packed half spectrum -> Re IFFT(G)
     float* d_rho_keep = nullptr;    // optional copy of rho (introspection)
     float2 *d_twx = nullptr, *d_twy = nullptr, *d_twz = nullptr;
-    float* d_fx = nullptr;          // {scale, 1/scale} of the fixed-point density
+    float* d_fx = nullptr;          // {scale, 1/scale} of the fixed-point density (+ a 16-byte copy of 1/scale at [4])
     double* d_sums = nullptr;       // [0] sum a^2  [1] sum a  [2] particles outside the slab
     double* d_tile_sums = nullptr;
     unsigned* d_counters = nullptr; // [0] ticket [1] drifted particles [2] particles outside the slab [3] cells near the range limit
@@ -73,6 +74,16 @@ struct metad_mesh {
     double* d_partials = nullptr;
     unsigned* d_ticket = nullptr;
     unsigned n_partials = 0;
+    // peer-memory mode of the slab path (mesh_p2p.cuh): arena of this rank, the peers' arenas mapped through CUDA IPC
+    char* arena = nullptr;
+    p2p::ArenaLayout lay = {};
+    p2p::PeerTable peers = {};
+    bool peers_mapped[p2p::kMaxPeers] = {};     // opened with cudaIpcOpenMemHandle (to be closed)
+    bool p2p_ready = false;
+    unsigned epoch = 0;
+    double* d_sums_global = nullptr;            // [4] sums over all ranks
+    double* d_cv_partial = nullptr;
+    unsigned* d_p2p_status = nullptr;
     // state
     bool have_cv = false;
     unsigned last_N = 0;
@@ -109,11 +120,12 @@ template <class K> int set_smem(K kernel, size_t bytes) {
 // x pass over the local rows.  io: nullptr = the plan's own buffer; otherwise the packed all-to-all buffer (output of
 // the forward pass / input of the inverse pass), [part][row][kx in part] with parts of width kxl.
 // Forward: consumes (and clears) the integer density; d_sums = (global) sums, d_ghost = received halo planes (slab).
-template <int LC> int run_x(metad_mesh* p, bool inverse, float2* io, const double* d_sums, const int* d_ghost, cudaStream_t st) {
+template <int LC> int run_x(metad_mesh* p, bool inverse, float2* io, const double* d_sums, const int* d_ghost, cudaStream_t st,
+                            const PeerOut* peer_out = nullptr) {
     const size_t smem = sizeof(float2) * (LayoutRow::size(LC) + 2 * LC);
     const unsigned rows = p->g.ny * p->g.nz;
     float2* buf = reinterpret_cast<float2*>(p->d_buf);
-    const unsigned lg_part = io ? ilog2(p->kxl) : ilog2(LC);
+    const unsigned lg_part = (io || peer_out) ? ilog2(p->kxl) : ilog2(LC);
     if (!inverse) {
         int rc = set_smem(fft_x_fwd_kernel<LC>, smem); if (rc) return rc;
         DensityIn in;
@@ -124,7 +136,10 @@ template <int LC> int run_x(metad_mesh* p, bool inverse, float2* io, const doubl
         in.ghost = reinterpret_cast<const int2*>(d_ghost);
         in.lgy = p->g.lgy; in.nz = p->g.nz;
         in.rho_keep = p->keep_rho ? reinterpret_cast<float2*>(p->d_rho_keep) : nullptr;
-        fft_x_fwd_kernel<LC><<<rows / kLines, kLines * LC / kE, smem, st>>>(in, p->d_twx, io ? io : buf, lg_part, rows);
+        PeerOut po;
+        memset(&po, 0, sizeof po);
+        if (peer_out) po = *peer_out;
+        fft_x_fwd_kernel<LC><<<rows / kLines, kLines * LC / kE, smem, st>>>(in, p->d_twx, io ? io : buf, lg_part, rows, po);
         METAD_LAUNCH_CHECK();
         // the accumulator is empty again for the next spread (a plain memset runs at the full write bandwidth)
         METAD_CUDA(cudaMemsetAsync(p->d_mesh_i, 0, sizeof(int) * p->M(), st));
@@ -136,15 +151,20 @@ template <int LC> int run_x(metad_mesh* p, bool inverse, float2* io, const doubl
     return METAD_OK;
 }
 // y pass on buf = [nz_rows][ny][row_len]
-template <int L> int run_y(metad_mesh* p, bool inverse, float2* buf, unsigned row_len, unsigned nz_rows, cudaStream_t st) {
+template <int L> int run_y(metad_mesh* p, bool inverse, float2* buf, unsigned row_len, unsigned nz_rows, cudaStream_t st,
+                           const PeerOut* peer_out = nullptr) {
     const size_t smem = sizeof(float2) * (LayoutCol::size(L) + L);
     dim3 grid(row_len / kLines, nz_rows);
+    PeerOut po;
+    memset(&po, 0, sizeof po);
+    if (peer_out) po = *peer_out;
+    const unsigned lg_planes = ilog2(p->g.nz);
     if (!inverse) {
         int rc = set_smem(fft_y_kernel<L, -1>, smem); if (rc) return rc;
-        fft_y_kernel<L, -1><<<grid, kLines * L / kE, smem, st>>>(buf, p->d_twy, row_len);
+        fft_y_kernel<L, -1><<<grid, kLines * L / kE, smem, st>>>(buf, p->d_twy, row_len, po, lg_planes);
     } else {
         int rc = set_smem(fft_y_kernel<L, +1>, smem); if (rc) return rc;
-        fft_y_kernel<L, +1><<<grid, kLines * L / kE, smem, st>>>(buf, p->d_twy, row_len);
+        fft_y_kernel<L, +1><<<grid, kLines * L / kE, smem, st>>>(buf, p->d_twy, row_len, po, lg_planes);
     }
     METAD_LAUNCH_CHECK();
     return METAD_OK;
@@ -388,7 +408,7 @@ int create_common(metad_mesh** out, unsigned nx, unsigned ny, unsigned nzg, unsi
     p->n_partials = nby + (p->kxl / kLines) * ny;
     const size_t plane = (size_t)nx * ny;
     const size_t mesh_ints = M + (slab ? 2 * plane : 0);
-    const float fx_init[2] = {1.0f, 1.0f};
+    const float fx_init[8] = {1.0f, 1.0f, 0.f, 0.f, 1.0f, 0.f, 0.f, 0.f};
     int rc = METAD_OK;
     auto fail = [&](cudaError_t e, const char* what) { rc = cuda_fail(e, what, __FILE__, __LINE__); };
     cudaError_t e;
@@ -405,7 +425,7 @@ int create_common(metad_mesh** out, unsigned nx, unsigned ny, unsigned nzg, unsi
     TRY(cudaMalloc(&p->d_mesh_alloc, sizeof(int) * mesh_ints));
     TRY(cudaMemset(p->d_mesh_alloc, 0, sizeof(int) * mesh_ints));
     TRY(cudaMalloc(&p->d_buf, sizeof(float) * M));
-    TRY(cudaMalloc(&p->d_fx, sizeof(float) * 2));
+    TRY(cudaMalloc(&p->d_fx, sizeof(float) * 8));      // {scale, 1/scale, -, -, 1/scale, 0, 0, 0}: [4..7] = trailer of a halo message
     TRY(cudaMemcpy(p->d_fx, fx_init, sizeof fx_init, cudaMemcpyHostToDevice));
     TRY(cudaMalloc(&p->d_sums, sizeof(double) * 4));
     TRY(cudaMemset(p->d_sums, 0, sizeof(double) * 4));
@@ -416,6 +436,11 @@ int create_common(metad_mesh** out, unsigned nx, unsigned ny, unsigned nzg, unsi
     TRY(cudaMalloc(&p->d_partials, sizeof(double) * p->n_partials));
     TRY(cudaMalloc(&p->d_ticket, sizeof(unsigned)));
     TRY(cudaMemset(p->d_ticket, 0, sizeof(unsigned)));
+    TRY(cudaMalloc(&p->d_sums_global, sizeof(double) * 4));
+    TRY(cudaMemset(p->d_sums_global, 0, sizeof(double) * 4));
+    TRY(cudaMalloc(&p->d_cv_partial, sizeof(double)));
+    TRY(cudaMalloc(&p->d_p2p_status, sizeof(unsigned)));
+    TRY(cudaMemset(p->d_p2p_status, 0, sizeof(unsigned)));
 #undef TRY
     if (rc == METAD_OK) {
         memset(p->h_counters, 0, sizeof(unsigned) * 4);
@@ -449,6 +474,10 @@ extern "C" int metad_mesh_destroy(metad_mesh* p) {
     if (p->h_counters) cudaFreeHost(p->h_counters);
     cudaFree(p->d_rho_keep); cudaFree(p->d_twx); cudaFree(p->d_twy); cudaFree(p->d_twz); cudaFree(p->d_sums);
     cudaFree(p->d_partials); cudaFree(p->d_ticket);
+    cudaFree(p->d_sums_global); cudaFree(p->d_cv_partial); cudaFree(p->d_p2p_status);
+    for (unsigned r = 0; r < p2p::kMaxPeers; ++r)
+        if (p->peers_mapped[r]) cudaIpcCloseMemHandle(p->peers.arena[r]);
+    cudaFree(p->arena);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     delete p;
     return METAD_OK;
@@ -560,6 +589,177 @@ extern "C" int metad_mesh_slab_forces(metad_mesh* p, const float* d_ghost_inv, c
     return launch_gather(p, d_postype, d_ghost_inv, d_force, N_global, global_box, d_bias, stream);
 }
 
+// ---- z-slab stages over peer memory (NVLink): no library collective inside a step ----------------------------
+namespace {
+
+int ensure_arena(metad_mesh* p) {
+    if (p->arena) return METAD_OK;
+    METAD_REQUIRE(p->g.slab, "peer-memory mode: not a slab plan");
+    METAD_REQUIRE(p->n_ranks <= (unsigned)p2p::kMaxPeers, "peer-memory mode supports up to 8 ranks");
+    p->lay = p2p::arena_layout(p->M(), (size_t)p->g.nx * p->g.ny);
+    METAD_CUDA(cudaMalloc(&p->arena, p->lay.total));
+    METAD_CUDA(cudaMemset(p->arena, 0, p->lay.total));
+    return METAD_OK;
+}
+
+int p2p_barrier(metad_mesh* p, int wait, const double* table, unsigned per_rank, unsigned width, double* out, cudaStream_t st) {
+    if (wait) ++p->epoch;
+    p2p::barrier_reduce_kernel<<<1, 32, 0, st>>>(p->peers, p->lay.flags, p->epoch, wait, table, per_rank, width, out, p->d_p2p_status);
+    METAD_LAUNCH_CHECK();
+    return METAD_OK;
+}
+
+int p2p_stage(metad_mesh* p, int stage, int wait, const float* d_postype, unsigned N_local, unsigned N_global, const metad_box* box,
+              double* d_cv, cudaStream_t st) {
+    const Geom& g = p->g;
+    const size_t plane = (size_t)g.nx * g.ny;
+    const unsigned P = p->n_ranks, r = p->rank, down = (r + P - 1) % P, up = (r + 1) % P;
+    char* mine = p->arena;
+    int rc = METAD_OK;
+    switch (stage) {
+        case 0: {   // local spread; halo planes of the density (+ their scale) to the neighbours, partial sums to everyone
+            rc = set_box(p, box); if (rc) return rc;
+            p->have_cv = false;
+            rc = order_and_spread(p, d_postype, N_local, st); if (rc) return rc;
+            int* below = p->d_mesh_alloc;
+            int* above = p->d_mesh_alloc + plane * (g.nz + 1);
+            const size_t msg = (plane + 4) * sizeof(int);
+            p2p::PushJob job;
+            memset(&job, 0, sizeof job);
+            // what goes down arrives as the lower rank's message [1] (added to its last plane), what goes up as message [0]
+            char* gd = p->peers.arena[down] + p->lay.ghost_rho + msg;
+            char* gu = p->peers.arena[up] + p->lay.ghost_rho;
+            job.dst[0] = (int4*)gd; job.src[0] = (const int4*)below; job.n16[0] = (unsigned)(plane * sizeof(int) / 16);
+            job.dst[1] = (int4*)(gd + plane * sizeof(int)); job.src[1] = (const int4*)(p->d_fx + 4); job.n16[1] = 1;
+            job.dst[2] = (int4*)gu; job.src[2] = (const int4*)above; job.n16[2] = (unsigned)(plane * sizeof(int) / 16);
+            job.dst[3] = (int4*)(gu + plane * sizeof(int)); job.src[3] = (const int4*)(p->d_fx + 4); job.n16[3] = 1;
+            p2p::push_kernel<<<32, 256, 0, st>>>(job);
+            METAD_LAUNCH_CHECK();
+            p2p::push_scalars_kernel<<<1, 64, 0, st>>>(p->peers, p->lay.sums, 4, p->d_sums, 3);
+            METAD_LAUNCH_CHECK();
+            METAD_CUDA(cudaMemsetAsync(below, 0, plane * sizeof(int), st));
+            METAD_CUDA(cudaMemsetAsync(above, 0, plane * sizeof(int), st));
+            p->last_N = N_local;
+            return METAD_OK;
+        }
+        case 1: {   // [barrier: halos and sums have arrived] x forward pass, every kx pencil stored into its owner's memory
+            rc = p2p_barrier(p, wait, (const double*)(mine + p->lay.sums), 4, 3, p->d_sums_global, st); if (rc) return rc;
+            if (p->keep_rho && !p->d_rho_keep) METAD_CUDA(cudaMalloc(&p->d_rho_keep, sizeof(float) * p->M()));
+            PeerOut po;
+            memset(&po, 0, sizeof po);
+            po.n = P; po.rank = r;
+            for (unsigned q = 0; q < P; ++q) po.ptr[q] = (float2*)(p->peers.arena[q] + p->lay.pencil);
+            METAD_DISPATCH_LEN(g.nx / 2, (run_x<LL>(p, false, nullptr, p->d_sums_global, (const int*)(mine + p->lay.ghost_rho), st, &po)));
+            return rc;
+        }
+        case 2: {   // [barrier: the pencil is complete] y, fused z, inverse y with every plane stored into its owner's memory
+            rc = p2p_barrier(p, wait, nullptr, 0, 0, nullptr, st); if (rc) return rc;
+            float2* pen = (float2*)(mine + p->lay.pencil);
+            METAD_DISPATCH_LEN(g.ny, (run_y<LL>(p, false, pen, p->kxl, p->nzg, st))); if (rc) return rc;
+            METAD_DISPATCH_LEN(p->nzg, (run_z<LL>(p, pen, p->kxl, r * p->kxl, p->d_sums_global, N_global, p->d_cv_partial, st))); if (rc) return rc;
+            PeerOut po;
+            memset(&po, 0, sizeof po);
+            po.n = P; po.rank = r;
+            for (unsigned q = 0; q < P; ++q) po.ptr[q] = (float2*)(p->peers.arena[q] + p->lay.recv);
+            METAD_DISPATCH_LEN(g.ny, (run_y<LL>(p, true, pen, p->kxl, p->nzg, st, &po))); if (rc) return rc;
+            p2p::push_scalars_kernel<<<1, 64, 0, st>>>(p->peers, p->lay.cv, 1, p->d_cv_partial, 1);
+            METAD_LAUNCH_CHECK();
+            return METAD_OK;
+        }
+        case 3: {   // [barrier: planes and CV partials have arrived] CV, inverse x pass, halo planes of Re IFFT(G) to the neighbours
+            rc = p2p_barrier(p, wait, (const double*)(mine + p->lay.cv), 1, 1, d_cv, st); if (rc) return rc;
+            METAD_DISPATCH_LEN(g.nx / 2, (run_x<LL>(p, true, (float2*)(mine + p->lay.recv), nullptr, nullptr, st))); if (rc) return rc;
+            p2p::PushJob job;
+            memset(&job, 0, sizeof job);
+            // my first plane is the lower rank's plane z0+nz (its ghost [1]); my last plane the upper rank's plane z0-1 (ghost [0])
+            job.dst[0] = (int4*)(p->peers.arena[down] + p->lay.ghost_inv + plane * sizeof(float));
+            job.src[0] = (const int4*)p->d_buf; job.n16[0] = (unsigned)(plane * sizeof(float) / 16);
+            job.dst[1] = (int4*)(p->peers.arena[up] + p->lay.ghost_inv);
+            job.src[1] = (const int4*)(p->d_buf + plane * (g.nz - 1)); job.n16[1] = (unsigned)(plane * sizeof(float) / 16);
+            p2p::push_kernel<<<32, 256, 0, st>>>(job);
+            METAD_LAUNCH_CHECK();
+            return METAD_OK;
+        }
+        case 4:     // [barrier: the halo planes of Re IFFT(G) have arrived]
+            rc = p2p_barrier(p, wait, nullptr, 0, 0, nullptr, st); if (rc) return rc;
+            p->have_cv = true;
+            return METAD_OK;
+        default:
+            set_error("metad_mesh_slab_p2p_cv: stage must be -1 (whole step) or 0..4");
+            return METAD_ERR_INVALID;
+    }
+}
+
+}  // namespace
+
+extern "C" int metad_mesh_slab_p2p_arena(metad_mesh* p, void* handle_out, unsigned long long* bytes_out) {
+    METAD_REQUIRE(p && handle_out, "metad_mesh_slab_p2p_arena: null argument");
+    int rc = ensure_arena(p); if (rc) return rc;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    cudaIpcMemHandle_t h;
+    METAD_CUDA(cudaIpcGetMemHandle(&h, p->arena));
+    memcpy(handle_out, &h, sizeof h);
+    if (bytes_out) *bytes_out = p->lay.total;
+    return METAD_OK;
+}
+
+extern "C" int metad_mesh_slab_p2p_connect(metad_mesh* p, const void* handles) {
+    METAD_REQUIRE(p && handles, "metad_mesh_slab_p2p_connect: null argument");
+    int rc = ensure_arena(p); if (rc) return rc;
+    p->peers.n = p->n_ranks; p->peers.rank = p->rank;
+    for (unsigned r = 0; r < p->n_ranks; ++r) {
+        if (r == p->rank) { p->peers.arena[r] = p->arena; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles + 64 * (size_t)r, sizeof h);
+        void* ptr = nullptr;
+        METAD_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        p->peers.arena[r] = (char*)ptr;
+        p->peers_mapped[r] = true;
+    }
+    p->p2p_ready = true;
+    return METAD_OK;
+}
+
+extern "C" int metad_mesh_slab_p2p_connect_local(metad_mesh* p, metad_mesh* const* plans) {
+    METAD_REQUIRE(p && plans, "metad_mesh_slab_p2p_connect_local: null argument");
+    int rc = ensure_arena(p); if (rc) return rc;
+    p->peers.n = p->n_ranks; p->peers.rank = p->rank;
+    for (unsigned r = 0; r < p->n_ranks; ++r) {
+        METAD_REQUIRE(plans[r] && plans[r]->n_ranks == p->n_ranks && plans[r]->rank == r, "metad_mesh_slab_p2p_connect_local: plans must be in rank order");
+        rc = ensure_arena(plans[r]); if (rc) return rc;
+        p->peers.arena[r] = plans[r]->arena;
+    }
+    p->p2p_ready = true;
+    return METAD_OK;
+}
+
+extern "C" int metad_mesh_slab_p2p_cv(metad_mesh* p, const float* d_postype, unsigned N_local, unsigned N_global, const metad_box* box,
+                                      double* d_cv, int stage, metad_stream_t stream) {
+    METAD_REQUIRE(p && box && d_cv, "metad_mesh_slab_p2p_cv: null argument");
+    METAD_REQUIRE(p->g.slab && p->p2p_ready, "metad_mesh_slab_p2p_cv: connect the peers first (metad_mesh_slab_p2p_connect)");
+    METAD_REQUIRE(N_local == 0 || d_postype, "metad_mesh_slab_p2p_cv: null positions");
+    METAD_REQUIRE(N_global > 0, "metad_mesh_slab_p2p_cv: N_global must be positive");
+    if (stage >= 0) return p2p_stage(p, stage, 0, d_postype, N_local, N_global, box, d_cv, stream);
+    for (int s = 0; s <= 4; ++s) {
+        const int rc = p2p_stage(p, s, 1, d_postype, N_local, N_global, box, d_cv, stream);
+        if (rc) return rc;
+    }
+    return METAD_OK;
+}
+
+extern "C" int metad_mesh_slab_p2p_forces(metad_mesh* p, const float* d_postype, float* d_force, unsigned N_local, unsigned N_global,
+                                          const metad_box* box, const double* d_bias, metad_stream_t stream) {
+    METAD_REQUIRE(p && box && d_bias, "metad_mesh_slab_p2p_forces: null argument");
+    METAD_REQUIRE(p->g.slab && p->p2p_ready, "metad_mesh_slab_p2p_forces: connect the peers first");
+    if (!p->have_cv || p->last_N != N_local) {
+        set_error("metad_mesh_slab_p2p_forces: run metad_mesh_slab_p2p_cv for the same particles first");
+        return METAD_ERR_STATE;
+    }
+    if (N_local == 0) return METAD_OK;
+    METAD_REQUIRE(d_postype && d_force, "metad_mesh_slab_p2p_forces: null particle arrays");
+    return launch_gather(p, d_postype, (const float*)(p->arena + p->lay.ghost_inv), d_force, N_global, box, d_bias, stream);
+}
+
 extern "C" int metad_mesh_get(metad_mesh* p, int which, void* h_out) {
     METAD_REQUIRE(p && h_out, "metad_mesh_get: null argument");
     METAD_CUDA(cudaDeviceSynchronize());
@@ -606,6 +806,14 @@ extern "C" int metad_mesh_get(metad_mesh* p, int which, void* h_out) {
             METAD_CUDA(cudaMemcpy(c, p->d_counters, sizeof c, cudaMemcpyDeviceToHost));
             METAD_CUDA(cudaMemcpy(fx, p->d_fx, sizeof fx, cudaMemcpyDeviceToHost));
             out[0] = (double)p->n_rebuilds; out[1] = c[1]; out[2] = c[2]; out[3] = c[3]; out[4] = fx[0]; out[5] = p->calls_since_rebuild;
+            return METAD_OK;
+        }
+        case 6: {   // peer-memory mode: unsigned[2] = {a barrier timed out (a peer never arrived), sum over ranks of particles outside their slab}
+            unsigned* out = (unsigned*)h_out;
+            double sg[4];
+            METAD_CUDA(cudaMemcpy(out, p->d_p2p_status, sizeof(unsigned), cudaMemcpyDeviceToHost));
+            METAD_CUDA(cudaMemcpy(sg, p->d_sums_global, sizeof sg, cudaMemcpyDeviceToHost));
+            out[1] = (unsigned)sg[2];
             return METAD_OK;
         }
         default:

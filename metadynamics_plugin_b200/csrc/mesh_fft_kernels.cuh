@@ -83,6 +83,17 @@ template <int TWL> __device__ __forceinline__ void load_twiddles(float2* s_tw, c
 // spread (mesh_kernels.cuh): it is converted to float and the mean density is removed (DC removal, see mesh.cu) inside
 // this sweep.
 // ---------------------------------------------------------------------------------------------------
+// Peer-memory output of a sweep (multi-GPU, NVLink): the all-to-all transposes of the slab decomposition are not a
+// separate collective -- the x forward pass stores every kx pencil straight into the owning rank's pencil buffer, and the
+// inverse y pass stores every plane straight into the owning rank's receive buffer (P2P stores over NVLink, overlapped
+// with the transform of the other tiles).  n == 0: single buffer (unsharded, or staged for a library all-to-all).
+constexpr int kMaxPeers = 8;
+struct PeerOut {
+    float2* ptr[kMaxPeers];   // ptr[r] = destination buffer in rank r's memory
+    unsigned n;               // number of ranks (0 = not used)
+    unsigned rank;            // this rank
+};
+
 struct DensityIn {
     const int2* mesh;       // integer density of the local planes, row-major [z][y][x] (the caller clears it afterwards)
     const float* d_fx;      // device: {scale, 1/scale} of the fixed-point density
@@ -101,7 +112,7 @@ MHD float2 density_to_float(int2 v, float inv_scale) { return make_float2((float
 template <int LC>
 __global__ void __launch_bounds__(kLines * LC / kE)
 fft_x_fwd_kernel(DensityIn in, const float2* __restrict__ g_tw /* length 2*LC */, float2* out,
-                 unsigned lg_part /* log2 of the kx pencil width */, unsigned rows_total) {
+                 unsigned lg_part /* log2 of the kx pencil width */, unsigned rows_total, const __grid_constant__ PeerOut peers) {
     // lg_part = log2(LC): out is the plain [row][kx] buffer.  Sharded: out = send buffer laid out [part][row][kx in part],
     // i.e. already packed for the slab -> pencil all-to-all.
     extern __shared__ float2 smem[];
@@ -163,6 +174,15 @@ fft_x_fwd_kernel(DensityIn in, const float2* __restrict__ g_tw /* length 2*LC */
     }
     __syncthreads();
     const unsigned part_len = 1u << lg_part;
+    if (peers.n) {
+        // rank (l >> lg_part) owns this kx range; in its pencil [z global][y][kx] our rows start at rank * rows_total
+        for (int idx = threadIdx.x; idx < kLines * LC; idx += nthr) {
+            const int ww = idx / LC, l = idx % LC;
+            const size_t dst = ((size_t)peers.rank * rows_total + (row0 + ww)) * part_len + (l & (part_len - 1));
+            peers.ptr[l >> lg_part][dst] = tile[LayoutRow::addr(ww, l, LC)];
+        }
+        return;
+    }
     for (int idx = threadIdx.x; idx < kLines * LC; idx += nthr) {
         const int ww = idx / LC, l = idx % LC;
         const size_t dst = ((size_t)(l >> lg_part) * rows_total + (row0 + ww)) * part_len + (l & (part_len - 1));
@@ -210,7 +230,8 @@ fft_x_inv_kernel(float2* buf, const float2* __restrict__ g_tw, const float2* in,
 // ---------------------------------------------------------------------------------------------------
 template <int L, int SIGN>
 __global__ void __launch_bounds__(kLines * L / kE)
-fft_y_kernel(float2* __restrict__ buf, const float2* __restrict__ g_tw, unsigned nxh) {
+fft_y_kernel(float2* __restrict__ buf, const float2* __restrict__ g_tw, unsigned nxh, const __grid_constant__ PeerOut peers,
+             unsigned lg_planes /* peers.n != 0: log2 of the planes per rank */) {
     extern __shared__ float2 smem[];
     float2* tile = smem;
     float2* s_tw = smem + LayoutCol::size(L);
@@ -224,6 +245,17 @@ fft_y_kernel(float2* __restrict__ buf, const float2* __restrict__ g_tw, unsigned
     __syncthreads();
     const int w = threadIdx.x & (kLines - 1), t = threadIdx.x / kLines;
     line_fft<L, SIGN, L, LayoutCol>(tile, w, t, s_tw);
+    if (peers.n) {
+        // plane z = blockIdx.y of the pencil belongs to rank z >> lg_planes; its receive buffer is laid out
+        // [source rank][local plane][y][kx in the source's pencil] (what the inverse x pass unpacks)
+        const unsigned z = blockIdx.y, dest = z >> lg_planes, zl = z & ((1u << lg_planes) - 1);
+        float2* out = peers.ptr[dest] + (((size_t)peers.rank << lg_planes) + zl) * L * nxh + (size_t)blockIdx.x * kLines;
+        for (int idx = threadIdx.x; idx < kLines * L; idx += nthr) {
+            const int ww = idx & (kLines - 1), l = idx / kLines;
+            out[(size_t)l * nxh + ww] = tile[idx];
+        }
+        return;
+    }
     for (int idx = threadIdx.x; idx < kLines * L; idx += nthr) {
         const int ww = idx & (kLines - 1), l = idx / kLines;
         buf[base + (size_t)l * nxh + ww] = tile[idx];

@@ -438,6 +438,7 @@ __global__ void mesh_fx_scale_kernel(const unsigned* __restrict__ max_count, flo
     const float s = fx_scale_for(amax, amax * (float)*max_count);
     d_fx[0] = s;
     d_fx[1] = 1.0f / s;
+    d_fx[4] = 1.0f / s;          // 16-byte aligned copy: trailer of the halo messages (peer-memory mode)
 }
 
 // ---- exclusive scan of count[0..n) -> start[0..n].  Three launches: per-block sums, scan of the block sums (single

@@ -1,0 +1,100 @@
+// mesh_p2p.cuh -- peer-memory (NVLink) plumbing of the z-slab sharded mesh path: no NCCL call inside a step.
+//
+// Every rank owns one "arena" allocation that its peers map through CUDA IPC.  A step uses it as follows
+// (reference for the decomposition: HOOMD domain decomposition + CommunicatorGrid + dfft, OrderParameterMesh.cc:263-315,
+// 659-746; the reference moves the same data with MPI messages and three host-synchronous MPI_Allreduce calls):
+//   * halo planes of the fixed-point density, of Re IFFT(G), and the per-rank partial sums are PUSHED into the
+//     neighbours' / all peers' arenas by a small copy kernel (plain P2P stores);
+//   * the two transposes of the distributed FFT are fused into the FFT sweeps themselves (mesh_fft_kernels.cuh, PeerOut);
+//   * ranks synchronise with a flag barrier in peer memory (one 32-thread kernel), which also performs the tiny
+//     all-reduces (sum of the P partial results, in rank order: deterministic and identical on every rank).
+#pragma once
+#include "common.cuh"
+#include "mesh_fft_kernels.cuh"
+
+namespace metad {
+namespace p2p {
+
+constexpr int kMaxPeers = fft::kMaxPeers;
+
+// layout of an arena (all offsets in bytes, 256-byte aligned)
+struct ArenaLayout {
+    size_t pencil, recv, ghost_rho, ghost_inv, sums, cv, flags, total;
+};
+inline ArenaLayout arena_layout(size_t m_local /* local mesh cells */, size_t plane) {
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    ArenaLayout a;
+    size_t o = 0;
+    a.pencil = o; o = up(o + m_local * sizeof(float));                 // [nz][ny][kxl] complex
+    a.recv = o; o = up(o + m_local * sizeof(float));                   // [src rank][local plane][y][kxl] complex
+    a.ghost_rho = o; o = up(o + 2 * (plane + 4) * sizeof(int));        // two halo messages of the fixed-point density
+    a.ghost_inv = o; o = up(o + 2 * plane * sizeof(float));            // planes z0-1 and z0+nz of Re IFFT(G)
+    a.sums = o; o = up(o + kMaxPeers * 4 * sizeof(double));            // per-rank {sum a^2, sum a, outside, -}
+    a.cv = o; o = up(o + kMaxPeers * sizeof(double));                  // per-rank CV partials
+    a.flags = o; o = up(o + kMaxPeers * sizeof(unsigned));             // barrier flags, one per peer
+    a.total = o;
+    return a;
+}
+
+struct PeerTable {
+    char* arena[kMaxPeers];
+    unsigned n, rank;
+};
+
+// ---- copy kernel: up to 4 segments of 16-byte units, destination in any rank's memory ------------------
+struct PushJob {
+    int4* dst[4];
+    const int4* src[4];
+    unsigned n16[4];      // 16-byte units per segment (0 = unused)
+};
+__global__ void __launch_bounds__(256) push_kernel(PushJob job) {
+    const unsigned stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+        for (unsigned i = t0; i < job.n16[s]; i += stride) job.dst[s][i] = job.src[s][i];
+}
+// broadcast of a few doubles into slot [rank] of every peer's table
+__global__ void push_scalars_kernel(PeerTable pt, size_t table_offset, unsigned per_rank, const double* __restrict__ src, unsigned n) {
+    const unsigned r = threadIdx.x / 8, k = threadIdx.x % 8;
+    if (r < pt.n && k < n) reinterpret_cast<double*>(pt.arena[r] + table_offset)[pt.rank * per_rank + k] = src[k];
+}
+
+// ---- flag barrier + rank-ordered reduction ----------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// All ranks launch this kernel with the same `epoch` (a counter that only grows).  Lane r publishes the epoch in rank
+// r's flag slot of THIS rank and waits until rank r has published it here.  Everything the peers stored before their
+// barrier launch (earlier kernels of their stream) is visible afterwards.  Then table[0..n_ranks) rows of `width` doubles
+// are summed in rank order into out[0..width) (skipped if out == nullptr).  wait == 0: reduction only (single-process
+// emulation of the ranks, where launches are already ordered).
+// status[0] is set to 1 if a peer did not arrive within ~4 s (a crashed rank must not hang the GPU).
+__global__ void barrier_reduce_kernel(PeerTable pt, size_t flags_offset, unsigned epoch, int wait, const double* __restrict__ table,
+                                      unsigned per_rank, unsigned width, double* __restrict__ out, unsigned* __restrict__ status) {
+    const unsigned lane = threadIdx.x;
+    if (wait && lane < pt.n) {
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<unsigned*>(pt.arena[lane] + flags_offset) + pt.rank, epoch);
+        const unsigned* mine = reinterpret_cast<const unsigned*>(pt.arena[pt.rank] + flags_offset) + lane;
+        const long long t0 = clock64();
+        // epochs are compared as signed distances so that the counter may wrap
+        while ((int)(ld_acquire_sys(mine) - epoch) < 0) {
+            if (clock64() - t0 > 8000000000LL) { atomicExch(status, 1u); break; }
+            __nanosleep(64);
+        }
+    }
+    __syncwarp();
+    if (out && lane < width) {
+        double s = 0.0;
+        for (unsigned r = 0; r < pt.n; ++r) s += __ldcv(table + r * per_rank + lane);
+        out[lane] = s;
+    }
+}
+
+}  // namespace p2p
+}  // namespace metad

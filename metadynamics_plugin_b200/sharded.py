@@ -7,6 +7,9 @@ MeshSlab          z-slab decomposition of the particle mesh (reference: HOOMD do
                   two all-to-all transposes (slab <-> kx pencil) and two tiny all-reduces per step.
 The bias grid is replicated: every rank applies the identical metad_grid_step after the CV all-reduce.
 
+MeshSlabP2P       the same decomposition over peer memory (NVLink, CUDA IPC): no NCCL call inside a step -- the transposes
+                  are fused into the FFT sweeps, halos / partial sums are P2P stores, ranks meet at flag barriers.
+                  torch.distributed is only used once, to all-gather the 64-byte IPC handles.
 The communication pattern is written against a small `Comm` interface so that the same driver code runs
   * over NCCL (TorchComm, one process per GPU),
   * over gloo on CPU tensors with a numpy stand-in for the local compute (tests/test_distributed_cpu.py), and
@@ -230,3 +233,61 @@ def mesh_slab_step_local(ranks, comm, postypes, n_global, box, bias):
                             [r.inv_ghost[0] for r in ranks], [r.inv_ghost[1] for r in ranks])
     forces = [r.stage_forces(pt, n_global, box, bias) for r, pt in zip(ranks, postypes)]
     return [r.cv for r in ranks], forces
+
+
+# ---------------------------------------------------------------------------------------------------- mesh over peer memory
+class MeshSlabP2P:
+    """One rank of the sharded mesh CV over peer memory (metad_mesh_slab_p2p_*)."""
+
+    def __init__(self, comm, nx, ny, nz, mode):
+        self.comm = comm
+        self.r = MeshSlabRank(nx, ny, nz, comm.size, comm.rank, mode)
+        handle = (C.c_ubyte * 64)()
+        nbytes = C.c_ulonglong(0)
+        check(lib.metad_mesh_slab_p2p_arena(self.r.h, handle, C.byref(nbytes)))
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device="cuda")
+        allh = torch.empty(comm.size * 64, dtype=torch.uint8, device="cuda")
+        comm.dist.all_gather_into_tensor(allh, mine, group=comm.group)
+        buf = (C.c_ubyte * (64 * comm.size))(*allh.cpu().tolist())
+        check(lib.metad_mesh_slab_p2p_connect(self.r.h, buf))
+        self.arena_bytes = int(nbytes.value)
+        comm.dist.barrier(group=comm.group)          # every rank has mapped its peers before the first step
+
+    def compute_cv(self, postype_local, n_global, box):
+        r = self.r
+        r._n = postype_local.shape[0]
+        check(lib.metad_mesh_slab_p2p_cv(r.h, _ptr(postype_local), r._n, int(n_global), C.byref(box), _ptr(r.cv), -1, _stream()))
+        return r.cv
+
+    def forces(self, postype_local, n_global, box, bias, out=None):
+        if out is None:
+            out = torch.empty_like(postype_local)
+        check(lib.metad_mesh_slab_p2p_forces(self.r.h, _ptr(postype_local), _ptr(out), postype_local.shape[0], int(n_global),
+                                             C.byref(box), _ptr(bias), _stream()))
+        return out
+
+    def status(self):
+        out = np.zeros(2, dtype=np.uint32)
+        check(lib.metad_mesh_get(self.r.h, 6, out.ctypes.data_as(C.c_void_p)))
+        return dict(barrier_timeout=int(out[0]), outside_slab=int(out[1]))
+
+
+def mesh_slab_p2p_step_local(ranks, postypes, n_global, box, bias):
+    """All ranks in one process on one GPU: stage k for every rank, then stage k+1 (the launch order replaces the flag
+    barriers).  ranks: MeshSlabRank objects already connected with connect_local()."""
+    for stage in range(5):
+        for r, pt in zip(ranks, postypes):
+            r._n = pt.shape[0]
+            check(lib.metad_mesh_slab_p2p_cv(r.h, _ptr(pt), pt.shape[0], int(n_global), C.byref(box), _ptr(r.cv), stage, _stream()))
+    forces = []
+    for r, pt in zip(ranks, postypes):
+        out = torch.empty_like(pt)
+        check(lib.metad_mesh_slab_p2p_forces(r.h, _ptr(pt), _ptr(out), pt.shape[0], int(n_global), C.byref(box), _ptr(bias), _stream()))
+        forces.append(out)
+    return [r.cv for r in ranks], forces
+
+
+def connect_local(ranks):
+    arr = (C.c_void_p * len(ranks))(*[r.h for r in ranks])
+    for r in ranks:
+        check(lib.metad_mesh_slab_p2p_connect_local(r.h, arr))

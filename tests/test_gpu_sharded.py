@@ -80,6 +80,63 @@ def test_mesh_slab_matches_single_plan_and_oracle(gpu, oracle, N, dims, L, P, mo
     assert np.abs(rho - o.mesh).max() < 2e-6 * max(1.0, np.abs(o.mesh).max())
 
 
+@pytest.mark.parametrize("N,dims,L,P,modes", [
+    (20000, (64, 32, 32), (20.0, 11.0, 13.0), 2, (1.0,)),
+    (60000, (128, 32, 64), (40.0, 10.0, 20.0), 4, (1.0, -1.0)),
+    (200000, (256, 64, 64), (64.0, 16.0, 16.0), 8, (1.0,)),
+])
+def test_mesh_slab_peer_memory_path(gpu, oracle, N, dims, L, P, modes):
+    """The peer-memory (P2P) slab path, all ranks emulated in one process: transposes fused into the FFT sweeps, pushed
+    halos, rank-ordered reductions.  Must agree with the single plan (bitwise for the density when the scales agree) and
+    with the staged path that leaves the collectives to the caller."""
+    import torch
+    ops, sharded = gpu
+    nx, ny, nz = dims
+    rng = np.random.default_rng(N + 3 * P)
+    Lf = np.asarray(L, float)
+    pos = ((rng.random((N, 3)) - 0.5) * Lf).astype(np.float32)
+    pos[0] = [0.0, 0.0, np.float32(Lf[2]) / 2]
+    types = rng.integers(0, len(modes), N).astype(np.int32)
+    owner = sharded.slab_of(pos[:, 2], Lf[2], nz, P)
+    box = ops.Box.make(Lf)
+    idx = [np.nonzero(owner == r)[0] for r in range(P)]
+    pts = [ops.make_postype(pos[i], types[i]) for i in idx]
+    bias = torch.tensor([0.9], dtype=torch.float64, device="cuda")
+    ranks = [sharded.MeshSlabRank(nx, ny, nz, P, r, modes) for r in range(P)]
+    for r in ranks:
+        r.set(1, 1)
+    sharded.connect_local(ranks)
+    for _ in range(2):                                            # twice: buffers and flags are reused across steps
+        cvs, forces = sharded.mesh_slab_p2p_step_local(ranks, pts, N, box, bias)
+    cv = cvs[0].cpu().item()
+    assert all(c.cpu().item() == cv for c in cvs)
+    f = np.zeros((N, 4), np.float32)
+    for i, fr in zip(idx, forces):
+        f[i] = fr.cpu().numpy()
+    # staged path (caller-side collectives, emulated)
+    ranks2 = [sharded.MeshSlabRank(nx, ny, nz, P, r, modes) for r in range(P)]
+    cvs2, forces2 = sharded.mesh_slab_step_local(ranks2, sharded.LocalComm(P), pts, N, box, bias)
+    assert cv == pytest.approx(cvs2[0].cpu().item(), rel=1e-12)
+    f2 = np.zeros((N, 4), np.float32)
+    for i, fr in zip(idx, forces2):
+        f2[i] = fr.cpu().numpy()
+    assert np.abs(f - f2).max() <= 1e-6 * np.abs(f2).max()
+    # single plan and oracle
+    single = ops.Mesh(nx, ny, nz, modes)
+    single.set(1, 1)
+    d_all = ops.make_postype(pos, types)
+    cv1 = single.compute_cv(d_all, N, box).cpu().item()
+    assert cv == pytest.approx(cv1, rel=2e-7)
+    rho = np.concatenate([r.local_mesh(1) for r in ranks], axis=0)
+    if len({r.stats()["fx_scale"] for r in ranks} | {single.stats()["fx_scale"]}) == 1:
+        assert np.array_equal(rho, single.rho())
+    h_pt = oracle.make_postype(pos, types)
+    o = oracle.Mesh(nx, ny, nz, modes, Lf, N, "f64", literal_copysignf=False)
+    assert cv == pytest.approx(o.current_value(h_pt), rel=1e-6)
+    fo = o.forces(h_pt, 0.9)
+    assert np.abs(f - fo).max() < 1e-5 * np.abs(fo).max()
+
+
 def test_mesh_slab_counts_misplaced_particles(gpu):
     import torch
     ops, sharded = gpu
