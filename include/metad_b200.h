@@ -163,7 +163,10 @@ int metad_mesh_slab_p2p_forces(metad_mesh* p, const float* d_postype, float* d_f
 int metad_mesh_get(metad_mesh* p, int which, void* h_out);
 /* knobs: key 0 = rebuild period of the tile order in calls (default 32; value 0 = rebuild at the next call)
  *        key 1 = keep a copy of rho for metad_mesh_get(1)      key 2 = record per-stage CUDA events (profiling)
- *        key 3 = record the cell index of every particle for metad_mesh_get(0)                                         */
+ *        key 3 = record the cell index of every particle for metad_mesh_get(0)
+ *        key 4 = CUDA-graph replay: everything metad_mesh_cv / metad_mesh_slab_p2p_cv enqueue after the tile-order
+ *                decision is captured once per argument signature (pointers, N, box, stream) and replayed with one launch
+ *                (metad_mesh_get(p, 7, unsigned long long*) = replays so far)                                           */
 int metad_mesh_set(metad_mesh* p, int key, long value);
 
 /* ------------------------------------------------------------------------------------------------

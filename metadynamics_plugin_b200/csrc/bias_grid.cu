@@ -173,12 +173,43 @@ grid_step_kernel(GridParams P, GridArrays A, const double* __restrict__ cv_in, d
         __syncthreads();
     }
 
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < P.d; ++i) bias_out[i] = grid_derivative(P, A.grid, i, cur, &sh_oob);
-        A.scalars[0] = grid_interpolate(P, A.grid, cur, &sh_oob);
-        A.scalars[1] = grid_interpolate(P, A.weight, cur, &sh_oob);
-        if (deposit) A.scalars[2] += 1.0;
-        A.scalars[3] += sh_oob;
+    // The 2d + 2 interpolations of the hand-off (two samples per finite difference, V(s), weight(s)) are independent:
+    // one lane each, so the dependent-load latency of this one-block kernel is paid once, not 2d + 2 times (it sits on
+    // the critical path of every step).  Arithmetic per interpolation is unchanged (grid_derivative above is the
+    // serial statement of the same rule).
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x, d = P.d;
+        double y = 0.0, oob = 0.0;
+        if (lane < 2 * d) {
+            const int cv = lane >> 1, side = lane & 1;          // side 0: lower sample, 1: upper sample
+            const double delta = grid_delta_of(P, cv);
+            double v[kMaxCV];
+            for (int i = 0; i < d; ++i) v[i] = cur[i];
+            if (cur[cv] - delta < P.cv_min[cv]) { if (side) v[cv] += delta; }              // forward: (V(s+d) - V(s))/d
+            else if (cur[cv] + delta > P.cv_max[cv]) { if (!side) v[cv] -= delta; }        // backward: (V(s) - V(s-d))/d
+            else v[cv] += side ? delta : -delta;                                            // central
+            y = grid_interpolate(P, A.grid, v, &oob);
+        } else if (lane == 2 * d) {
+            y = grid_interpolate(P, A.grid, cur, &oob);
+        } else if (lane == 2 * d + 1) {
+            y = grid_interpolate(P, A.weight, cur, &oob);
+        }
+        const double y_up = __shfl_down_sync(0xffffffffu, y, 1);
+        double oob_sum = oob;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) oob_sum += __shfl_xor_sync(0xffffffffu, oob_sum, o);
+        if (lane < 2 * d && !(lane & 1)) {
+            const int cv = lane >> 1;
+            const double delta = grid_delta_of(P, cv);
+            const bool one_sided = (cur[cv] - delta < P.cv_min[cv]) || (cur[cv] + delta > P.cv_max[cv]);
+            bias_out[cv] = (y_up - y) / (one_sided ? delta : 2.0 * delta);
+        }
+        if (lane == 2 * d) A.scalars[0] = y;
+        if (lane == 2 * d + 1) A.scalars[1] = y;
+        if (lane == 0) {
+            if (deposit) A.scalars[2] += 1.0;
+            A.scalars[3] += sh_oob + oob_sum;
+        }
     }
 }
 

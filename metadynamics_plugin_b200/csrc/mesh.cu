@@ -31,6 +31,7 @@
 #include "mesh_p2p.cuh"
 
 #include <cmath>
+#include <map>
 #include <vector>
 
 using namespace metad;
@@ -80,7 +81,16 @@ struct metad_mesh {
     p2p::PeerTable peers = {};
     bool peers_mapped[p2p::kMaxPeers] = {};     // opened with cudaIpcOpenMemHandle (to be closed)
     bool p2p_ready = false;
-    unsigned epoch = 0;
+    unsigned* d_epoch = nullptr;                // barrier epoch (device-side counter: launches can be replayed from a graph)
+    // CUDA-graph replay of the per-call kernel sequence (metad_mesh_set key 4): everything a call enqueues after the
+    // (eager) tile-order decision is captured once per argument signature and replayed with one launch
+    bool graph_mode = false;
+    struct GraphKey { const void* postype; unsigned N, N_global; double L[3]; const void* d_cv; cudaStream_t stream; int kind; bool keep_rho, keep_cells; };
+    GraphKey gkey = {};
+    int gwarm = 0;
+    cudaGraphExec_t gexec = nullptr;
+    cudaStream_t capture_stream = nullptr;
+    unsigned long long n_graph_launches = 0;
     double* d_sums_global = nullptr;            // [4] sums over all ranks
     double* d_cv_partial = nullptr;
     unsigned* d_p2p_status = nullptr;
@@ -111,8 +121,15 @@ int upload_twiddles(float2** dst, unsigned n) {
     return METAD_OK;
 }
 
+// opt-in dynamic shared memory, once per kernel (the attribute call must not sit inside a stream capture)
 template <class K> int set_smem(K kernel, size_t bytes) {
-    if (bytes > 48 * 1024) METAD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    static std::map<const void*, size_t> configured;
+    if (bytes <= 48 * 1024) return METAD_OK;
+    size_t& have = configured[(const void*)kernel];
+    if (have < bytes) {
+        METAD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        have = bytes;
+    }
     return METAD_OK;
 }
 
@@ -141,8 +158,10 @@ template <int LC> int run_x(metad_mesh* p, bool inverse, float2* io, const doubl
         if (peer_out) po = *peer_out;
         fft_x_fwd_kernel<LC><<<rows / kLines, kLines * LC / kE, smem, st>>>(in, p->d_twx, io ? io : buf, lg_part, rows, po);
         METAD_LAUNCH_CHECK();
-        // the accumulator is empty again for the next spread (a plain memset runs at the full write bandwidth)
-        METAD_CUDA(cudaMemsetAsync(p->d_mesh_i, 0, sizeof(int) * p->M(), st));
+        // the accumulator is empty again for the next spread (a plain memset runs at the full write bandwidth); in
+        // peer-memory mode the two ghost planes (already pushed to the neighbours) are cleared by the same memset
+        if (peer_out) METAD_CUDA(cudaMemsetAsync(p->d_mesh_alloc, 0, sizeof(int) * (p->M() + 2 * (size_t)p->g.nx * p->g.ny), st));
+        else METAD_CUDA(cudaMemsetAsync(p->d_mesh_i, 0, sizeof(int) * p->M(), st));
     } else {
         int rc = set_smem(fft_x_inv_kernel<LC>, smem); if (rc) return rc;
         fft_x_inv_kernel<LC><<<rows / kLines, kLines * LC / kE, smem, st>>>(buf, p->d_twx, io ? io : buf, lg_part, rows);
@@ -305,15 +324,11 @@ template <int LGT> size_t tile_smem_bytes() {
 template <int LGT> size_t gather_smem_bytes() { return tile_smem_bytes<LGT>() + 2 * kGatherThreads * (sizeof(float4) + sizeof(uint2)); }
 
 // tile order of this call (rebuilt if needed) + spread into the integer mesh; sums -> p->d_sums
-int order_and_spread(metad_mesh* p, const float* d_postype, unsigned N, cudaStream_t stream) {
-    const Geom& g = p->g;
+// host-side decision + (rare) rebuild of the tile order: never part of a captured graph
+int prepare_order(metad_mesh* p, const float* d_postype, unsigned N, cudaStream_t stream) {
     int rc = ensure_capacity(p, N); if (rc) return rc;
     rc = mark(p, 0, stream); if (rc) return rc;
-    if (N == 0) {
-        METAD_CUDA(cudaMemsetAsync(p->d_sums, 0, 4 * sizeof(double), stream));
-        rc = mark(p, 1, stream); if (rc) return rc;
-        return METAD_OK;
-    }
+    if (N == 0) return METAD_OK;
     // drifted particles / range warnings reported by an earlier spread (asynchronous copy: may lag by a call)
     const bool drift = p->h_counters[1] > N / 256u || p->h_counters[3] > 0;
     if (!p->order_valid || p->order_N != N || p->calls_since_rebuild >= p->period || drift) {
@@ -321,7 +336,17 @@ int order_and_spread(metad_mesh* p, const float* d_postype, unsigned N, cudaStre
         p->h_counters[1] = p->h_counters[3] = 0;
     }
     ++p->calls_since_rebuild;
-    rc = mark(p, 1, stream); if (rc) return rc;
+    return METAD_OK;
+}
+
+// spread into the integer mesh through the current tile order; sums -> p->d_sums
+int enqueue_spread(metad_mesh* p, const float* d_postype, unsigned N, cudaStream_t stream) {
+    const Geom& g = p->g;
+    int rc = mark(p, 1, stream); if (rc) return rc;
+    if (N == 0) {
+        METAD_CUDA(cudaMemsetAsync(p->d_sums, 0, 4 * sizeof(double), stream));
+        return METAD_OK;
+    }
     METAD_CUDA(cudaMemsetAsync(p->d_counters + 1, 0, 3 * sizeof(unsigned), stream));
     SpreadOut out;
     out.mesh = p->d_mesh_i;
@@ -342,6 +367,58 @@ int order_and_spread(metad_mesh* p, const float* d_postype, unsigned N, cudaStre
     METAD_LAUNCH_CHECK();
     METAD_CUDA(cudaMemcpyAsync(p->h_counters, p->d_counters, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
     return METAD_OK;
+}
+
+int order_and_spread(metad_mesh* p, const float* d_postype, unsigned N, cudaStream_t stream) {
+    int rc = prepare_order(p, d_postype, N, stream); if (rc) return rc;
+    return enqueue_spread(p, d_postype, N, stream);
+}
+
+// Run `body` (which only enqueues work on `stream`) either directly or -- in graph mode -- through a CUDA graph that is
+// captured the second time the same argument signature is seen and replayed afterwards.
+template <class Body>
+int run_captured(metad_mesh* p, const metad_mesh::GraphKey& key, cudaStream_t stream, Body body) {
+    if (!p->graph_mode || p->profile) return body(stream);
+    const bool same = memcmp(&key, &p->gkey, sizeof key) == 0;
+    if (same && p->gexec) {
+        METAD_CUDA(cudaGraphLaunch(p->gexec, stream));
+        ++p->n_graph_launches;
+        return METAD_OK;
+    }
+    if (!same) {
+        if (p->gexec) { cudaGraphExecDestroy(p->gexec); p->gexec = nullptr; }
+        p->gkey = key;
+        p->gwarm = 1;
+        return body(stream);            // first call with this signature: eager (lazy allocations, kernel attributes)
+    }
+    // capture on a private stream (the caller's may be the legacy default stream, which cannot be captured); the
+    // instantiated graph is then launched into the caller's stream
+    if (!p->capture_stream) METAD_CUDA(cudaStreamCreateWithFlags(&p->capture_stream, cudaStreamNonBlocking));
+    cudaGraph_t graph = nullptr;
+    METAD_CUDA(cudaStreamBeginCapture(p->capture_stream, cudaStreamCaptureModeRelaxed));
+    const int rc = body(p->capture_stream);
+    const cudaError_t e = cudaStreamEndCapture(p->capture_stream, &graph);
+    if (rc != METAD_OK || e != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        if (rc == METAD_OK) return cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
+        return rc;
+    }
+    const cudaError_t ei = cudaGraphInstantiate(&p->gexec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess) { p->gexec = nullptr; return cuda_fail(ei, "cudaGraphInstantiate", __FILE__, __LINE__); }
+    METAD_CUDA(cudaGraphLaunch(p->gexec, stream));
+    ++p->n_graph_launches;
+    return METAD_OK;
+}
+
+metad_mesh::GraphKey make_key(metad_mesh* p, const void* postype, unsigned N, unsigned N_global, const metad_box* box, const void* d_cv,
+                              cudaStream_t stream, int kind) {
+    metad_mesh::GraphKey k;
+    memset(&k, 0, sizeof k);
+    k.postype = postype; k.N = N; k.N_global = N_global;
+    for (int i = 0; i < 3; ++i) k.L[i] = box->L[i];
+    k.d_cv = d_cv; k.stream = stream; k.kind = kind; k.keep_rho = p->keep_rho; k.keep_cells = p->keep_cells;
+    return k;
 }
 
 int launch_gather(metad_mesh* p, const float* d_postype, const float* d_ghost, float* d_force, unsigned N_global, const metad_box* box,
@@ -441,6 +518,8 @@ int create_common(metad_mesh** out, unsigned nx, unsigned ny, unsigned nzg, unsi
     TRY(cudaMalloc(&p->d_cv_partial, sizeof(double)));
     TRY(cudaMalloc(&p->d_p2p_status, sizeof(unsigned)));
     TRY(cudaMemset(p->d_p2p_status, 0, sizeof(unsigned)));
+    TRY(cudaMalloc(&p->d_epoch, sizeof(unsigned)));
+    TRY(cudaMemset(p->d_epoch, 0, sizeof(unsigned)));
 #undef TRY
     if (rc == METAD_OK) {
         memset(p->h_counters, 0, sizeof(unsigned) * 4);
@@ -474,7 +553,9 @@ extern "C" int metad_mesh_destroy(metad_mesh* p) {
     if (p->h_counters) cudaFreeHost(p->h_counters);
     cudaFree(p->d_rho_keep); cudaFree(p->d_twx); cudaFree(p->d_twy); cudaFree(p->d_twz); cudaFree(p->d_sums);
     cudaFree(p->d_partials); cudaFree(p->d_ticket);
-    cudaFree(p->d_sums_global); cudaFree(p->d_cv_partial); cudaFree(p->d_p2p_status);
+    cudaFree(p->d_sums_global); cudaFree(p->d_cv_partial); cudaFree(p->d_p2p_status); cudaFree(p->d_epoch);
+    if (p->gexec) cudaGraphExecDestroy(p->gexec);
+    if (p->capture_stream) cudaStreamDestroy(p->capture_stream);
     for (unsigned r = 0; r < p2p::kMaxPeers; ++r)
         if (p->peers_mapped[r]) cudaIpcCloseMemHandle(p->peers.arena[r]);
     cudaFree(p->arena);
@@ -491,8 +572,12 @@ extern "C" int metad_mesh_cv(metad_mesh* p, const float* d_postype, unsigned N, 
     METAD_REQUIRE(N_global > 0, "metad_mesh_cv: N_global must be positive");
     int rc = set_box(p, box); if (rc) return rc;
     p->have_cv = false;
-    rc = order_and_spread(p, d_postype, N, stream); if (rc) return rc;
-    rc = fft_pipeline(p, N_global, d_cv, stream); if (rc) return rc;
+    rc = prepare_order(p, d_postype, N, stream); if (rc) return rc;
+    rc = run_captured(p, make_key(p, d_postype, N, N_global, box, d_cv, stream, 0), stream, [&](cudaStream_t st) -> int {
+        int r = enqueue_spread(p, d_postype, N, st); if (r) return r;
+        return fft_pipeline(p, N_global, d_cv, st);
+    });
+    if (rc) return rc;
     p->have_cv = true;
     p->last_N = N;
     return METAD_OK;
@@ -602,9 +687,8 @@ int ensure_arena(metad_mesh* p) {
     return METAD_OK;
 }
 
-int p2p_barrier(metad_mesh* p, int wait, const double* table, unsigned per_rank, unsigned width, double* out, cudaStream_t st) {
-    if (wait) ++p->epoch;
-    p2p::barrier_reduce_kernel<<<1, 32, 0, st>>>(p->peers, p->lay.flags, p->epoch, wait, table, per_rank, width, out, p->d_p2p_status);
+int p2p_barrier(metad_mesh* p, int wait, p2p::Publish pub, p2p::Reduce red, cudaStream_t st) {
+    p2p::barrier_kernel<<<1, 32, 0, st>>>(p->peers, p->lay.flags, p->d_epoch, wait, pub, red, p->d_p2p_status);
     METAD_LAUNCH_CHECK();
     return METAD_OK;
 }
@@ -618,9 +702,7 @@ int p2p_stage(metad_mesh* p, int stage, int wait, const float* d_postype, unsign
     int rc = METAD_OK;
     switch (stage) {
         case 0: {   // local spread; halo planes of the density (+ their scale) to the neighbours, partial sums to everyone
-            rc = set_box(p, box); if (rc) return rc;
-            p->have_cv = false;
-            rc = order_and_spread(p, d_postype, N_local, st); if (rc) return rc;
+            rc = enqueue_spread(p, d_postype, N_local, st); if (rc) return rc;
             int* below = p->d_mesh_alloc;
             int* above = p->d_mesh_alloc + plane * (g.nz + 1);
             const size_t msg = (plane + 4) * sizeof(int);
@@ -635,15 +717,16 @@ int p2p_stage(metad_mesh* p, int stage, int wait, const float* d_postype, unsign
             job.dst[3] = (int4*)(gu + plane * sizeof(int)); job.src[3] = (const int4*)(p->d_fx + 4); job.n16[3] = 1;
             p2p::push_kernel<<<32, 256, 0, st>>>(job);
             METAD_LAUNCH_CHECK();
-            p2p::push_scalars_kernel<<<1, 64, 0, st>>>(p->peers, p->lay.sums, 4, p->d_sums, 3);
-            METAD_LAUNCH_CHECK();
-            METAD_CUDA(cudaMemsetAsync(below, 0, plane * sizeof(int), st));
-            METAD_CUDA(cudaMemsetAsync(above, 0, plane * sizeof(int), st));
-            p->last_N = N_local;
+            if (!wait) {    // emulation: the partial sums must be in place before ANY rank reduces them in stage 1
+                p2p::push_scalars_kernel<<<1, 64, 0, st>>>(p->peers, p->lay.sums, 4, p->d_sums, 3);
+                METAD_LAUNCH_CHECK();
+            }
             return METAD_OK;
         }
         case 1: {   // [barrier: halos and sums have arrived] x forward pass, every kx pencil stored into its owner's memory
-            rc = p2p_barrier(p, wait, (const double*)(mine + p->lay.sums), 4, 3, p->d_sums_global, st); if (rc) return rc;
+            rc = p2p_barrier(p, wait, p2p::Publish{p->d_sums, p->lay.sums, 4, wait ? 3u : 0u},
+                             p2p::Reduce{(const double*)(mine + p->lay.sums), 4, 3, p->d_sums_global}, st);
+            if (rc) return rc;
             if (p->keep_rho && !p->d_rho_keep) METAD_CUDA(cudaMalloc(&p->d_rho_keep, sizeof(float) * p->M()));
             PeerOut po;
             memset(&po, 0, sizeof po);
@@ -653,7 +736,7 @@ int p2p_stage(metad_mesh* p, int stage, int wait, const float* d_postype, unsign
             return rc;
         }
         case 2: {   // [barrier: the pencil is complete] y, fused z, inverse y with every plane stored into its owner's memory
-            rc = p2p_barrier(p, wait, nullptr, 0, 0, nullptr, st); if (rc) return rc;
+            rc = p2p_barrier(p, wait, p2p::Publish{nullptr, 0, 0, 0}, p2p::Reduce{nullptr, 0, 0, nullptr}, st); if (rc) return rc;
             float2* pen = (float2*)(mine + p->lay.pencil);
             METAD_DISPATCH_LEN(g.ny, (run_y<LL>(p, false, pen, p->kxl, p->nzg, st))); if (rc) return rc;
             METAD_DISPATCH_LEN(p->nzg, (run_z<LL>(p, pen, p->kxl, r * p->kxl, p->d_sums_global, N_global, p->d_cv_partial, st))); if (rc) return rc;
@@ -662,12 +745,16 @@ int p2p_stage(metad_mesh* p, int stage, int wait, const float* d_postype, unsign
             po.n = P; po.rank = r;
             for (unsigned q = 0; q < P; ++q) po.ptr[q] = (float2*)(p->peers.arena[q] + p->lay.recv);
             METAD_DISPATCH_LEN(g.ny, (run_y<LL>(p, true, pen, p->kxl, p->nzg, st, &po))); if (rc) return rc;
-            p2p::push_scalars_kernel<<<1, 64, 0, st>>>(p->peers, p->lay.cv, 1, p->d_cv_partial, 1);
-            METAD_LAUNCH_CHECK();
+            if (!wait) {    // emulation: see stage 0
+                p2p::push_scalars_kernel<<<1, 64, 0, st>>>(p->peers, p->lay.cv, 1, p->d_cv_partial, 1);
+                METAD_LAUNCH_CHECK();
+            }
             return METAD_OK;
         }
         case 3: {   // [barrier: planes and CV partials have arrived] CV, inverse x pass, halo planes of Re IFFT(G) to the neighbours
-            rc = p2p_barrier(p, wait, (const double*)(mine + p->lay.cv), 1, 1, d_cv, st); if (rc) return rc;
+            rc = p2p_barrier(p, wait, p2p::Publish{p->d_cv_partial, p->lay.cv, 1, wait ? 1u : 0u},
+                             p2p::Reduce{(const double*)(mine + p->lay.cv), 1, 1, d_cv}, st);
+            if (rc) return rc;
             METAD_DISPATCH_LEN(g.nx / 2, (run_x<LL>(p, true, (float2*)(mine + p->lay.recv), nullptr, nullptr, st))); if (rc) return rc;
             p2p::PushJob job;
             memset(&job, 0, sizeof job);
@@ -681,8 +768,7 @@ int p2p_stage(metad_mesh* p, int stage, int wait, const float* d_postype, unsign
             return METAD_OK;
         }
         case 4:     // [barrier: the halo planes of Re IFFT(G) have arrived]
-            rc = p2p_barrier(p, wait, nullptr, 0, 0, nullptr, st); if (rc) return rc;
-            p->have_cv = true;
+            rc = p2p_barrier(p, wait, p2p::Publish{nullptr, 0, 0, 0}, p2p::Reduce{nullptr, 0, 0, nullptr}, st); if (rc) return rc;
             return METAD_OK;
         default:
             set_error("metad_mesh_slab_p2p_cv: stage must be -1 (whole step) or 0..4");
@@ -739,11 +825,26 @@ extern "C" int metad_mesh_slab_p2p_cv(metad_mesh* p, const float* d_postype, uns
     METAD_REQUIRE(p->g.slab && p->p2p_ready, "metad_mesh_slab_p2p_cv: connect the peers first (metad_mesh_slab_p2p_connect)");
     METAD_REQUIRE(N_local == 0 || d_postype, "metad_mesh_slab_p2p_cv: null positions");
     METAD_REQUIRE(N_global > 0, "metad_mesh_slab_p2p_cv: N_global must be positive");
-    if (stage >= 0) return p2p_stage(p, stage, 0, d_postype, N_local, N_global, box, d_cv, stream);
-    for (int s = 0; s <= 4; ++s) {
-        const int rc = p2p_stage(p, s, 1, d_postype, N_local, N_global, box, d_cv, stream);
-        if (rc) return rc;
+    if (stage <= 0) {       // host side of a step: geometry, tile-order decision (never captured)
+        int rc = set_box(p, box); if (rc) return rc;
+        p->have_cv = false;
+        rc = prepare_order(p, d_postype, N_local, stream); if (rc) return rc;
+        p->last_N = N_local;
     }
+    if (stage >= 0) {
+        const int rc = p2p_stage(p, stage, 0, d_postype, N_local, N_global, box, d_cv, stream);
+        if (rc == METAD_OK && stage == 4) p->have_cv = true;
+        return rc;
+    }
+    const int rc = run_captured(p, make_key(p, d_postype, N_local, N_global, box, d_cv, stream, 1), stream, [&](cudaStream_t st) -> int {
+        for (int s = 0; s <= 4; ++s) {
+            const int r = p2p_stage(p, s, 1, d_postype, N_local, N_global, box, d_cv, st);
+            if (r) return r;
+        }
+        return METAD_OK;
+    });
+    if (rc) return rc;
+    p->have_cv = true;
     return METAD_OK;
 }
 
@@ -808,6 +909,7 @@ extern "C" int metad_mesh_get(metad_mesh* p, int which, void* h_out) {
             out[0] = (double)p->n_rebuilds; out[1] = c[1]; out[2] = c[2]; out[3] = c[3]; out[4] = fx[0]; out[5] = p->calls_since_rebuild;
             return METAD_OK;
         }
+        case 7: *(unsigned long long*)h_out = p->n_graph_launches; return METAD_OK;
         case 6: {   // peer-memory mode: unsigned[2] = {a barrier timed out (a peer never arrived), sum over ranks of particles outside their slab}
             unsigned* out = (unsigned*)h_out;
             double sg[4];
@@ -832,6 +934,7 @@ extern "C" int metad_mesh_set(metad_mesh* p, int key, long value) {
         case 1: p->keep_rho = value != 0; return METAD_OK;
         case 2: p->profile = value != 0; return METAD_OK;
         case 3: p->keep_cells = value != 0; return METAD_OK;
+        case 4: p->graph_mode = value != 0; return METAD_OK;
         default: set_error("metad_mesh_set: unknown key"); return METAD_ERR_INVALID;
     }
 }

@@ -68,31 +68,45 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// All ranks launch this kernel with the same `epoch` (a counter that only grows).  Lane r publishes the epoch in rank
-// r's flag slot of THIS rank and waits until rank r has published it here.  Everything the peers stored before their
-// barrier launch (earlier kernels of their stream) is visible afterwards.  Then table[0..n_ranks) rows of `width` doubles
-// are summed in rank order into out[0..width) (skipped if out == nullptr).  wait == 0: reduction only (single-process
-// emulation of the ranks, where launches are already ordered).
-// status[0] is set to 1 if a peer did not arrive within ~4 s (a crashed rank must not hang the GPU).
-__global__ void barrier_reduce_kernel(PeerTable pt, size_t flags_offset, unsigned epoch, int wait, const double* __restrict__ table,
-                                      unsigned per_rank, unsigned width, double* __restrict__ out, unsigned* __restrict__ status) {
+// All ranks launch this kernel the same number of times; the epoch is a device-side counter that every launch advances
+// (so the launch can sit in a CUDA graph).  Steps of one launch:
+//   1. publish: `n_pub` doubles of this rank go into row [rank] of a table in EVERY peer's arena (tiny all-gather);
+//   2. barrier: lane r publishes the new epoch in rank r's flag slot of THIS rank and waits until rank r has published it
+//      here; everything the peers stored before their barrier launch (earlier kernels of their streams, step 1) is visible;
+//   3. reduce: rows [0, n_ranks) x `width` doubles of a table are summed in rank order into out[0..width) -- the tiny
+//      all-reduces of the path, deterministic and identical on every rank.
+// wait == 0: steps 1 and 3 only (single-process emulation of the ranks, where the launch order already orders the data).
+// status[0] is set to 1 if a peer did not arrive within a few seconds (a crashed rank must not hang the GPU).
+struct Publish { const double* src; size_t table_offset; unsigned per_rank, n; };
+struct Reduce { const double* table; unsigned per_rank, width; double* out; };
+__global__ void barrier_kernel(PeerTable pt, size_t flags_offset, unsigned* __restrict__ d_epoch, int wait, Publish pub, Reduce red,
+                               unsigned* __restrict__ status) {
     const unsigned lane = threadIdx.x;
-    if (wait && lane < pt.n) {
-        __threadfence_system();
-        st_release_sys(reinterpret_cast<unsigned*>(pt.arena[lane] + flags_offset) + pt.rank, epoch);
-        const unsigned* mine = reinterpret_cast<const unsigned*>(pt.arena[pt.rank] + flags_offset) + lane;
-        const long long t0 = clock64();
-        // epochs are compared as signed distances so that the counter may wrap
-        while ((int)(ld_acquire_sys(mine) - epoch) < 0) {
-            if (clock64() - t0 > 8000000000LL) { atomicExch(status, 1u); break; }
-            __nanosleep(64);
-        }
+    if (pub.n) {
+        const unsigned r = lane / 4, k = lane % 4;          // up to 8 ranks x 4 values
+        if (r < pt.n && k < pub.n) reinterpret_cast<double*>(pt.arena[r] + pub.table_offset)[pt.rank * pub.per_rank + k] = pub.src[k];
     }
-    __syncwarp();
-    if (out && lane < width) {
+    if (wait) {
+        const unsigned epoch = *d_epoch + 1u;
+        __threadfence_system();
+        __syncwarp();
+        if (lane < pt.n) {
+            st_release_sys(reinterpret_cast<unsigned*>(pt.arena[lane] + flags_offset) + pt.rank, epoch);
+            const unsigned* mine = reinterpret_cast<const unsigned*>(pt.arena[pt.rank] + flags_offset) + lane;
+            const long long t0 = clock64();
+            // epochs are compared as signed distances so that the counter may wrap
+            while ((int)(ld_acquire_sys(mine) - epoch) < 0) {
+                if (clock64() - t0 > 8000000000LL) { atomicExch(status, 1u); break; }
+                __nanosleep(32);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) *d_epoch = epoch;
+    }
+    if (red.out && lane < red.width) {
         double s = 0.0;
-        for (unsigned r = 0; r < pt.n; ++r) s += __ldcv(table + r * per_rank + lane);
-        out[lane] = s;
+        for (unsigned r = 0; r < pt.n; ++r) s += __ldcv(red.table + r * red.per_rank + lane);
+        red.out[lane] = s;
     }
 }
 

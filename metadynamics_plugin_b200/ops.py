@@ -140,6 +140,12 @@ class Mesh:
         check(lib.metad_mesh_get(self.h, 3, out.ctypes.data_as(C.c_void_p)))
         return float(out[0])
 
+    def graph_launches(self):
+        """CUDA-graph replays so far (knob 4)."""
+        out = C.c_ulonglong(0)
+        check(lib.metad_mesh_get(self.h, 7, C.byref(out)))
+        return int(out.value)
+
     def stats(self):
         """Tile-order / fixed-point statistics of the last spread (synchronises)."""
         out = np.empty(6, dtype=np.float64)

@@ -213,6 +213,39 @@ def test_mesh_stale_tile_order(gpu, oracle):
     assert mesh.stats()["rebuilds"] == 4
 
 
+def test_mesh_cuda_graph_replay(gpu):
+    """Knob 4: the kernel sequence of metad_mesh_cv is captured into a CUDA graph and replayed.  Positions change in place
+    between the calls, the tile order is rebuilt on its period (outside the graph): every call must be bitwise equal to a
+    fresh eager plan."""
+    import torch
+    N, dims, L = 50000, (64, 64, 64), 35.0
+    rng = np.random.default_rng(21)
+    pos, types = rand_pt(N, L, 2, 9)
+    modes = [1.0, -0.5]
+    box = gpu.Box.make(L)
+    bias = torch.tensor([1.1], dtype=torch.float64, device="cuda")
+    mesh = gpu.Mesh(*dims, modes)
+    mesh.set(4, 1)
+    mesh.set(0, 3)                                       # rebuild every third call
+    d_pt = to_dev(gpu, pos, types)
+    for step in range(8):
+        pos = pos + (rng.random((N, 3)).astype(np.float32) - 0.5) * np.float32(0.2)
+        pos = (((pos + L / 2) % L) - L / 2).astype(np.float32)
+        pos[pos >= np.float32(L / 2)] = -np.float32(L / 2)
+        d_pt.copy_(to_dev(gpu, pos, types))              # same device buffer, new contents
+        cv = mesh.compute_cv(d_pt, N, box).cpu().item()
+        f = mesh.forces(d_pt, N, box, bias).cpu().numpy()
+        fresh = gpu.Mesh(*dims, modes)
+        cvf = fresh.compute_cv(d_pt, N, box).cpu().item()
+        ff = fresh.forces(d_pt, N, box, bias).cpu().numpy()
+        assert cv == cvf and np.array_equal(f, ff), step
+    assert mesh.graph_launches() >= 6                   # call 0 eager, call 1 captures + replays, then replays
+    assert mesh.stats()["rebuilds"] == 3
+    # a different buffer is a different signature: falls back to eager, then a new graph
+    d2 = d_pt.clone()
+    assert mesh.compute_cv(d2, N, box).cpu().item() == cv
+
+
 @pytest.mark.parametrize("sigma,cv_tol", [(3.0, 1e-6), (0.8, None)])
 def test_mesh_dense_cells_fixed_point_range(gpu, oracle, sigma, cv_tol):
     """Many particles per cell and large mode coefficients: the fixed-point scale adapts (no range warnings).  The 32-bit
