@@ -463,7 +463,7 @@ def run_reference(args):
               "1 thread (reference CPU path is serial per MPI rank); host has %d cores" % (n, args.steps, done_w, os.cpu_count()))
     out = {"impl": "reference", "metric": "cv_bias_force_steps_per_sec", "value": 1.0 / dt, "unit": "steps/s",
            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": n, "warmup": done_w, "ms_per_step": dt * 1e3,
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "ns_per_particle_step": dt * 1e9 / N,
            "config": {"workload": "%s: %s" % (w["name"], describe(w)), "N": N},
            "cpu_baseline": {"value": 1.0 / dt, "unit": "steps/s", "cores": 1, "kind": "port", "sample": sample,
