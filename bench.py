@@ -211,8 +211,11 @@ class LamellarStep:
             self.lam.compute_modes(self.d_pt, self.N_global, self.box, finalize=False)
             self.comm.all_reduce_sum(self.lam.modes)
             cv = self.lam.finalize(self.N_global)
-        self.cvs[0:1].copy_(cv)
-        bias = self.grid.step(self.t, self.cvs)
+        if self.ncv == 1:
+            bias = self.grid.step(self.t, cv)
+        else:
+            self.cvs[0:1].copy_(cv)
+            bias = self.grid.step(self.t, self.cvs)
         self.lam.forces(self.d_pt, self.N_global, self.box, bias[0:1], out=self.d_force)
         self.t += 1
 

@@ -6,9 +6,9 @@
 //
 // Design (HBM-bound, 16 B read per particle for the CV pass, 16 B read + 16 B write for the force pass):
 //   * one coalesced 128-bit streaming load per particle, all n_wave modes evaluated from that one load;
-//   * phases are evaluated in *turns* in fp64 (t = (q_k/2pi).r, t -= rint(t)) and fed to sincospif, so the
-//     range reduction is exact and the result tracks the double-precision CPU build to ~1e-7 although the
-//     transcendental itself is fp32;
+//   * phases are evaluated in *turns* in fp64 (t = (q_k/2pi).r), reduced exactly to [-1/2, 1/2] and fed to an fp32
+//     polynomial sin/cos(pi u) (no conversion- or transcendental-pipe instruction per term), so the result tracks
+//     the double-precision CPU build to ~1e-7 although the transcendental itself is fp32;
 //   * per-thread fp64 accumulators -> warp shuffles -> one partial per block -> the last block to finish
 //     (ticket counter) sums the block partials in block order: deterministic, no second launch, no host sum;
 //   * the CV and the bias factor stay in device memory (double), the force pass reads dV/ds from there.
@@ -26,6 +26,38 @@ template <int NW> struct WaveSet {
     float q[NW][3];     // q_k in rad per unit length (force prefactor)
 };
 
+// ---- phase arithmetic without the conversion / transcendental pipe ------------------------------------------------
+// (measured: with fp64 rint, float<->double conversions of every term and sincospif the kernels ran at 70-76 % of the
+// XU pipe and 2x above their HBM time; profiles/r01i_lamellar_c5_metrics_before.csv)
+// fractional part of a phase given in turns, in [-1/2, 1/2]: rint by the fp64 magic constant 1.5 * 2^52 (two DADDs)
+__device__ __forceinline__ float frac_turns(double t) {
+    const double r = (t + 6755399441055744.0) - 6755399441055744.0;
+    return (float)(t - r);
+}
+// sin(pi u), cos(pi u) for |u| <= 1: quadrant k = rint(2u) by the fp32 magic constant, then Taylor polynomials in
+// v = u - k/2, |v| <= 1/4 (truncation error < 3e-9), all on the FMA pipe
+__device__ __forceinline__ void sincospi_small(float u, float& s, float& c) {
+    const float km = fmaf(2.0f, u, 12582912.0f);
+    const int q = __float_as_int(km) & 3;                 // low bits of the integer k (two's complement: valid for k < 0)
+    const float k = km - 12582912.0f;
+    const float v = fmaf(k, -0.5f, u);
+    const float v2 = v * v;
+    float sp = fmaf(v2, 0.0821458866f, -0.599264529f);
+    sp = fmaf(sp, v2, 2.55016404f);
+    sp = fmaf(sp, v2, -5.16771278f);
+    sp = fmaf(sp, v2, 3.14159265f);
+    sp *= v;
+    float cp = fmaf(v2, -0.0258068913f, 0.235330630f);
+    cp = fmaf(cp, v2, -1.33526277f);
+    cp = fmaf(cp, v2, 4.05871213f);
+    cp = fmaf(cp, v2, -4.93480220f);
+    cp = fmaf(cp, v2, 1.0f);
+    // rotate by k quarter turns: k=1: (c,-s) ... stated as sin/cos of pi(v + k/2)
+    const float s1 = (q & 1) ? cp : sp, c1 = (q & 1) ? sp : cp;
+    s = (q & 2) ? -s1 : s1;
+    c = ((q + 1) & 2) ? -c1 : c1;
+}
+
 template <int NW>
 __global__ void __launch_bounds__(kLamThreads)
 lamellar_modes_kernel(const float4* __restrict__ postype, unsigned N, WaveSet<NW> ws, const float* __restrict__ mode,
@@ -35,21 +67,32 @@ lamellar_modes_kernel(const float4* __restrict__ postype, unsigned N, WaveSet<NW
 #pragma unroll
     for (int k = 0; k < NW; ++k) { accr[k] = 0.0; acci[k] = 0.0; }
 
+    // terms are summed in fp32 over short runs (8 particles: error ~1e-7 of a run) and the runs in fp64
+    float runr[NW], runi[NW];
+#pragma unroll
+    for (int k = 0; k < NW; ++k) { runr[k] = 0.f; runi[k] = 0.f; }
     const unsigned stride = gridDim.x * blockDim.x;
+    unsigned in_run = 0;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
         const float4 p = ld_stream(postype + i);
         const float a = __ldg(mode + __float_as_int(p.w));
         const double x = (double)p.x, y = (double)p.y, z = (double)p.z;
 #pragma unroll
         for (int k = 0; k < NW; ++k) {
-            double t = fma(ws.qt[k][0], x, fma(ws.qt[k][1], y, ws.qt[k][2] * z));
-            t -= rint(t);
+            const double t = fma(ws.qt[k][0], x, fma(ws.qt[k][1], y, ws.qt[k][2] * z));
             float s, c;
-            sincospif((float)(2.0 * t), &s, &c);
-            accr[k] += (double)(a * c);
-            acci[k] += (double)(a * s);
+            sincospi_small(2.0f * frac_turns(t), s, c);
+            runr[k] = fmaf(a, c, runr[k]);
+            runi[k] = fmaf(a, s, runi[k]);
+        }
+        if (++in_run == 8) {
+#pragma unroll
+            for (int k = 0; k < NW; ++k) { accr[k] += (double)runr[k]; acci[k] += (double)runi[k]; runr[k] = 0.f; runi[k] = 0.f; }
+            in_run = 0;
         }
     }
+#pragma unroll
+    for (int k = 0; k < NW; ++k) { accr[k] += (double)runr[k]; acci[k] += (double)runi[k]; }
 
     __shared__ double red[32];
     __shared__ bool is_last;
@@ -100,7 +143,7 @@ __global__ void __launch_bounds__(kLamThreads)
 lamellar_force_kernel(const float4* __restrict__ postype, float4* __restrict__ force, unsigned N, WaveSet<NW> ws,
                       const float* __restrict__ mode, const double* __restrict__ d_bias, double n_global,
                       int accumulate) {
-    const double scale = *d_bias / n_global;
+    const float scale = (float)(*d_bias / n_global);
     const unsigned stride = gridDim.x * blockDim.x;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
         const float4 p = ld_stream(postype + i);
@@ -109,14 +152,15 @@ lamellar_force_kernel(const float4* __restrict__ postype, float4* __restrict__ f
         float fx = 0.f, fy = 0.f, fz = 0.f;
 #pragma unroll
         for (int k = 0; k < NW; ++k) {
-            double t = fma(ws.qt[k][0], x, fma(ws.qt[k][1], y, ws.qt[k][2] * z));
-            t -= rint(t);
-            const float f = 2.0f * a * sinpif((float)(2.0 * t));
+            const double t = fma(ws.qt[k][0], x, fma(ws.qt[k][1], y, ws.qt[k][2] * z));
+            float sn, cs;
+            sincospi_small(2.0f * frac_turns(t), sn, cs);
+            const float f = 2.0f * a * sn;
             fx = fmaf(ws.q[k][0], f, fx);
             fy = fmaf(ws.q[k][1], f, fy);
             fz = fmaf(ws.q[k][2], f, fz);
         }
-        float4 out = make_float4((float)((double)fx * scale), (float)((double)fy * scale), (float)((double)fz * scale), 0.f);
+        float4 out = make_float4(fx * scale, fy * scale, fz * scale, 0.f);
         if (accumulate) {
             const float4 old = force[i];
             out.x += old.x; out.y += old.y; out.z += old.z;

@@ -89,7 +89,9 @@ def test_lamellar_sharded_modes_allreduce_equivalence(gpu, oracle):
         part.compute_modes(to_dev(gpu, pos[lo:hi], types[lo:hi]), 30000, box, finalize=False)
         acc = part.modes.clone() if acc is None else acc + part.modes
     full.modes.copy_(acc)
-    assert full.finalize(30000).cpu().item() == pytest.approx(cv_full, rel=1e-12, abs=1e-15)
+    # terms are summed in fp32 over runs of 8 particles, the runs in fp64: regrouping the particles moves the sum by
+    # ~1e-7/sqrt(N) of the mode amplitude (this CV is ~0 for a disordered system, so the bound is absolute)
+    assert abs(full.finalize(30000).cpu().item() - cv_full) < 1e-8 * np.sqrt(30000) / 30000
 
 
 # ------------------------------------------------------------------------------------------------ mesh
