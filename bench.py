@@ -305,8 +305,16 @@ def run_ours(args):
         sb = runner.stage_bytes()
         top = max((k for k in acc if sb[k] > 0), key=lambda k: acc[k])
         achieved = sb[top] / (acc[top] * 1e-3) / 1e9
+        traffic, traffic_src = None, None
+        try:        # DRAM bytes per launch of that kernel from the committed ncu --set full capture of this workload
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            if tj["workload"] == w["name"]:
+                traffic, traffic_src = tj["dram_bytes_per_launch"].get(top), tj["source"]
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src, "stage_ms": {k: round(v, 4) for k, v in acc.items()},
+                    "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": sb[top], "peak_source": peak_src,
+                    "stage_ms": {k: round(v, 4) for k, v in acc.items()},
                     "step_frac": runner.algorithmic_bytes() / (ms_per_step * 1e-3) / 1e9 / peak}
     else:
         achieved = runner.algorithmic_bytes() / (ms_per_step * 1e-3) / 1e9
