@@ -146,6 +146,8 @@ OrderParameterMeshGPU::OrderParameterMeshGPU(std::shared_ptr<SystemDefinition> s
     std::vector<double> md(mode.begin(), mode.end());
     // zero_modes only feeds a kernel the reference never launches (SURVEY 8a note 1); accepted and ignored
     metad_check(metad_mesh_create(&m_plan, nx, ny, nz, (int)md.size(), md.data()), "Error initializing cv.mesh");
+    // the particle arrays of an MD engine keep their addresses: replay the per-step kernel sequence from a CUDA graph
+    metad_check(metad_mesh_set(m_plan, 4, 1), "Error initializing cv.mesh");
 }
 OrderParameterMeshGPU::~OrderParameterMeshGPU() { metad_mesh_destroy(m_plan); }
 

@@ -312,6 +312,24 @@ def test_mesh_c1_golden_with_umbrella(gpu, oracle):
     assert np.array_equal(mesh.cells(), data["c1_cells"])
 
 
+def test_mesh_empty_and_tiny_inputs(gpu, oracle):
+    """N = 0 (an MPI rank without particles) and N = 1: no kernel may trip over empty tiles."""
+    import torch
+    box = gpu.Box.make(6.0)
+    mesh = gpu.Mesh(32, 32, 32, [1.0])
+    empty = torch.empty((0, 4), dtype=torch.float32, device="cuda")
+    cv0 = mesh.compute_cv(empty, 5, box).cpu().item()
+    assert cv0 == 0.0
+    f0 = mesh.forces(empty, 5, box, torch.ones(1, dtype=torch.float64, device="cuda"))
+    assert f0.shape == (0, 4)
+    pos = np.array([[0.3, -1.2, 2.9]], np.float32)
+    d1 = to_dev(gpu, pos, np.zeros(1, np.int32))
+    cv1 = mesh.compute_cv(d1, 1, box).cpu().item()
+    m = oracle.Mesh(32, 32, 32, [1.0], [6.0] * 3, 1, "f64", literal_copysignf=False)
+    assert cv1 == pytest.approx(m.current_value(host_pt(oracle, pos, np.zeros(1, np.int32))), rel=1e-6)
+    assert mesh.compute_cv(empty, 5, box).cpu().item() == 0.0        # and back to empty: the accumulator was cleared
+
+
 def test_mesh_rejects_unsupported(gpu):
     from metadynamics_plugin_b200._abi import MetadError
     with pytest.raises(MetadError, match="power of two"):
