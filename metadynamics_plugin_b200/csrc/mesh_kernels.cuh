@@ -55,8 +55,7 @@ struct Geom {
     // the same two numbers as unevaluated float pairs: -lo = hl_hi + hl_lo, n/L = c_hi + c_lo
     float hl_hi[3], hl_lo[3], c_hi[3], c_lo[3];
     float fn[3];                // (float) global mesh dimensions
-    float rcpL[3];              // correctly rounded 1/L (single precision) for the exact constant division below
-    unsigned fast_div;          // 1: (x - lo)/L is evaluated as Markstein's FMA sequence (bit-identical to IEEE division)
+    float rcpL[3];              // 1/L in single precision (HOOMD BoxDim::m_Linv)
 };
 
 MHD void geom_set_dims(Geom& g, unsigned nx, unsigned ny, unsigned nz, unsigned lgT) {
@@ -81,22 +80,10 @@ inline void geom_set_box(Geom& g, const double* Ld) {
         g.c_hi[i] = (float)g.dscale[i]; g.c_lo[i] = (float)(g.dscale[i] - (double)g.c_hi[i]);
         g.fn[i] = (float)n[i];
     }
-    // correctly rounded reciprocal of the single-precision box length: the candidate next to (float)(1/L) with the
-    // smallest exact residual |1 - r L| (the product of two floats is exact in double)
-    g.fast_div = 1;
+    // HOOMD's BoxDim stores m_Linv = Scalar(1.0)/(hi - lo), a single-precision IEEE division
     for (int i = 0; i < 3; ++i) {
-        const float L = g.L[i];
-        float best = (float)(1.0 / (double)L);
-        double be = fabs(1.0 - (double)best * (double)L);
-        const float cand[2] = {nextafterf(best, 0.0f), nextafterf(best, 3.0e38f)};
-        for (float c : cand) {
-            const double e = fabs(1.0 - (double)c * (double)L);
-            if (e < be) { be = e; best = c; }
-        }
-        g.rcpL[i] = best;
-        // Markstein's theorem excludes divisors whose significand is all ones; also keep away from tiny / huge boxes
-        unsigned bits; memcpy(&bits, &L, 4);
-        if ((bits & 0x7fffffu) == 0x7fffffu || !(L > 1e-10f && L < 1e10f)) g.fast_div = 0;
+        volatile float one = 1.0f, Lf = g.L[i];
+        g.rcpL[i] = one / Lf;
     }
 }
 
@@ -156,29 +143,23 @@ MHD float f_fma(float a, float b, float c) {
 #endif
 }
 
-// cell coordinate along one axis: OrderParameterMesh.cc:543-561 with BoxDim::makeFraction = (x - lo)/L.
-//   f = (x - lo)/L ; r = f*n ; i = (int) r (truncation) ; i == n -> 0
-// Reference form (IEEE division, C truncation).  Out-of-box input (which HOOMD never hands over) is folded into the
-// mesh instead of indexing out of range.
-MHD int cell_coord_ref(float x, float lo, float L, unsigned n) {
-    const float f = f_div(f_sub(x, lo), L);
+// cell coordinate along one axis: OrderParameterMesh.cc:543-561 with HOOMD's BoxDim::makeFraction, which multiplies by
+// the stored reciprocal m_Linv = Scalar(1)/(hi - lo) (it does NOT divide; the two round differently and the cell index
+// of a particle next to a cell face depends on it -- confirmed against the reference's own assignParticles compiled
+// from its sources, tests/test_reference_build.py):
+//   f = (x - lo) * Linv ; r = f*n ; i = (int) r (truncation) ; i == n -> 0
+// Reference form (C truncation).  Out-of-box input (which HOOMD never hands over) is folded into the mesh instead of
+// indexing out of range.
+MHD int cell_coord_ref(float x, float lo, float Linv, unsigned n) {
+    const float f = f_mul(f_sub(x, lo), Linv);
     const float r = f_mul(f, (float)n);
     int i = (r >= 0.f && r < 4194304.f) ? (int)r : 0;
     if (i >= (int)n) i = 0;
     return i;
 }
-// a / L, correctly rounded, without the division unit: with y = RN(1/L), q = RN(a y), the residual r = a - q L is
-// exact in one FMA and RN(q + r y) = RN(a / L) (Markstein 1990; excluded divisors are filtered by geom_set_box;
-// tests/cpu_emul/mesh_emul.cu compares against IEEE division).
-MHD float div_by_const(float a, float L, float rcpL) {
-    const float q = f_mul(a, rcpL);
-    const float r = f_fma(-q, L, a);
-    return f_fma(r, rcpL, q);
-}
-// Hot form: same value as cell_coord_ref for every input, no division, no conversion-pipe instruction.
+// Hot form: same value for every input, no conversion-pipe instruction.
 MHD int cell_coord(float x, int axis, const Geom& g) {
-    const float a = f_sub(x, g.lo[axis]);
-    const float f = g.fast_div ? div_by_const(a, g.L[axis], g.rcpL[axis]) : f_div(a, g.L[axis]);
+    const float f = f_mul(f_sub(x, g.lo[axis]), g.rcpL[axis]);
     float r = f_mul(f, g.fn[axis]);
     const int n = (int)(axis == 0 ? g.nx : (axis == 1 ? g.ny : g.nzg));
 #ifdef __CUDA_ARCH__

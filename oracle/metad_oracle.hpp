@@ -4,17 +4,24 @@
 // tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 // load it, and only as the checker or the CPU baseline -- never as the thing shipped.
 //
-// *** PARITY UNPINNED. ***  The reference (jglaser/metadynamics-plugin) ships no golden
-// vectors, no unit tests and cannot be compiled here (every TU needs HOOMD-blue 2.x, which is
-// neither installed nor vendored).  This file restates the reference's *CPU* code path
-// formula by formula, each function citing the reference file:line it follows (paths relative
-// to /root/reference/metadynamics/).  It is cross-checked in tests/ against independent
-// numpy restatements (numpy.fft, closed-form TSC, analytic single-particle / lattice cases,
-// finite differences), but not against an executable of the reference.
-//
-// The pieces of HOOMD-blue 2.x arithmetic the path relies on (BoxDim, kiss_fftnd semantics)
-// are restated from the public HOOMD 2.x headers' documented behaviour; HOOMD's version is
-// not pinned by the reference (no submodule / lockfile).
+// *** PARITY: PINNED TO THE REFERENCE'S OWN CODE, EXCEPT FOR THE INTEGRATOR AND HOOMD'S BoxDim. ***
+// The reference (jglaser/metadynamics-plugin) ships no golden vectors and no unit tests, and its build needs
+// HOOMD-blue 2.x, which is neither installed nor vendored.  This file restates the reference's *CPU* code path
+// formula by formula, each function citing the reference file:line it follows (paths relative to
+// /root/reference/metadynamics/).  It is pinned in two ways:
+//   (1) against the reference's own classes: CollectiveVariable.cc, LamellarOrderParameter.cc, OrderParameterMesh.cc,
+//       AspectRatio.cc and IndexGrid.cc are compiled UNMODIFIED from /root/reference against a HOOMD stand-in
+//       (oracle/ref_shim/, oracle/ref_capi.cc, `make -C oracle ref` -> oracle/_ref/) and run on seeded inputs
+//       (tests/golden/make_ref_golden.py -> tests/golden/ref_golden.npz; tests/test_reference_build.py).  The density
+//       mesh of this file equals the reference's BIT FOR BIT in the float and the double build (every cell index, weight
+//       and summation order), CV values and forces agree to 1e-12 in double (the FFTs differ), Lamellar modes / CV /
+//       forces to 1e-13, umbrella, aspect ratio and IndexGrid exactly;
+//   (2) against independent numpy restatements (numpy.fft, closed-form TSC, analytic single-particle / lattice cases,
+//       finite differences) in tests/test_oracle.py.
+// NOT pinned by an executable: IntegratorMetaDynamics.cc (needs HOOMD's IntegratorTwoStep and Eigen; its grid arithmetic
+// is restated here and checked by closed forms only), WellTemperedEnsemble.cc, and the two pieces of HOOMD itself that
+// the stand-in has to restate as well -- BoxDim (lo/hi/L/Linv, makeFraction = (v - lo) * Linv, branching minImage) and
+// kiss_fftnd (unnormalised DFT, dims slowest first).  HOOMD's version is not pinned by the reference (no submodule).
 //
 // Everything is templated on S = float (HOOMD SINGLE_PRECISION build) or double (HOOMD
 // default build).  The double instance is the "truth" for floating-point tolerances, the
@@ -53,7 +60,7 @@ template <class S> inline S dot(V3<S> a, V3<S> b) { return a.x * b.x + a.y * b.y
 // BoxDim -- restates the HOOMD-blue 2.x hoomd/BoxDim.h members the path calls
 // (call sites: OrderParameterMesh.cc:543,570-573,783,807-810,362-369;
 //  LamellarOrderParameter.cc:151-159).  lo = -L/2, hi = +L/2.
-//   makeFraction(v)    = ((v - lo) - tilt terms) / L          (ghost width 0)
+//   makeFraction(v)    = ((v - lo) - tilt terms) * Linv, Linv = 1/(hi - lo)   (ghost width 0)
 //   makeCoordinates(f) = lo + f*L, then x += xy*y + xz*z, y += yz*z
 //   minImage(v)        = host (branching) variant: one box length per direction
 //   getLatticeVector   = (Lx,0,0), (Ly*xy,Ly,0), (Lz*xz,Lz*yz,Lz)
@@ -76,7 +83,7 @@ template <class S> struct Box {
         V3<S> d = v - lo;
         d.x -= (xz - yz * xy) * v.z + xy * v.y;
         d.y -= yz * v.z;
-        return d / L;
+        return d * Linv;          // HOOMD multiplies by the stored reciprocal m_Linv = 1/(hi - lo); a division would round differently
     }
     V3<S> makeCoordinates(V3<S> f) const {
         V3<S> v = lo + f * L;

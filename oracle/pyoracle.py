@@ -1,6 +1,7 @@
 """ctypes front-end of the CPU oracle (oracle/_build/liboracle.so).
 
-TEST INFRASTRUCTURE ONLY -- "parity unpinned" (see oracle/metad_oracle.hpp).  Only tests/,
+TEST INFRASTRUCTURE ONLY -- pinned against the reference's own sources for the CV classes, unpinned for the integrator
+(see the header of oracle/metad_oracle.hpp and tests/test_reference_build.py).  Only tests/,
 ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` legs may import
 this module; the product package (metadynamics_plugin_b200) never does.
 """
@@ -333,3 +334,8 @@ def indexgrid_coords(lengths, idx):
     c = np.empty(len(l), dtype=np.uint32)
     lib().orc_indexgrid_coords(l.ctypes.data_as(_up), len(l), int(idx), c.ctypes.data_as(_up))
     return c
+
+
+def indexgrid_num(lengths):
+    l = np.ascontiguousarray(lengths, dtype=np.uint32)
+    return int(lib().orc_indexgrid_num(l.ctypes.data_as(_up), len(l)))

@@ -1,0 +1,113 @@
+"""ctypes access to oracle/_ref/libref_{f32,f64}.so: the REFERENCE's own CPU classes (CollectiveVariable, LamellarOrderParameter,
+OrderParameterMesh, AspectRatio, IndexGrid), compiled from the reference's sources where they lie against the HOOMD stand-in in
+oracle/ref_shim/ (see oracle/Makefile target `ref`, oracle/ref_capi.cc).  TEST INFRASTRUCTURE ONLY: used by
+tests/test_reference_build.py and tests/golden/make_ref_golden.py to pin the oracle's restatement."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REFERENCE = "/root/reference/metadynamics"
+_libs = {}
+_dp, _fp, _ip, _up = C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_uint)
+
+
+def available():
+    return os.path.isdir(REFERENCE) or all(os.path.exists(os.path.join(_HERE, "_ref", "libref_%s.so" % p)) for p in ("f32", "f64"))
+
+
+def build():
+    if os.path.isdir(REFERENCE):
+        subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+
+
+def lib(prec):
+    if prec not in _libs:
+        build()
+        _libs[prec] = C.CDLL(os.path.join(_HERE, "_ref", "libref_%s.so" % prec))
+        assert _libs[prec].ref_scalar_bytes() == (4 if prec == "f32" else 8)
+    return _libs[prec]
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _box(L, tilt):
+    return (np.ascontiguousarray(np.broadcast_to(np.asarray(L, np.float64), (3,))), np.ascontiguousarray(np.asarray(tilt, np.float64)))
+
+
+def mesh(dims, mode, L, postype, bias, prec="f64", tilt=(0, 0, 0)):
+    nx, ny, nz = dims
+    M, N = nx * ny * nz, postype.shape[0]
+    mode = np.ascontiguousarray(mode, np.float64)
+    Lb, tb = _box(L, tilt)
+    pt = np.ascontiguousarray(postype, np.float32)
+    cv, msq = C.c_double(), C.c_double()
+    force, rho, inv, interp = np.empty((N, 4)), np.empty(M), np.empty(M), np.empty(M)
+    rc = lib(prec).ref_mesh(nx, ny, nz, _d(mode), len(mode), _d(Lb), _d(tb), pt.ctypes.data_as(_fp), N, C.c_double(bias), C.byref(cv), C.byref(msq),
+                            _d(force), _d(rho), _d(inv), _d(interp))
+    assert rc == 0
+    return dict(cv=cv.value, mode_sq=msq.value, force=force, rho=rho.reshape(nz, ny, nx), inv=inv.reshape(nz, ny, nx),
+                interp=interp.reshape(nz, ny, nx))
+
+
+def lamellar(mode, lattice_vectors, L, postype, bias, prec="f64", tilt=(0, 0, 0)):
+    N = postype.shape[0]
+    mode = np.ascontiguousarray(mode, np.float64)
+    lv = np.ascontiguousarray(lattice_vectors, np.int32).reshape(-1, 3)
+    Lb, tb = _box(L, tilt)
+    pt = np.ascontiguousarray(postype, np.float32)
+    cv = C.c_double()
+    modes, force = np.empty(2 * lv.shape[0]), np.empty((N, 4))
+    rc = lib(prec).ref_lamellar(_d(mode), len(mode), lv.ctypes.data_as(_ip), lv.shape[0], _d(Lb), _d(tb), pt.ctypes.data_as(_fp), N,
+                                C.c_double(bias), C.byref(cv), _d(modes), _d(force))
+    assert rc == 0
+    return dict(cv=cv.value, modes=modes.reshape(-1, 2), force=force)
+
+
+def umbrella(kind, mode, lattice_vectors, L, postype, bias_in=0.0, cv0=0.0, kappa=1.0, width_flat=0.0, scale=1.0, prec="f64"):
+    N = postype.shape[0]
+    mode = np.ascontiguousarray(mode, np.float64)
+    lv = np.ascontiguousarray(lattice_vectors, np.int32).reshape(-1, 3)
+    Lb, _ = _box(L, (0, 0, 0))
+    pt = np.ascontiguousarray(postype, np.float32)
+    cv, en = C.c_double(), C.c_double()
+    force = np.empty((N, 4))
+    kinds = dict(no_umbrella=0, linear=1, harmonic=2, wall=3, gaussian=4)
+    rc = lib(prec).ref_umbrella(kinds[kind], C.c_double(cv0), C.c_double(kappa), C.c_double(width_flat), C.c_double(scale), _d(mode), len(mode),
+                                lv.ctypes.data_as(_ip), lv.shape[0], _d(Lb), pt.ctypes.data_as(_fp), N, C.c_double(bias_in), C.byref(cv), C.byref(en),
+                                _d(force))
+    assert rc == 0
+    return dict(cv=cv.value, energy=en.value, force=force)
+
+
+def aspect(dir1, dir2, L, bias, prec="f64", tilt=(0, 0, 0)):
+    Lb, tb = _box(L, tilt)
+    cv = C.c_double()
+    vir = np.empty(6)
+    assert lib(prec).ref_aspect(dir1, dir2, _d(Lb), _d(tb), C.c_double(bias), C.byref(cv), _d(vir)) == 0
+    return cv.value, vir
+
+
+def indexgrid_index(lengths, coords):
+    l, c = np.ascontiguousarray(lengths, np.uint32), np.ascontiguousarray(coords, np.uint32)
+    f = lib("f64").ref_indexgrid_index
+    f.restype = C.c_uint
+    return int(f(l.ctypes.data_as(_up), len(l), c.ctypes.data_as(_up)))
+
+
+def indexgrid_coords(lengths, idx):
+    l = np.ascontiguousarray(lengths, np.uint32)
+    out = np.empty(len(l), np.uint32)
+    lib("f64").ref_indexgrid_coords(l.ctypes.data_as(_up), len(l), C.c_uint(idx), out.ctypes.data_as(_up))
+    return out
+
+
+def indexgrid_num(lengths):
+    l = np.ascontiguousarray(lengths, np.uint32)
+    f = lib("f64").ref_indexgrid_num
+    f.restype = C.c_uint
+    return int(f(l.ctypes.data_as(_up), len(l)))

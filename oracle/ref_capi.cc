@@ -1,0 +1,141 @@
+// ref_capi.cc -- C entry points into the REFERENCE's own CPU classes, compiled from the reference's sources where they lie
+// (oracle/Makefile, target `_ref`; the HOOMD types they need come from the stand-in under oracle/ref_shim/).
+// Used by tests/test_reference_build.py and tests/golden/make_ref_golden.py to check the oracle's restatement
+// against the reference's own arithmetic.  TEST INFRASTRUCTURE ONLY -- never loaded by the product path.
+//
+// The access-specifier override below only affects THIS translation unit (the reference's .cc files are compiled
+// unmodified); it lets the checker read the meshes and call the protected computeBiasForces directly.
+#include <hoomd/ForceCompute.h>       // the stand-in and every standard header first, with their real access specifiers
+#include <hoomd/extern/kiss_fftnd.h>
+#include <hoomd/extern/pybind/include/pybind11/pybind11.h>
+#include <cstdio>
+#include <string.h>
+#define private public
+#define protected public
+#include "OrderParameterMesh.h"
+#include "LamellarOrderParameter.h"
+#include "AspectRatio.h"
+#include "IndexGrid.h"
+#undef private
+#undef protected
+
+namespace {
+std::shared_ptr<SystemDefinition> make_system(const float* postype, unsigned N, const double* L, const double* tilt, unsigned ntypes) {
+    BoxDim box((Scalar)L[0], (Scalar)L[1], (Scalar)L[2]);
+    box.setTiltFactors((Scalar)tilt[0], (Scalar)tilt[1], (Scalar)tilt[2]);
+    std::shared_ptr<ExecutionConfiguration> exec(new ExecutionConfiguration());
+    std::shared_ptr<ParticleData> pdata(new ParticleData(N, box, ntypes, exec));
+    ArrayHandle<Scalar4> h_pos(pdata->getPositions(), access_location::host, access_mode::overwrite);
+    for (unsigned i = 0; i < N; ++i) {
+        int type;
+        memcpy(&type, postype + 4 * (size_t)i + 3, 4);
+        h_pos.data[i] = make_scalar4((Scalar)postype[4 * (size_t)i], (Scalar)postype[4 * (size_t)i + 1], (Scalar)postype[4 * (size_t)i + 2],
+                                     __int_as_scalar(type));
+    }
+    return std::shared_ptr<SystemDefinition>(new SystemDefinition(pdata));
+}
+void copy_force(ForceCompute& fc, unsigned N, double* out) {
+    ArrayHandle<Scalar4> h(fc.getForceArray(), access_location::host, access_mode::read);
+    for (unsigned i = 0; i < N; ++i) { out[4 * (size_t)i] = h.data[i].x; out[4 * (size_t)i + 1] = h.data[i].y; out[4 * (size_t)i + 2] = h.data[i].z; out[4 * (size_t)i + 3] = h.data[i].w; }
+}
+}  // namespace
+
+extern "C" {
+
+int ref_scalar_bytes() { return (int)sizeof(Scalar); }
+
+// OrderParameterMesh: getCurrentValue (assignParticles + updateMeshes + computeCV), then computeBiasForces with `bias`.
+// Outputs (double): cv, mode_sq, force[4N], rho[M] = Re(mesh), inv[M] = Re(inverse mesh), interp[M]
+int ref_mesh(unsigned nx, unsigned ny, unsigned nz, const double* mode, unsigned ntypes, const double* L, const double* tilt,
+             const float* postype, unsigned N, double bias, double* cv, double* mode_sq, double* force, double* rho, double* inv, double* interp) {
+    try {
+        auto sys = make_system(postype, N, L, tilt, ntypes);
+        std::vector<Scalar> m(mode, mode + ntypes);
+        OrderParameterMesh op(sys, nx, ny, nz, m);
+        *cv = op.getCurrentValue(1);
+        *mode_sq = op.m_mode_sq;
+        op.setBiasFactor((Scalar)bias);
+        op.computeBiasForces(1);
+        copy_force(op, N, force);
+        const size_t M = (size_t)nx * ny * nz;
+        ArrayHandle<kiss_fft_cpx> h_mesh(op.m_mesh, access_location::host, access_mode::read);
+        ArrayHandle<kiss_fft_cpx> h_inv(op.m_inv_fourier_mesh, access_location::host, access_mode::read);
+        ArrayHandle<Scalar> h_interp(op.m_interpolation_f, access_location::host, access_mode::read);
+        for (size_t i = 0; i < M; ++i) { rho[i] = h_mesh.data[i].r; inv[i] = h_inv.data[i].r; interp[i] = h_interp.data[i]; }
+        return 0;
+    } catch (const std::exception& e) { fprintf(stderr, "ref_mesh: %s\n", e.what()); return -1; }
+}
+
+// LamellarOrderParameter: getCurrentValue, Fourier modes, computeBiasForces with `bias`
+int ref_lamellar(const double* mode, unsigned ntypes, const int* lattice, unsigned n_wave, const double* L, const double* tilt,
+                 const float* postype, unsigned N, double bias, double* cv, double* modes_out /* 2*n_wave */, double* force) {
+    try {
+        auto sys = make_system(postype, N, L, tilt, ntypes);
+        std::vector<Scalar> m(mode, mode + ntypes);
+        std::vector<int3> lv(n_wave);
+        for (unsigned k = 0; k < n_wave; ++k) lv[k] = make_int3(lattice[3 * k], lattice[3 * k + 1], lattice[3 * k + 2]);
+        LamellarOrderParameter op(sys, m, lv, "");
+        *cv = op.getCurrentValue(1);
+        {
+            ArrayHandle<Scalar2> h(op.m_fourier_modes, access_location::host, access_mode::read);
+            for (unsigned k = 0; k < n_wave; ++k) { modes_out[2 * k] = h.data[k].x; modes_out[2 * k + 1] = h.data[k].y; }
+        }
+        op.setBiasFactor((Scalar)bias);
+        op.computeBiasForces(1);
+        copy_force(op, N, force);
+        return 0;
+    } catch (const std::exception& e) { fprintf(stderr, "ref_lamellar: %s\n", e.what()); return -1; }
+}
+
+// CollectiveVariable::computeForces / getUmbrellaPotential through a Lamellar CV: returns the bias factor that reached
+// computeBiasForces (read back from the force: F = bias * dCV-like term, so the ratio to a unit-bias run) and the umbrella energy
+int ref_umbrella(int kind, double cv0, double kappa, double width_flat, double scale, const double* mode, unsigned ntypes,
+                 const int* lattice, unsigned n_wave, const double* L, const float* postype, unsigned N, double bias_in,
+                 double* cv, double* energy, double* force) {
+    try {
+        const double tilt[3] = {0, 0, 0};
+        auto sys = make_system(postype, N, L, tilt, ntypes);
+        std::vector<Scalar> m(mode, mode + ntypes);
+        std::vector<int3> lv(n_wave);
+        for (unsigned k = 0; k < n_wave; ++k) lv[k] = make_int3(lattice[3 * k], lattice[3 * k + 1], lattice[3 * k + 2]);
+        LamellarOrderParameter op(sys, m, lv, "");
+        op.setUmbrella((CollectiveVariable::umbrella_Enum)kind);
+        op.setMinimum((Scalar)cv0); op.setKappa((Scalar)kappa); op.setWidthFlat((Scalar)width_flat); op.setScale((Scalar)scale);
+        op.setBiasFactor((Scalar)bias_in);
+        *cv = op.getCurrentValue(1);
+        *energy = op.getUmbrellaPotential(1);
+        op.compute(1);                       // ForceCompute::compute -> CollectiveVariable::computeForces
+        copy_force(op, N, force);
+        return 0;
+    } catch (const std::exception& e) { fprintf(stderr, "ref_umbrella: %s\n", e.what()); return -1; }
+}
+
+int ref_aspect(unsigned dir1, unsigned dir2, const double* L, const double* tilt, double bias, double* cv, double* ext_virial6) {
+    try {
+        const float dummy[4] = {0, 0, 0, 0};
+        auto sys = make_system(dummy, 1, L, tilt, 1);
+        AspectRatio ar(sys, dir1, dir2);
+        *cv = ar.getCurrentValue(1);
+        ar.setBiasFactor((Scalar)bias);
+        ar.computeBiasForces(1);
+        for (int i = 0; i < 6; ++i) ext_virial6[i] = ar.getExternalVirial(i);
+        return 0;
+    } catch (const std::exception& e) { fprintf(stderr, "ref_aspect: %s\n", e.what()); return -1; }
+}
+
+unsigned ref_indexgrid_index(const unsigned* lengths, int d, const unsigned* coords) {
+    IndexGrid g(std::vector<unsigned int>(lengths, lengths + d));
+    return g.getIndex(std::vector<unsigned int>(coords, coords + d));
+}
+void ref_indexgrid_coords(const unsigned* lengths, int d, unsigned idx, unsigned* coords) {
+    IndexGrid g(std::vector<unsigned int>(lengths, lengths + d));
+    std::vector<unsigned int> c(d);
+    g.getCoordinates(idx, c);
+    for (int i = 0; i < d; ++i) coords[i] = c[i];
+}
+unsigned ref_indexgrid_num(const unsigned* lengths, int d) {
+    IndexGrid g(std::vector<unsigned int>(lengths, lengths + d));
+    return g.getNumElements();
+}
+
+}  // extern "C"

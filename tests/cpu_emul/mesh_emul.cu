@@ -41,13 +41,13 @@ int main(int argc, char** argv) {
     const size_t M = (size_t)g.nx * g.ny * g.nz;
     const unsigned n3[3] = {g.nx, g.ny, g.nz};
 
-    // ---- hot cell rule (Markstein division, magic truncation) against its reference form (IEEE division, C cast):
+    // ---- hot cell rule (magic truncation) against its reference form (C cast):
     // the input particles, positions within a few ulps of every cell boundary, and random positions
     unsigned long long cell_mismatch = 0;
     {
         auto check = [&](float x, int axis) {
             const unsigned nn = axis == 0 ? g.nx : (axis == 1 ? g.ny : g.nzg);
-            if (cell_coord(x, axis, g) != cell_coord_ref(x, g.lo[axis], g.L[axis], nn)) ++cell_mismatch;
+            if (cell_coord(x, axis, g) != cell_coord_ref(x, g.lo[axis], g.rcpL[axis], nn)) ++cell_mismatch;
         };
         for (unsigned i = 0; i < N; ++i) { check(postype[i].x, 0); check(postype[i].y, 1); check(postype[i].z, 2); }
         for (int axis = 0; axis < 3; ++axis) {

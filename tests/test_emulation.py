@@ -108,7 +108,7 @@ def test_mesh_pipeline_matches_oracle(oracle, N, dims, L, lgT, modes, edge, stal
     m32.assign(pt)
     assert np.array_equal(r["cells"], m32.cells())                  # bit-exact against the single-precision build
     assert r["msq"] == m.mode_sq()
-    assert r["cell_mismatch"] == 0                                  # division-free cell rule == IEEE division + C truncation
+    assert r["cell_mismatch"] == 0                                  # conversion-free cell rule == its reference form (C truncation)
     assert r["shift_err"] < 1e-7                                    # compensated fp32 in-cell offset vs its fp64 form
     assert (r["strays"] > 0) == (stale > 2.0)
     assert r["cv"] == pytest.approx(cvo, rel=1e-6)                  # north-star tolerance for CVs
