@@ -41,7 +41,15 @@ def mesh_case(seed, N, dims, L, modes):
         x = np.float32(-Lf[d] / 2 + k * Lf[d] / n[d])
         for _ in range(int(rng.integers(0, 4))):
             x = np.nextafter(x, np.float32(1e9 if rng.random() < 0.5 else -1e9))
-        pos[i, d] = min(max(x, np.float32(-Lf[d] / 2)), np.float32(Lf[d] / 2))
+        pos[i, d] = x
+    # HOOMD keeps particles inside the box it computes with: pull everything that float rounding pushed outside the
+    # DOUBLE box [-L/2, L/2] back by whole ulps (both builds of the reference are fed the same float positions)
+    for d in range(3):
+        for _ in range(4):
+            lo_out = pos[:, d].astype(np.float64) < -Lf[d] / 2
+            hi_out = pos[:, d].astype(np.float64) > Lf[d] / 2
+            pos[lo_out, d] = np.nextafter(pos[lo_out, d], np.float32(1e9))
+            pos[hi_out, d] = np.nextafter(pos[hi_out, d], np.float32(-1e9))
     return postype(pos, rng.integers(0, len(modes), N))
 
 

@@ -120,6 +120,25 @@ def test_mesh_pipeline_matches_oracle(oracle, N, dims, L, lgT, modes, edge, stal
     assert np.all(r["force"][:, 3] == 0)
 
 
+@pytest.mark.parametrize("name", ["m0", "m1", "m2"])
+def test_mesh_pipeline_matches_reference_vectors(name):
+    """The device code (CPU emulation) against outputs of the REFERENCE's own OrderParameterMesh.cc, double build
+    (tests/golden/ref_golden.npz; inputs include particles a few ulps around cell faces).  Forces: the reference's double
+    build rounds |x| to float in assignTSCderiv (copysignf), which moves ITS forces by up to 1e-4 of max|F| here."""
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_golden.npz"))
+    c = G[name + "_cfg"]
+    dims, L, bias, modes = tuple(int(v) for v in c[:3]), tuple(c[3:6]), float(c[6]), tuple(c[7:])
+    pt = G[name + "_postype"]
+    r = run_mesh(build_emul("mesh_emul"), pt, dims, L, pt.shape[0], bias, 3, modes, 0.9)
+    ref_cv, ref_msq = G[name + "_f64_cv"]
+    assert r["msq"] == ref_msq and r["cell_mismatch"] == 0
+    rho = G[name + "_f64_rho"]
+    assert np.abs(r["rho"] - rho).max() < 2e-6 * max(1.0, np.abs(rho).max())
+    assert r["cv"] == pytest.approx(ref_cv, rel=1e-6)
+    fr = G[name + "_f64_force"]
+    assert np.abs(r["force"] - fr).max() < 2e-4 * np.abs(fr).max()
+
+
 def test_mesh_density_is_order_independent(oracle):
     """Integer accumulation: the density, the CV and the forces are bitwise independent of the tile order."""
     exe = build_emul("mesh_emul")
