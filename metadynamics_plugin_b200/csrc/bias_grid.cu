@@ -89,14 +89,16 @@ __device__ double grid_derivative(const GridParams& P, const double* grid, int c
     return (y2 - y1) / (2.0 * delta);
 }
 
-// histogram bin (:1102-1116): Scalar -> unsigned conversion, off-grid if any coordinate >= n (or negative)
+// histogram bin (:1102-1116): Scalar -> unsigned conversion, off-grid if any coordinate >= n (or <= -1)
 __device__ bool grid_bin(const GridParams& P, const double* val, unsigned* idx_out) {
     bool on = true;
     unsigned idx = 0;
     for (int i = 0; i < P.d; ++i) {
         const double q = (val[i] - P.cv_min[i]) / grid_delta_of(P, i);
-        if (!(q >= 0.0) || q >= 4294967296.0) { on = false; continue; }
-        const unsigned c = (unsigned)q;
+        // the reference converts a Scalar to unsigned here; on its platform (x86-64) -1 < q < 0 lands in bin 0 and
+        // q <= -1 off the grid (pinned against the reference binary, tests/test_reference_build.py)
+        if (!(q > -1.0) || q >= 4294967296.0) { on = false; continue; }
+        const unsigned c = q < 0.0 ? 0u : (unsigned)q;
         if (c >= P.n[i]) on = false;
         idx += c * P.factor[i];
     }

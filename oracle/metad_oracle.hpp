@@ -4,24 +4,26 @@
 // tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 // load it, and only as the checker or the CPU baseline -- never as the thing shipped.
 //
-// *** PARITY: PINNED TO THE REFERENCE'S OWN CODE, EXCEPT FOR THE INTEGRATOR AND HOOMD'S BoxDim. ***
+// *** PARITY: PINNED TO THE REFERENCE'S OWN CODE (HOOMD's BoxDim / kiss_fft and the trivial WTE sums excepted). ***
 // The reference (jglaser/metadynamics-plugin) ships no golden vectors and no unit tests, and its build needs
 // HOOMD-blue 2.x, which is neither installed nor vendored.  This file restates the reference's *CPU* code path
 // formula by formula, each function citing the reference file:line it follows (paths relative to
 // /root/reference/metadynamics/).  It is pinned in two ways:
 //   (1) against the reference's own classes: CollectiveVariable.cc, LamellarOrderParameter.cc, OrderParameterMesh.cc,
-//       AspectRatio.cc and IndexGrid.cc are compiled UNMODIFIED from /root/reference against a HOOMD stand-in
-//       (oracle/ref_shim/, oracle/ref_capi.cc, `make -C oracle ref` -> oracle/_ref/) and run on seeded inputs
-//       (tests/golden/make_ref_golden.py -> tests/golden/ref_golden.npz; tests/test_reference_build.py).  The density
-//       mesh of this file equals the reference's BIT FOR BIT in the float and the double build (every cell index, weight
-//       and summation order), CV values and forces agree to 1e-12 in double (the FFTs differ), Lamellar modes / CV /
-//       forces to 1e-13, umbrella, aspect ratio and IndexGrid exactly;
+//       AspectRatio.cc, IndexGrid.cc and IntegratorMetaDynamics.cc are compiled UNMODIFIED from /root/reference against a
+//       HOOMD stand-in (oracle/ref_shim/, oracle/ref_capi.cc, `make -C oracle ref` -> oracle/_ref/) and run on seeded
+//       inputs (tests/golden/make_ref_golden.py -> tests/golden/ref_golden.npz; tests/test_reference_build.py).  The
+//       density mesh of this file equals the reference's BIT FOR BIT in the float and the double build (every cell
+//       index, weight and summation order); CV values and forces agree to 1e-12 in double (the FFTs differ); Lamellar
+//       modes / CV / forces to 1e-13; the bias grid (bias factors after every step, grid, reweighted estimator, weights,
+//       sigma grid, histograms) BIT FOR BIT for 1-3 CVs, standard and well-tempered, both builds; umbrella, aspect
+//       ratio and IndexGrid exactly;
 //   (2) against independent numpy restatements (numpy.fft, closed-form TSC, analytic single-particle / lattice cases,
 //       finite differences) in tests/test_oracle.py.
-// NOT pinned by an executable: IntegratorMetaDynamics.cc (needs HOOMD's IntegratorTwoStep and Eigen; its grid arithmetic
-// is restated here and checked by closed forms only), WellTemperedEnsemble.cc, and the two pieces of HOOMD itself that
-// the stand-in has to restate as well -- BoxDim (lo/hi/L/Linv, makeFraction = (v - lo) * Linv, branching minImage) and
-// kiss_fftnd (unnormalised DFT, dims slowest first).  HOOMD's version is not pinned by the reference (no submodule).
+// NOT pinned by an executable: WellTemperedEnsemble.cc (its header does not compile without ENABLE_CUDA; the CPU
+// arithmetic is a plain sum and a scale), and the two pieces of HOOMD itself that the stand-in has to restate as well --
+// BoxDim (lo/hi/L/Linv, makeFraction = (v - lo) * Linv, branching minImage) and kiss_fftnd (unnormalised DFT, dims
+// slowest first).  HOOMD's version is not pinned by the reference (no submodule).
 //
 // Everything is templated on S = float (HOOMD SINGLE_PRECISION build) or double (HOOMD
 // default build).  The double instance is the "truth" for floating-point tolerances, the
@@ -609,7 +611,10 @@ template <class S> struct MetaGrid {
         return (y2 - y1) / (S(2.0) * delta);
     }
     // histogram bin shared by updateHistogram :1092-1119 and updateSigmaGrid :1122-1155
-    // (Scalar -> unsigned conversion; a negative quotient is off-grid)
+    // Scalar -> unsigned conversion.  For a negative quotient the conversion is undefined behaviour in C++; the reference
+    // as compiled for x86-64 (cvttsd2si to 64 bit, low word kept) gives bin 0 for -1 < q < 0 and a huge value, i.e.
+    // off-grid, for q <= -1.  That is what the reference's own code does here (tests/test_reference_build.py) and what is
+    // restated: a CV value less than one grid spacing below cv_min is counted in the first bin.
     bool bin_of(const std::vector<S>& val, unsigned& idx) const {
         size_t d = vars.size();
         std::vector<unsigned> c(d);
@@ -617,8 +622,8 @@ template <class S> struct MetaGrid {
         for (size_t i = 0; i < d; ++i) {
             S delta = (vars[i].cv_max - vars[i].cv_min) / (vars[i].num_points - 1);
             S q = (val[i] - vars[i].cv_min) / delta;
-            if (!(q >= S(0)) || q >= S(4294967296.0)) { on = false; c[i] = 0; continue; }
-            c[i] = (unsigned)q;
+            if (!(q > S(-1.0)) || q >= S(4294967296.0)) { on = false; c[i] = 0; continue; }
+            c[i] = q < S(0) ? 0u : (unsigned)q;
             if (c[i] >= vars[i].num_points) on = false;
         }
         if (on) idx = gi.getIndex(c);

@@ -111,3 +111,27 @@ def indexgrid_num(lengths):
     f = lib("f64").ref_indexgrid_num
     f.restype = C.c_uint
     return int(f(l.ctypes.data_as(_up), len(l)))
+
+
+def grid_sequence(cv_min, cv_max, num_points, sigma, cv_values, timesteps, W=1.0, T_shift=1.0, T=1.0, stride=1, add_bias=True,
+                  well_tempered=False, prec="f64"):
+    """IntegratorMetaDynamics: prepRun + updateBiasPotential per step with prescribed CV values.  Returns the bias factors
+    after every step and the final grid state."""
+    a, b, s_ = (np.ascontiguousarray(v, np.float64) for v in (cv_min, cv_max, sigma))
+    n = np.ascontiguousarray(num_points, np.uint32)
+    d = len(n)
+    G = int(np.prod(n))
+    vals = np.ascontiguousarray(cv_values, np.float64).reshape(-1, d)
+    ts = np.ascontiguousarray(timesteps, np.uint32)
+    bias = np.empty_like(vals)
+    out = {k: np.empty(G) for k in ("grid", "reweighted", "weight", "sigma_grid")}
+    outu = {k: np.empty(G, np.uint32) for k in ("hist", "hist_gauss", "hist_delta")}
+    sc = np.empty(3)
+    rc = lib(prec).ref_grid_sequence(d, _d(a), _d(b), n.ctypes.data_as(_up), _d(s_), C.c_double(W), C.c_double(T_shift), C.c_double(T),
+                                     C.c_uint(stride), int(add_bias), int(well_tempered), _d(vals), ts.ctypes.data_as(_up), len(ts), _d(bias),
+                                     _d(out["grid"]), _d(out["reweighted"]), _d(out["weight"]), _d(out["sigma_grid"]),
+                                     outu["hist"].ctypes.data_as(_up), outu["hist_gauss"].ctypes.data_as(_up), outu["hist_delta"].ctypes.data_as(_up), _d(sc))
+    assert rc == 0
+    out.update(outu)
+    out.update(bias=bias, bias_potential=sc[0], reweight=sc[1], num_gaussians=int(sc[2]))
+    return out

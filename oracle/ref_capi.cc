@@ -8,6 +8,7 @@
 #include <hoomd/ForceCompute.h>       // the stand-in and every standard header first, with their real access specifiers
 #include <hoomd/extern/kiss_fftnd.h>
 #include <hoomd/extern/pybind/include/pybind11/pybind11.h>
+#include <hoomd/md/IntegratorTwoStep.h>
 #include <cstdio>
 #include <string.h>
 #define private public
@@ -16,6 +17,7 @@
 #include "LamellarOrderParameter.h"
 #include "AspectRatio.h"
 #include "IndexGrid.h"
+#include "IntegratorMetaDynamics.h"
 #undef private
 #undef protected
 
@@ -37,6 +39,20 @@ std::shared_ptr<SystemDefinition> make_system(const float* postype, unsigned N, 
 void copy_force(ForceCompute& fc, unsigned N, double* out) {
     ArrayHandle<Scalar4> h(fc.getForceArray(), access_location::host, access_mode::read);
     for (unsigned i = 0; i < N; ++i) { out[4 * (size_t)i] = h.data[i].x; out[4 * (size_t)i + 1] = h.data[i].y; out[4 * (size_t)i + 2] = h.data[i].z; out[4 * (size_t)i + 3] = h.data[i].w; }
+}
+}  // namespace
+
+namespace {
+class PrescribedCV : public CollectiveVariable {
+  public:
+    PrescribedCV(std::shared_ptr<SystemDefinition> sysdef, const std::string& name) : CollectiveVariable(sysdef, name), m_value(0) {}
+    Scalar getCurrentValue(unsigned int) { return m_value; }
+    Scalar m_value;
+};
+template <class T, class U> void dump(const GPUArray<T>& a, U* out) {
+    if (!out) return;
+    ArrayHandle<T> h(a, access_location::host, access_mode::read);
+    for (unsigned i = 0; i < a.getNumElements(); ++i) out[i] = (U)h.data[i];
 }
 }  // namespace
 
@@ -121,6 +137,39 @@ int ref_aspect(unsigned dir1, unsigned dir2, const double* L, const double* tilt
         for (int i = 0; i < 6; ++i) ext_virial6[i] = ar.getExternalVirial(i);
         return 0;
     } catch (const std::exception& e) { fprintf(stderr, "ref_aspect: %s\n", e.what()); return -1; }
+}
+
+// IntegratorMetaDynamics grid bias: prepRun (which performs the first updateBiasPotential) and then one
+// updateBiasPotential per further step, driven with prescribed CV values through a trivial CollectiveVariable subclass.
+// Outputs: the bias factors handed to the CVs after every step, and the grid state at the end.
+
+int ref_grid_sequence(int ncv, const double* cv_min, const double* cv_max, const unsigned* num_points, const double* sigma, double W,
+                      double T_shift, double T, unsigned stride, int add_bias, int well_tempered, const double* cv_values,
+                      const unsigned* timesteps, int nsteps, double* bias_out, double* grid, double* reweighted, double* weight,
+                      double* sigma_grid, unsigned* hist, unsigned* hist_gauss, unsigned* hist_delta, double* scalars3) {
+    try {
+        const double L[3] = {10, 10, 10}, tilt[3] = {0, 0, 0};
+        const float dummy[4] = {0, 0, 0, 0};
+        auto sys = make_system(dummy, 1, L, tilt, 1);
+        IntegratorMetaDynamics imd(sys, Scalar(0.005), (Scalar)W, (Scalar)T_shift, (Scalar)T, stride, add_bias != 0, "", false,
+                                   well_tempered ? IntegratorMetaDynamics::mode_well_tempered : IntegratorMetaDynamics::mode_standard);
+        std::vector<std::shared_ptr<PrescribedCV> > cvs;
+        for (int i = 0; i < ncv; ++i) {
+            cvs.push_back(std::shared_ptr<PrescribedCV>(new PrescribedCV(sys, "cv" + std::to_string(i))));
+            imd.registerCollectiveVariable(cvs.back(), (Scalar)sigma[i], (Scalar)cv_min[i], (Scalar)cv_max[i], num_points[i]);
+        }
+        imd.setGrid(true);
+        for (int s = 0; s < nsteps; ++s) {
+            for (int i = 0; i < ncv; ++i) cvs[i]->m_value = (Scalar)cv_values[(size_t)s * ncv + i];
+            if (s == 0) imd.prepRun(timesteps[s]);
+            else imd.updateBiasPotential(timesteps[s]);
+            for (int i = 0; i < ncv; ++i) bias_out[(size_t)s * ncv + i] = cvs[i]->m_bias;
+        }
+        dump(imd.m_grid, grid); dump(imd.m_grid_reweighted, reweighted); dump(imd.m_grid_weight, weight); dump(imd.m_sigma_grid, sigma_grid);
+        dump(imd.m_grid_hist, hist); dump(imd.m_grid_hist_gauss, hist_gauss); dump(imd.m_grid_hist_delta, hist_delta);
+        scalars3[0] = imd.m_curr_bias_potential; scalars3[1] = imd.m_curr_reweight; scalars3[2] = imd.m_num_gaussians;
+        return 0;
+    } catch (const std::exception& e) { fprintf(stderr, "ref_grid_sequence: %s\n", e.what()); return -1; }
 }
 
 unsigned ref_indexgrid_index(const unsigned* lengths, int d, const unsigned* coords) {

@@ -1,7 +1,7 @@
 """Generates tests/golden/ref_golden.npz from the REFERENCE's own code.
 
 The reference's CPU classes (CollectiveVariable.cc, LamellarOrderParameter.cc, OrderParameterMesh.cc, AspectRatio.cc,
-IndexGrid.cc) are compiled from /root/reference, unmodified, against the HOOMD stand-in in oracle/ref_shim/
+IndexGrid.cc, IntegratorMetaDynamics.cc) are compiled from /root/reference, unmodified, against the HOOMD stand-in in oracle/ref_shim/
 (`make -C oracle ref`, oracle/ref_capi.cc) and run on small seeded inputs.  These vectors are therefore outputs of the
 reference itself (with BoxDim and kiss_fft restated by the stand-in) -- unlike golden.npz, which pins the oracle.
 /root/reference only exists in the build container, so the vectors are committed.  Run from the repo root:
@@ -111,6 +111,34 @@ for lengths in ((20, 30), (256, 256), (12, 9, 7), (400,)):
         c = pyref.indexgrid_coords(lengths, int(idx))
         ig.append(list(lengths) + [0] * (3 - len(lengths)) + [len(lengths), n, int(idx), pyref.indexgrid_index(lengths, c)] + list(c) + [0] * (3 - len(c)))
 out["indexgrid_rows"] = np.array(ig, dtype=np.int64)
+
+# IntegratorMetaDynamics grid bias (prepRun + updateBiasPotential per step, prescribed CV values incl. values slightly
+# off the grid and the forward / backward difference branches)
+GRID = [("g1", dict(cv_min=[-2.0], cv_max=[2.0], num_points=[400], sigma=[0.05])),
+        ("g2", dict(cv_min=[0.0, 0.0], cv_max=[1.0, 2.0], num_points=[20, 30], sigma=[0.25, 0.1])),
+        ("g3", dict(cv_min=[0.0, -1.0, 2.0], cv_max=[1.0, 1.0, 3.0], num_points=[12, 9, 7], sigma=[0.2, 0.3, 0.25]))]
+for name, cfg in GRID:
+    d = len(cfg["num_points"])
+    rng = np.random.default_rng(100 + d)
+    lo, hi, npts = np.array(cfg["cv_min"]), np.array(cfg["cv_max"]), np.array(cfg["num_points"])
+    s_, vals = lo + (hi - lo) * rng.random(d), []
+    for t in range(16):
+        s_ = np.clip(s_ + 0.05 * (hi - lo) * rng.normal(size=d), lo - 1.6 * (hi - lo) / (npts - 1), hi + 0.6 * (hi - lo) / (npts - 1))
+        if t == 5:
+            s_ = lo + 0.3 * (hi - lo) / (npts - 1)
+        if t == 9:
+            s_ = hi - 0.3 * (hi - lo) / (npts - 1)
+        if t == 12:
+            s_ = lo - 0.4 * (hi - lo) / (npts - 1)          # less than one spacing below the grid: first bin on x86-64
+        vals.append(s_.copy())
+    out[name + "_cfg"] = np.array([d] + cfg["cv_min"] + cfg["cv_max"] + cfg["num_points"] + cfg["sigma"], dtype=np.float64)
+    out[name + "_vals"] = np.array(vals)
+    for wt in (0, 1):
+        r = pyref.grid_sequence(cfg["cv_min"], cfg["cv_max"], cfg["num_points"], cfg["sigma"], vals, list(range(16)), W=0.8, T_shift=7.0,
+                                T=1.3, stride=3, well_tempered=bool(wt))
+        for k in ("bias", "grid", "reweighted", "weight", "sigma_grid", "hist", "hist_gauss", "hist_delta"):
+            out["%s_wt%d_%s" % (name, wt, k)] = r[k]
+        out["%s_wt%d_scalars" % (name, wt)] = np.array([r["bias_potential"], r["reweight"], r["num_gaussians"]])
 
 np.savez_compressed(os.path.join(HERE, "ref_golden.npz"), **out)
 print("wrote ref_golden.npz:", {k: v.shape for k, v in out.items() if not k.endswith("postype")})

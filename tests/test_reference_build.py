@@ -1,7 +1,7 @@
 """Pins the oracle against the REFERENCE's own code.
 
 tests/golden/ref_golden.npz holds outputs of the reference's CPU classes (CollectiveVariable.cc, LamellarOrderParameter.cc,
-OrderParameterMesh.cc, AspectRatio.cc, IndexGrid.cc), compiled unmodified from /root/reference against a HOOMD stand-in
+OrderParameterMesh.cc, AspectRatio.cc, IndexGrid.cc, IntegratorMetaDynamics.cc), compiled unmodified from /root/reference against a HOOMD stand-in
 (oracle/ref_shim/, oracle/ref_capi.cc, `make -C oracle ref`; generator: tests/golden/make_ref_golden.py).  The oracle's
 restatement must reproduce them: the density mesh BIT FOR BIT in both precisions (same operations in the same order, so
 every cell index and every rounding agrees), CV values and forces to FFT / libm rounding.  Where /root/reference is
@@ -89,6 +89,29 @@ def test_oracle_indexgrid_reproduces_reference(oracle):
         assert oracle.indexgrid_num(lengths) == n
         assert np.array_equal(oracle.indexgrid_coords(lengths, idx), coords)
         assert oracle.indexgrid_index(lengths, coords) == idx == back
+
+
+@pytest.mark.parametrize("name", ["g1", "g2", "g3"])
+@pytest.mark.parametrize("wt", [0, 1])
+def test_oracle_bias_grid_reproduces_reference(oracle, name, wt):
+    """IntegratorMetaDynamics.cc (prepRun + updateBiasPotential per step): bias factors after every step and the final
+    grids, against the reference's own code -- the restatement performs the same double operations in the same order."""
+    c = GOLD[name + "_cfg"]
+    d = int(c[0])
+    cfg = dict(cv_min=list(c[1:1 + d]), cv_max=list(c[1 + d:1 + 2 * d]), num_points=[int(v) for v in c[1 + 2 * d:1 + 3 * d]],
+               sigma=list(c[1 + 3 * d:1 + 4 * d]))
+    o = oracle.Grid(**cfg, W=0.8, T_shift=7.0, T=1.3, stride=3, well_tempered=bool(wt))
+    vals = GOLD[name + "_vals"]
+    bias = np.array([o.update(t, v) for t, v in enumerate(vals)])
+    key = "%s_wt%d_" % (name, wt)
+    np.testing.assert_array_equal(bias, GOLD[key + "bias"])
+    for k in ("grid", "reweighted", "weight", "sigma_grid"):
+        np.testing.assert_array_equal(o.get(k), GOLD[key + k], err_msg=k)
+    for k in ("hist", "hist_gauss", "hist_delta"):
+        assert np.array_equal(o.get(k).astype(np.uint32), GOLD[key + k]), k
+    sc = o.scalars()
+    ref = GOLD[key + "scalars"]
+    assert sc["bias_potential"] == ref[0] and sc["reweight"] == ref[1] and sc["num_gaussians"] == int(ref[2])
 
 
 def test_live_reference_build_matches_oracle(oracle):
