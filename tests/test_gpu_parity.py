@@ -440,6 +440,31 @@ def test_bias_grid_sequence(gpu, oracle, dims_cfg, well_tempered):
     assert gs["out_of_bounds"] == os_["out_of_bounds"]
 
 
+@pytest.mark.parametrize("name", ["g1", "g2", "g3"])
+@pytest.mark.parametrize("wt", [0, 1])
+def test_bias_grid_against_reference_vectors(gpu, name, wt):
+    """metad_grid_step against outputs of the REFERENCE's own IntegratorMetaDynamics.cc (prepRun + updateBiasPotential per
+    step; tests/golden/ref_golden.npz): bias factors after every step, final grids, integer histograms bit-exact."""
+    import torch
+    G = _ref_gold()
+    c = G[name + "_cfg"]
+    d = int(c[0])
+    cfg = dict(cv_min=list(c[1:1 + d]), cv_max=list(c[1 + d:1 + 2 * d]), num_points=[int(v) for v in c[1 + 2 * d:1 + 3 * d]],
+               sigma=list(c[1 + 3 * d:1 + 4 * d]))
+    g = gpu.BiasGrid(**cfg, W=0.8, T_shift=7.0, T=1.3, stride=3, well_tempered=bool(wt))
+    key = "%s_wt%d_" % (name, wt)
+    for t, v in enumerate(G[name + "_vals"]):
+        b = g.step(t, torch.tensor(v, dtype=torch.float64, device="cuda")).cpu().numpy()
+        np.testing.assert_allclose(b, G[key + "bias"][t], rtol=1e-9, atol=1e-12)
+    for k in ("grid", "reweighted", "weight", "sigma_grid"):
+        np.testing.assert_allclose(g.get(k), G[key + k], rtol=1e-10, atol=1e-300, err_msg=k)
+    for k in ("hist", "hist_gauss", "hist_delta"):
+        assert np.array_equal(g.get(k), G[key + k]), k
+    sc, ref = g.scalars(), G[key + "scalars"]
+    assert sc["num_gaussians"] == int(ref[2])
+    assert sc["bias_potential"] == pytest.approx(ref[0], rel=1e-10, abs=1e-14) and sc["reweight"] == pytest.approx(ref[1], rel=1e-10)
+
+
 def test_bias_grid_restart_and_flags(gpu, oracle):
     import torch
     cfg = dict(cv_min=[0.0, 0.0], cv_max=[1.0, 2.0], num_points=[20, 30], sigma=[0.25, 0.1])
