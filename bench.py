@@ -146,7 +146,13 @@ class MeshSlabStep(MeshStep):
         self.d_pt = torch.from_numpy(local).cuda()
         cv_nccl = nccl.compute_cv(self.d_pt, self.N_global, self.box).cpu().item()
         if mode == "p2p":
-            self.slab = sharded.MeshSlabP2P(comm, *w["mesh"], w["mode"])
+            try:
+                self.slab = sharded.MeshSlabP2P(comm, *w["mesh"], w["mode"])
+            except RuntimeError as e:       # raised on every rank together (see MeshSlabP2P): fall back to the staged path
+                if comm.rank == 0:
+                    print("bench: %s -- falling back to --comm nccl" % e, file=sys.stderr)
+                mode = self.comm_mode = "nccl"
+        if mode == "p2p":
             cv_p2p = self.slab.compute_cv(self.d_pt, self.N_global, self.box).cpu().item()
             self.cv_check = abs(cv_p2p / cv_nccl - 1.0)
             st = self.slab.status()
@@ -366,7 +372,7 @@ def run_ours(args):
         "config": {"workload": "%s: %s" % (w["name"], describe(w)), "N": n_global, "l2": "inputs larger than L2 (no flush)",
                    "parallelism": "1 GPU" if world == 1 else (("z-slab mesh + particle sharding over %d GPUs, %s" % (
                        world, "peer memory over NVLink: transposes fused into the FFT sweeps, pushed halos, flag barriers (no NCCL call in a step; "
-                       "CV agrees with the NCCL path to %.1e)" % runner.cv_check if args.comm == "p2p" else "NCCL all-to-all / halo exchange / all-reduce"))
+                       "CV agrees with the NCCL path to %.1e)" % runner.cv_check if runner.comm_mode == "p2p" else "NCCL all-to-all / halo exchange / all-reduce"))
                                                               if w["kind"] == "mesh" else "particles sharded over %d GPUs, one NCCL all-reduce per step" % world),
                    "tile_order_rebuild_period": getattr(runner, "period", None), "tile_order_rebuilds_in_timed_region": rebuilds_timed},
         "roofline": roofline,

@@ -229,7 +229,7 @@ fft_x_inv_kernel(float2* buf, const float2* __restrict__ g_tw, const float2* in,
 // y pass: tile = 16 consecutive kx  x  all y, fixed z.  grid = (nxh/16, nz)
 // ---------------------------------------------------------------------------------------------------
 template <int L, int SIGN>
-__global__ void __launch_bounds__(kLines * L / kE)
+__global__ void __launch_bounds__(kLines * L / kE, (kLines * L / kE) <= 512 ? 2048 / (kLines * L / kE) : 1)
 fft_y_kernel(float2* __restrict__ buf, const float2* __restrict__ g_tw, unsigned nxh, const __grid_constant__ PeerOut peers,
              unsigned lg_planes /* peers.n != 0: log2 of the planes per rank */) {
     extern __shared__ float2 smem[];
@@ -238,9 +238,12 @@ fft_y_kernel(float2* __restrict__ buf, const float2* __restrict__ g_tw, unsigned
     const int nthr = kLines * L / kE;
     const size_t base = (size_t)blockIdx.y * L * nxh + (size_t)blockIdx.x * kLines;
     load_twiddles<L>(s_tw, g_tw);
-    for (int idx = threadIdx.x; idx < kLines * L; idx += nthr) {
-        const int w = idx & (kLines - 1), l = idx / kLines;
-        tile[idx] = buf[base + (size_t)l * nxh + w];
+    // 128-bit accesses: two neighbouring kx per thread (a line of the tile is 16 complex = 128 contiguous bytes)
+    float4* tile4 = reinterpret_cast<float4*>(tile);
+#pragma unroll
+    for (int q = 0; q < kE / 2; ++q) {
+        const int p = threadIdx.x + q * nthr, l = p / (kLines / 2), w2 = p % (kLines / 2);
+        tile4[p] = *reinterpret_cast<const float4*>(buf + base + (size_t)l * nxh + 2 * w2);
     }
     __syncthreads();
     const int w = threadIdx.x & (kLines - 1), t = threadIdx.x / kLines;
@@ -250,15 +253,17 @@ fft_y_kernel(float2* __restrict__ buf, const float2* __restrict__ g_tw, unsigned
         // [source rank][local plane][y][kx in the source's pencil] (what the inverse x pass unpacks)
         const unsigned z = blockIdx.y, dest = z >> lg_planes, zl = z & ((1u << lg_planes) - 1);
         float2* out = peers.ptr[dest] + (((size_t)peers.rank << lg_planes) + zl) * L * nxh + (size_t)blockIdx.x * kLines;
-        for (int idx = threadIdx.x; idx < kLines * L; idx += nthr) {
-            const int ww = idx & (kLines - 1), l = idx / kLines;
-            out[(size_t)l * nxh + ww] = tile[idx];
+#pragma unroll
+        for (int q = 0; q < kE / 2; ++q) {
+            const int p = threadIdx.x + q * nthr, l = p / (kLines / 2), w2 = p % (kLines / 2);
+            *reinterpret_cast<float4*>(out + (size_t)l * nxh + 2 * w2) = tile4[p];
         }
         return;
     }
-    for (int idx = threadIdx.x; idx < kLines * L; idx += nthr) {
-        const int ww = idx & (kLines - 1), l = idx / kLines;
-        buf[base + (size_t)l * nxh + ww] = tile[idx];
+#pragma unroll
+    for (int q = 0; q < kE / 2; ++q) {
+        const int p = threadIdx.x + q * nthr, l = p / (kLines / 2), w2 = p % (kLines / 2);
+        *reinterpret_cast<float4*>(buf + base + (size_t)l * nxh + 2 * w2) = tile4[p];
     }
 }
 
@@ -300,9 +305,11 @@ __device__ __forceinline__ void z_general_body(float2* __restrict__ buf, const f
     const size_t base = (size_t)ky * nxh + kx0;
     const size_t zstride = (size_t)ny * nxh;
     load_twiddles<L>(s_tw, g_tw);
-    for (int idx = threadIdx.x; idx < kLines * L; idx += nthr) {
-        const int w = idx & (kLines - 1), l = idx / kLines;
-        tile[idx] = buf[base + (size_t)l * zstride + w];
+    float4* tile4 = reinterpret_cast<float4*>(tile);
+#pragma unroll
+    for (int q = 0; q < kE / 2; ++q) {
+        const int p = threadIdx.x + q * nthr, l = p / (kLines / 2), w2 = p % (kLines / 2);
+        tile4[p] = *reinterpret_cast<const float4*>(buf + base + (size_t)l * zstride + 2 * w2);
     }
     __syncthreads();
     const int w = threadIdx.x & (kLines - 1), t = threadIdx.x / kLines;
@@ -320,10 +327,14 @@ __device__ __forceinline__ void z_general_body(float2* __restrict__ buf, const f
     }
     __syncthreads();
     line_fft<L, +1, L, LayoutCol>(tile, w, t, s_tw);
-    for (int idx = threadIdx.x; idx < kLines * L; idx += nthr) {
-        const int ww = idx & (kLines - 1), l = idx / kLines;
-        if (cp.kx_off + kx0 + ww == 0) continue;
-        buf[base + (size_t)l * zstride + ww] = tile[idx];
+    const bool has_col0 = cp.kx_off + kx0 == 0;          // column kx = 0 belongs to the plane0 blocks
+#pragma unroll
+    for (int q = 0; q < kE / 2; ++q) {
+        const int p = threadIdx.x + q * nthr, l = p / (kLines / 2), w2 = p % (kLines / 2);
+        float2* dst = buf + base + (size_t)l * zstride + 2 * w2;
+        const float4 v = tile4[p];
+        if (has_col0 && w2 == 0) dst[1] = make_float2(v.z, v.w);
+        else *reinterpret_cast<float4*>(dst) = v;
     }
     energy_block_finish(e, cp);
 }

@@ -153,25 +153,30 @@ MHD float f_fma(float a, float b, float c) {
 MHD int cell_coord_ref(float x, float lo, float Linv, unsigned n) {
     const float f = f_mul(f_sub(x, lo), Linv);
     const float r = f_mul(f, (float)n);
-    int i = (r >= 0.f && r < 4194304.f) ? (int)r : 0;
+    int i = (r >= 0.f) ? (r < 4194303.f ? (int)r : 4194303) : 0;
     if (i >= (int)n) i = 0;
     return i;
 }
 // Hot form: same value for every input, no conversion-pipe instruction.
-MHD int cell_coord(float x, int axis, const Geom& g) {
+// `raw` receives the index before the upper-edge wrap (n for a particle on the upper face): the in-cell offset is
+// measured from that cell, which is the periodic image of cell 0 the particle actually sits in.
+MHD int cell_coord(float x, int axis, const Geom& g, int& raw) {
     const float f = f_mul(f_sub(x, g.lo[axis]), g.rcpL[axis]);
     float r = f_mul(f, g.fn[axis]);
     const int n = (int)(axis == 0 ? g.nx : (axis == 1 ? g.ny : g.nzg));
 #ifdef __CUDA_ARCH__
-    // truncation: for 0 <= r < 2^22, RZ(r + 2^23) = 2^23 + trunc(r) exactly; anything else (out-of-box input, NaN) -> 0
-    r = (r >= 0.f && r < 4194304.f) ? r : 0.f;
+    // truncation: for 0 <= r < 2^22, RZ(r + 2^23) = 2^23 + trunc(r) exactly.  Out-of-box input (which HOOMD never hands
+    // over) is clamped: below the box (and NaN) -> cell 0, beyond it -> wrapped to 0 below
+    r = fminf(fmaxf(r, 0.f), 4194303.f);
     int i = __float_as_int(__fadd_rz(r, 8388608.f)) & 0x7fffff;
 #else
-    int i = (r >= 0.f && r < 4194304.f) ? (int)r : 0;
+    int i = (r >= 0.f) ? (r < 4194303.f ? (int)r : 4194303) : 0;
 #endif
+    raw = i <= n ? i : 0;
     if (i >= n) i = 0;
     return i;
 }
+MHD int cell_coord(float x, int axis, const Geom& g) { int raw; return cell_coord(x, axis, g, raw); }
 
 // tile-major key: tile index * T^3 + local cell index (x fastest inside the tile)
 MHD unsigned key_of(unsigned ix, unsigned iy, unsigned iz, const Geom& g) {
@@ -205,7 +210,7 @@ MHD float cell_shift_f64(float x, unsigned i, int axis, const Geom& g) {
 // -lo = hl_hi + hl_lo and n/L = c_hi + c_lo,  x - lo = d + e exactly (Fast2Sum, |x| <= L/2), (d + e)(c_hi + c_lo)
 // is evaluated as fma(d, c_hi, -(i + 1/2)) -- one rounding of a number of magnitude <= 1/2 -- plus the two small terms.
 // |cell_shift - cell_shift_f64| < 1e-7 for in-box particles (tests/cpu_emul/mesh_emul.cu checks it).
-MHD float cell_shift(float x, unsigned i, int axis, const Geom& g) {
+MHD float cell_shift(float x, unsigned i /* cell index BEFORE the upper-edge wrap (cell_coord's raw) */, int axis, const Geom& g) {
     const float hl = g.hl_hi[axis], ch = g.c_hi[axis];
     const float d = f_add(hl, x);
     const float e = f_add(f_sub(x, f_sub(d, hl)), g.hl_lo[axis]);
@@ -215,11 +220,8 @@ MHD float cell_shift(float x, unsigned i, int axis, const Geom& g) {
 #else
     const float ci = (float)i + 0.5f;
 #endif
-    // d*ch - (i + 1/2) in ONE rounding (the product is exact inside the FMA; |result| <= 1/2 unless the cell wrapped)
-    float t = f_fma(d, ch, -ci);
-    // periodic image: only the upper-edge particle, whose cell wrapped to 0, is affected; redo the single rounding there
-    if (t > 0.5f * g.fn[axis]) t = f_fma(d, ch, -(ci + g.fn[axis]));
-    return f_add(t, f_fma(e, ch, f_mul(d, g.c_lo[axis])));
+    // d*ch - (i + 1/2) in ONE rounding (the product is exact inside the FMA; |result| <= 1/2), plus the two small terms
+    return f_add(f_fma(d, ch, -ci), f_fma(e, ch, f_mul(d, g.c_lo[axis])));
 }
 
 // TSC weights of the three taps i = -1, 0, +1 for offset s (assignTSC, OrderParameterMesh.cc:457-468, with
@@ -274,13 +276,14 @@ MHD float fx_scale_for(float amax, float max_cell_load) {
 // ---------------------------------------------------------------------------------------------------
 struct Cell {
     int ix, iy, iz;      // global cell (bit-exact reference rule); iz is the GLOBAL plane
+    int rx, ry, rz;      // the same before the upper-edge wrap (n instead of 0 for a particle on an upper face)
     bool owned;          // slab mode: the plane belongs to this rank
 };
 MHD Cell particle_cell(float4 p, const Geom& g) {
     Cell c;
-    c.ix = cell_coord(p.x, 0, g);
-    c.iy = cell_coord(p.y, 1, g);
-    c.iz = cell_coord(p.z, 2, g);
+    c.ix = cell_coord(p.x, 0, g, c.rx);
+    c.iy = cell_coord(p.y, 1, g, c.ry);
+    c.iz = cell_coord(p.z, 2, g, c.rz);
     c.owned = (unsigned)(c.iz - (int)g.z0) < g.nz;
     return c;
 }
@@ -309,7 +312,7 @@ MHD bool tile_row(int ox, int oy, int oz, int py, int pz, int PX, const Geom& g,
 }
 // in-cell offsets of a particle (cell units)
 MHD float3 particle_shift(float4 p, const Cell& c, const Geom& g) {
-    return make_float3(cell_shift(p.x, c.ix, 0, g), cell_shift(p.y, c.iy, 1, g), cell_shift(p.z, c.iz, 2, g));
+    return make_float3(cell_shift(p.x, c.rx, 0, g), cell_shift(p.y, c.ry, 1, g), cell_shift(p.z, c.rz, 2, g));
 }
 // separable weights: w[0..2] = Wx(tap -1,0,+1), w[3..5] = Wy, w[6..8] = amp * Wz
 MHD void spread_weights(float3 s, float amp, float (&w)[9]) {

@@ -249,9 +249,16 @@ class MeshSlabP2P:
         allh = torch.empty(comm.size * 64, dtype=torch.uint8, device="cuda")
         comm.dist.all_gather_into_tensor(allh, mine, group=comm.group)
         buf = (C.c_ubyte * (64 * comm.size))(*allh.cpu().tolist())
-        check(lib.metad_mesh_slab_p2p_connect(self.r.h, buf))
+        err = None
+        try:
+            check(lib.metad_mesh_slab_p2p_connect(self.r.h, buf))
+        except Exception as e:              # e.g. no peer access between two devices: every rank must learn about it
+            err = e
+        ok = torch.tensor([0 if err else 1], dtype=torch.int32, device="cuda")
+        comm.dist.all_reduce(ok, op=comm.dist.ReduceOp.MIN, group=comm.group)   # also: every rank has mapped its peers
+        if ok.item() == 0:
+            raise RuntimeError("peer-memory mode is not available on every rank (%s); use the staged MeshSlab (NCCL) driver" % (err or "another rank failed"))
         self.arena_bytes = int(nbytes.value)
-        comm.dist.barrier(group=comm.group)          # every rank has mapped its peers before the first step
 
     def compute_cv(self, postype_local, n_global, box):
         r = self.r

@@ -135,9 +135,9 @@ int main(int argc, char** argv) {
             const float3 sh = particle_shift(p, c, g);
             spread_weights(sh, a * scale, w);
             const float xyz[3] = {p.x, p.y, p.z};
-            const int cxyz[3] = {c.ix, c.iy, c.iz};
+            const int cxyz[3] = {c.ix, c.iy, c.iz}, rxyz[3] = {c.rx, c.ry, c.rz};
             for (int d = 0; d < 3; ++d)
-                shift_err = std::max(shift_err, (double)std::fabs(cell_shift(xyz[d], cxyz[d], d, g) - cell_shift_f64(xyz[d], cxyz[d], d, g)));
+                shift_err = std::max(shift_err, (double)std::fabs(cell_shift(xyz[d], rxyz[d], d, g) - cell_shift_f64(xyz[d], cxyz[d], d, g)));
             unsigned lx, ly, lz;
             const bool inside = padded_coords(c, ox, oy, oz, g, PX, PY, PZ, lx, ly, lz);
             cache4[j] = make_float4(sh.x, sh.y, sh.z, a);
