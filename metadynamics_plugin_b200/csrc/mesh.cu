@@ -30,6 +30,7 @@
 #include "mesh_fft_kernels.cuh"
 #include "mesh_p2p.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <map>
 #include <vector>
@@ -172,18 +173,34 @@ template <int LC> int run_x(metad_mesh* p, bool inverse, float2* io, const doubl
 // y pass on buf = [nz_rows][ny][row_len]
 template <int L> int run_y(metad_mesh* p, bool inverse, float2* buf, unsigned row_len, unsigned nz_rows, cudaStream_t st,
                            const PeerOut* peer_out = nullptr) {
-    const size_t smem = sizeof(float2) * (LayoutCol::size(L) + L);
-    dim3 grid(row_len / kLines, nz_rows);
     PeerOut po;
     memset(&po, 0, sizeof po);
     if (peer_out) po = *peer_out;
     const unsigned lg_planes = ilog2(p->g.nz);
-    if (!inverse) {
-        int rc = set_smem(fft_y_kernel<L, -1>, smem); if (rc) return rc;
-        fft_y_kernel<L, -1><<<grid, kLines * L / kE, smem, st>>>(buf, p->d_twy, row_len, po, lg_planes);
+    // Two groups of 16 lines per tile (256-byte rows) are implemented (G = 2) but measured SLOWER on B200 (C4: 48.5 / 39.1 us
+    // against 38.9 / 34.8 us for the forward / inverse sweep: 1024-thread CTAs, two per SM), so they stay off.
+    constexpr bool can_wide = false;
+    if (can_wide && row_len % (2 * kLines) == 0) {
+        constexpr int G = can_wide ? 2 : 1;
+        const size_t smem = sizeof(float2) * (LayoutColWide<G>::size(L) + L);
+        dim3 grid(row_len / (G * kLines), nz_rows);
+        if (!inverse) {
+            int rc = set_smem(fft_y_kernel<L, -1, G>, smem); if (rc) return rc;
+            fft_y_kernel<L, -1, G><<<grid, G * kLines * L / kE, smem, st>>>(buf, p->d_twy, row_len, po, lg_planes);
+        } else {
+            int rc = set_smem(fft_y_kernel<L, +1, G>, smem); if (rc) return rc;
+            fft_y_kernel<L, +1, G><<<grid, G * kLines * L / kE, smem, st>>>(buf, p->d_twy, row_len, po, lg_planes);
+        }
     } else {
-        int rc = set_smem(fft_y_kernel<L, +1>, smem); if (rc) return rc;
-        fft_y_kernel<L, +1><<<grid, kLines * L / kE, smem, st>>>(buf, p->d_twy, row_len, po, lg_planes);
+        const size_t smem = sizeof(float2) * (LayoutColWide<1>::size(L) + L);
+        dim3 grid(row_len / kLines, nz_rows);
+        if (!inverse) {
+            int rc = set_smem(fft_y_kernel<L, -1, 1>, smem); if (rc) return rc;
+            fft_y_kernel<L, -1, 1><<<grid, kLines * L / kE, smem, st>>>(buf, p->d_twy, row_len, po, lg_planes);
+        } else {
+            int rc = set_smem(fft_y_kernel<L, +1, 1>, smem); if (rc) return rc;
+            fft_y_kernel<L, +1, 1><<<grid, kLines * L / kE, smem, st>>>(buf, p->d_twy, row_len, po, lg_planes);
+        }
     }
     METAD_LAUNCH_CHECK();
     return METAD_OK;

@@ -78,6 +78,10 @@ struct LayoutCol {   // y/z passes: tile[l][w], w fastest (16 float2 = 128 B per
     MHD static int addr(int w, int l, int /*L*/) { return l * kLines + w; }
     MHD static int size(int L) { return L * kLines; }
 };
+template <int G> struct LayoutColWide {   // y pass: G side-by-side groups of 16 lines, tile[l][16 G]; a group starts at column 16 g
+    MHD static int addr(int w, int l, int /*L*/) { return l * (kLines * G) + w; }
+    MHD static int size(int L) { return L * kLines * G; }
+};
 struct LayoutRow {   // x pass: tile[w][l] with one float2 of padding per line (odd stride: conflict-free)
     MHD static int addr(int w, int l, int L) { return w * (L + 1) + l; }
     MHD static int size(int L) { return kLines * (L + 1); }

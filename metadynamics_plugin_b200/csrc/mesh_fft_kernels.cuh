@@ -15,6 +15,9 @@
 #pragma once
 #include "common.cuh"
 #include "mesh_fft.cuh"
+#ifdef __CUDACC__
+#include <cuda_pipeline.h>
+#endif
 
 namespace metad {
 namespace fft {
@@ -228,42 +231,43 @@ fft_x_inv_kernel(float2* buf, const float2* __restrict__ g_tw, const float2* in,
 // ---------------------------------------------------------------------------------------------------
 // y pass: tile = 16 consecutive kx  x  all y, fixed z.  grid = (nxh/16, nz)
 // ---------------------------------------------------------------------------------------------------
-template <int L, int SIGN>
-__global__ void __launch_bounds__(kLines * L / kE, (kLines * L / kE) <= 512 ? 2048 / (kLines * L / kE) : 1)
+// G groups of 16 lines side by side: a row of the tile is 16 G consecutive kx = 128 G contiguous bytes in memory.
+// Measured on B200 (profiles/r01m_notes.md): G = 2 is slower than G = 1 (coarser CTAs), and a persistent, double-buffered
+// (cp.async) variant of the G = 1 kernel gained nothing -- the sweep runs at ~3.7 TB/s of L2 traffic either way.
+template <int L, int SIGN, int G>
+__global__ void __launch_bounds__(G * kLines * L / kE)
 fft_y_kernel(float2* __restrict__ buf, const float2* __restrict__ g_tw, unsigned nxh, const __grid_constant__ PeerOut peers,
              unsigned lg_planes /* peers.n != 0: log2 of the planes per rank */) {
-    extern __shared__ float2 smem[];
+    extern __shared__ __align__(16) float2 smem[];
+    using Lay = LayoutColWide<G>;
+    constexpr int gthr = kLines * L / kE, nthr = G * gthr, W = kLines * G, PAIRS = W * L / 2;
     float2* tile = smem;
-    float2* s_tw = smem + LayoutCol::size(L);
-    const int nthr = kLines * L / kE;
-    const size_t base = (size_t)blockIdx.y * L * nxh + (size_t)blockIdx.x * kLines;
+    float2* s_tw = smem + Lay::size(L);
+    const size_t base = (size_t)blockIdx.y * L * nxh + (size_t)blockIdx.x * W;
     load_twiddles<L>(s_tw, g_tw);
-    // 128-bit accesses: two neighbouring kx per thread (a line of the tile is 16 complex = 128 contiguous bytes)
     float4* tile4 = reinterpret_cast<float4*>(tile);
 #pragma unroll
-    for (int q = 0; q < kE / 2; ++q) {
-        const int p = threadIdx.x + q * nthr, l = p / (kLines / 2), w2 = p % (kLines / 2);
-        tile4[p] = *reinterpret_cast<const float4*>(buf + base + (size_t)l * nxh + 2 * w2);
+    for (int q = 0; q < PAIRS / nthr; ++q) {
+        const int p = threadIdx.x + q * nthr, l = p / (W / 2), c2 = p % (W / 2);
+        tile4[p] = *reinterpret_cast<const float4*>(buf + base + (size_t)l * nxh + 2 * c2);
     }
     __syncthreads();
-    const int w = threadIdx.x & (kLines - 1), t = threadIdx.x / kLines;
-    line_fft<L, SIGN, L, LayoutCol>(tile, w, t, s_tw);
+    const int g = threadIdx.x / gthr, lt = threadIdx.x % gthr;
+    const int w = lt & (kLines - 1), t = lt / kLines;
+    line_fft<L, SIGN, L, Lay>(tile + kLines * g, w, t, s_tw);
+    float2* out;
     if (peers.n) {
         // plane z = blockIdx.y of the pencil belongs to rank z >> lg_planes; its receive buffer is laid out
         // [source rank][local plane][y][kx in the source's pencil] (what the inverse x pass unpacks)
         const unsigned z = blockIdx.y, dest = z >> lg_planes, zl = z & ((1u << lg_planes) - 1);
-        float2* out = peers.ptr[dest] + (((size_t)peers.rank << lg_planes) + zl) * L * nxh + (size_t)blockIdx.x * kLines;
-#pragma unroll
-        for (int q = 0; q < kE / 2; ++q) {
-            const int p = threadIdx.x + q * nthr, l = p / (kLines / 2), w2 = p % (kLines / 2);
-            *reinterpret_cast<float4*>(out + (size_t)l * nxh + 2 * w2) = tile4[p];
-        }
-        return;
+        out = peers.ptr[dest] + (((size_t)peers.rank << lg_planes) + zl) * L * nxh + (size_t)blockIdx.x * W;
+    } else {
+        out = buf + base;
     }
 #pragma unroll
-    for (int q = 0; q < kE / 2; ++q) {
-        const int p = threadIdx.x + q * nthr, l = p / (kLines / 2), w2 = p % (kLines / 2);
-        *reinterpret_cast<float4*>(buf + base + (size_t)l * nxh + 2 * w2) = tile4[p];
+    for (int q = 0; q < PAIRS / nthr; ++q) {
+        const int p = threadIdx.x + q * nthr, l = p / (W / 2), c2 = p % (W / 2);
+        *reinterpret_cast<float4*>(out + (size_t)l * nxh + 2 * c2) = tile4[p];
     }
 }
 
