@@ -131,7 +131,7 @@ class MeshSlabStep(MeshStep):
     particle number, every rank owns the particles of its slab."""
     launches_per_step = 16      # p2p: spread, 2 pushes + 2 scalar pushes, 4 barriers, x/y fwd, z fused, y/x inv, grid step, gather
 
-    def __init__(self, w, ops, torch, comm, period=32, mode="p2p"):
+    def __init__(self, w, ops, torch, comm, period=32, mode="p2p", sync="barrier"):
         from metadynamics_plugin_b200 import sharded
         self.comm_mode = mode
         self.ops, self.torch, self.w = ops, torch, w
@@ -166,7 +166,8 @@ class MeshSlabStep(MeshStep):
         self.period = period
         self.mesh.set(0, period)
         if mode == "p2p":
-            self.mesh.set(4, 1)         # the whole sharded step (incl. the flag barriers) replays from one CUDA graph
+            self.mesh.set(5, 1 if sync == "fused" else 0)
+            self.mesh.set(4, 1)         # the whole sharded step (incl. the inter-rank waits) replays from one CUDA graph
         self.d_force = torch.empty_like(self.d_pt)
         self.t = 0
         cv = self.slab.compute_cv(self.d_pt, self.N_global, self.box).cpu().item()
@@ -248,7 +249,7 @@ def run_ours(args):
         from metadynamics_plugin_b200 import sharded
         comm = sharded.TorchComm()
     if w["kind"] == "mesh":
-        runner = MeshStep(w, ops, torch) if world == 1 else MeshSlabStep(w, ops, torch, comm, mode=args.comm)
+        runner = MeshStep(w, ops, torch) if world == 1 else MeshSlabStep(w, ops, torch, comm, mode=args.comm, sync=args.p2p_sync)
     else:
         runner = LamellarStep(w, ops, torch, comm)
 
@@ -498,6 +499,8 @@ def main():
     ap.add_argument("--workload", default="C4", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"], help="multi-GPU mesh path: peer memory (default) or NCCL collectives")
+    ap.add_argument("--p2p-sync", default="barrier", choices=["fused", "barrier"],
+                    help="peer-memory mode: separate barrier launches (default, measured faster) or inter-rank signal/wait inside the kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     args = ap.parse_args()

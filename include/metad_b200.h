@@ -166,7 +166,9 @@ int metad_mesh_get(metad_mesh* p, int which, void* h_out);
  *        key 3 = record the cell index of every particle for metad_mesh_get(0)
  *        key 4 = CUDA-graph replay: everything metad_mesh_cv / metad_mesh_slab_p2p_cv enqueue after the tile-order
  *                decision is captured once per argument signature (pointers, N, box, stream) and replayed with one launch
- *                (metad_mesh_get(p, 7, unsigned long long*) = replays so far)                                           */
+ *                (metad_mesh_get(p, 7, unsigned long long*) = replays so far)
+ *        key 5 = peer-memory mode: 1 folds the inter-rank signal / wait into the producer / consumer kernels, 0 (default,
+ *                measured faster) uses separate barrier launches                                                        */
 int metad_mesh_set(metad_mesh* p, int key, long value);
 
 /* ------------------------------------------------------------------------------------------------

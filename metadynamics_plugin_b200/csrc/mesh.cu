@@ -83,6 +83,12 @@ struct metad_mesh {
     bool peers_mapped[p2p::kMaxPeers] = {};     // opened with cudaIpcOpenMemHandle (to be closed)
     bool p2p_ready = false;
     unsigned* d_epoch = nullptr;                // barrier epoch (device-side counter: launches can be replayed from a graph)
+    bool last_cv_fused = false;                 // the last metad_mesh_slab_p2p_cv published phase 3 for the gather to wait on
+    // signal / wait folded into the producer / consumer kernels instead of barrier launches (knob 5).  Off by default:
+    // measured slower on B200 (2 GPUs, C4: 0.506 vs 0.464 ms/step) -- every producer CTA has to fence its peer stores at
+    // system scope before taking the ticket, which stalls the CTA tails that otherwise drain asynchronously.
+    bool fused_sync = false;
+    unsigned* d_sync = nullptr;                 // [4] phase epochs + [4] CTA tickets of the fused synchronisation
     // CUDA-graph replay of the per-call kernel sequence (metad_mesh_set key 4): everything a call enqueues after the
     // (eager) tile-order decision is captured once per argument signature and replayed with one launch
     bool graph_mode = false;
@@ -139,7 +145,11 @@ template <class K> int set_smem(K kernel, size_t bytes) {
 // the forward pass / input of the inverse pass), [part][row][kx in part] with parts of width kxl.
 // Forward: consumes (and clears) the integer density; d_sums = (global) sums, d_ghost = received halo planes (slab).
 template <int LC> int run_x(metad_mesh* p, bool inverse, float2* io, const double* d_sums, const int* d_ghost, cudaStream_t st,
-                            const PeerOut* peer_out = nullptr) {
+                            const PeerOut* peer_out = nullptr, const PeerSync* sync = nullptr, const double* table = nullptr,
+                            double* d_out = nullptr) {
+    PeerSync ps;
+    memset(&ps, 0, sizeof ps);
+    if (sync) ps = *sync;
     const size_t smem = sizeof(float2) * (LayoutRow::size(LC) + 2 * LC);
     const unsigned rows = p->g.ny * p->g.nz;
     float2* buf = reinterpret_cast<float2*>(p->d_buf);
@@ -153,11 +163,13 @@ template <int LC> int run_x(metad_mesh* p, bool inverse, float2* io, const doubl
         in.inv_cells = 1.0 / ((double)p->g.nx * (double)p->g.ny * (double)p->nzg);
         in.ghost = reinterpret_cast<const int2*>(d_ghost);
         in.lgy = p->g.lgy; in.nz = p->g.nz;
+        in.sums_table = sync ? table : nullptr;
+        in.sums_out = d_out;
         in.rho_keep = p->keep_rho ? reinterpret_cast<float2*>(p->d_rho_keep) : nullptr;
         PeerOut po;
         memset(&po, 0, sizeof po);
         if (peer_out) po = *peer_out;
-        fft_x_fwd_kernel<LC><<<rows / kLines, kLines * LC / kE, smem, st>>>(in, p->d_twx, io ? io : buf, lg_part, rows, po);
+        fft_x_fwd_kernel<LC><<<rows / kLines, kLines * LC / kE, smem, st>>>(in, p->d_twx, io ? io : buf, lg_part, rows, po, ps);
         METAD_LAUNCH_CHECK();
         // the accumulator is empty again for the next spread (a plain memset runs at the full write bandwidth); in
         // peer-memory mode the two ghost planes (already pushed to the neighbours) are cleared by the same memset
@@ -165,14 +177,17 @@ template <int LC> int run_x(metad_mesh* p, bool inverse, float2* io, const doubl
         else METAD_CUDA(cudaMemsetAsync(p->d_mesh_i, 0, sizeof(int) * p->M(), st));
     } else {
         int rc = set_smem(fft_x_inv_kernel<LC>, smem); if (rc) return rc;
-        fft_x_inv_kernel<LC><<<rows / kLines, kLines * LC / kE, smem, st>>>(buf, p->d_twx, io ? io : buf, lg_part, rows);
+        fft_x_inv_kernel<LC><<<rows / kLines, kLines * LC / kE, smem, st>>>(buf, p->d_twx, io ? io : buf, lg_part, rows, ps, sync ? table : nullptr, d_out);
     }
     METAD_LAUNCH_CHECK();
     return METAD_OK;
 }
 // y pass on buf = [nz_rows][ny][row_len]
 template <int L> int run_y(metad_mesh* p, bool inverse, float2* buf, unsigned row_len, unsigned nz_rows, cudaStream_t st,
-                           const PeerOut* peer_out = nullptr) {
+                           const PeerOut* peer_out = nullptr, const PeerSync* sync = nullptr) {
+    PeerSync ps;
+    memset(&ps, 0, sizeof ps);
+    if (sync) ps = *sync;
     PeerOut po;
     memset(&po, 0, sizeof po);
     if (peer_out) po = *peer_out;
@@ -186,20 +201,20 @@ template <int L> int run_y(metad_mesh* p, bool inverse, float2* buf, unsigned ro
         dim3 grid(row_len / (G * kLines), nz_rows);
         if (!inverse) {
             int rc = set_smem(fft_y_kernel<L, -1, G>, smem); if (rc) return rc;
-            fft_y_kernel<L, -1, G><<<grid, G * kLines * L / kE, smem, st>>>(buf, p->d_twy, row_len, po, lg_planes);
+            fft_y_kernel<L, -1, G><<<grid, G * kLines * L / kE, smem, st>>>(buf, p->d_twy, row_len, po, lg_planes, ps);
         } else {
             int rc = set_smem(fft_y_kernel<L, +1, G>, smem); if (rc) return rc;
-            fft_y_kernel<L, +1, G><<<grid, G * kLines * L / kE, smem, st>>>(buf, p->d_twy, row_len, po, lg_planes);
+            fft_y_kernel<L, +1, G><<<grid, G * kLines * L / kE, smem, st>>>(buf, p->d_twy, row_len, po, lg_planes, ps);
         }
     } else {
         const size_t smem = sizeof(float2) * (LayoutColWide<1>::size(L) + L);
         dim3 grid(row_len / kLines, nz_rows);
         if (!inverse) {
             int rc = set_smem(fft_y_kernel<L, -1, 1>, smem); if (rc) return rc;
-            fft_y_kernel<L, -1, 1><<<grid, kLines * L / kE, smem, st>>>(buf, p->d_twy, row_len, po, lg_planes);
+            fft_y_kernel<L, -1, 1><<<grid, kLines * L / kE, smem, st>>>(buf, p->d_twy, row_len, po, lg_planes, ps);
         } else {
             int rc = set_smem(fft_y_kernel<L, +1, 1>, smem); if (rc) return rc;
-            fft_y_kernel<L, +1, 1><<<grid, kLines * L / kE, smem, st>>>(buf, p->d_twy, row_len, po, lg_planes);
+            fft_y_kernel<L, +1, 1><<<grid, kLines * L / kE, smem, st>>>(buf, p->d_twy, row_len, po, lg_planes, ps);
         }
     }
     METAD_LAUNCH_CHECK();
@@ -207,7 +222,7 @@ template <int L> int run_y(metad_mesh* p, bool inverse, float2* buf, unsigned ro
 }
 // fused z pass on buf = [nzg][ny][row_len]; d_sums: (global) sum a^2; d_cv receives 0.5 * (local) energy sum
 template <int L> int run_z(metad_mesh* p, float2* buf, unsigned row_len, unsigned kx_off, const double* d_sums, unsigned N_global,
-                           double* d_cv, cudaStream_t st) {
+                           double* d_cv, cudaStream_t st, bool publish_cv = false) {
     const size_t smem = sizeof(float2) * (LayoutCol::size(L) + L);
     const unsigned ny = p->g.ny;
     ConvParams cp;
@@ -220,6 +235,12 @@ template <int L> int run_z(metad_mesh* p, float2* buf, unsigned row_len, unsigne
     cp.ticket = p->d_ticket;
     cp.n_blocks_plane0 = kx_off == 0 ? (ny / 2 + 1 + kLines / 2 - 1) / (kLines / 2) : 0;
     cp.d_cv = d_cv;
+    memset(cp.cv_arena, 0, sizeof cp.cv_arena);
+    cp.cv_off = 0; cp.cv_n = 0; cp.cv_rank = 0;
+    if (publish_cv) {
+        for (unsigned r = 0; r < p->n_ranks; ++r) cp.cv_arena[r] = p->peers.arena[r];
+        cp.cv_off = p->lay.cv; cp.cv_n = p->n_ranks; cp.cv_rank = p->rank;
+    }
     int rc = set_smem(fft_z_fused_kernel<L>, smem); if (rc) return rc;
     const unsigned nblocks = cp.n_blocks_plane0 + (row_len / kLines) * ny;
     fft_z_fused_kernel<L><<<nblocks, kLines * L / kE, smem, st>>>(buf, p->d_twz, cp);
@@ -439,7 +460,10 @@ metad_mesh::GraphKey make_key(metad_mesh* p, const void* postype, unsigned N, un
 }
 
 int launch_gather(metad_mesh* p, const float* d_postype, const float* d_ghost, float* d_force, unsigned N_global, const metad_box* box,
-                  const double* d_bias, cudaStream_t stream) {
+                  const double* d_bias, cudaStream_t stream, const PeerSync* sync = nullptr) {
+    PeerSync ps;
+    memset(&ps, 0, sizeof ps);
+    if (sync) ps = *sync;
     const Geom& g = p->g;
     // reciprocal lattice vectors of the (orthorhombic) box without 2 pi, times the mesh dimensions (:761-769, :852-854)
     ForceParams fp;
@@ -453,11 +477,11 @@ int launch_gather(metad_mesh* p, const float* d_postype, const float* d_ghost, f
         rc = set_smem(mesh_gather_kernel<4>, gather_smem_bytes<4>()); if (rc) return rc;
         mesh_gather_kernel<4><<<num_tiles(g), kGatherThreads, gather_smem_bytes<4>(), stream>>>((const float4*)d_postype, p->d_tstart,
                                                                                            p->d_cache4, p->d_cache_code, g, p->d_buf, d_ghost, fp, d_bias,
-                                                                                           (float4*)d_force);
+                                                                                           (float4*)d_force, ps);
     } else {
         mesh_gather_kernel<3><<<num_tiles(g), kGatherThreads, gather_smem_bytes<3>(), stream>>>((const float4*)d_postype, p->d_tstart,
                                                                                            p->d_cache4, p->d_cache_code, g, p->d_buf, d_ghost, fp, d_bias,
-                                                                                           (float4*)d_force);
+                                                                                           (float4*)d_force, ps);
     }
     METAD_LAUNCH_CHECK();
     return mark(p, 9, stream);
@@ -537,6 +561,8 @@ int create_common(metad_mesh** out, unsigned nx, unsigned ny, unsigned nzg, unsi
     TRY(cudaMemset(p->d_p2p_status, 0, sizeof(unsigned)));
     TRY(cudaMalloc(&p->d_epoch, sizeof(unsigned)));
     TRY(cudaMemset(p->d_epoch, 0, sizeof(unsigned)));
+    TRY(cudaMalloc(&p->d_sync, sizeof(unsigned) * 8));
+    TRY(cudaMemset(p->d_sync, 0, sizeof(unsigned) * 8));
 #undef TRY
     if (rc == METAD_OK) {
         memset(p->h_counters, 0, sizeof(unsigned) * 4);
@@ -570,7 +596,7 @@ extern "C" int metad_mesh_destroy(metad_mesh* p) {
     if (p->h_counters) cudaFreeHost(p->h_counters);
     cudaFree(p->d_rho_keep); cudaFree(p->d_twx); cudaFree(p->d_twy); cudaFree(p->d_twz); cudaFree(p->d_sums);
     cudaFree(p->d_partials); cudaFree(p->d_ticket);
-    cudaFree(p->d_sums_global); cudaFree(p->d_cv_partial); cudaFree(p->d_p2p_status); cudaFree(p->d_epoch);
+    cudaFree(p->d_sums_global); cudaFree(p->d_cv_partial); cudaFree(p->d_p2p_status); cudaFree(p->d_epoch); cudaFree(p->d_sync);
     if (p->gexec) cudaGraphExecDestroy(p->gexec);
     if (p->capture_stream) cudaStreamDestroy(p->capture_stream);
     for (unsigned r = 0; r < p2p::kMaxPeers; ++r)
@@ -705,13 +731,27 @@ int ensure_arena(metad_mesh* p) {
 }
 
 int p2p_barrier(metad_mesh* p, int wait, p2p::Publish pub, p2p::Reduce red, cudaStream_t st) {
-    p2p::barrier_kernel<<<1, 32, 0, st>>>(p->peers, p->lay.flags, p->d_epoch, wait, pub, red, p->d_p2p_status);
+    p2p::barrier_kernel<<<1, 32, 0, st>>>(p->peers, p->lay.flags + 4 * p2p::kMaxPeers * sizeof(unsigned), p->d_epoch, wait, pub, red,
+                                           p->d_p2p_status);
     METAD_LAUNCH_CHECK();
     return METAD_OK;
 }
 
+PeerSync make_sync(metad_mesh* p, int wait_k, int signal_k) {
+    PeerSync ps;
+    memset(&ps, 0, sizeof ps);
+    for (unsigned r = 0; r < p->n_ranks; ++r) ps.arena[r] = p->peers.arena[r];
+    ps.n = p->n_ranks; ps.rank = p->rank;
+    ps.flags_off = p->lay.flags;
+    ps.d_epoch = p->d_sync; ps.ticket = p->d_sync + 4;
+    ps.status = p->d_p2p_status;
+    ps.wait_k = wait_k; ps.signal_k = signal_k;
+    return ps;
+}
+
 int p2p_stage(metad_mesh* p, int stage, int wait, const float* d_postype, unsigned N_local, unsigned N_global, const metad_box* box,
               double* d_cv, cudaStream_t st) {
+    const bool fused = wait && p->fused_sync;      // signal / wait inside the kernels instead of barrier launches
     const Geom& g = p->g;
     const size_t plane = (size_t)g.nx * g.ny;
     const unsigned P = p->n_ranks, r = p->rank, down = (r + P - 1) % P, up = (r + 1) % P;
@@ -732,7 +772,13 @@ int p2p_stage(metad_mesh* p, int stage, int wait, const float* d_postype, unsign
             job.dst[1] = (int4*)(gd + plane * sizeof(int)); job.src[1] = (const int4*)(p->d_fx + 4); job.n16[1] = 1;
             job.dst[2] = (int4*)gu; job.src[2] = (const int4*)above; job.n16[2] = (unsigned)(plane * sizeof(int) / 16);
             job.dst[3] = (int4*)(gu + plane * sizeof(int)); job.src[3] = (const int4*)(p->d_fx + 4); job.n16[3] = 1;
-            p2p::push_kernel<<<32, 256, 0, st>>>(job);
+            if (fused) {
+                p2p::push_kernel<<<32, 256, 0, st>>>(job, p2p::Publish{p->d_sums, p->lay.sums, 4, 3}, make_sync(p, -1, 0));
+            } else {
+                PeerSync none;
+                memset(&none, 0, sizeof none);
+                p2p::push_kernel<<<32, 256, 0, st>>>(job, p2p::Publish{nullptr, 0, 0, 0}, none);
+            }
             METAD_LAUNCH_CHECK();
             if (!wait) {    // emulation: the partial sums must be in place before ANY rank reduces them in stage 1
                 p2p::push_scalars_kernel<<<1, 64, 0, st>>>(p->peers, p->lay.sums, 4, p->d_sums, 3);
@@ -741,26 +787,44 @@ int p2p_stage(metad_mesh* p, int stage, int wait, const float* d_postype, unsign
             return METAD_OK;
         }
         case 1: {   // [barrier: halos and sums have arrived] x forward pass, every kx pencil stored into its owner's memory
-            rc = p2p_barrier(p, wait, p2p::Publish{p->d_sums, p->lay.sums, 4, wait ? 3u : 0u},
-                             p2p::Reduce{(const double*)(mine + p->lay.sums), 4, 3, p->d_sums_global}, st);
-            if (rc) return rc;
+            if (!fused) {
+                rc = p2p_barrier(p, wait, p2p::Publish{p->d_sums, p->lay.sums, 4, wait ? 3u : 0u},
+                                 p2p::Reduce{(const double*)(mine + p->lay.sums), 4, 3, p->d_sums_global}, st);
+                if (rc) return rc;
+            }
             if (p->keep_rho && !p->d_rho_keep) METAD_CUDA(cudaMalloc(&p->d_rho_keep, sizeof(float) * p->M()));
             PeerOut po;
             memset(&po, 0, sizeof po);
             po.n = P; po.rank = r;
             for (unsigned q = 0; q < P; ++q) po.ptr[q] = (float2*)(p->peers.arena[q] + p->lay.pencil);
-            METAD_DISPATCH_LEN(g.nx / 2, (run_x<LL>(p, false, nullptr, p->d_sums_global, (const int*)(mine + p->lay.ghost_rho), st, &po)));
+            if (fused) {
+                const PeerSync ps = make_sync(p, 0, 1);
+                METAD_DISPATCH_LEN(g.nx / 2, (run_x<LL>(p, false, nullptr, p->d_sums_global, (const int*)(mine + p->lay.ghost_rho), st, &po, &ps,
+                                                        (const double*)(mine + p->lay.sums), p->d_sums_global)));
+            } else {
+                METAD_DISPATCH_LEN(g.nx / 2, (run_x<LL>(p, false, nullptr, p->d_sums_global, (const int*)(mine + p->lay.ghost_rho), st, &po)));
+            }
             return rc;
         }
         case 2: {   // [barrier: the pencil is complete] y, fused z, inverse y with every plane stored into its owner's memory
-            rc = p2p_barrier(p, wait, p2p::Publish{nullptr, 0, 0, 0}, p2p::Reduce{nullptr, 0, 0, nullptr}, st); if (rc) return rc;
             float2* pen = (float2*)(mine + p->lay.pencil);
-            METAD_DISPATCH_LEN(g.ny, (run_y<LL>(p, false, pen, p->kxl, p->nzg, st))); if (rc) return rc;
-            METAD_DISPATCH_LEN(p->nzg, (run_z<LL>(p, pen, p->kxl, r * p->kxl, p->d_sums_global, N_global, p->d_cv_partial, st))); if (rc) return rc;
+            if (fused) {
+                const PeerSync ps = make_sync(p, 1, -1);
+                METAD_DISPATCH_LEN(g.ny, (run_y<LL>(p, false, pen, p->kxl, p->nzg, st, nullptr, &ps))); if (rc) return rc;
+            } else {
+                rc = p2p_barrier(p, wait, p2p::Publish{nullptr, 0, 0, 0}, p2p::Reduce{nullptr, 0, 0, nullptr}, st); if (rc) return rc;
+                METAD_DISPATCH_LEN(g.ny, (run_y<LL>(p, false, pen, p->kxl, p->nzg, st))); if (rc) return rc;
+            }
+            METAD_DISPATCH_LEN(p->nzg, (run_z<LL>(p, pen, p->kxl, r * p->kxl, p->d_sums_global, N_global, p->d_cv_partial, st, fused))); if (rc) return rc;
             PeerOut po;
             memset(&po, 0, sizeof po);
             po.n = P; po.rank = r;
             for (unsigned q = 0; q < P; ++q) po.ptr[q] = (float2*)(p->peers.arena[q] + p->lay.recv);
+            if (fused) {
+                const PeerSync ps = make_sync(p, -1, 2);
+                METAD_DISPATCH_LEN(g.ny, (run_y<LL>(p, true, pen, p->kxl, p->nzg, st, &po, &ps))); if (rc) return rc;
+                return METAD_OK;
+            }
             METAD_DISPATCH_LEN(g.ny, (run_y<LL>(p, true, pen, p->kxl, p->nzg, st, &po))); if (rc) return rc;
             if (!wait) {    // emulation: see stage 0
                 p2p::push_scalars_kernel<<<1, 64, 0, st>>>(p->peers, p->lay.cv, 1, p->d_cv_partial, 1);
@@ -769,10 +833,17 @@ int p2p_stage(metad_mesh* p, int stage, int wait, const float* d_postype, unsign
             return METAD_OK;
         }
         case 3: {   // [barrier: planes and CV partials have arrived] CV, inverse x pass, halo planes of Re IFFT(G) to the neighbours
-            rc = p2p_barrier(p, wait, p2p::Publish{p->d_cv_partial, p->lay.cv, 1, wait ? 1u : 0u},
-                             p2p::Reduce{(const double*)(mine + p->lay.cv), 1, 1, d_cv}, st);
-            if (rc) return rc;
-            METAD_DISPATCH_LEN(g.nx / 2, (run_x<LL>(p, true, (float2*)(mine + p->lay.recv), nullptr, nullptr, st))); if (rc) return rc;
+            if (fused) {
+                const PeerSync ps = make_sync(p, 2, -1);
+                METAD_DISPATCH_LEN(g.nx / 2, (run_x<LL>(p, true, (float2*)(mine + p->lay.recv), nullptr, nullptr, st, nullptr, &ps,
+                                                        (const double*)(mine + p->lay.cv), d_cv)));
+                if (rc) return rc;
+            } else {
+                rc = p2p_barrier(p, wait, p2p::Publish{p->d_cv_partial, p->lay.cv, 1, wait ? 1u : 0u},
+                                 p2p::Reduce{(const double*)(mine + p->lay.cv), 1, 1, d_cv}, st);
+                if (rc) return rc;
+                METAD_DISPATCH_LEN(g.nx / 2, (run_x<LL>(p, true, (float2*)(mine + p->lay.recv), nullptr, nullptr, st))); if (rc) return rc;
+            }
             p2p::PushJob job;
             memset(&job, 0, sizeof job);
             // my first plane is the lower rank's plane z0+nz (its ghost [1]); my last plane the upper rank's plane z0-1 (ghost [0])
@@ -780,11 +851,18 @@ int p2p_stage(metad_mesh* p, int stage, int wait, const float* d_postype, unsign
             job.src[0] = (const int4*)p->d_buf; job.n16[0] = (unsigned)(plane * sizeof(float) / 16);
             job.dst[1] = (int4*)(p->peers.arena[up] + p->lay.ghost_inv);
             job.src[1] = (const int4*)(p->d_buf + plane * (g.nz - 1)); job.n16[1] = (unsigned)(plane * sizeof(float) / 16);
-            p2p::push_kernel<<<32, 256, 0, st>>>(job);
+            if (fused) {
+                p2p::push_kernel<<<32, 256, 0, st>>>(job, p2p::Publish{nullptr, 0, 0, 0}, make_sync(p, -1, 3));
+            } else {
+                PeerSync none;
+                memset(&none, 0, sizeof none);
+                p2p::push_kernel<<<32, 256, 0, st>>>(job, p2p::Publish{nullptr, 0, 0, 0}, none);
+            }
             METAD_LAUNCH_CHECK();
             return METAD_OK;
         }
-        case 4:     // [barrier: the halo planes of Re IFFT(G) have arrived]
+        case 4:     // [barrier: the halo planes of Re IFFT(G) have arrived]; fused mode: the gather waits for phase 3 itself
+            if (fused) return METAD_OK;
             rc = p2p_barrier(p, wait, p2p::Publish{nullptr, 0, 0, 0}, p2p::Reduce{nullptr, 0, 0, nullptr}, st); if (rc) return rc;
             return METAD_OK;
         default:
@@ -850,10 +928,10 @@ extern "C" int metad_mesh_slab_p2p_cv(metad_mesh* p, const float* d_postype, uns
     }
     if (stage >= 0) {
         const int rc = p2p_stage(p, stage, 0, d_postype, N_local, N_global, box, d_cv, stream);
-        if (rc == METAD_OK && stage == 4) p->have_cv = true;
+        if (rc == METAD_OK && stage == 4) { p->have_cv = true; p->last_cv_fused = false; }
         return rc;
     }
-    const int rc = run_captured(p, make_key(p, d_postype, N_local, N_global, box, d_cv, stream, 1), stream, [&](cudaStream_t st) -> int {
+    const int rc = run_captured(p, make_key(p, d_postype, N_local, N_global, box, d_cv, stream, p->fused_sync ? 2 : 1), stream, [&](cudaStream_t st) -> int {
         for (int s = 0; s <= 4; ++s) {
             const int r = p2p_stage(p, s, 1, d_postype, N_local, N_global, box, d_cv, st);
             if (r) return r;
@@ -862,6 +940,7 @@ extern "C" int metad_mesh_slab_p2p_cv(metad_mesh* p, const float* d_postype, uns
     });
     if (rc) return rc;
     p->have_cv = true;
+    p->last_cv_fused = p->fused_sync;
     return METAD_OK;
 }
 
@@ -875,6 +954,10 @@ extern "C" int metad_mesh_slab_p2p_forces(metad_mesh* p, const float* d_postype,
     }
     if (N_local == 0) return METAD_OK;
     METAD_REQUIRE(d_postype && d_force, "metad_mesh_slab_p2p_forces: null particle arrays");
+    if (p->last_cv_fused) {
+        const PeerSync ps = make_sync(p, 3, -1);
+        return launch_gather(p, d_postype, (const float*)(p->arena + p->lay.ghost_inv), d_force, N_global, box, d_bias, stream, &ps);
+    }
     return launch_gather(p, d_postype, (const float*)(p->arena + p->lay.ghost_inv), d_force, N_global, box, d_bias, stream);
 }
 
@@ -952,6 +1035,7 @@ extern "C" int metad_mesh_set(metad_mesh* p, int key, long value) {
         case 2: p->profile = value != 0; return METAD_OK;
         case 3: p->keep_cells = value != 0; return METAD_OK;
         case 4: p->graph_mode = value != 0; return METAD_OK;
+        case 5: p->fused_sync = value != 0; return METAD_OK;
         default: set_error("metad_mesh_set: unknown key"); return METAD_ERR_INVALID;
     }
 }

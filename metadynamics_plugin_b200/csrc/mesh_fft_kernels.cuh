@@ -22,6 +22,8 @@
 namespace metad {
 namespace fft {
 
+constexpr int kMaxPeers = 8;
+
 struct ConvParams {
     unsigned nx, ny, nz;          // GLOBAL mesh dimensions
     unsigned row_len;             // complex elements per (z,y) row of the buffer: nx/2, or the kx pencil width when sharded
@@ -33,6 +35,10 @@ struct ConvParams {
     unsigned* ticket;
     unsigned n_blocks_plane0;     // plane0 blocks write partials[0 .. n_blocks_plane0)
     double* d_cv;                 // device output: CV
+    // fused peer mode: the last block also stores the partial into slot [rank] of every rank's CV table
+    char* cv_arena[kMaxPeers];
+    size_t cv_off;
+    unsigned cv_n, cv_rank;
 };
 
 // chi for one dimension: [k < ceil(n/2)] (non-negative Miller index), OrderParameterMesh.cc:417-422
@@ -90,12 +96,66 @@ template <int TWL> __device__ __forceinline__ void load_twiddles(float2* s_tw, c
 // separate collective -- the x forward pass stores every kx pencil straight into the owning rank's pencil buffer, and the
 // inverse y pass stores every plane straight into the owning rank's receive buffer (P2P stores over NVLink, overlapped
 // with the transform of the other tiles).  n == 0: single buffer (unsharded, or staged for a library all-to-all).
-constexpr int kMaxPeers = 8;
 struct PeerOut {
     float2* ptr[kMaxPeers];   // ptr[r] = destination buffer in rank r's memory
     unsigned n;               // number of ranks (0 = not used)
     unsigned rank;            // this rank
 };
+
+// Fused inter-rank synchronisation (peer-memory mode): instead of separate barrier launches, the LAST CTA of a producer
+// kernel publishes "rank r has finished phase k" in every peer's flag table (release at system scope, after all CTAs of
+// the kernel fenced their peer stores), and every CTA of the consumer kernel starts by waiting until all ranks have
+// published phase k (acquire).  Epochs are device-side counters, so the kernels replay from a CUDA graph.  Phases:
+// 0 halos + partial sums pushed, 1 pencils stored (x forward), 2 planes + CV partials stored (y inverse), 3 halo planes
+// of Re IFFT(G) pushed.  n == 0: no synchronisation (single GPU, staged path, single-process emulation).
+struct PeerSync {
+    char* arena[kMaxPeers];
+    unsigned n, rank;
+    size_t flags_off;          // unsigned flags[4][kMaxPeers] in every arena
+    unsigned* d_epoch;         // [4] phases completed by THIS rank
+    unsigned* ticket;          // [4] CTA tickets of the producer kernels
+    unsigned* status;          // [0] set if a wait timed out
+    int wait_k, signal_k;      // phase this kernel waits for / publishes (-1: none)
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ void peer_wait(const PeerSync& ps) {
+    if (ps.n == 0 || ps.wait_k < 0) return;
+    if (threadIdx.x < ps.n) {
+        const unsigned epoch = *(volatile unsigned*)(ps.d_epoch + ps.wait_k);
+        const unsigned* flag = reinterpret_cast<const unsigned*>(ps.arena[ps.rank] + ps.flags_off) + ps.wait_k * kMaxPeers + threadIdx.x;
+        const long long t0 = clock64();
+        unsigned v;
+        do {        // relaxed polling (every CTA of the kernel does this), one acquire fence once the flag is there
+            asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            if ((int)(v - epoch) >= 0) break;
+            if (clock64() - t0 > 8000000000LL) { atomicExch(ps.status, 1u); break; }
+            __nanosleep(32);
+        } while (true);
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
+    }
+    __syncthreads();
+}
+// call at the very end of a producer kernel, by all threads of every CTA
+__device__ __forceinline__ void peer_signal(const PeerSync& ps) {
+    if (ps.n == 0 || ps.signal_k < 0) return;
+    __shared__ bool last_cta;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();                                 // this CTA's peer stores, made visible before the ticket
+        last_cta = atomicAdd(ps.ticket + ps.signal_k, 1u) == gridDim.x * gridDim.y - 1;
+    }
+    __syncthreads();
+    if (!last_cta) return;
+    const unsigned epoch = *(volatile unsigned*)(ps.d_epoch + ps.signal_k) + 1u;
+    __threadfence_system();
+    if (threadIdx.x < ps.n) {
+        unsigned* flag = reinterpret_cast<unsigned*>(ps.arena[threadIdx.x] + ps.flags_off) + ps.signal_k * kMaxPeers + ps.rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { ps.d_epoch[ps.signal_k] = epoch; ps.ticket[ps.signal_k] = 0; }
+}
+#endif
 
 struct DensityIn {
     const int2* mesh;       // integer density of the local planes, row-major [z][y][x] (the caller clears it afterwards)
@@ -105,6 +165,8 @@ struct DensityIn {
     const int2* ghost;      // z slab: the two halo messages received from the neighbours, each ny*nx ints of fixed-point density
                             // followed by 4 ints of which the first holds the bits of the sender's 1/scale; message [0] is
                             // added to the first local plane, [1] to the last; nullptr if unsharded
+    const double* sums_table;   // fused peer mode: per-rank {sum a^2, sum a, outside, -} rows of this rank's arena (else nullptr)
+    double* sums_out;           //   ... block 0 stores the rank-ordered totals here for the later sweeps
     unsigned lgy, nz;       // log2(ny), local planes
     float2* rho_keep;       // optional: float copy of the density (before the mean is removed), or nullptr
 };
@@ -115,7 +177,8 @@ MHD float2 density_to_float(int2 v, float inv_scale) { return make_float2((float
 template <int LC>
 __global__ void __launch_bounds__(kLines * LC / kE)
 fft_x_fwd_kernel(DensityIn in, const float2* __restrict__ g_tw /* length 2*LC */, float2* out,
-                 unsigned lg_part /* log2 of the kx pencil width */, unsigned rows_total, const __grid_constant__ PeerOut peers) {
+                 unsigned lg_part /* log2 of the kx pencil width */, unsigned rows_total, const __grid_constant__ PeerOut peers,
+                 const __grid_constant__ PeerSync sync) {
     // lg_part = log2(LC): out is the plain [row][kx] buffer.  Sharded: out = send buffer laid out [part][row][kx in part],
     // i.e. already packed for the slab -> pencil all-to-all.
     extern __shared__ float2 smem[];
@@ -124,8 +187,22 @@ fft_x_fwd_kernel(DensityIn in, const float2* __restrict__ g_tw /* length 2*LC */
     const int nthr = kLines * LC / kE;
     const size_t row0 = (size_t)blockIdx.x * kLines;
     load_twiddles<2 * LC>(s_tw, g_tw);
+    peer_wait(sync);                                         // halos and partial sums of every rank have arrived
     const float inv_scale = __ldg(in.d_fx + 1);
-    const float mean = (float)(in.d_sums[1] * in.inv_cells);
+    __shared__ double s_sum_a;
+    if (threadIdx.x == 0) {
+        if (in.sums_table) {                                 // rank-ordered totals (identical on every rank)
+            double tot[3] = {0.0, 0.0, 0.0};
+            for (unsigned r = 0; r < sync.n; ++r)
+                for (int k = 0; k < 3; ++k) tot[k] += in.sums_table[4 * r + k];
+            s_sum_a = tot[1];
+            if (blockIdx.x == 0) { in.sums_out[0] = tot[0]; in.sums_out[1] = tot[1]; in.sums_out[2] = tot[2]; }
+        } else {
+            s_sum_a = in.d_sums[1];
+        }
+    }
+    __syncthreads();
+    const float mean = (float)(s_sum_a * in.inv_cells);
     const unsigned ny = 1u << in.lgy;
     // 128-bit loads: kE/2 per thread, all issued before the first use
     int4 vin[kE / 2];
@@ -184,6 +261,7 @@ fft_x_fwd_kernel(DensityIn in, const float2* __restrict__ g_tw /* length 2*LC */
             const size_t dst = ((size_t)peers.rank * rows_total + (row0 + ww)) * part_len + (l & (part_len - 1));
             peers.ptr[l >> lg_part][dst] = tile[LayoutRow::addr(ww, l, LC)];
         }
+        peer_signal(sync);                                   // phase 1: my share of every pencil is stored
         return;
     }
     for (int idx = threadIdx.x; idx < kLines * LC; idx += nthr) {
@@ -197,7 +275,7 @@ fft_x_fwd_kernel(DensityIn in, const float2* __restrict__ g_tw /* length 2*LC */
 template <int LC>
 __global__ void __launch_bounds__(kLines * LC / kE)
 fft_x_inv_kernel(float2* buf, const float2* __restrict__ g_tw, const float2* in, unsigned lg_part,
-                 unsigned rows_total) {
+                 unsigned rows_total, const __grid_constant__ PeerSync sync, const double* cv_table, double* d_cv) {
     // in == buf, lg_part = log2(LC): plain in-place transform.  Sharded: in = receive buffer of the pencil -> slab
     // all-to-all, laid out [part][row][kx in part].
     extern __shared__ float2 smem[];
@@ -206,6 +284,12 @@ fft_x_inv_kernel(float2* buf, const float2* __restrict__ g_tw, const float2* in,
     const int nthr = kLines * LC / kE;
     const size_t row0 = (size_t)blockIdx.x * kLines;
     load_twiddles<2 * LC>(s_tw, g_tw);
+    peer_wait(sync);                                         // planes and CV partials of every rank have arrived
+    if (cv_table && blockIdx.x == 0 && threadIdx.x == 0) {   // the CV: rank-ordered sum of the partials
+        double cv = 0.0;
+        for (unsigned r = 0; r < sync.n; ++r) cv += __ldcv(cv_table + r);
+        *d_cv = cv;
+    }
     const unsigned part_len = 1u << lg_part;
     for (int idx = threadIdx.x; idx < kLines * LC; idx += nthr) {
         const int w = idx / LC, l = idx % LC;
@@ -237,7 +321,7 @@ fft_x_inv_kernel(float2* buf, const float2* __restrict__ g_tw, const float2* in,
 template <int L, int SIGN, int G>
 __global__ void __launch_bounds__(G * kLines * L / kE)
 fft_y_kernel(float2* __restrict__ buf, const float2* __restrict__ g_tw, unsigned nxh, const __grid_constant__ PeerOut peers,
-             unsigned lg_planes /* peers.n != 0: log2 of the planes per rank */) {
+             unsigned lg_planes /* peers.n != 0: log2 of the planes per rank */, const __grid_constant__ PeerSync sync) {
     extern __shared__ __align__(16) float2 smem[];
     using Lay = LayoutColWide<G>;
     constexpr int gthr = kLines * L / kE, nthr = G * gthr, W = kLines * G, PAIRS = W * L / 2;
@@ -245,6 +329,7 @@ fft_y_kernel(float2* __restrict__ buf, const float2* __restrict__ g_tw, unsigned
     float2* s_tw = smem + Lay::size(L);
     const size_t base = (size_t)blockIdx.y * L * nxh + (size_t)blockIdx.x * W;
     load_twiddles<L>(s_tw, g_tw);
+    peer_wait(sync);                                         // forward sweep: every rank's share of my pencil has arrived
     float4* tile4 = reinterpret_cast<float4*>(tile);
 #pragma unroll
     for (int q = 0; q < PAIRS / nthr; ++q) {
@@ -269,6 +354,7 @@ fft_y_kernel(float2* __restrict__ buf, const float2* __restrict__ g_tw, unsigned
         const int p = threadIdx.x + q * nthr, l = p / (W / 2), c2 = p % (W / 2);
         *reinterpret_cast<float4*>(out + (size_t)l * nxh + 2 * c2) = tile4[p];
     }
+    peer_signal(sync);                                       // inverse sweep: phase 2, my share of every slab is stored
 }
 
 // energy partial -> per-block slot; the last block of the LAST kernel (main z pass) sums all slots in order
@@ -292,6 +378,8 @@ __device__ __forceinline__ void energy_block_finish(double e, const ConvParams& 
         *cp.d_cv = 0.5 * s;      // sum *= 1/2, OrderParameterMesh.cc:905
         *cp.ticket = 0;
     }
+    if (threadIdx.x == 0)
+        for (unsigned r = 0; r < cp.cv_n; ++r) reinterpret_cast<double*>(cp.cv_arena[r] + cp.cv_off)[cp.cv_rank] = 0.5 * s;
 }
 
 // ---------------------------------------------------------------------------------------------------

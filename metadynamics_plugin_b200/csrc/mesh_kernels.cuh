@@ -24,6 +24,7 @@
 // double-precision box.
 #pragma once
 #include "common.cuh"
+#include "mesh_fft_kernels.cuh"
 #ifdef __CUDACC__
 #include <cuda_pipeline.h>
 #include <cuda/ptx>
@@ -766,9 +767,10 @@ mesh_gather_kernel(const float4* __restrict__ postype, const unsigned* __restric
                    const float4* __restrict__ cache4, const uint2* __restrict__ cache_code,
                    const __grid_constant__ Geom g, const float* __restrict__ inv,
                    const float* __restrict__ ghost /* slab mode: planes z0-1 and z0+nz of Re IFFT(G) */, ForceParams fp,
-                   const double* __restrict__ d_bias, float4* __restrict__ force) {
+                   const double* __restrict__ d_bias, float4* __restrict__ force, const __grid_constant__ fft::PeerSync sync) {
     constexpr int T = 1 << LGT, PX = T + 2 * kHaloX, PY = T + 2 * kHalo, PZ = PY, P3 = PX * PY * PZ;
     extern __shared__ __align__(16) float ftile[];          // P3 floats, then the staging buffers of the particle cache
+    fft::peer_wait(sync);                                   // fused peer mode: the neighbours' halo planes of Re IFFT(G) have arrived
     float4* s_q = reinterpret_cast<float4*>(ftile + P3);    // [2][kGatherThreads]
     uint2* s_c = reinterpret_cast<uint2*>(s_q + 2 * kGatherThreads);
     __shared__ uint64_t bar;

@@ -31,7 +31,7 @@ inline ArenaLayout arena_layout(size_t m_local /* local mesh cells */, size_t pl
     a.ghost_inv = o; o = up(o + 2 * plane * sizeof(float));            // planes z0-1 and z0+nz of Re IFFT(G)
     a.sums = o; o = up(o + kMaxPeers * 4 * sizeof(double));            // per-rank {sum a^2, sum a, outside, -}
     a.cv = o; o = up(o + kMaxPeers * sizeof(double));                  // per-rank CV partials
-    a.flags = o; o = up(o + kMaxPeers * sizeof(unsigned));             // barrier flags, one per peer
+    a.flags = o; o = up(o + 8 * kMaxPeers * sizeof(unsigned));         // flags[4 phases][peer] of the fused synchronisation, then [peer] of the barrier kernel
     a.total = o;
     return a;
 }
@@ -41,17 +41,27 @@ struct PeerTable {
     unsigned n, rank;
 };
 
+struct Publish { const double* src; size_t table_offset; unsigned per_rank, n; };
+
 // ---- copy kernel: up to 4 segments of 16-byte units, destination in any rank's memory ------------------
 struct PushJob {
     int4* dst[4];
     const int4* src[4];
     unsigned n16[4];      // 16-byte units per segment (0 = unused)
 };
-__global__ void __launch_bounds__(256) push_kernel(PushJob job) {
+// fused mode: block 0 also publishes `pub.n` doubles into row [rank] of a table in every arena, and the last CTA signals
+// the phase (fft::peer_signal)
+__global__ void __launch_bounds__(256) push_kernel(PushJob job, Publish pub, const __grid_constant__ fft::PeerSync sync) {
     const unsigned stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    fft::peer_wait(sync);
 #pragma unroll
     for (int s = 0; s < 4; ++s)
         for (unsigned i = t0; i < job.n16[s]; i += stride) job.dst[s][i] = job.src[s][i];
+    if (pub.n && blockIdx.x == 0) {
+        const unsigned r = threadIdx.x / 4, k = threadIdx.x % 4;
+        if (r < sync.n && k < pub.n) reinterpret_cast<double*>(sync.arena[r] + pub.table_offset)[sync.rank * pub.per_rank + k] = pub.src[k];
+    }
+    fft::peer_signal(sync);
 }
 // broadcast of a few doubles into slot [rank] of every peer's table
 __global__ void push_scalars_kernel(PeerTable pt, size_t table_offset, unsigned per_rank, const double* __restrict__ src, unsigned n) {
@@ -77,7 +87,6 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
 //      all-reduces of the path, deterministic and identical on every rank.
 // wait == 0: steps 1 and 3 only (single-process emulation of the ranks, where the launch order already orders the data).
 // status[0] is set to 1 if a peer did not arrive within a few seconds (a crashed rank must not hang the GPU).
-struct Publish { const double* src; size_t table_offset; unsigned per_rank, n; };
 struct Reduce { const double* table; unsigned per_rank, width; double* out; };
 __global__ void barrier_kernel(PeerTable pt, size_t flags_offset, unsigned* __restrict__ d_epoch, int wait, Publish pub, Reduce red,
                                unsigned* __restrict__ status) {
