@@ -85,6 +85,9 @@ def make_workload(name, shard=None):
 
 
 # ---------------------------------------------------------------------------------------------------- ours
+TILE_ORDER = None       # --tile-order: A/B switch of the order inside a tile (library default when None)
+
+
 class MeshStep:
     """mesh CV -> 1-D grid bias -> forces, everything device-resident."""
     # spread, x/y fwd, z fused (+plane0), y/x inv, grid step, gather; a rebuild of the tile order adds bin, 3 scan, place, layer order, scale
@@ -99,6 +102,8 @@ class MeshStep:
         self.period = period
         self.mesh.set(0, period)
         self.mesh.set(4, 1)             # CUDA-graph replay of the per-call kernel sequence
+        if TILE_ORDER is not None:
+            self.mesh.set(6, {"bank": 1, "layer": 0}[TILE_ORDER])
         self.d_pt = torch.from_numpy(w["postype"]).cuda()
         self.d_force = torch.empty_like(self.d_pt)
         self.t = 0
@@ -501,9 +506,12 @@ def main():
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"], help="multi-GPU mesh path: peer memory (default) or NCCL collectives")
     ap.add_argument("--p2p-sync", default="barrier", choices=["fused", "barrier"],
                     help="peer-memory mode: separate barrier launches (default, measured faster) or inter-rank signal/wait inside the kernels")
+    ap.add_argument("--tile-order", default=None, choices=["bank", "layer"], help="order of the particles inside a tile (single GPU; default: library default = bank)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     args = ap.parse_args()
+    global TILE_ORDER
+    TILE_ORDER = args.tile_order
     if args.impl == "reference":
         run_reference(args)
     else:

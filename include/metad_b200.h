@@ -168,7 +168,9 @@ int metad_mesh_get(metad_mesh* p, int which, void* h_out);
  *                decision is captured once per argument signature (pointers, N, box, stream) and replayed with one launch
  *                (metad_mesh_get(p, 7, unsigned long long*) = replays so far)
  *        key 5 = peer-memory mode: 1 folds the inter-rank signal / wait into the producer / consumer kernels, 0 (default,
- *                measured faster) uses separate barrier launches                                                        */
+ *                measured faster) uses separate barrier launches
+ *        key 6 = order of the particles inside a tile: 1 (default) bank order, 0 layer order (mesh_kernels.cuh); results
+ *                do not depend on it                                                                                     */
 int metad_mesh_set(metad_mesh* p, int key, long value);
 
 /* ------------------------------------------------------------------------------------------------

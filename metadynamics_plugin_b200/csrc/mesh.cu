@@ -88,6 +88,7 @@ struct metad_mesh {
     // measured slower on B200 (2 GPUs, C4: 0.506 vs 0.464 ms/step) -- every producer CTA has to fence its peer stores at
     // system scope before taking the ticket, which stalls the CTA tails that otherwise drain asynchronously.
     bool fused_sync = false;
+    int order_kind = 1;                         // order inside a tile: 0 = layer order, 1 = bank order (knob 6)
     unsigned* d_sync = nullptr;                 // [4] phase epochs + [4] CTA tickets of the fused synchronisation
     // CUDA-graph replay of the per-call kernel sequence (metad_mesh_set key 4): everything a call enqueues after the
     // (eager) tile-order decision is captured once per argument signature and replayed with one launch
@@ -343,8 +344,13 @@ int rebuild_order(metad_mesh* p, const float* d_postype, unsigned N, cudaStream_
                                                            p->d_tstart);
     METAD_LAUNCH_CHECK();
     // layer order inside every tile; the arrival ranks are no longer needed, their buffer receives the final order
-    if (g.lgT == 4) mesh_layer_order_kernel<4><<<num_tiles(g), kLayerThreads, 0, stream>>>(p->d_start, p->d_perm, p->d_ranks);
-    else mesh_layer_order_kernel<3><<<num_tiles(g), kLayerThreads, 0, stream>>>(p->d_start, p->d_perm, p->d_ranks);
+    if (p->order_kind == 1) {
+        if (g.lgT == 4) mesh_bank_order_kernel<4><<<num_tiles(g), kLayerThreads, 0, stream>>>(p->d_start, p->d_perm, p->d_ranks);
+        else mesh_bank_order_kernel<3><<<num_tiles(g), kLayerThreads, 0, stream>>>(p->d_start, p->d_perm, p->d_ranks);
+    } else {
+        if (g.lgT == 4) mesh_layer_order_kernel<4><<<num_tiles(g), kLayerThreads, 0, stream>>>(p->d_start, p->d_perm, p->d_ranks);
+        else mesh_layer_order_kernel<3><<<num_tiles(g), kLayerThreads, 0, stream>>>(p->d_start, p->d_perm, p->d_ranks);
+    }
     METAD_LAUNCH_CHECK();
     mesh_fx_scale_kernel<<<1, 1, 0, stream>>>(p->d_max_count, p->amax, p->d_fx);
     METAD_LAUNCH_CHECK();
@@ -1036,6 +1042,7 @@ extern "C" int metad_mesh_set(metad_mesh* p, int key, long value) {
         case 3: p->keep_cells = value != 0; return METAD_OK;
         case 4: p->graph_mode = value != 0; return METAD_OK;
         case 5: p->fused_sync = value != 0; return METAD_OK;
+        case 6: p->order_kind = value != 0 ? 1 : 0; p->order_valid = false; return METAD_OK;
         default: set_error("metad_mesh_set: unknown key"); return METAD_ERR_INVALID;
     }
 }

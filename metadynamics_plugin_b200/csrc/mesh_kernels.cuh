@@ -594,6 +594,65 @@ mesh_layer_order_kernel(const unsigned* __restrict__ start, const unsigned* __re
     }
 }
 
+// bank order inside a tile.  All 27 taps of a particle sit at a fixed offset from the shared-memory word of its base
+// cell, so whether two lanes of a warp collide in a bank is decided by the BANK CLASS of their base cells alone
+// (word index of the cell in the padded tile, modulo 32).  The order interleaves the 32 classes: slot 32 r + b holds the
+// r-th particle of class b (cells ascending inside a class), so that lane b of every warp works on bank b for every tap:
+// no bank conflict and no same-address serialisation, for the spread's atomics and the gather's loads alike.  Once the
+// smallest classes run out, the remaining ones close ranks (at most two particles per bank and warp while more than half
+// of the classes are alive).  One CTA per tile; amortised like the layer order it replaces.
+template <int LGT> MHD unsigned bank_class(unsigned local_cell) {
+    constexpr unsigned T = 1u << LGT, PX = T + 2 * kHaloX, PY = T + 2 * kHalo;
+    const unsigned lx = local_cell & (T - 1), ly = (local_cell >> LGT) & (T - 1), lz = local_cell >> (2 * LGT);
+    return (lx + PX * (ly + PY * lz)) & 31u;
+}
+// slot (relative to the tile) of the r-th particle of class b: all particles of lower rank, then the lower classes of
+// rank r
+MHD unsigned bank_order_slot(unsigned r, unsigned b, const unsigned* class_count) {
+    unsigned slot = 0;
+    for (unsigned c = 0; c < 32; ++c) {
+        const unsigned n = class_count[c];
+        slot += (n < r ? n : r) + ((c < b && n > r) ? 1u : 0u);
+    }
+    return slot;
+}
+template <int LGT>
+__global__ void __launch_bounds__(kLayerThreads)
+mesh_bank_order_kernel(const unsigned* __restrict__ start, const unsigned* __restrict__ perm, unsigned* __restrict__ order) {
+    constexpr int CELLS = 1 << (3 * LGT), CPT = CELLS / kLayerThreads, SEGS = kLayerThreads / 32, SEG = CELLS / SEGS;
+    __shared__ unsigned s_start[CELLS + 1];
+    __shared__ unsigned s_base[CELLS];              // rank inside its class of the first particle of a cell
+    __shared__ unsigned s_seg[SEGS][32];
+    __shared__ unsigned s_count[32];
+    const size_t key0 = (size_t)blockIdx.x << (3 * LGT);
+    for (int i = threadIdx.x; i <= CELLS; i += kLayerThreads) s_start[i] = __ldg(start + key0 + i);
+    __syncthreads();
+    const unsigned tile_begin = s_start[0];
+    if (s_start[CELLS] == tile_begin) return;
+    // class totals and the per-cell base ranks: thread (segment, class) walks the cells of its class in its segment
+    const unsigned cls = threadIdx.x & 31, seg = threadIdx.x >> 5;
+    unsigned cnt = 0;
+    for (unsigned c = seg * SEG; c < (seg + 1) * SEG; ++c)
+        if (bank_class<LGT>(c) == cls) cnt += s_start[c + 1] - s_start[c];
+    s_seg[seg][cls] = cnt;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        unsigned run = 0;
+        for (int k = 0; k < SEGS; ++k) { const unsigned t = s_seg[k][threadIdx.x]; s_seg[k][threadIdx.x] = run; run += t; }
+        s_count[threadIdx.x] = run;
+    }
+    __syncthreads();
+    unsigned run = s_seg[seg][cls];
+    for (unsigned c = seg * SEG; c < (seg + 1) * SEG; ++c)
+        if (bank_class<LGT>(c) == cls) { s_base[c] = run; run += s_start[c + 1] - s_start[c]; }
+    __syncthreads();
+    for (int k = 0; k < CPT; ++k) {
+        const unsigned c = threadIdx.x + k * kLayerThreads;
+        const unsigned b = s_start[c], n = s_start[c + 1] - b, r0 = s_base[c], cb = bank_class<LGT>(c);
+        for (unsigned i = 0; i < n; ++i) order[tile_begin + bank_order_slot(r0 + i, cb, s_count)] = __ldg(perm + b + i);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // spread
 // ---------------------------------------------------------------------------------------------------

@@ -135,3 +135,11 @@ def grid_sequence(cv_min, cv_max, num_points, sigma, cv_values, timesteps, W=1.0
     out.update(outu)
     out.update(bias=bias, bias_potential=sc[0], reweight=sc[1], num_gaussians=int(sc[2]))
     return out
+
+
+def test2d_files(directory, restart=False, prec="f64"):
+    """The reference's test/test_2d.py scenario through the reference's own IntegratorMetaDynamics / Density / AspectRatio,
+    including the files they write into `directory` (grid dumps, hills log); returns num_gaussians."""
+    rc = lib(prec).ref_test2d_files(os.fsencode(directory), 1 if restart else 0)
+    assert rc >= 0
+    return rc

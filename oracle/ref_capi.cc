@@ -16,6 +16,7 @@
 #include "OrderParameterMesh.h"
 #include "LamellarOrderParameter.h"
 #include "AspectRatio.h"
+#include "Density.h"
 #include "IndexGrid.h"
 #include "IntegratorMetaDynamics.h"
 #undef private
@@ -170,6 +171,42 @@ int ref_grid_sequence(int ncv, const double* cv_min, const double* cv_max, const
         scalars3[0] = imd.m_curr_bias_potential; scalars3[1] = imd.m_curr_reweight; scalars3[2] = imd.m_num_gaussians;
         return 0;
     } catch (const std::exception& e) { fprintf(stderr, "ref_grid_sequence: %s\n", e.what()); return -1; }
+}
+
+// The reference's test/test_2d.py scenario through the reference's own classes, files and all: one particle, Density +
+// AspectRatio CVs on a 20 x 30 grid, well-tempered, stride 1, grid dumped every step with the hills log switched on, the
+// box rescaled between the two run(1) calls.  run(1) = prepRun(t) [first updateBiasPotential(t)] + update(t)
+// [updateBiasPotential(t + 1)].  restart != 0: a fresh integrator restarts from <dir>/bias.dat_1, rescales, runs one step
+// and dumps <dir>/bias_restart.dat_{0,1}.  Every file is written by IntegratorMetaDynamics itself.
+int ref_test2d_files(const char* dir, int restart) {
+    try {
+        const double L0 = std::pow(10.0, 1.0 / 3.0), sc = std::pow(0.125, 1.0 / 3.0);
+        const double L[3] = {L0, L0, L0}, tilt[3] = {0, 0, 0};
+        const float one[4] = {0, 0, 0, 0};
+        auto sys = make_system(one, 1, L, tilt, 1);
+        const std::string d(dir);
+        IntegratorMetaDynamics imd(sys, Scalar(0.005), Scalar(1.0), Scalar(1.0), Scalar(1.0), 1, true, restart ? "" : d + "/hills.dat", true,
+                                   IntegratorMetaDynamics::mode_well_tempered);
+        std::shared_ptr<ParticleGroup> all(new ParticleGroup(1));
+        std::shared_ptr<Density> density(new Density(sys, all, ""));
+        std::shared_ptr<AspectRatio> aspect(new AspectRatio(sys, 0, 1));
+        imd.registerCollectiveVariable(density, Scalar(0.25), Scalar(0.0), Scalar(1.0), 20);
+        imd.registerCollectiveVariable(aspect, Scalar(0.1), Scalar(0.0), Scalar(2.0), 30);
+        imd.setGrid(true);
+        auto rescale = [&]() { sys->getParticleData()->setGlobalBox(BoxDim((Scalar)(L0 * sc), (Scalar)(L0 * sc), (Scalar)(L0 * sc))); };
+        if (!restart) {
+            imd.dumpGrid(d + "/bias.dat", "", 1);
+            imd.prepRun(0); imd.updateBiasPotential(1);
+            rescale();
+            imd.prepRun(1); imd.updateBiasPotential(2);
+        } else {
+            imd.restartFromGridFile(d + "/bias.dat_1");
+            imd.dumpGrid(d + "/bias_restart.dat", "", 1);
+            rescale();
+            imd.prepRun(0); imd.updateBiasPotential(1);
+        }
+        return (int)imd.m_num_gaussians;
+    } catch (const std::exception& e) { fprintf(stderr, "ref_test2d_files: %s\n", e.what()); return -1; }
 }
 
 unsigned ref_indexgrid_index(const unsigned* lengths, int d, const unsigned* coords) {

@@ -94,18 +94,27 @@ int main(int argc, char** argv) {
     const unsigned T = 1u << g.lgT, PX = T + 2 * kHaloX, PY = T + 2 * kHalo, PZ = PY, P3 = PX * PY * PZ, ntiles = num_tiles(g);
     std::vector<unsigned> tstart(ntiles + 1);
     for (unsigned t = 0; t <= ntiles; ++t) tstart[t] = start[(size_t)t << (3 * g.lgT)];
-    // layer order inside every tile (mesh_layer_order_kernel)
+    // bank order inside every tile (mesh_bank_order_kernel): slot of the r-th particle of bank class b
     {
-        std::vector<unsigned> order(N);
+        std::vector<unsigned> order(N, 0xffffffffu);
         const unsigned cells = 1u << (3 * g.lgT);
         for (unsigned t = 0; t < ntiles; ++t) {
             const size_t key0 = (size_t)t << (3 * g.lgT);
-            unsigned out = tstart[t], layers = 0;
-            for (unsigned c = 0; c < cells; ++c) layers = std::max(layers, start[key0 + c + 1] - start[key0 + c]);
-            for (unsigned r = 0; r < layers; ++r)
-                for (unsigned c = 0; c < cells; ++c)
-                    if (start[key0 + c + 1] - start[key0 + c] > r) order[out++] = perm[start[key0 + c] + r];
-            if (out != tstart[t + 1]) { fprintf(stderr, "layer order lost particles\n"); return 3; }
+            unsigned class_count[32] = {0};
+            std::vector<unsigned> base(cells);
+            for (unsigned c = 0; c < cells; ++c) {
+                const unsigned b = g.lgT == 4 ? bank_class<4>(c) : bank_class<3>(c);
+                base[c] = class_count[b];
+                class_count[b] += start[key0 + c + 1] - start[key0 + c];
+            }
+            for (unsigned c = 0; c < cells; ++c) {
+                const unsigned b = g.lgT == 4 ? bank_class<4>(c) : bank_class<3>(c);
+                for (unsigned i = 0; i < start[key0 + c + 1] - start[key0 + c]; ++i) {
+                    const unsigned slot = tstart[t] + bank_order_slot(base[c] + i, b, class_count);
+                    if (slot >= tstart[t + 1] || order[slot] != 0xffffffffu) { fprintf(stderr, "bank order: bad slot\n"); return 3; }
+                    order[slot] = perm[start[key0 + c] + i];
+                }
+            }
         }
         perm.swap(order);
     }

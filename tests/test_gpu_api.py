@@ -104,6 +104,61 @@ def test_reference_test_2d_scenario(api, oracle, tmp_path):
     assert abs(a[:, 2] - o.get("grid")).max() < 1e-5 * o.get("grid").max()
 
 
+def test_grid_and_hills_files_match_the_reference_files(api, tmp_path):
+    """The same scenario against the files the REFERENCE's own IntegratorMetaDynamics wrote for it
+    (tests/golden/test2d_*, generated by tests/golden/make_ref_test2d.py): header lines token for token, integer columns
+    exactly, floating columns within the CV's float rounding; and a restart from the reference-written bias.dat_1."""
+    cv, integrate, hoomd = api
+    from metadynamics_plugin_b200 import _metadynamics
+    gold32 = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "test2d_f32")
+    gold64 = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "test2d_f64")
+    L0 = 10 ** (1. / 3.)
+    s = 0.125 ** (1. / 3.)
+
+    def setup(filename=""):
+        hoomd.context.initialize()
+        hoomd.init.from_arrays(np.zeros((1, 3), np.float32), [0], ["A"], L0)
+        meta = integrate.mode_metadynamics(dt=0.005, mode='well_tempered', stride=1, deltaT=1, W=1, filename=filename, overwrite=True)
+        cv.density(sigma=0.25).set_grid(cv_min=0, cv_max=1, num_points=20)
+        cv.aspect_ratio(sigma=0.1, dir1=0, dir2=1).set_grid(cv_min=0, cv_max=2, num_points=30)
+        return meta
+
+    def rescale():
+        hoomd.context.current.system_definition.getParticleData().setGlobalBox(_metadynamics.BoxDim(L0 * s, L0 * s, L0 * s))
+
+    def same_file(ours, ref, rtol):
+        a, b = open(ours).read().splitlines(), open(ref).read().splitlines()
+        assert a[:4] == b[:4] and len(a) == len(b) == 604
+        x, y = np.loadtxt(ours, skiprows=4), np.loadtxt(ref, skiprows=4)
+        assert np.array_equal(x[:, 4:6], y[:, 4:6])                               # num_gaussians, hist
+        for c in (0, 1, 2, 3, 6, 7):
+            assert np.abs(x[:, c] - y[:, c]).max() <= rtol * np.abs(y[:, c]).max(), c
+
+    meta = setup(str(tmp_path / "hills.dat"))
+    meta.dump_grid(str(tmp_path / 'bias.dat'), period=1)
+    hoomd.run(1)
+    rescale()
+    hoomd.run(1)
+    del meta
+    for name in ("bias.dat_1", "bias.dat_2"):
+        same_file(tmp_path / name, os.path.join(gold32, name), 2e-6)              # reference float build: float grid arithmetic
+        same_file(tmp_path / name, os.path.join(gold64, name), 2e-7)              # reference double build: CV values differ by float rounding
+    hoomd.context.initialize()                                                    # closes the hills log of the first integrator
+    ours, ref = open(tmp_path / "hills.dat").read().splitlines(), open(os.path.join(gold32, "hills.dat")).read().splitlines()
+    assert ours[0] == ref[0] and len(ours) == len(ref) == 5
+    for a, b in zip(ours[1:], ref[1:]):
+        a, b = a.split("\t"), b.split("\t")
+        assert a[0] == b[0] and a[3:] == b[3:] and len(a) == len(b) == 6         # timestep; "40", "1", "010": sigma_inv rows without delimiter
+        assert float(a[1]) == pytest.approx(float(b[1]), rel=2e-6) and float(a[2]) == pytest.approx(float(b[2]), rel=2e-7)
+
+    meta2 = setup()
+    meta2.restart_from_grid(os.path.join(gold64, 'bias.dat_1'))                   # a file written by the reference
+    meta2.dump_grid(str(tmp_path / 'bias_restart.dat'), period=1)
+    rescale()
+    hoomd.run(1)
+    same_file(tmp_path / "bias_restart.dat_0", os.path.join(gold64, "bias_restart.dat_0"), 2e-7)
+
+
 def test_lamellar_metadynamics_steps(api, oracle):
     """cv.lamellar + integrate.mode_metadynamics over a few steps: CV log value, bias factor hand-off, forces, grid."""
     cv, integrate, hoomd = api

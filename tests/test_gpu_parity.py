@@ -227,6 +227,32 @@ def test_mesh_order_independence(gpu):
     assert np.array_equal(f2, f[perm])
 
 
+@pytest.mark.parametrize("dims,N", [((64, 64, 64), 70000), ((128, 128, 128), 300000)])
+def test_mesh_bank_order_equals_layer_order(gpu, dims, N):
+    """The two orders of the particles inside a tile (knob 6: bank order, layer order) are permutations of one another:
+    density, CV and forces are bitwise equal (8-cell and 16-cell tiles)."""
+    import torch
+    L = 30.0
+    pos, types = rand_pt(N, L, 2, 5)
+    modes = [1.0, -0.5]
+    box = gpu.Box.make(L)
+    bias = torch.tensor([1.1], dtype=torch.float64, device="cuda")
+    d_pt = to_dev(gpu, pos, types)
+    out = []
+    for kind in (1, 0):
+        mesh = gpu.Mesh(*dims, modes)
+        mesh.set(6, kind)
+        mesh.set(1, 1)
+        cv = mesh.compute_cv(d_pt, N, box).cpu().item()
+        rho = np.asarray(mesh.rho())
+        f = mesh.forces(d_pt, N, box, bias).cpu().numpy()
+        assert mesh.stats()["drifted"] == 0
+        out.append((cv, f, rho))
+    assert out[0][0] == out[1][0]
+    assert np.array_equal(out[0][1], out[1][1])
+    assert np.array_equal(out[0][2], out[1][2])
+
+
 def test_mesh_stale_tile_order(gpu, oracle):
     """The tile order is reused across calls while the particles move: every call is still exact (cells are recomputed
     from the current positions), drifted particles take the direct path and trigger a rebuild; results are bitwise those

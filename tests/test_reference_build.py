@@ -133,3 +133,63 @@ def test_live_reference_build_matches_oracle(oracle):
             assert cv == pytest.approx(r["cv"], rel=1e-11 if prec == "f64" else 5e-6)
             f = m.forces(pt, 0.9)
             assert np.abs(f - r["force"]).max() < (1e-10 if prec == "f64" else 5e-2) * np.abs(r["force"]).max()
+
+
+# ---- on-disk formats: files written by the reference's own IntegratorMetaDynamics -------------------
+T2D = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "test2d_f64")
+T2D_HEADER = ["#n_cv: 2", "#dim:  20 30"]
+T2D_COLUMNS = ["cv_density", "cv_aspect_ratio", "grid_value", "det_sigma", "num_gaussians", "hist", "hist_reweight", "weight"]
+
+
+def read_grid_file(path):
+    lines = open(path).read().splitlines()
+    return lines[:4], np.loadtxt(path, skiprows=4)
+
+
+def test_oracle_reproduces_reference_test2d_grid_files(oracle):
+    """reference test/test_2d.py through the reference's own classes (tests/golden/make_ref_test2d.py): the grid dumps after
+    every step and the hills log, against the restated update sequence (rho = 1/V = 0.1 then 0.8, aspect ratio 1)."""
+    L0, s = 10 ** (1. / 3.), 0.125 ** (1. / 3.)
+    rho0, rho1 = 1.0 / (L0 * L0 * L0), 1.0 / ((L0 * s) * (L0 * s) * (L0 * s))
+    o = oracle.Grid([0.0, 0.0], [1.0, 2.0], [20, 30], [0.25, 0.1], W=1.0, T_shift=1.0, T=1.0, stride=1, well_tempered=True)
+    hills = open(os.path.join(T2D, "hills.dat")).read().splitlines()
+    assert hills[0].split("\t") == ["timestep", "W", "cv_density", "sigma_cv_density_0_0", "sigma_cv_density_0_1", "cv_aspect_ratio",
+                                    "sigma_cv_aspect_ratio_1_0", "sigma_cv_aspect_ratio_1_1", ""]
+    dumps = {0: "bias.dat_0", 2: "bias.dat_1", 3: "bias.dat_2"}          # update number -> dump that holds its state
+    for n, (t, rho) in enumerate([(0, rho0), (1, rho0), (1, rho1), (2, rho1)]):
+        o.update(t, [rho, 1.0])
+        # hills row: timestep, W exp(-V/T_shift), then per CV its value and its row of sigma_inv written WITHOUT delimiter
+        row = hills[1 + n].split("\t")
+        assert int(row[0]) == t
+        assert float(row[1]) == pytest.approx(np.exp(-o.scalars()["bias_potential"]), rel=6e-10)
+        assert float(row[2]) == pytest.approx(rho, rel=6e-10) and row[3] == "40" and float(row[4]) == 1.0 and row[5] == "010"
+        if n in dumps:
+            hdr, a = read_grid_file(os.path.join(T2D, dumps[n]))
+            assert hdr[:2] == T2D_HEADER and hdr[2] == "#num_gaussians: %d" % (n + 1) and hdr[3].split("\t") == T2D_COLUMNS
+            assert a.shape == (600, 8)
+            cv1, cv2 = np.meshgrid(np.arange(20) / 19.0, 2.0 * np.arange(30) / 29.0, indexing="xy")      # CV 0 fastest
+            np.testing.assert_allclose(a[:, 0], cv1.ravel(), rtol=6e-10, atol=0)
+            np.testing.assert_allclose(a[:, 1], cv2.ravel(), rtol=6e-10, atol=0)
+            np.testing.assert_allclose(a[:, 2], o.get("grid"), rtol=6e-10, atol=0)
+            hg = o.get("hist_gauss")
+            np.testing.assert_allclose(a[:, 3], np.where(hg > 0, o.get("sigma_grid") / np.maximum(hg, 1), 0.0), rtol=6e-10)
+            assert np.array_equal(a[:, 4], hg) and np.array_equal(a[:, 5], o.get("hist"))
+            np.testing.assert_allclose(a[:, 6], o.get("reweighted"), rtol=6e-10, atol=0)
+            np.testing.assert_allclose(a[:, 7], o.get("weight"), rtol=6e-10, atol=0)
+    # the reference's own restart claim: "bias.restart_0.dat and bias.dat_2 should be identical up to rounding errors"
+    _, a = read_grid_file(os.path.join(T2D, "bias.dat_2"))
+    _, b = read_grid_file(os.path.join(T2D, "bias_restart.dat_0"))
+    np.testing.assert_allclose(b, a, rtol=2e-9, atol=0)
+
+
+def test_live_reference_build_rewrites_the_golden_files(tmp_path):
+    from oracle import pyref
+    if not os.path.isdir(pyref.REFERENCE):
+        pytest.skip("/root/reference is not mounted here; the committed files were generated from it")
+    for prec in ("f64", "f32"):
+        d = str(tmp_path / prec)
+        os.makedirs(d)
+        assert pyref.test2d_files(d, False, prec) == 4 and pyref.test2d_files(d, True, prec) == 5
+        gold = os.path.join(os.path.dirname(T2D), "test2d_" + prec)
+        for name in os.listdir(gold):
+            assert open(os.path.join(gold, name)).read() == open(os.path.join(d, name)).read(), (prec, name)
