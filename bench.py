@@ -304,6 +304,24 @@ def run_ours(args):
         roofline = {"bound": "hbm", "kernel": "whole sharded step (compute stages + NCCL collectives)", "achieved": achieved,
                     "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world), "traffic": None,
                     "peak_source": peak_src + " x %d GPUs" % world}
+        if runner.comm_mode == "p2p" and args.p2p_sync == "barrier":
+            # where the sharded step spends its time: events around the 12 segments of the peer-memory step (no graph
+            # replay while profiling); a barrier's time is the wait for the slowest rank plus the flag round trip
+            runner.mesh.set(2, 1)
+            acc = {}
+            nprof = 10
+            for _ in range(nprof):
+                runner.step()
+                torch.cuda.synchronize()
+                for k, v in runner.mesh.p2p_timings().items():
+                    acc[k] = acc.get(k, 0.0) + v / nprof
+            runner.mesh.set(2, 0)
+            keys = list(acc)
+            t = torch.tensor([acc[k] for k in keys], dtype=torch.float64, device="cuda")
+            tmax = t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            roofline["segment_ms_rank0"] = {k: round(v, 4) for k, v in zip(keys, t.tolist())}
+            roofline["segment_ms_max_over_ranks"] = {k: round(v, 4) for k, v in zip(keys, tmax.tolist())}
     elif w["kind"] == "mesh":
         runner.mesh.set(2, 1)
         acc = {}

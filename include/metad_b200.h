@@ -159,7 +159,10 @@ int metad_mesh_slab_p2p_forces(metad_mesh* p, const float* d_postype, float* d_f
  *           5: statistics, double[6]: rebuilds of the tile order so far; of the last spread: particles that took the
  *              direct path (drifted out of their padded tile), particles outside the slab, padded-tile cells past 1/8 of
  *              the fixed-point range; the fixed-point scale; calls since the last rebuild
- *           6: peer-memory mode, unsigned[2]: {a barrier timed out, particles outside their slab summed over the ranks}    */
+ *           6: peer-memory mode, unsigned[2]: {a barrier timed out, particles outside their slab summed over the ranks}
+ *           7: unsigned long long: CUDA-graph replays so far
+ *           8: peer-memory step with profiling on (key 2), float[12]: milliseconds of spread, halo push, barrier 1, x forward,
+ *              barrier 2, y forward, fused z, y inverse, barrier 3, x inverse, halo push, barrier 4 of the last step        */
 int metad_mesh_get(metad_mesh* p, int which, void* h_out);
 /* knobs: key 0 = rebuild period of the tile order in calls (default 32; value 0 = rebuild at the next call)
  *        key 1 = keep a copy of rho for metad_mesh_get(1)      key 2 = record per-stage CUDA events (profiling)

@@ -109,6 +109,7 @@ struct metad_mesh {
     // optional per-stage timing (CUDA events on the caller's stream): ev[i] = start of stage i for i < 7, ev[7] = end of the
     // cv pipeline, ev[8]/ev[9] = start/end of the gather
     bool profile = false;
+    cudaEvent_t evp[13] = {};                   // peer-memory step, profiling: boundaries of its 12 segments (metad_mesh_get 8)
     cudaEvent_t ev[kNumStages + 2] = {};
     size_t M() const { return (size_t)g.nx * g.ny * g.nz; }
 };
@@ -264,6 +265,13 @@ int mark(metad_mesh* p, int i, cudaStream_t st) {
     if (!p->profile) return METAD_OK;
     if (!p->ev[i]) METAD_CUDA(cudaEventCreate(&p->ev[i]));
     METAD_CUDA(cudaEventRecord(p->ev[i], st));
+    return METAD_OK;
+}
+
+int markp(metad_mesh* p, int i, cudaStream_t st) {
+    if (!p->profile) return METAD_OK;
+    if (!p->evp[i]) METAD_CUDA(cudaEventCreate(&p->evp[i]));
+    METAD_CUDA(cudaEventRecord(p->evp[i], st));
     return METAD_OK;
 }
 
@@ -609,6 +617,7 @@ extern "C" int metad_mesh_destroy(metad_mesh* p) {
         if (p->peers_mapped[r]) cudaIpcCloseMemHandle(p->peers.arena[r]);
     cudaFree(p->arena);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : p->evp) if (e) cudaEventDestroy(e);
     delete p;
     return METAD_OK;
 }
@@ -765,7 +774,9 @@ int p2p_stage(metad_mesh* p, int stage, int wait, const float* d_postype, unsign
     int rc = METAD_OK;
     switch (stage) {
         case 0: {   // local spread; halo planes of the density (+ their scale) to the neighbours, partial sums to everyone
+            rc = markp(p, 0, st); if (rc) return rc;
             rc = enqueue_spread(p, d_postype, N_local, st); if (rc) return rc;
+            rc = markp(p, 1, st); if (rc) return rc;
             int* below = p->d_mesh_alloc;
             int* above = p->d_mesh_alloc + plane * (g.nz + 1);
             const size_t msg = (plane + 4) * sizeof(int);
@@ -790,7 +801,7 @@ int p2p_stage(metad_mesh* p, int stage, int wait, const float* d_postype, unsign
                 p2p::push_scalars_kernel<<<1, 64, 0, st>>>(p->peers, p->lay.sums, 4, p->d_sums, 3);
                 METAD_LAUNCH_CHECK();
             }
-            return METAD_OK;
+            return markp(p, 2, st);
         }
         case 1: {   // [barrier: halos and sums have arrived] x forward pass, every kx pencil stored into its owner's memory
             if (!fused) {
@@ -798,6 +809,7 @@ int p2p_stage(metad_mesh* p, int stage, int wait, const float* d_postype, unsign
                                  p2p::Reduce{(const double*)(mine + p->lay.sums), 4, 3, p->d_sums_global}, st);
                 if (rc) return rc;
             }
+            rc = markp(p, 3, st); if (rc) return rc;
             if (p->keep_rho && !p->d_rho_keep) METAD_CUDA(cudaMalloc(&p->d_rho_keep, sizeof(float) * p->M()));
             PeerOut po;
             memset(&po, 0, sizeof po);
@@ -810,7 +822,8 @@ int p2p_stage(metad_mesh* p, int stage, int wait, const float* d_postype, unsign
             } else {
                 METAD_DISPATCH_LEN(g.nx / 2, (run_x<LL>(p, false, nullptr, p->d_sums_global, (const int*)(mine + p->lay.ghost_rho), st, &po)));
             }
-            return rc;
+            if (rc) return rc;
+            return markp(p, 4, st);
         }
         case 2: {   // [barrier: the pencil is complete] y, fused z, inverse y with every plane stored into its owner's memory
             float2* pen = (float2*)(mine + p->lay.pencil);
@@ -819,9 +832,12 @@ int p2p_stage(metad_mesh* p, int stage, int wait, const float* d_postype, unsign
                 METAD_DISPATCH_LEN(g.ny, (run_y<LL>(p, false, pen, p->kxl, p->nzg, st, nullptr, &ps))); if (rc) return rc;
             } else {
                 rc = p2p_barrier(p, wait, p2p::Publish{nullptr, 0, 0, 0}, p2p::Reduce{nullptr, 0, 0, nullptr}, st); if (rc) return rc;
+                rc = markp(p, 5, st); if (rc) return rc;
                 METAD_DISPATCH_LEN(g.ny, (run_y<LL>(p, false, pen, p->kxl, p->nzg, st))); if (rc) return rc;
             }
+            rc = markp(p, 6, st); if (rc) return rc;
             METAD_DISPATCH_LEN(p->nzg, (run_z<LL>(p, pen, p->kxl, r * p->kxl, p->d_sums_global, N_global, p->d_cv_partial, st, fused))); if (rc) return rc;
+            rc = markp(p, 7, st); if (rc) return rc;
             PeerOut po;
             memset(&po, 0, sizeof po);
             po.n = P; po.rank = r;
@@ -832,6 +848,7 @@ int p2p_stage(metad_mesh* p, int stage, int wait, const float* d_postype, unsign
                 return METAD_OK;
             }
             METAD_DISPATCH_LEN(g.ny, (run_y<LL>(p, true, pen, p->kxl, p->nzg, st, &po))); if (rc) return rc;
+            rc = markp(p, 8, st); if (rc) return rc;
             if (!wait) {    // emulation: see stage 0
                 p2p::push_scalars_kernel<<<1, 64, 0, st>>>(p->peers, p->lay.cv, 1, p->d_cv_partial, 1);
                 METAD_LAUNCH_CHECK();
@@ -848,8 +865,10 @@ int p2p_stage(metad_mesh* p, int stage, int wait, const float* d_postype, unsign
                 rc = p2p_barrier(p, wait, p2p::Publish{p->d_cv_partial, p->lay.cv, 1, wait ? 1u : 0u},
                                  p2p::Reduce{(const double*)(mine + p->lay.cv), 1, 1, d_cv}, st);
                 if (rc) return rc;
+                rc = markp(p, 9, st); if (rc) return rc;
                 METAD_DISPATCH_LEN(g.nx / 2, (run_x<LL>(p, true, (float2*)(mine + p->lay.recv), nullptr, nullptr, st))); if (rc) return rc;
             }
+            rc = markp(p, 10, st); if (rc) return rc;
             p2p::PushJob job;
             memset(&job, 0, sizeof job);
             // my first plane is the lower rank's plane z0+nz (its ghost [1]); my last plane the upper rank's plane z0-1 (ghost [0])
@@ -865,12 +884,12 @@ int p2p_stage(metad_mesh* p, int stage, int wait, const float* d_postype, unsign
                 p2p::push_kernel<<<32, 256, 0, st>>>(job, p2p::Publish{nullptr, 0, 0, 0}, none);
             }
             METAD_LAUNCH_CHECK();
-            return METAD_OK;
+            return markp(p, 11, st);
         }
         case 4:     // [barrier: the halo planes of Re IFFT(G) have arrived]; fused mode: the gather waits for phase 3 itself
             if (fused) return METAD_OK;
             rc = p2p_barrier(p, wait, p2p::Publish{nullptr, 0, 0, 0}, p2p::Reduce{nullptr, 0, 0, nullptr}, st); if (rc) return rc;
-            return METAD_OK;
+            return markp(p, 12, st);
         default:
             set_error("metad_mesh_slab_p2p_cv: stage must be -1 (whole step) or 0..4");
             return METAD_ERR_INVALID;
@@ -1002,6 +1021,16 @@ extern "C" int metad_mesh_get(metad_mesh* p, int which, void* h_out) {
             float* out = (float*)h_out;
             for (int i = 0; i < 7; ++i) METAD_CUDA(cudaEventElapsedTime(out + i, p->ev[i], p->ev[i + 1]));
             METAD_CUDA(cudaEventElapsedTime(out + 7, p->ev[8], p->ev[9]));
+            return METAD_OK;
+        }
+        case 8: {
+            // peer-memory step (barrier launches), profiling on: milliseconds of its 12 segments (float[12]): spread, halo push,
+            // barrier 1, x forward, barrier 2, y forward, z fused, y inverse, barrier 3, x inverse, halo push, barrier 4
+            float* out = (float*)h_out;
+            for (int i = 0; i < 12; ++i) {
+                if (!p->profile || !p->evp[i] || !p->evp[i + 1]) { set_error("metad_mesh_get: no profiled peer-memory step yet"); return METAD_ERR_STATE; }
+                METAD_CUDA(cudaEventElapsedTime(out + i, p->evp[i], p->evp[i + 1]));
+            }
             return METAD_OK;
         }
         case 5: {

@@ -144,6 +144,20 @@ MHD float f_fma(float a, float b, float c) {
 #endif
 }
 
+#ifdef __CUDACC__
+// Packed fp32 pairs (sm_100: fma/mul.rn.f32x2 -> FFMA2 / FMUL2, two IEEE operations per issue slot).  The spread and the
+// gather are bound by instruction issue, not by the FMA pipe, so pairing halves the cost of their tap arithmetic.  Every
+// lane performs the same correctly rounded operation as the scalar code, so results are bit-identical.  A pair built from
+// the same scalar twice costs nothing: the instruction takes a scalar register as a broadcast operand.
+struct F2 { unsigned long long r; };
+__device__ __forceinline__ F2 f2_pack(float lo, float hi) { F2 o; asm("mov.b64 %0, {%1, %2};" : "=l"(o.r) : "f"(lo), "f"(hi)); return o; }
+__device__ __forceinline__ F2 f2_dup(float v) { return f2_pack(v, v); }
+__device__ __forceinline__ void f2_unpack(F2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v.r)); }
+__device__ __forceinline__ float f2_lo(F2 v) { float lo, hi; f2_unpack(v, lo, hi); return lo; }
+__device__ __forceinline__ F2 f2_fma(F2 a, F2 b, F2 c) { F2 o; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(o.r) : "l"(a.r), "l"(b.r), "l"(c.r)); return o; }
+__device__ __forceinline__ F2 f2_mul(F2 a, F2 b) { F2 o; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(o.r) : "l"(a.r), "l"(b.r)); return o; }
+#endif
+
 // cell coordinate along one axis: OrderParameterMesh.cc:543-561 with HOOMD's BoxDim::makeFraction, which multiplies by
 // the stored reciprocal m_Linv = Scalar(1)/(hi - lo) (it does NOT divide; the two round differently and the cell index
 // of a particle next to a cell face depends on it -- confirmed against the reference's own assignParticles compiled
@@ -354,6 +368,29 @@ MHD void gather_sums(const float* base, long long sy_, long long sz_, const floa
                      const float (&dz)[3], float& Sx, float& Sy, float& Sz) {
     Sx = 0.f; Sy = 0.f; Sz = 0.f;
     // plane by plane (9 values live at a time): a_j = sum_i Wx_i v_ij, b_j = sum_i W'x_i v_ij, then the y and z contractions
+#ifdef __CUDA_ARCH__
+    // the same operations, two per instruction: {a_j, b_j} from {Wx_i, W'x_i} * v (v broadcast), {p_k, q_k} += Wy_j * {a_j, b_j},
+    // {Sz, Sx} += {W'z_k, Wz_k} * {p_k, q_k}
+    const F2 wdx0 = f2_pack(wx[0], dx[0]), wdx1 = f2_pack(wx[1], dx[1]), wdx2 = f2_pack(wx[2], dx[2]);
+    F2 Szx = f2_pack(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        F2 pq = f2_pack(0.f, 0.f);
+        float rk = 0.f;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float* row = base + k * sz_ + j * sy_;
+            const float v0 = row[0], v1 = row[1], v2 = row[2];
+            const F2 ab = f2_fma(wdx2, f2_dup(v2), f2_fma(wdx1, f2_dup(v1), f2_mul(wdx0, f2_dup(v0))));
+            pq = f2_fma(f2_dup(wy[j]), ab, pq);
+            rk = fmaf(dy[j], f2_lo(ab), rk);
+        }
+        Szx = f2_fma(f2_pack(dz[k], wz[k]), pq, Szx);
+        Sy = fmaf(wz[k], rk, Sy);
+    }
+    f2_unpack(Szx, Sz, Sx);
+    return;
+#endif
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         float pk = 0.f, qk = 0.f, rk = 0.f;
@@ -688,15 +725,18 @@ mesh_spread_kernel(const float4* __restrict__ postype, const unsigned* __restric
         const float scale = __ldg(d_fx);
         unsigned strays = 0, foreign = 0;
         // software pipeline: the index and the position of the next particle are in flight while this one is spread
+        // (the index two particles ahead, so that the position load of the next one never waits for its index)
         unsigned j = s + threadIdx.x;
-        unsigned n = 0;
+        unsigned n = 0, n_next = 0;
         float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
         if (j < e) { n = __ldg(perm + j); p = __ldg(postype + n); }
+        if (j + kSpreadThreads < e) n_next = __ldg(perm + j + kSpreadThreads);
         while (j < e) {
             const unsigned jn = j + kSpreadThreads;
-            unsigned n_next = 0;
+            unsigned n_next2 = 0;
             float4 p_next = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (jn < e) { n_next = __ldg(perm + jn); p_next = __ldg(postype + n_next); }
+            if (jn < e) p_next = __ldg(postype + n_next);
+            if (jn + kSpreadThreads < e) n_next2 = __ldg(perm + jn + kSpreadThreads);
             const float a = __ldg(mode + __float_as_int(p.w));
             const Cell c = particle_cell(p, g);
             if (out.keys) out.keys[n] = key_of(c.ix, c.iy, (unsigned)(c.iz - (int)g.z0) & (g.nz - 1), g);
@@ -712,14 +752,23 @@ mesh_spread_kernel(const float4* __restrict__ postype, const unsigned* __restric
                 spread_weights(sh, a * scale, w);
                 if (inside) {
                     int* base = tile + ((lz - 1) * PY + (ly - 1)) * PX + (lx - 1);
+                    // tap (i, jj, k) = fx_round(w[i], w[3 + jj] * w[6 + k]) as on every other path, two per instruction
+                    const F2 w01 = f2_pack(w[0], w[1]), wy01 = f2_pack(w[3], w[4]), magic = f2_dup(kFxMagic);
 #pragma unroll
-                    for (int k = 0; k < 3; ++k)
+                    for (int k = 0; k < 3; ++k) {
+                        float wyz[3];
+                        f2_unpack(f2_mul(wy01, f2_dup(w[6 + k])), wyz[0], wyz[1]);
+                        wyz[2] = f_mul(w[5], w[6 + k]);
 #pragma unroll
                         for (int jj = 0; jj < 3; ++jj) {
-                            const float wyz = f_mul(w[3 + jj], w[6 + k]);
-#pragma unroll
-                            for (int i = 0; i < 3; ++i) atomicAdd(base + (k * PY + jj) * PX + i, fx_round(w[i], wyz));
+                            float t0, t1;
+                            f2_unpack(f2_fma(w01, f2_dup(wyz[jj]), magic), t0, t1);
+                            int* row = base + (k * PY + jj) * PX;
+                            atomicAdd(row, __float_as_int(t0) - kFxMagicBits);
+                            atomicAdd(row + 1, __float_as_int(t1) - kFxMagicBits);
+                            atomicAdd(row + 2, fx_round(w[2], wyz[jj]));
                         }
+                    }
                 } else {
                     ++strays;
                     for (int k = 0; k < 3; ++k)
@@ -732,7 +781,7 @@ mesh_spread_kernel(const float4* __restrict__ postype, const unsigned* __restric
             } else {
                 ++foreign;
             }
-            j = jn; n = n_next; p = p_next;
+            j = jn; n = n_next; n_next = n_next2; p = p_next;
         }
         if (strays) atomicAdd(out.counters + 1, strays);
         if (foreign) atomicAdd(out.counters + 2, foreign);

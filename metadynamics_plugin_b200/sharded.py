@@ -145,6 +145,15 @@ class MeshSlabRank:
             lib.metad_mesh_destroy(self.h)
             self.h = None
 
+    P2P_SEGMENTS = ("spread", "halo_push_rho", "barrier_1", "fft_x_fwd", "barrier_2", "fft_y_fwd", "fft_z_fused", "fft_y_inv",
+                    "barrier_3", "fft_x_inv", "halo_push_inv", "barrier_4")
+
+    def p2p_timings(self):
+        """Milliseconds of the 12 segments of the last peer-memory step (profiling knob 2 on; barrier launches)."""
+        out = np.empty(len(self.P2P_SEGMENTS), dtype=np.float32)
+        check(lib.metad_mesh_get(self.h, 8, out.ctypes.data_as(C.c_void_p)))
+        return dict(zip(self.P2P_SEGMENTS, (float(v) for v in out)))
+
     def set(self, key, value):
         check(lib.metad_mesh_set(self.h, int(key), int(value)))
 
