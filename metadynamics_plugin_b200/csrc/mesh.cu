@@ -409,12 +409,12 @@ int enqueue_spread(metad_mesh* p, const float* d_postype, unsigned N, cudaStream
     out.cache4 = p->d_cache4;
     out.cache_code = p->d_cache_code;
     if (g.lgT == 4) {
-        rc = set_smem(mesh_spread_kernel<4>, tile_smem_bytes<4>()); if (rc) return rc;
-        mesh_spread_kernel<4><<<num_tiles(g), kSpreadThreads, tile_smem_bytes<4>(), stream>>>((const float4*)d_postype, p->d_ranks, p->d_tstart, g,
-                                                                                           p->d_mode, p->d_fx, out);
+        rc = set_smem(mesh_spread_kernel<4>, tile_smem_bytes<4>() + sizeof(float) * kSpreadModes); if (rc) return rc;
+        mesh_spread_kernel<4><<<num_tiles(g), kSpreadThreads, tile_smem_bytes<4>() + sizeof(float) * p->ntypes, stream>>>((const float4*)d_postype, p->d_ranks, p->d_tstart, g,
+                                                                                           p->d_mode, p->ntypes, p->d_fx, out);
     } else {
-        mesh_spread_kernel<3><<<num_tiles(g), kSpreadThreads, tile_smem_bytes<3>(), stream>>>((const float4*)d_postype, p->d_ranks, p->d_tstart, g,
-                                                                                           p->d_mode, p->d_fx, out);
+        mesh_spread_kernel<3><<<num_tiles(g), kSpreadThreads, tile_smem_bytes<3>() + sizeof(float) * p->ntypes, stream>>>((const float4*)d_postype, p->d_ranks, p->d_tstart, g,
+                                                                                           p->d_mode, p->ntypes, p->d_fx, out);
     }
     METAD_LAUNCH_CHECK();
     METAD_CUDA(cudaMemcpyAsync(p->h_counters, p->d_counters, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
@@ -488,10 +488,30 @@ int launch_gather(metad_mesh* p, const float* d_postype, const float* d_ghost, f
     fp.two_over_n = 2.0 / (double)N_global;
     int rc = mark(p, 8, stream); if (rc) return rc;
     if (g.lgT == 4) {
-        rc = set_smem(mesh_gather_kernel<4>, gather_smem_bytes<4>()); if (rc) return rc;
-        mesh_gather_kernel<4><<<num_tiles(g), kGatherThreads, gather_smem_bytes<4>(), stream>>>((const float4*)d_postype, p->d_tstart,
-                                                                                           p->d_cache4, p->d_cache_code, g, p->d_buf, d_ghost, fp, d_bias,
-                                                                                           (float4*)d_force, ps);
+        // CTA size / residency of the gather.  Measured on B200 (C4, ms per launch): 256 threads x 3 CTAs/SM (80 registers, the loop
+        // state spills) 0.238; 256 x 2 0.210; 192 x 3 (96 registers, no spill) 0.201; 128 x 5 0.216; 128 x 4 0.212; 192 x 4 0.247.
+        // METAD_GATHER_VARIANT selects the others for experiments.
+        static const int variant = getenv("METAD_GATHER_VARIANT") ? atoi(getenv("METAD_GATHER_VARIANT")) : 2;
+#define METAD_GATHER_LAUNCH(T_, B_)                                                                                               \
+    {                                                                                                                             \
+        const size_t sm = tile_smem_bytes<4>() + 2 * (T_) * (sizeof(float4) + sizeof(uint2));                                       \
+        rc = set_smem(mesh_gather_kernel<4, T_, B_>, sm); if (rc) return rc;                                                       \
+        mesh_gather_kernel<4, T_, B_><<<num_tiles(g), T_, sm, stream>>>((const float4*)d_postype, p->d_tstart, p->d_cache4,        \
+                                                                        p->d_cache_code, g, p->d_buf, d_ghost, fp, d_bias, (float4*)d_force, ps); \
+    }
+        switch (variant) {
+            case 1: METAD_GATHER_LAUNCH(256, 2) break;
+            case 2: METAD_GATHER_LAUNCH(192, 3) break;
+            case 3: METAD_GATHER_LAUNCH(128, 5) break;
+            case 4: METAD_GATHER_LAUNCH(128, 6) break;
+            case 5: METAD_GATHER_LAUNCH(192, 4) break;
+            case 6: METAD_GATHER_LAUNCH(128, 4) break;
+            case 7: METAD_GATHER_LAUNCH(224, 3) break;
+            case 8: METAD_GATHER_LAUNCH(160, 4) break;
+            case 9: METAD_GATHER_LAUNCH(160, 3) break;
+            default: METAD_GATHER_LAUNCH(256, 3) break;
+        }
+#undef METAD_GATHER_LAUNCH
     } else {
         mesh_gather_kernel<3><<<num_tiles(g), kGatherThreads, gather_smem_bytes<3>(), stream>>>((const float4*)d_postype, p->d_tstart,
                                                                                            p->d_cache4, p->d_cache_code, g, p->d_buf, d_ghost, fp, d_bias,
@@ -505,6 +525,7 @@ int create_common(metad_mesh** out, unsigned nx, unsigned ny, unsigned nzg, unsi
                   const double* mode) {
     METAD_REQUIRE(out && mode, "metad_mesh_create: null argument");
     METAD_REQUIRE(ntypes > 0, "Number of modes unequal number of particle types.");
+    if (ntypes > kSpreadModes) { set_error("cv.mesh: at most 1024 particle types"); return METAD_ERR_UNSUPPORTED; }
     if (!is_pow2(nx) || !is_pow2(ny) || !is_pow2(nzg)) {
         set_error("cv.mesh: the number of mesh points along every direction must be a power of two");
         return METAD_ERR_UNSUPPORTED;
@@ -527,6 +548,10 @@ int create_common(metad_mesh** out, unsigned nx, unsigned ny, unsigned nzg, unsi
     // 16^3 tiles once there are enough of them to fill the GPU twice, 8^3 otherwise
     unsigned lgT = (M / 4096 >= (size_t)2 * device_sm_count()) ? 4 : 3;
     if (nzl < 16) lgT = 3;
+    if (const char* e = getenv("METAD_TILE_LOG2")) {            // experiments: force 8^3 or 16^3 tiles
+        if (e[0] == '3') lgT = 3;
+        if (e[0] == '4' && nzl >= 16) lgT = 4;
+    }
     geom_set_dims(g, nx, ny, nzl, lgT);
     g.nzg = nzg; g.z0 = rank * nzl; g.slab = slab ? 1 : 0;
     p->n_ranks = n_ranks; p->rank = rank; p->nzg = nzg; p->kxl = nx / 2 / n_ranks;

@@ -653,24 +653,37 @@ MHD unsigned bank_order_slot(unsigned r, unsigned b, const unsigned* class_count
     }
     return slot;
 }
+// x coordinate (inside the tile) of the one cell of bank class `cls` in tile row (ly, lz), or >= T if the row has none
+template <int LGT> MHD unsigned bank_class_cell_x(unsigned cls, unsigned row /* ly + T * lz */) {
+    constexpr unsigned T = 1u << LGT, PX = T + 2 * kHaloX, PY = T + 2 * kHalo;
+    const unsigned ly = row & (T - 1), lz = row >> LGT;
+    return (cls - PX * (ly + PY * lz)) & 31u;
+}
+constexpr int kBankTable = 1024;      // ranks covered by the slot table (larger class populations use bank_order_slot directly)
 template <int LGT>
 __global__ void __launch_bounds__(kLayerThreads)
 mesh_bank_order_kernel(const unsigned* __restrict__ start, const unsigned* __restrict__ perm, unsigned* __restrict__ order) {
-    constexpr int CELLS = 1 << (3 * LGT), CPT = CELLS / kLayerThreads, SEGS = kLayerThreads / 32, SEG = CELLS / SEGS;
+    constexpr int T = 1 << LGT, CELLS = 1 << (3 * LGT), CPT = CELLS / kLayerThreads, SEGS = kLayerThreads / 32, ROWS = T * T / SEGS;
+    static_assert(T <= 32, "one cell per class and tile row");
     __shared__ unsigned s_start[CELLS + 1];
     __shared__ unsigned s_base[CELLS];              // rank inside its class of the first particle of a cell
     __shared__ unsigned s_seg[SEGS][32];
     __shared__ unsigned s_count[32];
+    __shared__ unsigned s_below[kBankTable];        // particles of rank < r, all classes: sum_c min(n_c, r)
+    __shared__ unsigned s_alive[kBankTable];        // bit c: class c has a particle of rank r
     const size_t key0 = (size_t)blockIdx.x << (3 * LGT);
     for (int i = threadIdx.x; i <= CELLS; i += kLayerThreads) s_start[i] = __ldg(start + key0 + i);
     __syncthreads();
     const unsigned tile_begin = s_start[0];
     if (s_start[CELLS] == tile_begin) return;
-    // class totals and the per-cell base ranks: thread (segment, class) walks the cells of its class in its segment
+    // class totals and the per-cell base ranks: thread (segment, class) walks the tile rows of its segment; a row holds
+    // at most one cell of its class
     const unsigned cls = threadIdx.x & 31, seg = threadIdx.x >> 5;
     unsigned cnt = 0;
-    for (unsigned c = seg * SEG; c < (seg + 1) * SEG; ++c)
-        if (bank_class<LGT>(c) == cls) cnt += s_start[c + 1] - s_start[c];
+    for (unsigned row = seg * ROWS; row < (seg + 1) * ROWS; ++row) {
+        const unsigned lx = bank_class_cell_x<LGT>(cls, row);
+        if (lx < (unsigned)T) { const unsigned c = (row << LGT) + lx; cnt += s_start[c + 1] - s_start[c]; }
+    }
     s_seg[seg][cls] = cnt;
     __syncthreads();
     if (threadIdx.x < 32) {
@@ -680,13 +693,30 @@ mesh_bank_order_kernel(const unsigned* __restrict__ start, const unsigned* __res
     }
     __syncthreads();
     unsigned run = s_seg[seg][cls];
-    for (unsigned c = seg * SEG; c < (seg + 1) * SEG; ++c)
-        if (bank_class<LGT>(c) == cls) { s_base[c] = run; run += s_start[c + 1] - s_start[c]; }
+    for (unsigned row = seg * ROWS; row < (seg + 1) * ROWS; ++row) {
+        const unsigned lx = bank_class_cell_x<LGT>(cls, row);
+        if (lx < (unsigned)T) { const unsigned c = (row << LGT) + lx; s_base[c] = run; run += s_start[c + 1] - s_start[c]; }
+    }
+    unsigned rmax = 0;
+    for (int c = 0; c < 32; ++c) rmax = max(rmax, s_count[c]);
+    for (unsigned r = threadIdx.x; r < min(rmax, (unsigned)kBankTable); r += kLayerThreads) {
+        unsigned below = 0, alive = 0;
+        for (unsigned c = 0; c < 32; ++c) {
+            const unsigned n = s_count[c];
+            below += min(n, r);
+            alive |= (n > r ? 1u : 0u) << c;
+        }
+        s_below[r] = below; s_alive[r] = alive;
+    }
     __syncthreads();
     for (int k = 0; k < CPT; ++k) {
         const unsigned c = threadIdx.x + k * kLayerThreads;
         const unsigned b = s_start[c], n = s_start[c + 1] - b, r0 = s_base[c], cb = bank_class<LGT>(c);
-        for (unsigned i = 0; i < n; ++i) order[tile_begin + bank_order_slot(r0 + i, cb, s_count)] = __ldg(perm + b + i);
+        for (unsigned i = 0; i < n; ++i) {
+            const unsigned r = r0 + i;
+            const unsigned slot = r < (unsigned)kBankTable ? s_below[r] + __popc(s_alive[r] & ((1u << cb) - 1u)) : bank_order_slot(r, cb, s_count);
+            order[tile_begin + slot] = __ldg(perm + b + i);
+        }
     }
 }
 
@@ -694,6 +724,7 @@ mesh_bank_order_kernel(const unsigned* __restrict__ start, const unsigned* __res
 // spread
 // ---------------------------------------------------------------------------------------------------
 constexpr int kSpreadThreads = 256;
+constexpr int kSpreadModes = 1024;     // most particle types supported (their mode coefficients are staged in shared memory)
 // counters[] (device, unsigned): [0] ticket, [1] particles handled by the direct path (drifted out of their padded
 // tile), [2] particles outside the slab (caller error), [3] cells past half of the fixed-point range
 struct SpreadOut {
@@ -709,11 +740,16 @@ struct SpreadOut {
 template <int LGT>
 __global__ void __launch_bounds__(kSpreadThreads)
 mesh_spread_kernel(const float4* __restrict__ postype, const unsigned* __restrict__ perm, const unsigned* __restrict__ tstart,
-                   Geom g, const float* __restrict__ mode, const float* __restrict__ d_fx, SpreadOut out) {
+                   Geom g, const float* __restrict__ mode, int ntypes, const float* __restrict__ d_fx, SpreadOut out) {
     constexpr int T = 1 << LGT, PX = T + 2 * kHaloX, PY = T + 2 * kHalo, PZ = PY, P3 = PX * PY * PZ;
     extern __shared__ __align__(16) int tile[];
     __shared__ double red[32];
     __shared__ bool is_last;
+    // mode coefficients in shared memory: a global load here shares a scoreboard with the position prefetch of the NEXT
+    // particle (ptxas puts all three loads of the loop on one), so its first consumer waited for that prefetch in every
+    // iteration (measured: 35 % of all stall samples)
+    float* s_mode = reinterpret_cast<float*>(tile + P3);          // [ntypes], behind the tile
+    for (int i = threadIdx.x; i < ntypes; i += kSpreadThreads) s_mode[i] = __ldg(mode + i);
     const unsigned s = __ldg(tstart + blockIdx.x), e = __ldg(tstart + blockIdx.x + 1);
     unsigned tx, ty, tz;
     tile_coords(blockIdx.x, g, tx, ty, tz);
@@ -737,7 +773,7 @@ mesh_spread_kernel(const float4* __restrict__ postype, const unsigned* __restric
             float4 p_next = make_float4(0.f, 0.f, 0.f, 0.f);
             if (jn < e) p_next = __ldg(postype + n_next);
             if (jn + kSpreadThreads < e) n_next2 = __ldg(perm + jn + kSpreadThreads);
-            const float a = __ldg(mode + __float_as_int(p.w));
+            const float a = s_mode[__float_as_int(p.w)];
             const Cell c = particle_cell(p, g);
             if (out.keys) out.keys[n] = key_of(c.ix, c.iy, (unsigned)(c.iz - (int)g.z0) & (g.nz - 1), g);
             const float3 sh = particle_shift(p, c, g);
@@ -869,8 +905,8 @@ __device__ __noinline__ float3 gather_direct(float4 p, GatherDirectArgs a) {
     return S;
 }
 
-template <int LGT>
-__global__ void __launch_bounds__(kGatherThreads, 3)
+template <int LGT, int THREADS = kGatherThreads, int MINB = 3>
+__global__ void __launch_bounds__(THREADS, MINB)
 mesh_gather_kernel(const float4* __restrict__ postype, const unsigned* __restrict__ tstart,
                    const float4* __restrict__ cache4, const uint2* __restrict__ cache_code,
                    const __grid_constant__ Geom g, const float* __restrict__ inv,
@@ -879,8 +915,8 @@ mesh_gather_kernel(const float4* __restrict__ postype, const unsigned* __restric
     constexpr int T = 1 << LGT, PX = T + 2 * kHaloX, PY = T + 2 * kHalo, PZ = PY, P3 = PX * PY * PZ;
     extern __shared__ __align__(16) float ftile[];          // P3 floats, then the staging buffers of the particle cache
     fft::peer_wait(sync);                                   // fused peer mode: the neighbours' halo planes of Re IFFT(G) have arrived
-    float4* s_q = reinterpret_cast<float4*>(ftile + P3);    // [2][kGatherThreads]
-    uint2* s_c = reinterpret_cast<uint2*>(s_q + 2 * kGatherThreads);
+    float4* s_q = reinterpret_cast<float4*>(ftile + P3);    // [2][THREADS]
+    uint2* s_c = reinterpret_cast<uint2*>(s_q + 2 * THREADS);
     __shared__ uint64_t bar;
     const unsigned s = __ldg(tstart + blockIdx.x), e = __ldg(tstart + blockIdx.x + 1);
     if (e == s) return;                                   // empty tile: nothing to interpolate
@@ -888,13 +924,13 @@ mesh_gather_kernel(const float4* __restrict__ postype, const unsigned* __restric
     tile_coords(blockIdx.x, g, tx, ty, tz);
     const int ox = (int)(tx << LGT) - kHaloX, oy = (int)(ty << LGT) - kHalo, oz = (int)(tz << LGT) - kHalo;
     const size_t plane = (size_t)g.nx * g.ny;
-    if (threadIdx.x == 0) cuda::ptx::mbarrier_init(&bar, kGatherThreads);
+    if (threadIdx.x == 0) cuda::ptx::mbarrier_init(&bar, THREADS);
     __syncthreads();
     // padded tile of Re IFFT(G): one bulk asynchronous copy (cp.async.bulk, TMA engine) per row, two if the row wraps in x;
     // completion is counted in bytes on an mbarrier
     {
         unsigned bytes = 0;
-        for (int row = threadIdx.x; row < PY * PZ; row += kGatherThreads) {
+        for (int row = threadIdx.x; row < PY * PZ; row += THREADS) {
             TileRow r;
             float* dst = ftile + row * PX;
             if (tile_row(ox, oy, oz, row % PY, row / PY, PX, g, r)) {
@@ -927,16 +963,16 @@ mesh_gather_kernel(const float4* __restrict__ postype, const unsigned* __restric
     __pipeline_commit();
     while (!cuda::ptx::mbarrier_try_wait_parity(&bar, 0)) {}
     __syncthreads();                                       // zero-filled rows (generic stores) are visible too
-    for (; j < e; j += kGatherThreads) {
-        const unsigned jn = j + kGatherThreads;
+    for (; j < e; j += THREADS) {
+        const unsigned jn = j + THREADS;
         if (jn < e) {
-            __pipeline_memcpy_async(s_q + (buf ^ 1) * kGatherThreads + threadIdx.x, cache4 + jn, sizeof(float4));
-            __pipeline_memcpy_async(s_c + (buf ^ 1) * kGatherThreads + threadIdx.x, cache_code + jn, sizeof(uint2));
+            __pipeline_memcpy_async(s_q + (buf ^ 1) * THREADS + threadIdx.x, cache4 + jn, sizeof(float4));
+            __pipeline_memcpy_async(s_c + (buf ^ 1) * THREADS + threadIdx.x, cache_code + jn, sizeof(uint2));
         }
         __pipeline_commit();
         __pipeline_wait_prior(1);                          // everything but the copies just issued has landed
-        const float4 q = s_q[buf * kGatherThreads + threadIdx.x];
-        const uint2 cn = s_c[buf * kGatherThreads + threadIdx.x];
+        const float4 q = s_q[buf * THREADS + threadIdx.x];
+        const uint2 cn = s_c[buf * THREADS + threadIdx.x];
         const unsigned code = cn.x, n = cn.y;
         buf ^= 1;
         float4 f = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -111,7 +111,8 @@ class LamellarSharded:
 def slab_of(z, L, nz, n_ranks):
     """Owner rank of a particle: the slab holding its global mesh plane (single-precision cell rule of the path)."""
     Lf = np.float32(L)
-    f = (np.asarray(z, np.float32) - (-(Lf / np.float32(2)))) / Lf
+    Linv = np.float32(1) / Lf                                   # HOOMD's BoxDim::makeFraction multiplies by the stored 1/L
+    f = (np.asarray(z, np.float32) - (-(Lf / np.float32(2)))) * Linv
     iz = (f * np.float32(nz)).astype(np.int64)
     iz[iz == nz] = 0
     return iz // (nz // n_ranks)
