@@ -85,6 +85,7 @@ def make_workload(name, shard=None):
 
 
 # ---------------------------------------------------------------------------------------------------- ours
+NO_PDL = False          # --no-pdl: A/B switch of programmatic dependent launch
 TILE_ORDER = None       # --tile-order: A/B switch of the order inside a tile (library default when None)
 
 
@@ -104,6 +105,8 @@ class MeshStep:
         self.mesh.set(4, 1)             # CUDA-graph replay of the per-call kernel sequence
         if TILE_ORDER is not None:
             self.mesh.set(6, {"bank": 1, "layer": 0}[TILE_ORDER])
+        if NO_PDL:
+            self.mesh.set(7, 0)
         self.d_pt = torch.from_numpy(w["postype"]).cuda()
         self.d_force = torch.empty_like(self.d_pt)
         self.t = 0
@@ -170,6 +173,8 @@ class MeshSlabStep(MeshStep):
         self.mesh = self.slab.r
         self.period = period
         self.mesh.set(0, period)
+        if NO_PDL:
+            self.mesh.set(7, 0)
         if mode == "p2p":
             self.mesh.set(5, 1 if sync == "fused" else 0)
             self.mesh.set(4, 1)         # the whole sharded step (incl. the inter-rank waits) replays from one CUDA graph
@@ -525,11 +530,13 @@ def main():
     ap.add_argument("--p2p-sync", default="barrier", choices=["fused", "barrier"],
                     help="peer-memory mode: separate barrier launches (default, measured faster) or inter-rank signal/wait inside the kernels")
     ap.add_argument("--tile-order", default=None, choices=["bank", "layer"], help="order of the particles inside a tile (single GPU; default: library default = bank)")
+    ap.add_argument("--no-pdl", action="store_true", help="launch the per-step kernels without programmatic dependent launch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     args = ap.parse_args()
-    global TILE_ORDER
+    global TILE_ORDER, NO_PDL
     TILE_ORDER = args.tile_order
+    NO_PDL = args.no_pdl
     if args.impl == "reference":
         run_reference(args)
     else:

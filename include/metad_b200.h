@@ -173,7 +173,8 @@ int metad_mesh_get(metad_mesh* p, int which, void* h_out);
  *        key 5 = peer-memory mode: 1 folds the inter-rank signal / wait into the producer / consumer kernels, 0 (default,
  *                measured faster) uses separate barrier launches
  *        key 6 = order of the particles inside a tile: 1 (default) bank order, 0 layer order (mesh_kernels.cuh); results
- *                do not depend on it                                                                                     */
+ *                do not depend on it
+ *        key 7 = programmatic dependent launch of the per-step kernels: 1 (default) on, 0 off                            */
 int metad_mesh_set(metad_mesh* p, int key, long value);
 
 /* ------------------------------------------------------------------------------------------------

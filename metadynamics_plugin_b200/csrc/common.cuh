@@ -21,6 +21,27 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 #define METAD_LAUNCH_CHECK() METAD_CUDA(cudaGetLastError())
 
+#ifdef __CUDACC__
+// Programmatic dependent launch (sm_90+).  Kernels of the per-step sequence are launched with the
+// programmatic-stream-serialization attribute (launch_pdl below): the next kernel's CTAs may be scheduled as soon as
+// every CTA of this one has passed pdl_trigger(), and they block in pdl_wait() until this grid has completed and its
+// memory is visible.  Everything before pdl_wait() must therefore touch only shared memory and data that no kernel of
+// the sequence writes (twiddle tables).  Without the attribute both are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <class... Exp, class... Act>
+inline cudaError_t launch_pdl(bool pdl, void (*kernel)(Exp...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Act&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<Exp>(args)...);
+}
+#endif
+
 #define METAD_REQUIRE(cond, msg)                 \
     do {                                         \
         if (!(cond)) {                           \

@@ -88,6 +88,7 @@ struct metad_mesh {
     // measured slower on B200 (2 GPUs, C4: 0.506 vs 0.464 ms/step) -- every producer CTA has to fence its peer stores at
     // system scope before taking the ticket, which stalls the CTA tails that otherwise drain asynchronously.
     bool fused_sync = false;
+    bool pdl = true;                            // programmatic dependent launch of the per-step kernels (knob 7)
     int order_kind = 1;                         // order inside a tile: 0 = layer order, 1 = bank order (knob 6)
     unsigned* d_sync = nullptr;                 // [4] phase epochs + [4] CTA tickets of the fused synchronisation
     // CUDA-graph replay of the per-call kernel sequence (metad_mesh_set key 4): everything a call enqueues after the
@@ -171,7 +172,7 @@ template <int LC> int run_x(metad_mesh* p, bool inverse, float2* io, const doubl
         PeerOut po;
         memset(&po, 0, sizeof po);
         if (peer_out) po = *peer_out;
-        fft_x_fwd_kernel<LC><<<rows / kLines, kLines * LC / kE, smem, st>>>(in, p->d_twx, io ? io : buf, lg_part, rows, po, ps);
+        METAD_CUDA(launch_pdl(p->pdl, fft_x_fwd_kernel<LC>, rows / kLines, kLines * LC / kE, smem, st, in, p->d_twx, io ? io : buf, lg_part, rows, po, ps));
         METAD_LAUNCH_CHECK();
         // the accumulator is empty again for the next spread (a plain memset runs at the full write bandwidth); in
         // peer-memory mode the two ghost planes (already pushed to the neighbours) are cleared by the same memset
@@ -179,7 +180,7 @@ template <int LC> int run_x(metad_mesh* p, bool inverse, float2* io, const doubl
         else METAD_CUDA(cudaMemsetAsync(p->d_mesh_i, 0, sizeof(int) * p->M(), st));
     } else {
         int rc = set_smem(fft_x_inv_kernel<LC>, smem); if (rc) return rc;
-        fft_x_inv_kernel<LC><<<rows / kLines, kLines * LC / kE, smem, st>>>(buf, p->d_twx, io ? io : buf, lg_part, rows, ps, sync ? table : nullptr, d_out);
+        METAD_CUDA(launch_pdl(p->pdl, fft_x_inv_kernel<LC>, rows / kLines, kLines * LC / kE, smem, st, buf, p->d_twx, io ? io : buf, lg_part, rows, ps, sync ? table : nullptr, d_out));
     }
     METAD_LAUNCH_CHECK();
     return METAD_OK;
@@ -203,20 +204,20 @@ template <int L> int run_y(metad_mesh* p, bool inverse, float2* buf, unsigned ro
         dim3 grid(row_len / (G * kLines), nz_rows);
         if (!inverse) {
             int rc = set_smem(fft_y_kernel<L, -1, G>, smem); if (rc) return rc;
-            fft_y_kernel<L, -1, G><<<grid, G * kLines * L / kE, smem, st>>>(buf, p->d_twy, row_len, po, lg_planes, ps);
+            METAD_CUDA(launch_pdl(p->pdl, fft_y_kernel<L, -1, G>, grid, G * kLines * L / kE, smem, st, buf, p->d_twy, row_len, po, lg_planes, ps));
         } else {
             int rc = set_smem(fft_y_kernel<L, +1, G>, smem); if (rc) return rc;
-            fft_y_kernel<L, +1, G><<<grid, G * kLines * L / kE, smem, st>>>(buf, p->d_twy, row_len, po, lg_planes, ps);
+            METAD_CUDA(launch_pdl(p->pdl, fft_y_kernel<L, +1, G>, grid, G * kLines * L / kE, smem, st, buf, p->d_twy, row_len, po, lg_planes, ps));
         }
     } else {
         const size_t smem = sizeof(float2) * (LayoutColWide<1>::size(L) + L);
         dim3 grid(row_len / kLines, nz_rows);
         if (!inverse) {
             int rc = set_smem(fft_y_kernel<L, -1, 1>, smem); if (rc) return rc;
-            fft_y_kernel<L, -1, 1><<<grid, kLines * L / kE, smem, st>>>(buf, p->d_twy, row_len, po, lg_planes, ps);
+            METAD_CUDA(launch_pdl(p->pdl, fft_y_kernel<L, -1, 1>, grid, kLines * L / kE, smem, st, buf, p->d_twy, row_len, po, lg_planes, ps));
         } else {
             int rc = set_smem(fft_y_kernel<L, +1, 1>, smem); if (rc) return rc;
-            fft_y_kernel<L, +1, 1><<<grid, kLines * L / kE, smem, st>>>(buf, p->d_twy, row_len, po, lg_planes, ps);
+            METAD_CUDA(launch_pdl(p->pdl, fft_y_kernel<L, +1, 1>, grid, kLines * L / kE, smem, st, buf, p->d_twy, row_len, po, lg_planes, ps));
         }
     }
     METAD_LAUNCH_CHECK();
@@ -245,7 +246,7 @@ template <int L> int run_z(metad_mesh* p, float2* buf, unsigned row_len, unsigne
     }
     int rc = set_smem(fft_z_fused_kernel<L>, smem); if (rc) return rc;
     const unsigned nblocks = cp.n_blocks_plane0 + (row_len / kLines) * ny;
-    fft_z_fused_kernel<L><<<nblocks, kLines * L / kE, smem, st>>>(buf, p->d_twz, cp);
+    METAD_CUDA(launch_pdl(p->pdl, fft_z_fused_kernel<L>, nblocks, kLines * L / kE, smem, st, buf, p->d_twz, cp));
     METAD_LAUNCH_CHECK();
     return METAD_OK;
 }
@@ -410,11 +411,11 @@ int enqueue_spread(metad_mesh* p, const float* d_postype, unsigned N, cudaStream
     out.cache_code = p->d_cache_code;
     if (g.lgT == 4) {
         rc = set_smem(mesh_spread_kernel<4>, tile_smem_bytes<4>() + sizeof(float) * kSpreadModes); if (rc) return rc;
-        mesh_spread_kernel<4><<<num_tiles(g), kSpreadThreads, tile_smem_bytes<4>() + sizeof(float) * p->ntypes, stream>>>((const float4*)d_postype, p->d_ranks, p->d_tstart, g,
-                                                                                           p->d_mode, p->ntypes, p->d_fx, out);
+        METAD_CUDA(launch_pdl(p->pdl, mesh_spread_kernel<4>, num_tiles(g), kSpreadThreads, tile_smem_bytes<4>() + sizeof(float) * p->ntypes, stream, (const float4*)d_postype, p->d_ranks, p->d_tstart, g,
+                                                                                           p->d_mode, p->ntypes, p->d_fx, out));
     } else {
-        mesh_spread_kernel<3><<<num_tiles(g), kSpreadThreads, tile_smem_bytes<3>() + sizeof(float) * p->ntypes, stream>>>((const float4*)d_postype, p->d_ranks, p->d_tstart, g,
-                                                                                           p->d_mode, p->ntypes, p->d_fx, out);
+        METAD_CUDA(launch_pdl(p->pdl, mesh_spread_kernel<3>, num_tiles(g), kSpreadThreads, tile_smem_bytes<3>() + sizeof(float) * p->ntypes, stream, (const float4*)d_postype, p->d_ranks, p->d_tstart, g,
+                                                                                           p->d_mode, p->ntypes, p->d_fx, out));
     }
     METAD_LAUNCH_CHECK();
     METAD_CUDA(cudaMemcpyAsync(p->h_counters, p->d_counters, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
@@ -496,8 +497,8 @@ int launch_gather(metad_mesh* p, const float* d_postype, const float* d_ghost, f
     {                                                                                                                             \
         const size_t sm = tile_smem_bytes<4>() + 2 * (T_) * (sizeof(float4) + sizeof(uint2));                                       \
         rc = set_smem(mesh_gather_kernel<4, T_, B_>, sm); if (rc) return rc;                                                       \
-        mesh_gather_kernel<4, T_, B_><<<num_tiles(g), T_, sm, stream>>>((const float4*)d_postype, p->d_tstart, p->d_cache4,        \
-                                                                        p->d_cache_code, g, p->d_buf, d_ghost, fp, d_bias, (float4*)d_force, ps); \
+        METAD_CUDA(launch_pdl(p->pdl, mesh_gather_kernel<4, T_, B_>, num_tiles(g), T_, sm, stream, (const float4*)d_postype, p->d_tstart, p->d_cache4,        \
+                                                                        p->d_cache_code, g, p->d_buf, d_ghost, fp, d_bias, (float4*)d_force, ps)); \
     }
         switch (variant) {
             case 1: METAD_GATHER_LAUNCH(256, 2) break;
@@ -513,9 +514,9 @@ int launch_gather(metad_mesh* p, const float* d_postype, const float* d_ghost, f
         }
 #undef METAD_GATHER_LAUNCH
     } else {
-        mesh_gather_kernel<3><<<num_tiles(g), kGatherThreads, gather_smem_bytes<3>(), stream>>>((const float4*)d_postype, p->d_tstart,
+        METAD_CUDA(launch_pdl(p->pdl, mesh_gather_kernel<3>, num_tiles(g), kGatherThreads, gather_smem_bytes<3>(), stream, (const float4*)d_postype, p->d_tstart,
                                                                                            p->d_cache4, p->d_cache_code, g, p->d_buf, d_ghost, fp, d_bias,
-                                                                                           (float4*)d_force, ps);
+                                                                                           (float4*)d_force, ps));
     }
     METAD_LAUNCH_CHECK();
     return mark(p, 9, stream);
@@ -771,8 +772,8 @@ int ensure_arena(metad_mesh* p) {
 }
 
 int p2p_barrier(metad_mesh* p, int wait, p2p::Publish pub, p2p::Reduce red, cudaStream_t st) {
-    p2p::barrier_kernel<<<1, 32, 0, st>>>(p->peers, p->lay.flags + 4 * p2p::kMaxPeers * sizeof(unsigned), p->d_epoch, wait, pub, red,
-                                           p->d_p2p_status);
+    METAD_CUDA(launch_pdl(p->pdl, p2p::barrier_kernel, 1, 32, 0, st, p->peers, p->lay.flags + 4 * p2p::kMaxPeers * sizeof(unsigned), p->d_epoch, wait, pub, red,
+                                           p->d_p2p_status));
     METAD_LAUNCH_CHECK();
     return METAD_OK;
 }
@@ -815,15 +816,15 @@ int p2p_stage(metad_mesh* p, int stage, int wait, const float* d_postype, unsign
             job.dst[2] = (int4*)gu; job.src[2] = (const int4*)above; job.n16[2] = (unsigned)(plane * sizeof(int) / 16);
             job.dst[3] = (int4*)(gu + plane * sizeof(int)); job.src[3] = (const int4*)(p->d_fx + 4); job.n16[3] = 1;
             if (fused) {
-                p2p::push_kernel<<<32, 256, 0, st>>>(job, p2p::Publish{p->d_sums, p->lay.sums, 4, 3}, make_sync(p, -1, 0));
+                METAD_CUDA(launch_pdl(p->pdl, p2p::push_kernel, 32, 256, 0, st, job, p2p::Publish{p->d_sums, p->lay.sums, 4, 3}, make_sync(p, -1, 0)));
             } else {
                 PeerSync none;
                 memset(&none, 0, sizeof none);
-                p2p::push_kernel<<<32, 256, 0, st>>>(job, p2p::Publish{nullptr, 0, 0, 0}, none);
+                METAD_CUDA(launch_pdl(p->pdl, p2p::push_kernel, 32, 256, 0, st, job, p2p::Publish{nullptr, 0, 0, 0}, none));
             }
             METAD_LAUNCH_CHECK();
             if (!wait) {    // emulation: the partial sums must be in place before ANY rank reduces them in stage 1
-                p2p::push_scalars_kernel<<<1, 64, 0, st>>>(p->peers, p->lay.sums, 4, p->d_sums, 3);
+                METAD_CUDA(launch_pdl(p->pdl, p2p::push_scalars_kernel, 1, 64, 0, st, p->peers, p->lay.sums, 4, p->d_sums, 3));
                 METAD_LAUNCH_CHECK();
             }
             return markp(p, 2, st);
@@ -875,7 +876,7 @@ int p2p_stage(metad_mesh* p, int stage, int wait, const float* d_postype, unsign
             METAD_DISPATCH_LEN(g.ny, (run_y<LL>(p, true, pen, p->kxl, p->nzg, st, &po))); if (rc) return rc;
             rc = markp(p, 8, st); if (rc) return rc;
             if (!wait) {    // emulation: see stage 0
-                p2p::push_scalars_kernel<<<1, 64, 0, st>>>(p->peers, p->lay.cv, 1, p->d_cv_partial, 1);
+                METAD_CUDA(launch_pdl(p->pdl, p2p::push_scalars_kernel, 1, 64, 0, st, p->peers, p->lay.cv, 1, p->d_cv_partial, 1));
                 METAD_LAUNCH_CHECK();
             }
             return METAD_OK;
@@ -902,11 +903,11 @@ int p2p_stage(metad_mesh* p, int stage, int wait, const float* d_postype, unsign
             job.dst[1] = (int4*)(p->peers.arena[up] + p->lay.ghost_inv);
             job.src[1] = (const int4*)(p->d_buf + plane * (g.nz - 1)); job.n16[1] = (unsigned)(plane * sizeof(float) / 16);
             if (fused) {
-                p2p::push_kernel<<<32, 256, 0, st>>>(job, p2p::Publish{nullptr, 0, 0, 0}, make_sync(p, -1, 3));
+                METAD_CUDA(launch_pdl(p->pdl, p2p::push_kernel, 32, 256, 0, st, job, p2p::Publish{nullptr, 0, 0, 0}, make_sync(p, -1, 3)));
             } else {
                 PeerSync none;
                 memset(&none, 0, sizeof none);
-                p2p::push_kernel<<<32, 256, 0, st>>>(job, p2p::Publish{nullptr, 0, 0, 0}, none);
+                METAD_CUDA(launch_pdl(p->pdl, p2p::push_kernel, 32, 256, 0, st, job, p2p::Publish{nullptr, 0, 0, 0}, none));
             }
             METAD_LAUNCH_CHECK();
             return markp(p, 11, st);
@@ -1097,6 +1098,7 @@ extern "C" int metad_mesh_set(metad_mesh* p, int key, long value) {
         case 4: p->graph_mode = value != 0; return METAD_OK;
         case 5: p->fused_sync = value != 0; return METAD_OK;
         case 6: p->order_kind = value != 0 ? 1 : 0; p->order_valid = false; return METAD_OK;
+        case 7: p->pdl = value != 0; return METAD_OK;
         default: set_error("metad_mesh_set: unknown key"); return METAD_ERR_INVALID;
     }
 }

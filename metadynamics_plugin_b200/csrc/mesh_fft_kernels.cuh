@@ -187,6 +187,7 @@ fft_x_fwd_kernel(DensityIn in, const float2* __restrict__ g_tw /* length 2*LC */
     const int nthr = kLines * LC / kE;
     const size_t row0 = (size_t)blockIdx.x * kLines;
     load_twiddles<2 * LC>(s_tw, g_tw);
+    pdl_wait(); pdl_trigger();
     peer_wait(sync);                                         // halos and partial sums of every rank have arrived
     const float inv_scale = __ldg(in.d_fx + 1);
     __shared__ double s_sum_a;
@@ -284,6 +285,7 @@ fft_x_inv_kernel(float2* buf, const float2* __restrict__ g_tw, const float2* in,
     const int nthr = kLines * LC / kE;
     const size_t row0 = (size_t)blockIdx.x * kLines;
     load_twiddles<2 * LC>(s_tw, g_tw);
+    pdl_wait(); pdl_trigger();
     peer_wait(sync);                                         // planes and CV partials of every rank have arrived
     if (cv_table && blockIdx.x == 0 && threadIdx.x == 0) {   // the CV: rank-ordered sum of the partials
         double cv = 0.0;
@@ -329,6 +331,7 @@ fft_y_kernel(float2* __restrict__ buf, const float2* __restrict__ g_tw, unsigned
     float2* s_tw = smem + Lay::size(L);
     const size_t base = (size_t)blockIdx.y * L * nxh + (size_t)blockIdx.x * W;
     load_twiddles<L>(s_tw, g_tw);
+    pdl_wait(); pdl_trigger();
     peer_wait(sync);                                         // forward sweep: every rank's share of my pencil has arrived
     float4* tile4 = reinterpret_cast<float4*>(tile);
 #pragma unroll
@@ -499,6 +502,7 @@ template <int L>
 __global__ void __launch_bounds__(kLines * L / kE, (kLines * L / kE) <= 512 ? 3 : 1)
 fft_z_fused_kernel(float2* __restrict__ buf, const float2* __restrict__ g_tw, ConvParams cp) {
     extern __shared__ float2 smem[];
+    pdl_wait(); pdl_trigger();
     if (blockIdx.x < cp.n_blocks_plane0) {
         z_plane0_body<L>(buf, g_tw, cp, blockIdx.x, smem);
     } else {

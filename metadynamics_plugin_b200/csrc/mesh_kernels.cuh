@@ -749,6 +749,9 @@ mesh_spread_kernel(const float4* __restrict__ postype, const unsigned* __restric
     // particle (ptxas puts all three loads of the loop on one), so its first consumer waited for that prefetch in every
     // iteration (measured: 35 % of all stall samples)
     float* s_mode = reinterpret_cast<float*>(tile + P3);          // [ntypes], behind the tile
+    // the tile is cleared before the programmatic-launch wait: this part overlaps the tail of the previous kernel
+    for (int i = threadIdx.x; i < P3 / 4; i += kSpreadThreads) reinterpret_cast<int4*>(tile)[i] = make_int4(0, 0, 0, 0);
+    pdl_wait(); pdl_trigger();
     for (int i = threadIdx.x; i < ntypes; i += kSpreadThreads) s_mode[i] = __ldg(mode + i);
     const unsigned s = __ldg(tstart + blockIdx.x), e = __ldg(tstart + blockIdx.x + 1);
     unsigned tx, ty, tz;
@@ -756,7 +759,6 @@ mesh_spread_kernel(const float4* __restrict__ postype, const unsigned* __restric
     const int ox = (int)(tx << LGT) - kHaloX, oy = (int)(ty << LGT) - kHalo, oz = (int)(tz << LGT) - kHalo;
     double sq = 0.0, s1 = 0.0;
     if (e > s) {
-        for (int i = threadIdx.x; i < P3 / 4; i += kSpreadThreads) reinterpret_cast<int4*>(tile)[i] = make_int4(0, 0, 0, 0);
         __syncthreads();
         const float scale = __ldg(d_fx);
         unsigned strays = 0, foreign = 0;
@@ -914,6 +916,7 @@ mesh_gather_kernel(const float4* __restrict__ postype, const unsigned* __restric
                    const double* __restrict__ d_bias, float4* __restrict__ force, const __grid_constant__ fft::PeerSync sync) {
     constexpr int T = 1 << LGT, PX = T + 2 * kHaloX, PY = T + 2 * kHalo, PZ = PY, P3 = PX * PY * PZ;
     extern __shared__ __align__(16) float ftile[];          // P3 floats, then the staging buffers of the particle cache
+    pdl_wait(); pdl_trigger();
     fft::peer_wait(sync);                                   // fused peer mode: the neighbours' halo planes of Re IFFT(G) have arrived
     float4* s_q = reinterpret_cast<float4*>(ftile + P3);    // [2][THREADS]
     uint2* s_c = reinterpret_cast<uint2*>(s_q + 2 * THREADS);

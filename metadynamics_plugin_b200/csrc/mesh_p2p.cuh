@@ -53,6 +53,7 @@ struct PushJob {
 // the phase (fft::peer_signal)
 __global__ void __launch_bounds__(256) push_kernel(PushJob job, Publish pub, const __grid_constant__ fft::PeerSync sync) {
     const unsigned stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_wait(); pdl_trigger();
     fft::peer_wait(sync);
 #pragma unroll
     for (int s = 0; s < 4; ++s)
@@ -66,6 +67,7 @@ __global__ void __launch_bounds__(256) push_kernel(PushJob job, Publish pub, con
 // broadcast of a few doubles into slot [rank] of every peer's table
 __global__ void push_scalars_kernel(PeerTable pt, size_t table_offset, unsigned per_rank, const double* __restrict__ src, unsigned n) {
     const unsigned r = threadIdx.x / 8, k = threadIdx.x % 8;
+    pdl_wait(); pdl_trigger();
     if (r < pt.n && k < n) reinterpret_cast<double*>(pt.arena[r] + table_offset)[pt.rank * per_rank + k] = src[k];
 }
 
@@ -91,6 +93,7 @@ struct Reduce { const double* table; unsigned per_rank, width; double* out; };
 __global__ void barrier_kernel(PeerTable pt, size_t flags_offset, unsigned* __restrict__ d_epoch, int wait, Publish pub, Reduce red,
                                unsigned* __restrict__ status) {
     const unsigned lane = threadIdx.x;
+    pdl_wait(); pdl_trigger();
     if (pub.n) {
         const unsigned r = lane / 4, k = lane % 4;          // up to 8 ranks x 4 values
         if (r < pt.n && k < pub.n) reinterpret_cast<double*>(pt.arena[r] + pub.table_offset)[pt.rank * pub.per_rank + k] = pub.src[k];
