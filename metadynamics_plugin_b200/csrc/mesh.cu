@@ -374,7 +374,8 @@ template <int LGT> size_t tile_smem_bytes() {
     return sizeof(int) * (size_t)((1 << LGT) + 2 * kHaloX) * ((1 << LGT) + 2 * kHalo) * ((1 << LGT) + 2 * kHalo);
 }
 // gather: the tile plus two staging buffers of the particle cache (float4 + uint2 per thread)
-template <int LGT> size_t gather_smem_bytes() { return tile_smem_bytes<LGT>() + 2 * kGatherThreads * (sizeof(float4) + sizeof(uint2)); }
+template <int LGT> size_t spread_smem_bytes(int ntypes) { return tile_smem_bytes<LGT>() + kSpreadStages * kSpreadThreads * sizeof(float4) + sizeof(float) * ntypes; }
+template <int LGT> size_t gather_smem_bytes() { return tile_smem_bytes<LGT>() + kGatherStages * kGatherThreads * (sizeof(float4) + sizeof(uint2)); }
 
 // tile order of this call (rebuilt if needed) + spread into the integer mesh; sums -> p->d_sums
 // host-side decision + (rare) rebuild of the tile order: never part of a captured graph
@@ -410,11 +411,11 @@ int enqueue_spread(metad_mesh* p, const float* d_postype, unsigned N, cudaStream
     out.cache4 = p->d_cache4;
     out.cache_code = p->d_cache_code;
     if (g.lgT == 4) {
-        rc = set_smem(mesh_spread_kernel<4>, tile_smem_bytes<4>() + sizeof(float) * kSpreadModes); if (rc) return rc;
-        METAD_CUDA(launch_pdl(p->pdl, mesh_spread_kernel<4>, num_tiles(g), kSpreadThreads, tile_smem_bytes<4>() + sizeof(float) * p->ntypes, stream, (const float4*)d_postype, p->d_ranks, p->d_tstart, g,
+        rc = set_smem(mesh_spread_kernel<4>, spread_smem_bytes<4>(kSpreadModes)); if (rc) return rc;
+        METAD_CUDA(launch_pdl(p->pdl, mesh_spread_kernel<4>, num_tiles(g), kSpreadThreads, spread_smem_bytes<4>(p->ntypes), stream, (const float4*)d_postype, p->d_ranks, p->d_tstart, g,
                                                                                            p->d_mode, p->ntypes, p->d_fx, out));
     } else {
-        METAD_CUDA(launch_pdl(p->pdl, mesh_spread_kernel<3>, num_tiles(g), kSpreadThreads, tile_smem_bytes<3>() + sizeof(float) * p->ntypes, stream, (const float4*)d_postype, p->d_ranks, p->d_tstart, g,
+        METAD_CUDA(launch_pdl(p->pdl, mesh_spread_kernel<3>, num_tiles(g), kSpreadThreads, spread_smem_bytes<3>(p->ntypes), stream, (const float4*)d_postype, p->d_ranks, p->d_tstart, g,
                                                                                            p->d_mode, p->ntypes, p->d_fx, out));
     }
     METAD_LAUNCH_CHECK();
@@ -495,7 +496,7 @@ int launch_gather(metad_mesh* p, const float* d_postype, const float* d_ghost, f
         static const int variant = getenv("METAD_GATHER_VARIANT") ? atoi(getenv("METAD_GATHER_VARIANT")) : 2;
 #define METAD_GATHER_LAUNCH(T_, B_)                                                                                               \
     {                                                                                                                             \
-        const size_t sm = tile_smem_bytes<4>() + 2 * (T_) * (sizeof(float4) + sizeof(uint2));                                       \
+        const size_t sm = tile_smem_bytes<4>() + kGatherStages * (T_) * (sizeof(float4) + sizeof(uint2));                                       \
         rc = set_smem(mesh_gather_kernel<4, T_, B_>, sm); if (rc) return rc;                                                       \
         METAD_CUDA(launch_pdl(p->pdl, mesh_gather_kernel<4, T_, B_>, num_tiles(g), T_, sm, stream, (const float4*)d_postype, p->d_tstart, p->d_cache4,        \
                                                                         p->d_cache_code, g, p->d_buf, d_ghost, fp, d_bias, (float4*)d_force, ps)); \

@@ -724,6 +724,8 @@ mesh_bank_order_kernel(const unsigned* __restrict__ start, const unsigned* __res
 // spread
 // ---------------------------------------------------------------------------------------------------
 constexpr int kSpreadThreads = 256;
+constexpr int kSpreadL2Lead = 4;      // iterations between the L2 prefetch of a permutation index and its load
+constexpr int kSpreadStages = 3;       // staging buffers of the positions (kSpreadStages - 1 particles in flight per thread)
 constexpr int kSpreadModes = 1024;     // most particle types supported (their mode coefficients are staged in shared memory)
 // counters[] (device, unsigned): [0] ticket, [1] particles handled by the direct path (drifted out of their padded
 // tile), [2] particles outside the slab (caller error), [3] cells past half of the fixed-point range
@@ -748,7 +750,8 @@ mesh_spread_kernel(const float4* __restrict__ postype, const unsigned* __restric
     // mode coefficients in shared memory: a global load here shares a scoreboard with the position prefetch of the NEXT
     // particle (ptxas puts all three loads of the loop on one), so its first consumer waited for that prefetch in every
     // iteration (measured: 35 % of all stall samples)
-    float* s_mode = reinterpret_cast<float*>(tile + P3);          // [ntypes], behind the tile
+    float4* s_pos = reinterpret_cast<float4*>(tile + P3);         // [kSpreadStages][kSpreadThreads] staged positions, behind the tile
+    float* s_mode = reinterpret_cast<float*>(s_pos + kSpreadStages * kSpreadThreads);       // [ntypes]
     // the tile is cleared before the programmatic-launch wait: this part overlaps the tail of the previous kernel
     for (int i = threadIdx.x; i < P3 / 4; i += kSpreadThreads) reinterpret_cast<int4*>(tile)[i] = make_int4(0, 0, 0, 0);
     pdl_wait(); pdl_trigger();
@@ -762,19 +765,38 @@ mesh_spread_kernel(const float4* __restrict__ postype, const unsigned* __restric
         __syncthreads();
         const float scale = __ldg(d_fx);
         unsigned strays = 0, foreign = 0;
-        // software pipeline: the index and the position of the next particle are in flight while this one is spread
-        // (the index two particles ahead, so that the position load of the next one never waits for its index)
+        // software pipeline: positions are staged through shared memory with asynchronous copies, kSpreadStages - 1
+        // particles ahead (one iteration is shorter than the loaded DRAM latency: with one position in flight 27 % of
+        // all stall samples sat on its first use); the index of the particle after those is in flight in a register
+        constexpr int D = kSpreadStages - 1, PA = 2;      // positions D particles ahead, indices PA particles further
         unsigned j = s + threadIdx.x;
-        unsigned n = 0, n_next = 0;
-        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j < e) { n = __ldg(perm + j); p = __ldg(postype + n); }
-        if (j + kSpreadThreads < e) n_next = __ldg(perm + j + kSpreadThreads);
+        unsigned nq[D + PA];
+        int buf = 0;
+#pragma unroll
+        for (int d = 0; d < D + PA; ++d) {
+            const unsigned jd = j + d * kSpreadThreads;
+            nq[d] = jd < e ? __ldg(perm + jd) : 0u;
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            if (j + d * kSpreadThreads < e) __pipeline_memcpy_async(s_pos + d * kSpreadThreads + threadIdx.x, postype + nq[d], sizeof(float4));
+            __pipeline_commit();
+        }
         while (j < e) {
-            const unsigned jn = j + kSpreadThreads;
-            unsigned n_next2 = 0;
-            float4 p_next = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (jn < e) p_next = __ldg(postype + n_next);
-            if (jn + kSpreadThreads < e) n_next2 = __ldg(perm + jn + kSpreadThreads);
+            const unsigned jn = j + D * kSpreadThreads;
+            int bn = buf + D;
+            if (bn >= kSpreadStages) bn -= kSpreadStages;
+            if (jn < e) __pipeline_memcpy_async(s_pos + bn * kSpreadThreads + threadIdx.x, postype + nq[D], sizeof(float4));
+            __pipeline_commit();
+            const unsigned n_far = (jn + PA * kSpreadThreads < e) ? __ldg(perm + jn + PA * kSpreadThreads) : 0u;
+            // the register ring shifts at the end of the iteration, so this load must land within one iteration: an L2
+            // prefetch a few iterations earlier (one lane per warp: a warp reads one 128-byte line) turns it into an L2 hit
+            if ((threadIdx.x & 31) == 0 && jn + (PA + kSpreadL2Lead) * kSpreadThreads < e)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(perm + jn + (PA + kSpreadL2Lead) * kSpreadThreads));
+            __pipeline_wait_prior(D);
+            const float4 p = s_pos[buf * kSpreadThreads + threadIdx.x];
+            const unsigned n = nq[0];
+            if (++buf == kSpreadStages) buf = 0;
             const float a = s_mode[__float_as_int(p.w)];
             const Cell c = particle_cell(p, g);
             if (out.keys) out.keys[n] = key_of(c.ix, c.iy, (unsigned)(c.iz - (int)g.z0) & (g.nz - 1), g);
@@ -819,7 +841,10 @@ mesh_spread_kernel(const float4* __restrict__ postype, const unsigned* __restric
             } else {
                 ++foreign;
             }
-            j = jn; n = n_next; n_next = n_next2; p = p_next;
+            j += kSpreadThreads;
+#pragma unroll
+            for (int d = 0; d < D + PA - 1; ++d) nq[d] = nq[d + 1];
+            nq[D + PA - 1] = n_far;
         }
         if (strays) atomicAdd(out.counters + 1, strays);
         if (foreign) atomicAdd(out.counters + 2, foreign);
@@ -881,6 +906,7 @@ mesh_spread_kernel(const float4* __restrict__ postype, const unsigned* __restric
 // gather: one CTA per tile; shared tile of Re(IFFT(G)) with halo; one thread per particle of the tile
 // ---------------------------------------------------------------------------------------------------
 constexpr int kGatherThreads = 256;
+constexpr int kGatherStages = 4;       // staging buffers of the particle cache (kGatherStages - 1 entries in flight per thread)
 
 // slow path of a particle that drifted out of its padded tile: the 27 taps come from global memory.  Not inlined and
 // fed by value, so that the fast path keeps its weights in registers; recomputes cell and weights from the position.
@@ -918,8 +944,8 @@ mesh_gather_kernel(const float4* __restrict__ postype, const unsigned* __restric
     extern __shared__ __align__(16) float ftile[];          // P3 floats, then the staging buffers of the particle cache
     pdl_wait(); pdl_trigger();
     fft::peer_wait(sync);                                   // fused peer mode: the neighbours' halo planes of Re IFFT(G) have arrived
-    float4* s_q = reinterpret_cast<float4*>(ftile + P3);    // [2][THREADS]
-    uint2* s_c = reinterpret_cast<uint2*>(s_q + 2 * THREADS);
+    float4* s_q = reinterpret_cast<float4*>(ftile + P3);    // [kGatherStages][THREADS]
+    uint2* s_c = reinterpret_cast<uint2*>(s_q + kGatherStages * THREADS);
     __shared__ uint64_t bar;
     const unsigned s = __ldg(tstart + blockIdx.x), e = __ldg(tstart + blockIdx.x + 1);
     if (e == s) return;                                   // empty tile: nothing to interpolate
@@ -956,28 +982,36 @@ mesh_gather_kernel(const float4* __restrict__ postype, const unsigned* __restric
     }
     const float scale = (float)(fp.two_over_n * *d_bias);
     // one thread per particle of the tile; offsets, amplitude, padded-tile cell and particle index come from the cache
-    // the spread wrote.  The entries are staged through shared memory with asynchronous copies, one iteration ahead.
+    // the spread wrote.  The entries are staged through shared memory with asynchronous copies.
+    // kGatherStages - 1 entries in flight per thread: one iteration of this loop is shorter than the loaded DRAM latency
+    // (with a single entry in flight 26 % of all stall samples sat on the wait below)
     unsigned j = s + threadIdx.x;
     int buf = 0;
-    if (j < e) {
-        __pipeline_memcpy_async(s_q + threadIdx.x, cache4 + j, sizeof(float4));
-        __pipeline_memcpy_async(s_c + threadIdx.x, cache_code + j, sizeof(uint2));
+#pragma unroll
+    for (int d = 0; d < kGatherStages - 1; ++d) {
+        const unsigned jd = j + d * THREADS;
+        if (jd < e) {
+            __pipeline_memcpy_async(s_q + d * THREADS + threadIdx.x, cache4 + jd, sizeof(float4));
+            __pipeline_memcpy_async(s_c + d * THREADS + threadIdx.x, cache_code + jd, sizeof(uint2));
+        }
+        __pipeline_commit();
     }
-    __pipeline_commit();
     while (!cuda::ptx::mbarrier_try_wait_parity(&bar, 0)) {}
     __syncthreads();                                       // zero-filled rows (generic stores) are visible too
     for (; j < e; j += THREADS) {
-        const unsigned jn = j + THREADS;
+        const unsigned jn = j + (kGatherStages - 1) * THREADS;
+        int bn = buf + kGatherStages - 1;
+        if (bn >= kGatherStages) bn -= kGatherStages;
         if (jn < e) {
-            __pipeline_memcpy_async(s_q + (buf ^ 1) * THREADS + threadIdx.x, cache4 + jn, sizeof(float4));
-            __pipeline_memcpy_async(s_c + (buf ^ 1) * THREADS + threadIdx.x, cache_code + jn, sizeof(uint2));
+            __pipeline_memcpy_async(s_q + bn * THREADS + threadIdx.x, cache4 + jn, sizeof(float4));
+            __pipeline_memcpy_async(s_c + bn * THREADS + threadIdx.x, cache_code + jn, sizeof(uint2));
         }
         __pipeline_commit();
-        __pipeline_wait_prior(1);                          // everything but the copies just issued has landed
+        __pipeline_wait_prior(kGatherStages - 1);          // everything but the newest kGatherStages - 1 groups has landed
         const float4 q = s_q[buf * THREADS + threadIdx.x];
         const uint2 cn = s_c[buf * THREADS + threadIdx.x];
         const unsigned code = cn.x, n = cn.y;
-        buf ^= 1;
+        if (++buf == kGatherStages) buf = 0;
         float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
         if (code & kCacheOwned) {
             float Sx, Sy, Sz;
