@@ -113,12 +113,15 @@ grid_step_kernel(GridParams P, GridArrays A, const double* __restrict__ cv_in, d
     __shared__ double red[32];
     __shared__ double sh_oob;
 
+    // every thread reads the CV values itself: the hand-off lanes below do not wait for thread 0 on steps without a deposit
+    double mine[kMaxCV];
+    for (int i = 0; i < P.d; ++i) mine[i] = cv_in[i];
     if (threadIdx.x == 0) {
         sh_oob = 0.0;
-        for (int i = 0; i < P.d; ++i) cur[i] = cv_in[i];
+        for (int i = 0; i < P.d; ++i) cur[i] = mine[i];
         unsigned idx;
         const bool on = grid_bin(P, cur, &idx);
-        if (on) A.hist_delta[idx] += 1u;
+        if (on) atomicAdd(A.hist_delta + idx, 1u);            // no return value: the kernel does not wait for the round trip
         if (deposit) {
             if (on) { A.sigma_grid_delta[idx] += P.sigma_det; A.hist_gauss_delta[idx] += 1u; }
             double scal = 1.0;
@@ -129,7 +132,7 @@ grid_step_kernel(GridParams P, GridArrays A, const double* __restrict__ cv_in, d
             sh_scal = scal;
         }
     }
-    __syncthreads();
+    if (deposit) __syncthreads();
 
     if (deposit) {
         const double scal = sh_scal;
@@ -186,9 +189,9 @@ grid_step_kernel(GridParams P, GridArrays A, const double* __restrict__ cv_in, d
             const int cv = lane >> 1, side = lane & 1;          // side 0: lower sample, 1: upper sample
             const double delta = grid_delta_of(P, cv);
             double v[kMaxCV];
-            for (int i = 0; i < d; ++i) v[i] = cur[i];
-            if (cur[cv] - delta < P.cv_min[cv]) { if (side) v[cv] += delta; }              // forward: (V(s+d) - V(s))/d
-            else if (cur[cv] + delta > P.cv_max[cv]) { if (!side) v[cv] -= delta; }        // backward: (V(s) - V(s-d))/d
+            for (int i = 0; i < d; ++i) v[i] = mine[i];
+            if (mine[cv] - delta < P.cv_min[cv]) { if (side) v[cv] += delta; }              // forward: (V(s+d) - V(s))/d
+            else if (mine[cv] + delta > P.cv_max[cv]) { if (!side) v[cv] -= delta; }        // backward: (V(s) - V(s-d))/d
             else v[cv] += side ? delta : -delta;                                            // central
             y = grid_interpolate(P, A.grid, v, &oob);
         } else if (lane == 2 * d) {
@@ -203,14 +206,14 @@ grid_step_kernel(GridParams P, GridArrays A, const double* __restrict__ cv_in, d
         if (lane < 2 * d && !(lane & 1)) {
             const int cv = lane >> 1;
             const double delta = grid_delta_of(P, cv);
-            const bool one_sided = (cur[cv] - delta < P.cv_min[cv]) || (cur[cv] + delta > P.cv_max[cv]);
+            const bool one_sided = (mine[cv] - delta < P.cv_min[cv]) || (mine[cv] + delta > P.cv_max[cv]);
             bias_out[cv] = (y_up - y) / (one_sided ? delta : 2.0 * delta);
         }
         if (lane == 2 * d) A.scalars[0] = y;
         if (lane == 2 * d + 1) A.scalars[1] = y;
         if (lane == 0) {
             if (deposit) A.scalars[2] += 1.0;
-            A.scalars[3] += sh_oob + oob_sum;
+            A.scalars[3] += sh_oob + oob_sum;                   // lane 0 is thread 0: sh_oob is its own write
         }
     }
 }
