@@ -79,8 +79,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+PARTICLE_ORDER = "sorted"   # --order: C3 / C4 input order, cell-sorted (an MD engine's spatial sort; headline) or random (stress)
+
+
 def make_workload(name, shard=None):
     from metadynamics_plugin_b200 import workloads
+    if name in ("C3", "C4") and PARTICLE_ORDER == "random":
+        w = {"C3": workloads.c3, "C4": workloads.c4}[name](sort=False)
+        w["order"] = "random particle order (stress case, SURVEY 8d C3 ii)"
+        return w
     return {"C1": workloads.c1, "C2": workloads.c2, "C3": workloads.c3, "C4": workloads.c4, "C5": workloads.c5}[name]()
 
 
@@ -398,7 +405,7 @@ def run_ours(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32 (fixed-point density, fp64 accumulation of the CV)", "data": "synthetic",
         "ns_per_particle_step": ms_per_step * 1e6 / n_global,
-        "config": {"workload": "%s: %s" % (w["name"], describe(w)), "N": n_global, "l2": "inputs larger than L2 (no flush)",
+        "config": {"workload": "%s: %s" % (w["name"], describe(w)) + (", " + w["order"] if "order" in w else ""), "N": n_global, "l2": "inputs larger than L2 (no flush)",
                    "parallelism": "1 GPU" if world == 1 else (("z-slab mesh + particle sharding over %d GPUs, %s" % (
                        world, "peer memory over NVLink: transposes fused into the FFT sweeps, pushed halos, flag barriers (no NCCL call in a step; "
                        "CV agrees with the NCCL path to %.1e)" % runner.cv_check if runner.comm_mode == "p2p" else "NCCL all-to-all / halo exchange / all-reduce"))
@@ -411,6 +418,10 @@ def run_ours(args):
         "gpu_launches": runner.launches_per_step * args.steps + getattr(runner, "launches_per_rebuild", 0) * rebuilds_timed,
         "clocks": clocks,
     }
+    # the same fractions against the nominal 8 TB/s of the north star (SURVEY 8d names both denominators)
+    roofline["frac_nominal_8TBps"] = roofline["achieved"] / (8000.0 * world)
+    if "step_frac" in roofline:
+        roofline["step_frac_nominal_8TBps"] = roofline["step_frac"] * peak / 8000.0
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(w, budget_s=args.cpu_budget)
@@ -530,11 +541,13 @@ def main():
     ap.add_argument("--p2p-sync", default="barrier", choices=["fused", "barrier"],
                     help="peer-memory mode: separate barrier launches (default, measured faster) or inter-rank signal/wait inside the kernels")
     ap.add_argument("--tile-order", default=None, choices=["bank", "layer"], help="order of the particles inside a tile (single GPU; default: library default = bank)")
+    ap.add_argument("--order", default="sorted", choices=["sorted", "random"], help="C3 / C4: particle order of the input (cell-sorted headline, random stress case)")
     ap.add_argument("--no-pdl", action="store_true", help="launch the per-step kernels without programmatic dependent launch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     args = ap.parse_args()
-    global TILE_ORDER, NO_PDL
+    global TILE_ORDER, NO_PDL, PARTICLE_ORDER
+    PARTICLE_ORDER = args.order
     TILE_ORDER = args.tile_order
     NO_PDL = args.no_pdl
     if args.impl == "reference":

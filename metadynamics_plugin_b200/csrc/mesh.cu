@@ -493,7 +493,10 @@ int launch_gather(metad_mesh* p, const float* d_postype, const float* d_ghost, f
         // CTA size / residency of the gather.  Measured on B200 (C4, ms per launch): 256 threads x 3 CTAs/SM (80 registers, the loop
         // state spills) 0.238; 256 x 2 0.210; 192 x 3 (96 registers, no spill) 0.201; 128 x 5 0.216; 128 x 4 0.212; 192 x 4 0.247.
         // METAD_GATHER_VARIANT selects the others for experiments.
-        static const int variant = getenv("METAD_GATHER_VARIANT") ? atoi(getenv("METAD_GATHER_VARIANT")) : 2;
+        // With at most 5 tiles per SM (C3, or a rank's slab on 8 GPUs) 128 x 5 keeps every CTA resident in one round:
+        // C3 0.0266 -> 0.0245 ms.
+        static const int forced = getenv("METAD_GATHER_VARIANT") ? atoi(getenv("METAD_GATHER_VARIANT")) : -1;
+        const int variant = forced >= 0 ? forced : (num_tiles(g) <= 5u * (unsigned)device_sm_count() ? 3 : 2);
 #define METAD_GATHER_LAUNCH(T_, B_)                                                                                               \
     {                                                                                                                             \
         const size_t sm = tile_smem_bytes<4>() + kGatherStages * (T_) * (sizeof(float4) + sizeof(uint2));                                       \

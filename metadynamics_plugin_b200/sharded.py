@@ -107,6 +107,31 @@ class LamellarSharded:
         return self.lam.forces(postype_local, n_global, box, bias, out=out)
 
 
+class WTESharded:
+    """WellTemperedEnsemble over particle shards (any partition).  Reference: the local sum of net_force.w is reduced with
+    one MPI_Allreduce of a double and the external energy is added once (WellTemperedEnsemble.cc:46-66); the scaling of
+    net force / torque / virial by (1 + bias) is local to every rank (:135-188)."""
+
+    def __init__(self, comm, reduce_fn=None, scale_fn=None):
+        """reduce_fn / scale_fn: functions with the interface of ops.wte_reduce / ops.wte_scale (tests substitute CPU
+        stand-ins)."""
+        if reduce_fn is None or scale_fn is None:
+            from . import ops
+            reduce_fn, scale_fn = reduce_fn or ops.wte_reduce, scale_fn or ops.wte_scale
+        self.comm, self.reduce_fn, self.scale_fn = comm, reduce_fn, scale_fn
+        self.cv = None
+
+    def compute_cv(self, net_force_local, external_energy=0.0):
+        # every rank contributes its particles only; the external energy enters once, after the reduction
+        self.cv = self.reduce_fn(net_force_local, 0.0, out=self.cv)
+        self.comm.all_reduce_sum(self.cv)
+        self.cv += float(external_energy)
+        return self.cv
+
+    def scale(self, net_force_local, net_torque_local, net_virial_local, pitch, bias):
+        return self.scale_fn(net_force_local, net_torque_local, net_virial_local, pitch, bias)
+
+
 # ---------------------------------------------------------------------------------------------------- mesh
 def slab_of(z, L, nz, n_ranks):
     """Owner rank of a particle: the slab holding its global mesh plane (single-precision cell rule of the path)."""

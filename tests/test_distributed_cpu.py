@@ -242,6 +242,42 @@ def _lamellar_worker(rank, world, port, N, out_q):
         dist.destroy_process_group()
 
 
+def _wte_worker(rank, world, port, N, out_q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from metadynamics_plugin_b200 import sharded
+
+        def np_reduce(net_force, external_energy=0.0, out=None):      # stand-in for ops.wte_reduce
+            if out is None:
+                out = torch.zeros(1, dtype=torch.float64)
+            out[0] = float(net_force.numpy()[:, 3].astype(np.float64).sum()) + external_energy
+            return out
+
+        def np_scale(nf, tq, vir, pitch, bias):                        # stand-in for ops.wte_scale
+            fac = 1.0 + float(bias[0])
+            nf[:, :3] *= fac
+            tq[:, :3] *= fac
+            vir *= fac
+
+        rng = np.random.default_rng(99)
+        nf = rng.standard_normal((N, 4)).astype(np.float32)
+        part = np.array_split(np.arange(N), world)[rank]
+        w = sharded.WTESharded(sharded.TorchComm(), np_reduce, np_scale)
+        local = torch.from_numpy(nf[part].copy())
+        cv = w.compute_cv(local, external_energy=1.25)
+        cv2 = float(w.compute_cv(local, external_energy=1.25)[0])      # the cached output tensor must not accumulate
+        tq = torch.zeros(len(part), 4)
+        vir = torch.zeros(6, len(part))
+        w.scale(local, tq, vir, len(part), torch.tensor([0.5], dtype=torch.float64))
+        out_q.put((rank, float(cv[0]), cv2, part, local.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
 def _run(worker, world, *args):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
@@ -286,3 +322,16 @@ def test_lamellar_sharded_driver_over_gloo(oracle):
     cvo, _ = oracle.lamellar_cv(oracle.make_postype(pos, types), N, [1.0, -1.0], [(0, 0, 2), (1, 1, 0)], 9.0)
     assert res[0][1] == res[1][1]
     assert res[0][1] == pytest.approx(cvo, abs=1e-9)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_wte_sharded_driver_over_gloo(oracle, world):
+    """WellTemperedEnsemble over particle shards: one all-reduce of a double, external energy added once."""
+    N = 5000
+    res = _run(_wte_worker, world, N)
+    nf = np.random.default_rng(99).standard_normal((N, 4)).astype(np.float32)
+    pe = oracle.wte_pe(nf, 1.25)
+    for rank, cv, cv2, part, scaled in res:
+        assert cv == pytest.approx(pe, rel=1e-12) and cv2 == cv
+        np.testing.assert_allclose(scaled[:, :3], nf[part][:, :3] * np.float32(1.5), rtol=1e-6)
+        np.testing.assert_array_equal(scaled[:, 3], nf[part][:, 3])
