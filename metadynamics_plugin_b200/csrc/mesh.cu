@@ -169,15 +169,16 @@ template <int LC> int run_x(metad_mesh* p, bool inverse, float2* io, const doubl
         in.sums_table = sync ? table : nullptr;
         in.sums_out = d_out;
         in.rho_keep = p->keep_rho ? reinterpret_cast<float2*>(p->d_rho_keep) : nullptr;
+        // the kernel clears the rows it consumes (and, in peer-memory mode, this rank's two ghost planes, which were
+        // pushed to the neighbours before): the accumulator is empty again for the next spread
+        in.zero = reinterpret_cast<int4*>(p->d_mesh_i);
+        in.zero_lo = peer_out ? reinterpret_cast<int4*>(p->d_mesh_alloc) : nullptr;
+        in.zero_hi = peer_out ? reinterpret_cast<int4*>(p->d_mesh_alloc + ((size_t)p->g.nz + 1) * p->g.nx * p->g.ny) : nullptr;
         PeerOut po;
         memset(&po, 0, sizeof po);
         if (peer_out) po = *peer_out;
         METAD_CUDA(launch_pdl(p->pdl, fft_x_fwd_kernel<LC>, rows / kLines, kLines * LC / kE, smem, st, in, p->d_twx, io ? io : buf, lg_part, rows, po, ps));
         METAD_LAUNCH_CHECK();
-        // the accumulator is empty again for the next spread (a plain memset runs at the full write bandwidth); in
-        // peer-memory mode the two ghost planes (already pushed to the neighbours) are cleared by the same memset
-        if (peer_out) METAD_CUDA(cudaMemsetAsync(p->d_mesh_alloc, 0, sizeof(int) * (p->M() + 2 * (size_t)p->g.nx * p->g.ny), st));
-        else METAD_CUDA(cudaMemsetAsync(p->d_mesh_i, 0, sizeof(int) * p->M(), st));
     } else {
         int rc = set_smem(fft_x_inv_kernel<LC>, smem); if (rc) return rc;
         METAD_CUDA(launch_pdl(p->pdl, fft_x_inv_kernel<LC>, rows / kLines, kLines * LC / kE, smem, st, buf, p->d_twx, io ? io : buf, lg_part, rows, ps, sync ? table : nullptr, d_out));
@@ -401,12 +402,12 @@ int enqueue_spread(metad_mesh* p, const float* d_postype, unsigned N, cudaStream
         METAD_CUDA(cudaMemsetAsync(p->d_sums, 0, 4 * sizeof(double), stream));
         return METAD_OK;
     }
-    METAD_CUDA(cudaMemsetAsync(p->d_counters + 1, 0, 3 * sizeof(unsigned), stream));
     SpreadOut out;
     out.mesh = p->d_mesh_i;
     out.tile_sums = p->d_tile_sums;
     out.sums = p->d_sums;
     out.counters = p->d_counters;
+    out.h_counters = p->h_counters;
     out.keys = p->keep_cells ? p->d_keys : nullptr;
     out.cache4 = p->d_cache4;
     out.cache_code = p->d_cache_code;
@@ -419,7 +420,6 @@ int enqueue_spread(metad_mesh* p, const float* d_postype, unsigned N, cudaStream
                                                                                            p->d_mode, p->ntypes, p->d_fx, out));
     }
     METAD_LAUNCH_CHECK();
-    METAD_CUDA(cudaMemcpyAsync(p->h_counters, p->d_counters, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
     return METAD_OK;
 }
 
@@ -592,8 +592,8 @@ int create_common(metad_mesh** out, unsigned nx, unsigned ny, unsigned nzg, unsi
     TRY(cudaMalloc(&p->d_sums, sizeof(double) * 4));
     TRY(cudaMemset(p->d_sums, 0, sizeof(double) * 4));
     TRY(cudaMalloc(&p->d_tile_sums, sizeof(double) * 2 * num_tiles(g)));
-    TRY(cudaMalloc(&p->d_counters, sizeof(unsigned) * 4));
-    TRY(cudaMemset(p->d_counters, 0, sizeof(unsigned) * 4));
+    TRY(cudaMalloc(&p->d_counters, sizeof(unsigned) * 8));
+    TRY(cudaMemset(p->d_counters, 0, sizeof(unsigned) * 8));
     TRY(cudaMallocHost(&p->h_counters, sizeof(unsigned) * 4));
     TRY(cudaMalloc(&p->d_partials, sizeof(double) * p->n_partials));
     TRY(cudaMalloc(&p->d_ticket, sizeof(unsigned)));
@@ -1067,11 +1067,11 @@ extern "C" int metad_mesh_get(metad_mesh* p, int which, void* h_out) {
             // statistics, double[6]: rebuilds of the tile order so far; of the LAST spread: particles that took the direct
             // path, particles outside the slab, cells past half of the fixed-point range; fixed-point scale; calls since rebuild
             double* out = (double*)h_out;
-            unsigned c[4];
+            unsigned c[8];
             float fx[2];
             METAD_CUDA(cudaMemcpy(c, p->d_counters, sizeof c, cudaMemcpyDeviceToHost));
             METAD_CUDA(cudaMemcpy(fx, p->d_fx, sizeof fx, cudaMemcpyDeviceToHost));
-            out[0] = (double)p->n_rebuilds; out[1] = c[1]; out[2] = c[2]; out[3] = c[3]; out[4] = fx[0]; out[5] = p->calls_since_rebuild;
+            out[0] = (double)p->n_rebuilds; out[1] = c[4]; out[2] = c[5]; out[3] = c[6]; out[4] = fx[0]; out[5] = p->calls_since_rebuild;
             return METAD_OK;
         }
         case 7: *(unsigned long long*)h_out = p->n_graph_launches; return METAD_OK;

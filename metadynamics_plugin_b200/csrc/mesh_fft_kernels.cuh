@@ -169,6 +169,10 @@ struct DensityIn {
     double* sums_out;           //   ... block 0 stores the rank-ordered totals here for the later sweeps
     unsigned lgy, nz;       // log2(ny), local planes
     float2* rho_keep;       // optional: float copy of the density (before the mean is removed), or nullptr
+    int4* zero;             // the same rows, writable: every thread clears what it has read, so that the accumulator is empty
+                            // for the next spread without a separate memset on the critical path (nullptr: leave it)
+    int4* zero_lo;          // peer-memory mode: this rank's own ghost planes z = -1 and z = nz (already pushed to the
+    int4* zero_hi;          //   neighbours), cleared by the CTAs of the first / last local plane; else nullptr
 };
 
 // density of mesh cell pair `v` (+ ghost contribution) as float: value = v / scale
@@ -243,6 +247,20 @@ fft_x_fwd_kernel(DensityIn in, const float2* __restrict__ g_tw /* length 2*LC */
         if (in.rho_keep) in.rho_keep[row * LC + l] = r;
         r.x -= mean; r.y -= mean;
         tile[LayoutRow::addr(w, l, LC)] = r;
+    }
+    if (in.zero) {
+        const int4 z4 = make_int4(0, 0, 0, 0);
+#pragma unroll
+        for (int q = 0; q < kE / 2; ++q) {
+            const int idx = threadIdx.x + q * nthr;
+            const size_t row = row0 + idx / (LC / 2);
+            in.zero[row * (LC / 2) + idx % (LC / 2)] = z4;
+            if (in.zero_lo) {
+                const unsigned z = (unsigned)(row >> in.lgy), y = (unsigned)row & (ny - 1);
+                if (z == 0) in.zero_lo[(size_t)y * (LC / 2) + idx % (LC / 2)] = z4;
+                if (z == in.nz - 1) in.zero_hi[(size_t)y * (LC / 2) + idx % (LC / 2)] = z4;
+            }
+        }
     }
     __syncthreads();
     const int w = threadIdx.x & (kLines - 1), t = threadIdx.x / kLines;

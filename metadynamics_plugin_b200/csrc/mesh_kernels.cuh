@@ -733,7 +733,8 @@ struct SpreadOut {
     int* mesh;               // integer density, local plane 0 (slab: ghost planes at -1 and nz)
     double* tile_sums;       // [ntiles][2] partial sum a^2, sum a
     double* sums;            // [0] sum a^2 (m_mode_sq, OrderParameterMesh.cc:623), [1] sum a, [2] particles outside the slab
-    unsigned* counters;
+    unsigned* counters;      // [0] ticket, [1..3] running counters of this launch, [4..6] counters of the last finished spread
+    unsigned* h_counters;    // pinned host words [1..3] (device-visible address), or nullptr
     unsigned* keys;          // optional: tile-major cell key per particle (introspection), or nullptr
     float4* cache4;          // particle cache for the gather, tile order: {sx, sy, sz, a}
     uint2* cache_code;       //   ... and {code word (cache_code()), particle index}
@@ -895,9 +896,16 @@ mesh_spread_kernel(const float4* __restrict__ postype, const unsigned* __restric
     a2 = block_sum(a2, red);
     a1 = block_sum(a1, red);
     if (threadIdx.x == 0) {
+        // every other CTA has taken its ticket, i.e. finished its counter updates: publish the counters of this spread
+        // (device snapshot for metad_mesh_get, pinned host words for the drift / range decision of a later call -- a
+        // plain store to mapped host memory instead of a copy node on the critical path) and clear them for the next one
+        const unsigned c1 = __ldcg(out.counters + 1), c2 = __ldcg(out.counters + 2), c3 = __ldcg(out.counters + 3);
         out.sums[0] = a2;
         out.sums[1] = a1;
-        out.sums[2] = (double)__ldcg(out.counters + 2);
+        out.sums[2] = (double)c2;
+        out.counters[4] = c1; out.counters[5] = c2; out.counters[6] = c3;
+        if (out.h_counters) { out.h_counters[1] = c1; out.h_counters[2] = c2; out.h_counters[3] = c3; }
+        out.counters[1] = 0; out.counters[2] = 0; out.counters[3] = 0;
         out.counters[0] = 0;
     }
 }
