@@ -92,6 +92,7 @@ def make_workload(name, shard=None):
 
 
 # ---------------------------------------------------------------------------------------------------- ours
+MERGE_PUSH = False      # --merge-push: peer-memory mode with halo push and barrier in one launch (measured slower)
 NO_PDL = False          # --no-pdl: A/B switch of programmatic dependent launch
 TILE_ORDER = None       # --tile-order: A/B switch of the order inside a tile (library default when None)
 
@@ -182,6 +183,8 @@ class MeshSlabStep(MeshStep):
         self.mesh.set(0, period)
         if NO_PDL:
             self.mesh.set(7, 0)
+        if MERGE_PUSH:
+            self.mesh.set(8, 1)
         if mode == "p2p":
             self.mesh.set(5, 1 if sync == "fused" else 0)
             self.mesh.set(4, 1)         # the whole sharded step (incl. the inter-rank waits) replays from one CUDA graph
@@ -542,11 +545,13 @@ def main():
                     help="peer-memory mode: separate barrier launches (default, measured faster) or inter-rank signal/wait inside the kernels")
     ap.add_argument("--tile-order", default=None, choices=["bank", "layer"], help="order of the particles inside a tile (single GPU; default: library default = bank)")
     ap.add_argument("--order", default="sorted", choices=["sorted", "random"], help="C3 / C4: particle order of the input (cell-sorted headline, random stress case)")
+    ap.add_argument("--merge-push", action="store_true", help="peer-memory mode: halo push and barrier in one launch (measured slower)")
     ap.add_argument("--no-pdl", action="store_true", help="launch the per-step kernels without programmatic dependent launch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     args = ap.parse_args()
-    global TILE_ORDER, NO_PDL, PARTICLE_ORDER
+    global TILE_ORDER, NO_PDL, PARTICLE_ORDER, MERGE_PUSH
+    MERGE_PUSH = args.merge_push
     PARTICLE_ORDER = args.order
     TILE_ORDER = args.tile_order
     NO_PDL = args.no_pdl

@@ -174,7 +174,8 @@ int metad_mesh_get(metad_mesh* p, int which, void* h_out);
  *                measured faster) uses separate barrier launches
  *        key 6 = order of the particles inside a tile: 1 (default) bank order, 0 layer order (mesh_kernels.cuh); results
  *                do not depend on it
- *        key 7 = programmatic dependent launch of the per-step kernels: 1 (default) on, 0 off                            */
+ *        key 7 = programmatic dependent launch of the per-step kernels: 1 (default) on, 0 off
+ *        key 8 = peer-memory mode: halo push and the barrier after it in one launch: 1 on, 0 (default, measured faster) off */
 int metad_mesh_set(metad_mesh* p, int key, long value);
 
 /* ------------------------------------------------------------------------------------------------

@@ -90,7 +90,10 @@ struct metad_mesh {
     bool fused_sync = false;
     bool pdl = true;                            // programmatic dependent launch of the per-step kernels (knob 7)
     int order_kind = 1;                         // order inside a tile: 0 = layer order, 1 = bank order (knob 6)
-    unsigned* d_sync = nullptr;                 // [4] phase epochs + [4] CTA tickets of the fused synchronisation
+    unsigned* d_sync = nullptr;                 // [4] phase epochs + [4] CTA tickets of the fused synchronisation, [8] ticket of push_barrier_kernel
+    // halo push and the barrier after it in one launch (knob 8).  Off: measured slower (2 GPUs: C4 0.392 vs 0.381 ms, C3 0.127 vs
+    // 0.118 ms) -- the per-CTA system-scope fence + ticket costs more than the kernel boundary it removes.
+    bool merge_push = false;
     // CUDA-graph replay of the per-call kernel sequence (metad_mesh_set key 4): everything a call enqueues after the
     // (eager) tile-order decision is captured once per argument signature and replayed with one launch
     bool graph_mode = false;
@@ -605,8 +608,8 @@ int create_common(metad_mesh** out, unsigned nx, unsigned ny, unsigned nzg, unsi
     TRY(cudaMemset(p->d_p2p_status, 0, sizeof(unsigned)));
     TRY(cudaMalloc(&p->d_epoch, sizeof(unsigned)));
     TRY(cudaMemset(p->d_epoch, 0, sizeof(unsigned)));
-    TRY(cudaMalloc(&p->d_sync, sizeof(unsigned) * 8));
-    TRY(cudaMemset(p->d_sync, 0, sizeof(unsigned) * 8));
+    TRY(cudaMalloc(&p->d_sync, sizeof(unsigned) * 12));
+    TRY(cudaMemset(p->d_sync, 0, sizeof(unsigned) * 12));
 #undef TRY
     if (rc == METAD_OK) {
         memset(p->h_counters, 0, sizeof(unsigned) * 4);
@@ -782,6 +785,13 @@ int p2p_barrier(metad_mesh* p, int wait, p2p::Publish pub, p2p::Reduce red, cuda
     return METAD_OK;
 }
 
+int p2p_push_barrier(metad_mesh* p, const p2p::PushJob& job, p2p::Publish pub, p2p::Reduce red, cudaStream_t st) {
+    METAD_CUDA(launch_pdl(p->pdl, p2p::push_barrier_kernel, 32, 256, 0, st, job, p->peers, p->lay.flags + 4 * p2p::kMaxPeers * sizeof(unsigned),
+                          p->d_epoch, pub, red, p->d_p2p_status, p->d_sync + 8));
+    METAD_LAUNCH_CHECK();
+    return METAD_OK;
+}
+
 PeerSync make_sync(metad_mesh* p, int wait_k, int signal_k) {
     PeerSync ps;
     memset(&ps, 0, sizeof ps);
@@ -819,6 +829,14 @@ int p2p_stage(metad_mesh* p, int stage, int wait, const float* d_postype, unsign
             job.dst[1] = (int4*)(gd + plane * sizeof(int)); job.src[1] = (const int4*)(p->d_fx + 4); job.n16[1] = 1;
             job.dst[2] = (int4*)gu; job.src[2] = (const int4*)above; job.n16[2] = (unsigned)(plane * sizeof(int) / 16);
             job.dst[3] = (int4*)(gu + plane * sizeof(int)); job.src[3] = (const int4*)(p->d_fx + 4); job.n16[3] = 1;
+            const bool merged = wait && !fused && p->merge_push;
+            if (merged) {       // push + barrier 1 (+ all-reduce of the partial sums) in one launch
+                rc = p2p_push_barrier(p, job, p2p::Publish{p->d_sums, p->lay.sums, 4, 3},
+                                      p2p::Reduce{(const double*)(mine + p->lay.sums), 4, 3, p->d_sums_global}, st);
+                if (rc) return rc;
+                rc = markp(p, 2, st); if (rc) return rc;
+                return markp(p, 3, st);
+            }
             if (fused) {
                 METAD_CUDA(launch_pdl(p->pdl, p2p::push_kernel, 32, 256, 0, st, job, p2p::Publish{p->d_sums, p->lay.sums, 4, 3}, make_sync(p, -1, 0)));
             } else {
@@ -834,12 +852,12 @@ int p2p_stage(metad_mesh* p, int stage, int wait, const float* d_postype, unsign
             return markp(p, 2, st);
         }
         case 1: {   // [barrier: halos and sums have arrived] x forward pass, every kx pencil stored into its owner's memory
-            if (!fused) {
+            if (!fused && !(wait && p->merge_push)) {
                 rc = p2p_barrier(p, wait, p2p::Publish{p->d_sums, p->lay.sums, 4, wait ? 3u : 0u},
                                  p2p::Reduce{(const double*)(mine + p->lay.sums), 4, 3, p->d_sums_global}, st);
                 if (rc) return rc;
+                rc = markp(p, 3, st); if (rc) return rc;
             }
-            rc = markp(p, 3, st); if (rc) return rc;
             if (p->keep_rho && !p->d_rho_keep) METAD_CUDA(cudaMalloc(&p->d_rho_keep, sizeof(float) * p->M()));
             PeerOut po;
             memset(&po, 0, sizeof po);
@@ -906,6 +924,12 @@ int p2p_stage(metad_mesh* p, int stage, int wait, const float* d_postype, unsign
             job.src[0] = (const int4*)p->d_buf; job.n16[0] = (unsigned)(plane * sizeof(float) / 16);
             job.dst[1] = (int4*)(p->peers.arena[up] + p->lay.ghost_inv);
             job.src[1] = (const int4*)(p->d_buf + plane * (g.nz - 1)); job.n16[1] = (unsigned)(plane * sizeof(float) / 16);
+            if (wait && !fused && p->merge_push) {      // push + barrier 4 in one launch
+                rc = p2p_push_barrier(p, job, p2p::Publish{nullptr, 0, 0, 0}, p2p::Reduce{nullptr, 0, 0, nullptr}, st);
+                if (rc) return rc;
+                rc = markp(p, 11, st); if (rc) return rc;
+                return markp(p, 12, st);
+            }
             if (fused) {
                 METAD_CUDA(launch_pdl(p->pdl, p2p::push_kernel, 32, 256, 0, st, job, p2p::Publish{nullptr, 0, 0, 0}, make_sync(p, -1, 3)));
             } else {
@@ -917,7 +941,7 @@ int p2p_stage(metad_mesh* p, int stage, int wait, const float* d_postype, unsign
             return markp(p, 11, st);
         }
         case 4:     // [barrier: the halo planes of Re IFFT(G) have arrived]; fused mode: the gather waits for phase 3 itself
-            if (fused) return METAD_OK;
+            if (fused || (wait && p->merge_push)) return METAD_OK;
             rc = p2p_barrier(p, wait, p2p::Publish{nullptr, 0, 0, 0}, p2p::Reduce{nullptr, 0, 0, nullptr}, st); if (rc) return rc;
             return markp(p, 12, st);
         default:
@@ -986,7 +1010,7 @@ extern "C" int metad_mesh_slab_p2p_cv(metad_mesh* p, const float* d_postype, uns
         if (rc == METAD_OK && stage == 4) { p->have_cv = true; p->last_cv_fused = false; }
         return rc;
     }
-    const int rc = run_captured(p, make_key(p, d_postype, N_local, N_global, box, d_cv, stream, p->fused_sync ? 2 : 1), stream, [&](cudaStream_t st) -> int {
+    const int rc = run_captured(p, make_key(p, d_postype, N_local, N_global, box, d_cv, stream, (p->fused_sync ? 2 : 1) + (p->merge_push ? 4 : 0)), stream, [&](cudaStream_t st) -> int {
         for (int s = 0; s <= 4; ++s) {
             const int r = p2p_stage(p, s, 1, d_postype, N_local, N_global, box, d_cv, st);
             if (r) return r;
@@ -1103,6 +1127,7 @@ extern "C" int metad_mesh_set(metad_mesh* p, int key, long value) {
         case 5: p->fused_sync = value != 0; return METAD_OK;
         case 6: p->order_kind = value != 0 ? 1 : 0; p->order_valid = false; return METAD_OK;
         case 7: p->pdl = value != 0; return METAD_OK;
+        case 8: p->merge_push = value != 0; return METAD_OK;
         default: set_error("metad_mesh_set: unknown key"); return METAD_ERR_INVALID;
     }
 }

@@ -90,10 +90,10 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
 // wait == 0: steps 1 and 3 only (single-process emulation of the ranks, where the launch order already orders the data).
 // status[0] is set to 1 if a peer did not arrive within a few seconds (a crashed rank must not hang the GPU).
 struct Reduce { const double* table; unsigned per_rank, width; double* out; };
-__global__ void barrier_kernel(PeerTable pt, size_t flags_offset, unsigned* __restrict__ d_epoch, int wait, Publish pub, Reduce red,
-                               unsigned* __restrict__ status) {
-    const unsigned lane = threadIdx.x;
-    pdl_wait(); pdl_trigger();
+// executed by one warp
+__device__ __forceinline__ void barrier_body(const PeerTable& pt, size_t flags_offset, unsigned* __restrict__ d_epoch, int wait,
+                                             const Publish& pub, const Reduce& red, unsigned* __restrict__ status) {
+    const unsigned lane = threadIdx.x & 31;
     if (pub.n) {
         const unsigned r = lane / 4, k = lane % 4;          // up to 8 ranks x 4 values
         if (r < pt.n && k < pub.n) reinterpret_cast<double*>(pt.arena[r] + pub.table_offset)[pt.rank * pub.per_rank + k] = pub.src[k];
@@ -120,6 +120,34 @@ __global__ void barrier_kernel(PeerTable pt, size_t flags_offset, unsigned* __re
         for (unsigned r = 0; r < pt.n; ++r) s += __ldcv(red.table + r * red.per_rank + lane);
         red.out[lane] = s;
     }
+}
+__global__ void barrier_kernel(PeerTable pt, size_t flags_offset, unsigned* __restrict__ d_epoch, int wait, Publish pub, Reduce red,
+                               unsigned* __restrict__ status) {
+    pdl_wait(); pdl_trigger();
+    barrier_body(pt, flags_offset, d_epoch, wait, pub, red, status);
+}
+
+// halo push and the barrier that follows it in one launch: every CTA copies its share, fences its peer stores at system
+// scope and takes a ticket; the last one runs the barrier (publish, flags, wait, reduce) in its first warp.  With 32 CTAs
+// the per-CTA fence is cheap (it is what made the same idea too slow inside the 4096-CTA FFT sweeps).
+__global__ void __launch_bounds__(256) push_barrier_kernel(PushJob job, PeerTable pt, size_t flags_offset, unsigned* __restrict__ d_epoch,
+                                                           Publish pub, Reduce red, unsigned* __restrict__ status,
+                                                           unsigned* __restrict__ ticket) {
+    const unsigned stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ bool is_last;
+    pdl_wait(); pdl_trigger();
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+        for (unsigned i = t0; i < job.n16[s]; i += stride) job.dst[s][i] = job.src[s][i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    if (threadIdx.x == 0) *ticket = 0;
+    if (threadIdx.x < 32) barrier_body(pt, flags_offset, d_epoch, 1, pub, red, status);
 }
 
 }  // namespace p2p
