@@ -54,6 +54,18 @@ def mesh(dims, mode, L, postype, bias, prec="f64", tilt=(0, 0, 0)):
                 interp=interp.reshape(nz, ny, nx))
 
 
+def mesh_qmax(dims, mode, L, postype, prec="f64", tilt=(0, 0, 0)):
+    """OrderParameterMesh::computeQmax of the reference: array {q_max.x, q_max.y, q_max.z, sq_max}."""
+    nx, ny, nz = dims
+    mode = np.ascontiguousarray(mode, np.float64)
+    Lb, tb = _box(L, tilt)
+    pt = np.ascontiguousarray(postype, np.float32)
+    out = np.empty(4)
+    rc = lib(prec).ref_mesh_qmax(nx, ny, nz, _d(mode), len(mode), _d(Lb), _d(tb), pt.ctypes.data_as(_fp), pt.shape[0], _d(out))
+    assert rc == 0
+    return out
+
+
 def lamellar(mode, lattice_vectors, L, postype, bias, prec="f64", tilt=(0, 0, 0)):
     N = postype.shape[0]
     mode = np.ascontiguousarray(mode, np.float64)

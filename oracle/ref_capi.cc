@@ -83,6 +83,19 @@ int ref_mesh(unsigned nx, unsigned ny, unsigned nz, const double* mode, unsigned
     } catch (const std::exception& e) { fprintf(stderr, "ref_mesh: %s\n", e.what()); return -1; }
 }
 
+// OrderParameterMesh::computeQmax (the q*_max / sq_max log quantities): out4 = {q_max.x, q_max.y, q_max.z, sq_max}
+int ref_mesh_qmax(unsigned nx, unsigned ny, unsigned nz, const double* mode, unsigned ntypes, const double* L, const double* tilt,
+                  const float* postype, unsigned N, double* out4) {
+    try {
+        auto sys = make_system(postype, N, L, tilt, ntypes);
+        std::vector<Scalar> m(mode, mode + ntypes);
+        OrderParameterMesh op(sys, nx, ny, nz, m);
+        op.computeQmax(1);
+        out4[0] = op.m_q_max.x; out4[1] = op.m_q_max.y; out4[2] = op.m_q_max.z; out4[3] = op.m_sq_max;
+        return 0;
+    } catch (const std::exception& e) { fprintf(stderr, "ref_mesh_qmax: %s\n", e.what()); return -1; }
+}
+
 // LamellarOrderParameter: getCurrentValue, Fourier modes, computeBiasForces with `bias`
 int ref_lamellar(const double* mode, unsigned ntypes, const int* lattice, unsigned n_wave, const double* L, const double* tilt,
                  const float* postype, unsigned N, double bias, double* cv, double* modes_out /* 2*n_wave */, double* force) {

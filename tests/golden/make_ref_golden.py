@@ -68,6 +68,7 @@ for name, seed, N, dims, L, modes, bias in MESH:
         out["%s_%s_rho" % (name, prec)] = r["rho"] if prec == "f64" else r["rho"].astype(np.float32)
         if prec == "f64":
             out["%s_%s_inv" % (name, prec)] = r["inv"]
+            out["%s_%s_qmax" % (name, prec)] = pyref.mesh_qmax(dims, modes, L, pt, prec)
 
 LAM = [("l0", 21, 4000, (16.0, 16.0, 16.0), (0, 0, 0), [(0, 0, 3), (0, 3, 0), (3, 0, 0)], (1.0, -1.0), 0.83),
        ("l1", 22, 3000, (20.0, 24.0, 18.0), (0.1, -0.2, 0.05), [(1, 2, 0), (2, -1, 1)], (1.0, -1.0, 0.5), -0.4)]

@@ -193,3 +193,18 @@ def test_live_reference_build_rewrites_the_golden_files(tmp_path):
         gold = os.path.join(os.path.dirname(T2D), "test2d_" + prec)
         for name in os.listdir(gold):
             assert open(os.path.join(gold, name)).read() == open(os.path.join(d, name)).read(), (prec, name)
+
+
+@pytest.mark.parametrize("name", MESH_CASES)
+def test_oracle_qmax_reproduces_reference(oracle, name):
+    """OrderParameterMesh::computeQmax (log quantities q*_max, sq_max; SURVEY 8f rank 2) against the reference's own code.
+    The reference does not exclude k = 0, so a one-component density reports q_max = 0 and sq_max = N.  A mode and its
+    mirror image have the same amplitude up to FFT rounding, so the wave vector is compared up to its sign."""
+    dims, L, bias, modes = mesh_cfg(name)
+    pt = GOLD[name + "_postype"]
+    m = oracle.Mesh(*dims, modes, L, pt.shape[0], "f64")
+    m.current_value(pt)
+    q = m.qmax()
+    ref = GOLD[name + "_f64_qmax"]
+    assert q[3] == pytest.approx(ref[3], rel=1e-10)
+    assert np.allclose(q[:3], ref[:3], rtol=1e-12, atol=1e-12) or np.allclose(q[:3], -ref[:3], rtol=1e-12, atol=1e-12)
