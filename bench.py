@@ -99,7 +99,8 @@ TILE_ORDER = None       # --tile-order: A/B switch of the order inside a tile (l
 
 class MeshStep:
     """mesh CV -> 1-D grid bias -> forces, everything device-resident."""
-    # spread, x/y fwd, z fused (+plane0), y/x inv, grid step, gather; a rebuild of the tile order adds bin, 3 scan, place, layer order, scale
+    # spread, x/y fwd, z fused (+plane0), y/x inv, grid step, gather (no memset / copy nodes); a rebuild of the tile order adds bin,
+    # 3 scan, place, bank order, scale
     launches_per_step = 8
     launches_per_rebuild = 7
 
@@ -145,7 +146,9 @@ class MeshSlabStep(MeshStep):
     """The same step with the mesh sharded into z slabs over the ranks (sharded.MeshSlab: NCCL all-to-all transposes,
     halo exchanges and two tiny all-reduces per step); the bias grid is replicated.  Strong scaling: N is the global
     particle number, every rank owns the particles of its slab."""
-    launches_per_step = 16      # p2p: spread, 2 pushes + 2 scalar pushes, 4 barriers, x/y fwd, z fused, y/x inv, grid step, gather
+    # our kernels per step.  peer memory: spread, 2 halo pushes, 4 barriers, x/y forward, fused z, y/x inverse, grid step, gather;
+    # staged (NCCL): the same 8 compute kernels as on one GPU (the collectives are NCCL's kernels, not counted)
+    launches_per_step = 14
 
     def __init__(self, w, ops, torch, comm, period=32, mode="p2p", sync="barrier"):
         from metadynamics_plugin_b200 import sharded
@@ -179,6 +182,7 @@ class MeshSlabStep(MeshStep):
             self.slab = nccl
             self.cv_check = 0.0
         self.mesh = self.slab.r
+        self.launches_per_step = 14 if mode == "p2p" else 8
         self.period = period
         self.mesh.set(0, period)
         if NO_PDL:
