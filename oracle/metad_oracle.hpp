@@ -10,7 +10,7 @@
 // formula by formula, each function citing the reference file:line it follows (paths relative to
 // /root/reference/metadynamics/).  It is pinned in two ways:
 //   (1) against the reference's own classes: CollectiveVariable.cc, LamellarOrderParameter.cc, OrderParameterMesh.cc,
-//       AspectRatio.cc, IndexGrid.cc and IntegratorMetaDynamics.cc are compiled UNMODIFIED from /root/reference against a
+//       AspectRatio.cc, Density.cc, IndexGrid.cc, IntegratorMetaDynamics.cc and WellTemperedEnsemble.cc are compiled UNMODIFIED from /root/reference against a
 //       HOOMD stand-in (oracle/ref_shim/, oracle/ref_capi.cc, `make -C oracle ref` -> oracle/_ref/) and run on seeded
 //       inputs (tests/golden/make_ref_golden.py -> tests/golden/ref_golden.npz; tests/test_reference_build.py).  The
 //       density mesh of this file equals the reference's BIT FOR BIT in the float and the double build (every cell
@@ -20,8 +20,9 @@
 //       ratio and IndexGrid exactly;
 //   (2) against independent numpy restatements (numpy.fft, closed-form TSC, analytic single-particle / lattice cases,
 //       finite differences) in tests/test_oracle.py.
-// NOT pinned by an executable: WellTemperedEnsemble.cc (its header does not compile without ENABLE_CUDA; the CPU
-// arithmetic is a plain sum and a scale), and the two pieces of HOOMD itself that the stand-in has to restate as well --
+//       WellTemperedEnsemble.cc likewise (its header needs ENABLE_CUDA to compile: oracle/ref_shim_cuda/ provides inert
+//       stand-ins, the CPU branch runs): CV and the scaled arrays BIT FOR BIT, both builds; Density.cc and computeQmax too.
+// NOT pinned by an executable: the two pieces of HOOMD itself that the stand-in has to restate as well --
 // BoxDim (lo/hi/L/Linv, makeFraction = (v - lo) * Linv, branching minImage) and kiss_fftnd (unnormalised DFT, dims
 // slowest first).  HOOMD's version is not pinned by the reference (no submodule).
 //

@@ -1,6 +1,6 @@
 """ctypes front-end of the CPU oracle (oracle/_build/liboracle.so).
 
-TEST INFRASTRUCTURE ONLY -- pinned against the reference's own sources for the CV classes, unpinned for the integrator
+TEST INFRASTRUCTURE ONLY -- pinned against the reference's own sources for the CV classes and the integrator
 (see the header of oracle/metad_oracle.hpp and tests/test_reference_build.py).  Only tests/,
 ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` legs may import
 this module; the product package (metadynamics_plugin_b200) never does.

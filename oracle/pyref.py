@@ -155,3 +155,16 @@ def test2d_files(directory, restart=False, prec="f64"):
     rc = lib(prec).ref_test2d_files(os.fsencode(directory), 1 if restart else 0)
     assert rc >= 0
     return rc
+
+
+def wte(net_force, net_torque, net_virial6N, external_energy, external_virial6, bias, prec="f64"):
+    """The reference's WellTemperedEnsemble (CPU branch): CV = sum net_force.w + external energy, then computeBiasForces.
+    net_force / net_torque: (N, 4); net_virial6N: (6, N).  Returns dict(pe, force, torque, virial, external_virial)."""
+    f = np.array(net_force, dtype=np.float64, copy=True, order="C")
+    t = np.array(net_torque, dtype=np.float64, copy=True, order="C")
+    v = np.array(net_virial6N, dtype=np.float64, copy=True, order="C")
+    e = np.array(external_virial6, dtype=np.float64, copy=True)
+    pe = C.c_double()
+    rc = lib(prec).ref_wte(f.shape[0], _d(f), _d(t), _d(v), C.c_double(external_energy), _d(e), C.c_double(bias), C.byref(pe))
+    assert rc == 0
+    return dict(pe=pe.value, force=f, torque=t, virial=v, external_virial=e)

@@ -207,11 +207,19 @@ class Profiler {
     template <class E> void pop(E) {}
     template <class E, class A, class B> void pop(E, A, B) {}
 };
+struct cudaDeviceProp { int warpSize = 32, maxThreadsPerBlock = 1024; };      // named by WellTemperedEnsemble.cc's GPU branch
+class GPUPartition {};
+struct CachedAllocator {};
 class ExecutionConfiguration {
   public:
     ExecutionConfiguration() : msg(new Messenger()) {}
     enum executionMode { GPU, CPU, AUTO };
     executionMode exec_mode = CPU;
+    cudaDeviceProp dev_prop;
+    void beginMultiGPU() const {}
+    void endMultiGPU() const {}
+    unsigned int getNumActiveGPUs() const { return 1; }
+    const CachedAllocator& getCachedAllocatorManaged() const { static CachedAllocator a; return a; }
     std::shared_ptr<Messenger> msg;
     bool isCUDAEnabled() const { return false; }
     bool isCUDAErrorCheckingEnabled() const { return false; }
@@ -254,6 +262,7 @@ class ParticleData {
     PDataFlags getFlags() const { return m_flags; }
     void setFlags(const PDataFlags& f) { m_flags = f; }
     std::shared_ptr<DomainDecomposition> getDomainDecomposition() const { return std::shared_ptr<DomainDecomposition>(); }
+    const GPUPartition& getGPUPartition() const { static GPUPartition g; return g; }
     Nano::Signal<void()>& getBoxChangeSignal() { return m_box_signal; }
     std::shared_ptr<ExecutionConfiguration> getExecConf() const { return m_exec_conf; }
     BoxDim m_box;

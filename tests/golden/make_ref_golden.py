@@ -1,7 +1,7 @@
 """Generates tests/golden/ref_golden.npz from the REFERENCE's own code.
 
 The reference's CPU classes (CollectiveVariable.cc, LamellarOrderParameter.cc, OrderParameterMesh.cc, AspectRatio.cc,
-IndexGrid.cc, IntegratorMetaDynamics.cc) are compiled from /root/reference, unmodified, against the HOOMD stand-in in oracle/ref_shim/
+IndexGrid.cc, IntegratorMetaDynamics.cc, Density.cc, WellTemperedEnsemble.cc) are compiled from /root/reference, unmodified, against the HOOMD stand-in in oracle/ref_shim/
 (`make -C oracle ref`, oracle/ref_capi.cc) and run on small seeded inputs.  These vectors are therefore outputs of the
 reference itself (with BoxDim and kiss_fft restated by the stand-in) -- unlike golden.npz, which pins the oracle.
 /root/reference only exists in the build container, so the vectors are committed.  Run from the repo root:
@@ -140,6 +140,21 @@ for name, cfg in GRID:
         for k in ("bias", "grid", "reweighted", "weight", "sigma_grid", "hist", "hist_gauss", "hist_delta"):
             out["%s_wt%d_%s" % (name, wt, k)] = r[k]
         out["%s_wt%d_scalars" % (name, wt)] = np.array([r["bias_potential"], r["reweight"], r["num_gaussians"]])
+
+# WellTemperedEnsemble (CPU branch of the reference's own class): CV and the scaling of net force / torque / virial
+rng = np.random.default_rng(41)
+NW = 777
+out["wte_force"] = rng.standard_normal((NW, 4)).astype(np.float32)
+out["wte_torque"] = rng.standard_normal((NW, 4)).astype(np.float32)
+out["wte_virial"] = rng.standard_normal((6, NW)).astype(np.float32)
+out["wte_cfg"] = np.array([1.25, 0.5] + list(np.arange(1, 7.0)))             # external energy, bias, external virial
+for prec in ("f64", "f32"):
+    r = pyref.wte(out["wte_force"], out["wte_torque"], out["wte_virial"], 1.25, np.arange(1, 7.0), 0.5, prec)
+    out["wte_%s_pe" % prec] = np.array([r["pe"]])
+    out["wte_%s_force" % prec] = r["force"]
+    out["wte_%s_torque" % prec] = r["torque"]
+    out["wte_%s_virial" % prec] = r["virial"]
+    out["wte_%s_external_virial" % prec] = r["external_virial"]
 
 np.savez_compressed(os.path.join(HERE, "ref_golden.npz"), **out)
 print("wrote ref_golden.npz:", {k: v.shape for k, v in out.items() if not k.endswith("postype")})

@@ -208,3 +208,19 @@ def test_oracle_qmax_reproduces_reference(oracle, name):
     ref = GOLD[name + "_f64_qmax"]
     assert q[3] == pytest.approx(ref[3], rel=1e-10)
     assert np.allclose(q[:3], ref[:3], rtol=1e-12, atol=1e-12) or np.allclose(q[:3], -ref[:3], rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_oracle_wte_reproduces_reference(oracle, prec):
+    """WellTemperedEnsemble.cc (CPU branch, :30-68 and :135-188) through the reference's own class: the potential-energy CV
+    and the scaling of net force, net torque (all four components on the CPU), the six virial rows and the external virial."""
+    nf, tq, vir = GOLD["wte_force"], GOLD["wte_torque"], GOLD["wte_virial"]
+    ext_e, bias = GOLD["wte_cfg"][:2]
+    ev = GOLD["wte_cfg"][2:]
+    N = nf.shape[0]
+    assert oracle.wte_pe(nf, ext_e, prec) == GOLD["wte_%s_pe" % prec][0]
+    f, t, v, e = oracle.wte_scale(nf, tq, vir.reshape(-1), N, bias, ev, prec)
+    assert np.array_equal(f, GOLD["wte_%s_force" % prec].astype(np.float32))
+    assert np.array_equal(t, GOLD["wte_%s_torque" % prec].astype(np.float32))
+    assert np.array_equal(v, GOLD["wte_%s_virial" % prec].astype(np.float32).reshape(-1))
+    assert np.array_equal(e, GOLD["wte_%s_external_virial" % prec])
