@@ -248,8 +248,16 @@ template <int L> int run_z(metad_mesh* p, float2* buf, unsigned row_len, unsigne
         for (unsigned r = 0; r < p->n_ranks; ++r) cp.cv_arena[r] = p->peers.arena[r];
         cp.cv_off = p->lay.cv; cp.cv_n = p->n_ranks; cp.cv_rank = p->rank;
     }
-    int rc = set_smem(fft_z_fused_kernel<L>, smem); if (rc) return rc;
     const unsigned nblocks = cp.n_blocks_plane0 + (row_len / kLines) * ny;
+    // experiment (METAD_Z_CTAS=4): four CTAs per SM (32 registers) instead of three (40 registers) for 512-thread CTAs
+    static const bool four = getenv("METAD_Z_CTAS") && atoi(getenv("METAD_Z_CTAS")) == 4;
+    if (four && kLines * L / kE == 512) {
+        int rc4 = set_smem(fft_z_fused_kernel<L, 4>, smem); if (rc4) return rc4;
+        METAD_CUDA(launch_pdl(p->pdl, fft_z_fused_kernel<L, 4>, nblocks, kLines * L / kE, smem, st, buf, p->d_twz, cp));
+        METAD_LAUNCH_CHECK();
+        return METAD_OK;
+    }
+    int rc = set_smem(fft_z_fused_kernel<L>, smem); if (rc) return rc;
     METAD_CUDA(launch_pdl(p->pdl, fft_z_fused_kernel<L>, nblocks, kLines * L / kE, smem, st, buf, p->d_twz, cp));
     METAD_LAUNCH_CHECK();
     return METAD_OK;
