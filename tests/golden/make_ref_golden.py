@@ -70,6 +70,28 @@ for name, seed, N, dims, L, modes, bias in MESH:
             out["%s_%s_inv" % (name, prec)] = r["inv"]
             out["%s_%s_qmax" % (name, prec)] = pyref.mesh_qmax(dims, modes, L, pt, prec)
 
+# triclinic boxes and mesh sizes that are not powers of two: not on the device path yet, but the oracle must already be
+# right about them (keys t*: cfg = dims, L, tilt, bias, modes)
+TRI = [("t0", 31, 2500, (32, 16, 32), (12.0, 9.0, 10.0), (0.2, -0.1, 0.15), (1.0, -1.0), 0.8),
+       ("t1", 32, 2000, (24, 20, 18), (11.0, 9.5, 8.0), (0.0, 0.0, 0.0), (1.0,), 0.8),
+       ("t2", 33, 1500, (20, 12, 18), (10.0, 7.0, 9.0), (-0.15, 0.1, 0.05), (1.0, -0.5), -0.6)]
+for name, seed, N, dims, L, tilt, modes, bias in TRI:
+    rng = np.random.default_rng(seed)
+    f = rng.random((N, 3)) * 0.998 + 0.001
+    Lf = np.asarray(L)
+    v = -Lf / 2 + f * Lf                                  # BoxDim::makeCoordinates: lo + f L, then the shear
+    v[:, 0] += tilt[0] * v[:, 1] + tilt[1] * v[:, 2]
+    v[:, 1] += tilt[2] * v[:, 2]
+    pt = postype(v.astype(np.float32), rng.integers(0, len(modes), N))
+    out[name + "_postype"] = pt
+    out[name + "_cfg"] = np.array(list(dims) + list(L) + list(tilt) + [bias] + list(modes), dtype=np.float64)
+    for prec in ("f64", "f32"):
+        r = pyref.mesh(dims, modes, L, pt, bias, prec, tilt=tilt)
+        out["%s_%s_cv" % (name, prec)] = np.array([r["cv"], r["mode_sq"]])
+        out["%s_%s_rho" % (name, prec)] = r["rho"] if prec == "f64" else r["rho"].astype(np.float32)
+        if prec == "f64":
+            out["%s_%s_force" % (name, prec)] = r["force"]
+
 LAM = [("l0", 21, 4000, (16.0, 16.0, 16.0), (0, 0, 0), [(0, 0, 3), (0, 3, 0), (3, 0, 0)], (1.0, -1.0), 0.83),
        ("l1", 22, 3000, (20.0, 24.0, 18.0), (0.1, -0.2, 0.05), [(1, 2, 0), (2, -1, 1)], (1.0, -1.0, 0.5), -0.4)]
 for name, seed, N, L, tilt, lv, modes, bias in LAM:
