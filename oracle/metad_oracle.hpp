@@ -4,7 +4,7 @@
 // tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 // load it, and only as the checker or the CPU baseline -- never as the thing shipped.
 //
-// *** PARITY: PINNED TO THE REFERENCE'S OWN CODE (HOOMD's BoxDim / kiss_fft and the trivial WTE sums excepted). ***
+// *** PARITY: PINNED TO THE REFERENCE'S OWN CODE (HOOMD's BoxDim / kiss_fft, which are not in the reference tree, excepted). ***
 // The reference (jglaser/metadynamics-plugin) ships no golden vectors and no unit tests, and its build needs
 // HOOMD-blue 2.x, which is neither installed nor vendored.  This file restates the reference's *CPU* code path
 // formula by formula, each function citing the reference file:line it follows (paths relative to
