@@ -227,6 +227,50 @@ def test_mesh_order_independence(gpu):
     assert np.array_equal(f2, f[perm])
 
 
+def test_mesh_full_size_c3(gpu, oracle):
+    """BASELINE configuration C3 at its full size (N = 2^20 particles, 128^3 mesh, the bench's own workload generator):
+    direct parity with the double oracle (which needs a few seconds at this size), bit-exact cell indices, and the
+    size-independent properties of the path: mass conservation of the assignment (TSC weights sum to one), exact linearity
+    of the force in the bias factor, bitwise independence of the particle order."""
+    import torch
+    from metadynamics_plugin_b200 import workloads
+    w = workloads.c3()
+    pt = w["postype"]
+    N, dims, L, modes = pt.shape[0], w["mesh"], w["L"], w["mode"]
+    assert N == 1 << 20 and tuple(dims) == (128, 128, 128)
+    box = gpu.Box.make(L)
+    d_pt = torch.from_numpy(pt).cuda()
+    mesh = gpu.Mesh(*dims, modes)
+    mesh.set(1, 1)
+    mesh.set(3, 1)
+    cv = mesh.compute_cv(d_pt, N, box).cpu().item()
+    one = torch.tensor([1.0], dtype=torch.float64, device="cuda")
+    f = mesh.forces(d_pt, N, box, one).cpu().numpy()
+    # parity at full size
+    m = oracle.Mesh(*dims, modes, L, N, "f64", literal_copysignf=False)
+    cvo = m.current_value(pt)
+    fo = m.forces(pt, 1.0)
+    m32 = oracle.Mesh(*dims, modes, L, N, "f32")
+    m32.assign(pt)
+    assert np.array_equal(mesh.cells(), m32.cells())
+    assert cv == pytest.approx(cvo, rel=1e-6)
+    assert np.abs(f - fo).max() < 1e-5 * np.abs(fo).max()
+    # mass conservation
+    assert abs(np.asarray(mesh.rho(), dtype=np.float64).sum() - N) < 1e-6 * N
+    # linearity in the bias factor: doubling it doubles every force component exactly
+    mesh.compute_cv(d_pt, N, box)
+    f2 = mesh.forces(d_pt, N, box, 2.0 * one).cpu().numpy()
+    assert np.array_equal(f2, 2.0 * f)
+    # particle order
+    perm = np.random.default_rng(3).permutation(N)
+    d_pp = torch.from_numpy(np.ascontiguousarray(pt[perm])).cuda()
+    other = gpu.Mesh(*dims, modes)
+    cvp = other.compute_cv(d_pp, N, box).cpu().item()
+    fp = other.forces(d_pp, N, box, one).cpu().numpy()
+    assert cvp == cv
+    assert np.array_equal(fp, f[perm])
+
+
 @pytest.mark.parametrize("dims,N", [((64, 64, 64), 70000), ((128, 128, 128), 300000)])
 def test_mesh_bank_order_equals_layer_order(gpu, dims, N):
     """The two orders of the particles inside a tile (knob 6: bank order, layer order) are permutations of one another:
