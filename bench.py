@@ -94,6 +94,7 @@ def make_workload(name, shard=None):
 # ---------------------------------------------------------------------------------------------------- ours
 MERGE_PUSH = False      # --merge-push: peer-memory mode with halo push and barrier in one launch (measured slower)
 NO_PDL = False          # --no-pdl: A/B switch of programmatic dependent launch
+MESH_KNOBS = []         # --mesh-knob K=V: metad_mesh_set(plan, K, V) before the first step (A/B experiments)
 TILE_ORDER = None       # --tile-order: A/B switch of the order inside a tile (library default when None)
 
 
@@ -116,6 +117,8 @@ class MeshStep:
             self.mesh.set(6, {"bank": 1, "layer": 0}[TILE_ORDER])
         if NO_PDL:
             self.mesh.set(7, 0)
+        for k, v in MESH_KNOBS:
+            self.mesh.set(k, v)
         self.d_pt = torch.from_numpy(w["postype"]).cuda()
         self.d_force = torch.empty_like(self.d_pt)
         self.t = 0
@@ -189,6 +192,8 @@ class MeshSlabStep(MeshStep):
             self.mesh.set(7, 0)
         if MERGE_PUSH:
             self.mesh.set(8, 1)
+        for k, v in MESH_KNOBS:
+            self.mesh.set(k, v)
         if mode == "p2p":
             self.mesh.set(5, 1 if sync == "fused" else 0)
             self.mesh.set(4, 1)         # the whole sharded step (incl. the inter-rank waits) replays from one CUDA graph
@@ -235,13 +240,17 @@ class LamellarStep:
             self.cvs[1] = 1.0
         self.t = 0
 
+    def sharded_cv(self):
+        # partial modes -> all-reduce of 2*n_wave doubles -> CV (LamellarOrderParameterGPU.cc:70-77)
+        self.lam.compute_modes(self.d_pt, self.N_global, self.box, finalize=False)
+        self.comm.all_reduce_sum(self.lam.modes)
+        return self.lam.finalize(self.N_global)
+
     def step(self):
         if self.comm is None:
             cv = self.lam.compute_modes(self.d_pt, self.N_global, self.box)
-        else:                           # partial modes -> all-reduce of 2*n_wave doubles -> CV (LamellarOrderParameterGPU.cc:70-77)
-            self.lam.compute_modes(self.d_pt, self.N_global, self.box, finalize=False)
-            self.comm.all_reduce_sum(self.lam.modes)
-            cv = self.lam.finalize(self.N_global)
+        else:
+            cv = self.sharded_cv()
         if self.ncv == 1:
             bias = self.grid.step(self.t, cv)
         else:
@@ -276,6 +285,10 @@ def run_ours(args):
         runner = MeshStep(w, ops, torch) if world == 1 else MeshSlabStep(w, ops, torch, comm, mode=args.comm, sync=args.p2p_sync)
     else:
         runner = LamellarStep(w, ops, torch, comm)
+
+    for kv in args.late_knob:               # experiments that break the results (timing only): set after the calibration
+        k, v = (int(x) for x in kv.split("="))
+        runner.mesh.set(k, v)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -429,12 +442,20 @@ def run_ours(args):
     roofline["frac_nominal_8TBps"] = roofline["achieved"] / (8000.0 * world)
     if "step_frac" in roofline:
         roofline["step_frac_nominal_8TBps"] = roofline["step_frac"] * peak / 8000.0
+    parity = None if args.no_parity else parity_block(w, runner, world, rank, torch)
+    if world > 1:
+        dist.barrier()
     if rank == 0:
+        if parity is not None:
+            out["parity"] = parity
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(w, budget_s=args.cpu_budget)
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+    if rank == 0 and parity is not None and not parity["ok"]:
+        print("bench: PARITY FAILURE against the oracle: %r" % parity, file=sys.stderr)
+        sys.exit(3)
 
 
 def describe(w):
@@ -443,6 +464,70 @@ def describe(w):
             w["postype"].shape[0], *w["mesh"], w["L"])
     return "LamellarOrderParameter %d wave vectors + %d-D well-tempered grid bias, N=%d, L=%.3f" % (
         len(w["lattice_vectors"]), len(w["grid"]["num_points"]), w["postype"].shape[0], w["L"])
+
+
+# ---------------------------------------------------------------------------------------------------- parity
+CV_TOL, FORCE_TOL = 1e-6, 1e-5      # north star: CV 1e-6 relative, forces 1e-5 of max|F|, cell indices bit-exact
+
+
+def parity_block(w, runner, world, rank, torch):
+    """The bench's own workload against the double oracle, in the same run (the checker, never the thing measured):
+    one extra device evaluation with bias = 1 next to one oracle step.  Multi-GPU: every rank evaluates its shard, rank 0
+    compares the (global) CV and the forces / cells of its own shard.  Raises SystemExit(3) outside the tolerances."""
+    one = torch.tensor([1.0], dtype=torch.float64, device="cuda")
+    pt_local = getattr(runner, "h_local", w["postype"])
+    n_global = w["postype"].shape[0]
+    out = {"oracle": "f64 instance of the CPU restatement (pinned to the reference's own sources, tests/test_reference_build.py); "
+                     "mesh forces with |x| exact instead of the double build's copysignf rounding (DESIGN.md section 2)",
+           "cv_tol": CV_TOL, "force_tol": FORCE_TOL, "shard": "rank 0 of %d" % world if world > 1 else "all particles"}
+    if w["kind"] == "mesh":
+        m = runner.mesh
+        if world == 1:
+            m.set(3, 1)                                  # keep the cell indices of this evaluation
+            cv = m.compute_cv(runner.d_pt, runner.N, runner.box).cpu().item()
+            f = m.forces(runner.d_pt, runner.N, runner.box, one).cpu().numpy()
+            cells = m.cells()
+            m.set(3, 0)
+        else:
+            m.set(3, 1)
+            cv = runner.slab.compute_cv(runner.d_pt, n_global, runner.box).cpu().item()
+            f = runner.slab.forces(runner.d_pt, n_global, runner.box, one).cpu().numpy()
+            cells = m.cells()
+            m.set(3, 0)
+        if rank != 0:
+            return None
+        from oracle import pyoracle as po
+        t0 = time.perf_counter()
+        o32 = po.Mesh(*w["mesh"], w["mode"], w["L"], n_global, "f32")
+        o32.assign(pt_local)
+        out["cells_bitexact"] = bool(np.array_equal(cells, o32.cells()))
+        del o32
+        o = po.Mesh(*w["mesh"], w["mode"], w["L"], n_global, "f64", literal_copysignf=False)
+        cvo = o.current_value(w["postype"])
+        fo = o.forces(pt_local, 1.0)
+        out["oracle_seconds"] = round(time.perf_counter() - t0, 2)
+    else:
+        lam = runner.lam
+        if runner.comm is None:
+            cv = lam.compute_modes(runner.d_pt, n_global, runner.box).cpu().item()
+        else:
+            cv = runner.sharded_cv().cpu().item()
+        f = lam.forces(runner.d_pt, n_global, runner.box, one).cpu().numpy()
+        if rank != 0:
+            return None
+        from oracle import pyoracle as po
+        t0 = time.perf_counter()
+        cvo, _ = po.lamellar_cv(w["postype"], n_global, w["mode"], w["lattice_vectors"], w["L"])
+        fo = po.lamellar_forces(pt_local, n_global, w["mode"], w["lattice_vectors"], w["L"], 1.0)
+        out["cells_bitexact"] = None                     # no integer work on the Lamellar path
+        out["oracle_seconds"] = round(time.perf_counter() - t0, 2)
+    out["cv"] = cv
+    out["cv_oracle"] = cvo
+    out["cv_rel"] = abs(cv - cvo) / abs(cvo) if cvo != 0 else abs(cv)
+    fmax = float(np.abs(fo).max())
+    out["force_rel_max"] = float(np.abs(f - fo).max() / fmax) if fmax > 0 else float(np.abs(f).max())
+    out["ok"] = bool(out["cv_rel"] <= CV_TOL and out["force_rel_max"] <= FORCE_TOL and out["cells_bitexact"] in (True, None))
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------- CPU side
@@ -551,10 +636,14 @@ def main():
     ap.add_argument("--order", default="sorted", choices=["sorted", "random"], help="C3 / C4: particle order of the input (cell-sorted headline, random stress case)")
     ap.add_argument("--merge-push", action="store_true", help="peer-memory mode: halo push and barrier in one launch (measured slower)")
     ap.add_argument("--no-pdl", action="store_true", help="launch the per-step kernels without programmatic dependent launch")
+    ap.add_argument("--mesh-knob", action="append", default=[], metavar="K=V", help="metad_mesh_set(plan, K, V) before the first step (experiments)")
+    ap.add_argument("--late-knob", action="append", default=[], metavar="K=V", help="like --mesh-knob, applied after the set-up (timing experiments)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity block (experiments only)")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     args = ap.parse_args()
-    global TILE_ORDER, NO_PDL, PARTICLE_ORDER, MERGE_PUSH
+    global TILE_ORDER, NO_PDL, PARTICLE_ORDER, MERGE_PUSH, MESH_KNOBS
+    MESH_KNOBS = [tuple(int(x) for x in kv.split("=")) for kv in args.mesh_knob]
     MERGE_PUSH = args.merge_push
     PARTICLE_ORDER = args.order
     TILE_ORDER = args.tile_order

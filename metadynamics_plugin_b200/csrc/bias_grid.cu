@@ -194,10 +194,10 @@ grid_step_kernel(GridParams P, GridArrays A, const double* __restrict__ cv_in, d
             else if (mine[cv] + delta > P.cv_max[cv]) { if (!side) v[cv] -= delta; }        // backward: (V(s) - V(s-d))/d
             else v[cv] += side ? delta : -delta;                                            // central
             y = grid_interpolate(P, A.grid, v, &oob);
-        } else if (lane == 2 * d) {
-            y = grid_interpolate(P, A.grid, cur, &oob);
+        } else if (lane == 2 * d) {             // the per-thread copy `mine`, like the derivative lanes: on steps without a deposit
+            y = grid_interpolate(P, A.grid, mine, &oob);     // no barrier orders thread 0's stores to the shared cur[] before these reads
         } else if (lane == 2 * d + 1) {
-            y = grid_interpolate(P, A.weight, cur, &oob);
+            y = grid_interpolate(P, A.weight, mine, &oob);
         }
         const double y_up = __shfl_down_sync(0xffffffffu, y, 1);
         double oob_sum = oob;

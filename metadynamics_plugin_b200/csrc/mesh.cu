@@ -30,6 +30,7 @@
 #include "mesh_fft_kernels.cuh"
 #include "mesh_p2p.cuh"
 
+#include <cuda.h>            // CUtensorMap + cuTensorMapEncodeTiled (resolved through cudaGetDriverEntryPoint, no -lcuda)
 #include <algorithm>
 #include <cmath>
 #include <map>
@@ -65,6 +66,23 @@ struct metad_mesh {
     // mesh
     int* d_mesh_alloc = nullptr;    // integer density: nz planes (+ one ghost plane on each side in slab mode)
     int* d_mesh_i = nullptr;        // local plane 0 inside d_mesh_alloc
+    long long* d_mesh64 = nullptr;  // 64-bit density (wide accumulation; allocated when first needed)
+    // accumulator width: the 32-bit density shares its range between the resolution of one tap and the total of a cell, so
+    // beyond ~11 |a|max of load in one cell the scale -- and with it the precision of the CV -- would have to drop; then
+    // the plan switches to 64-bit accumulation (kSpWide).  Decided at a rebuild of the tile order from the largest cell
+    // load: h_mode[0] (pinned) = 1: 32 bits suffice, 2: wide needed, 3: more particles per cell than the wide tile can
+    // count.  The first rebuild waits for the answer; later ones read it one call late.
+    bool wide = false;
+    unsigned* h_mode = nullptr;
+    // knob 9: the spread writes a per-particle cache for the gather.  Measured at C4 (profiles/r02_*): spread 0.219 + gather
+    // 0.182 ms with the cache, 0.202 + 0.234 ms without (the gather then re-reads the positions through the tile order)
+    bool cache = true;
+    bool tma_flush = true;          // knob 10: flush the spread tile with 3-D tensor-map reductions
+    int spread_debug = 0;           // knob 12: timing experiments (wrong results)
+    bool tma_gather = true;         // knob 11: load the gather tile with one 3-D tensor-map copy when it does not wrap
+    alignas(64) CUtensorMap tmap_mesh = {};     // integer mesh (incl. ghost planes), box = padded tile
+    alignas(64) CUtensorMap tmap_inv = {};      // Re IFFT(G) (d_buf), box = padded tile
+    bool have_tmaps = false;
     float* d_buf = nullptr;         // M_local floats: packed half spectrum -> Re IFFT(G)
     float* d_rho_keep = nullptr;    // optional copy of rho (introspection)
     float2 *d_twx = nullptr, *d_twy = nullptr, *d_twz = nullptr;
@@ -97,7 +115,7 @@ struct metad_mesh {
     // CUDA-graph replay of the per-call kernel sequence (metad_mesh_set key 4): everything a call enqueues after the
     // (eager) tile-order decision is captured once per argument signature and replayed with one launch
     bool graph_mode = false;
-    struct GraphKey { const void* postype; unsigned N, N_global; double L[3]; const void* d_cv; cudaStream_t stream; int kind; bool keep_rho, keep_cells; };
+    struct GraphKey { const void* postype; unsigned N, N_global; double L[3]; const void* d_cv; cudaStream_t stream; int kind; bool keep_rho, keep_cells; int variant; };
     GraphKey gkey = {};
     int gwarm = 0;
     cudaGraphExec_t gexec = nullptr;
@@ -161,7 +179,7 @@ template <int LC> int run_x(metad_mesh* p, bool inverse, float2* io, const doubl
     float2* buf = reinterpret_cast<float2*>(p->d_buf);
     const unsigned lg_part = (io || peer_out) ? ilog2(p->kxl) : ilog2(LC);
     if (!inverse) {
-        int rc = set_smem(fft_x_fwd_kernel<LC>, smem); if (rc) return rc;
+        int rc = set_smem(fft_x_fwd_kernel<LC, false>, smem); if (rc) return rc;
         DensityIn in;
         in.mesh = reinterpret_cast<const int2*>(p->d_mesh_i);
         in.d_fx = p->d_fx;
@@ -177,10 +195,19 @@ template <int LC> int run_x(metad_mesh* p, bool inverse, float2* io, const doubl
         in.zero = reinterpret_cast<int4*>(p->d_mesh_i);
         in.zero_lo = peer_out ? reinterpret_cast<int4*>(p->d_mesh_alloc) : nullptr;
         in.zero_hi = peer_out ? reinterpret_cast<int4*>(p->d_mesh_alloc + ((size_t)p->g.nz + 1) * p->g.nx * p->g.ny) : nullptr;
+        in.mesh64 = reinterpret_cast<const longlong2*>(p->d_mesh64);
+        in.zero64 = reinterpret_cast<int4*>(p->d_mesh64);
+        in.range_counter = p->d_counters + 6;
+        in.h_range = p->h_counters + 3;
         PeerOut po;
         memset(&po, 0, sizeof po);
         if (peer_out) po = *peer_out;
-        METAD_CUDA(launch_pdl(p->pdl, fft_x_fwd_kernel<LC>, rows / kLines, kLines * LC / kE, smem, st, in, p->d_twx, io ? io : buf, lg_part, rows, po, ps));
+        if (p->wide) {
+            rc = set_smem(fft_x_fwd_kernel<LC, true>, smem); if (rc) return rc;
+            METAD_CUDA(launch_pdl(p->pdl, fft_x_fwd_kernel<LC, true>, rows / kLines, kLines * LC / kE, smem, st, in, p->d_twx, io ? io : buf, lg_part, rows, po, ps));
+        } else {
+            METAD_CUDA(launch_pdl(p->pdl, fft_x_fwd_kernel<LC, false>, rows / kLines, kLines * LC / kE, smem, st, in, p->d_twx, io ? io : buf, lg_part, rows, po, ps));
+        }
         METAD_LAUNCH_CHECK();
     } else {
         int rc = set_smem(fft_x_inv_kernel<LC>, smem); if (rc) return rc;
@@ -316,8 +343,10 @@ int ensure_capacity(metad_mesh* p, unsigned N) {
     METAD_CUDA(cudaMalloc(&p->d_keys, sizeof(unsigned) * cap));
     METAD_CUDA(cudaMalloc(&p->d_ranks, sizeof(unsigned) * cap));
     METAD_CUDA(cudaMalloc(&p->d_perm, sizeof(unsigned) * cap));
-    METAD_CUDA(cudaMalloc(&p->d_cache4, sizeof(float4) * cap));
-    METAD_CUDA(cudaMalloc(&p->d_cache_code, sizeof(uint2) * cap));
+    if (p->cache) {
+        METAD_CUDA(cudaMalloc(&p->d_cache4, sizeof(float4) * cap));
+        METAD_CUDA(cudaMalloc(&p->d_cache_code, sizeof(uint2) * cap));
+    }
     p->cap = cap;
     return METAD_OK;
 }
@@ -333,7 +362,7 @@ int set_box(metad_mesh* p, const metad_box* box) {
 }
 
 // counting sort of the particles by tile-major cell key -> perm, tstart; fixed-point scale for the following calls
-int rebuild_order(metad_mesh* p, const float* d_postype, unsigned N, cudaStream_t stream) {
+int rebuild_order(metad_mesh* p, const float* d_postype, unsigned N, cudaStream_t stream, bool sync_mode) {
     const Geom& g = p->g;
     const size_t M = p->M();
     const int sms = device_sm_count();
@@ -373,7 +402,25 @@ int rebuild_order(metad_mesh* p, const float* d_postype, unsigned N, cudaStream_
         else mesh_layer_order_kernel<3><<<num_tiles(g), kLayerThreads, 0, stream>>>(p->d_start, p->d_perm, p->d_ranks);
     }
     METAD_LAUNCH_CHECK();
-    mesh_fx_scale_kernel<<<1, 1, 0, stream>>>(p->d_max_count, p->amax, p->d_fx);
+    // accumulator width for the calls until the next rebuild (see metad_mesh::wide).  The first rebuild of a particle set
+    // waits for the device's answer (nothing is in flight that early); afterwards the answer of rebuild k is read by the
+    // host before rebuild k+1 at the latest (prepare_order), so a step never synchronises.
+    const bool can_wide = !p->g.slab;
+    if (sync_mode) {
+        mesh_fx_mode_kernel<<<1, 1, 0, stream>>>(p->d_max_count, p->amax, p->h_mode);
+        METAD_LAUNCH_CHECK();
+        METAD_CUDA(cudaStreamSynchronize(stream));
+        if (p->h_mode[0] == 3 && can_wide) {
+            set_error("cv.mesh: more than 38 000 particles in one mesh cell -- beyond the range of the fixed-point density");
+            return METAD_ERR_UNSUPPORTED;
+        }
+        p->wide = can_wide && p->h_mode[0] >= 2;
+    }
+    if (p->wide && !p->d_mesh64) {
+        METAD_CUDA(cudaMalloc(&p->d_mesh64, sizeof(long long) * M));
+        METAD_CUDA(cudaMemsetAsync(p->d_mesh64, 0, sizeof(long long) * M, stream));
+    }
+    mesh_fx_scale_kernel<<<1, 1, 0, stream>>>(p->d_max_count, p->amax, p->wide ? 1 : 0, p->d_fx, p->h_mode);
     METAD_LAUNCH_CHECK();
     p->order_valid = true;
     p->order_N = N;
@@ -386,8 +433,57 @@ template <int LGT> size_t tile_smem_bytes() {
     return sizeof(int) * (size_t)((1 << LGT) + 2 * kHaloX) * ((1 << LGT) + 2 * kHalo) * ((1 << LGT) + 2 * kHalo);
 }
 // gather: the tile plus two staging buffers of the particle cache (float4 + uint2 per thread)
-template <int LGT> size_t spread_smem_bytes(int ntypes) { return tile_smem_bytes<LGT>() + kSpreadStages * kSpreadThreads * sizeof(float4) + sizeof(float) * ntypes; }
-template <int LGT> size_t gather_smem_bytes() { return tile_smem_bytes<LGT>() + kGatherStages * kGatherThreads * (sizeof(float4) + sizeof(uint2)); }
+template <int LGT> size_t spread_smem_bytes(int ntypes, int flags) {
+    return sizeof(int) * (size_t)spread_tile_words<LGT>(flags) + kSpreadStages * kSpreadThreads * sizeof(float4) + sizeof(float) * ntypes;
+}
+// staging buffers of the gather: cache entries (float4 + uint2 per thread and stage), or positions + the mode table
+size_t gather_stage_bytes(int threads, bool cache, int ntypes) {
+    return cache ? (size_t)kGatherStages * threads * (sizeof(float4) + sizeof(uint2)) : (size_t)kGatherStages * threads * sizeof(float4) + sizeof(float) * ntypes;
+}
+
+template <int LGT, int FLAGS>
+int launch_spread(metad_mesh* p, const float* d_postype, const SpreadOut& out, cudaStream_t stream) {
+    const Geom& g = p->g;
+    int rc = set_smem(mesh_spread_kernel<LGT, FLAGS>, spread_smem_bytes<LGT>(kSpreadModes, FLAGS)); if (rc) return rc;
+    METAD_CUDA(launch_pdl(p->pdl, mesh_spread_kernel<LGT, FLAGS>, num_tiles(g), kSpreadThreads, spread_smem_bytes<LGT>(p->ntypes, FLAGS), stream,
+                          (const float4*)d_postype, p->d_ranks, p->d_tstart, g, p->d_mode, p->ntypes, p->d_fx, out));
+    return METAD_OK;
+}
+template <int LGT>
+int dispatch_spread(metad_mesh* p, int flags, const float* d_postype, const SpreadOut& out, cudaStream_t stream) {
+    switch (flags) {
+#define METAD_SP(F) case F: return launch_spread<LGT, F>(p, d_postype, out, stream);
+        METAD_SP(0) METAD_SP(1) METAD_SP(2) METAD_SP(3) METAD_SP(4) METAD_SP(5) METAD_SP(6) METAD_SP(7)
+        METAD_SP(8) METAD_SP(9) METAD_SP(10) METAD_SP(11)
+#undef METAD_SP
+        default: set_error("spread: unknown kernel variant"); return METAD_ERR_INVALID;
+    }
+}
+
+// tensor maps of the integer mesh and of Re IFFT(G) with the padded tile as box (the driver entry point is resolved at run
+// time: the library does not link libcuda)
+int ensure_tmaps(metad_mesh* p) {
+    if (p->have_tmaps) return METAD_OK;
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    METAD_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled is not available in this driver"); return METAD_ERR_CUDA; }
+    const Geom& g = p->g;
+    const unsigned T = 1u << g.lgT;
+    const cuuint32_t box[3] = {T + 2 * kHaloX, T + 2 * kHalo, T + 2 * kHalo}, estr[3] = {1, 1, 1};
+    const cuuint64_t planes = (cuuint64_t)g.nz + (g.slab ? 2 : 0);
+    const cuuint64_t dims_mesh[3] = {g.nx, g.ny, planes}, dims_inv[3] = {g.nx, g.ny, g.nz};
+    const cuuint64_t strides[2] = {(cuuint64_t)g.nx * 4, (cuuint64_t)g.nx * g.ny * 4};
+    CUresult r1 = ((EncodeFn)fn)(&p->tmap_mesh, CU_TENSOR_MAP_DATA_TYPE_INT32, 3, p->d_mesh_alloc, dims_mesh, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r2 = ((EncodeFn)fn)(&p->tmap_inv, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p->d_buf, dims_inv, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed for the mesh tiles"); return METAD_ERR_CUDA; }
+    p->have_tmaps = true;
+    return METAD_OK;
+}
 
 // tile order of this call (rebuilt if needed) + spread into the integer mesh; sums -> p->d_sums
 // host-side decision + (rare) rebuild of the tile order: never part of a captured graph
@@ -397,8 +493,17 @@ int prepare_order(metad_mesh* p, const float* d_postype, unsigned N, cudaStream_
     if (N == 0) return METAD_OK;
     // drifted particles / range warnings reported by an earlier spread (asynchronous copy: may lag by a call)
     const bool drift = p->h_counters[1] > N / 256u || p->h_counters[3] > 0;
-    if (!p->order_valid || p->order_N != N || p->calls_since_rebuild >= p->period || drift) {
-        rc = rebuild_order(p, d_postype, N, stream); if (rc) return rc;
+    // accumulator width asked for by the last rebuild (read one or more calls late): a change re-runs the rebuild
+    const unsigned mode = p->h_mode[0];
+    bool mode_change = false;
+    if (p->order_valid && mode != 0 && !p->g.slab) {
+        if (mode == 3) { set_error("cv.mesh: more than 38 000 particles in one mesh cell -- beyond the range of the fixed-point density"); return METAD_ERR_UNSUPPORTED; }
+        mode_change = (mode == 2) != p->wide;
+        if (mode_change) p->wide = mode == 2;
+    }
+    if (!p->order_valid || p->order_N != N || p->calls_since_rebuild >= p->period || drift || mode_change) {
+        const bool first = !p->order_valid || p->order_N != N;
+        rc = rebuild_order(p, d_postype, N, stream, first); if (rc) return rc;
         p->h_counters[1] = p->h_counters[3] = 0;
     }
     ++p->calls_since_rebuild;
@@ -414,7 +519,9 @@ int enqueue_spread(metad_mesh* p, const float* d_postype, unsigned N, cudaStream
         return METAD_OK;
     }
     SpreadOut out;
+    memset(&out, 0, sizeof out);
     out.mesh = p->d_mesh_i;
+    out.mesh64 = p->d_mesh64;
     out.tile_sums = p->d_tile_sums;
     out.sums = p->d_sums;
     out.counters = p->d_counters;
@@ -422,14 +529,17 @@ int enqueue_spread(metad_mesh* p, const float* d_postype, unsigned N, cudaStream
     out.keys = p->keep_cells ? p->d_keys : nullptr;
     out.cache4 = p->d_cache4;
     out.cache_code = p->d_cache_code;
-    if (g.lgT == 4) {
-        rc = set_smem(mesh_spread_kernel<4>, spread_smem_bytes<4>(kSpreadModes)); if (rc) return rc;
-        METAD_CUDA(launch_pdl(p->pdl, mesh_spread_kernel<4>, num_tiles(g), kSpreadThreads, spread_smem_bytes<4>(p->ntypes), stream, (const float4*)d_postype, p->d_ranks, p->d_tstart, g,
-                                                                                           p->d_mode, p->ntypes, p->d_fx, out));
-    } else {
-        METAD_CUDA(launch_pdl(p->pdl, mesh_spread_kernel<3>, num_tiles(g), kSpreadThreads, spread_smem_bytes<3>(p->ntypes), stream, (const float4*)d_postype, p->d_ranks, p->d_tstart, g,
-                                                                                           p->d_mode, p->ntypes, p->d_fx, out));
+    out.debug = p->spread_debug;
+    int flags = (p->keep_cells ? kSpKeys : 0) | (p->cache ? kSpCache : 0);
+    if (p->wide) flags |= kSpWide;
+    else if (p->tma_flush && !g.slab) {
+        rc = ensure_tmaps(p); if (rc) return rc;
+        flags |= kSpTma;
+        out.tmap = p->tmap_mesh;
+        out.tmap_z0 = 0;
     }
+    rc = g.lgT == 4 ? dispatch_spread<4>(p, flags, d_postype, out, stream) : dispatch_spread<3>(p, flags, d_postype, out, stream);
+    if (rc) return rc;
     METAD_LAUNCH_CHECK();
     return METAD_OK;
 }
@@ -483,6 +593,7 @@ metad_mesh::GraphKey make_key(metad_mesh* p, const void* postype, unsigned N, un
     k.postype = postype; k.N = N; k.N_global = N_global;
     for (int i = 0; i < 3; ++i) k.L[i] = box->L[i];
     k.d_cv = d_cv; k.stream = stream; k.kind = kind; k.keep_rho = p->keep_rho; k.keep_cells = p->keep_cells;
+    k.variant = (p->wide ? 1 : 0) | (p->cache ? 2 : 0) | (p->tma_flush ? 4 : 0) | (p->tma_gather ? 8 : 0);
     return k;
 }
 
@@ -500,6 +611,19 @@ int launch_gather(metad_mesh* p, const float* d_postype, const float* d_ghost, f
     fp.nb3[2] = (float)((double)g.nzg / box->L[2]);
     fp.two_over_n = 2.0 / (double)N_global;
     int rc = mark(p, 8, stream); if (rc) return rc;
+    GatherIn gin;
+    memset(&gin, 0, sizeof gin);
+    gin.postype = (const float4*)d_postype;
+    gin.order = p->d_ranks;
+    gin.cache4 = p->d_cache4;
+    gin.cache_code = p->d_cache_code;
+    gin.mode = p->d_mode;
+    gin.ntypes = p->ntypes;
+    if (p->tma_gather && !g.slab) {
+        rc = ensure_tmaps(p); if (rc) return rc;
+        gin.tmap = p->tmap_inv;
+        gin.use_tmap = 1;
+    }
     if (g.lgT == 4) {
         // CTA size / residency of the gather.  Measured on B200 (C4, ms per launch): 256 threads x 3 CTAs/SM (80 registers, the loop
         // state spills) 0.238; 256 x 2 0.210; 192 x 3 (96 registers, no spill) 0.201; 128 x 5 0.216; 128 x 4 0.212; 192 x 4 0.247.
@@ -508,13 +632,14 @@ int launch_gather(metad_mesh* p, const float* d_postype, const float* d_ghost, f
         // C3 0.0266 -> 0.0245 ms.
         static const int forced = getenv("METAD_GATHER_VARIANT") ? atoi(getenv("METAD_GATHER_VARIANT")) : -1;
         const int variant = forced >= 0 ? forced : (num_tiles(g) <= 5u * (unsigned)device_sm_count() ? 3 : 2);
-#define METAD_GATHER_LAUNCH(T_, B_)                                                                                               \
+#define METAD_GATHER_LAUNCH_C(T_, B_, C_)                                                                                         \
     {                                                                                                                             \
-        const size_t sm = tile_smem_bytes<4>() + kGatherStages * (T_) * (sizeof(float4) + sizeof(uint2));                                       \
-        rc = set_smem(mesh_gather_kernel<4, T_, B_>, sm); if (rc) return rc;                                                       \
-        METAD_CUDA(launch_pdl(p->pdl, mesh_gather_kernel<4, T_, B_>, num_tiles(g), T_, sm, stream, (const float4*)d_postype, p->d_tstart, p->d_cache4,        \
-                                                                        p->d_cache_code, g, p->d_buf, d_ghost, fp, d_bias, (float4*)d_force, ps)); \
+        const size_t sm = tile_smem_bytes<4>() + gather_stage_bytes(T_, C_, p->ntypes);                                           \
+        rc = set_smem(mesh_gather_kernel<4, T_, B_, C_>, tile_smem_bytes<4>() + gather_stage_bytes(T_, C_, kSpreadModes)); if (rc) return rc; \
+        METAD_CUDA(launch_pdl(p->pdl, mesh_gather_kernel<4, T_, B_, C_>, num_tiles(g), T_, sm, stream, gin, p->d_tstart, g, p->d_buf, d_ghost, fp, \
+                              d_bias, (float4*)d_force, ps));                                                                     \
     }
+#define METAD_GATHER_LAUNCH(T_, B_) { if (p->cache) METAD_GATHER_LAUNCH_C(T_, B_, true) else METAD_GATHER_LAUNCH_C(T_, B_, false) }
         switch (variant) {
             case 1: METAD_GATHER_LAUNCH(256, 2) break;
             case 2: METAD_GATHER_LAUNCH(192, 3) break;
@@ -528,10 +653,15 @@ int launch_gather(metad_mesh* p, const float* d_postype, const float* d_ghost, f
             default: METAD_GATHER_LAUNCH(256, 3) break;
         }
 #undef METAD_GATHER_LAUNCH
+#undef METAD_GATHER_LAUNCH_C
     } else {
-        METAD_CUDA(launch_pdl(p->pdl, mesh_gather_kernel<3>, num_tiles(g), kGatherThreads, gather_smem_bytes<3>(), stream, (const float4*)d_postype, p->d_tstart,
-                                                                                           p->d_cache4, p->d_cache_code, g, p->d_buf, d_ghost, fp, d_bias,
-                                                                                           (float4*)d_force, ps));
+        const size_t sm = tile_smem_bytes<3>() + gather_stage_bytes(kGatherThreads, p->cache, p->ntypes);
+        if (p->cache)
+            METAD_CUDA(launch_pdl(p->pdl, mesh_gather_kernel<3, kGatherThreads, 3, true>, num_tiles(g), kGatherThreads, sm, stream, gin, p->d_tstart, g, p->d_buf,
+                                  d_ghost, fp, d_bias, (float4*)d_force, ps));
+        else
+            METAD_CUDA(launch_pdl(p->pdl, mesh_gather_kernel<3, kGatherThreads, 3, false>, num_tiles(g), kGatherThreads, sm, stream, gin, p->d_tstart, g, p->d_buf,
+                                  d_ghost, fp, d_bias, (float4*)d_force, ps));
     }
     METAD_LAUNCH_CHECK();
     return mark(p, 9, stream);
@@ -606,6 +736,7 @@ int create_common(metad_mesh** out, unsigned nx, unsigned ny, unsigned nzg, unsi
     TRY(cudaMalloc(&p->d_counters, sizeof(unsigned) * 8));
     TRY(cudaMemset(p->d_counters, 0, sizeof(unsigned) * 8));
     TRY(cudaMallocHost(&p->h_counters, sizeof(unsigned) * 4));
+    TRY(cudaMallocHost(&p->h_mode, sizeof(unsigned) * 4));
     TRY(cudaMalloc(&p->d_partials, sizeof(double) * p->n_partials));
     TRY(cudaMalloc(&p->d_ticket, sizeof(unsigned)));
     TRY(cudaMemset(p->d_ticket, 0, sizeof(unsigned)));
@@ -621,6 +752,7 @@ int create_common(metad_mesh** out, unsigned nx, unsigned ny, unsigned nzg, unsi
 #undef TRY
     if (rc == METAD_OK) {
         memset(p->h_counters, 0, sizeof(unsigned) * 4);
+        memset(p->h_mode, 0, sizeof(unsigned) * 4);
         p->d_mesh_i = p->d_mesh_alloc + (slab ? plane : 0);
     }
     if (rc == METAD_OK) rc = upload_twiddles(&p->d_twx, nx);
@@ -649,6 +781,8 @@ extern "C" int metad_mesh_destroy(metad_mesh* p) {
     cudaFree(p->d_count); cudaFree(p->d_start); cudaFree(p->d_block_sums); cudaFree(p->d_tstart); cudaFree(p->d_max_count);
     cudaFree(p->d_mesh_alloc); cudaFree(p->d_buf); cudaFree(p->d_fx); cudaFree(p->d_tile_sums); cudaFree(p->d_counters);
     if (p->h_counters) cudaFreeHost(p->h_counters);
+    if (p->h_mode) cudaFreeHost(p->h_mode);
+    cudaFree(p->d_mesh64);
     cudaFree(p->d_rho_keep); cudaFree(p->d_twx); cudaFree(p->d_twy); cudaFree(p->d_twz); cudaFree(p->d_sums);
     cudaFree(p->d_partials); cudaFree(p->d_ticket);
     cudaFree(p->d_sums_global); cudaFree(p->d_cv_partial); cudaFree(p->d_p2p_status); cudaFree(p->d_epoch); cudaFree(p->d_sync);
@@ -1106,6 +1240,11 @@ extern "C" int metad_mesh_get(metad_mesh* p, int which, void* h_out) {
             out[0] = (double)p->n_rebuilds; out[1] = c[4]; out[2] = c[5]; out[3] = c[6]; out[4] = fx[0]; out[5] = p->calls_since_rebuild;
             return METAD_OK;
         }
+        case 9: {   // accumulator width, unsigned[2]: {in use: 0 = 32-bit, 1 = 64-bit (wide); asked for by the last rebuild: 1 / 2 / 3, see metad_mesh::wide}
+            unsigned* out = (unsigned*)h_out;
+            out[0] = p->wide ? 1u : 0u; out[1] = p->h_mode[0];
+            return METAD_OK;
+        }
         case 7: *(unsigned long long*)h_out = p->n_graph_launches; return METAD_OK;
         case 6: {   // peer-memory mode: unsigned[2] = {a barrier timed out (a peer never arrived), sum over ranks of particles outside their slab}
             unsigned* out = (unsigned*)h_out;
@@ -1136,6 +1275,12 @@ extern "C" int metad_mesh_set(metad_mesh* p, int key, long value) {
         case 6: p->order_kind = value != 0 ? 1 : 0; p->order_valid = false; return METAD_OK;
         case 7: p->pdl = value != 0; return METAD_OK;
         case 8: p->merge_push = value != 0; return METAD_OK;
+        case 9:                                         // particle cache spread -> gather (round-1 data flow; default off)
+            if (p->cache != (value != 0)) { p->cache = value != 0; p->cap = 0; }
+            return METAD_OK;
+        case 10: p->tma_flush = value != 0; return METAD_OK;
+        case 11: p->tma_gather = value != 0; return METAD_OK;
+        case 12: p->spread_debug = (int)value; return METAD_OK;
         default: set_error("metad_mesh_set: unknown key"); return METAD_ERR_INVALID;
     }
 }

@@ -173,12 +173,16 @@ struct DensityIn {
                             // for the next spread without a separate memset on the critical path (nullptr: leave it)
     int4* zero_lo;          // peer-memory mode: this rank's own ghost planes z = -1 and z = nz (already pushed to the
     int4* zero_hi;          //   neighbours), cleared by the CTAs of the first / last local plane; else nullptr
+    const longlong2* mesh64;    // WIDE instantiation: the density in 64-bit fixed point (unsharded plans only), cleared through zero64
+    int4* zero64;
+    unsigned* range_counter;    // 32-bit density: incremented when a cell has passed half of the range (|v| > 2^30) ...
+    unsigned* h_range;          //   ... and the pinned host word that makes the next call rebuild with a smaller scale
 };
 
 // density of mesh cell pair `v` (+ ghost contribution) as float: value = v / scale
 MHD float2 density_to_float(int2 v, float inv_scale) { return make_float2((float)v.x * inv_scale, (float)v.y * inv_scale); }
 
-template <int LC>
+template <int LC, bool WIDE = false>
 __global__ void __launch_bounds__(kLines * LC / kE)
 fft_x_fwd_kernel(DensityIn in, const float2* __restrict__ g_tw /* length 2*LC */, float2* out,
                  unsigned lg_part /* log2 of the kx pencil width */, unsigned rows_total, const __grid_constant__ PeerOut peers,
@@ -209,12 +213,27 @@ fft_x_fwd_kernel(DensityIn in, const float2* __restrict__ g_tw /* length 2*LC */
     __syncthreads();
     const float mean = (float)(s_sum_a * in.inv_cells);
     const unsigned ny = 1u << in.lgy;
-    // 128-bit loads: kE/2 per thread, all issued before the first use
+    // 128-bit loads: kE/2 per thread (twice as many for the 64-bit density), all issued before the first use
     int4 vin[kE / 2];
+    longlong2 win[WIDE ? kE : 1];
 #pragma unroll
     for (int q = 0; q < kE / 2; ++q) {
         const int idx = threadIdx.x + q * nthr;          // pair index: row w = idx / (LC/2), columns 2*(idx % (LC/2)) and +1
-        vin[q] = __ldcs(reinterpret_cast<const int4*>(in.mesh + (row0 + idx / (LC / 2)) * LC) + idx % (LC / 2));
+        if (WIDE) {
+            const longlong2* src = in.mesh64 + (row0 + idx / (LC / 2)) * LC + 2 * (idx % (LC / 2));
+            win[(2 * q) % (WIDE ? kE : 1)] = __ldcs(src);
+            win[(2 * q + 1) % (WIDE ? kE : 1)] = __ldcs(src + 1);
+        } else {
+            vin[q] = __ldcs(reinterpret_cast<const int4*>(in.mesh + (row0 + idx / (LC / 2)) * LC) + idx % (LC / 2));
+        }
+    }
+    if (!WIDE && in.range_counter) {
+        // the spread accumulates in 32 bits: a cell past half of the range asks for a rebuild with a smaller scale before
+        // anything can wrap (the scale leaves a factor 4 of headroom over the largest cell load at the last rebuild)
+        int m = 0;
+#pragma unroll
+        for (int q = 0; q < kE / 2; ++q) m = max(m, max(max(abs(vin[q].x), abs(vin[q].y)), max(abs(vin[q].z), abs(vin[q].w))));
+        if (m > (1 << 30)) { atomicAdd(in.range_counter, 1u); if (in.h_range) *reinterpret_cast<volatile unsigned*>(in.h_range) = 1u; }
     }
 #pragma unroll
     for (int q2 = 0; q2 < kE; ++q2) {
@@ -223,7 +242,10 @@ fft_x_fwd_kernel(DensityIn in, const float2* __restrict__ g_tw /* length 2*LC */
         const size_t row = row0 + w;
         int2 v = (q2 & 1) ? make_int2(vin[q2 >> 1].z, vin[q2 >> 1].w) : make_int2(vin[q2 >> 1].x, vin[q2 >> 1].y);
         float2 r;
-        if (in.ghost) {
+        if (WIDE) {
+            const longlong2 v64 = win[q2 % (WIDE ? kE : 1)];
+            r = make_float2(__ll2float_rn(v64.x) * inv_scale, __ll2float_rn(v64.y) * inv_scale);
+        } else if (in.ghost) {
             // ranks choose their fixed-point scales independently: equal scales (the common case) add as integers, which
             // reproduces the unsharded density bit for bit; different scales add as floats
             const unsigned z = (unsigned)(row >> in.lgy), y = (unsigned)row & (ny - 1);
@@ -248,7 +270,15 @@ fft_x_fwd_kernel(DensityIn in, const float2* __restrict__ g_tw /* length 2*LC */
         r.x -= mean; r.y -= mean;
         tile[LayoutRow::addr(w, l, LC)] = r;
     }
-    if (in.zero) {
+    if (WIDE) {
+        const int4 z4 = make_int4(0, 0, 0, 0);
+#pragma unroll
+        for (int q = 0; q < kE / 2; ++q) {
+            const int idx = threadIdx.x + q * nthr;
+            int4* dst = in.zero64 + (row0 + idx / (LC / 2)) * LC + 2 * (idx % (LC / 2));
+            dst[0] = z4; dst[1] = z4;
+        }
+    } else if (in.zero) {
         const int4 z4 = make_int4(0, 0, 0, 0);
 #pragma unroll
         for (int q = 0; q < kE / 2; ++q) {

@@ -26,6 +26,7 @@
 #include "common.cuh"
 #include "mesh_fft_kernels.cuh"
 #ifdef __CUDACC__
+#include <cuda.h>            // CUtensorMap
 #include <cuda_pipeline.h>
 #include <cuda/ptx>
 #endif
@@ -259,6 +260,7 @@ MHD void tsc_deriv(float s, float (&w)[3]) {
 // ---------------------------------------------------------------------------------------------------
 // round(a*b) as an integer without the conversion pipe: fma(a, b, 1.5*2^23) has ulp 1, its mantissa bits are
 // 0x4B400000 + rint(a*b) for |a*b| < 2^22 (single rounding, round to nearest even).
+constexpr unsigned kWideMaxCount = (1u << 20) / 27u;    // particles per cell the wide (64-bit) spread can count, see kSpWide
 constexpr float kFxMagic = 12582912.0f;
 constexpr int kFxMagicBits = 0x4B400000;
 MHD int fx_round(float a, float b) { return f2i_bits(f_fma(a, b, kFxMagic)) - kFxMagicBits; }
@@ -328,6 +330,28 @@ MHD bool tile_row(int ox, int oy, int oz, int py, int pz, int PX, const Geom& g,
 // in-cell offsets of a particle (cell units)
 MHD float3 particle_shift(float4 p, const Cell& c, const Geom& g) {
     return make_float3(cell_shift(p.x, c.rx, 0, g), cell_shift(p.y, c.ry, 1, g), cell_shift(p.z, c.rz, 2, g));
+}
+// Stencil base.  The cell of particle_cell() follows the reference's SINGLE-precision rule bit for bit (that is what is
+// reported as "the cell of the particle"), but for a particle within ~n 2^-23 cells of a face it can differ from the
+// cell that holds the particle in exact arithmetic -- the cell a double-precision build of the reference picks.  The
+// offset measured from it then lies outside [-1/2, 1/2] by that much, and because the TSC derivative weights are only
+// piecewise linear (W'' jumps at |x| = 1/2, OrderParameterMesh.cc:470-483) extending the inner polynomials would put a
+// FIRST-order error of 3 (|s| - 1/2) into the force of that particle (measured: 1.6e-5 of max|F| for 512 cells per
+// axis, 3.9e-5 for 1024 -- the parity tolerance is 1e-5).  So the 27 taps are placed around the cell the accurate offset
+// points to: s > 1/2 moves the base one cell up, s < -1/2 one cell down (periodic).  A z slab keeps its own base when
+// the move would leave the slab (its ghost planes hold one layer only).
+MHD void rebase_axis(int& i, float& s, unsigned n) {
+    const int adj = (s > 0.5f ? 1 : 0) - (s < -0.5f ? 1 : 0);
+    i = (int)((unsigned)(i + adj) & (n - 1));
+    s -= (float)adj;
+}
+MHD void particle_rebase(Cell& c, float3& s, const Geom& g) {
+    rebase_axis(c.ix, s.x, g.nx);
+    rebase_axis(c.iy, s.y, g.ny);
+    int iz = c.iz;
+    float sz = s.z;
+    rebase_axis(iz, sz, g.nzg);
+    if (!g.slab || (unsigned)(iz - (int)g.z0) < g.nz) { c.iz = iz; s.z = sz; }
 }
 // separable weights: w[0..2] = Wx(tap -1,0,+1), w[3..5] = Wy, w[6..8] = amp * Wz
 MHD void spread_weights(float3 s, float amp, float (&w)[9]) {
@@ -456,11 +480,23 @@ mesh_bin_kernel(const float4* __restrict__ postype, unsigned N, Geom g, const fl
 }
 
 // fixed-point scale of the density for the calls until the next rebuild: d_fx = {scale, 1/scale}
-__global__ void mesh_fx_scale_kernel(const unsigned* __restrict__ max_count, float amax, float* __restrict__ d_fx) {
-    const float s = fx_scale_for(amax, amax * (float)*max_count);
+// wide: the accumulators are 64 bits wide, only the tap limit applies.  h_mode (pinned host word, may be null) receives
+// what the cell loads of this rebuild ask for: 1 = 32-bit accumulation keeps the full tap resolution, 2 = 64-bit
+// accumulation needed for that, 3 = more particles in one cell than the split 32-bit tiles of the wide spread can count
+MHD unsigned fx_mode_for(float amax, unsigned max_count) {
+    if (max_count > kWideMaxCount) return 3u;
+    return fx_scale_for(amax, amax * (float)max_count) < fx_scale_for(amax, amax) ? 2u : 1u;
+}
+__global__ void mesh_fx_mode_kernel(const unsigned* __restrict__ max_count, float amax, unsigned* __restrict__ h_mode) {
+    *h_mode = fx_mode_for(amax, *max_count);
+}
+__global__ void mesh_fx_scale_kernel(const unsigned* __restrict__ max_count, float amax, int wide, float* __restrict__ d_fx,
+                                     unsigned* __restrict__ h_mode) {
+    const float s = wide ? fx_scale_for(amax, amax) : fx_scale_for(amax, amax * (float)*max_count);
     d_fx[0] = s;
     d_fx[1] = 1.0f / s;
     d_fx[4] = 1.0f / s;          // 16-byte aligned copy: trailer of the halo messages (peer-memory mode)
+    if (h_mode) *h_mode = fx_mode_for(amax, *max_count);
 }
 
 // ---- exclusive scan of count[0..n) -> start[0..n].  Three launches: per-block sums, scan of the block sums (single
@@ -727,34 +763,59 @@ constexpr int kSpreadThreads = 256;
 constexpr int kSpreadL2Lead = 4;      // iterations between the L2 prefetch of a permutation index and its load
 constexpr int kSpreadStages = 3;       // staging buffers of the positions (kSpreadStages - 1 particles in flight per thread)
 constexpr int kSpreadModes = 1024;     // most particle types supported (their mode coefficients are staged in shared memory)
+// kernel variants (template FLAGS of the spread, CACHE also of the gather)
+constexpr int kSpKeys = 1;             // store the tile-major cell key of every particle (introspection, tests)
+constexpr int kSpCache = 2;            // write the particle cache {offsets, amplitude, code word, index} for the gather
+constexpr int kSpWide = 4;             // 64-bit accumulation: the density of a cell no longer shares 32 bits with the resolution
+constexpr int kSpTma = 8;              // flush interior tiles with one 3-D tensor-map reduction (cp.reduce.async.bulk.tensor)
+// Wide accumulation.  sm_100a has no native 64-bit shared-memory atomic add (atom.shared.add.u64 compiles to a
+// ATOMS.CAST.SPIN loop), so a tap v (|v| < 2^22) is split as v = hi * 2^12 + lo, 0 <= lo < 2^12, and the two parts are
+// added to two 32-bit tiles with the native ATOMS.ADD; a tile cell can take 2^20 taps (lo) / 2^21 taps (hi), i.e. about
+// 38 000 particles per mesh cell.  The flush adds hi * 2^12 + lo to a 64-bit global mesh (RED.E.ADD.64, native).
+constexpr int kWideLoBits = 12;
 // counters[] (device, unsigned): [0] ticket, [1] particles handled by the direct path (drifted out of their padded
-// tile), [2] particles outside the slab (caller error), [3] cells past half of the fixed-point range
+// tile), [2] particles outside the slab (caller error), [3] unused; [4..5] = [1..2] of the last finished spread,
+// [6] cells past half of the 32-bit range seen by the x sweep that consumed the density of the last spread
 struct SpreadOut {
     int* mesh;               // integer density, local plane 0 (slab: ghost planes at -1 and nz)
+    long long* mesh64;       // the same in 64 bits (wide accumulation; unsharded plans only)
     double* tile_sums;       // [ntiles][2] partial sum a^2, sum a
     double* sums;            // [0] sum a^2 (m_mode_sq, OrderParameterMesh.cc:623), [1] sum a, [2] particles outside the slab
-    unsigned* counters;      // [0] ticket, [1..3] running counters of this launch, [4..6] counters of the last finished spread
+    unsigned* counters;      // see above
     unsigned* h_counters;    // pinned host words [1..3] (device-visible address), or nullptr
-    unsigned* keys;          // optional: tile-major cell key per particle (introspection), or nullptr
-    float4* cache4;          // particle cache for the gather, tile order: {sx, sy, sz, a}
+    unsigned* keys;          // kSpKeys: tile-major cell key per particle
+    float4* cache4;          // kSpCache: particle cache for the gather, tile order: {sx, sy, sz, a}
     uint2* cache_code;       //   ... and {code word (cache_code()), particle index}
+    // kSpTma: tensor map of the integer mesh (dims nx, ny, planes incl. ghosts; box = padded tile).  It travels inside this
+    // __grid_constant__ kernel parameter: the TMA unit fetches descriptors through its own cache, parameter space is the
+    // one place that needs no tensormap proxy fence
+    alignas(64) CUtensorMap tmap;
+    int tmap_z0;             //   ... plane index of local plane 0 inside that tensor (1 for a slab, else 0)
+    int debug;               // timing experiments only (knob 12; results are WRONG): 1 = no flush, 2 = no tile atomics
 };
 
-template <int LGT>
+template <int LGT> MHD constexpr int spread_tile_words(int flags) {
+    return ((1 << LGT) + 2 * kHaloX) * ((1 << LGT) + 2 * kHalo) * ((1 << LGT) + 2 * kHalo) * ((flags & kSpWide) ? 2 : 1);
+}
+
+template <int LGT, int FLAGS>
 __global__ void __launch_bounds__(kSpreadThreads)
 mesh_spread_kernel(const float4* __restrict__ postype, const unsigned* __restrict__ perm, const unsigned* __restrict__ tstart,
-                   Geom g, const float* __restrict__ mode, int ntypes, const float* __restrict__ d_fx, SpreadOut out) {
+                   const __grid_constant__ Geom g, const float* __restrict__ mode, int ntypes, const float* __restrict__ d_fx,
+                   const __grid_constant__ SpreadOut out) {
+    constexpr bool KEYS = FLAGS & kSpKeys, CACHE = FLAGS & kSpCache, WIDE = FLAGS & kSpWide, TMA = (FLAGS & kSpTma) && !WIDE;
     constexpr int T = 1 << LGT, PX = T + 2 * kHaloX, PY = T + 2 * kHalo, PZ = PY, P3 = PX * PY * PZ;
-    extern __shared__ __align__(16) int tile[];
+    constexpr int TW = spread_tile_words<LGT>(FLAGS);
+    extern __shared__ __align__(128) int tile[];      // P3 words (WIDE: the low parts, then P3 words of high parts)
     __shared__ double red[32];
     __shared__ bool is_last;
     // mode coefficients in shared memory: a global load here shares a scoreboard with the position prefetch of the NEXT
     // particle (ptxas puts all three loads of the loop on one), so its first consumer waited for that prefetch in every
     // iteration (measured: 35 % of all stall samples)
-    float4* s_pos = reinterpret_cast<float4*>(tile + P3);         // [kSpreadStages][kSpreadThreads] staged positions, behind the tile
+    float4* s_pos = reinterpret_cast<float4*>(tile + TW);         // [kSpreadStages][kSpreadThreads] staged positions, behind the tile
     float* s_mode = reinterpret_cast<float*>(s_pos + kSpreadStages * kSpreadThreads);       // [ntypes]
     // the tile is cleared before the programmatic-launch wait: this part overlaps the tail of the previous kernel
-    for (int i = threadIdx.x; i < P3 / 4; i += kSpreadThreads) reinterpret_cast<int4*>(tile)[i] = make_int4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < TW / 4; i += kSpreadThreads) reinterpret_cast<int4*>(tile)[i] = make_int4(0, 0, 0, 0);
     pdl_wait(); pdl_trigger();
     for (int i = threadIdx.x; i < ntypes; i += kSpreadThreads) s_mode[i] = __ldg(mode + i);
     const unsigned s = __ldg(tstart + blockIdx.x), e = __ldg(tstart + blockIdx.x + 1);
@@ -766,6 +827,7 @@ mesh_spread_kernel(const float4* __restrict__ postype, const unsigned* __restric
         __syncthreads();
         const float scale = __ldg(d_fx);
         unsigned strays = 0, foreign = 0;
+        int outer = 0;          // a tap of this thread landed in the outermost y / z layer of the padded tile
         // software pipeline: positions are staged through shared memory with asynchronous copies, kSpreadStages - 1
         // particles ahead (one iteration is shorter than the loaded DRAM latency: with one position in flight 27 % of
         // all stall samples sat on its first use); the index of the particle after those is in flight in a register
@@ -799,19 +861,25 @@ mesh_spread_kernel(const float4* __restrict__ postype, const unsigned* __restric
             const unsigned n = nq[0];
             if (++buf == kSpreadStages) buf = 0;
             const float a = s_mode[__float_as_int(p.w)];
-            const Cell c = particle_cell(p, g);
-            if (out.keys) out.keys[n] = key_of(c.ix, c.iy, (unsigned)(c.iz - (int)g.z0) & (g.nz - 1), g);
-            const float3 sh = particle_shift(p, c, g);
+            Cell c = particle_cell(p, g);
+            if (KEYS) out.keys[n] = key_of(c.ix, c.iy, (unsigned)(c.iz - (int)g.z0) & (g.nz - 1), g);
+            float3 sh = particle_shift(p, c, g);
+            particle_rebase(c, sh, g);
             unsigned lx = 0, ly = 0, lz = 0;
             const bool inside = c.owned && padded_coords(c, ox, oy, oz, g, PX, PY, PZ, lx, ly, lz);
-            out.cache4[j] = make_float4(sh.x, sh.y, sh.z, a);
-            out.cache_code[j] = make_uint2(cache_code(lx, ly, lz, inside, c.owned), n);
+            if (CACHE) {
+                out.cache4[j] = make_float4(sh.x, sh.y, sh.z, a);
+                out.cache_code[j] = make_uint2(cache_code(lx, ly, lz, inside, c.owned), n);
+            }
             if (c.owned) {
                 sq += (double)a * (double)a;
                 s1 += (double)a;
                 float w[9];
                 spread_weights(sh, a * scale, w);
-                if (inside) {
+                if (inside && (out.debug & 2)) {
+                } else if (inside) {
+                    // the flush skips the outermost y / z layers of the padded tile unless a particle has drifted that far
+                    outer |= (int)((ly - 2u) >= (unsigned)(PY - 4)) | (int)((lz - 2u) >= (unsigned)(PZ - 4));
                     int* base = tile + ((lz - 1) * PY + (ly - 1)) * PX + (lx - 1);
                     // tap (i, jj, k) = fx_round(w[i], w[3 + jj] * w[6 + k]) as on every other path, two per instruction
                     const F2 w01 = f2_pack(w[0], w[1]), wy01 = f2_pack(w[3], w[4]), magic = f2_dup(kFxMagic);
@@ -825,9 +893,17 @@ mesh_spread_kernel(const float4* __restrict__ postype, const unsigned* __restric
                             float t0, t1;
                             f2_unpack(f2_fma(w01, f2_dup(wyz[jj]), magic), t0, t1);
                             int* row = base + (k * PY + jj) * PX;
-                            atomicAdd(row, __float_as_int(t0) - kFxMagicBits);
-                            atomicAdd(row + 1, __float_as_int(t1) - kFxMagicBits);
-                            atomicAdd(row + 2, fx_round(w[2], wyz[jj]));
+                            const int v0 = __float_as_int(t0) - kFxMagicBits, v1 = __float_as_int(t1) - kFxMagicBits, v2 = fx_round(w[2], wyz[jj]);
+                            if (WIDE) {
+                                constexpr int LO = (1 << kWideLoBits) - 1;
+                                atomicAdd(row, v0 & LO); atomicAdd(row + P3, v0 >> kWideLoBits);
+                                atomicAdd(row + 1, v1 & LO); atomicAdd(row + 1 + P3, v1 >> kWideLoBits);
+                                atomicAdd(row + 2, v2 & LO); atomicAdd(row + 2 + P3, v2 >> kWideLoBits);
+                            } else {
+                                atomicAdd(row, v0);
+                                atomicAdd(row + 1, v1);
+                                atomicAdd(row + 2, v2);
+                            }
                         }
                     }
                 } else {
@@ -836,7 +912,10 @@ mesh_spread_kernel(const float4* __restrict__ postype, const unsigned* __restric
                         for (int jj = 0; jj < 3; ++jj)
                             for (int i = 0; i < 3; ++i) {
                                 long long idx;
-                                if (tap_index(c, i, jj, k, g, idx)) atomicAdd(out.mesh + idx, tap_value(w, i, jj, k));
+                                if (tap_index(c, i, jj, k, g, idx)) {
+                                    if (WIDE) atomicAdd(reinterpret_cast<unsigned long long*>(out.mesh64 + idx), (unsigned long long)(long long)tap_value(w, i, jj, k));
+                                    else atomicAdd(out.mesh + idx, tap_value(w, i, jj, k));
+                                }
                             }
                 }
             } else {
@@ -849,35 +928,55 @@ mesh_spread_kernel(const float4* __restrict__ postype, const unsigned* __restric
         }
         if (strays) atomicAdd(out.counters + 1, strays);
         if (foreign) atomicAdd(out.counters + 2, foreign);
-        __syncthreads();
-        // flush: one thread per row of the padded tile; a row that received anything is added to the mesh by ONE bulk
-        // asynchronous reduction (cp.reduce.async.bulk .add.s32, executed by the TMA engine / L2), two if it wraps in x
-        cuda::ptx::fence_proxy_async(cuda::ptx::space_shared);      // the tile was written through the generic proxy
+        const int any_outer = __syncthreads_or(outer);
         const size_t plane = (size_t)g.nx * g.ny;
-        int vmax = 0;
-        for (int row = threadIdx.x; row < PY * PZ; row += kSpreadThreads) {
-            const int4* r4 = reinterpret_cast<const int4*>(tile + row * PX);
-            int m = 0;
-#pragma unroll
-            for (int q = 0; q < PX / 4; ++q) {
-                const int4 v = r4[q];
-                m = max(m, max(max(abs(v.x), abs(v.y)), max(abs(v.z), abs(v.w))));
+        if (out.debug & 1) {
+        } else if (WIDE) {
+            // flush into the 64-bit mesh, one thread per row of the padded tile
+            for (int row = threadIdx.x; row < PY * PZ; row += kSpreadThreads) {
+                TileRow r;
+                if (!tile_row(ox, oy, oz, row % PY, row / PY, PX, g, r)) continue;
+                long long* dst = out.mesh64 + (long long)r.z * (long long)plane + (size_t)r.y * g.nx;
+                const int* lo = tile + row * PX;
+#pragma unroll 4
+                for (int i = 0; i < PX; ++i) {
+                    const long long v = ((long long)lo[i + P3] << kWideLoBits) + (long long)(unsigned)lo[i];
+                    if (v != 0) atomicAdd(reinterpret_cast<unsigned long long*>(dst + ((r.x0 + i) & (g.nx - 1))), (unsigned long long)v);
+                }
             }
-            TileRow r;
-            if (m != 0 && tile_row(ox, oy, oz, row % PY, row / PY, PX, g, r)) {
-                vmax = max(vmax, m);
-                int* dst = out.mesh + (long long)r.z * (long long)plane + (size_t)r.y * g.nx;
-                cuda::ptx::cp_reduce_async_bulk(cuda::ptx::space_global, cuda::ptx::space_shared, cuda::ptx::op_add, dst + r.x0,
-                                                tile + row * PX, (unsigned)(r.first * sizeof(int)));
-                if (r.first < PX)
-                    cuda::ptx::cp_reduce_async_bulk(cuda::ptx::space_global, cuda::ptx::space_shared, cuda::ptx::op_add, dst,
-                                                    tile + row * PX + r.first, (unsigned)((PX - r.first) * sizeof(int)));
+        } else if (TMA && !g.slab && ox >= 0 && oy >= 0 && oz >= 0 && ox + PX <= (int)g.nx && oy + PY <= (int)g.ny && oz + PZ <= (int)g.nz) {
+            // flush of a tile that does not wrap periodically: ONE 3-D tensor-map reduction adds the whole padded tile to the
+            // mesh (cp.reduce.async.bulk.tensor, UTMAREDG in SASS).  Measured on B200 (tools/micro/tma_reduce_test.cu): the
+            // reduction form of the instruction faults with "illegal instruction" when the box leaves the tensor (negative
+            // or overhanging coordinates are fine for loads, not for reductions), so boundary tiles take the row path below.
+            cuda::ptx::fence_proxy_async(cuda::ptx::space_shared);      // the tile was written through the generic proxy
+            if (threadIdx.x == 0) {
+                const int32_t crd[3] = {ox, oy, oz};
+                cuda::ptx::cp_reduce_async_bulk_tensor(cuda::ptx::space_global, cuda::ptx::space_shared, cuda::ptx::op_add, &out.tmap, crd, tile);
+                cuda::ptx::cp_async_bulk_commit_group();
+                cuda::ptx::cp_async_bulk_wait_group_read(cuda::ptx::n32_t<0>());       // the tile must outlive the reads
             }
+        } else {
+            // flush: one thread per row of the padded tile, ONE bulk asynchronous reduction per row (cp.reduce.async.bulk
+            // .add.s32, executed by the TMA engine / L2), two if it wraps in x.  The outermost y / z layers are skipped
+            // unless a particle of this tile has drifted that far.
+            cuda::ptx::fence_proxy_async(cuda::ptx::space_shared);      // the tile was written through the generic proxy
+            for (int row = threadIdx.x; row < PY * PZ; row += kSpreadThreads) {
+                const int py = row % PY, pz = row / PY;
+                const bool inner = (unsigned)(py - 1) < (unsigned)(PY - 2) && (unsigned)(pz - 1) < (unsigned)(PZ - 2);
+                TileRow r;
+                if ((inner || any_outer) && tile_row(ox, oy, oz, py, pz, PX, g, r)) {
+                    int* dst = out.mesh + (long long)r.z * (long long)plane + (size_t)r.y * g.nx;
+                    cuda::ptx::cp_reduce_async_bulk(cuda::ptx::space_global, cuda::ptx::space_shared, cuda::ptx::op_add, dst + r.x0,
+                                                    tile + row * PX, (unsigned)(r.first * sizeof(int)));
+                    if (r.first < PX)
+                        cuda::ptx::cp_reduce_async_bulk(cuda::ptx::space_global, cuda::ptx::space_shared, cuda::ptx::op_add, dst,
+                                                        tile + row * PX + r.first, (unsigned)((PX - r.first) * sizeof(int)));
+                }
+            }
+            cuda::ptx::cp_async_bulk_commit_group();
+            cuda::ptx::cp_async_bulk_wait_group_read(cuda::ptx::n32_t<0>());       // the tile must outlive the reads
         }
-        cuda::ptx::cp_async_bulk_commit_group();
-        // one eighth of the range: a cell sums at most 8 padded tiles, so no total has left the 32-bit range
-        if (__any_sync(0xffffffffu, vmax > (1 << 28)) && (threadIdx.x & 31) == 0) atomicAdd(out.counters + 3, 1u);
-        cuda::ptx::cp_async_bulk_wait_group_read(cuda::ptx::n32_t<0>());       // the tile must outlive the reads
     }
     // deterministic sums: per-tile partials, the last CTA adds them in tile order
     const double tsq = block_sum(sq, red);
@@ -897,14 +996,15 @@ mesh_spread_kernel(const float4* __restrict__ postype, const unsigned* __restric
     a1 = block_sum(a1, red);
     if (threadIdx.x == 0) {
         // every other CTA has taken its ticket, i.e. finished its counter updates: publish the counters of this spread
-        // (device snapshot for metad_mesh_get, pinned host words for the drift / range decision of a later call -- a
-        // plain store to mapped host memory instead of a copy node on the critical path) and clear them for the next one
-        const unsigned c1 = __ldcg(out.counters + 1), c2 = __ldcg(out.counters + 2), c3 = __ldcg(out.counters + 3);
+        // (device snapshot for metad_mesh_get, pinned host words for the drift decision of a later call -- a plain store
+        // to mapped host memory instead of a copy node on the critical path) and clear them for the next one.  The range
+        // counter [6] / host word [3] belongs to the x sweep that consumes this density (fft_x_fwd_kernel).
+        const unsigned c1 = __ldcg(out.counters + 1), c2 = __ldcg(out.counters + 2);
         out.sums[0] = a2;
         out.sums[1] = a1;
         out.sums[2] = (double)c2;
-        out.counters[4] = c1; out.counters[5] = c2; out.counters[6] = c3;
-        if (out.h_counters) { out.h_counters[1] = c1; out.h_counters[2] = c2; out.h_counters[3] = c3; }
+        out.counters[4] = c1; out.counters[5] = c2; out.counters[6] = 0;
+        if (out.h_counters) { out.h_counters[1] = c1; out.h_counters[2] = c2; }
         out.counters[1] = 0; out.counters[2] = 0; out.counters[3] = 0;
         out.counters[0] = 0;
     }
@@ -914,16 +1014,18 @@ mesh_spread_kernel(const float4* __restrict__ postype, const unsigned* __restric
 // gather: one CTA per tile; shared tile of Re(IFFT(G)) with halo; one thread per particle of the tile
 // ---------------------------------------------------------------------------------------------------
 constexpr int kGatherThreads = 256;
-constexpr int kGatherStages = 4;       // staging buffers of the particle cache (kGatherStages - 1 entries in flight per thread)
+constexpr int kGatherStages = 4;       // staging buffers of the particle data (kGatherStages - 1 entries in flight per thread)
 
 // slow path of a particle that drifted out of its padded tile: the 27 taps come from global memory.  Not inlined and
 // fed by value, so that the fast path keeps its weights in registers; recomputes cell and weights from the position.
 struct GatherDirectArgs { const float* inv; const float* ghost; const Geom* g; };
 __device__ __noinline__ float3 gather_direct(float4 p, GatherDirectArgs a) {
     const Geom g = *a.g;
-    const Cell c = particle_cell(p, g);
+    Cell c = particle_cell(p, g);
+    float3 sh = particle_shift(p, c, g);
+    particle_rebase(c, sh, g);
     GatherWeights w;
-    gather_weights(particle_shift(p, c, g), w);
+    gather_weights(sh, w);
     const size_t plane = (size_t)g.nx * g.ny;
     float t27[27];
     for (int k = 0; k < 3; ++k)
@@ -941,19 +1043,32 @@ __device__ __noinline__ float3 gather_direct(float4 p, GatherDirectArgs a) {
     return S;
 }
 
-template <int LGT, int THREADS = kGatherThreads, int MINB = 3>
+// what the gather reads per particle: CACHE -- the entries the spread wrote (24 B, tile order); otherwise the tile order
+// (4 B) and the position (16 B, through the order), from which cell, offsets and amplitude are recomputed: the spread then
+// writes nothing per particle (its DRAM traffic drops from 2.45x to ~1.2x of the algorithmic bytes at C4).
+struct GatherIn {
+    const float4* postype;
+    const unsigned* order;          // tile order (no cache)
+    const float4* cache4;           // particle cache
+    const uint2* cache_code;
+    const float* mode;              // mode coefficients per type (no cache)
+    int ntypes;
+    int use_tmap;                   // tmap is valid
+    alignas(64) CUtensorMap tmap;   // tensor map of Re IFFT(G) (dims nx, ny, nz; box = padded tile), inside the __grid_constant__ parameter
+};
+
+template <int LGT, int THREADS = kGatherThreads, int MINB = 3, bool CACHE = true>
 __global__ void __launch_bounds__(THREADS, MINB)
-mesh_gather_kernel(const float4* __restrict__ postype, const unsigned* __restrict__ tstart,
-                   const float4* __restrict__ cache4, const uint2* __restrict__ cache_code,
-                   const __grid_constant__ Geom g, const float* __restrict__ inv,
-                   const float* __restrict__ ghost /* slab mode: planes z0-1 and z0+nz of Re IFFT(G) */, ForceParams fp,
-                   const double* __restrict__ d_bias, float4* __restrict__ force, const __grid_constant__ fft::PeerSync sync) {
+mesh_gather_kernel(const __grid_constant__ GatherIn in, const unsigned* __restrict__ tstart, const __grid_constant__ Geom g,
+                   const float* __restrict__ inv, const float* __restrict__ ghost /* slab mode: planes z0-1 and z0+nz of Re IFFT(G) */,
+                   ForceParams fp, const double* __restrict__ d_bias, float4* __restrict__ force, const __grid_constant__ fft::PeerSync sync) {
     constexpr int T = 1 << LGT, PX = T + 2 * kHaloX, PY = T + 2 * kHalo, PZ = PY, P3 = PX * PY * PZ;
-    extern __shared__ __align__(16) float ftile[];          // P3 floats, then the staging buffers of the particle cache
+    extern __shared__ __align__(128) float ftile[];          // P3 floats, then the staging buffers
     pdl_wait(); pdl_trigger();
     fft::peer_wait(sync);                                   // fused peer mode: the neighbours' halo planes of Re IFFT(G) have arrived
-    float4* s_q = reinterpret_cast<float4*>(ftile + P3);    // [kGatherStages][THREADS]
-    uint2* s_c = reinterpret_cast<uint2*>(s_q + kGatherStages * THREADS);
+    float4* s_q = reinterpret_cast<float4*>(ftile + P3);    // [kGatherStages][THREADS]: cache entries / positions
+    uint2* s_c = reinterpret_cast<uint2*>(s_q + kGatherStages * THREADS);        // CACHE: code words; else the mode coefficients
+    float* s_mode = reinterpret_cast<float*>(s_c);
     __shared__ uint64_t bar;
     const unsigned s = __ldg(tstart + blockIdx.x), e = __ldg(tstart + blockIdx.x + 1);
     if (e == s) return;                                   // empty tile: nothing to interpolate
@@ -962,10 +1077,20 @@ mesh_gather_kernel(const float4* __restrict__ postype, const unsigned* __restric
     const int ox = (int)(tx << LGT) - kHaloX, oy = (int)(ty << LGT) - kHalo, oz = (int)(tz << LGT) - kHalo;
     const size_t plane = (size_t)g.nx * g.ny;
     if (threadIdx.x == 0) cuda::ptx::mbarrier_init(&bar, THREADS);
+    if (!CACHE) for (int i = threadIdx.x; i < in.ntypes; i += THREADS) s_mode[i] = __ldg(in.mode + i);
     __syncthreads();
-    // padded tile of Re IFFT(G): one bulk asynchronous copy (cp.async.bulk, TMA engine) per row, two if the row wraps in x;
-    // completion is counted in bytes on an mbarrier
-    {
+    // padded tile of Re IFFT(G).  A tile that does not wrap periodically comes with ONE 3-D tensor-map copy
+    // (cp.async.bulk.tensor, UTMALDG); otherwise one bulk asynchronous copy per row (two if the row wraps in x).
+    // Completion is counted in bytes on an mbarrier.
+    const bool interior = in.use_tmap && !g.slab && ox >= 0 && oy >= 0 && oz >= 0 && ox + PX <= (int)g.nx && oy + PY <= (int)g.ny && oz + PZ <= (int)g.nz;
+    if (interior) {
+        if (threadIdx.x == 0) {
+            const int32_t crd[3] = {ox, oy, oz};
+            cuda::ptx::cp_async_bulk_tensor(cuda::ptx::space_cluster, cuda::ptx::space_global, ftile, &in.tmap, crd, &bar);
+        }
+        cuda::ptx::mbarrier_arrive_expect_tx(cuda::ptx::sem_release, cuda::ptx::scope_cta, cuda::ptx::space_shared, &bar,
+                                             threadIdx.x == 0 ? (unsigned)(P3 * sizeof(float)) : 0u);
+    } else {
         unsigned bytes = 0;
         for (int row = threadIdx.x; row < PY * PZ; row += THREADS) {
             TileRow r;
@@ -989,54 +1114,109 @@ mesh_gather_kernel(const float4* __restrict__ postype, const unsigned* __restric
         cuda::ptx::mbarrier_arrive_expect_tx(cuda::ptx::sem_release, cuda::ptx::scope_cta, cuda::ptx::space_shared, &bar, bytes);
     }
     const float scale = (float)(fp.two_over_n * *d_bias);
-    // one thread per particle of the tile; offsets, amplitude, padded-tile cell and particle index come from the cache
-    // the spread wrote.  The entries are staged through shared memory with asynchronous copies.
-    // kGatherStages - 1 entries in flight per thread: one iteration of this loop is shorter than the loaded DRAM latency
-    // (with a single entry in flight 26 % of all stall samples sat on the wait below)
     unsigned j = s + threadIdx.x;
     int buf = 0;
+    if constexpr (CACHE) {
+        // one thread per particle of the tile; offsets, amplitude, padded-tile cell and particle index come from the cache
+        // the spread wrote.  The entries are staged through shared memory with asynchronous copies, kGatherStages - 1 in
+        // flight per thread: one iteration of this loop is shorter than the loaded DRAM latency
 #pragma unroll
-    for (int d = 0; d < kGatherStages - 1; ++d) {
-        const unsigned jd = j + d * THREADS;
-        if (jd < e) {
-            __pipeline_memcpy_async(s_q + d * THREADS + threadIdx.x, cache4 + jd, sizeof(float4));
-            __pipeline_memcpy_async(s_c + d * THREADS + threadIdx.x, cache_code + jd, sizeof(uint2));
-        }
-        __pipeline_commit();
-    }
-    while (!cuda::ptx::mbarrier_try_wait_parity(&bar, 0)) {}
-    __syncthreads();                                       // zero-filled rows (generic stores) are visible too
-    for (; j < e; j += THREADS) {
-        const unsigned jn = j + (kGatherStages - 1) * THREADS;
-        int bn = buf + kGatherStages - 1;
-        if (bn >= kGatherStages) bn -= kGatherStages;
-        if (jn < e) {
-            __pipeline_memcpy_async(s_q + bn * THREADS + threadIdx.x, cache4 + jn, sizeof(float4));
-            __pipeline_memcpy_async(s_c + bn * THREADS + threadIdx.x, cache_code + jn, sizeof(uint2));
-        }
-        __pipeline_commit();
-        __pipeline_wait_prior(kGatherStages - 1);          // everything but the newest kGatherStages - 1 groups has landed
-        const float4 q = s_q[buf * THREADS + threadIdx.x];
-        const uint2 cn = s_c[buf * THREADS + threadIdx.x];
-        const unsigned code = cn.x, n = cn.y;
-        if (++buf == kGatherStages) buf = 0;
-        float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (code & kCacheOwned) {
-            float Sx, Sy, Sz;
-            if (code & kCacheInside) {
-                GatherWeights w;
-                gather_weights(make_float3(q.x, q.y, q.z), w);
-                const unsigned lx = code & 1023u, ly = (code >> 10) & 1023u, lz = (code >> 20) & 1023u;
-                gather_sums(ftile + ((lz - 1) * PY + (ly - 1)) * PX + (lx - 1), PX, PX * PY, w.wx, w.wy, w.wz, w.dx, w.dy, w.dz, Sx, Sy, Sz);
-            } else {
-                GatherDirectArgs da;
-                da.inv = inv; da.ghost = ghost; da.g = &g;
-                const float3 S = gather_direct(__ldg(postype + n), da);
-                Sx = S.x; Sy = S.y; Sz = S.z;
+        for (int d = 0; d < kGatherStages - 1; ++d) {
+            const unsigned jd = j + d * THREADS;
+            if (jd < e) {
+                __pipeline_memcpy_async(s_q + d * THREADS + threadIdx.x, in.cache4 + jd, sizeof(float4));
+                __pipeline_memcpy_async(s_c + d * THREADS + threadIdx.x, in.cache_code + jd, sizeof(uint2));
             }
-            f = force_from_sums(Sx, Sy, Sz, q.w, fp, scale);
+            __pipeline_commit();
         }
-        force[n] = f;
+        while (!cuda::ptx::mbarrier_try_wait_parity(&bar, 0)) {}
+        __syncthreads();                                       // zero-filled rows (generic stores) are visible too
+        for (; j < e; j += THREADS) {
+            const unsigned jn = j + (kGatherStages - 1) * THREADS;
+            int bn = buf + kGatherStages - 1;
+            if (bn >= kGatherStages) bn -= kGatherStages;
+            if (jn < e) {
+                __pipeline_memcpy_async(s_q + bn * THREADS + threadIdx.x, in.cache4 + jn, sizeof(float4));
+                __pipeline_memcpy_async(s_c + bn * THREADS + threadIdx.x, in.cache_code + jn, sizeof(uint2));
+            }
+            __pipeline_commit();
+            __pipeline_wait_prior(kGatherStages - 1);          // everything but the newest kGatherStages - 1 groups has landed
+            const float4 q = s_q[buf * THREADS + threadIdx.x];
+            const uint2 cn = s_c[buf * THREADS + threadIdx.x];
+            const unsigned code = cn.x, n = cn.y;
+            if (++buf == kGatherStages) buf = 0;
+            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (code & kCacheOwned) {
+                float Sx, Sy, Sz;
+                if (code & kCacheInside) {
+                    GatherWeights w;
+                    gather_weights(make_float3(q.x, q.y, q.z), w);
+                    const unsigned lx = code & 1023u, ly = (code >> 10) & 1023u, lz = (code >> 20) & 1023u;
+                    gather_sums(ftile + ((lz - 1) * PY + (ly - 1)) * PX + (lx - 1), PX, PX * PY, w.wx, w.wy, w.wz, w.dx, w.dy, w.dz, Sx, Sy, Sz);
+                } else {
+                    GatherDirectArgs da;
+                    da.inv = inv; da.ghost = ghost; da.g = &g;
+                    const float3 S = gather_direct(__ldg(in.postype + n), da);
+                    Sx = S.x; Sy = S.y; Sz = S.z;
+                }
+                f = force_from_sums(Sx, Sy, Sz, q.w, fp, scale);
+            }
+            force[n] = f;
+        }
+    } else {
+        // no cache: positions come through the tile order (index two stages ahead of its position, like the spread), cell
+        // and offsets are recomputed with the expressions of the spread
+        constexpr int D = kGatherStages - 1, PA = 2;
+        unsigned nq[D + PA];
+#pragma unroll
+        for (int d = 0; d < D + PA; ++d) {
+            const unsigned jd = j + d * THREADS;
+            nq[d] = jd < e ? __ldg(in.order + jd) : 0u;
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            if (j + d * THREADS < e) __pipeline_memcpy_async(s_q + d * THREADS + threadIdx.x, in.postype + nq[d], sizeof(float4));
+            __pipeline_commit();
+        }
+        while (!cuda::ptx::mbarrier_try_wait_parity(&bar, 0)) {}
+        __syncthreads();
+        for (; j < e; j += THREADS) {
+            const unsigned jn = j + D * THREADS;
+            int bn = buf + D;
+            if (bn >= kGatherStages) bn -= kGatherStages;
+            if (jn < e) __pipeline_memcpy_async(s_q + bn * THREADS + threadIdx.x, in.postype + nq[D], sizeof(float4));
+            __pipeline_commit();
+            const unsigned n_far = (jn + PA * THREADS < e) ? __ldg(in.order + jn + PA * THREADS) : 0u;
+            if ((threadIdx.x & 31) == 0 && jn + (PA + kSpreadL2Lead) * THREADS < e)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(in.order + jn + (PA + kSpreadL2Lead) * THREADS));
+            __pipeline_wait_prior(D);
+            const float4 p = s_q[buf * THREADS + threadIdx.x];
+            const unsigned n = nq[0];
+            if (++buf == kGatherStages) buf = 0;
+            Cell c = particle_cell(p, g);
+            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c.owned) {
+                unsigned lx, ly, lz;
+                float Sx, Sy, Sz;
+                float3 sh = particle_shift(p, c, g);
+                particle_rebase(c, sh, g);
+                if (padded_coords(c, ox, oy, oz, g, PX, PY, PZ, lx, ly, lz)) {
+                    GatherWeights w;
+                    gather_weights(sh, w);
+                    gather_sums(ftile + ((lz - 1) * PY + (ly - 1)) * PX + (lx - 1), PX, PX * PY, w.wx, w.wy, w.wz, w.dx, w.dy, w.dz, Sx, Sy, Sz);
+                } else {
+                    GatherDirectArgs da;
+                    da.inv = inv; da.ghost = ghost; da.g = &g;
+                    const float3 S = gather_direct(p, da);
+                    Sx = S.x; Sy = S.y; Sz = S.z;
+                }
+                f = force_from_sums(Sx, Sy, Sz, s_mode[__float_as_int(p.w)], fp, scale);
+            }
+            force[n] = f;
+#pragma unroll
+            for (int d = 0; d < D + PA - 1; ++d) nq[d] = nq[d + 1];
+            nq[D + PA - 1] = n_far;
+        }
     }
 }
 #endif  // __CUDACC__

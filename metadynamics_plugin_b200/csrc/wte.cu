@@ -6,6 +6,9 @@
 // Reference GPU drivers replaced: gpu_reduce_potential_energy / gpu_scale_netforce
 // (WellTemperedEnsemble.cu:19-243; atomicCAS double add, autotuned block size, managed scratch).
 #include "common.cuh"
+#include <map>
+#include <mutex>
+#include <utility>
 
 namespace metad {
 
@@ -97,14 +100,24 @@ struct WteScratch {
     unsigned* ticket = nullptr;
     int blocks = 0;
 };
-static WteScratch g_wte;   // per process (= per GPU)
+// One scratch (partials + ticket of the last-block finalisation) per device AND stream: two reduces in flight on different
+// streams, or one process driving several devices, must not share a ticket.  The handful of (device, stream) pairs a process
+// uses live until it exits.
+static std::mutex g_wte_mutex;
+static std::map<std::pair<int, cudaStream_t>, WteScratch> g_wte;
 
-static int wte_scratch() {
-    if (g_wte.partials) return METAD_OK;
-    g_wte.blocks = device_sm_count() * 8;
-    METAD_CUDA(cudaMalloc(&g_wte.partials, sizeof(double) * g_wte.blocks));
-    METAD_CUDA(cudaMalloc(&g_wte.ticket, sizeof(unsigned)));
-    METAD_CUDA(cudaMemset(g_wte.ticket, 0, sizeof(unsigned)));
+static int wte_scratch(cudaStream_t stream, WteScratch** out) {
+    int dev = 0;
+    METAD_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_wte_mutex);
+    WteScratch& w = g_wte[std::make_pair(dev, stream)];
+    if (!w.partials) {
+        w.blocks = device_sm_count() * 8;
+        METAD_CUDA(cudaMalloc(&w.partials, sizeof(double) * w.blocks));
+        METAD_CUDA(cudaMalloc(&w.ticket, sizeof(unsigned)));
+        METAD_CUDA(cudaMemset(w.ticket, 0, sizeof(unsigned)));
+    }
+    *out = &w;
     return METAD_OK;
 }
 
@@ -116,13 +129,14 @@ extern "C" int metad_wte_reduce(const float* d_net_force, unsigned N, double ext
                                 metad_stream_t stream) {
     METAD_REQUIRE(d_pe, "metad_wte_reduce: null output");
     METAD_REQUIRE(N == 0 || d_net_force, "metad_wte_reduce: null net force array");
-    int rc = wte_scratch();
+    WteScratch* w = nullptr;
+    int rc = wte_scratch(stream, &w);
     if (rc) return rc;
     long b = ((long)N + kWteThreads * 8L - 1) / (kWteThreads * 8L);
     if (b < 1) b = 1;
-    if (b > g_wte.blocks) b = g_wte.blocks;
-    wte_reduce_kernel<<<(int)b, kWteThreads, 0, stream>>>((const float4*)d_net_force, N, external_energy, g_wte.partials,
-                                                         g_wte.ticket, d_pe);
+    if (b > w->blocks) b = w->blocks;
+    wte_reduce_kernel<<<(int)b, kWteThreads, 0, stream>>>((const float4*)d_net_force, N, external_energy, w->partials,
+                                                         w->ticket, d_pe);
     METAD_LAUNCH_CHECK();
     return METAD_OK;
 }

@@ -10,12 +10,9 @@ arguments, defaults and error behaviour, bound to the B200-native `_metadynamics
     reweight)                                                                     reference cv.py:11-171
 cv.wrap and cv.steinhardt need arbitrary HOOMD force fields / neighbour lists and are out of scope.
 """
-try:                                     # a real HOOMD-blue 2.x takes precedence
-    import hoomd                         # noqa: F401
-    from hoomd import _hoomd             # noqa: F401
-    raise ImportError("binding to a real hoomd is described in INTEGRATION.md; this build uses the shim")
-except ImportError:
-    from . import hoomd_shim as hoomd
+# This build always binds to the stand-in for the handful of HOOMD-blue 2.x objects the scripts touch (hoomd_shim.py);
+# binding the classes to a real HOOMD installation is a build-time step described in INTEGRATION.md.
+from . import hoomd_shim as hoomd
 from . import _metadynamics
 
 _force_base = hoomd._force

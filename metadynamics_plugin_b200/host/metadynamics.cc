@@ -37,6 +37,13 @@ Scalar CollectiveVariable::getBiasFactor() {
     return (Scalar)b;
 }
 
+Scalar CollectiveVariable::biasHost() {
+    double b = 0;
+    cuda_check(cudaStreamSynchronize(stream_of(m_exec_conf)), "sync");
+    cuda_check(cudaMemcpy(&b, biasDevice(), sizeof(double), cudaMemcpyDeviceToHost), "bias download");
+    return (Scalar)b;
+}
+
 // CollectiveVariable.cc:22-66: umbrella increment (evaluated on the device), computeBiasForces, bias reset
 void CollectiveVariable::computeForces(unsigned int timestep) {
     m_bias_with_umbrella = false;
@@ -221,7 +228,7 @@ void WellTemperedEnsemble::computeBiasForces(unsigned int) {
     metad_check(metad_wte_scale((float*)m_pdata->getNetForce().data(), (float*)m_pdata->getNetTorqueArray().data(),
                                 m_pdata->getNetVirial().data(), m_pdata->getNetVirialPitch(), m_pdata->getN(), biasDevice(),
                                 stream_of(m_exec_conf)), "metad_wte_scale");
-    const Scalar fac = Scalar(1.0) + getBiasFactor();
+    const Scalar fac = Scalar(1.0) + biasHost();        // the same factor as the device side: bias incl. the umbrella increment
     for (unsigned int i = 0; i < 6; ++i) m_pdata->setExternalVirial(i, fac * m_pdata->getExternalVirial(i));
 }
 std::vector<std::string> WellTemperedEnsemble::getProvidedLogQuantities() {
@@ -255,7 +262,7 @@ Scalar AspectRatio::getCurrentValue(unsigned int) {
 void AspectRatio::computeBiasForces(unsigned int) {
     const BoxDim& box = m_pdata->getGlobalBox();
     const Scalar3 L = box.getL();
-    const Scalar bias = getBiasFactor();
+    const Scalar bias = biasHost();
     Scalar dx(0.0), dy(0.0), dz(0.0);
     if (m_dir1 == 0 && m_dir2 == 1) { dx = Scalar(1.0) / L.y; dy = -L.x / L.y / L.y; }
     else if (m_dir1 == 0 && m_dir2 == 2) { dx = Scalar(1.0) / L.z; dz = -L.x / L.z / L.z; }
@@ -281,7 +288,7 @@ void Density::computeBiasForces(unsigned int) {
     const Scalar V = (Scalar)box.getVolume();
     const Scalar3 L = box.getL();
     const Scalar fac = -(Scalar)m_pdata->getNGlobal() / (V * V);
-    const Scalar v = -getBiasFactor() * fac * L.x * L.y * L.z;
+    const Scalar v = -biasHost() * fac * L.x * L.y * L.z;
     m_external_virial[0] = v; m_external_virial[1] = 0; m_external_virial[2] = 0;
     m_external_virial[3] = v; m_external_virial[4] = 0; m_external_virial[5] = v;
 }

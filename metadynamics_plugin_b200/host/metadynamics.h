@@ -54,6 +54,9 @@ class CollectiveVariable : public ForceCompute {
     void computeForces(unsigned int timestep) override;
     virtual void computeBiasForces(unsigned int timestep) {}
     const double* biasDevice() const { return m_d_scalars.data() + (m_bias_with_umbrella ? 1 : 0); }
+    // host copy of the factor that computeBiasForces must apply: the integrator's dV/ds PLUS the umbrella increment of
+    // computeForces (the reference's m_bias at the time it calls computeBiasForces, CollectiveVariable.cc:22-66)
+    Scalar biasHost();
 
     std::string m_cv_name;
     DeviceArray<double> m_d_scalars;   // [0] bias factor from the integrator/host, [1] bias incl. umbrella, [2] CV value

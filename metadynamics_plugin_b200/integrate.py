@@ -1,11 +1,8 @@
 """Metadynamics integration mode -- the reference's `metadynamics.integrate` Python API (integrate.py:204-357),
 same signatures and defaults, bound to the B200-native `_metadynamics.IntegratorMetaDynamics`."""
-try:
-    import hoomd                         # noqa: F401
-    from hoomd import _hoomd             # noqa: F401
-    raise ImportError("binding to a real hoomd is described in INTEGRATION.md; this build uses the shim")
-except ImportError:
-    from . import hoomd_shim as hoomd
+# This build always binds to the stand-in for the handful of HOOMD-blue 2.x objects the scripts touch (hoomd_shim.py);
+# binding the classes to a real HOOMD installation is a build-time step described in INTEGRATION.md.
+from . import hoomd_shim as hoomd
 from . import _metadynamics
 from . import cv
 

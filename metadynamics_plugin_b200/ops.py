@@ -154,6 +154,14 @@ class Mesh:
                     fx_scale=float(out[4]), calls_since_rebuild=int(out[5]))
 
 
+    def accumulator(self):
+        """Width of the density accumulators: {"wide": 64-bit accumulation in use, "requested": what the cell loads of the
+        last rebuild of the tile order ask for (1 = 32 bits suffice, 2 = 64 bits, 3 = beyond the range)}."""
+        out = np.zeros(2, dtype=np.uint32)
+        check(lib.metad_mesh_get(self.h, 9, out.ctypes.data_as(C.c_void_p)))
+        return dict(wide=bool(out[0]), requested=int(out[1]))
+
+
 class BiasGrid:
     """IntegratorMetaDynamics grid bias on the device (reference: IntegratorMetaDynamics.cc:363-451)."""
     ARR = dict(grid=(0, np.float64), reweighted=(1, np.float64), weight=(2, np.float64), sigma_grid=(3, np.float64),

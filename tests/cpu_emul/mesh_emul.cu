@@ -137,16 +137,17 @@ int main(int argc, char** argv) {
             const float4 p = postype[n];
             int t; memcpy(&t, &p.w, 4);
             const float a = mode[t];
-            const Cell c = particle_cell(p, g);
+            Cell c = particle_cell(p, g);
             cell_keys[n] = key_of(c.ix, c.iy, c.iz, g);
             sq += (double)a * (double)a; s1 += (double)a;
             float w[9];
-            const float3 sh = particle_shift(p, c, g);
-            spread_weights(sh, a * scale, w);
+            float3 sh = particle_shift(p, c, g);
             const float xyz[3] = {p.x, p.y, p.z};
             const int cxyz[3] = {c.ix, c.iy, c.iz}, rxyz[3] = {c.rx, c.ry, c.rz};
             for (int d = 0; d < 3; ++d)
                 shift_err = std::max(shift_err, (double)std::fabs(cell_shift(xyz[d], rxyz[d], d, g) - cell_shift_f64(xyz[d], cxyz[d], d, g)));
+            particle_rebase(c, sh, g);       // stencil base = the cell the accurate offset points to (see mesh_kernels.cuh)
+            spread_weights(sh, a * scale, w);
             unsigned lx, ly, lz;
             const bool inside = padded_coords(c, ox, oy, oz, g, PX, PY, PZ, lx, ly, lz);
             cache4[j] = make_float4(sh.x, sh.y, sh.z, a);
@@ -218,7 +219,9 @@ int main(int argc, char** argv) {
             const float4 p = postype[n];
             const unsigned code = cache_code_v[j];
             const float4 q = cache4[j];
-            const Cell c = particle_cell(p, g);
+            Cell c = particle_cell(p, g);
+            float3 sh_g = particle_shift(p, c, g);
+            particle_rebase(c, sh_g, g);
             GatherWeights w;
             gather_weights(make_float3(q.x, q.y, q.z), w);
             float Sx, Sy, Sz;

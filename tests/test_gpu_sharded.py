@@ -84,6 +84,7 @@ def test_mesh_slab_matches_single_plan_and_oracle(gpu, oracle, N, dims, L, P, mo
     (20000, (64, 32, 32), (20.0, 11.0, 13.0), 2, (1.0,)),
     (60000, (128, 32, 64), (40.0, 10.0, 20.0), 4, (1.0, -1.0)),
     (200000, (256, 64, 64), (64.0, 16.0, 16.0), 8, (1.0,)),
+    (1 << 21, (256, 256, 256), (128.0, 128.0, 128.0), 8, (1.0,)),       # the C4 mesh on 8 ranks: fft_y<256>, fft_z<256>, 16^3 tiles
 ])
 def test_mesh_slab_peer_memory_path(gpu, oracle, N, dims, L, P, modes):
     """The peer-memory (P2P) slab path, all ranks emulated in one process: transposes fused into the FFT sweeps, pushed
