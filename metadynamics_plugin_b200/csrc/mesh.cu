@@ -58,7 +58,6 @@ struct metad_mesh {
     // (layer order, see mesh_layer_order_kernel); d_perm: cell-sorted permutation (intermediate)
     unsigned *d_keys = nullptr, *d_ranks = nullptr, *d_perm = nullptr;
     float4* d_cache4 = nullptr;     // particle cache spread -> gather (tile order): offsets + amplitude
-    uint2* d_cache_code = nullptr;     // {code word, particle index}
     unsigned *d_count = nullptr, *d_start = nullptr, *d_block_sums = nullptr, *d_tstart = nullptr, *d_max_count = nullptr;
     bool order_valid = false;
     unsigned order_N = 0, calls_since_rebuild = 0, period = 32;
@@ -278,7 +277,7 @@ template <int L> int run_z(metad_mesh* p, float2* buf, unsigned row_len, unsigne
     const unsigned nblocks = cp.n_blocks_plane0 + (row_len / kLines) * ny;
     // experiment (METAD_Z_CTAS=4): four CTAs per SM (32 registers) instead of three (40 registers) for 512-thread CTAs
     static const bool four = getenv("METAD_Z_CTAS") && atoi(getenv("METAD_Z_CTAS")) == 4;
-    if (four && kLines * L / kE == 512) {
+    if (four && kLines * L / kE == 256) {
         int rc4 = set_smem(fft_z_fused_kernel<L, 4>, smem); if (rc4) return rc4;
         METAD_CUDA(launch_pdl(p->pdl, fft_z_fused_kernel<L, 4>, nblocks, kLines * L / kE, smem, st, buf, p->d_twz, cp));
         METAD_LAUNCH_CHECK();
@@ -336,8 +335,8 @@ int fft_pipeline(metad_mesh* p, unsigned N_global, double* d_cv, cudaStream_t st
 
 int ensure_capacity(metad_mesh* p, unsigned N) {
     if (N <= p->cap) return METAD_OK;
-    cudaFree(p->d_keys); cudaFree(p->d_ranks); cudaFree(p->d_perm); cudaFree(p->d_cache4); cudaFree(p->d_cache_code);
-    p->d_keys = p->d_ranks = p->d_perm = nullptr; p->d_cache_code = nullptr; p->d_cache4 = nullptr; p->cap = 0;
+    cudaFree(p->d_keys); cudaFree(p->d_ranks); cudaFree(p->d_perm); cudaFree(p->d_cache4);
+    p->d_keys = p->d_ranks = p->d_perm = nullptr; p->d_cache4 = nullptr; p->cap = 0;
     p->order_valid = false;
     const unsigned cap = N + N / 16 + 1024;
     METAD_CUDA(cudaMalloc(&p->d_keys, sizeof(unsigned) * cap));
@@ -345,7 +344,6 @@ int ensure_capacity(metad_mesh* p, unsigned N) {
     METAD_CUDA(cudaMalloc(&p->d_perm, sizeof(unsigned) * cap));
     if (p->cache) {
         METAD_CUDA(cudaMalloc(&p->d_cache4, sizeof(float4) * cap));
-        METAD_CUDA(cudaMalloc(&p->d_cache_code, sizeof(uint2) * cap));
     }
     p->cap = cap;
     return METAD_OK;
@@ -438,7 +436,7 @@ template <int LGT> size_t spread_smem_bytes(int ntypes, int flags) {
 }
 // staging buffers of the gather: cache entries (float4 + uint2 per thread and stage), or positions + the mode table
 size_t gather_stage_bytes(int threads, bool cache, int ntypes) {
-    return cache ? (size_t)kGatherStages * threads * (sizeof(float4) + sizeof(uint2)) : (size_t)kGatherStages * threads * sizeof(float4) + sizeof(float) * ntypes;
+    return (size_t)kGatherStages * threads * (sizeof(float4) + (cache ? sizeof(unsigned) : 0)) + sizeof(float) * ntypes;
 }
 
 template <int LGT, int FLAGS>
@@ -528,7 +526,6 @@ int enqueue_spread(metad_mesh* p, const float* d_postype, unsigned N, cudaStream
     out.h_counters = p->h_counters;
     out.keys = p->keep_cells ? p->d_keys : nullptr;
     out.cache4 = p->d_cache4;
-    out.cache_code = p->d_cache_code;
     out.debug = p->spread_debug;
     int flags = (p->keep_cells ? kSpKeys : 0) | (p->cache ? kSpCache : 0);
     if (p->wide) flags |= kSpWide;
@@ -616,7 +613,6 @@ int launch_gather(metad_mesh* p, const float* d_postype, const float* d_ghost, f
     gin.postype = (const float4*)d_postype;
     gin.order = p->d_ranks;
     gin.cache4 = p->d_cache4;
-    gin.cache_code = p->d_cache_code;
     gin.mode = p->d_mode;
     gin.ntypes = p->ntypes;
     if (p->tma_gather && !g.slab) {
@@ -777,7 +773,7 @@ extern "C" int metad_mesh_slab_create(metad_mesh** out, unsigned nx, unsigned ny
 
 extern "C" int metad_mesh_destroy(metad_mesh* p) {
     if (!p) return METAD_OK;
-    cudaFree(p->d_mode); cudaFree(p->d_keys); cudaFree(p->d_ranks); cudaFree(p->d_perm); cudaFree(p->d_cache4); cudaFree(p->d_cache_code);
+    cudaFree(p->d_mode); cudaFree(p->d_keys); cudaFree(p->d_ranks); cudaFree(p->d_perm); cudaFree(p->d_cache4);
     cudaFree(p->d_count); cudaFree(p->d_start); cudaFree(p->d_block_sums); cudaFree(p->d_tstart); cudaFree(p->d_max_count);
     cudaFree(p->d_mesh_alloc); cudaFree(p->d_buf); cudaFree(p->d_fx); cudaFree(p->d_tile_sums); cudaFree(p->d_counters);
     if (p->h_counters) cudaFreeHost(p->h_counters);

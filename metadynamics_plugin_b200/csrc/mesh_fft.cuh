@@ -7,8 +7,9 @@
 // Semantics are those of the reference's transforms (kiss_fftnd on the CPU path, OrderParameterMesh.cc:319-325,
 // 655,719): unnormalised, forward e^{-i}, inverse e^{+i}, index x + nx*(y + ny*z).
 //
-// Engine: a line of L complex points (L = 8..512, power of two) is transformed by T = L/8 threads, 8 points per
-// thread in registers, as a Stockham autosort sequence of radix-8/4/2 stages; between stages the points are
+// Engine: a line of L complex points (L = 16..512, power of two) is transformed by T = L/16 threads, 16 points per
+// thread in registers, as a Stockham autosort sequence of radix-16/8/4/2 stages (256 points: two radix-16 stages, ONE
+// exchange; round 1 used 8 points per thread and three stages -- the sweeps were bound by shared-memory traffic); between stages the points are
 // exchanged through a shared-memory tile.  16 lines are processed side by side so that every global and shared
 // access of a half-warp is one contiguous 128-byte segment (16 x float2).
 //
@@ -24,7 +25,7 @@
 namespace metad {
 namespace fft {
 
-constexpr int kE = 8;        // points per thread
+constexpr int kE = 16;       // points per thread (16: a 256-point line is two radix-16 stages, ONE exchange through shared memory)
 constexpr int kLines = 16;   // lines per tile
 
 MHD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
@@ -63,15 +64,41 @@ template <int SIGN> MHD void dft8(float2 (&v)[8]) {
     v[1] = o0; v[3] = o1; v[5] = o2; v[7] = o3;
 }
 
+template <int SIGN> MHD void dft16(float2 (&v)[16]) {
+    // n = n1 + 4 n2, k = 4 k1 + k2:  X[4 k1 + k2] = sum_n1 w4^(n1 k1) [ w16^(n1 k2) sum_n2 w4^(n2 k2) v[n1 + 4 n2] ]
+    const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f, h = 0.70710678118654752440f;
+#pragma unroll
+    for (int n1 = 0; n1 < 4; ++n1) dft4<SIGN>(v[n1], v[n1 + 4], v[n1 + 8], v[n1 + 12]);       // -> y[n1][k2] in v[n1 + 4 k2]
+    // twiddles w16^(n1 k2), forward: cos - i sin; inverse: cos + i sin
+    auto rot = [](float2 a, float c, float sn) { return SIGN < 0 ? make_float2(a.x * c + a.y * sn, a.y * c - a.x * sn) : make_float2(a.x * c - a.y * sn, a.y * c + a.x * sn); };
+    v[1 + 4 * 1] = rot(v[1 + 4 * 1], c1, s1);          // m = 1
+    v[1 + 4 * 2] = rot(v[1 + 4 * 2], h, h);            // m = 2
+    v[1 + 4 * 3] = rot(v[1 + 4 * 3], s1, c1);          // m = 3
+    v[2 + 4 * 1] = rot(v[2 + 4 * 1], h, h);            // m = 2
+    v[2 + 4 * 2] = mul_i<SIGN>(v[2 + 4 * 2]);          // m = 4
+    v[2 + 4 * 3] = rot(v[2 + 4 * 3], -h, h);           // m = 6
+    v[3 + 4 * 1] = rot(v[3 + 4 * 1], s1, c1);          // m = 3
+    v[3 + 4 * 2] = rot(v[3 + 4 * 2], -h, h);           // m = 6
+    v[3 + 4 * 3] = rot(v[3 + 4 * 3], -c1, -s1);        // m = 9
+    float2 o[16];
+#pragma unroll
+    for (int k2 = 0; k2 < 4; ++k2) {
+        float2 a0 = v[0 + 4 * k2], a1 = v[1 + 4 * k2], a2 = v[2 + 4 * k2], a3 = v[3 + 4 * k2];
+        dft4<SIGN>(a0, a1, a2, a3);                    // over n1 -> k1
+        o[k2] = a0; o[4 + k2] = a1; o[8 + k2] = a2; o[12 + k2] = a3;
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = o[k];
+}
+
 // radix sequence per line length
 template <int L> struct Plan;
-template <> struct Plan<8>   { static constexpr int n = 1; static constexpr int r0 = 8, r1 = 1, r2 = 1; };
-template <> struct Plan<16>  { static constexpr int n = 2; static constexpr int r0 = 8, r1 = 2, r2 = 1; };
-template <> struct Plan<32>  { static constexpr int n = 2; static constexpr int r0 = 8, r1 = 4, r2 = 1; };
-template <> struct Plan<64>  { static constexpr int n = 2; static constexpr int r0 = 8, r1 = 8, r2 = 1; };
-template <> struct Plan<128> { static constexpr int n = 3; static constexpr int r0 = 8, r1 = 8, r2 = 2; };
-template <> struct Plan<256> { static constexpr int n = 3; static constexpr int r0 = 8, r1 = 8, r2 = 4; };
-template <> struct Plan<512> { static constexpr int n = 3; static constexpr int r0 = 8, r1 = 8, r2 = 8; };
+template <> struct Plan<16>  { static constexpr int n = 1; static constexpr int r0 = 16, r1 = 1, r2 = 1; };
+template <> struct Plan<32>  { static constexpr int n = 2; static constexpr int r0 = 16, r1 = 2, r2 = 1; };
+template <> struct Plan<64>  { static constexpr int n = 2; static constexpr int r0 = 16, r1 = 4, r2 = 1; };
+template <> struct Plan<128> { static constexpr int n = 2; static constexpr int r0 = 16, r1 = 8, r2 = 1; };
+template <> struct Plan<256> { static constexpr int n = 2; static constexpr int r0 = 16, r1 = 16, r2 = 1; };
+template <> struct Plan<512> { static constexpr int n = 3; static constexpr int r0 = 16, r1 = 16, r2 = 2; };
 
 // shared-memory tile layouts: element (line w, index l)
 struct LayoutCol {   // y/z passes: tile[l][w], w fastest (16 float2 = 128 B per l)
@@ -110,7 +137,14 @@ template <int L, int R, int NS, int SIGN, int TWL> MHD void stage_compute(float2
 #pragma unroll
             for (int r = 1; r < R; ++r) v[r] = twiddle<SIGN>(v[r], tw[k * r * (TWL / (NS * R))]);
         }
-        if (R == 8) {
+        if (R == 16) {
+            float2 u[16];
+#pragma unroll
+            for (int r = 0; r < 16; ++r) u[r] = v[r % R];
+            dft16<SIGN>(u);
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[r] = u[r];
+        } else if (R == 8) {
             float2 u[8];
 #pragma unroll
             for (int r = 0; r < 8; ++r) u[r] = v[r % R];

@@ -546,7 +546,7 @@ __device__ __forceinline__ void z_plane0_body(float2* __restrict__ buf, const fl
 }
 
 // one launch: blocks [0, n_blocks_plane0) untangle the kx = 0 slot, the rest are (kx tile, ky) blocks of the general case
-template <int L, int MINB = ((kLines * L / kE) <= 512 ? 3 : 1)>
+template <int L, int MINB = ((kLines * L / kE) <= 256 ? 3 : 1)>
 __global__ void __launch_bounds__(kLines * L / kE, MINB)
 fft_z_fused_kernel(float2* __restrict__ buf, const float2* __restrict__ g_tw, ConvParams cp) {
     extern __shared__ float2 smem[];

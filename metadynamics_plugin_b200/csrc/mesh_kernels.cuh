@@ -353,6 +353,58 @@ MHD void particle_rebase(Cell& c, float3& s, const Geom& g) {
     rebase_axis(iz, sz, g.nzg);
     if (!g.slab || (unsigned)(iz - (int)g.z0) < g.nz) { c.iz = iz; s.z = sz; }
 }
+// Hot form of "cell + offset + re-base" in one go (what the spread and the gather run per particle): the cell that holds
+// the particle in (nearly) exact arithmetic and the offset from its centre, |s| <= 1/2.  With x - lo = d + e exactly
+// (Fast2Sum, as in cell_shift) and n/L = c_hi + c_lo, the cell coordinate is r = rh + rl + e c_hi + d c_lo where
+// rh = fl(d c_hi) and rl = fma(d, c_hi, -rh) is its rounding error, exactly.  trunc(rh) comes from RZ(rh + 2^23) (no
+// conversion-pipe instruction), rh - trunc(rh) and the subtraction of 1/2 are exact (or rounded once below 1/4), the small
+// terms are added last: |s - exact| < 1e-7.  Because rh is itself rounded, trunc(rh) can be one cell off at a face; the
+// offset then leaves [-1/2, 1/2] and the final rint() step moves cell and offset back together (the re-base above).
+// Agrees with particle_cell + particle_shift + particle_rebase (tests/cpu_emul/mesh_emul.cu compares the two on every
+// particle); 20 instead of 34 instructions per axis.
+MHD void axis_stencil(float x, int axis, const Geom& g, unsigned n, int& i, float& s) {
+    const float hl = g.hl_hi[axis], ch = g.c_hi[axis];
+    const float d = f_add(hl, x);
+    const float e = f_add(f_sub(x, f_sub(d, hl)), g.hl_lo[axis]);
+    const float rh = f_mul(d, ch);
+    const float rl = f_fma(d, ch, -rh);
+    const float small = f_add(rl, f_fma(e, ch, f_mul(d, g.c_lo[axis])));
+#ifdef __CUDA_ARCH__
+    const float u = __fadd_rz(fmaxf(rh, 0.f), 8388608.f);                 // 2^23 + trunc(rh)
+    const float t = __fsub_rn(u, 8388608.f);
+    const float sv = __fadd_rn(__fadd_rn(__fsub_rn(rh, t), -0.5f), small);
+    const float ur = __fadd_rn(sv, kFxMagic);                             // 1.5 2^23 + rint(sv)
+    i = (int)((unsigned)(__float_as_int(u) + __float_as_int(ur) - (0x4B000000 + kFxMagicBits)) & (n - 1));
+    s = __fsub_rn(sv, __fsub_rn(ur, kFxMagic));
+#else
+    const float rc = rh > 0.f ? rh : 0.f;
+    const int i0 = rc < 4194303.f ? (int)rc : 4194303;
+    const float t = (float)i0;
+    const float sv = f_add(f_add(f_sub(rh, t), -0.5f), small);
+    const float ur = f_add(sv, kFxMagic);
+    i = (int)((unsigned)(i0 + (f2i_bits(ur) - kFxMagicBits)) & (n - 1));
+    s = f_sub(sv, f_sub(ur, kFxMagic));
+#endif
+}
+// stencil base (global cell, z = global plane) and offsets of a particle; `owned` = the float-rule plane of the particle
+// belongs to this rank's slab (always true for an unsharded plan).  A slab keeps the base inside its planes (see
+// particle_rebase): the particle's taps must not reach beyond the one ghost layer.
+MHD void particle_stencil(float4 p, const Geom& g, Cell& c, float3& s) {
+    axis_stencil(p.x, 0, g, g.nx, c.ix, s.x);
+    axis_stencil(p.y, 1, g, g.ny, c.iy, s.y);
+    axis_stencil(p.z, 2, g, g.nzg, c.iz, s.z);
+    c.owned = true;
+    if (g.slab) {
+        const int izf = cell_coord(p.z, 2, g);
+        c.owned = (unsigned)(izf - (int)g.z0) < g.nz;
+        if (c.owned && (unsigned)(c.iz - (int)g.z0) >= g.nz) {
+            // the float rule (which assigns particles to ranks) and the accurate cell disagree across the slab face
+            const float dlt = (((unsigned)(izf - c.iz)) & (g.nzg - 1)) == 1u ? 1.0f : -1.0f;
+            c.iz = izf;
+            s.z -= dlt;
+        }
+    }
+}
 // separable weights: w[0..2] = Wx(tap -1,0,+1), w[3..5] = Wy, w[6..8] = amp * Wz
 MHD void spread_weights(float3 s, float amp, float (&w)[9]) {
     float wx[3], wy[3], wz[3];
@@ -362,12 +414,13 @@ MHD void spread_weights(float3 s, float amp, float (&w)[9]) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) { w[i] = wx[i]; w[3 + i] = wy[i]; w[6 + i] = amp * wz[i]; }
 }
-// Particle cache written by the spread for the gather of the same call pair (tile order): {sx, sy, sz, a(type)} and a
-// code word: padded-tile coordinates of the cell (10 bits each) | kCacheInside (all taps inside the padded tile) |
-// kCacheOwned (the plane belongs to this rank).  The gather then needs neither the positions nor the cell arithmetic.
+// Particle cache written by the spread for the gather of the same call pair (tile order), 16 bytes per particle:
+// {sx, sy, sz, code} with the code word = padded-tile coordinates of the stencil base (5 bits each) | particle type << 15
+// (10 bits) | kCacheInside (all taps inside the padded tile) | kCacheOwned (the plane belongs to this rank).  The gather then
+// needs neither the positions nor the cell arithmetic; the particle index comes from the tile order (4 bytes, sequential).
 constexpr unsigned kCacheInside = 1u << 30, kCacheOwned = 1u << 31;
-MHD unsigned cache_code(unsigned lx, unsigned ly, unsigned lz, bool inside, bool owned) {
-    return inside ? (lx | (ly << 10) | (lz << 20) | kCacheInside | kCacheOwned) : (owned ? kCacheOwned : 0u);
+MHD unsigned cache_code(unsigned lx, unsigned ly, unsigned lz, unsigned type, bool inside, bool owned) {
+    return inside ? (lx | (ly << 5) | (lz << 10) | (type << 15) | kCacheInside | kCacheOwned) : ((type << 15) | (owned ? kCacheOwned : 0u));
 }
 // fixed-point value of tap (i,j,k) in {0,1,2}^3: the SAME expression on every path (tile, stray, emulation)
 MHD int tap_value(const float (&w)[9], int i, int j, int k) { return fx_round(w[i], f_mul(w[3 + j], w[6 + k])); }
@@ -784,8 +837,7 @@ struct SpreadOut {
     unsigned* counters;      // see above
     unsigned* h_counters;    // pinned host words [1..3] (device-visible address), or nullptr
     unsigned* keys;          // kSpKeys: tile-major cell key per particle
-    float4* cache4;          // kSpCache: particle cache for the gather, tile order: {sx, sy, sz, a}
-    uint2* cache_code;       //   ... and {code word (cache_code()), particle index}
+    float4* cache4;          // kSpCache: particle cache for the gather, tile order: {sx, sy, sz, code word (cache_code())}
     // kSpTma: tensor map of the integer mesh (dims nx, ny, planes incl. ghosts; box = padded tile).  It travels inside this
     // __grid_constant__ kernel parameter: the TMA unit fetches descriptors through its own cache, parameter space is the
     // one place that needs no tensormap proxy fence
@@ -861,16 +913,16 @@ mesh_spread_kernel(const float4* __restrict__ postype, const unsigned* __restric
             const unsigned n = nq[0];
             if (++buf == kSpreadStages) buf = 0;
             const float a = s_mode[__float_as_int(p.w)];
-            Cell c = particle_cell(p, g);
-            if (KEYS) out.keys[n] = key_of(c.ix, c.iy, (unsigned)(c.iz - (int)g.z0) & (g.nz - 1), g);
-            float3 sh = particle_shift(p, c, g);
-            particle_rebase(c, sh, g);
+            if (KEYS) {          // the reported cell: the reference's single-precision rule, bit for bit
+                const Cell cf = particle_cell(p, g);
+                out.keys[n] = key_of(cf.ix, cf.iy, (unsigned)(cf.iz - (int)g.z0) & (g.nz - 1), g);
+            }
+            Cell c;
+            float3 sh;
+            particle_stencil(p, g, c, sh);
             unsigned lx = 0, ly = 0, lz = 0;
             const bool inside = c.owned && padded_coords(c, ox, oy, oz, g, PX, PY, PZ, lx, ly, lz);
-            if (CACHE) {
-                out.cache4[j] = make_float4(sh.x, sh.y, sh.z, a);
-                out.cache_code[j] = make_uint2(cache_code(lx, ly, lz, inside, c.owned), n);
-            }
+            if (CACHE) out.cache4[j] = make_float4(sh.x, sh.y, sh.z, __uint_as_float(cache_code(lx, ly, lz, (unsigned)__float_as_int(p.w), inside, c.owned)));
             if (c.owned) {
                 sq += (double)a * (double)a;
                 s1 += (double)a;
@@ -961,17 +1013,25 @@ mesh_spread_kernel(const float4* __restrict__ postype, const unsigned* __restric
             // .add.s32, executed by the TMA engine / L2), two if it wraps in x.  The outermost y / z layers are skipped
             // unless a particle of this tile has drifted that far.
             cuda::ptx::fence_proxy_async(cuda::ptx::space_shared);      // the tile was written through the generic proxy
+            const unsigned x0 = (unsigned)ox & (g.nx - 1);
+            const int room = (int)g.nx - (int)x0, first = room < PX ? room : PX;
+            const unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile);
             for (int row = threadIdx.x; row < PY * PZ; row += kSpreadThreads) {
                 const int py = row % PY, pz = row / PY;
                 const bool inner = (unsigned)(py - 1) < (unsigned)(PY - 2) && (unsigned)(pz - 1) < (unsigned)(PZ - 2);
-                TileRow r;
-                if ((inner || any_outer) && tile_row(ox, oy, oz, py, pz, PX, g, r)) {
-                    int* dst = out.mesh + (long long)r.z * (long long)plane + (size_t)r.y * g.nx;
-                    cuda::ptx::cp_reduce_async_bulk(cuda::ptx::space_global, cuda::ptx::space_shared, cuda::ptx::op_add, dst + r.x0,
-                                                    tile + row * PX, (unsigned)(r.first * sizeof(int)));
-                    if (r.first < PX)
-                        cuda::ptx::cp_reduce_async_bulk(cuda::ptx::space_global, cuda::ptx::space_shared, cuda::ptx::op_add, dst,
-                                                        tile + row * PX + r.first, (unsigned)((PX - r.first) * sizeof(int)));
+                int z = oz + pz;
+                bool ok = inner || any_outer;
+                if (g.slab) ok = ok && z >= -1 && z <= (int)g.nz;
+                else z = (int)((unsigned)z & (g.nz - 1));
+                if (ok) {
+                    const unsigned y = (unsigned)(oy + py) & (g.ny - 1);
+                    int* dst = out.mesh + (long long)z * (long long)plane + (size_t)y * g.nx;
+                    const unsigned src = tile_s + (unsigned)(row * PX * sizeof(int));
+                    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.s32 [%0], [%1], %2;"
+                                 ::"l"(dst + x0), "r"(src), "r"((unsigned)(first * sizeof(int))) : "memory");
+                    if (first < PX)
+                        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.s32 [%0], [%1], %2;"
+                                     ::"l"(dst), "r"(src + (unsigned)(first * sizeof(int))), "r"((unsigned)((PX - first) * sizeof(int))) : "memory");
                 }
             }
             cuda::ptx::cp_async_bulk_commit_group();
@@ -1021,9 +1081,9 @@ constexpr int kGatherStages = 4;       // staging buffers of the particle data (
 struct GatherDirectArgs { const float* inv; const float* ghost; const Geom* g; };
 __device__ __noinline__ float3 gather_direct(float4 p, GatherDirectArgs a) {
     const Geom g = *a.g;
-    Cell c = particle_cell(p, g);
-    float3 sh = particle_shift(p, c, g);
-    particle_rebase(c, sh, g);
+    Cell c;
+    float3 sh;
+    particle_stencil(p, g, c, sh);
     GatherWeights w;
     gather_weights(sh, w);
     const size_t plane = (size_t)g.nx * g.ny;
@@ -1043,14 +1103,13 @@ __device__ __noinline__ float3 gather_direct(float4 p, GatherDirectArgs a) {
     return S;
 }
 
-// what the gather reads per particle: CACHE -- the entries the spread wrote (24 B, tile order); otherwise the tile order
-// (4 B) and the position (16 B, through the order), from which cell, offsets and amplitude are recomputed: the spread then
-// writes nothing per particle (its DRAM traffic drops from 2.45x to ~1.2x of the algorithmic bytes at C4).
+// what the gather reads per particle: CACHE -- the entry the spread wrote (16 B, tile order) and the tile order (4 B), both
+// sequential; otherwise the tile order and the position (16 B, through the order), from which cell and offsets are
+// recomputed (the spread then writes nothing per particle, but the gather is slower: profiles/r02_notes.md).
 struct GatherIn {
     const float4* postype;
     const unsigned* order;          // tile order (no cache)
     const float4* cache4;           // particle cache
-    const uint2* cache_code;
     const float* mode;              // mode coefficients per type (no cache)
     int ntypes;
     int use_tmap;                   // tmap is valid
@@ -1067,8 +1126,8 @@ mesh_gather_kernel(const __grid_constant__ GatherIn in, const unsigned* __restri
     pdl_wait(); pdl_trigger();
     fft::peer_wait(sync);                                   // fused peer mode: the neighbours' halo planes of Re IFFT(G) have arrived
     float4* s_q = reinterpret_cast<float4*>(ftile + P3);    // [kGatherStages][THREADS]: cache entries / positions
-    uint2* s_c = reinterpret_cast<uint2*>(s_q + kGatherStages * THREADS);        // CACHE: code words; else the mode coefficients
-    float* s_mode = reinterpret_cast<float*>(s_c);
+    unsigned* s_c = reinterpret_cast<unsigned*>(s_q + kGatherStages * THREADS);  // CACHE: [kGatherStages][THREADS] particle indices
+    float* s_mode = reinterpret_cast<float*>(s_c + (CACHE ? kGatherStages * THREADS : 0));       // [ntypes] mode coefficients
     __shared__ uint64_t bar;
     const unsigned s = __ldg(tstart + blockIdx.x), e = __ldg(tstart + blockIdx.x + 1);
     if (e == s) return;                                   // empty tile: nothing to interpolate
@@ -1077,7 +1136,7 @@ mesh_gather_kernel(const __grid_constant__ GatherIn in, const unsigned* __restri
     const int ox = (int)(tx << LGT) - kHaloX, oy = (int)(ty << LGT) - kHalo, oz = (int)(tz << LGT) - kHalo;
     const size_t plane = (size_t)g.nx * g.ny;
     if (threadIdx.x == 0) cuda::ptx::mbarrier_init(&bar, THREADS);
-    if (!CACHE) for (int i = threadIdx.x; i < in.ntypes; i += THREADS) s_mode[i] = __ldg(in.mode + i);
+    for (int i = threadIdx.x; i < in.ntypes; i += THREADS) s_mode[i] = __ldg(in.mode + i);
     __syncthreads();
     // padded tile of Re IFFT(G).  A tile that does not wrap periodically comes with ONE 3-D tensor-map copy
     // (cp.async.bulk.tensor, UTMALDG); otherwise one bulk asynchronous copy per row (two if the row wraps in x).
@@ -1125,7 +1184,7 @@ mesh_gather_kernel(const __grid_constant__ GatherIn in, const unsigned* __restri
             const unsigned jd = j + d * THREADS;
             if (jd < e) {
                 __pipeline_memcpy_async(s_q + d * THREADS + threadIdx.x, in.cache4 + jd, sizeof(float4));
-                __pipeline_memcpy_async(s_c + d * THREADS + threadIdx.x, in.cache_code + jd, sizeof(uint2));
+                __pipeline_memcpy_async(s_c + d * THREADS + threadIdx.x, in.order + jd, sizeof(unsigned));
             }
             __pipeline_commit();
         }
@@ -1137,13 +1196,13 @@ mesh_gather_kernel(const __grid_constant__ GatherIn in, const unsigned* __restri
             if (bn >= kGatherStages) bn -= kGatherStages;
             if (jn < e) {
                 __pipeline_memcpy_async(s_q + bn * THREADS + threadIdx.x, in.cache4 + jn, sizeof(float4));
-                __pipeline_memcpy_async(s_c + bn * THREADS + threadIdx.x, in.cache_code + jn, sizeof(uint2));
+                __pipeline_memcpy_async(s_c + bn * THREADS + threadIdx.x, in.order + jn, sizeof(unsigned));
             }
             __pipeline_commit();
             __pipeline_wait_prior(kGatherStages - 1);          // everything but the newest kGatherStages - 1 groups has landed
             const float4 q = s_q[buf * THREADS + threadIdx.x];
-            const uint2 cn = s_c[buf * THREADS + threadIdx.x];
-            const unsigned code = cn.x, n = cn.y;
+            const unsigned n = s_c[buf * THREADS + threadIdx.x];
+            const unsigned code = __float_as_uint(q.w);
             if (++buf == kGatherStages) buf = 0;
             float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
             if (code & kCacheOwned) {
@@ -1151,7 +1210,7 @@ mesh_gather_kernel(const __grid_constant__ GatherIn in, const unsigned* __restri
                 if (code & kCacheInside) {
                     GatherWeights w;
                     gather_weights(make_float3(q.x, q.y, q.z), w);
-                    const unsigned lx = code & 1023u, ly = (code >> 10) & 1023u, lz = (code >> 20) & 1023u;
+                    const unsigned lx = code & 31u, ly = (code >> 5) & 31u, lz = (code >> 10) & 31u;
                     gather_sums(ftile + ((lz - 1) * PY + (ly - 1)) * PX + (lx - 1), PX, PX * PY, w.wx, w.wy, w.wz, w.dx, w.dy, w.dz, Sx, Sy, Sz);
                 } else {
                     GatherDirectArgs da;
@@ -1159,7 +1218,7 @@ mesh_gather_kernel(const __grid_constant__ GatherIn in, const unsigned* __restri
                     const float3 S = gather_direct(__ldg(in.postype + n), da);
                     Sx = S.x; Sy = S.y; Sz = S.z;
                 }
-                f = force_from_sums(Sx, Sy, Sz, q.w, fp, scale);
+                f = force_from_sums(Sx, Sy, Sz, s_mode[(code >> 15) & 1023u], fp, scale);
             }
             force[n] = f;
         }
@@ -1193,13 +1252,13 @@ mesh_gather_kernel(const __grid_constant__ GatherIn in, const unsigned* __restri
             const float4 p = s_q[buf * THREADS + threadIdx.x];
             const unsigned n = nq[0];
             if (++buf == kGatherStages) buf = 0;
-            Cell c = particle_cell(p, g);
+            Cell c;
+            float3 sh;
+            particle_stencil(p, g, c, sh);
             float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
             if (c.owned) {
                 unsigned lx, ly, lz;
                 float Sx, Sy, Sz;
-                float3 sh = particle_shift(p, c, g);
-                particle_rebase(c, sh, g);
                 if (padded_coords(c, ox, oy, oz, g, PX, PY, PZ, lx, ly, lz)) {
                     GatherWeights w;
                     gather_weights(sh, w);

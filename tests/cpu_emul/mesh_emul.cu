@@ -125,7 +125,7 @@ int main(int argc, char** argv) {
     std::vector<int> mesh_i(M, 0), tile(P3);
     std::vector<unsigned> cell_keys(N), cache_code_v(N);
     std::vector<float4> cache4(N);
-    double sums[2] = {0, 0}, shift_err = 0.0;
+    double sums[2] = {0, 0}, shift_err = 0.0, stencil_err = 0.0;
     unsigned strays = 0;
     for (unsigned tile_id = 0; tile_id < ntiles; ++tile_id) {
         unsigned tx, ty, tz; tile_coords(tile_id, g, tx, ty, tz);
@@ -147,11 +147,24 @@ int main(int argc, char** argv) {
             for (int d = 0; d < 3; ++d)
                 shift_err = std::max(shift_err, (double)std::fabs(cell_shift(xyz[d], rxyz[d], d, g) - cell_shift_f64(xyz[d], cxyz[d], d, g)));
             particle_rebase(c, sh, g);       // stencil base = the cell the accurate offset points to (see mesh_kernels.cuh)
+            {   // the hot form used by the kernels must pick the same base (or the neighbour across a face it sits on) and the same offset
+                Cell ch; float3 sh2;
+                particle_stencil(p, g, ch, sh2);
+                const int dc[3] = {ch.ix - c.ix, ch.iy - c.iy, ch.iz - c.iz};
+                const float ds[3] = {sh2.x - sh.x, sh2.y - sh.y, sh2.z - sh.z};
+                const int nn[3] = {(int)g.nx, (int)g.ny, (int)g.nz};
+                for (int d = 0; d < 3; ++d) {
+                    const int dd = ((dc[d] % nn[d]) + nn[d]) % nn[d];           // 0, 1 or n-1
+                    const double err = dd == 0 ? std::fabs(ds[d]) : (dd == 1 ? std::fabs(ds[d] + 1.0f) : (dd == nn[d] - 1 ? std::fabs(ds[d] - 1.0f) : 1e9));
+                    stencil_err = std::max(stencil_err, err);
+                }
+                c = ch; sh = sh2;
+            }
             spread_weights(sh, a * scale, w);
             unsigned lx, ly, lz;
             const bool inside = padded_coords(c, ox, oy, oz, g, PX, PY, PZ, lx, ly, lz);
             cache4[j] = make_float4(sh.x, sh.y, sh.z, a);
-            cache_code_v[j] = cache_code(lx, ly, lz, inside, true);
+            cache_code_v[j] = cache_code(lx, ly, lz, (unsigned)t, inside, true);
             if (inside) {
                 int* base = tile.data() + ((lz - 1) * PY + (ly - 1)) * PX + (lx - 1);
                 for (int k = 0; k < 3; ++k) for (int jj = 0; jj < 3; ++jj) {
@@ -219,14 +232,14 @@ int main(int argc, char** argv) {
             const float4 p = postype[n];
             const unsigned code = cache_code_v[j];
             const float4 q = cache4[j];
-            Cell c = particle_cell(p, g);
-            float3 sh_g = particle_shift(p, c, g);
-            particle_rebase(c, sh_g, g);
+            Cell c;
+            float3 sh_g;
+            particle_stencil(p, g, c, sh_g);
             GatherWeights w;
             gather_weights(make_float3(q.x, q.y, q.z), w);
             float Sx, Sy, Sz;
             if (code & kCacheInside) {
-                const unsigned lx = code & 1023u, ly = (code >> 10) & 1023u, lz = (code >> 20) & 1023u;
+                const unsigned lx = code & 31u, ly = (code >> 5) & 31u, lz = (code >> 10) & 31u;
                 gather_sums(ftile.data() + ((lz - 1) * PY + (ly - 1)) * PX + (lx - 1), PX, PX * PY, w.wx, w.wy, w.wz, w.dx, w.dy, w.dz, Sx, Sy, Sz);
             } else {        // gather_direct
                 float t27[27];
@@ -242,6 +255,8 @@ int main(int argc, char** argv) {
     // ---- dump: cv, mode_sq, shift_err, strays, scale, cell rule mismatches, rho[M], inv[M], force[4N], cells[3N]
     f = fopen(fout, "wb");
     const double dstrays = strays, dscale = scale, dmis = (double)cell_mismatch;
+    fprintf(stderr, "shift_err %.3e stencil_err %.3e\n", shift_err, stencil_err);
+    shift_err = std::max(shift_err, stencil_err);      // both against the 1e-7 bound of the test
     fwrite(&cv, 8, 1, f); fwrite(&sums[0], 8, 1, f); fwrite(&shift_err, 8, 1, f); fwrite(&dstrays, 8, 1, f); fwrite(&dscale, 8, 1, f);
     fwrite(&dmis, 8, 1, f);
     fwrite(rho.data(), 4, M, f); fwrite(buf.data(), 4, M, f); fwrite(force.data(), 16, N, f);
