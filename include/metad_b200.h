@@ -194,6 +194,24 @@ int metad_grid_destroy(metad_grid* g);
 /* d_cv_values: n_cv doubles (device); d_bias_out: n_cv doubles (device) = dV/ds_i. */
 int metad_grid_step(metad_grid* g, unsigned timestep, const double* d_cv_values, double* d_bias_out,
                     metad_stream_t stream);
+/* Multiple walkers (IntegratorMetaDynamics.cc:65-71, 392-410: MPI_Allreduce of the four delta arrays over the partition
+ * communicator between the Gaussian deposit and the merge): the step in two halves.  On every step
+ *   metad_grid_step_deposit   updateHistogram; on deposit steps also updateSigmaGrid, the well-tempered scale and the
+ *                             Gaussian into grid_delta;
+ *   [deposit steps only]      metad_grid_deltas_export -> all-reduce (sum) over the walkers -> metad_grid_deltas_import;
+ *   metad_grid_step_merge     on deposit steps updateReweightedEstimator + the merge of the deltas; always the hand-off
+ *                             (dV/ds_i, V(s), weight).
+ * deposit + merge without an exchange in between == metad_grid_step.  The delta arrays travel as two device buffers:
+ * double[2G] = grid_delta | sigma_grid_delta, unsigned[2G] = hist_delta | hist_gauss_delta. */
+int metad_grid_step_deposit(metad_grid* g, unsigned timestep, const double* d_cv_values, metad_stream_t stream);
+int metad_grid_step_merge(metad_grid* g, unsigned timestep, const double* d_cv_values, double* d_bias_out,
+                          metad_stream_t stream);
+int metad_grid_is_deposit_step(const metad_grid* g, unsigned timestep);
+int metad_grid_deltas_export(metad_grid* g, double* d_out_2G, unsigned* d_out_u_2G, metad_stream_t stream);
+int metad_grid_deltas_import(metad_grid* g, const double* d_in_2G, const unsigned* d_in_u_2G, metad_stream_t stream);
+/* Adaptive Gaussians (setAdaptive, IntegratorMetaDynamics.cc:333-341): the inverse sigma matrix (n_cv x n_cv, row-major,
+ * host) that computeSigma (:1205-1294) derives from the CV derivatives replaces diag(1/sigma_i); see metad_force_dot. */
+int metad_grid_set_sigma_inv(metad_grid* g, const double* sigma_inv);
 int metad_grid_set_flags(metad_grid* g, int add_bias, int well_tempered, unsigned stride);
 int metad_grid_reset_histogram(metad_grid* g, metad_stream_t stream);
 /* Synchronous host access for dump/restart (writeGrid/readGrid, IntegratorMetaDynamics.cc:831-1000).
@@ -218,6 +236,10 @@ int metad_umbrella_apply(int kind, double cv0, double kappa, double width_flat, 
  * WellTemperedEnsemble
  * replaces gpu_reduce_potential_energy and gpu_scale_netforce (WellTemperedEnsemble.cuh:3-19).
  * ---------------------------------------------------------------------------------------------- */
+/* *d_out = scale * sum_n (f_i[n].xyz . f_j[n].xyz): the sums of products of CV derivatives of computeSigma
+ * (IntegratorMetaDynamics.cc:1238-1247; scale = sigma_g^2), f = Scalar4 force arrays filled by computeDerivatives */
+int metad_force_dot(const float* d_force_i, const float* d_force_j, unsigned N, double scale, double* d_out,
+                    metad_stream_t stream);
 /* *d_pe = sum_i net_force[i].w + external_energy */
 int metad_wte_reduce(const float* d_net_force, unsigned N, double external_energy, double* d_pe,
                      metad_stream_t stream);

@@ -75,6 +75,13 @@ SIGNATURES = {
                                     C.c_uint, C.c_int, C.c_int]),
     "metad_grid_destroy": (C.c_int, [_vp]),
     "metad_grid_step": (C.c_int, [_vp, C.c_uint, _vp, _vp, _vp]),
+    "metad_grid_step_deposit": (C.c_int, [_vp, C.c_uint, _vp, _vp]),
+    "metad_grid_step_merge": (C.c_int, [_vp, C.c_uint, _vp, _vp, _vp]),
+    "metad_grid_is_deposit_step": (C.c_int, [_vp, C.c_uint]),
+    "metad_grid_deltas_export": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "metad_grid_deltas_import": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "metad_grid_set_sigma_inv": (C.c_int, [_vp, C.POINTER(C.c_double)]),
+    "metad_force_dot": (C.c_int, [_vp, _vp, C.c_uint, C.c_double, _vp, _vp]),
     "metad_grid_set_flags": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint]),
     "metad_grid_reset_histogram": (C.c_int, [_vp, _vp]),
     "metad_grid_download": (C.c_int, [_vp, C.c_int, _vp]),

@@ -107,7 +107,10 @@ __device__ bool grid_bin(const GridParams& P, const double* val, unsigned* idx_o
 }
 
 __global__ void __launch_bounds__(kGridThreads)
-grid_step_kernel(GridParams P, GridArrays A, const double* __restrict__ cv_in, double* __restrict__ bias_out, int deposit) {
+grid_step_kernel(GridParams P, GridArrays A, const double* __restrict__ cv_in, double* __restrict__ bias_out, int deposit, int phase) {
+    // phase 0: the whole step.  Multiple walkers (IntegratorMetaDynamics.cc:392-410) put an all-reduce of the four delta
+    // arrays between the deposit and the merge: phase 1 = histogram + sigma grid + Gaussian into the delta arrays,
+    // phase 2 = reweighted estimator + merge of the (summed) deltas + hand-off of dV/ds, V(s) and the weight.
     __shared__ double cur[kMaxCV];
     __shared__ double sh_scal, sh_avg;
     __shared__ double red[32];
@@ -120,9 +123,9 @@ grid_step_kernel(GridParams P, GridArrays A, const double* __restrict__ cv_in, d
         sh_oob = 0.0;
         for (int i = 0; i < P.d; ++i) cur[i] = mine[i];
         unsigned idx;
-        const bool on = grid_bin(P, cur, &idx);
+        const bool on = phase != 2 && grid_bin(P, cur, &idx);
         if (on) atomicAdd(A.hist_delta + idx, 1u);            // no return value: the kernel does not wait for the round trip
-        if (deposit) {
+        if (deposit && phase != 2) {
             if (on) { A.sigma_grid_delta[idx] += P.sigma_det; A.hist_gauss_delta[idx] += 1u; }
             double scal = 1.0;
             if (P.well_tempered) {
@@ -134,9 +137,8 @@ grid_step_kernel(GridParams P, GridArrays A, const double* __restrict__ cv_in, d
     }
     if (deposit) __syncthreads();
 
-    if (deposit) {
+    if (deposit && phase != 2) {
         const double scal = sh_scal;
-        double avg = 0.0, norm = 0.0;
         for (unsigned g = threadIdx.x; g < P.G; g += blockDim.x) {
             // IndexGrid::getCoordinates: first CV fastest
             unsigned rest = g, c[kMaxCV];
@@ -149,8 +151,13 @@ grid_step_kernel(GridParams P, GridArrays A, const double* __restrict__ cv_in, d
                     const double sij = P.sigma_inv[i * P.d + j];
                     gauss_exp += dd[i] * dd[j] * 0.5 * (sij * sij);
                 }
-            const double delta = P.W * scal * exp(-gauss_exp);
-            A.grid_delta[g] = delta;
+            A.grid_delta[g] = P.W * scal * exp(-gauss_exp);
+        }
+    }
+    if (deposit && phase != 1) {
+        double avg = 0.0, norm = 0.0;
+        for (unsigned g = threadIdx.x; g < P.G; g += blockDim.x) {      // phase 0: every thread re-reads what it wrote above
+            const double delta = A.grid_delta[g];
             const double rew = A.reweighted[g] + (double)A.hist_delta[g];
             A.reweighted[g] = rew;
             avg += rew * delta;
@@ -182,7 +189,7 @@ grid_step_kernel(GridParams P, GridArrays A, const double* __restrict__ cv_in, d
     // one lane each, so the dependent-load latency of this one-block kernel is paid once, not 2d + 2 times (it sits on
     // the critical path of every step).  Arithmetic per interpolation is unchanged (grid_derivative above is the
     // serial statement of the same rule).
-    if (threadIdx.x < 32) {
+    if (threadIdx.x < 32 && phase != 1) {
         const int lane = threadIdx.x, d = P.d;
         double y = 0.0, oob = 0.0;
         if (lane < 2 * d) {
@@ -323,12 +330,65 @@ extern "C" int metad_grid_destroy(metad_grid* g) {
 
 extern "C" unsigned metad_grid_num_elements(const metad_grid* g) { return g ? g->P.G : 0; }
 
+namespace {
+int grid_step_phase(metad_grid* g, unsigned timestep, const double* d_cv_values, double* d_bias_out, int phase, cudaStream_t stream) {
+    const int deposit = (g->add_bias && (timestep % g->stride == 0)) ? 1 : 0;
+    grid_step_kernel<<<1, deposit ? kGridThreads : 32, 0, stream>>>(g->P, g->A, d_cv_values, d_bias_out, deposit, phase);
+    METAD_LAUNCH_CHECK();
+    return METAD_OK;
+}
+}  // namespace
+
 extern "C" int metad_grid_step(metad_grid* g, unsigned timestep, const double* d_cv_values, double* d_bias_out,
                                metad_stream_t stream) {
     METAD_REQUIRE(g && d_cv_values && d_bias_out, "metad_grid_step: null argument");
-    const int deposit = (g->add_bias && (timestep % g->stride == 0)) ? 1 : 0;
-    grid_step_kernel<<<1, deposit ? kGridThreads : 32, 0, stream>>>(g->P, g->A, d_cv_values, d_bias_out, deposit);
-    METAD_LAUNCH_CHECK();
+    return grid_step_phase(g, timestep, d_cv_values, d_bias_out, 0, stream);
+}
+
+extern "C" int metad_grid_step_deposit(metad_grid* g, unsigned timestep, const double* d_cv_values, metad_stream_t stream) {
+    METAD_REQUIRE(g && d_cv_values, "metad_grid_step_deposit: null argument");
+    return grid_step_phase(g, timestep, d_cv_values, nullptr, 1, stream);
+}
+
+extern "C" int metad_grid_step_merge(metad_grid* g, unsigned timestep, const double* d_cv_values, double* d_bias_out,
+                                     metad_stream_t stream) {
+    METAD_REQUIRE(g && d_cv_values && d_bias_out, "metad_grid_step_merge: null argument");
+    return grid_step_phase(g, timestep, d_cv_values, d_bias_out, 2, stream);
+}
+
+extern "C" int metad_grid_is_deposit_step(const metad_grid* g, unsigned timestep) {
+    return (g && g->add_bias && (timestep % g->stride == 0)) ? 1 : 0;
+}
+
+// the four delta arrays as two contiguous device buffers (what a multiple-walker all-reduce sums): doubles
+// [grid_delta | sigma_grid_delta], unsigned [hist_delta | hist_gauss_delta], G entries each
+extern "C" int metad_grid_deltas_export(metad_grid* g, double* d_out_2G, unsigned* d_out_u_2G, metad_stream_t stream) {
+    METAD_REQUIRE(g && d_out_2G && d_out_u_2G, "metad_grid_deltas_export: null argument");
+    const size_t G = g->P.G;
+    METAD_CUDA(cudaMemcpyAsync(d_out_2G, g->A.grid_delta, G * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    METAD_CUDA(cudaMemcpyAsync(d_out_2G + G, g->A.sigma_grid_delta, G * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    METAD_CUDA(cudaMemcpyAsync(d_out_u_2G, g->A.hist_delta, G * sizeof(unsigned), cudaMemcpyDeviceToDevice, stream));
+    METAD_CUDA(cudaMemcpyAsync(d_out_u_2G + G, g->A.hist_gauss_delta, G * sizeof(unsigned), cudaMemcpyDeviceToDevice, stream));
+    return METAD_OK;
+}
+
+extern "C" int metad_grid_deltas_import(metad_grid* g, const double* d_in_2G, const unsigned* d_in_u_2G, metad_stream_t stream) {
+    METAD_REQUIRE(g && d_in_2G && d_in_u_2G, "metad_grid_deltas_import: null argument");
+    const size_t G = g->P.G;
+    METAD_CUDA(cudaMemcpyAsync(g->A.grid_delta, d_in_2G, G * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    METAD_CUDA(cudaMemcpyAsync(g->A.sigma_grid_delta, d_in_2G + G, G * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    METAD_CUDA(cudaMemcpyAsync(g->A.hist_delta, d_in_u_2G, G * sizeof(unsigned), cudaMemcpyDeviceToDevice, stream));
+    METAD_CUDA(cudaMemcpyAsync(g->A.hist_gauss_delta, d_in_u_2G + G, G * sizeof(unsigned), cudaMemcpyDeviceToDevice, stream));
+    return METAD_OK;
+}
+
+// adaptive Gaussians: install the inverse sigma matrix computed by computeSigma (IntegratorMetaDynamics.cc:1205-1294);
+// the sigma grid then receives its determinant (sigmaDeterminant :1296-1313)
+extern "C" int metad_grid_set_sigma_inv(metad_grid* g, const double* sigma_inv) {
+    METAD_REQUIRE(g && sigma_inv, "metad_grid_set_sigma_inv: null argument");
+    const int d = g->P.d;
+    for (int i = 0; i < d * d; ++i) g->P.sigma_inv[i] = sigma_inv[i];
+    g->P.sigma_det = det_small(g->P.sigma_inv, d);
     return METAD_OK;
 }
 

@@ -37,6 +37,34 @@ wte_reduce_kernel(const float4* __restrict__ net_force, unsigned N, double exter
     if (threadIdx.x == 0) { *d_pe = s + external_energy; *ticket = 0; }
 }
 
+// sum_n f_i(n) . f_j(n) over the xyz components of two force arrays (computeSigma, IntegratorMetaDynamics.cc:1238-1247:
+// the products of the CV derivatives); fp64 accumulation, per-block partials, last block adds them in order
+__global__ void __launch_bounds__(kWteThreads)
+force_dot_kernel(const float4* __restrict__ fi, const float4* __restrict__ fj, unsigned N, double scale, double* __restrict__ partials,
+                 unsigned* __restrict__ ticket, double* __restrict__ d_out) {
+    double acc = 0.0;
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+        const float4 a = ld_stream(fi + i), b = ld_stream(fj + i);
+        acc += (double)a.x * (double)b.x + (double)a.y * (double)b.y + (double)a.z * (double)b.z;
+    }
+    __shared__ double red[32];
+    __shared__ bool is_last;
+    const double r = block_sum(acc, red);
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = r;
+        __threadfence();
+        is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double s = 0.0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) s += __ldcg(partials + b);
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) { *d_out = scale * s; *ticket = 0; }
+}
+
 __global__ void __launch_bounds__(kWteThreads)
 wte_scale_kernel(float4* __restrict__ net_force, float4* __restrict__ net_torque, float* __restrict__ net_virial,
                  unsigned pitch, unsigned N, const double* __restrict__ d_bias) {
@@ -124,6 +152,21 @@ static int wte_scratch(cudaStream_t stream, WteScratch** out) {
 }  // namespace metad
 
 using namespace metad;
+
+extern "C" int metad_force_dot(const float* d_force_i, const float* d_force_j, unsigned N, double scale, double* d_out,
+                               metad_stream_t stream) {
+    METAD_REQUIRE(d_out, "metad_force_dot: null output");
+    METAD_REQUIRE(N == 0 || (d_force_i && d_force_j), "metad_force_dot: null force array");
+    WteScratch* w = nullptr;
+    int rc = wte_scratch(stream, &w);
+    if (rc) return rc;
+    long b = ((long)N + kWteThreads * 8L - 1) / (kWteThreads * 8L);
+    if (b < 1) b = 1;
+    if (b > w->blocks) b = w->blocks;
+    force_dot_kernel<<<(int)b, kWteThreads, 0, stream>>>((const float4*)d_force_i, (const float4*)d_force_j, N, scale, w->partials, w->ticket, d_out);
+    METAD_LAUNCH_CHECK();
+    return METAD_OK;
+}
 
 extern "C" int metad_wte_reduce(const float* d_net_force, unsigned N, double external_energy, double* d_pe,
                                 metad_stream_t stream) {

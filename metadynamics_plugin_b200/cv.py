@@ -8,7 +8,8 @@ arguments, defaults and error behaviour, bound to the B200-native `_metadynamics
     cv.density(group=None, sigma=1.0)                                             reference cv.py:309-339
     base class: set_grid(cv_min, cv_max, num_points), set_params(sigma, kappa, cv0, umbrella, width_flat, scale,
     reweight)                                                                     reference cv.py:11-171
-cv.wrap and cv.steinhardt need arbitrary HOOMD force fields / neighbour lists and are out of scope.
+    cv.wrap(force, sigma=1.0)                                                     reference cv.py:504-541
+cv.steinhardt needs HOOMD's neighbour list and is out of scope (OUT OF SCOPE).
 """
 # This build always binds to the stand-in for the handful of HOOMD-blue 2.x objects the scripts touch (hoomd_shim.py);
 # binding the classes to a real HOOMD installation is a build-time step described in INTEGRATION.md.
@@ -194,3 +195,31 @@ class potential_energy(_collective_variable):
         self.cpp_force = _metadynamics.WellTemperedEnsemble(hoomd.context.current.system_definition, name)
         self.cpp_force.enabled = False
         hoomd.context.current.system.addCompute(self.cpp_force, name)
+
+
+class wrap(_collective_variable):
+    """Force wrapper: use the potential energy of an arbitrary force as collective variable (reference cv.py:504-541).
+    `force` is a force object of the MD engine (`md.force._force`; with the stand-in: hoomd_shim.prescribed_force).  The
+    reference's disable() / enable() recurse into themselves and name an undefined variable (cv.py:531-537); here they do
+    what they were written for: switch this CV and the wrapped force together."""
+
+    def __init__(self, force, sigma=1.0):
+        hoomd.util.print_status_line()
+        if not isinstance(force, _force_base):
+            hoomd.context.msg.error("cv.wrap needs a md._force instance as argument.")
+            raise RuntimeError("Error creating cv.wrap")
+        name = 'cv_' + force.name
+        _collective_variable.__init__(self, sigma, name)
+        self.force = force
+        self.cpp_force = _metadynamics.CollectiveWrapper(hoomd.context.current.system_definition, force.cpp_force, name)
+        if force.enabled or force.log:
+            hoomd.context.current.system.addCompute(self.cpp_force, name)
+        self.log = force.log
+
+    def disable(self, log=False):
+        _collective_variable.disable(self, log)
+        self.force.disable(log)
+
+    def enable(self):
+        _collective_variable.enable(self)
+        self.force.enable()

@@ -123,6 +123,27 @@ class _force:
         return self.cpp_force.getForces()
 
 
+class prescribed_force(_force):
+    """Stand-in for "any force of the MD engine" (pair, bond, ...): per-particle force / energy (N,4), torque (N,4), virial
+    (6,N) and an external energy given as arrays; what cv.wrap wraps when HOOMD-blue itself is absent."""
+
+    def __init__(self, force4, torque4=None, virial6N=None, external_energy=0.0, name=None):
+        import numpy as np
+        from . import _metadynamics
+        _force.__init__(self, name)
+        sd = context.current.system_definition
+        f = np.ascontiguousarray(force4, dtype=np.float32)
+        n = f.shape[0]
+        self.cpp_force = _metadynamics.PrescribedForce(sd)
+        pitch = self.cpp_force.getVirialPitch()
+        t = np.zeros((n, 4), np.float32) if torque4 is None else np.ascontiguousarray(torque4, dtype=np.float32)
+        v = np.zeros((6, pitch), np.float32)
+        if virial6N is not None:
+            v[:, :n] = np.asarray(virial6N, dtype=np.float32)
+        self.cpp_force.setArrays(f, t, v.reshape(-1), float(external_energy))
+        context.current.system.addCompute(self.cpp_force, self.force_name)
+
+
 class _integrator:
     """hoomd.md.integrate._integrator."""
 

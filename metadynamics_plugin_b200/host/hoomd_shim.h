@@ -165,6 +165,13 @@ class ForceCompute {
         m_computed_once = true;
     }
     DeviceArray<Scalar4>& getForceArray() { return m_force; }
+    // per-particle torque and virial (6 x pitch) of a force compute: allocated when first asked for (the CVs of this plugin
+    // never fill them; CollectiveWrapper scales the ones of the force it wraps)
+    DeviceArray<Scalar4>& getTorqueArray() { if (m_torque.size() != m_force.size()) m_torque.resize(m_force.size()); return m_torque; }
+    DeviceArray<Scalar>& getVirialArray() { if (m_virial.size() != 6 * getVirialPitch()) m_virial.resize(6 * getVirialPitch()); return m_virial; }
+    size_t getVirialPitch() const { return (m_force.size() + 15) / 16 * 16; }
+    Scalar getExternalEnergy() const { return m_external_energy; }
+    void setExternalEnergy(Scalar e) { m_external_energy = e; }
     Scalar getExternalVirial(unsigned i) const { return m_external_virial[i]; }
     virtual std::vector<std::string> getProvidedLogQuantities() { return {}; }
     virtual Scalar getLogValue(const std::string& quantity, unsigned) { throw std::runtime_error("Error querying log quantity " + quantity); }
@@ -175,10 +182,34 @@ class ForceCompute {
     std::shared_ptr<SystemDefinition> m_sysdef;
     std::shared_ptr<ParticleData> m_pdata;
     std::shared_ptr<ExecutionConfiguration> m_exec_conf;
-    DeviceArray<Scalar4> m_force;
+    DeviceArray<Scalar4> m_force, m_torque;
+    DeviceArray<Scalar> m_virial;
+    Scalar m_external_energy = 0;
     Scalar m_external_virial[6];
     unsigned m_last_computed = 0;
     bool m_computed_once = false;
+};
+
+// Stand-in for "any HOOMD force": a ForceCompute whose per-particle force / energy, torque and virial are prescribed
+// arrays, re-installed at every new timestep (what a pair or bond force would recompute).  cv.wrap needs something to wrap.
+class PrescribedForce : public ForceCompute {
+  public:
+    explicit PrescribedForce(std::shared_ptr<SystemDefinition> sysdef) : ForceCompute(sysdef) {}
+    void setArrays(const std::vector<Scalar4>& force, const std::vector<Scalar4>& torque, const std::vector<Scalar>& virial6pitch, Scalar external_energy) {
+        if (force.size() != m_force.size() || torque.size() != m_force.size() || virial6pitch.size() != 6 * getVirialPitch())
+            throw std::runtime_error("PrescribedForce: array sizes do not match the particle number");
+        m_h_force = force; m_h_torque = torque; m_h_virial = virial6pitch; m_external_energy = external_energy;
+    }
+
+  protected:
+    void computeForces(unsigned) override {
+        if (m_h_force.empty()) return;
+        m_force.upload(m_h_force.data(), m_h_force.size());
+        getTorqueArray().upload(m_h_torque.data(), m_h_torque.size());
+        getVirialArray().upload(m_h_virial.data(), m_h_virial.size());
+    }
+    std::vector<Scalar4> m_h_force, m_h_torque;
+    std::vector<Scalar> m_h_virial;
 };
 
 }  // namespace shim

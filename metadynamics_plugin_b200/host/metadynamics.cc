@@ -241,6 +241,48 @@ Scalar WellTemperedEnsemble::getLogValue(const std::string& quantity, unsigned i
     return CollectiveVariable::getLogValue(quantity, timestep);
 }
 
+// ================================================================================================ CollectiveWrapper
+CollectiveWrapper::CollectiveWrapper(std::shared_ptr<SystemDefinition> sysdef, std::shared_ptr<ForceCompute> fc, const std::string& name)
+    : CollectiveVariable(sysdef, name), m_fc(fc), m_d_fac(1) {
+    if (!fc) throw std::runtime_error("cv.wrap needs a force to wrap");
+}
+// CollectiveWrapper.cc:31-73: the wrapped force is computed (once per time step), its per-particle energies are summed,
+// its external energy is added, the ranks of a domain decomposition are reduced
+const double* CollectiveWrapper::getCurrentValueDevice(unsigned int timestep) {
+    m_fc->compute(timestep);
+    double* d_cv = m_d_scalars.data() + 2;
+    metad_check(metad_wte_reduce((const float*)m_fc->getForceArray().data(), m_pdata->getN(), allreduce ? 0.0 : (double)m_fc->getExternalEnergy(),
+                                 d_cv, stream_of(m_exec_conf)), "metad_wte_reduce");
+    if (allreduce) {        // local sums first, the external energy of every rank is part of its local sum in the reference (:60-61 before :63-69)
+        const double ext = (double)m_fc->getExternalEnergy();
+        double local = 0;
+        cuda_check(cudaStreamSynchronize(stream_of(m_exec_conf)), "sync");
+        cuda_check(cudaMemcpy(&local, d_cv, sizeof(double), cudaMemcpyDeviceToHost), "download");
+        local += ext;
+        cuda_check(cudaMemcpy(d_cv, &local, sizeof(double), cudaMemcpyHostToDevice), "upload");
+        allreduce((size_t)d_cv, 1);
+    }
+    return d_cv;
+}
+Scalar CollectiveWrapper::getCurrentValue(unsigned int timestep) {
+    getCurrentValueDevice(timestep);
+    double v = 0;
+    cuda_check(cudaStreamSynchronize(stream_of(m_exec_conf)), "sync");
+    cuda_check(cudaMemcpy(&v, m_d_scalars.data() + 2, sizeof(double), cudaMemcpyDeviceToHost), "cv download");
+    return (Scalar)v;
+}
+// CollectiveWrapper.cc:140-188: force, torque (all four components) and virial of the WRAPPED force times the bias factor.
+// metad_wte_scale multiplies by (1 + *d_bias) -- hand it bias - 1.
+void CollectiveWrapper::computeBiasForces(unsigned int timestep) {
+    m_fc->compute(timestep);
+    cudaStream_t st = stream_of(m_exec_conf);
+    const double fac_minus_one = (double)biasHost() - 1.0;
+    cuda_check(cudaMemcpyAsync(m_d_fac.data(), &fac_minus_one, sizeof(double), cudaMemcpyHostToDevice, st), "fac upload");
+    cuda_check(cudaStreamSynchronize(st), "fac upload sync");
+    metad_check(metad_wte_scale((float*)m_fc->getForceArray().data(), (float*)m_fc->getTorqueArray().data(), m_fc->getVirialArray().data(),
+                                (unsigned)m_fc->getVirialPitch(), m_pdata->getN(), m_d_fac.data(), st), "metad_wte_scale");
+}
+
 // ================================================================================================ box CVs
 AspectRatio::AspectRatio(std::shared_ptr<SystemDefinition> sysdef, unsigned int dir1, unsigned int dir2)
     : CollectiveVariable(sysdef, "cv_aspect_ratio"), m_dir1(dir1), m_dir2(dir2) {
@@ -361,12 +403,49 @@ void IntegratorMetaDynamics::pushFlags() {
 void IntegratorMetaDynamics::setMode(Enum mode) { m_mode = mode; pushFlags(); }
 void IntegratorMetaDynamics::setStride(unsigned int stride) { m_stride = stride; pushFlags(); }
 void IntegratorMetaDynamics::setAddHills(bool add_bias) { m_add_bias = add_bias; pushFlags(); }
-void IntegratorMetaDynamics::setAdaptive(bool adaptive) {
-    if (adaptive) {
-        m_exec_conf->msg->error("integrate.mode_metadynamics: adaptive Gaussians are not supported by the sm_100a path yet.");
-        throw std::runtime_error("Error setting up metadynamics parameters.");
+void IntegratorMetaDynamics::setAdaptive(bool adaptive) { m_adaptive = adaptive; }
+
+// computeSigma, IntegratorMetaDynamics.cc:1205-1294: sigma^2_ij = sigma_g^2 sum_n dCV_i/dr_n . dCV_j/dr_n for CVs that can
+// compute derivatives (their force arrays hold the derivatives after computeDerivatives), sigma_i^2 on the diagonal
+// otherwise; sigma_inv = inverse of the matrix of element-wise square roots (Eigen -> Gauss-Jordan with partial pivoting).
+// The N-length sums run on the device (metad_force_dot, fp64); the n_cv x n_cv algebra on the host, on deposit steps only.
+void IntegratorMetaDynamics::computeSigma() {
+    const size_t d = m_variables.size();
+    cudaStream_t st = stream_of(m_exec_conf);
+    m_d_sigmasq.resize(d * d);
+    cuda_check(cudaMemsetAsync(m_d_sigmasq.data(), 0, sizeof(double) * d * d, st), "sigmasq reset");
+    for (size_t i = 0; i < d; ++i)
+        for (size_t j = 0; j < d; ++j)
+            if (m_variables[i].m_cv->canComputeDerivatives() && m_variables[j].m_cv->canComputeDerivatives())
+                metad_check(metad_force_dot((const float*)m_variables[i].m_cv->getForceArray().data(),
+                                            (const float*)m_variables[j].m_cv->getForceArray().data(), m_pdata->getN(),
+                                            (double)m_sigma_g * (double)m_sigma_g, m_d_sigmasq.data() + i * d + j, st), "metad_force_dot");
+    if (domain_allreduce) {
+        cuda_check(cudaStreamSynchronize(st), "sync");
+        domain_allreduce((size_t)m_d_sigmasq.data(), d * d);
     }
-    m_adaptive = false;
+    std::vector<double> sq(d * d);
+    cuda_check(cudaStreamSynchronize(st), "sync");
+    m_d_sigmasq.download(sq.data(), d * d);
+    for (size_t i = 0; i < d; ++i)
+        if (!m_variables[i].m_cv->canComputeDerivatives()) sq[i * d + i] = (double)m_variables[i].m_sigma * (double)m_variables[i].m_sigma;
+    std::vector<double> m(d * d), inv(d * d, 0.0);
+    for (size_t k = 0; k < d * d; ++k) m[k] = std::sqrt(sq[k]);
+    for (size_t i = 0; i < d; ++i) inv[i * d + i] = 1.0;
+    for (size_t c = 0; c < d; ++c) {
+        size_t piv = c;
+        for (size_t r = c + 1; r < d; ++r) if (std::fabs(m[r * d + c]) > std::fabs(m[piv * d + c])) piv = r;
+        if (piv != c) for (size_t k = 0; k < d; ++k) { std::swap(m[piv * d + k], m[c * d + k]); std::swap(inv[piv * d + k], inv[c * d + k]); }
+        const double p = m[c * d + c];
+        for (size_t k = 0; k < d; ++k) { m[c * d + k] /= p; inv[c * d + k] /= p; }
+        for (size_t r = 0; r < d; ++r) {
+            if (r == c) continue;
+            const double f = m[r * d + c];
+            for (size_t k = 0; k < d; ++k) { m[r * d + k] -= f * m[c * d + k]; inv[r * d + k] -= f * inv[c * d + k]; }
+        }
+    }
+    m_sigma_inv = inv;
+    metad_check(metad_grid_set_sigma_inv(m_grid, inv.data()), "metad_grid_set_sigma_inv");
 }
 
 // IntegratorMetaDynamics.cc:590-661: the grid arrays live in device memory (metad_grid)
@@ -449,7 +528,26 @@ void IntegratorMetaDynamics::updateBiasPotential(unsigned int timestep) {
         const double* d_val = m_variables[i].m_cv->getCurrentValueDevice(timestep);
         cuda_check(cudaMemcpyAsync(m_d_cv.data() + i, d_val, sizeof(double), cudaMemcpyDeviceToDevice, st), "cv gather");
     }
-    metad_check(metad_grid_step(m_grid, timestep, m_d_cv.data(), m_d_bias.data(), st), "metad_grid_step");
+    // adaptive Gaussians (:333-341): derivatives of every CV, then the instantaneous sigma matrix
+    if (m_adaptive && (timestep % m_stride == 0)) {
+        for (size_t i = 0; i < d; ++i) m_variables[i].m_cv->computeDerivatives(timestep);
+        computeSigma();
+    }
+    if (m_multiple_walkers && walker_allreduce) {
+        // multiple walkers (:392-410): the four delta arrays are summed over the walkers between deposit and merge
+        metad_check(metad_grid_step_deposit(m_grid, timestep, m_d_cv.data(), st), "metad_grid_step_deposit");
+        if (metad_grid_is_deposit_step(m_grid, timestep)) {
+            const size_t G = metad_grid_num_elements(m_grid);
+            m_d_walk_d.resize(2 * G); m_d_walk_u.resize(2 * G);
+            metad_check(metad_grid_deltas_export(m_grid, m_d_walk_d.data(), m_d_walk_u.data(), st), "metad_grid_deltas_export");
+            cuda_check(cudaStreamSynchronize(st), "sync");
+            walker_allreduce((size_t)m_d_walk_d.data(), 2 * G, (size_t)m_d_walk_u.data(), 2 * G);
+            metad_check(metad_grid_deltas_import(m_grid, m_d_walk_d.data(), m_d_walk_u.data(), st), "metad_grid_deltas_import");
+        }
+        metad_check(metad_grid_step_merge(m_grid, timestep, m_d_cv.data(), m_d_bias.data(), st), "metad_grid_step_merge");
+    } else {
+        metad_check(metad_grid_step(m_grid, timestep, m_d_cv.data(), m_d_bias.data(), st), "metad_grid_step");
+    }
 
     // hills file (:523-550) -- needs the current bias potential on the host, only when a log file was requested
     if (m_is_initialized && (timestep % m_stride == 0) && m_add_bias && m_file.is_open()) {
@@ -462,7 +560,8 @@ void IntegratorMetaDynamics::updateBiasPotential(unsigned int timestep) {
         m_file << std::setprecision(10) << W << m_delimiter;
         for (size_t i = 0; i < d; ++i) {
             m_file << std::setprecision(10) << (Scalar)cur[i] << m_delimiter;
-            for (size_t j = 0; j < d; ++j) m_file << std::setprecision(10) << (i == j ? Scalar(1.0) / m_variables[i].m_sigma : Scalar(0.0));
+            for (size_t j = 0; j < d; ++j)
+                m_file << std::setprecision(10) << (m_sigma_inv.size() == d * d ? (Scalar)m_sigma_inv[i * d + j] : (i == j ? Scalar(1.0) / m_variables[i].m_sigma : Scalar(0.0)));
             if (i != d - 1) m_file << m_delimiter;
         }
         m_file << std::endl;
@@ -483,6 +582,20 @@ Scalar IntegratorMetaDynamics::getLogValue(const std::string& quantity, unsigned
     if (m_grid) metad_check(metad_grid_scalars(m_grid, sc), "metad_grid_scalars");
     if (quantity == m_log_names[0]) return (Scalar)sc[0];
     if (quantity == m_log_names[1]) {
+        const size_t d = m_variables.size();
+        if (m_sigma_inv.size() == d * d && d) {          // adaptive Gaussians: determinant of the current inverse sigma matrix (sigmaDeterminant :1296-1313)
+            std::vector<double> m(m_sigma_inv);
+            double det = 1.0;
+            for (size_t c = 0; c < d; ++c) {
+                size_t piv = c;
+                for (size_t r = c + 1; r < d; ++r) if (std::fabs(m[r * d + c]) > std::fabs(m[piv * d + c])) piv = r;
+                if (m[piv * d + c] == 0.0) return Scalar(0.0);
+                if (piv != c) { for (size_t k = 0; k < d; ++k) std::swap(m[piv * d + k], m[c * d + k]); det = -det; }
+                det *= m[c * d + c];
+                for (size_t r = c + 1; r < d; ++r) { const double f = m[r * d + c] / m[c * d + c]; for (size_t k = c; k < d; ++k) m[r * d + k] -= f * m[c * d + k]; }
+            }
+            return (Scalar)det;
+        }
         Scalar det = 1;
         for (auto& v : m_variables) det *= Scalar(1.0) / v.m_sigma;
         return det;

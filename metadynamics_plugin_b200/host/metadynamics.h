@@ -148,6 +148,23 @@ class Density : public CollectiveVariable {
     void computeBiasForces(unsigned int timestep) override;
 };
 
+//! Wraps a CollectiveVariable around a regular ForceCompute: CV = its potential energy (CollectiveWrapper.cc:31-73), the
+//! bias force = its own force, torque and virial arrays scaled IN PLACE by the bias factor (:140-188 -- by m_bias, not
+//! 1 + m_bias as in WellTemperedEnsemble; restated as written).  Reuses the WTE kernels, like the reference.
+class CollectiveWrapper : public CollectiveVariable {
+  public:
+    CollectiveWrapper(std::shared_ptr<SystemDefinition> sysdef, std::shared_ptr<ForceCompute> fc, const std::string& name);
+    Scalar getCurrentValue(unsigned int timestep) override;
+    const double* getCurrentValueDevice(unsigned int timestep) override;
+    //! sum over the ranks of one walker of the local energy (MPI_Allreduce, CollectiveWrapper.cc:63-69): device double, in place
+    std::function<void(size_t, size_t)> allreduce;
+
+  protected:
+    void computeBiasForces(unsigned int timestep) override;
+    std::shared_ptr<ForceCompute> m_fc;
+    DeviceArray<double> m_d_fac;
+};
+
 class IndexGrid {
   public:
     IndexGrid();
@@ -210,6 +227,14 @@ class IntegratorMetaDynamics {
     void setAdaptive(bool adaptive);
     void setSigmaG(Scalar sigma_g) { m_sigma_g = sigma_g; }
     void setMultipleWalkers(bool multiple) { m_multiple_walkers = multiple; }
+    //! Multiple walkers: sum two device buffers in place over the walkers (the partition communicator of the reference,
+    //! IntegratorMetaDynamics.cc:65-71): called with (device pointer of n_d doubles, n_d, device pointer of n_u unsigned, n_u)
+    //! on deposit steps; must have completed when it returns.  Unset: one walker (nothing to share).
+    std::function<void(size_t, size_t, size_t, size_t)> walker_allreduce;
+    //! Domain decomposition: sum n doubles in device memory over the ranks of one walker (computeSigma's MPI_Allreduce, :1265-1274)
+    std::function<void(size_t, size_t)> domain_allreduce;
+    //! the inverse sigma matrix in use (adaptive Gaussians; row-major n_cv x n_cv)
+    std::vector<double> getSigmaInv() const { return m_sigma_inv; }
     void resetHistogram();
     //! bias grid arrays for inspection: "grid", "reweighted", "weight", "sigma_grid" (double), "hist", "hist_gauss" (as double)
     std::vector<double> getGridArray(const std::string& name);
@@ -217,6 +242,7 @@ class IntegratorMetaDynamics {
 
   private:
     void updateBiasPotential(unsigned int timestep);
+    void computeSigma();
     void computeNetForce(unsigned int timestep);
     void setupGrid();
     void readGrid(const std::string& filename);
@@ -250,6 +276,10 @@ class IntegratorMetaDynamics {
     bool m_multiple_walkers = false;
     metad_grid* m_grid = nullptr;
     DeviceArray<double> m_d_cv, m_d_bias;     // n_cv each
+    DeviceArray<double> m_d_sigmasq;          // n_cv^2 sums of products of the CV derivatives (adaptive Gaussians)
+    DeviceArray<double> m_d_walk_d;           // multiple walkers: grid_delta | sigma_grid_delta
+    DeviceArray<unsigned int> m_d_walk_u;     //                   hist_delta | hist_gauss_delta
+    std::vector<double> m_sigma_inv;
     double* m_h_pinned = nullptr;             // pinned staging for host-scalar CVs
 };
 

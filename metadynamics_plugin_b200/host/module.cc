@@ -81,6 +81,22 @@ PYBIND11_MODULE(_metadynamics, m) {
         .def("getProvidedLogQuantities", &ForceCompute::getProvidedLogQuantities)
         .def("getLogValue", &ForceCompute::getLogValue)
         .def_readwrite("enabled", &ForceCompute::enabled);
+    py::class_<PrescribedForce, ForceCompute, std::shared_ptr<PrescribedForce>>(m, "PrescribedForce")
+        .def(py::init<std::shared_ptr<SystemDefinition>>())
+        .def("setArrays", [](PrescribedForce& f, const farray& force, const farray& torque, const farray& virial, Scalar ext) {
+            auto v4 = [](const farray& a) { std::vector<Scalar4> o(a.shape(0)); memcpy(o.data(), a.data(), sizeof(Scalar4) * o.size()); return o; };
+            std::vector<Scalar> v(virial.data(), virial.data() + virial.size());
+            f.setArrays(v4(force), v4(torque), v, ext);
+        })
+        .def("getVirialPitch", &PrescribedForce::getVirialPitch)
+        .def("getTorques", [](ForceCompute& f) { return download4(f.getTorqueArray()); })
+        .def("getVirial", [](ForceCompute& f) {
+            auto& a = f.getVirialArray();
+            py::array_t<float> out((py::ssize_t)a.size());
+            cuda_check(cudaDeviceSynchronize(), "sync");
+            if (a.size()) a.download(out.mutable_data(), a.size());
+            return out;
+        });
     py::class_<System, std::shared_ptr<System>>(m, "System")
         .def(py::init<std::shared_ptr<SystemDefinition>>())
         .def("addCompute", &System::addCompute);
@@ -126,6 +142,10 @@ PYBIND11_MODULE(_metadynamics, m) {
     py::class_<Density, CollectiveVariable, std::shared_ptr<Density>>(m, "Density")
         .def(py::init<std::shared_ptr<SystemDefinition>, const std::string&>());
 
+    py::class_<CollectiveWrapper, CollectiveVariable, std::shared_ptr<CollectiveWrapper>>(m, "CollectiveWrapper")
+        .def(py::init<std::shared_ptr<SystemDefinition>, std::shared_ptr<ForceCompute>, const std::string&>())
+        .def_readwrite("allreduce", &CollectiveWrapper::allreduce);
+
     py::class_<IndexGrid>(m, "IndexGrid")
         .def(py::init<const std::vector<unsigned int>&>())
         .def("getIndex", &IndexGrid::getIndex)
@@ -156,7 +176,10 @@ PYBIND11_MODULE(_metadynamics, m) {
         .def("getProvidedLogQuantities", &IntegratorMetaDynamics::getProvidedLogQuantities)
         .def("getLogValue", &IntegratorMetaDynamics::getLogValue)
         .def("getGridArray", &IntegratorMetaDynamics::getGridArray)
-        .def("getNumGaussians", &IntegratorMetaDynamics::getNumGaussians);
+        .def("getNumGaussians", &IntegratorMetaDynamics::getNumGaussians)
+        .def("getSigmaInv", &IntegratorMetaDynamics::getSigmaInv)
+        .def_readwrite("walker_allreduce", &IntegratorMetaDynamics::walker_allreduce)
+        .def_readwrite("domain_allreduce", &IntegratorMetaDynamics::domain_allreduce);
     py::enum_<IntegratorMetaDynamics::Enum>(integrator_metad, "mode")
         .value("standard", IntegratorMetaDynamics::mode_standard)
         .value("well_tempered", IntegratorMetaDynamics::mode_well_tempered)

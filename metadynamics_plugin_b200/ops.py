@@ -190,6 +190,43 @@ class BiasGrid:
         check(lib.metad_grid_step(self.h, int(timestep), _ptr(cv_values), _ptr(self.bias), _stream()))
         return self.bias
 
+    # ---- multiple walkers: the step in two halves with an all-reduce of the delta arrays in between on deposit steps
+    def is_deposit_step(self, timestep):
+        return bool(lib.metad_grid_is_deposit_step(self.h, int(timestep)))
+
+    def step_deposit(self, timestep, cv_values):
+        check(lib.metad_grid_step_deposit(self.h, int(timestep), _ptr(cv_values), _stream()))
+
+    def step_merge(self, timestep, cv_values):
+        check(lib.metad_grid_step_merge(self.h, int(timestep), _ptr(cv_values), _ptr(self.bias), _stream()))
+        return self.bias
+
+    def deltas_export(self):
+        """(double[2G] = grid_delta | sigma_grid_delta, int32[2G] = hist_delta | hist_gauss_delta) as device tensors."""
+        if getattr(self, "_dd", None) is None:
+            self._dd = torch.empty(2 * self.G, dtype=torch.float64, device="cuda")
+            self._du = torch.empty(2 * self.G, dtype=torch.int32, device="cuda")
+        check(lib.metad_grid_deltas_export(self.h, _ptr(self._dd), _ptr(self._du), _stream()))
+        return self._dd, self._du
+
+    def deltas_import(self, dd, du):
+        check(lib.metad_grid_deltas_import(self.h, _ptr(dd), _ptr(du), _stream()))
+
+    def step_walkers(self, timestep, cv_values, all_reduce_sum):
+        """One step of a walker in multiple-walker mode (IntegratorMetaDynamics.cc:392-410): all_reduce_sum(tensor) sums a
+        device tensor in place over the walkers' partition communicator."""
+        self.step_deposit(timestep, cv_values)
+        if self.is_deposit_step(timestep):
+            dd, du = self.deltas_export()
+            all_reduce_sum(dd)
+            all_reduce_sum(du)
+            self.deltas_import(dd, du)
+        return self.step_merge(timestep, cv_values)
+
+    def set_sigma_inv(self, m):
+        a, ap = _np_d(np.asarray(m, dtype=np.float64).reshape(-1))
+        check(lib.metad_grid_set_sigma_inv(self.h, ap))
+
     def get(self, name):
         which, dt = self.ARR[name]
         out = np.empty(self.G, dtype=dt)
@@ -225,6 +262,14 @@ def umbrella_apply(kind, cv, bias_in=None, cv0=0.0, kappa=1.0, width_flat=0.0, s
     check(lib.metad_umbrella_apply(UMBRELLA[kind], cv0, kappa, width_flat, scale, _ptr(cv), _ptr(bias_in), _ptr(bias_out),
                                    _ptr(energy_out), _stream()))
     return bias_out
+
+
+def force_dot(f_i, f_j, scale=1.0, out=None):
+    """scale * sum_n f_i[n].xyz . f_j[n].xyz (computeSigma's sums of products of the CV derivatives), device double."""
+    if out is None:
+        out = torch.zeros(1, dtype=torch.float64, device="cuda")
+    check(lib.metad_force_dot(_ptr(f_i), _ptr(f_j), f_i.shape[0], float(scale), _ptr(out), _stream()))
+    return out
 
 
 def wte_reduce(net_force, external_energy=0.0, out=None):

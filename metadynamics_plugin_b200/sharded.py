@@ -90,6 +90,29 @@ class LocalComm:
             recv_from_down[(r + 1) % P].copy_(send_up[r])
 
 
+# ---------------------------------------------------------------------------------------------------- raw device buffers
+class _DevicePtr:
+    """__cuda_array_interface__ view of a raw device pointer handed over by the host classes (no copy)."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = dict(shape=(int(n),), typestr=typestr, data=(int(ptr), False), version=2)
+
+
+def tensor_from_ptr(ptr, n, dtype):
+    """torch tensor aliasing n elements of device memory at `ptr` (float64 or int32)."""
+    return torch.as_tensor(_DevicePtr(ptr, n, {torch.float64: "<f8", torch.int32: "<i4"}[dtype]), device="cuda")
+
+
+def walker_allreduce_hook(comm):
+    """Callable for IntegratorMetaDynamics.walker_allreduce: sums the two delta buffers over the walkers of `comm` (one
+    walker per process; reference: MPI_Allreduce over the partition communicator, IntegratorMetaDynamics.cc:401-408)."""
+    def hook(ptr_d, n_d, ptr_u, n_u):
+        comm.all_reduce_sum(tensor_from_ptr(ptr_d, n_d, torch.float64))
+        comm.all_reduce_sum(tensor_from_ptr(ptr_u, n_u, torch.int32))
+        torch.cuda.current_stream().synchronize()
+    return hook
+
+
 # ---------------------------------------------------------------------------------------------------- lamellar
 class LamellarSharded:
     def __init__(self, comm, mode, lattice_vectors, lamellar_factory=None):
@@ -130,6 +153,27 @@ class WTESharded:
 
     def scale(self, net_force_local, net_torque_local, net_virial_local, pitch, bias):
         return self.scale_fn(net_force_local, net_torque_local, net_virial_local, pitch, bias)
+
+
+class WalkerBias:
+    """Multiple walkers sharing one bias potential (reference: setMultipleWalkers + the partition communicator,
+    IntegratorMetaDynamics.cc:65-71, 392-410): every process is one walker with its own replica of the bias grid; on deposit
+    steps the four delta arrays (Gaussian, sigma grid, histogram, Gaussian histogram) are summed over the walkers between
+    the deposit and the merge, so all replicas stay identical.  `grid`: ops.BiasGrid, or any object with its step_deposit /
+    is_deposit_step / deltas_export / deltas_import / step_merge interface (tests substitute a CPU stand-in)."""
+
+    def __init__(self, comm, grid):
+        self.comm, self.grid = comm, grid
+
+    def step(self, timestep, cv_values):
+        g = self.grid
+        g.step_deposit(timestep, cv_values)
+        if g.is_deposit_step(timestep):
+            dd, du = g.deltas_export()
+            self.comm.all_reduce_sum(dd)
+            self.comm.all_reduce_sum(du)
+            g.deltas_import(dd, du)
+        return g.step_merge(timestep, cv_values)
 
 
 # ---------------------------------------------------------------------------------------------------- mesh

@@ -173,6 +173,36 @@ template <class S> void wte_scale_c(float* f4, float* t4, float* vir, unsigned p
     void orc_grid_update_##SFX(void* g, unsigned timestep, const double* cur, double* bias_out) {                     \
         grid_update<S>(g, timestep, cur, bias_out);                                                                   \
     }                                                                                                                 \
+    void orc_grid_update_deposit_##SFX(void* g, unsigned timestep, const double* cur) {                               \
+        auto* m = (MetaGrid<S>*)g; std::vector<S> c(m->vars.size()); for (size_t i = 0; i < c.size(); ++i) c[i] = (S)cur[i]; \
+        m->update_deposit(timestep, c);                                                                               \
+    }                                                                                                                 \
+    void orc_grid_update_merge_##SFX(void* g, unsigned timestep, const double* cur, double* bias_out) {               \
+        auto* m = (MetaGrid<S>*)g; std::vector<S> c(m->vars.size()), b; for (size_t i = 0; i < c.size(); ++i) c[i] = (S)cur[i]; \
+        m->update_merge(timestep, c, b); for (size_t i = 0; i < b.size(); ++i) bias_out[i] = b[i];                     \
+    }                                                                                                                 \
+    /* which: 0 grid_delta, 1 sigma_grid_delta, 2 hist_delta, 3 hist_gauss_delta; dir 0 = read into buf, 1 = write from buf */ \
+    void orc_grid_delta_io_##SFX(void* g, int which, int dir, double* buf) {                                          \
+        auto* m = (MetaGrid<S>*)g; const size_t G = m->grid.size();                                                   \
+        for (size_t i = 0; i < G; ++i) {                                                                              \
+            if (which == 0) { if (dir) m->grid_delta[i] = (S)buf[i]; else buf[i] = m->grid_delta[i]; }                \
+            else if (which == 1) { if (dir) m->sigma_grid_delta[i] = (S)buf[i]; else buf[i] = m->sigma_grid_delta[i]; } \
+            else if (which == 2) { if (dir) m->hist_delta[i] = (unsigned)buf[i]; else buf[i] = m->hist_delta[i]; }    \
+            else { if (dir) m->hist_gauss_delta[i] = (unsigned)buf[i]; else buf[i] = m->hist_gauss_delta[i]; }        \
+        }                                                                                                             \
+    }                                                                                                                 \
+    /* forces: ncv pointers (float4 arrays of N particles) or null */                                                 \
+    void orc_grid_compute_sigma_##SFX(void* g, const float* const* forces, unsigned N, double sigma_g, double* sigma_inv_out) { \
+        auto* m = (MetaGrid<S>*)g; std::vector<const float*> f(forces, forces + m->vars.size());                      \
+        m->compute_sigma(f, N, (S)sigma_g);                                                                           \
+        for (size_t i = 0; i < m->sigma_inv.size(); ++i) sigma_inv_out[i] = m->sigma_inv[i];                          \
+    }                                                                                                                 \
+    void orc_grid_get_sigma_inv_##SFX(void* g, double* si) {                                                          \
+        auto* m = (MetaGrid<S>*)g; for (size_t i = 0; i < m->sigma_inv.size(); ++i) si[i] = m->sigma_inv[i];          \
+    }                                                                                                                 \
+    void orc_grid_set_sigma_inv_##SFX(void* g, const double* si) {                                                    \
+        auto* m = (MetaGrid<S>*)g; for (size_t i = 0; i < m->sigma_inv.size(); ++i) m->sigma_inv[i] = (S)si[i];       \
+    }                                                                                                                 \
     void orc_grid_get_##SFX(void* g, int which, double* out) { grid_get<S>(g, which, out); }                          \
     void orc_grid_scalars_##SFX(void* g, double* out4) { grid_scalars<S>(g, out4); }                                  \
     double orc_grid_interpolate_##SFX(void* g, const double* val, int reweight) { return grid_interp<S>(g, val, reweight); } \

@@ -689,7 +689,69 @@ template <class S> struct MetaGrid {
             grid_weight[g] /= fac;
         }
     }
-    // updateBiasPotential, grid branch, root rank, no file output: IntegratorMetaDynamics.cc:314-588
+    // computeSigma: IntegratorMetaDynamics.cc:1205-1294 (adaptive Gaussians).  force[i] = derivative array of CV i as left in
+    // its force array by computeDerivatives (Scalar4 per particle, bias factor 1), or null if the CV cannot compute
+    // derivatives (then its diagonal entry is sigma_i^2 and its off-diagonal entries are 0).  sigma_inv = inverse of the
+    // matrix of element-wise square roots -- a negative sum of products gives NaN, as in the reference.  Accumulation in
+    // Scalar, particle order.  (Eigen's inverse -> Gauss-Jordan with partial pivoting.)
+    void compute_sigma(const std::vector<const float*>& force, unsigned N, S sigma_g) {
+        const size_t d = vars.size();
+        std::vector<S> sigmasq(d * d, S(0));
+        for (size_t i = 0; i < d; ++i)
+            for (size_t j = 0; j < d; ++j) {
+                if (force[i] && force[j]) {
+                    for (unsigned n = 0; n < N; ++n) {
+                        const float* fi = force[i] + 4 * (size_t)n; const float* fj = force[j] + 4 * (size_t)n;
+                        sigmasq[i * d + j] += sigma_g * sigma_g * ((S)fi[0] * (S)fj[0] + (S)fi[1] * (S)fj[1] + (S)fi[2] * (S)fj[2]);
+                    }
+                } else if (i == j) sigmasq[i * d + j] = vars[i].sigma * vars[i].sigma;
+            }
+        std::vector<S> m(d * d), inv(d * d, S(0));
+        for (size_t k = 0; k < d * d; ++k) m[k] = std::sqrt(sigmasq[k]);
+        for (size_t i = 0; i < d; ++i) inv[i * d + i] = S(1);
+        for (size_t c = 0; c < d; ++c) {
+            size_t piv = c;
+            for (size_t r = c + 1; r < d; ++r) if (std::fabs(m[r * d + c]) > std::fabs(m[piv * d + c])) piv = r;
+            if (piv != c) for (size_t k = 0; k < d; ++k) { std::swap(m[piv * d + k], m[c * d + k]); std::swap(inv[piv * d + k], inv[c * d + k]); }
+            const S p = m[c * d + c];
+            for (size_t k = 0; k < d; ++k) { m[c * d + k] /= p; inv[c * d + k] /= p; }
+            for (size_t r = 0; r < d; ++r) {
+                if (r == c) continue;
+                const S f = m[r * d + c];
+                for (size_t k = 0; k < d; ++k) { m[r * d + k] -= f * m[c * d + k]; inv[r * d + k] -= f * inv[c * d + k]; }
+            }
+        }
+        sigma_inv = inv;
+    }
+    // updateBiasPotential, grid branch, root rank, no file output: IntegratorMetaDynamics.cc:314-588.  The two halves on
+    // either side of the multiple-walker all-reduce of the four delta arrays (:392-410) are separate functions so that
+    // tests can put the sum over walkers in between; update() = both, one walker.
+    void update_deposit(unsigned timestep, const std::vector<S>& cur) {
+        unsigned idx;
+        if (bin_of(cur, idx)) hist_delta[idx]++;                       // updateHistogram
+        if (add_bias && (timestep % stride == 0)) {
+            if (bin_of(cur, idx)) { sigma_grid_delta[idx] += sigma_det(); hist_gauss_delta[idx]++; }   // updateSigmaGrid
+            S scal = S(1.0);
+            if (well_tempered) { S V = interpolate(cur, false); scal = std::exp(-V / T_shift); }
+            deposit(cur, scal);
+        }
+    }
+    void update_merge(unsigned timestep, const std::vector<S>& cur, std::vector<S>& bias) {
+        size_t d = vars.size();
+        bias.assign(d, S(0.0));
+        if (add_bias && (timestep % stride == 0)) {
+            reweight();
+            for (size_t g = 0; g < grid.size(); ++g) {
+                grid[g] += grid_delta[g]; sigma_grid[g] += sigma_grid_delta[g];
+                hist[g] += hist_delta[g]; hist_gauss[g] += hist_gauss_delta[g];
+                grid_delta[g] = S(0.0); sigma_grid_delta[g] = S(0.0); hist_delta[g] = 0; hist_gauss_delta[g] = 0;
+            }
+            num_gaussians++;
+        }
+        for (unsigned i = 0; i < d; ++i) bias[i] = derivative(i, cur);
+        curr_bias_potential = interpolate(cur, false);
+        curr_reweight = interpolate(cur, true);
+    }
     void update(unsigned timestep, const std::vector<S>& cur, std::vector<S>& bias) {
         size_t d = vars.size();
         bias.assign(d, S(0.0));

@@ -71,6 +71,12 @@ def lib():
                                              C.c_uint, C.c_int, C.c_int]
             g("orc_grid_destroy").argtypes = [C.c_void_p]
             g("orc_grid_update").argtypes = [C.c_void_p, C.c_uint, _dp, _dp]
+            g("orc_grid_update_deposit").argtypes = [C.c_void_p, C.c_uint, _dp]
+            g("orc_grid_update_merge").argtypes = [C.c_void_p, C.c_uint, _dp, _dp]
+            g("orc_grid_delta_io").argtypes = [C.c_void_p, C.c_int, C.c_int, _dp]
+            g("orc_grid_compute_sigma").argtypes = [C.c_void_p, C.POINTER(_fp), C.c_uint, C.c_double, _dp]
+            g("orc_grid_set_sigma_inv").argtypes = [C.c_void_p, _dp]
+            g("orc_grid_get_sigma_inv").argtypes = [C.c_void_p, _dp]
             g("orc_grid_get").argtypes = [C.c_void_p, C.c_int, _dp]
             g("orc_grid_scalars").argtypes = [C.c_void_p, _dp]
             g("orc_grid_interpolate").restype = C.c_double
@@ -241,6 +247,44 @@ class Grid:
         out = np.empty(self.G, dtype=np.float64)
         _fn("orc_grid_get", self.prec)(self.h, self.ARR[name], _d(out))
         return out
+
+    # the two halves of updateBiasPotential on either side of the multiple-walker all-reduce (IntegratorMetaDynamics.cc:392-410)
+    def update_deposit(self, timestep, cv_vals):
+        cur = np.ascontiguousarray(cv_vals, dtype=np.float64)
+        _fn("orc_grid_update_deposit", self.prec)(self.h, int(timestep), _d(cur))
+
+    def update_merge(self, timestep, cv_vals):
+        cur = np.ascontiguousarray(cv_vals, dtype=np.float64)
+        out = np.empty(self.d, dtype=np.float64)
+        _fn("orc_grid_update_merge", self.prec)(self.h, int(timestep), _d(cur), _d(out))
+        return out
+
+    DELTAS = ("grid_delta", "sigma_grid_delta", "hist_delta", "hist_gauss_delta")
+
+    def get_deltas(self):
+        out = np.empty((4, self.G), dtype=np.float64)
+        for k in range(4):
+            _fn("orc_grid_delta_io", self.prec)(self.h, k, 0, _d(out[k]))
+        return out
+
+    def set_deltas(self, arr):
+        arr = np.ascontiguousarray(arr, dtype=np.float64)
+        for k in range(4):
+            _fn("orc_grid_delta_io", self.prec)(self.h, k, 1, _d(arr[k]))
+
+    def compute_sigma(self, forces, sigma_g):
+        """computeSigma (adaptive Gaussians): forces = list of (N,4) float32 derivative arrays, None for a CV that cannot
+        compute derivatives; returns and installs sigma_inv (d x d)."""
+        arrs = [None if f is None else np.ascontiguousarray(f, dtype=np.float32) for f in forces]
+        n = next(a.shape[0] for a in arrs if a is not None) if any(a is not None for a in arrs) else 0
+        ptrs = (_fp * self.d)(*[(a.ctypes.data_as(_fp) if a is not None else _fp()) for a in arrs])
+        out = np.empty(self.d * self.d, dtype=np.float64)
+        _fn("orc_grid_compute_sigma", self.prec)(self.h, ptrs, n, float(sigma_g), _d(out))
+        return out.reshape(self.d, self.d)
+
+    def set_sigma_inv(self, m):
+        m = np.ascontiguousarray(m, dtype=np.float64)
+        _fn("orc_grid_set_sigma_inv", self.prec)(self.h, _d(m))
 
     def scalars(self):
         out = np.empty(4, dtype=np.float64)

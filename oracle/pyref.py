@@ -149,6 +149,29 @@ def grid_sequence(cv_min, cv_max, num_points, sigma, cv_values, timesteps, W=1.0
     return out
 
 
+def grid_adaptive(cv_min, cv_max, num_points, sigma, grads, can, sigma_g, cv_values, timesteps, W=1.0, T_shift=1.0, T=1.0, stride=1,
+                  well_tempered=False, prec="f64"):
+    """IntegratorMetaDynamics with adaptive Gaussians: prescribed CV values and gradients (grads: (ncv, N, 4) float32)."""
+    a, b, s_ = (np.ascontiguousarray(v, np.float64) for v in (cv_min, cv_max, sigma))
+    n = np.ascontiguousarray(num_points, np.uint32)
+    d = len(n)
+    G = int(np.prod(n))
+    g = np.ascontiguousarray(grads, np.float32)
+    N = g.shape[1]
+    cani = np.ascontiguousarray(can, np.int32)
+    vals = np.ascontiguousarray(cv_values, np.float64).reshape(-1, d)
+    ts = np.ascontiguousarray(timesteps, np.uint32)
+    bias = np.empty_like(vals)
+    sinv = np.empty((len(ts), d, d))
+    grid, sgrid = np.empty(G), np.empty(G)
+    rc = lib(prec).ref_grid_adaptive(d, _d(a), _d(b), n.ctypes.data_as(_up), _d(s_), C.c_double(W), C.c_double(T_shift), C.c_double(T),
+                                     C.c_uint(stride), int(well_tempered), C.c_double(sigma_g), g.ctypes.data_as(C.POINTER(C.c_float)),
+                                     cani.ctypes.data_as(C.POINTER(C.c_int)), C.c_uint(N), _d(vals), ts.ctypes.data_as(_up), len(ts),
+                                     _d(bias), _d(sinv), _d(grid), _d(sgrid))
+    assert rc == 0
+    return dict(bias=bias, sigma_inv=sinv, grid=grid, sigma_grid=sgrid)
+
+
 def test2d_files(directory, restart=False, prec="f64"):
     """The reference's test/test_2d.py scenario through the reference's own IntegratorMetaDynamics / Density / AspectRatio,
     including the files they write into `directory` (grid dumps, hills log); returns num_gaussians."""

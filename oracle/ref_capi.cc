@@ -50,6 +50,23 @@ class PrescribedCV : public CollectiveVariable {
     Scalar getCurrentValue(unsigned int) { return m_value; }
     Scalar m_value;
 };
+// a CV with a prescribed value AND a prescribed gradient: computeBiasForces (called by computeDerivatives with bias = 1)
+// leaves bias * gradient in the force array, which is what IntegratorMetaDynamics::computeSigma reads
+class GradientCV : public CollectiveVariable {
+  public:
+    GradientCV(std::shared_ptr<SystemDefinition> sysdef, const std::string& name, const float* grad4, unsigned N, bool can)
+        : CollectiveVariable(sysdef, name), m_value(0), m_grad(grad4, grad4 + 4 * (size_t)N), m_can(can) {}
+    Scalar getCurrentValue(unsigned int) { return m_value; }
+    virtual bool canComputeDerivatives() { return m_can; }
+    virtual void computeBiasForces(unsigned int) {
+        ArrayHandle<Scalar4> h(m_force, access_location::host, access_mode::overwrite);
+        for (size_t n = 0; n < m_grad.size() / 4; ++n)
+            h.data[n] = make_scalar4(m_bias * (Scalar)m_grad[4 * n], m_bias * (Scalar)m_grad[4 * n + 1], m_bias * (Scalar)m_grad[4 * n + 2], Scalar(0));
+    }
+    Scalar m_value;
+    std::vector<float> m_grad;
+    bool m_can;
+};
 template <class T, class U> void dump(const GPUArray<T>& a, U* out) {
     if (!out) return;
     ArrayHandle<T> h(a, access_location::host, access_mode::read);
@@ -184,6 +201,39 @@ int ref_grid_sequence(int ncv, const double* cv_min, const double* cv_max, const
         scalars3[0] = imd.m_curr_bias_potential; scalars3[1] = imd.m_curr_reweight; scalars3[2] = imd.m_num_gaussians;
         return 0;
     } catch (const std::exception& e) { fprintf(stderr, "ref_grid_sequence: %s\n", e.what()); return -1; }
+}
+
+// Adaptive Gaussians (setAdaptive(true), IntegratorMetaDynamics.cc:333-341, computeSigma :1205-1294) with prescribed CV
+// values and prescribed per-particle gradients: sigma_inv after every step, bias factors, final grid and sigma grid.
+int ref_grid_adaptive(int ncv, const double* cv_min, const double* cv_max, const unsigned* num_points, const double* sigma, double W,
+                      double T_shift, double T, unsigned stride, int well_tempered, double sigma_g, const float* grads /* [ncv][N][4] */,
+                      const int* can, unsigned N, const double* cv_values, const unsigned* timesteps, int nsteps, double* bias_out,
+                      double* sigma_inv_out /* [nsteps][ncv*ncv] */, double* grid, double* sigma_grid) {
+    try {
+        const double L[3] = {10, 10, 10}, tilt[3] = {0, 0, 0};
+        std::vector<float> pt(4 * (size_t)N, 0.f);
+        auto sys = make_system(pt.data(), N, L, tilt, 1);
+        IntegratorMetaDynamics imd(sys, Scalar(0.005), (Scalar)W, (Scalar)T_shift, (Scalar)T, stride, true, "", false,
+                                   well_tempered ? IntegratorMetaDynamics::mode_well_tempered : IntegratorMetaDynamics::mode_standard);
+        std::vector<std::shared_ptr<GradientCV> > cvs;
+        for (int i = 0; i < ncv; ++i) {
+            cvs.push_back(std::shared_ptr<GradientCV>(new GradientCV(sys, "cv" + std::to_string(i), grads + 4 * (size_t)N * i, N, can[i] != 0)));
+            imd.registerCollectiveVariable(cvs.back(), (Scalar)sigma[i], (Scalar)cv_min[i], (Scalar)cv_max[i], num_points[i]);
+        }
+        imd.setGrid(true);
+        imd.setAdaptive(true);
+        imd.setSigmaG((Scalar)sigma_g);
+        for (int s = 0; s < nsteps; ++s) {
+            for (int i = 0; i < ncv; ++i) cvs[i]->m_value = (Scalar)cv_values[(size_t)s * ncv + i];
+            if (s == 0) imd.prepRun(timesteps[s]);
+            else imd.updateBiasPotential(timesteps[s]);
+            for (int i = 0; i < ncv; ++i) bias_out[(size_t)s * ncv + i] = cvs[i]->m_bias;
+            ArrayHandle<Scalar> h(imd.m_sigma_inv, access_location::host, access_mode::read);
+            for (int k = 0; k < ncv * ncv; ++k) sigma_inv_out[(size_t)s * ncv * ncv + k] = h.data[k];
+        }
+        dump(imd.m_grid, grid); dump(imd.m_sigma_grid, sigma_grid);
+        return 0;
+    } catch (const std::exception& e) { fprintf(stderr, "ref_grid_adaptive: %s\n", e.what()); return -1; }
 }
 
 // The reference's test/test_2d.py scenario through the reference's own classes, files and all: one particle, Density +

@@ -163,6 +163,21 @@ for name, cfg in GRID:
             out["%s_wt%d_%s" % (name, wt, k)] = r[k]
         out["%s_wt%d_scalars" % (name, wt)] = np.array([r["bias_potential"], r["reweight"], r["num_gaussians"]])
 
+# adaptive Gaussians: computeSigma from prescribed per-particle gradients (all CVs differentiable; one that is not)
+rng = np.random.default_rng(77)
+NA = 50
+cfg = dict(cv_min=[0.0, 0.0], cv_max=[1.0, 2.0], num_points=[20, 30], sigma=[0.25, 0.1])
+g0 = np.abs(rng.normal(0.0, 0.05, (NA, 4))).astype(np.float32)          # positive components: the reference takes sqrt of the
+g1 = np.abs(rng.normal(0.0, 0.08, (NA, 4))).astype(np.float32)          # off-diagonal sums (NaN otherwise -- restated, not tested)
+out["ad_grads"] = np.stack([g0, g1])
+vals = [[0.3 + 0.02 * t, 1.0 + 0.03 * t] for t in range(8)]
+out["ad_vals"] = np.array(vals)
+for tag, can in (("ad_all", [1, 1]), ("ad_one", [1, 0])):
+    r = pyref.grid_adaptive(cfg["cv_min"], cfg["cv_max"], cfg["num_points"], cfg["sigma"], out["ad_grads"], can, 0.7, vals, list(range(8)),
+                            W=0.8, T_shift=7.0, T=1.3, stride=2, well_tempered=True)
+    for k in ("bias", "sigma_inv", "grid", "sigma_grid"):
+        out["%s_%s" % (tag, k)] = r[k]
+
 # WellTemperedEnsemble (CPU branch of the reference's own class): CV and the scaling of net force / torque / virial
 rng = np.random.default_rng(41)
 NW = 777

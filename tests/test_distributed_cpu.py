@@ -278,6 +278,61 @@ def _wte_worker(rank, world, port, N, out_q):
         dist.destroy_process_group()
 
 
+class OracleWalkerGrid:
+    """CPU stand-in with the interface of ops.BiasGrid's walker methods, on the oracle's restated updateBiasPotential."""
+
+    def __init__(self, po, torch, cfg, kw):
+        self.o, self.torch, self.stride = po.Grid(**cfg, **kw), torch, kw["stride"]
+
+    def step_deposit(self, t, cv):
+        self.o.update_deposit(t, cv)
+
+    def is_deposit_step(self, t):
+        return t % self.stride == 0
+
+    def deltas_export(self):
+        d = self.o.get_deltas()
+        return self.torch.from_numpy(np.ascontiguousarray(d[:2]).reshape(-1)), self.torch.from_numpy(np.ascontiguousarray(d[2:]).astype(np.int32).reshape(-1))
+
+    def deltas_import(self, dd, du):
+        G = self.o.G
+        self.o.set_deltas(np.concatenate([dd.numpy().reshape(2, G), du.numpy().astype(np.float64).reshape(2, G)]))
+
+    def step_merge(self, t, cv):
+        return self.o.update_merge(t, cv)
+
+
+WALKER_CFG = dict(cv_min=[0.0, 0.0], cv_max=[1.0, 2.0], num_points=[20, 30], sigma=[0.25, 0.1])
+WALKER_KW = dict(W=0.8, T_shift=7.0, T=1.3, stride=3, well_tempered=True)
+
+
+def _walker_trajectory(world, steps=10):
+    rng = np.random.default_rng(5)
+    lo, hi = np.array(WALKER_CFG["cv_min"]), np.array(WALKER_CFG["cv_max"])
+    s = lo + (hi - lo) * rng.random((world, 2))
+    out = []
+    for _ in range(steps):
+        s = np.clip(s + 0.05 * (hi - lo) * rng.normal(size=(world, 2)), lo, hi - 1e-9)
+        out.append(s.copy())
+    return out
+
+
+def _walker_worker(rank, world, port, out_q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from metadynamics_plugin_b200 import sharded
+        from oracle import pyoracle as po
+        wb = sharded.WalkerBias(sharded.TorchComm(), OracleWalkerGrid(po, torch, WALKER_CFG, WALKER_KW))
+        bias = [np.array(wb.step(t, s[rank])) for t, s in enumerate(_walker_trajectory(world))]
+        out_q.put((rank, np.array(bias), wb.grid.o.get("grid"), wb.grid.o.get("hist"), wb.grid.o.get("reweighted")))
+    finally:
+        dist.destroy_process_group()
+
+
 def _run(worker, world, *args):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
@@ -335,3 +390,27 @@ def test_wte_sharded_driver_over_gloo(oracle, world):
         assert cv == pytest.approx(pe, rel=1e-12) and cv2 == cv
         np.testing.assert_allclose(scaled[:, :3], nf[part][:, :3] * np.float32(1.5), rtol=1e-6)
         np.testing.assert_array_equal(scaled[:, 3], nf[part][:, 3])
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_multiple_walkers_over_gloo(oracle, world):
+    """Multiple walkers, one process each (the reference's partitions): sharded.WalkerBias over a gloo group against the
+    serial statement of IntegratorMetaDynamics.cc:392-410 (all walkers in one process, deltas summed by hand)."""
+    res = _run(_walker_worker, world)
+    serial = [oracle.Grid(**WALKER_CFG, **WALKER_KW) for _ in range(world)]
+    bias = [[] for _ in range(world)]
+    for t, s in enumerate(_walker_trajectory(world)):
+        for k in range(world):
+            serial[k].update_deposit(t, s[k])
+        if t % WALKER_KW["stride"] == 0:
+            tot = sum(o.get_deltas() for o in serial)
+            for o in serial:
+                o.set_deltas(tot)
+        for k in range(world):
+            bias[k].append(serial[k].update_merge(t, s[k]))
+    for rank, b, grid, hist, rew in res:
+        np.testing.assert_allclose(b, np.array(bias[rank]), rtol=1e-12, atol=1e-300)
+        np.testing.assert_allclose(grid, serial[rank].get("grid"), rtol=1e-12, atol=1e-300)
+        np.testing.assert_array_equal(hist, serial[rank].get("hist"))
+        np.testing.assert_allclose(rew, serial[rank].get("reweighted"), rtol=1e-12)
+    np.testing.assert_array_equal(res[0][2], res[1][2])        # every walker holds the same bias potential

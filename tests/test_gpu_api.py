@@ -187,6 +187,50 @@ def test_lamellar_metadynamics_steps(api, oracle):
         hoomd.run(1)
 
 
+def test_adaptive_gaussians_and_walker_exchange_through_the_api(api, oracle):
+    """integrate.mode_metadynamics.set_params(adaptive=True, sigma_g=..., multiple_walkers=True) with two Lamellar CVs: on
+    deposit steps the integrator calls computeDerivatives of both CVs, sums the products of their derivatives on the device
+    and installs the inverse sigma matrix (IntegratorMetaDynamics.cc:333-341, 1205-1294); the walker hook receives the four
+    delta arrays (here: one walker, the hook doubles them -- as if a second identical walker had deposited)."""
+    cv, integrate, hoomd = api
+    from metadynamics_plugin_b200 import workloads, sharded
+    w = workloads.c2(N=16384)
+    pt = w["postype"]
+    N = pt.shape[0]
+    hoomd.init.from_arrays(pt[:, :3], pt[:, 3].view(np.int32), ["A", "B"], w["L"])
+    meta = integrate.mode_metadynamics(dt=0.005, mode='well_tempered', stride=2, deltaT=7.0, W=1.0)
+    l1 = cv.lamellar(sigma=0.05, mode=dict(A=1.0, B=-1.0), lattice_vectors=[(0, 0, 3)], name="a")
+    l2 = cv.lamellar(sigma=0.07, mode=dict(A=1.0, B=-1.0), lattice_vectors=[(0, 3, 0), (3, 0, 0)], name="b")
+    l1.set_grid(cv_min=-2.0, cv_max=2.0, num_points=40)
+    l2.set_grid(cv_min=-2.0, cv_max=2.0, num_points=30)
+    meta.set_params(adaptive=True, sigma_g=0.3, multiple_walkers=True)
+    calls = []
+
+    def hook(ptr_d, n_d, ptr_u, n_u):
+        import torch
+        d, u = sharded.tensor_from_ptr(ptr_d, n_d, torch.float64), sharded.tensor_from_ptr(ptr_u, n_u, torch.int32)
+        calls.append((n_d, n_u, float(d[: n_d // 2].sum().item()), int(u.sum().item())))
+        d *= 2
+        u *= 2
+        torch.cuda.synchronize()
+    meta.cpp_integrator.walker_allreduce = hook
+    hoomd.run(2)                                          # timesteps 0 (prepRun), 1, 2: deposits at 0 and 2
+    # derivatives of both CVs from the oracle (force at bias 1), sigma matrix as the reference computes it
+    f1 = oracle.lamellar_forces(pt, N, [1.0, -1.0], [(0, 0, 3)], w["L"], 1.0).astype(np.float32)
+    f2 = oracle.lamellar_forces(pt, N, [1.0, -1.0], [(0, 3, 0), (3, 0, 0)], w["L"], 1.0).astype(np.float32)
+    o = oracle.Grid([-2.0, -2.0], [2.0, 2.0], [40, 30], [0.05, 0.07], W=1.0, T_shift=7.0, T=1.0, stride=2, well_tempered=True)
+    sinv = o.compute_sigma([f1, f2], 0.3)
+    got = np.array(meta.cpp_integrator.getSigmaInv()).reshape(2, 2)
+    if np.all(np.isfinite(sinv)):
+        np.testing.assert_allclose(got, sinv, rtol=1e-4)
+    else:                                                 # a negative sum of products: NaN in the reference, NaN here
+        assert not np.all(np.isfinite(got))
+    assert len(calls) == 2 and calls[0][0] == 2 * 40 * 30 and calls[0][1] == 2 * 40 * 30
+    assert calls[0][3] == 2                               # hist_delta and hist_gauss_delta of the first deposit: one count each
+    assert meta.cpp_integrator.getNumGaussians() == 2
+    assert np.array(meta.cpp_integrator.getGridArray("hist_gauss")).sum() == 4       # "two walkers" x two deposits
+
+
 def test_api_error_behaviour(api):
     cv, integrate, hoomd = api
     hoomd.init.from_arrays(np.zeros((8, 3), np.float32), np.zeros(8, np.int32), ["A", "B"], 5.0)
@@ -229,3 +273,65 @@ def test_potential_energy_cv(api, oracle):
     pe.cpp_force.compute(1)
     np.testing.assert_allclose(pd.getNetForce()[:, :3], nf[:, :3] * 1.25, rtol=1e-6)
     np.testing.assert_array_equal(pd.getNetForce()[:, 3], nf[:, 3])
+
+
+def test_collective_wrapper(api, oracle):
+    """cv.wrap (CollectiveWrapper.cc): CV = potential energy of the wrapped force (sum of force.w + its external energy);
+    computeBiasForces scales the wrapped force's own force, torque (all four components) and virial by the bias factor."""
+    cv, integrate, hoomd = api
+    N = 3000
+    rng = np.random.default_rng(12)
+    hoomd.init.from_arrays(rng.random((N, 3)) - 0.5, np.zeros(N, np.int32), ["A"], 4.0)
+    f4 = rng.normal(size=(N, 4)).astype(np.float32)
+    t4 = rng.normal(size=(N, 4)).astype(np.float32)
+    vir = rng.normal(size=(6, N)).astype(np.float32)
+    pair = hoomd.prescribed_force(f4, t4, vir, external_energy=0.75, name="pair")
+    w = cv.wrap(pair, sigma=2.0)
+    assert w.cpp_force.getName() == "cv_pair"
+    val = w.cpp_force.getCurrentValue(1)
+    assert val == pytest.approx(float(f4[:, 3].astype(np.float64).sum()) + 0.75, rel=1e-6)
+    assert val == pytest.approx(oracle.wte_pe(f4, 0.75), rel=1e-6)
+    w.cpp_force.setBiasFactor(0.4)
+    w.cpp_force.compute(1)
+    got = pair.cpp_force.getForces()
+    np.testing.assert_allclose(got[:, :3], f4[:, :3] * np.float32(0.4), rtol=1e-6)
+    np.testing.assert_array_equal(got[:, 3], f4[:, 3])                      # the energy column is not scaled
+    np.testing.assert_allclose(pair.cpp_force.getTorques(), t4 * np.float32(0.4), rtol=1e-6)       # torque: x, y, z AND w
+    pitch = pair.cpp_force.getVirialPitch()
+    np.testing.assert_allclose(pair.cpp_force.getVirial().reshape(6, pitch)[:, :N], vir * np.float32(0.4), rtol=1e-6)
+    with pytest.raises(RuntimeError):
+        cv.wrap("not a force")
+
+
+def test_umbrella_reaches_the_host_side_cvs(api, oracle):
+    """the factor handed to computeBiasForces is the integrator's dV/ds PLUS the umbrella increment
+    (CollectiveVariable.cc:22-66) -- also for the CVs whose bias "force" is a host-side external virial (AspectRatio,
+    Density) and for the external-virial part of WellTemperedEnsemble."""
+    cv, integrate, hoomd = api
+    L = (10.0, 12.0, 9.0)
+    sd = hoomd.init.from_arrays(np.zeros((4, 3), np.float32), np.zeros(4, np.int32), ["A"], L)
+    integrate.mode_standard(dt=0.001)
+    ar = cv.aspect_ratio(dir1=0, dir2=1)
+    ar.set_params(umbrella='harmonic', cv0=0.7, kappa=5.0)
+    dn = cv.density()
+    dn.set_params(umbrella='linear', scale=3.0)
+    hoomd.run(1)
+    val = oracle.aspect_value(L, 0, 1)
+    bias = oracle.umbrella_bias("harmonic", val, 0.0, cv0=0.7, kappa=5.0)
+    assert bias != 0.0
+    got = np.array([ar.cpp_force.getExternalVirial(i) for i in range(6)])
+    np.testing.assert_allclose(got, oracle.aspect_virial(L, 0, 1, bias), rtol=1e-6)
+    gotd = np.array([dn.cpp_force.getExternalVirial(i) for i in range(6)])
+    np.testing.assert_allclose(gotd, oracle.density_virial(L, 4, oracle.umbrella_bias("linear", oracle.density_value(L, 4), 0.0, scale=3.0)), rtol=1e-6)
+    assert np.abs(gotd).max() > 0
+    # WellTemperedEnsemble: net force and external virial are scaled by the SAME factor 1 + bias (incl. the umbrella)
+    pe = cv.potential_energy(sigma=2.0)
+    pe.set_params(umbrella='linear', scale=0.25)
+    pd = sd.getParticleData()
+    nf = np.arange(16, dtype=np.float32).reshape(4, 4)
+    pd.setNetForce(nf)
+    for i in range(6):
+        pd.setExternalVirial(i, float(i + 1))
+    pe.cpp_force.compute(5)
+    np.testing.assert_allclose(pd.getNetForce()[:, :3], nf[:, :3] * np.float32(1.25), rtol=1e-6)
+    np.testing.assert_allclose([pd.getExternalVirial(i) for i in range(6)], 1.25 * np.arange(1, 7.0), rtol=1e-6)

@@ -660,6 +660,91 @@ def test_bias_grid_against_reference_vectors(gpu, name, wt):
     assert sc["bias_potential"] == pytest.approx(ref[0], rel=1e-10, abs=1e-14) and sc["reweight"] == pytest.approx(ref[1], rel=1e-10)
 
 
+@pytest.mark.parametrize("well_tempered", [False, True])
+def test_bias_grid_multiple_walkers(gpu, oracle, well_tempered):
+    """Multiple walkers (IntegratorMetaDynamics.cc:392-410): three walkers with their own CV trajectories share one bias --
+    on deposit steps the four delta arrays are summed over the walkers between the Gaussian deposit and the merge.  Device:
+    metad_grid_step_deposit / deltas_export -> sum -> deltas_import / metad_grid_step_merge; oracle: the same two halves of
+    the restated updateBiasPotential with the sum in between."""
+    import torch
+    cfg = dict(cv_min=[0.0, 0.0], cv_max=[1.0, 2.0], num_points=[20, 30], sigma=[0.25, 0.1])
+    kw = dict(W=0.8, T_shift=7.0, T=1.3, stride=3, well_tempered=well_tempered)
+    nw = 3
+    gs = [gpu.BiasGrid(**cfg, **kw) for _ in range(nw)]
+    os_ = [oracle.Grid(**cfg, **kw) for _ in range(nw)]
+    rng = np.random.default_rng(17)
+    lo, hi = np.array(cfg["cv_min"]), np.array(cfg["cv_max"])
+    s = lo + (hi - lo) * rng.random((nw, 2))
+    for t in range(11):
+        s = np.clip(s + 0.05 * (hi - lo) * rng.normal(size=(nw, 2)), lo, hi - 1e-9)
+        cvs = [torch.tensor(s[k], dtype=torch.float64, device="cuda") for k in range(nw)]
+        # device walkers
+        for k in range(nw):
+            gs[k].step_deposit(t, cvs[k])
+        if gs[0].is_deposit_step(t):
+            exported = [tuple(x.clone() for x in g.deltas_export()) for g in gs]
+            dd = torch.stack([e[0] for e in exported]).sum(0)
+            du = torch.stack([e[1] for e in exported]).sum(0).to(torch.int32)
+            for g in gs:
+                g.deltas_import(dd, du)
+        b = [gs[k].step_merge(t, cvs[k]).cpu().numpy().copy() for k in range(nw)]
+        # oracle walkers
+        for k in range(nw):
+            os_[k].update_deposit(t, s[k])
+        if t % 3 == 0:
+            tot = sum(o.get_deltas() for o in os_)
+            for o in os_:
+                o.set_deltas(tot)
+        bo = [os_[k].update_merge(t, s[k]) for k in range(nw)]
+        for k in range(nw):
+            np.testing.assert_allclose(b[k], bo[k], rtol=1e-9, atol=1e-12)
+    for k in range(nw):
+        for name in ("grid", "reweighted", "weight", "sigma_grid"):
+            np.testing.assert_allclose(gs[k].get(name), os_[k].get(name), rtol=1e-10, atol=1e-300, err_msg=name)
+        for name in ("hist", "hist_gauss", "hist_delta"):
+            assert np.array_equal(gs[k].get(name), os_[k].get(name).astype(np.uint32)), name
+    # every walker ends with the same bias potential, and it holds all nw x 4 Gaussians
+    np.testing.assert_array_equal(gs[0].get("grid"), gs[1].get("grid"))
+    assert gs[0].get("hist_gauss").sum() == nw * 4
+    # one walker, the two halves back to back == the fused step
+    a, b2 = gpu.BiasGrid(**cfg, **kw), gpu.BiasGrid(**cfg, **kw)
+    for t in range(5):
+        c = torch.tensor(s[0] * (1 - 0.05 * t), dtype=torch.float64, device="cuda")
+        ba = a.step(t, c).cpu().numpy().copy()
+        bb = b2.step_walkers(t, c, lambda x: None).cpu().numpy().copy()
+        np.testing.assert_array_equal(ba, bb)
+    np.testing.assert_array_equal(a.get("grid"), b2.get("grid"))
+
+
+@pytest.mark.parametrize("tag,can", [("ad_all", (1, 1)), ("ad_one", (1, 0))])
+def test_bias_grid_adaptive_gaussians_against_reference_vectors(gpu, tag, can):
+    """Adaptive Gaussians against the REFERENCE's own integrator (tests/golden/ref_golden.npz, prescribed CV gradients): the
+    device sums of products (metad_force_dot), the inverse sigma matrix installed with metad_grid_set_sigma_inv, then the
+    bias factors after every step and the final grid / sigma grid."""
+    import torch
+    G = _ref_gold()
+    cfg = dict(cv_min=[0.0, 0.0], cv_max=[1.0, 2.0], num_points=[20, 30], sigma=[0.25, 0.1])
+    g = gpu.BiasGrid(**cfg, W=0.8, T_shift=7.0, T=1.3, stride=2, well_tempered=True)
+    grads = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in G["ad_grads"]]
+    sigma_g = 0.7
+    for t, v in enumerate(G["ad_vals"]):
+        if t % 2 == 0:
+            sq = np.zeros((2, 2))
+            for i in range(2):
+                for j in range(2):
+                    if can[i] and can[j]:
+                        sq[i, j] = gpu.force_dot(grads[i], grads[j], sigma_g ** 2).cpu().item()
+                    elif i == j:
+                        sq[i, j] = cfg["sigma"][i] ** 2
+            sinv = np.linalg.inv(np.sqrt(sq))
+            np.testing.assert_allclose(sinv, G[tag + "_sigma_inv"][t], rtol=1e-6)      # gradients are float32 products summed in fp64
+            g.set_sigma_inv(sinv)
+        b = g.step(t, torch.tensor(v, dtype=torch.float64, device="cuda")).cpu().numpy()
+        np.testing.assert_allclose(b, G[tag + "_bias"][t], rtol=1e-5, atol=1e-12)
+    np.testing.assert_allclose(g.get("grid"), G[tag + "_grid"], rtol=1e-5, atol=1e-300)
+    np.testing.assert_allclose(g.get("sigma_grid"), G[tag + "_sigma_grid"], rtol=1e-6, atol=1e-300)
+
+
 def test_bias_grid_restart_and_flags(gpu, oracle):
     import torch
     cfg = dict(cv_min=[0.0, 0.0], cv_max=[1.0, 2.0], num_points=[20, 30], sigma=[0.25, 0.1])

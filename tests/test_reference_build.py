@@ -114,6 +114,33 @@ def test_oracle_bias_grid_reproduces_reference(oracle, name, wt):
     assert sc["bias_potential"] == ref[0] and sc["reweight"] == ref[1] and sc["num_gaussians"] == int(ref[2])
 
 
+@pytest.mark.parametrize("tag,can", [("ad_all", (1, 1)), ("ad_one", (1, 0))])
+def test_oracle_adaptive_gaussians_reproduce_reference(oracle, tag, can):
+    """Adaptive Gaussians (IntegratorMetaDynamics.cc:333-341 + computeSigma :1205-1294) through the reference's own integrator
+    with prescribed values and per-particle gradients: sigma_inv after every step, bias factors, final grid / sigma grid."""
+    cfg = dict(cv_min=[0.0, 0.0], cv_max=[1.0, 2.0], num_points=[20, 30], sigma=[0.25, 0.1])
+    o = oracle.Grid(**cfg, W=0.8, T_shift=7.0, T=1.3, stride=2, well_tempered=True)
+    grads = GOLD["ad_grads"]
+    forces = [grads[i] if can[i] else None for i in range(2)]
+    for t, v in enumerate(GOLD["ad_vals"]):
+        if t % 2 == 0:
+            o.compute_sigma(forces, 0.7)
+        b = o.update(t, v)
+        np.testing.assert_allclose(b, GOLD[tag + "_bias"][t], rtol=1e-12, atol=1e-300)
+        np.testing.assert_allclose(o_sigma_inv(o), GOLD[tag + "_sigma_inv"][t], rtol=1e-12)
+    np.testing.assert_allclose(o.get("grid"), GOLD[tag + "_grid"], rtol=1e-12, atol=1e-300)
+    np.testing.assert_allclose(o.get("sigma_grid"), GOLD[tag + "_sigma_grid"], rtol=1e-12, atol=1e-300)
+
+
+def o_sigma_inv(o):
+    """current sigma_inv of an oracle grid (re-installing it is the identity)."""
+    import ctypes as C
+    from oracle import pyoracle as po
+    out = np.empty(o.d * o.d)
+    po._fn("orc_grid_get_sigma_inv", o.prec)(o.h, out.ctypes.data_as(C.POINTER(C.c_double)))
+    return out.reshape(o.d, o.d)
+
+
 def test_live_reference_build_matches_oracle(oracle):
     """Where the reference is mounted: build it and compare on fresh random inputs (more particles, more faces)."""
     from oracle import pyref
