@@ -78,7 +78,7 @@ int metad_lamellar_forces(metad_lamellar* p, const float* d_postype, float* d_fo
  * ---------------------------------------------------------------------------------------------- */
 typedef struct metad_mesh metad_mesh;
 
-/* nx,ny,nz: mesh points (powers of two, 8..1024 each); mode: ntypes per-type coefficients. */
+/* nx,ny,nz: mesh points (powers of two, 32 <= nx <= 1024, 16 <= ny,nz <= 512); mode: ntypes per-type coefficients. */
 int metad_mesh_create(metad_mesh** out, unsigned nx, unsigned ny, unsigned nz, int ntypes, const double* mode);
 int metad_mesh_destroy(metad_mesh* p);
 
@@ -91,6 +91,13 @@ int metad_mesh_cv(metad_mesh* p, const float* d_postype, unsigned N, unsigned N_
 /* interpolateForces for the positions last passed to metad_mesh_cv; bias read from *d_bias. */
 int metad_mesh_forces(metad_mesh* p, const float* d_postype, float* d_force, unsigned N, unsigned N_global,
                       const metad_box* box, const double* d_bias, metad_stream_t stream);
+
+/* Kernel table of cv.mesh.set_kernel (OrderParameterMesh::setTable / setUseTable, OrderParameterMesh.cc:148-189): only the
+ * derivative table dK enters the hot path, through the k-space virial (computeVirial, :970-1050).  n entries on
+ * [k_min, k_max]; n == 0 only switches use_table.  With metad_mesh_set(p, 13, 1) the fused z sweep of metad_mesh_cv also
+ * accumulates the virial sums and the arg-max of |f_k|^2 (computeQmax, :1108-1179); metad_mesh_get(p, 10, double[12])
+ * returns them: virial xx, xy, xz, yy, yz, zz (to be multiplied by the bias factor), q_max x, y, z, sq_max, flat index, |f|^2. */
+int metad_mesh_set_table(metad_mesh* p, const double* dK, unsigned n, double k_min, double k_max, int use_table);
 
 /* Multi-GPU: z-slab decomposition (reference: HOOMD domain decomposition + CommunicatorGrid ghost exchange + dfft,
  * OrderParameterMesh.cc:231-315, 659-746).  Rank r of n_ranks owns the planes [r nz/P, (r+1) nz/P) and the particles

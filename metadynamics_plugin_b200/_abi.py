@@ -56,6 +56,7 @@ SIGNATURES = {
     "metad_lamellar_forces": (C.c_int, [_vp, _vp, _vp, C.c_uint, C.c_uint, _boxp, _vp, _vp]),
     "metad_mesh_create": (C.c_int, [C.POINTER(_vp), C.c_uint, C.c_uint, C.c_uint, C.c_int, _dp]),
     "metad_mesh_destroy": (C.c_int, [_vp]),
+    "metad_mesh_set_table": (C.c_int, [_vp, C.POINTER(C.c_double), C.c_uint, C.c_double, C.c_double, C.c_int]),
     "metad_mesh_cv": (C.c_int, [_vp, _vp, C.c_uint, C.c_uint, _boxp, _vp, _vp]),
     "metad_mesh_forces": (C.c_int, [_vp, _vp, _vp, C.c_uint, C.c_uint, _boxp, _vp, _vp]),
     "metad_mesh_slab_create": (C.c_int, [C.POINTER(_vp), C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_int, _dp]),

@@ -78,6 +78,18 @@ struct metad_mesh {
     bool cache = true;
     bool tma_flush = true;          // knob 10: flush the spread tile with 3-D tensor-map reductions
     int spread_debug = 0;           // knob 12: timing experiments (wrong results)
+    // knob 13: epilogues of the fused z sweep -- arg-max of |f_k|^2 (q*_max / sq_max log quantities, computeQmax) and the
+    // k-space virial sums (computeVirial) with the tabulated kernel derivative of metad_mesh_set_table
+    bool extras = false;
+    bool use_table = false;
+    unsigned n_table = 0;
+    float* d_table_d = nullptr;
+    double k_min = 0, k_max = 0;
+    double* d_vir_partials = nullptr;
+    unsigned long long* d_amax_key = nullptr;
+    double* d_extras_out = nullptr;
+    double box_L[3] = {0, 0, 0};
+    unsigned extras_N_global = 0;
     bool tma_gather = true;         // knob 11: load the gather tile with one 3-D tensor-map copy when it does not wrap
     alignas(64) CUtensorMap tmap_mesh = {};     // integer mesh (incl. ghost planes), box = padded tile
     alignas(64) CUtensorMap tmap_inv = {};      // Re IFFT(G) (d_buf), box = padded tile
@@ -274,6 +286,23 @@ template <int L> int run_z(metad_mesh* p, float2* buf, unsigned row_len, unsigne
         for (unsigned r = 0; r < p->n_ranks; ++r) cp.cv_arena[r] = p->peers.arena[r];
         cp.cv_off = p->lay.cv; cp.cv_n = p->n_ranks; cp.cv_rank = p->rank;
     }
+    cp.extras = p->extras ? 1 : 0;
+    cp.use_table = (p->use_table && p->d_table_d && p->n_table >= 2) ? 1 : 0;
+    cp.n_table = p->n_table; cp.table_d = p->d_table_d;
+    cp.k_min = (float)p->k_min; cp.k_max = (float)p->k_max;
+    cp.delta_k = p->n_table >= 2 ? (float)((p->k_max - p->k_min) / (double)(p->n_table - 1)) : 1.0f;
+    for (int i = 0; i < 3; ++i) cp.bk[i] = (float)(2.0 * M_PI / p->box_L[i]);
+    cp.vir_partials = p->d_vir_partials; cp.amax_key = p->d_amax_key; cp.extras_out = p->d_extras_out;
+    if (p->extras) {
+        if (!p->d_vir_partials) {
+            METAD_CUDA(cudaMalloc(&p->d_vir_partials, sizeof(double) * 6 * p->n_partials));
+            METAD_CUDA(cudaMalloc(&p->d_amax_key, sizeof(unsigned long long)));
+            METAD_CUDA(cudaMalloc(&p->d_extras_out, sizeof(double) * 8));
+            cp.vir_partials = p->d_vir_partials; cp.amax_key = p->d_amax_key; cp.extras_out = p->d_extras_out;
+        }
+        METAD_CUDA(cudaMemsetAsync(p->d_amax_key, 0, sizeof(unsigned long long), st));
+        p->extras_N_global = N_global;
+    }
     const unsigned nblocks = cp.n_blocks_plane0 + (row_len / kLines) * ny;
     // experiment (METAD_Z_CTAS=4): four CTAs per SM (32 registers) instead of three (40 registers) for 512-thread CTAs
     static const bool four = getenv("METAD_Z_CTAS") && atoi(getenv("METAD_Z_CTAS")) == 4;
@@ -356,6 +385,7 @@ int set_box(metad_mesh* p, const metad_box* box) {
     }
     for (int i = 0; i < 3; ++i) METAD_REQUIRE(box->L[i] > 0.0, "cv.mesh: box lengths must be positive");
     geom_set_box(p->g, box->L);          // the box is the GLOBAL box
+    for (int i = 0; i < 3; ++i) p->box_L[i] = box->L[i];
     return METAD_OK;
 }
 
@@ -590,7 +620,8 @@ metad_mesh::GraphKey make_key(metad_mesh* p, const void* postype, unsigned N, un
     k.postype = postype; k.N = N; k.N_global = N_global;
     for (int i = 0; i < 3; ++i) k.L[i] = box->L[i];
     k.d_cv = d_cv; k.stream = stream; k.kind = kind; k.keep_rho = p->keep_rho; k.keep_cells = p->keep_cells;
-    k.variant = (p->wide ? 1 : 0) | (p->cache ? 2 : 0) | (p->tma_flush ? 4 : 0) | (p->tma_gather ? 8 : 0);
+    k.variant = (p->wide ? 1 : 0) | (p->cache ? 2 : 0) | (p->tma_flush ? 4 : 0) | (p->tma_gather ? 8 : 0) | (p->extras ? 16 : 0) | (p->use_table ? 32 : 0) |
+                (int)(p->n_table << 8);
     return k;
 }
 
@@ -778,7 +809,7 @@ extern "C" int metad_mesh_destroy(metad_mesh* p) {
     cudaFree(p->d_mesh_alloc); cudaFree(p->d_buf); cudaFree(p->d_fx); cudaFree(p->d_tile_sums); cudaFree(p->d_counters);
     if (p->h_counters) cudaFreeHost(p->h_counters);
     if (p->h_mode) cudaFreeHost(p->h_mode);
-    cudaFree(p->d_mesh64);
+    cudaFree(p->d_mesh64); cudaFree(p->d_table_d); cudaFree(p->d_vir_partials); cudaFree(p->d_amax_key); cudaFree(p->d_extras_out);
     cudaFree(p->d_rho_keep); cudaFree(p->d_twx); cudaFree(p->d_twy); cudaFree(p->d_twz); cudaFree(p->d_sums);
     cudaFree(p->d_partials); cudaFree(p->d_ticket);
     cudaFree(p->d_sums_global); cudaFree(p->d_cv_partial); cudaFree(p->d_p2p_status); cudaFree(p->d_epoch); cudaFree(p->d_sync);
@@ -1178,6 +1209,24 @@ extern "C" int metad_mesh_slab_p2p_forces(metad_mesh* p, const float* d_postype,
     return launch_gather(p, d_postype, (const float*)(p->arena + p->lay.ghost_inv), d_force, N_global, box, d_bias, stream);
 }
 
+extern "C" int metad_mesh_set_table(metad_mesh* p, const double* dK, unsigned n, double k_min, double k_max, int use_table) {
+    METAD_REQUIRE(p, "metad_mesh_set_table: null plan");
+    if (n) {
+        METAD_REQUIRE(dK, "metad_mesh_set_table: null table");
+        METAD_REQUIRE(n >= 2 && k_min >= 0.0 && k_max > k_min, "cv.mesh kmin, kmax is invalid");
+        std::vector<float> t(n);
+        for (unsigned i = 0; i < n; ++i) t[i] = (float)dK[i];
+        METAD_CUDA(cudaDeviceSynchronize());
+        cudaFree(p->d_table_d); p->d_table_d = nullptr;
+        METAD_CUDA(cudaMalloc(&p->d_table_d, sizeof(float) * (n + 1)));
+        METAD_CUDA(cudaMemset(p->d_table_d, 0, sizeof(float) * (n + 1)));
+        METAD_CUDA(cudaMemcpy(p->d_table_d, t.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
+        p->n_table = n; p->k_min = k_min; p->k_max = k_max;
+    }
+    p->use_table = use_table != 0;
+    return METAD_OK;
+}
+
 extern "C" int metad_mesh_get(metad_mesh* p, int which, void* h_out) {
     METAD_REQUIRE(p && h_out, "metad_mesh_get: null argument");
     METAD_CUDA(cudaDeviceSynchronize());
@@ -1236,6 +1285,36 @@ extern "C" int metad_mesh_get(metad_mesh* p, int which, void* h_out) {
             out[0] = (double)p->n_rebuilds; out[1] = c[4]; out[2] = c[5]; out[3] = c[6]; out[4] = fx[0]; out[5] = p->calls_since_rebuild;
             return METAD_OK;
         }
+        case 10: {  // epilogues of the last metad_mesh_cv with knob 13 on, double[12]: k-space virial sums xx, xy, xz, yy, yz, zz (times the
+                    // bias factor = external virial), q_max x, y, z, sq_max (computeQmax: arg-max over ALL k including k = 0, times N),
+                    // flat index of the arg-max, its |f|^2
+            if (!p->extras || !p->d_extras_out || !p->have_cv) { set_error("metad_mesh_get: no epilogue results (metad_mesh_set(p, 13, 1) before metad_mesh_cv)"); return METAD_ERR_STATE; }
+            if (p->g.slab) { set_error("metad_mesh_get: q_max / virial epilogues are available on unsharded plans only"); return METAD_ERR_UNSUPPORTED; }
+            double* out = (double*)h_out;
+            unsigned long long key = 0;
+            double sums[4];
+            METAD_CUDA(cudaMemcpy(out, p->d_extras_out, sizeof(double) * 6, cudaMemcpyDeviceToHost));
+            METAD_CUDA(cudaMemcpy(&key, p->d_amax_key, sizeof key, cudaMemcpyDeviceToHost));
+            METAD_CUDA(cudaMemcpy(sums, p->d_sums, sizeof(double) * 3, cudaMemcpyDeviceToHost));
+            unsigned vb = (unsigned)(key >> 32), flat = 0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFu);
+            float amp;
+            memcpy(&amp, &vb, 4);
+            // the mean density is removed before the transforms: the k = 0 mode, f_0 = sum a / N, competes analytically; it wins
+            // ties (flat index 0 comes first in the reference's scan)
+            const double ng = (double)p->extras_N_global, f0 = sums[1] / ng;
+            double a = (double)amp;
+            if (key == 0 || f0 * f0 >= a) { a = f0 * f0; flat = 0; }
+            if (!(a > 0.0)) flat = 0;
+            const unsigned nx = p->g.nx, ny = p->g.ny, nz = p->nzg;
+            const unsigned kx = flat % nx, ky = (flat / nx) % ny, kz = flat / (nx * ny);
+            out[6] = a > 0.0 ? (double)miller(kx, nx) * 2.0 * M_PI / p->box_L[0] : 0.0;
+            out[7] = a > 0.0 ? (double)miller(ky, ny) * 2.0 * M_PI / p->box_L[1] : 0.0;
+            out[8] = a > 0.0 ? (double)miller(kz, nz) * 2.0 * M_PI / p->box_L[2] : 0.0;
+            out[9] = a * ng;
+            out[10] = (double)flat;
+            out[11] = a;
+            return METAD_OK;
+        }
         case 9: {   // accumulator width, unsigned[2]: {in use: 0 = 32-bit, 1 = 64-bit (wide); asked for by the last rebuild: 1 / 2 / 3, see metad_mesh::wide}
             unsigned* out = (unsigned*)h_out;
             out[0] = p->wide ? 1u : 0u; out[1] = p->h_mode[0];
@@ -1277,6 +1356,8 @@ extern "C" int metad_mesh_set(metad_mesh* p, int key, long value) {
         case 10: p->tma_flush = value != 0; return METAD_OK;
         case 11: p->tma_gather = value != 0; return METAD_OK;
         case 12: p->spread_debug = (int)value; return METAD_OK;
+        case 13: p->extras = value != 0; return METAD_OK;
+        case 14: p->use_table = value != 0; return METAD_OK;
         default: set_error("metad_mesh_set: unknown key"); return METAD_ERR_INVALID;
     }
 }

@@ -39,7 +39,54 @@ struct ConvParams {
     char* cv_arena[kMaxPeers];
     size_t cv_off;
     unsigned cv_n, cv_rank;
+    // optional epilogues on the spectrum f = F/N while it is in shared memory (metad_mesh_set key 13; off by default):
+    //   * arg-max of |f_k|^2 over all k (computeQmax, OrderParameterMesh.cc:1108-1179: the q*_max / sq_max log quantities)
+    //   * the k-space virial sums (computeVirial, :970-1050) with the tabulated derivative of the convolution kernel
+    int extras;
+    int use_table;
+    unsigned n_table;
+    const float* table_d;         // device: derivative table dK(k), n_table entries on [k_min, k_max]
+    float k_min, k_max, delta_k;
+    float bk[3];                  // 2 pi / L per axis: k = Miller index * bk (orthorhombic box)
+    double* vir_partials;         // [blocks][6]
+    unsigned long long* amax_key; // packed {|f|^2 bits, ~flat index}: atomicMax over the blocks
+    double* extras_out;           // [6] virial sums (without the bias factor)
 };
+
+// accumulators of the optional epilogues, one per thread
+struct ExtraAcc { double v[6]; unsigned long long key; };
+MHD void extra_init(ExtraAcc& a) { for (int i = 0; i < 6; ++i) a.v[i] = 0.0; a.key = 0ull; }
+MHD int miller(unsigned k, unsigned n) { return (int)k - (k >= n / 2 + n % 2 ? (int)n : 0); }
+// one stored mode (kx, ky, kz) with |f|^2 = val; weight = 2 when its mirror image -k is not stored
+MHD void extra_add(ExtraAcc& a, const ConvParams& cp, float val, unsigned kx, unsigned ky, unsigned kz, float weight) {
+    // arg-max: ties between k and -k (equal by symmetry) go to the smaller flat index x + nx (y + ny z), like the
+    // reference's ascending scan with a strict comparison
+    const unsigned fk = kx + cp.nx * (ky + cp.ny * kz);
+    const unsigned fm = (cp.nx - kx) % cp.nx + cp.nx * ((cp.ny - ky) % cp.ny + cp.ny * ((cp.nz - kz) % cp.nz));
+    const unsigned flat = weight > 1.5f ? (fk < fm ? fk : fm) : fk;
+    unsigned vb;
+#ifdef __CUDA_ARCH__
+    vb = __float_as_uint(val);
+#else
+    memcpy(&vb, &val, 4);
+#endif
+    const unsigned long long key = ((unsigned long long)vb << 32) | (unsigned long long)(0xFFFFFFFFu - flat);
+    if (key > a.key) a.key = key;
+    if (cp.use_table && fk != 0) {
+        const float k0 = (float)miller(kx, cp.nx) * cp.bk[0], k1 = (float)miller(ky, cp.ny) * cp.bk[1], k2 = (float)miller(kz, cp.nz) * cp.bk[2];
+        const float knorm = sqrtf(k0 * k0 + k1 * k1 + k2 * k2);
+        if (knorm >= cp.k_min && knorm < cp.k_max) {
+            const float vf = (knorm - cp.k_min) / cp.delta_k;
+            const unsigned vi = (unsigned)vf;
+            const float d0 = cp.table_d[vi], d1 = cp.table_d[vi + 1];
+            const float val_D = d0 + (vf - (float)vi) * (d1 - d0);
+            // rhog = |f|^4 / N^2 (the reference divides the already normalised f by N twice more), kfac = dK / (2 |k|)
+            const double rk = (double)weight * (double)val * (double)val * (double)cp.inv_n * (double)cp.inv_n * (double)val_D / (2.0 * (double)knorm);
+            a.v[0] += rk * k0 * k0; a.v[1] += rk * k0 * k1; a.v[2] += rk * k0 * k2;
+            a.v[3] += rk * k1 * k1; a.v[4] += rk * k1 * k2; a.v[5] += rk * k2 * k2;
+        }
+    }
+}
 
 // chi for one dimension: [k < ceil(n/2)] (non-negative Miller index), OrderParameterMesh.cc:417-422
 MHD bool nonneg(unsigned k, unsigned n) { return k < n / 2 + n % 2; }
@@ -409,10 +456,27 @@ fft_y_kernel(float2* __restrict__ buf, const float2* __restrict__ g_tw, unsigned
 }
 
 // energy partial -> per-block slot; the last block of the LAST kernel (main z pass) sums all slots in order
-__device__ __forceinline__ void energy_block_finish(double e, const ConvParams& cp) {
+__device__ __forceinline__ void energy_block_finish(double e, const ConvParams& cp, const ExtraAcc* xa = nullptr) {
     __shared__ double red[32];
+    __shared__ unsigned long long kred[32];
     __shared__ bool is_last;
     const unsigned slot = blockIdx.x, total_slots = gridDim.x;
+    if (cp.extras && xa) {
+        for (int c = 0; c < 6; ++c) {
+            const double r = block_sum(xa->v[c], red);
+            if (threadIdx.x == 0) cp.vir_partials[6 * (size_t)slot + c] = r;
+        }
+        unsigned long long k = xa->key;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const unsigned long long y = __shfl_xor_sync(0xffffffffu, k, o); k = y > k ? y : k; }
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) kred[threadIdx.x >> 5] = k;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (unsigned w = 1; w < (blockDim.x + 31) / 32; ++w) k = kred[w] > k ? kred[w] : k;
+            atomicMax(cp.amax_key, k);
+        }
+    }
     const double r = block_sum(e, red);
     if (threadIdx.x == 0) cp.partials[slot] = r;
     if (threadIdx.x == 0) {
@@ -425,6 +489,14 @@ __device__ __forceinline__ void energy_block_finish(double e, const ConvParams& 
     double s = 0.0;
     for (unsigned b = threadIdx.x; b < total_slots; b += blockDim.x) s += __ldcg(cp.partials + b);
     s = block_sum(s, red);
+    if (cp.extras) {
+        for (int c = 0; c < 6; ++c) {
+            double v = 0.0;
+            for (unsigned b = threadIdx.x; b < total_slots; b += blockDim.x) v += __ldcg(cp.vir_partials + 6 * (size_t)b + c);
+            v = block_sum(v, red);
+            if (threadIdx.x == 0) cp.extras_out[c] = v;
+        }
+    }
     if (threadIdx.x == 0) {
         *cp.d_cv = 0.5 * s;      // sum *= 1/2, OrderParameterMesh.cc:905
         *cp.ticket = 0;
@@ -462,10 +534,16 @@ __device__ __forceinline__ void z_general_body(float2* __restrict__ buf, const f
     const float d = (float)(0.5 * (*cp.d_mode_sq) / nd / nd);
     const bool ky_nonneg = nonneg(ky, ny);
     double e = 0.0;
+    ExtraAcc xa;
+    extra_init(xa);
     for (int idx = threadIdx.x; idx < kLines * L; idx += nthr) {
         const int ww = idx & (kLines - 1);
         const unsigned kz = idx / kLines;
         if (cp.kx_off + kx0 + ww == 0) continue;
+        if (cp.extras) {
+            const float fr = tile[idx].x * cp.inv_n, fi = tile[idx].y * cp.inv_n;
+            extra_add(xa, cp, fr * fr + fi * fi, cp.kx_off + kx0 + ww, ky, kz, 2.0f);
+        }
         tile[idx] = conv_general(tile[idx], cp.inv_n, d, ky_nonneg && nonneg(kz, L), e);
     }
     __syncthreads();
@@ -479,7 +557,7 @@ __device__ __forceinline__ void z_general_body(float2* __restrict__ buf, const f
         if (has_col0 && w2 == 0) dst[1] = make_float2(v.z, v.w);
         else *reinterpret_cast<float4*>(dst) = v;
     }
-    energy_block_finish(e, cp);
+    energy_block_finish(e, cp, &xa);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -515,6 +593,8 @@ __device__ __forceinline__ void z_plane0_body(float2* __restrict__ buf, const fl
     const double nd = cp.n_global;
     const float d = (float)(0.5 * (*cp.d_mode_sq) / nd / nd);
     double e = 0.0;
+    ExtraAcc xa;
+    extra_init(xa);
     float2 outv[per_thread];
 #pragma unroll
     for (int it = 0; it < per_thread; ++it) {
@@ -526,6 +606,14 @@ __device__ __forceinline__ void z_plane0_body(float2* __restrict__ buf, const fl
         const unsigned ky = (ww & 1) ? pky : kyp;
         const bool valid = kyp <= ny / 2;
         const bool counted = valid && (!(ww & 1) || pky != kyp);
+        if (cp.extras && counted) {
+            // the kx = 0 mode A and the kx = nx/2 mode B of this (ky, kz), untangled as in conv_plane0
+            const float2 z1 = tile[idx], z2 = cconj(tile[((L - kz) % L) * kLines + (ww ^ 1)]);
+            const float ar = 0.5f * (z1.x + z2.x) * cp.inv_n, ai = 0.5f * (z1.y + z2.y) * cp.inv_n;
+            const float br = 0.5f * (z1.y - z2.y) * cp.inv_n, bi = -0.5f * (z1.x - z2.x) * cp.inv_n;
+            extra_add(xa, cp, ar * ar + ai * ai, 0u, ky, kz, 1.0f);
+            extra_add(xa, cp, br * br + bi * bi, cp.nx / 2, ky, kz, 1.0f);
+        }
         outv[it] = conv_plane0(tile[idx], tile[((L - kz) % L) * kLines + (ww ^ 1)], cp.inv_n, d, ky, kz, ny, L, counted, e);
     }
     __syncthreads();
@@ -542,7 +630,7 @@ __device__ __forceinline__ void z_plane0_body(float2* __restrict__ buf, const fl
         const unsigned ky = (ww & 1) ? pky : kyp;
         buf[(size_t)ky * nxh + (size_t)l * zstride] = tile[idx];
     }
-    energy_block_finish(e, cp);
+    energy_block_finish(e, cp, &xa);
 }
 
 // one launch: blocks [0, n_blocks_plane0) untangle the kx = 0 slot, the rest are (kx tile, ky) blocks of the general case

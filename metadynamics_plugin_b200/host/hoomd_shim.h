@@ -123,6 +123,10 @@ class ParticleData {
     void setExternalEnergy(Scalar e) { m_external_energy = e; }
     Scalar getExternalVirial(unsigned i) const { return m_external_virial[i]; }
     void setExternalVirial(unsigned i, Scalar v) { m_external_virial[i] = v; }
+    // PDataFlags pressure_tensor / isotropic_virial (set by an NPT integrator or a pressure log in HOOMD): force computes
+    // evaluate their virial only when one of them is set (e.g. OrderParameterMesh.cc:1062-1067)
+    bool getPressureFlag() const { return m_pressure_flag; }
+    void setPressureFlag(bool f) { m_pressure_flag = f; }
     std::shared_ptr<ExecutionConfiguration> getExecConf() const { return m_exec; }
 
   private:
@@ -133,6 +137,7 @@ class ParticleData {
     DeviceArray<Scalar4> m_pos, m_net_force, m_net_torque;
     DeviceArray<Scalar> m_net_virial;
     Scalar m_external_energy = 0;
+    bool m_pressure_flag = false;
     Scalar m_external_virial[6];
 };
 

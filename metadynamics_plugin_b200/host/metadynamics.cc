@@ -170,6 +170,36 @@ void OrderParameterMeshGPU::setTable(const std::vector<Scalar>& K, const std::ve
         throw std::runtime_error("Error setting up OrderParameterMesh");
     }
     m_k_min = kmin; m_k_max = kmax; m_table = K; m_table_d = d_K;
+    std::vector<double> dk(d_K.begin(), d_K.end());
+    metad_check(metad_mesh_set_table(m_plan, dk.data(), (unsigned)dk.size(), (double)kmin, (double)kmax, m_use_table ? 1 : 0), "metad_mesh_set_table");
+}
+void OrderParameterMeshGPU::setUseTable(bool use_table) {
+    m_use_table = use_table;
+    metad_check(metad_mesh_set_table(m_plan, nullptr, 0, 0.0, 0.0, use_table ? 1 : 0), "metad_mesh_set_table");
+}
+// the arg-max of |f_k|^2 and the virial sums are epilogues of the fused z sweep; they are switched on (for good) the first
+// time a log quantity or the pressure asks for them, and the current step is re-evaluated with them
+void OrderParameterMeshGPU::enableExtras() {
+    if (m_extras) return;
+    metad_check(metad_mesh_set(m_plan, 13, 1), "metad_mesh_set");
+    m_extras = true;
+    m_is_first_step = true;                // forces a re-evaluation of the current step
+}
+void OrderParameterMeshGPU::computeQmax(unsigned int timestep) {
+    enableExtras();
+    getCurrentValueDevice(timestep);
+    if (timestep && m_q_max_last_computed == timestep) return;
+    m_q_max_last_computed = timestep;
+    double out[12];
+    metad_check(metad_mesh_get(m_plan, 10, out), "metad_mesh_get");
+    for (int i = 0; i < 3; ++i) m_q_max[i] = (Scalar)out[6 + i];
+    m_sq_max = (Scalar)out[9];
+}
+void OrderParameterMeshGPU::computeVirial() {
+    double out[12];
+    metad_check(metad_mesh_get(m_plan, 10, out), "metad_mesh_get");
+    const Scalar bias = biasHost();
+    for (int i = 0; i < 6; ++i) m_external_virial[i] = bias * (Scalar)out[i];
 }
 
 const double* OrderParameterMeshGPU::getCurrentValueDevice(unsigned int timestep) {
@@ -188,21 +218,29 @@ Scalar OrderParameterMeshGPU::getCurrentValue(unsigned int timestep) {
     cuda_check(cudaMemcpy(&v, m_d_scalars.data() + 2, sizeof(double), cudaMemcpyDeviceToHost), "cv download");
     return (Scalar)v;
 }
-// OrderParameterMesh.cc:1052-1075 (virial: external virial stays zero, pressure flags are not modelled by the shim)
+// OrderParameterMesh.cc:1052-1075: forces; the k-space virial only when the pressure is asked for (PDataFlags).  Without a
+// kernel table the virial of the reference is identically zero (val_D = 0, :1011-1030): nothing to compute then.
 void OrderParameterMeshGPU::computeBiasForces(unsigned int timestep) {
+    const bool want_virial = m_pdata->getPressureFlag() && m_use_table && !m_table_d.empty();
+    if (want_virial) enableExtras();
     if (m_is_first_step || m_cv_last_updated != timestep) getCurrentValueDevice(timestep);
     const metad_box box = m_pdata->getBox().pod();
     metad_check(metad_mesh_forces(m_plan, (const float*)m_pdata->getPositions().data(), (float*)m_force.data(), m_pdata->getN(),
                                   m_pdata->getNGlobal(), &box, biasDevice(), stream_of(m_exec_conf)), "metad_mesh_forces");
-    for (auto& v : m_external_virial) v = Scalar(0.0);
+    if (want_virial) computeVirial();
+    else for (auto& v : m_external_virial) v = Scalar(0.0);
 }
 std::vector<std::string> OrderParameterMeshGPU::getProvidedLogQuantities() {
     auto l = CollectiveVariable::getProvidedLogQuantities();
-    l.push_back("cv_mesh");
+    for (const char* n : {"cv_mesh", "qx_max", "qy_max", "qz_max", "sq_max"}) l.push_back(n);      // OrderParameterMesh.cc:118-122
     return l;
 }
 Scalar OrderParameterMeshGPU::getLogValue(const std::string& quantity, unsigned int timestep) {
     if (quantity == "cv_mesh") return getCurrentValue(timestep);
+    if (quantity == "qx_max") { computeQmax(timestep); return m_q_max[0]; }
+    if (quantity == "qy_max") { computeQmax(timestep); return m_q_max[1]; }
+    if (quantity == "qz_max") { computeQmax(timestep); return m_q_max[2]; }
+    if (quantity == "sq_max") { computeQmax(timestep); return m_sq_max; }
     return CollectiveVariable::getLogValue(quantity, timestep);
 }
 

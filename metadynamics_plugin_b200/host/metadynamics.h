@@ -100,14 +100,19 @@ class OrderParameterMeshGPU : public CollectiveVariable {
     std::vector<std::string> getProvidedLogQuantities() override;
     Scalar getLogValue(const std::string& quantity, unsigned int timestep) override;
     void setTable(const std::vector<Scalar>& K, const std::vector<Scalar>& d_K, Scalar kmin, Scalar kmax);
-    void setUseTable(bool use_table) { m_use_table = use_table; }
+    void setUseTable(bool use_table);
 
   protected:
     void computeBiasForces(unsigned int timestep) override;
 
+    void computeQmax(unsigned int timestep);       // OrderParameterMesh.cc:1108-1179
+    void computeVirial();                          // OrderParameterMesh.cc:970-1050
+    void enableExtras();
+
     metad_mesh* m_plan = nullptr;
-    bool m_is_first_step = true, m_use_table = false;
-    unsigned int m_cv_last_updated = 0;
+    bool m_is_first_step = true, m_use_table = false, m_extras = false;
+    unsigned int m_cv_last_updated = 0, m_q_max_last_computed = 0;
+    Scalar m_q_max[3] = {0, 0, 0}, m_sq_max = 0;
     std::vector<Scalar> m_table, m_table_d;
     Scalar m_k_min = 0, m_k_max = 0;
 };

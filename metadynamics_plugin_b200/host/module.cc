@@ -67,6 +67,8 @@ PYBIND11_MODULE(_metadynamics, m) {
         .def("setNetTorque", [](ParticleData& p, const farray& a) { upload4(p.getNetTorqueArray(), a); })
         .def("getNetTorque", [](ParticleData& p) { return download4(p.getNetTorqueArray()); })
         .def("setExternalEnergy", &ParticleData::setExternalEnergy)
+        .def("setPressureFlag", &ParticleData::setPressureFlag)
+        .def("getPressureFlag", &ParticleData::getPressureFlag)
         .def("getExternalVirial", &ParticleData::getExternalVirial)
         .def("setExternalVirial", &ParticleData::setExternalVirial)
         .def("positionsPointer", [](ParticleData& p) { return (size_t)p.getPositions().data(); });

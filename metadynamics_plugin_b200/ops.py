@@ -154,6 +154,17 @@ class Mesh:
                     fx_scale=float(out[4]), calls_since_rebuild=int(out[5]))
 
 
+    def set_table(self, dK, k_min, k_max, use_table=True):
+        """Tabulated derivative of the convolution kernel (cv.mesh.set_kernel): enters the k-space virial only."""
+        a, ap = _np_d(dK)
+        check(lib.metad_mesh_set_table(self.h, ap, len(a), float(k_min), float(k_max), int(use_table)))
+
+    def extras(self):
+        """Epilogues of the last compute_cv with set(13, 1): dict(virial[6] (per unit bias factor), q_max[3], sq_max, flat)."""
+        out = np.empty(12, dtype=np.float64)
+        check(lib.metad_mesh_get(self.h, 10, out.ctypes.data_as(C.c_void_p)))
+        return dict(virial=out[:6].copy(), q_max=out[6:9].copy(), sq_max=float(out[9]), flat=int(out[10]), amplitude=float(out[11]))
+
     def accumulator(self):
         """Width of the density accumulators: {"wide": 64-bit accumulation in use, "requested": what the cell loads of the
         last rebuild of the tile order ask for (1 = 32 bits suffice, 2 = 64 bits, 3 = beyond the range)}."""

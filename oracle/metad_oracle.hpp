@@ -391,6 +391,40 @@ template <class S> struct MeshCV {
     }
 
     // computeQmax: OrderParameterMesh.cc:1108-1179 (log quantities q*_max, sq_max)
+    // computeVirial: OrderParameterMesh.cc:970-1050.  k-space virial of the bias: only the derivative table of the
+    // convolution kernel enters (val_D = 0 without a table, or outside [k_min, k_max)); `fourier` is f = F/N here (it is
+    // divided by N once more, twice, as written); flat index 0 excluded; result = bias * sum.
+    void virial(const std::vector<S>& table_d, S k_min, S k_max, bool use_table, S bias, S out6[6]) const {
+        V3<S> b1, b2, b3;
+        reciprocal(box, true, b1, b2, b3);
+        const S delta_k = (k_max - k_min) / S(table_d.size() - 1);
+        S vir[6] = {0, 0, 0, 0, 0, 0};
+        for (unsigned cell = 1; cell < M; ++cell) {
+            unsigned wz = cell / (ny * nx), wy = (cell - wz * nx * ny) / nx, wx = cell % nx;
+            int n_x = (int)wx, n_y = (int)wy, n_z = (int)wz;
+            if (n_x >= (int)(nx / 2 + nx % 2)) n_x -= (int)nx;
+            if (n_y >= (int)(ny / 2 + ny % 2)) n_y -= (int)ny;
+            if (n_z >= (int)(nz / 2 + nz % 2)) n_z -= (int)nz;
+            const V3<S> k = (S)n_x * b1 + (S)n_y * b2 + (S)n_z * b3;
+            const S ksq = dot(k, k), knorm = std::sqrt(ksq);
+            S kfac = S(1.0) / S(2.0) / knorm;
+            S val_D(0.0);
+            if (use_table && knorm >= k_min && knorm < k_max) {
+                const S value_f = (knorm - k_min) / delta_k;
+                const unsigned value_i = (unsigned)value_f;
+                const S dK0 = table_d[value_i], dK1 = table_d[value_i + 1];
+                const S f = value_f - S(value_i);
+                val_D = dK0 + f * (dK1 - dK0);
+            }
+            kfac *= val_D;
+            const S a2 = fourier[cell].real() * fourier[cell].real() + fourier[cell].imag() * fourier[cell].imag();
+            const S val = a2 / (S)N_global;
+            const S rhog = a2 * val / (S)N_global;
+            vir[0] += rhog * kfac * k.x * k.x; vir[1] += rhog * kfac * k.x * k.y; vir[2] += rhog * kfac * k.x * k.z;
+            vir[3] += rhog * kfac * k.y * k.y; vir[4] += rhog * kfac * k.y * k.z; vir[5] += rhog * kfac * k.z * k.z;
+        }
+        for (int i = 0; i < 6; ++i) out6[i] = bias * vir[i];
+    }
     void qmax(S out4[4]) const {
         V3<S> b1, b2, b3;
         reciprocal(box, true, b1, b2, b3);

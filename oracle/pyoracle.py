@@ -62,6 +62,7 @@ def lib():
             g("orc_mesh_mode_sq").restype = C.c_double
             g("orc_mesh_mode_sq").argtypes = [C.c_void_p]
             g("orc_mesh_qmax").argtypes = [C.c_void_p, _dp]
+            g("orc_mesh_virial").argtypes = [C.c_void_p, _dp, C.c_uint, C.c_double, C.c_double, C.c_int, C.c_double, _dp]
             g("orc_mesh_set_literal_copysignf").argtypes = [C.c_void_p, C.c_int]
             g("orc_lamellar_cv").restype = C.c_double
             g("orc_lamellar_cv").argtypes = [_fp, C.c_uint, C.c_uint, _dp, C.c_int, _ip, C.c_int, _dp, _dp]
@@ -189,6 +190,13 @@ class Mesh:
 
     def mode_sq(self):
         return _fn("orc_mesh_mode_sq", self.prec)(self.h)
+
+    def virial(self, table_d, kmin, kmax, bias, use_table=True):
+        """computeVirial (k-space virial of the bias, OrderParameterMesh.cc:970-1050): external virial xx, xy, xz, yy, yz, zz."""
+        t = np.ascontiguousarray(table_d, dtype=np.float64)
+        out = np.empty(6, dtype=np.float64)
+        _fn("orc_mesh_virial", self.prec)(self.h, _d(t), len(t), float(kmin), float(kmax), int(use_table), float(bias), _d(out))
+        return out
 
     def qmax(self):
         out = np.empty(4, dtype=np.float64)

@@ -54,6 +54,20 @@ def mesh(dims, mode, L, postype, bias, prec="f64", tilt=(0, 0, 0)):
                 interp=interp.reshape(nz, ny, nx))
 
 
+def mesh_virial(dims, mode, L, postype, K, dK, kmin, kmax, bias, prec="f64", tilt=(0, 0, 0)):
+    """OrderParameterMesh::computeVirial of the reference with a kernel table: external virial (6)."""
+    nx, ny, nz = dims
+    mode = np.ascontiguousarray(mode, np.float64)
+    Lb, tb = _box(L, tilt)
+    pt = np.ascontiguousarray(postype, np.float32)
+    K, dK = np.ascontiguousarray(K, np.float64), np.ascontiguousarray(dK, np.float64)
+    out = np.empty(6)
+    rc = lib(prec).ref_mesh_virial(nx, ny, nz, _d(mode), len(mode), _d(Lb), _d(tb), pt.ctypes.data_as(_fp), pt.shape[0], _d(K), _d(dK), len(K),
+                                   C.c_double(kmin), C.c_double(kmax), C.c_double(bias), _d(out))
+    assert rc == 0
+    return out
+
+
 def mesh_qmax(dims, mode, L, postype, prec="f64", tilt=(0, 0, 0)):
     """OrderParameterMesh::computeQmax of the reference: array {q_max.x, q_max.y, q_max.z, sq_max}."""
     nx, ny, nz = dims

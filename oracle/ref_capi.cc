@@ -100,6 +100,25 @@ int ref_mesh(unsigned nx, unsigned ny, unsigned nz, const double* mode, unsigned
     } catch (const std::exception& e) { fprintf(stderr, "ref_mesh: %s\n", e.what()); return -1; }
 }
 
+// OrderParameterMesh::computeVirial with a kernel table (setTable + setUseTable): external virial for bias factor `bias`
+int ref_mesh_virial(unsigned nx, unsigned ny, unsigned nz, const double* mode, unsigned ntypes, const double* L, const double* tilt,
+                    const float* postype, unsigned N, const double* K, const double* dK, unsigned ntable, double kmin, double kmax,
+                    double bias, double* out6) {
+    try {
+        auto sys = make_system(postype, N, L, tilt, ntypes);
+        std::vector<Scalar> m(mode, mode + ntypes);
+        OrderParameterMesh op(sys, nx, ny, nz, m);
+        std::vector<Scalar> k(K, K + ntable), dk(dK, dK + ntable);
+        op.setTable(k, dk, (Scalar)kmin, (Scalar)kmax);
+        op.setUseTable(true);
+        op.getCurrentValue(1);
+        op.setBiasFactor((Scalar)bias);
+        op.computeVirial();
+        for (int i = 0; i < 6; ++i) out6[i] = op.getExternalVirial(i);
+        return 0;
+    } catch (const std::exception& e) { fprintf(stderr, "ref_mesh_virial: %s\n", e.what()); return -1; }
+}
+
 // OrderParameterMesh::computeQmax (the q*_max / sq_max log quantities): out4 = {q_max.x, q_max.y, q_max.z, sq_max}
 int ref_mesh_qmax(unsigned nx, unsigned ny, unsigned nz, const double* mode, unsigned ntypes, const double* L, const double* tilt,
                   const float* postype, unsigned N, double* out4) {

@@ -54,6 +54,8 @@ def mesh_case(seed, N, dims, L, modes):
 
 
 out = {}
+VIR_KMIN, VIR_KMAX, VIR_N = 0.5, 6.0, 64
+out["virial_table"] = np.array([VIR_KMIN, VIR_KMAX, VIR_N])
 MESH = [("m0", 11, 1500, (32, 16, 16), (10.0, 7.3, 5.1), (1.0,), 0.7),
         ("m1", 12, 3000, (32, 32, 32), (10.159366, 10.159366, 10.159366), (1.0, -1.0), -1.3),
         ("m2", 13, 2000, (64, 16, 32), (21.1, 6.0, 9.7), (1.0, -0.5, 2.0), 0.25)]
@@ -69,6 +71,10 @@ for name, seed, N, dims, L, modes, bias in MESH:
         if prec == "f64":
             out["%s_%s_inv" % (name, prec)] = r["inv"]
             out["%s_%s_qmax" % (name, prec)] = pyref.mesh_qmax(dims, modes, L, pt, prec)
+            # k-space virial with a kernel table (K is not used by the virial, its derivative dK is): dK(k) = -2 (k - 2) exp(-(k - 2)^2)
+            kt = np.linspace(VIR_KMIN, VIR_KMAX, VIR_N)
+            out["%s_%s_virial" % (name, prec)] = pyref.mesh_virial(dims, modes, L, pt, np.exp(-(kt - 2.0) ** 2), -2.0 * (kt - 2.0) * np.exp(-(kt - 2.0) ** 2),
+                                                                  VIR_KMIN, VIR_KMAX, bias, prec)
 
 # triclinic boxes and mesh sizes that are not powers of two: not on the device path yet, but the oracle must already be
 # right about them (keys t*: cfg = dims, L, tilt, bias, modes)

@@ -335,3 +335,38 @@ def test_umbrella_reaches_the_host_side_cvs(api, oracle):
     pe.cpp_force.compute(5)
     np.testing.assert_allclose(pd.getNetForce()[:, :3], nf[:, :3] * np.float32(1.25), rtol=1e-6)
     np.testing.assert_allclose([pd.getExternalVirial(i) for i in range(6)], 1.25 * np.arange(1, 7.0), rtol=1e-6)
+
+
+def test_mesh_log_quantities_and_pressure(api, oracle):
+    """cv.mesh log quantities qx_max, qy_max, qz_max, sq_max (OrderParameterMesh.cc:118-122, 1077-1106) and the k-space virial
+    that reaches the pressure when the engine asks for it and a kernel table is set (cv.mesh.set_kernel + use_table)."""
+    cv, integrate, hoomd = api
+    from metadynamics_plugin_b200 import workloads
+    N, L = 20000, 20.0
+    pos, types = workloads.diblock(N, L, 3, 4)
+    sd = hoomd.init.from_arrays(pos, types, ["A", "B"], L)
+    integrate.mode_standard(dt=0.001)
+    mesh = cv.mesh(nx=32, mode=dict(A=1.0, B=-1.0))
+    mesh.set_params(umbrella='linear', scale=0.8)
+    assert set(["cv_mesh", "qx_max", "qy_max", "qz_max", "sq_max"]) <= set(mesh.cpp_force.getProvidedLogQuantities())
+    pt = oracle.make_postype(pos.astype(np.float32), types)
+    o = oracle.Mesh(32, 32, 32, [1.0, -1.0], L, N, "f64")
+    o.current_value(pt)
+    qo = o.qmax()
+    assert mesh.cpp_force.getLogValue("sq_max", 1) == pytest.approx(qo[3], rel=1e-5)
+    got = np.array([mesh.cpp_force.getLogValue(k, 1) for k in ("qx_max", "qy_max", "qz_max")])
+    assert np.allclose(np.abs(got), np.abs(qo[:3]), rtol=1e-5, atol=1e-9)
+
+    def kernel(k, kmin, kmax, k0):
+        return np.exp(-(k - k0) ** 2), -2.0 * (k - k0) * np.exp(-(k - k0) ** 2)
+    mesh.set_kernel(kernel, 0.5, 6.0, 64, coeff=dict(k0=2.0))
+    mesh.set_params(use_table=True)
+    hoomd.run(1)                                   # pressure not asked for: the external virial stays zero (:1062-1071)
+    assert all(mesh.cpp_force.getExternalVirial(i) == 0.0 for i in range(6))
+    sd.getParticleData().setPressureFlag(True)
+    hoomd.run(1)
+    kt = np.linspace(0.5, 6.0, 64)
+    vo = o.virial(-2.0 * (kt - 2.0) * np.exp(-(kt - 2.0) ** 2), 0.5, 6.0, 0.8)
+    got = np.array([mesh.cpp_force.getExternalVirial(i) for i in range(6)])
+    assert np.abs(vo).max() > 0
+    np.testing.assert_allclose(got, vo, rtol=1e-4, atol=1e-5 * np.abs(vo).max())

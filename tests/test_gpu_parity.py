@@ -179,6 +179,66 @@ def test_mesh_against_reference_vectors(gpu, oracle, name):
     assert np.abs(f - fo).max() < 1e-5 * np.abs(fo).max()
 
 
+@pytest.mark.parametrize("name", ["m0", "m1", "m2"])
+def test_mesh_qmax_and_virial_against_reference_vectors(gpu, oracle, name):
+    """The epilogues of the fused z sweep (knob 13) against the REFERENCE's own computeQmax and computeVirial
+    (tests/golden/ref_golden.npz): q*_max / sq_max (arg-max of |f_k|^2 over all k INCLUDING k = 0, as the reference scans) and
+    the k-space virial with a tabulated kernel derivative."""
+    import torch
+    G = _ref_gold()
+    c = G[name + "_cfg"]
+    dims, L, bias, modes = tuple(int(v) for v in c[:3]), tuple(c[3:6]), float(c[6]), tuple(c[7:])
+    pt = G[name + "_postype"]
+    N = pt.shape[0]
+    kmin, kmax, n = G["virial_table"]
+    kt = np.linspace(kmin, kmax, int(n))
+    dK = -2.0 * (kt - 2.0) * np.exp(-(kt - 2.0) ** 2)
+    d_pt = torch.from_numpy(pt).cuda()
+    box = gpu.Box.make(L)
+    mesh = gpu.Mesh(*dims, modes)
+    mesh.set(13, 1)
+    mesh.set_table(dK, kmin, kmax)
+    cv = mesh.compute_cv(d_pt, N, box).cpu().item()
+    assert cv == pytest.approx(G[name + "_f64_cv"][0], rel=1e-6)          # the epilogues do not disturb the CV
+    x = mesh.extras()
+    ref_q = G[name + "_f64_qmax"]
+    assert x["sq_max"] == pytest.approx(ref_q[3], rel=2e-6)
+    q = x["q_max"]
+    assert np.allclose(q, ref_q[:3], rtol=1e-6, atol=1e-12) or np.allclose(q, -ref_q[:3], rtol=1e-6, atol=1e-12)     # k and -k tie by symmetry
+    ref_v = G[name + "_f64_virial"]
+    np.testing.assert_allclose(bias * x["virial"], ref_v, rtol=2e-5, atol=2e-6 * np.abs(ref_v).max())
+    # without the table the reference's virial is identically zero
+    mesh.set_table([], 0, 0, use_table=False)
+    mesh.compute_cv(d_pt, N, box)
+    assert np.all(mesh.extras()["virial"] == 0.0)
+    # and with the epilogues off the getter refuses instead of returning stale numbers
+    mesh.set(13, 0)
+    mesh.compute_cv(d_pt, N, box)
+    from metadynamics_plugin_b200._abi import MetadError
+    with pytest.raises(MetadError):
+        mesh.extras()
+
+
+def test_mesh_qmax_at_c3_size(gpu, oracle):
+    """q_max / sq_max on 128^3 with a lamellar-ordered two-type melt (the peak is a real structure-factor peak, not k = 0)."""
+    import torch
+    from metadynamics_plugin_b200 import workloads
+    N, L = 1 << 18, 64.0
+    pos, types = workloads.diblock(N, L, 5, 11)
+    pt = gpu.make_postype(pos, types)
+    h_pt = host_pt(oracle, pos.astype(np.float32), types)
+    mesh = gpu.Mesh(128, 128, 128, [1.0, -1.0])
+    mesh.set(13, 1)
+    mesh.compute_cv(pt, N, gpu.Box.make(L))
+    x = mesh.extras()
+    m = oracle.Mesh(128, 128, 128, [1.0, -1.0], L, N, "f64")
+    m.current_value(h_pt)
+    qo = m.qmax()
+    assert x["sq_max"] == pytest.approx(qo[3], rel=2e-6)
+    assert np.allclose(np.abs(x["q_max"]), np.abs(qo[:3]), rtol=1e-6, atol=1e-12)
+    assert abs(abs(x["q_max"][2]) - 2 * np.pi * 5 / L) < 1e-6 and abs(x["q_max"][0]) < 1e-12       # the imposed lamellar period
+
+
 @pytest.mark.parametrize("name", ["l0", "l1"])
 def test_lamellar_against_reference_vectors(gpu, name):
     """The device path against outputs of the REFERENCE's own LamellarOrderParameter.cc (double build)."""

@@ -222,6 +222,28 @@ def test_live_reference_build_rewrites_the_golden_files(tmp_path):
             assert open(os.path.join(gold, name)).read() == open(os.path.join(d, name)).read(), (prec, name)
 
 
+def virial_table():
+    kmin, kmax, n = GOLD["virial_table"]
+    kt = np.linspace(kmin, kmax, int(n))
+    return kmin, kmax, -2.0 * (kt - 2.0) * np.exp(-(kt - 2.0) ** 2)
+
+
+@pytest.mark.parametrize("name", ["m0", "m1", "m2"])
+def test_oracle_virial_reproduces_reference(oracle, name):
+    """computeVirial (OrderParameterMesh.cc:970-1050) with a tabulated kernel derivative, against the reference's own code."""
+    c = GOLD[name + "_cfg"]
+    dims, L, bias, modes = tuple(int(v) for v in c[:3]), tuple(c[3:6]), float(c[6]), tuple(c[7:])
+    pt = GOLD[name + "_postype"]
+    m = oracle.Mesh(*dims, modes, L, pt.shape[0], "f64")
+    m.current_value(pt)
+    kmin, kmax, dK = virial_table()
+    v = m.virial(dK, kmin, kmax, bias)
+    ref = GOLD[name + "_f64_virial"]
+    assert np.abs(ref).max() > 0
+    np.testing.assert_allclose(v, ref, rtol=1e-9, atol=1e-12 * np.abs(ref).max())
+    assert np.all(m.virial(dK, kmin, kmax, bias, use_table=False) == 0.0)          # no table: val_D = 0
+
+
 @pytest.mark.parametrize("name", MESH_CASES)
 def test_oracle_qmax_reproduces_reference(oracle, name):
     """OrderParameterMesh::computeQmax (log quantities q*_max, sq_max; SURVEY 8f rank 2) against the reference's own code.
