@@ -88,7 +88,7 @@ def make_workload(name, shard=None):
         w = {"C3": workloads.c3, "C4": workloads.c4}[name](sort=False)
         w["order"] = "random particle order (stress case, SURVEY 8d C3 ii)"
         return w
-    return {"C1": workloads.c1, "C2": workloads.c2, "C3": workloads.c3, "C4": workloads.c4, "C5": workloads.c5}[name]()
+    return {"C1": workloads.c1, "C2": workloads.c2, "C3": workloads.c3, "C4": workloads.c4, "C5": workloads.c5, "WTE": workloads.wte}[name]()
 
 
 # ---------------------------------------------------------------------------------------------------- ours
@@ -215,17 +215,61 @@ class MeshSlabStep(MeshStep):
         return 48 * self.N_global + 48 * M
 
 
-class LamellarStep:
+class GraphedStep:
+    """CUDA-graph replay of a step whose launch sequence depends only on "deposit step or not": both variants are captured
+    once (torch.cuda.graph; the library launches on torch's current stream, the peer-memory / NCCL all-reduce inside is
+    capturable) and replayed.  The small workloads are bound by launch latency, not by bandwidth (C2: 3 launches of ~5 us)."""
+    use_graph = True
+
+    def _init_graphs(self, stride):
+        self._stride, self._graphs, self._eager_done = stride, {}, {True: 0, False: 0}
+
+    def step(self):
+        dep = self.t % self._stride == 0
+        g = self._graphs.get(dep)
+        if g is not None:
+            g.replay()
+        elif not self.use_graph or getattr(self, "comm_mode", None) == "nccl" or self._eager_done[dep] < 2:
+            # (a library collective is left out of graph capture: replaying a captured NCCL all-reduce on 8 ranks hung in this
+            #  environment, profiles/r02_notes.md; the peer-memory all-reduce is a plain kernel and replays)
+            self._body(self.t)                      # eager: lazy allocations, kernel attributes
+            self._eager_done[dep] += 1
+        else:
+            torch = self.torch
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._body(0 if dep else 1)         # only "deposit or not" reaches the kernels (metad_grid_step)
+            self._graphs[dep] = g
+            g.replay()
+        self.t += 1
+
+
+def make_comm(comm, mode):
+    """Small all-reduces over peer memory (default) or through the library (--comm nccl)."""
+    if comm is None or mode == "nccl":
+        return comm, "nccl" if comm is not None else None
+    from metadynamics_plugin_b200 import sharded
+    try:
+        return sharded.PeerComm(comm), "p2p"
+    except RuntimeError as e:
+        if comm.rank == 0:
+            print("bench: %s -- falling back to --comm nccl" % e, file=sys.stderr)
+        return comm, "nccl"
+
+
+class LamellarStep(GraphedStep):
     launches_per_step = 3
 
-    def __init__(self, w, ops, torch, comm=None):
+    def __init__(self, w, ops, torch, comm=None, comm_mode="p2p"):
         self.ops, self.torch, self.w = ops, torch, w
         self.N_global = w["postype"].shape[0]
         self.box = ops.Box.make(w["L"])
-        self.comm = comm
+        self.comm, self.comm_mode = make_comm(comm, comm_mode)
         pt = w["postype"]
         if comm is not None:            # any particle partition works: contiguous blocks
             pt = np.ascontiguousarray(np.array_split(pt, comm.size)[comm.rank])
+            self.launches_per_step = 5 if self.comm_mode == "p2p" else 4       # + finalize, + the all-reduce kernel when it is ours
         self.h_local = pt
         self.N = pt.shape[0]
         self.lam = ops.Lamellar(w["mode"], w["lattice_vectors"])
@@ -239,6 +283,7 @@ class LamellarStep:
         if self.ncv == 2:       # second CV = aspect ratio Lx/Ly of the (cubic) box: host scalar
             self.cvs[1] = 1.0
         self.t = 0
+        self._init_graphs(w["stride"])
 
     def sharded_cv(self):
         # partial modes -> all-reduce of 2*n_wave doubles -> CV (LamellarOrderParameterGPU.cc:70-77)
@@ -246,21 +291,57 @@ class LamellarStep:
         self.comm.all_reduce_sum(self.lam.modes)
         return self.lam.finalize(self.N_global)
 
-    def step(self):
+    def _body(self, t):
         if self.comm is None:
             cv = self.lam.compute_modes(self.d_pt, self.N_global, self.box)
         else:
             cv = self.sharded_cv()
         if self.ncv == 1:
-            bias = self.grid.step(self.t, cv)
+            bias = self.grid.step(t, cv)
         else:
             self.cvs[0:1].copy_(cv)
-            bias = self.grid.step(self.t, self.cvs)
+            bias = self.grid.step(t, self.cvs)
         self.lam.forces(self.d_pt, self.N_global, self.box, bias[0:1], out=self.d_force)
-        self.t += 1
 
     def algorithmic_bytes(self):
         return 48 * self.N_global
+
+
+class WteStep(GraphedStep):
+    """WellTemperedEnsemble (cv.potential_energy) over particle shards: reduce the potential energy (+ all-reduce of one
+    double, WellTemperedEnsemble.cc:58-64), 1-D grid bias, scale net force / torque / virial by 1 + bias (:135-188)."""
+    launches_per_step = 3
+
+    def __init__(self, w, ops, torch, comm=None, comm_mode="p2p"):
+        self.ops, self.torch, self.w = ops, torch, w
+        self.N_global = w["net_force"].shape[0]
+        self.comm, self.comm_mode = make_comm(comm, comm_mode)
+        part = slice(None) if comm is None else np.array_split(np.arange(self.N_global), comm.size)[comm.rank]
+        if comm is not None:
+            self.launches_per_step = 4 if self.comm_mode == "p2p" else 3
+        self.h_local = np.ascontiguousarray(w["net_force"][part])
+        self.N = self.h_local.shape[0]
+        self.pitch = (self.N + 15) // 16 * 16
+        self.d_pt = torch.from_numpy(self.h_local).cuda()            # "d_pt" = the array the e2e leg uploads: the net force
+        self.d_force = self.d_pt                                       # scaled in place: the array the e2e leg reads back
+        self.d_tq = torch.zeros_like(self.d_pt)
+        self.d_vir = torch.zeros(6 * self.pitch, dtype=torch.float32, device="cuda")
+        self.pe = torch.zeros(1, dtype=torch.float64, device="cuda")
+        pe0 = float(w["net_force"][:, 3].astype(np.float64).sum())
+        self.grid = ops.BiasGrid([pe0 - 0.2 * abs(pe0)], [pe0 + 0.2 * abs(pe0)], [400], [0.01 * abs(pe0)], W=1e-6, T_shift=7.0, T=1.0,
+                                 stride=w["stride"], well_tempered=True)
+        self.t = 0
+        self._init_graphs(w["stride"])
+
+    def _body(self, t):
+        self.ops.wte_reduce(self.d_pt, 0.0, out=self.pe)
+        if self.comm is not None:
+            self.comm.all_reduce_sum(self.pe)
+        bias = self.grid.step(t, self.pe)
+        self.ops.wte_scale(self.d_pt, self.d_tq, self.d_vir, self.pitch, bias)
+
+    def algorithmic_bytes(self):
+        return (16 + 2 * (16 + 16 + 24)) * self.N_global
 
 
 def run_ours(args):
@@ -281,10 +362,13 @@ def run_ours(args):
     if world > 1:
         from metadynamics_plugin_b200 import sharded
         comm = sharded.TorchComm()
+    GraphedStep.use_graph = not args.no_graph
     if w["kind"] == "mesh":
         runner = MeshStep(w, ops, torch) if world == 1 else MeshSlabStep(w, ops, torch, comm, mode=args.comm, sync=args.p2p_sync)
+    elif w["kind"] == "wte":
+        runner = WteStep(w, ops, torch, comm, args.comm)
     else:
-        runner = LamellarStep(w, ops, torch, comm)
+        runner = LamellarStep(w, ops, torch, comm, args.comm)
 
     for kv in args.late_knob:               # experiments that break the results (timing only): set after the calibration
         k, v = (int(x) for x in kv.split("="))
@@ -333,7 +417,8 @@ def run_ours(args):
     roofline = None
     if w["kind"] == "mesh" and world > 1:
         achieved = runner.algorithmic_bytes() / (ms_per_step * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "whole sharded step (compute stages + NCCL collectives)", "achieved": achieved,
+        roofline = {"bound": "hbm", "kernel": "whole sharded step (%s)" % ("compute stages with the transposes fused in, halo pushes, flag barriers over peer memory"
+                                                                          if runner.comm_mode == "p2p" else "compute stages + NCCL collectives"), "achieved": achieved,
                     "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world), "traffic": None,
                     "peak_source": peak_src + " x %d GPUs" % world}
         if runner.comm_mode == "p2p" and args.p2p_sync == "barrier":
@@ -380,14 +465,19 @@ def run_ours(args):
                     "step_frac": runner.algorithmic_bytes() / (ms_per_step * 1e-3) / 1e9 / peak}
     else:
         achieved = runner.algorithmic_bytes() / (ms_per_step * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "lamellar_modes+grid_step+lamellar_force (whole step)", "achieved": achieved, "peak": peak,
-                    "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src}
+        kern = "wte_reduce+grid_step+wte_scale (whole step)" if w["kind"] == "wte" else "lamellar_modes+grid_step+lamellar_force (whole step)"
+        if world > 1:
+            kern += " + one all-reduce of %s doubles (%s)" % ("1" if w["kind"] == "wte" else "2 n_q", "peer memory, csrc/peer.cu" if runner.comm_mode == "p2p" else "NCCL")
+        roofline = {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peak * world,
+                    "unit": "GB/s", "frac": achieved / (peak * world), "traffic": None,
+                    "peak_source": peak_src + (" x %d GPUs" % world if world > 1 else ""),
+                    "cuda_graph": bool(GraphedStep.use_graph)}
 
     # end to end through the same calls with host buffers
     h_pt = torch.from_numpy(getattr(runner, "h_local", w["postype"])).pin_memory()
     h_force = torch.empty_like(h_pt).pin_memory()
     h_cv = torch.zeros(1, dtype=torch.float64).pin_memory()
-    cv_t = runner.mesh.cv if w["kind"] == "mesh" else runner.lam.cv
+    cv_t = runner.mesh.cv if w["kind"] == "mesh" else (runner.pe if w["kind"] == "wte" else runner.lam.cv)
     if world > 1:
         h2d = torch.tensor([float(h_pt.numel() * 4), float(h_force.numel() * 4 + 8)], dtype=torch.float64, device="cuda")
         dist.all_reduce(h2d)
@@ -429,7 +519,8 @@ def run_ours(args):
                    "parallelism": "1 GPU" if world == 1 else (("z-slab mesh + particle sharding over %d GPUs, %s" % (
                        world, "peer memory over NVLink: transposes fused into the FFT sweeps, pushed halos, flag barriers (no NCCL call in a step; "
                        "CV agrees with the NCCL path to %.1e)" % runner.cv_check if runner.comm_mode == "p2p" else "NCCL all-to-all / halo exchange / all-reduce"))
-                                                              if w["kind"] == "mesh" else "particles sharded over %d GPUs, one NCCL all-reduce per step" % world),
+                                                              if w["kind"] == "mesh" else "particles sharded over %d GPUs, one all-reduce of a few doubles per step (%s)" % (
+                                                                  world, "peer memory over NVLink, csrc/peer.cu; step replayed from a CUDA graph" if runner.comm_mode == "p2p" else "NCCL")),
                    "tile_order_rebuild_period": getattr(runner, "period", None), "tile_order_rebuilds_in_timed_region": rebuilds_timed},
         "roofline": roofline,
         "e2e": {"value": 1e3 / e2e_ms, "unit": "steps/s", "h2d_bytes_per_step": h2d_bytes,
@@ -459,6 +550,8 @@ def run_ours(args):
 
 
 def describe(w):
+    if w["kind"] == "wte":
+        return "WellTemperedEnsemble (potential energy) + 1-D well-tempered grid bias, N=%d" % w["net_force"].shape[0]
     if w["kind"] == "mesh":
         return "OrderParameterMesh CV + 1-D well-tempered grid bias, N=%d, mesh %dx%dx%d, L=%.3f" % (
             w["postype"].shape[0], *w["mesh"], w["L"])
@@ -506,6 +599,23 @@ def parity_block(w, runner, world, rank, torch):
         cvo = o.current_value(w["postype"])
         fo = o.forces(pt_local, 1.0)
         out["oracle_seconds"] = round(time.perf_counter() - t0, 2)
+    elif w["kind"] == "wte":
+        nf = torch.from_numpy(pt_local).cuda()
+        pe = runner.ops.wte_reduce(nf, 0.0)
+        if runner.comm is not None:
+            runner.comm.all_reduce_sum(pe)
+        cv = pe.cpu().item()
+        half = torch.tensor([0.5], dtype=torch.float64, device="cuda")
+        runner.ops.wte_scale(nf, runner.d_tq, runner.d_vir, runner.pitch, half)
+        f = nf.cpu().numpy()
+        if rank != 0:
+            return None
+        from oracle import pyoracle as po
+        t0 = time.perf_counter()
+        cvo = po.wte_pe(w["net_force"], 0.0)
+        fo, _, _, _ = po.wte_scale(pt_local, np.zeros_like(pt_local), np.zeros(6 * runner.pitch, np.float32), runner.pitch, 0.5, np.zeros(6))
+        out["cells_bitexact"] = None
+        out["oracle_seconds"] = round(time.perf_counter() - t0, 2)
     else:
         lam = runner.lam
         if runner.comm is None:
@@ -548,6 +658,28 @@ def cpu_step_fn(w, prec="f32"):
             for k, v in (("assign", t1 - t0), ("fft+convolve", t2 - t1), ("cv_sum", t3 - t2), ("forces", t4 - t3)):
                 phases[k] = phases.get(k, 0.0) + v
             return cv
+        return step, phases
+    if w["kind"] == "wte":
+        nf = w["net_force"]
+        pe0 = float(nf[:, 3].astype(np.float64).sum())
+        grid = po.Grid([pe0 - 0.2 * abs(pe0)], [pe0 + 0.2 * abs(pe0)], [400], [0.01 * abs(pe0)], W=1e-6, T_shift=7.0, T=1.0, stride=w["stride"],
+                       well_tempered=True, prec=prec)
+        pitch = (N + 15) // 16 * 16
+        tq, vir = np.zeros_like(nf), np.zeros(6 * pitch, np.float32)
+        state, phases = {"t": 0}, {}
+
+        def step():
+            t0 = time.perf_counter()
+            pe = po.wte_pe(nf, 0.0, prec)
+            t1 = time.perf_counter()
+            b = grid.update(state["t"], [pe])
+            t2 = time.perf_counter()
+            po.wte_scale(nf, tq, vir, pitch, b[0], np.zeros(6), prec)
+            t3 = time.perf_counter()
+            state["t"] += 1
+            for k, v in (("reduce", t1 - t0), ("grid", t2 - t1), ("scale", t3 - t2)):
+                phases[k] = phases.get(k, 0.0) + v
+            return pe
         return step, phases
     g = w["grid"]
     grid = po.Grid(g["cv_min"], g["cv_max"], g["num_points"], g["sigma"], W=w["W"], T_shift=w["deltaT"], T=w["T"], stride=w["stride"],
@@ -627,7 +759,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="C4", choices=["C1", "C2", "C3", "C4", "C5"])
+    ap.add_argument("--workload", default="C4", choices=["C1", "C2", "C3", "C4", "C5", "WTE"])
+    ap.add_argument("--no-graph", action="store_true", help="Lamellar / WTE workloads: launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"], help="multi-GPU mesh path: peer memory (default) or NCCL collectives")
     ap.add_argument("--p2p-sync", default="barrier", choices=["fused", "barrier"],

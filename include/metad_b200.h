@@ -240,6 +240,25 @@ int metad_umbrella_apply(int kind, double cv0, double kappa, double width_flat, 
                          double* d_energy_out, metad_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Scalar all-reduce over peer memory (NVLink, CUDA IPC) for the sharded CVs
+ * replaces the host-synchronous MPI_Allreduce of a few Scalars per step: the 2 n_q Fourier modes
+ * (LamellarOrderParameterGPU.cc:70-77), the potential energy (WellTemperedEnsemble.cc:58-64, CollectiveWrapper.cc:63-69),
+ * computeSigma's matrix (IntegratorMetaDynamics.cc:1265-1274).  One 256-thread kernel on the caller's stream, graph-capturable;
+ * no library collective.  Set-up: every rank creates a handle, the 64-byte IPC handles are all-gathered once (any
+ * out-of-band channel), every rank connects.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct metad_peer metad_peer;
+int metad_peer_create(metad_peer** out, unsigned n_ranks, unsigned rank);           /* up to 8 ranks (one NVSwitch domain) */
+int metad_peer_destroy(metad_peer* p);
+int metad_peer_handle(metad_peer* p, void* handle_out64);
+int metad_peer_connect(metad_peer* p, const void* handles /* n_ranks x 64 bytes, rank order */);
+int metad_peer_connect_local(metad_peer* p, metad_peer* const* all /* all ranks of one process, rank order (tests) */);
+/* d_data[0..n) (device doubles, n <= 32) <- sum over the ranks, added in rank order (identical bits on every rank).
+ * phase: -1 in multi-process use; with connect_local 0 (publish; every rank first) then 1 (reduce). */
+int metad_peer_allreduce_sum(metad_peer* p, double* d_data, unsigned n, int phase, metad_stream_t stream);
+int metad_peer_status(metad_peer* p, unsigned* timed_out);
+
+/* ------------------------------------------------------------------------------------------------
  * WellTemperedEnsemble
  * replaces gpu_reduce_potential_energy and gpu_scale_netforce (WellTemperedEnsemble.cuh:3-19).
  * ---------------------------------------------------------------------------------------------- */

@@ -91,6 +91,13 @@ SIGNATURES = {
     "metad_grid_set_num_gaussians": (C.c_int, [_vp, C.c_uint]),
     "metad_grid_num_elements": (C.c_uint, [_vp]),
     "metad_umbrella_apply": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, _vp, _vp, _vp, _vp, _vp]),
+    "metad_peer_create": (C.c_int, [C.POINTER(_vp), C.c_uint, C.c_uint]),
+    "metad_peer_destroy": (C.c_int, [_vp]),
+    "metad_peer_handle": (C.c_int, [_vp, _vp]),
+    "metad_peer_connect": (C.c_int, [_vp, _vp]),
+    "metad_peer_connect_local": (C.c_int, [_vp, _vp]),
+    "metad_peer_allreduce_sum": (C.c_int, [_vp, _vp, C.c_uint, C.c_int, _vp]),
+    "metad_peer_status": (C.c_int, [_vp, C.POINTER(C.c_uint)]),
     "metad_wte_reduce": (C.c_int, [_vp, C.c_uint, C.c_double, _vp, _vp]),
     "metad_wte_scale": (C.c_int, [_vp, _vp, _vp, C.c_uint, C.c_uint, _vp, _vp]),
     "metad_accumulate_force": (C.c_int, [_vp, _vp, C.c_uint, C.c_int, _vp]),

@@ -140,10 +140,18 @@ static int wte_scratch(cudaStream_t stream, WteScratch** out) {
     std::lock_guard<std::mutex> lock(g_wte_mutex);
     WteScratch& w = g_wte[std::make_pair(dev, stream)];
     if (!w.partials) {
+        // the first use of a stream may happen while that stream is being captured into a CUDA graph (the capture stream of a
+        // framework is a fresh stream): allocations are legal there in relaxed capture mode, and the ticket is cleared by a
+        // memset ON the stream (captured as a node: it then also runs, harmlessly, at every replay)
+        cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
+        METAD_CUDA(cudaThreadExchangeStreamCaptureMode(&mode));
         w.blocks = device_sm_count() * 8;
-        METAD_CUDA(cudaMalloc(&w.partials, sizeof(double) * w.blocks));
-        METAD_CUDA(cudaMalloc(&w.ticket, sizeof(unsigned)));
-        METAD_CUDA(cudaMemset(w.ticket, 0, sizeof(unsigned)));
+        cudaError_t e1 = cudaMalloc(&w.partials, sizeof(double) * w.blocks);
+        cudaError_t e2 = cudaMalloc(&w.ticket, sizeof(unsigned));
+        METAD_CUDA(cudaThreadExchangeStreamCaptureMode(&mode));
+        METAD_CUDA(e1);
+        METAD_CUDA(e2);
+        METAD_CUDA(cudaMemsetAsync(w.ticket, 0, sizeof(unsigned), stream));
     }
     *out = &w;
     return METAD_OK;

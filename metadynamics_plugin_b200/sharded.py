@@ -65,6 +65,92 @@ class TorchComm:
             r.wait()
 
 
+class PeerAllReduce:
+    """All-reduce of up to 32 doubles over peer memory (metad_peer_*, csrc/peer.cu): one small kernel on the current stream
+    instead of a library collective -- the exchange of the Lamellar Fourier modes, of the WTE potential energy, of
+    computeSigma's matrix.  torch.distributed is used once, to all-gather the 64-byte IPC handles."""
+
+    def __init__(self, comm):
+        self.h = C.c_void_p()
+        check(lib.metad_peer_create(C.byref(self.h), comm.size, comm.rank))
+        if comm.size > 1:
+            handle = (C.c_ubyte * 64)()
+            check(lib.metad_peer_handle(self.h, handle))
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device="cuda")
+            allh = torch.empty(comm.size * 64, dtype=torch.uint8, device="cuda")
+            comm.dist.all_gather_into_tensor(allh, mine, group=comm.group)
+            buf = (C.c_ubyte * (64 * comm.size))(*allh.cpu().tolist())
+            err = None
+            try:
+                check(lib.metad_peer_connect(self.h, buf))
+            except Exception as e:
+                err = e
+            ok = torch.tensor([0 if err else 1], dtype=torch.int32, device="cuda")
+            comm.dist.all_reduce(ok, op=comm.dist.ReduceOp.MIN, group=comm.group)
+            if ok.item() == 0:
+                raise RuntimeError("peer memory is not available on every rank (%s)" % (err or "another rank failed"))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib.metad_peer_destroy(self.h)
+            self.h = None
+
+    def all_reduce_sum(self, t):
+        assert t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.numel() <= 32
+        check(lib.metad_peer_allreduce_sum(self.h, _ptr(t), t.numel(), -1, _stream()))
+
+    def timed_out(self):
+        out = C.c_uint(0)
+        check(lib.metad_peer_status(self.h, C.byref(out)))
+        return bool(out.value)
+
+
+class PeerComm:
+    """TorchComm whose small float64 all-reduces go over peer memory (PeerAllReduce); everything else is delegated."""
+
+    def __init__(self, comm):
+        self.comm, self.peer = comm, PeerAllReduce(comm)
+        self.rank, self.size, self.dist, self.group = comm.rank, comm.size, comm.dist, comm.group
+
+    def all_reduce_sum(self, t):
+        if t.is_cuda and t.dtype == torch.float64 and t.numel() <= 32 and t.is_contiguous():
+            self.peer.all_reduce_sum(t)
+        else:
+            self.comm.all_reduce_sum(t)
+
+    def all_to_all(self, out, inp):
+        self.comm.all_to_all(out, inp)
+
+    def neighbour_exchange(self, *a):
+        self.comm.neighbour_exchange(*a)
+
+
+class LocalPeerGroup:
+    """All ranks of a peer all-reduce in one process on one GPU (tests): publish for every rank, then reduce for every rank."""
+
+    def __init__(self, size):
+        self.size = size
+        self.hs = [C.c_void_p() for _ in range(size)]
+        for r, h in enumerate(self.hs):
+            check(lib.metad_peer_create(C.byref(h), size, r))
+        arr = (C.c_void_p * size)(*[h.value for h in self.hs])
+        for h in self.hs:
+            check(lib.metad_peer_connect_local(h, arr))
+
+    def __del__(self):
+        for h in getattr(self, "hs", []):
+            lib.metad_peer_destroy(h)
+        self.hs = []
+
+    def all_reduce_sum(self, ts):
+        if self.size == 1:
+            check(lib.metad_peer_allreduce_sum(self.hs[0], _ptr(ts[0]), ts[0].numel(), -1, _stream()))
+            return
+        for phase in (0, 1):
+            for h, t in zip(self.hs, ts):
+                check(lib.metad_peer_allreduce_sum(h, _ptr(t), t.numel(), phase, _stream()))
+
+
 class LocalComm:
     """All ranks in one process (bulk-synchronous emulation): every collective takes the list of per-rank tensors."""
 

@@ -78,3 +78,11 @@ def c5(seed=20260105, N=1 << 23):
                 lattice_vectors=[(0, 0, 10), (0, 10, 0), (10, 0, 0)],
                 grid=dict(cv_min=[-2.0, 0.0], cv_max=[2.0, 2.0], num_points=[256, 256], sigma=[0.05, 0.1]),
                 aspect=(0, 1), W=1.0, deltaT=7.0, T=1.0, stride=100)
+
+
+def wte(seed=20260106, N=1 << 23):
+    """WellTemperedEnsemble at the size of C5: a synthetic net-force array (force xyz, per-particle potential energy in w)."""
+    rng = np.random.default_rng(seed)
+    nf = rng.standard_normal((N, 4), dtype=np.float32)
+    nf[:, 3] = nf[:, 3] * 0.5 - 3.0
+    return dict(name="WTE", kind="wte", net_force=nf, postype=nf, stride=100)

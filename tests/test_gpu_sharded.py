@@ -176,3 +176,49 @@ def test_lamellar_sharded_local(gpu, oracle):
     cvo, _ = oracle.lamellar_cv(oracle.make_postype(pos, types), N, modes, lv, L)
     assert all(c == cvs[0] for c in cvs)
     assert abs(cvs[0] - cvo) < 2e-6 * np.sqrt(N) * 2 / N
+
+
+@pytest.mark.parametrize("P,n", [(1, 6), (2, 1), (4, 6), (8, 32)])
+def test_peer_allreduce_local(gpu, P, n):
+    """metad_peer_allreduce_sum with all ranks in one process: rank-ordered sums, identical on every rank, table slots
+    alternate with the epoch (three rounds)."""
+    import torch
+    ops, sharded = gpu
+    grp = sharded.LocalPeerGroup(P)
+    rng = np.random.default_rng(P + n)
+    for rnd in range(3):
+        vals = rng.normal(size=(P, n))
+        ts = [torch.tensor(v, dtype=torch.float64, device="cuda") for v in vals]
+        grp.all_reduce_sum(ts)
+        want = np.zeros(n)
+        for r in range(P):
+            want = want + vals[r]                     # rank order
+        for t in ts:
+            np.testing.assert_array_equal(t.cpu().numpy(), want)
+
+
+def test_lamellar_and_wte_sharded_over_peer_memory_local(gpu, oracle):
+    """LamellarSharded / WTESharded with the peer-memory all-reduce (all ranks emulated in one process)."""
+    import torch
+    ops, sharded = gpu
+    N, L, P = 60000, 17.0, 4
+    rng = np.random.default_rng(6)
+    pos = ((rng.random((N, 3)) - 0.5) * L).astype(np.float32)
+    types = rng.integers(0, 2, N).astype(np.int32)
+    lv, modes = [(0, 0, 3), (1, 1, 0), (2, 0, 1)], [1.0, -1.0]
+    box = ops.Box.make(L)
+    parts = np.array_split(np.arange(N), P)
+    lams = [ops.Lamellar(modes, lv) for _ in range(P)]
+    pts = [ops.make_postype(pos[i], types[i]) for i in parts]
+    for lam, pt in zip(lams, pts):
+        lam.compute_modes(pt, N, box, finalize=False)
+    sharded.LocalPeerGroup(P).all_reduce_sum([lam.modes for lam in lams])
+    cvs = [lam.finalize(N).cpu().item() for lam in lams]
+    cvo, _ = oracle.lamellar_cv(oracle.make_postype(pos, types), N, modes, lv, L)
+    assert all(c == cvs[0] for c in cvs)
+    assert abs(cvs[0] - cvo) < 2e-6 * np.sqrt(N) * 2 / N
+    nf = rng.normal(size=(N, 4)).astype(np.float32)
+    pes = [ops.wte_reduce(torch.from_numpy(nf[i]).cuda(), 0.0) for i in parts]
+    sharded.LocalPeerGroup(P).all_reduce_sum(pes)
+    assert all(p.cpu().item() == pes[0].cpu().item() for p in pes)
+    assert pes[0].cpu().item() + 1.25 == pytest.approx(oracle.wte_pe(nf, 1.25), rel=1e-12)
