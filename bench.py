@@ -82,11 +82,13 @@ class ClockSampler:
 PARTICLE_ORDER = "sorted"   # --order: C3 / C4 input order, cell-sorted (an MD engine's spatial sort; headline) or random (stress)
 
 
-def make_workload(name, shard=None):
+def make_workload(name, shard=None, order=None):
     from metadynamics_plugin_b200 import workloads
-    if name in ("C3", "C4") and PARTICLE_ORDER == "random":
-        w = {"C3": workloads.c3, "C4": workloads.c4}[name](sort=False)
-        w["order"] = "random particle order (stress case, SURVEY 8d C3 ii)"
+    order = order or PARTICLE_ORDER
+    if name in ("C3", "C4") and order in ("random", "sfc"):
+        w = {"C3": workloads.c3, "C4": workloads.c4}[name](sort=False if order == "random" else "sfc")
+        w["order"] = ("random particle order (stress case, SURVEY 8d C3 ii)" if order == "random" else
+                      "Morton order on 4^3-cell blocks, random inside a block (an MD engine's SFC sort)")
         return w
     return {"C1": workloads.c1, "C2": workloads.c2, "C3": workloads.c3, "C4": workloads.c4, "C5": workloads.c5, "WTE": workloads.wte}[name]()
 
@@ -473,6 +475,12 @@ def run_ours(args):
                     "peak_source": peak_src + (" x %d GPUs" % world if world > 1 else ""),
                     "cuda_graph": bool(GraphedStep.use_graph)}
 
+    extra = {}
+    if w["kind"] == "mesh" and world == 1 and not args.no_extra_legs:
+        extra = mesh_extra_legs(args, w, runner, ops, torch, ms_per_step, rebuilds_timed)
+        ms_per_step = extra["tile_order"]["ms_per_step_steady_state"]
+        roofline["step_frac"] = runner.algorithmic_bytes() / (ms_per_step * 1e-3) / 1e9 / peak
+
     # end to end through the same calls with host buffers
     h_pt = torch.from_numpy(getattr(runner, "h_local", w["postype"])).pin_memory()
     h_force = torch.empty_like(h_pt).pin_memory()
@@ -499,11 +507,51 @@ def run_ours(args):
     for _ in range(e2e_steps):
         e2e_step()
     sync_all()
+    e2e_serial_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+
+    # the same work as a pipeline: the upload of step i+1 and the read-back of step i-1 overlap step i (two copy streams, staging
+    # buffers on the device, two pinned result buffers); every step still uploads its inputs and reads back forces + CV
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    stage_in = [torch.empty_like(runner.d_pt) for _ in range(2)]
+    stage_out = [torch.empty_like(runner.d_force) for _ in range(2)]
+    stage_cv = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(2)]
+    h_forces = [h_force, torch.empty_like(h_force).pin_memory()]
+    h_cvs = [h_cv, torch.zeros(1, dtype=torch.float64).pin_memory()]
+    ev = {k: [torch.cuda.Event() for _ in range(2)] for k in ("in", "free", "done", "out")}
+
+    def e2e_pipeline(K):
+        main = torch.cuda.current_stream()
+        for b in range(2):
+            ev["free"][b].record(main); ev["out"][b].record(main)
+        with torch.cuda.stream(s_in):
+            stage_in[0].copy_(h_pt, non_blocking=True); ev["in"][0].record(s_in)
+        for i in range(K):
+            b = i & 1
+            if i + 1 < K:
+                with torch.cuda.stream(s_in):
+                    s_in.wait_event(ev["free"][1 - b])
+                    stage_in[1 - b].copy_(h_pt, non_blocking=True); ev["in"][1 - b].record(s_in)
+            main.wait_event(ev["in"][b])
+            runner.d_pt.copy_(stage_in[b]); ev["free"][b].record(main)
+            runner.step()
+            main.wait_event(ev["out"][b])
+            stage_out[b].copy_(runner.d_force); stage_cv[b].copy_(cv_t); ev["done"][b].record(main)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev["done"][b])
+                h_forces[b].copy_(stage_out[b], non_blocking=True); h_cvs[b].copy_(stage_cv[b], non_blocking=True); ev["out"][b].record(s_out)
+        torch.cuda.synchronize()
+
+    e2e_pipeline(2)
+    sync_all()
+    t0 = time.perf_counter()
+    e2e_pipeline(e2e_steps)
+    sync_all()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
     if world > 1:
-        t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([e2e_ms, e2e_serial_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = t.item()
+        e2e_ms, e2e_serial_ms = t.tolist()
+    del stage_in, stage_out
 
     n_global = w["postype"].shape[0]
     clocks = None
@@ -515,20 +563,23 @@ def run_ours(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32 (fixed-point density, fp64 accumulation of the CV)", "data": "synthetic",
         "ns_per_particle_step": ms_per_step * 1e6 / n_global,
-        "config": {"workload": "%s: %s" % (w["name"], describe(w)) + (", " + w["order"] if "order" in w else ""), "N": n_global, "l2": "inputs larger than L2 (no flush)",
-                   "parallelism": "1 GPU" if world == 1 else (("z-slab mesh + particle sharding over %d GPUs, %s" % (
+        "config": config_for(w, world),
+        "run_info": {"parallelism": "1 GPU" if world == 1 else (("z-slab mesh + particle sharding over %d GPUs, %s" % (
                        world, "peer memory over NVLink: transposes fused into the FFT sweeps, pushed halos, flag barriers (no NCCL call in a step; "
                        "CV agrees with the NCCL path to %.1e)" % runner.cv_check if runner.comm_mode == "p2p" else "NCCL all-to-all / halo exchange / all-reduce"))
                                                               if w["kind"] == "mesh" else "particles sharded over %d GPUs, one all-reduce of a few doubles per step (%s)" % (
                                                                   world, "peer memory over NVLink, csrc/peer.cu; step replayed from a CUDA graph" if runner.comm_mode == "p2p" else "NCCL")),
-                   "tile_order_rebuild_period": getattr(runner, "period", None), "tile_order_rebuilds_in_timed_region": rebuilds_timed},
+                     "tile_order_rebuild_period": getattr(runner, "period", None), "tile_order_rebuilds_in_timed_region": rebuilds_timed},
         "roofline": roofline,
         "e2e": {"value": 1e3 / e2e_ms, "unit": "steps/s", "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps},
+                "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps, "serial_value": 1e3 / e2e_serial_ms,
+                "note": "value: upload of step i+1 and read-back of step i-1 overlap step i (every step uploads its inputs from pinned "
+                        "memory and reads back forces + CV); serial_value: copy in, step, copy out, synchronise"},
         "host_enqueue_ms_per_step": host_enqueue_ms,
         "gpu_launches": runner.launches_per_step * args.steps + getattr(runner, "launches_per_rebuild", 0) * rebuilds_timed,
         "clocks": clocks,
     }
+    out.update(extra)
     # the same fractions against the nominal 8 TB/s of the north star (SURVEY 8d names both denominators)
     roofline["frac_nominal_8TBps"] = roofline["achieved"] / (8000.0 * world)
     if "step_frac" in roofline:
@@ -549,6 +600,13 @@ def run_ours(args):
         sys.exit(3)
 
 
+def config_for(w, world):
+    """The `config` object of the JSON line: identical for both arms (ours / --impl reference) of the same workload."""
+    return {"workload": "%s: %s" % (w["name"], describe(w)) + (", " + w["order"] if "order" in w else ""), "N": int(w["postype"].shape[0]),
+            "l2": "inputs larger than L2 (no flush)" if w["postype"].nbytes > 126e6 else "inputs smaller than L2 (small workload, latency-bound; no flush)",
+            "gpus": world}
+
+
 def describe(w):
     if w["kind"] == "wte":
         return "WellTemperedEnsemble (potential energy) + 1-D well-tempered grid bias, N=%d" % w["net_force"].shape[0]
@@ -557,6 +615,121 @@ def describe(w):
             w["postype"].shape[0], *w["mesh"], w["L"])
     return "LamellarOrderParameter %d wave vectors + %d-D well-tempered grid bias, N=%d, L=%.3f" % (
         len(w["lattice_vectors"]), len(w["grid"]["num_points"]), w["postype"].shape[0], w["L"])
+
+
+# ---------------------------------------------------------------------------------------------------- extra legs
+def _time_steps(torch, fn, n):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def mesh_extra_legs(args, w, runner, ops, torch, ms_measured, rebuilds_timed):
+    """What the headline number leaves out, measured in the same run:
+      tile_order   cost of one rebuild of the tile order and the steady-state step with it amortised over the period;
+      orders       the same step for other particle orders of the input (random; Morton order on 4^3-cell blocks);
+      moving       particles displaced by a Gaussian of 0.05 cell per step (stale order, drift counters, rebuilds);
+      host_class   the step through the reference-facing classes (cv.mesh + integrate.mode_metadynamics -> _metadynamics)."""
+    out = {}
+    period = runner.period
+    # -- rebuild cost: every call rebuilds vs no call rebuilds
+    runner.mesh.set(0, 1)
+    runner.step()
+    t_every = _time_steps(torch, runner.step, 6)
+    runner.mesh.set(0, 1 << 30)
+    runner.step()
+    t_never = _time_steps(torch, runner.step, 12)
+    runner.mesh.set(0, period)
+    rebuild_ms = max(t_every - t_never, 0.0)
+    steady = (ms_measured * args.steps - rebuilds_timed * rebuild_ms) / args.steps + rebuild_ms / period
+    out["tile_order"] = {"rebuild_ms": round(rebuild_ms, 4), "period": period, "amortised_ms_per_step": round(rebuild_ms / period, 5),
+                         "rebuilds_in_timed_region": rebuilds_timed, "ms_per_step_timed_region": ms_measured,
+                         "ms_per_step_steady_state": steady,
+                         "note": "ms_per_step / value = timed region with its rebuilds replaced by rebuild_ms / period per step"}
+    # -- other particle orders of the same configuration
+    orders = {"cell_sorted": round(t_never + rebuild_ms / period, 4)}
+    for order in ("sfc", "random"):
+        w2 = make_workload(args.workload, order=order)
+        r2 = MeshStep(w2, ops, torch, period=period)
+        for _ in range(3):
+            r2.step()
+        t = _time_steps(torch, r2.step, 2 * period)             # two periods: contains two rebuilds
+        r2.mesh.set(2, 1)
+        r2.step(); torch.cuda.synchronize()
+        st = r2.mesh.timings()
+        r2.mesh.set(2, 0)
+        orders[order] = round(t, 4)
+        orders[order + "_stage_ms"] = {k: round(v, 4) for k, v in st.items()}
+        del r2, w2
+        torch.cuda.empty_cache()
+    out["orders_ms_per_step"] = orders
+    # -- moving particles: Gaussian displacement of 0.05 cell per step, periodic wrap, 2 periods
+    mv = MeshStep(w, ops, torch, period=period)
+    L, h = float(w["L"]), float(w["L"]) / w["mesh"][0]
+    half = torch.tensor(L / 2, dtype=torch.float32, device="cuda")
+    for _ in range(3):
+        mv.step()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(2 * period)]
+    drift_max, rb0 = 0, mv.mesh.stats()["rebuilds"]
+    gen = torch.Generator(device="cuda"); gen.manual_seed(1)
+    for a, b in ev:
+        xyz = mv.d_pt[:, :3]
+        xyz.add_(torch.randn(xyz.shape, device="cuda", generator=gen) * (0.05 * h))
+        xyz.copy_(torch.remainder(xyz + half, 2 * half) - half)
+        xyz.clamp_(min=-L / 2, max=float(np.nextafter(np.float32(L / 2), np.float32(0))))
+        a.record(); mv.step(); b.record()
+    torch.cuda.synchronize()
+    st = mv.mesh.stats()
+    out["moving"] = {"displacement_cells_per_step": 0.05, "steps": len(ev), "ms_per_step": round(sum(a.elapsed_time(b) for a, b in ev) / len(ev), 4),
+                     "rebuilds": st["rebuilds"] - rb0, "drifted_particles_last_step": st["drifted"],
+                     "note": "the tile order goes stale between rebuilds: drifted particles take the direct path (global atomics / loads)"}
+    del mv
+    torch.cuda.empty_cache()
+    # -- the reference-facing host classes
+    try:
+        out["host_class"] = host_class_leg(w, torch, min(args.steps, 20))
+    except Exception as e:       # a failure here must not take the headline down with it, but it must be visible
+        out["host_class"] = {"error": repr(e)}
+    return out
+
+
+def host_class_leg(w, torch, steps):
+    """cv.mesh + integrate.mode_metadynamics (the reference's Python API over the pybind `_metadynamics` classes):
+    device-resident steps of IntegratorMetaDynamics::update, and the same with host arrays in and out per step."""
+    from metadynamics_plugin_b200 import cv, integrate, hoomd_shim as hoomd
+    hoomd.context.initialize()
+    pt = w["postype"]
+    N = pt.shape[0]
+    sd = hoomd.init.from_arrays(pt[:, :3], pt[:, 3].view(np.int32), ["A"], w["L"])
+    meta = integrate.mode_metadynamics(dt=0.005, mode="well_tempered", stride=w.get("stride", 100), deltaT=7.0, W=1e-12)
+    mesh = cv.mesh(nx=w["mesh"][0], ny=w["mesh"][1], nz=w["mesh"][2], mode={"A": float(w["mode"][0])})
+    val = mesh.cpp_force.getCurrentValue(0)
+    mesh.set_grid(cv_min=0.5 * val, cv_max=1.5 * val, num_points=400)
+    mesh.sigma = 0.05 * abs(val)
+    hoomd.run(3)                                                     # prepRun + warm-up
+    integ = hoomd.context.current.integrator.cpp_integrator
+    cur = hoomd.context.current
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        integ.update(cur.timestep); cur.timestep += 1
+    torch.cuda.synchronize()
+    dev_ms = (time.perf_counter() - t0) * 1e3 / steps
+    pd = sd.getParticleData()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        pd.setPositions(pt)                                          # host -> device (pageable numpy memory: what the API takes)
+        integ.update(cur.timestep); cur.timestep += 1
+        f = mesh.get_forces()                                        # device -> host
+        cvv = mesh.cpp_force.getLogValue("cv_mesh", cur.timestep)
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / steps
+    return {"api": "cv.mesh + integrate.mode_metadynamics -> _metadynamics.OrderParameterMeshGPU / IntegratorMetaDynamics.update",
+            "ms_per_step_device_resident": round(dev_ms, 4), "e2e_ms_per_step_host_arrays": round(e2e_ms, 3), "steps": steps,
+            "cv": float(cvv), "force_absmax": float(np.abs(f).max())}
 
 
 # ---------------------------------------------------------------------------------------------------- parity
@@ -746,7 +919,7 @@ def run_reference(args):
            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": n, "warmup": done_w, "ms_per_step": dt * 1e3,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "ns_per_particle_step": dt * 1e9 / N,
-           "config": {"workload": "%s: %s" % (w["name"], describe(w)), "N": N},
+           "config": config_for(w, int(os.environ.get("WORLD_SIZE", "1"))),
            "cpu_baseline": {"value": 1.0 / dt, "unit": "steps/s", "cores": 1, "kind": "port", "sample": sample,
                             "phases_s_per_step": {k: v / n for k, v in phases.items()}},
            "e2e": {"value": 1.0 / dt, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -766,11 +939,12 @@ def main():
     ap.add_argument("--p2p-sync", default="barrier", choices=["fused", "barrier"],
                     help="peer-memory mode: separate barrier launches (default, measured faster) or inter-rank signal/wait inside the kernels")
     ap.add_argument("--tile-order", default=None, choices=["bank", "layer"], help="order of the particles inside a tile (single GPU; default: library default = bank)")
-    ap.add_argument("--order", default="sorted", choices=["sorted", "random"], help="C3 / C4: particle order of the input (cell-sorted headline, random stress case)")
+    ap.add_argument("--order", default="sorted", choices=["sorted", "random", "sfc"], help="C3 / C4: particle order of the input (cell-sorted headline, random stress case)")
     ap.add_argument("--merge-push", action="store_true", help="peer-memory mode: halo push and barrier in one launch (measured slower)")
     ap.add_argument("--no-pdl", action="store_true", help="launch the per-step kernels without programmatic dependent launch")
     ap.add_argument("--mesh-knob", action="append", default=[], metavar="K=V", help="metad_mesh_set(plan, K, V) before the first step (experiments)")
     ap.add_argument("--late-knob", action="append", default=[], metavar="K=V", help="like --mesh-knob, applied after the set-up (timing experiments)")
+    ap.add_argument("--no-extra-legs", action="store_true", help="skip the rebuild-cost / particle-order / moving-particle / host-class legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity block (experiments only)")
     ap.add_argument("--cpu-budget", type=float, default=25.0)

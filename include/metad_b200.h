@@ -262,6 +262,9 @@ int metad_peer_status(metad_peer* p, unsigned* timed_out);
  * WellTemperedEnsemble
  * replaces gpu_reduce_potential_energy and gpu_scale_netforce (WellTemperedEnsemble.cuh:3-19).
  * ---------------------------------------------------------------------------------------------- */
+/* *d_dst = value, asynchronously on `stream` (the value is a kernel argument: no staging buffer, no synchronisation);
+ * how CVs that are host scalars (AspectRatio, Density) enter the device-resident step of IntegratorMetaDynamics::update */
+int metad_set_double(double* d_dst, double value, metad_stream_t stream);
 /* *d_out = scale * sum_n (f_i[n].xyz . f_j[n].xyz): the sums of products of CV derivatives of computeSigma
  * (IntegratorMetaDynamics.cc:1238-1247; scale = sigma_g^2), f = Scalar4 force arrays filled by computeDerivatives */
 int metad_force_dot(const float* d_force_i, const float* d_force_j, unsigned N, double scale, double* d_out,

@@ -82,6 +82,7 @@ SIGNATURES = {
     "metad_grid_deltas_export": (C.c_int, [_vp, _vp, _vp, _vp]),
     "metad_grid_deltas_import": (C.c_int, [_vp, _vp, _vp, _vp]),
     "metad_grid_set_sigma_inv": (C.c_int, [_vp, C.POINTER(C.c_double)]),
+    "metad_set_double": (C.c_int, [_vp, C.c_double, _vp]),
     "metad_force_dot": (C.c_int, [_vp, _vp, C.c_uint, C.c_double, _vp, _vp]),
     "metad_grid_set_flags": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint]),
     "metad_grid_reset_histogram": (C.c_int, [_vp, _vp]),

@@ -312,6 +312,13 @@ template <int L> int run_z(metad_mesh* p, float2* buf, unsigned row_len, unsigne
         METAD_LAUNCH_CHECK();
         return METAD_OK;
     }
+    if (p->extras) {
+        constexpr int MB = (kLines * L / kE) <= 256 ? 2 : 1;
+        int rcx = set_smem(fft_z_fused_kernel<L, MB, true>, smem); if (rcx) return rcx;
+        METAD_CUDA(launch_pdl(p->pdl, fft_z_fused_kernel<L, MB, true>, nblocks, kLines * L / kE, smem, st, buf, p->d_twz, cp));
+        METAD_LAUNCH_CHECK();
+        return METAD_OK;
+    }
     int rc = set_smem(fft_z_fused_kernel<L>, smem); if (rc) return rc;
     METAD_CUDA(launch_pdl(p->pdl, fft_z_fused_kernel<L>, nblocks, kLines * L / kE, smem, st, buf, p->d_twz, cp));
     METAD_LAUNCH_CHECK();

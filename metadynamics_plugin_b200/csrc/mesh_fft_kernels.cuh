@@ -456,12 +456,13 @@ fft_y_kernel(float2* __restrict__ buf, const float2* __restrict__ g_tw, unsigned
 }
 
 // energy partial -> per-block slot; the last block of the LAST kernel (main z pass) sums all slots in order
+template <bool EXTRAS = false>
 __device__ __forceinline__ void energy_block_finish(double e, const ConvParams& cp, const ExtraAcc* xa = nullptr) {
     __shared__ double red[32];
     __shared__ unsigned long long kred[32];
     __shared__ bool is_last;
     const unsigned slot = blockIdx.x, total_slots = gridDim.x;
-    if (cp.extras && xa) {
+    if (EXTRAS && xa) {
         for (int c = 0; c < 6; ++c) {
             const double r = block_sum(xa->v[c], red);
             if (threadIdx.x == 0) cp.vir_partials[6 * (size_t)slot + c] = r;
@@ -489,7 +490,7 @@ __device__ __forceinline__ void energy_block_finish(double e, const ConvParams& 
     double s = 0.0;
     for (unsigned b = threadIdx.x; b < total_slots; b += blockDim.x) s += __ldcg(cp.partials + b);
     s = block_sum(s, red);
-    if (cp.extras) {
+    if (EXTRAS) {
         for (int c = 0; c < 6; ++c) {
             double v = 0.0;
             for (unsigned b = threadIdx.x; b < total_slots; b += blockDim.x) v += __ldcg(cp.vir_partials + 6 * (size_t)b + c);
@@ -509,7 +510,7 @@ __device__ __forceinline__ void energy_block_finish(double e, const ConvParams& 
 // z pass fused with the convolution and the CV energy: forward z FFT -> G^H -> inverse z FFT.
 // tile = 16 consecutive kx  x  all z, fixed y.  Column kx = 0 is left to the plane0 blocks of the same launch.
 // ---------------------------------------------------------------------------------------------------
-template <int L>
+template <int L, bool EXTRAS>
 __device__ __forceinline__ void z_general_body(float2* __restrict__ buf, const float2* __restrict__ g_tw, const ConvParams& cp,
                                                unsigned bx, unsigned by, float2* smem) {
     float2* tile = smem;
@@ -540,7 +541,7 @@ __device__ __forceinline__ void z_general_body(float2* __restrict__ buf, const f
         const int ww = idx & (kLines - 1);
         const unsigned kz = idx / kLines;
         if (cp.kx_off + kx0 + ww == 0) continue;
-        if (cp.extras) {
+        if (EXTRAS) {
             const float fr = tile[idx].x * cp.inv_n, fi = tile[idx].y * cp.inv_n;
             extra_add(xa, cp, fr * fr + fi * fi, cp.kx_off + kx0 + ww, ky, kz, 2.0f);
         }
@@ -557,7 +558,7 @@ __device__ __forceinline__ void z_general_body(float2* __restrict__ buf, const f
         if (has_col0 && w2 == 0) dst[1] = make_float2(v.z, v.w);
         else *reinterpret_cast<float4*>(dst) = v;
     }
-    energy_block_finish(e, cp, &xa);
+    energy_block_finish<EXTRAS>(e, cp, &xa);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -566,7 +567,7 @@ __device__ __forceinline__ void z_general_body(float2* __restrict__ buf, const f
 // spectrum, B = (Z(ky,kz) - conj Z(-ky,-kz))/(2i) the kx = nx/2 spectrum; both are convolved, re-packed as
 // A' + i B' and transformed back.  grid = ceil((ny/2+1)/8)
 // ---------------------------------------------------------------------------------------------------
-template <int L>
+template <int L, bool EXTRAS>
 __device__ __forceinline__ void z_plane0_body(float2* __restrict__ buf, const float2* __restrict__ g_tw, const ConvParams& cp,
                                               unsigned blk, float2* smem) {
     float2* tile = smem;
@@ -606,7 +607,7 @@ __device__ __forceinline__ void z_plane0_body(float2* __restrict__ buf, const fl
         const unsigned ky = (ww & 1) ? pky : kyp;
         const bool valid = kyp <= ny / 2;
         const bool counted = valid && (!(ww & 1) || pky != kyp);
-        if (cp.extras && counted) {
+        if (EXTRAS && counted) {
             // the kx = 0 mode A and the kx = nx/2 mode B of this (ky, kz), untangled as in conv_plane0
             const float2 z1 = tile[idx], z2 = cconj(tile[((L - kz) % L) * kLines + (ww ^ 1)]);
             const float ar = 0.5f * (z1.x + z2.x) * cp.inv_n, ai = 0.5f * (z1.y + z2.y) * cp.inv_n;
@@ -630,20 +631,22 @@ __device__ __forceinline__ void z_plane0_body(float2* __restrict__ buf, const fl
         const unsigned ky = (ww & 1) ? pky : kyp;
         buf[(size_t)ky * nxh + (size_t)l * zstride] = tile[idx];
     }
-    energy_block_finish(e, cp, &xa);
+    energy_block_finish<EXTRAS>(e, cp, &xa);
 }
 
 // one launch: blocks [0, n_blocks_plane0) untangle the kx = 0 slot, the rest are (kx tile, ky) blocks of the general case
-template <int L, int MINB = ((kLines * L / kE) <= 256 ? 3 : 1)>
+// EXTRAS: with the q_max / virial epilogues (a separate instantiation: their accumulators cost registers the default step
+// should not pay for -- measured 0.059 -> 0.068 ms at C4 when they were a run-time branch)
+template <int L, int MINB = ((kLines * L / kE) <= 256 ? 3 : 1), bool EXTRAS = false>
 __global__ void __launch_bounds__(kLines * L / kE, MINB)
 fft_z_fused_kernel(float2* __restrict__ buf, const float2* __restrict__ g_tw, ConvParams cp) {
     extern __shared__ float2 smem[];
     pdl_wait(); pdl_trigger();
     if (blockIdx.x < cp.n_blocks_plane0) {
-        z_plane0_body<L>(buf, g_tw, cp, blockIdx.x, smem);
+        z_plane0_body<L, EXTRAS>(buf, g_tw, cp, blockIdx.x, smem);
     } else {
         const unsigned b = blockIdx.x - cp.n_blocks_plane0, ntx = cp.row_len / kLines;
-        z_general_body<L>(buf, g_tw, cp, b % ntx, b / ntx, smem);
+        z_general_body<L, EXTRAS>(buf, g_tw, cp, b % ntx, b / ntx, smem);
     }
 }
 

@@ -113,6 +113,8 @@ __global__ void umbrella_kernel(int kind, double cv0, double kappa, double width
     if (d_energy_out) *d_energy_out = energy;
 }
 
+__global__ void set_double_kernel(double* __restrict__ dst, double v) { *dst = v; }
+
 __global__ void __launch_bounds__(kWteThreads)
 accumulate_force_kernel(float4* __restrict__ net, const float4* __restrict__ f, unsigned N, int init) {
     const unsigned stride = gridDim.x * blockDim.x;
@@ -160,6 +162,15 @@ static int wte_scratch(cudaStream_t stream, WteScratch** out) {
 }  // namespace metad
 
 using namespace metad;
+
+// A host scalar into device memory WITHOUT a staging buffer or a synchronisation: the value travels as a kernel argument
+// (copied at launch).  What the host-side CVs (box ratios, densities) use to hand their value to the device-resident step.
+extern "C" int metad_set_double(double* d_dst, double value, metad_stream_t stream) {
+    METAD_REQUIRE(d_dst, "metad_set_double: null destination");
+    set_double_kernel<<<1, 1, 0, stream>>>(d_dst, value);
+    METAD_LAUNCH_CHECK();
+    return METAD_OK;
+}
 
 extern "C" int metad_force_dot(const float* d_force_i, const float* d_force_j, unsigned N, double scale, double* d_out,
                                metad_stream_t stream) {

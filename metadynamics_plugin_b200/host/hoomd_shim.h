@@ -177,7 +177,10 @@ class ForceCompute {
     size_t getVirialPitch() const { return (m_force.size() + 15) / 16 * 16; }
     Scalar getExternalEnergy() const { return m_external_energy; }
     void setExternalEnergy(Scalar e) { m_external_energy = e; }
-    Scalar getExternalVirial(unsigned i) const { return m_external_virial[i]; }
+    // force computes whose external virial needs a device -> host round trip evaluate it when it is read (HOOMD reads it only
+    // when the pressure is needed), not in every step
+    Scalar getExternalVirial(unsigned i) { updateExternalVirial(); return m_external_virial[i]; }
+    virtual void updateExternalVirial() {}
     virtual std::vector<std::string> getProvidedLogQuantities() { return {}; }
     virtual Scalar getLogValue(const std::string& quantity, unsigned) { throw std::runtime_error("Error querying log quantity " + quantity); }
     bool enabled = true;             // cv.potential_energy disables itself as a regular ForceCompute (cv.py:490)

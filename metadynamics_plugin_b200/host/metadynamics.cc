@@ -11,19 +11,17 @@ static cudaStream_t stream_of(const std::shared_ptr<ExecutionConfiguration>& e) 
 
 // ================================================================================================ CollectiveVariable
 CollectiveVariable::CollectiveVariable(std::shared_ptr<SystemDefinition> sysdef, const std::string& name)
-    : ForceCompute(sysdef), m_cv_name(name), m_d_scalars(3) {}
+    : ForceCompute(sysdef), m_cv_name(name), m_d_scalars(4) {}
 
+// host scalars travel to the device as kernel arguments (metad_set_double): no staging buffer, no synchronisation -- a CV
+// that is a host scalar (AspectRatio, Density) no longer stalls the device-resident step every time step
 const double* CollectiveVariable::getCurrentValueDevice(unsigned int timestep) {
-    const double v = (double)getCurrentValue(timestep);
-    cuda_check(cudaMemcpyAsync(m_d_scalars.data() + 2, &v, sizeof(double), cudaMemcpyHostToDevice, stream_of(m_exec_conf)), "cv upload");
-    cuda_check(cudaStreamSynchronize(stream_of(m_exec_conf)), "cv upload sync");     // v is a stack variable
+    metad_check(metad_set_double(m_d_scalars.data() + 2, (double)getCurrentValue(timestep), stream_of(m_exec_conf)), "metad_set_double");
     return m_d_scalars.data() + 2;
 }
 
 void CollectiveVariable::setBiasFactor(Scalar bias) {
-    const double b = (double)bias;
-    cuda_check(cudaMemcpyAsync(m_d_scalars.data(), &b, sizeof(double), cudaMemcpyHostToDevice, stream_of(m_exec_conf)), "bias upload");
-    cuda_check(cudaStreamSynchronize(stream_of(m_exec_conf)), "bias upload sync");
+    metad_check(metad_set_double(m_d_scalars.data(), (double)bias, stream_of(m_exec_conf)), "metad_set_double");
 }
 
 void CollectiveVariable::setBiasFactorDevice(const double* d_bias) {
@@ -41,6 +39,17 @@ Scalar CollectiveVariable::biasHost() {
     double b = 0;
     cuda_check(cudaStreamSynchronize(stream_of(m_exec_conf)), "sync");
     cuda_check(cudaMemcpy(&b, biasDevice(), sizeof(double), cudaMemcpyDeviceToHost), "bias download");
+    return (Scalar)b;
+}
+
+void CollectiveVariable::keepBiasForVirial() {
+    cuda_check(cudaMemcpyAsync(m_d_scalars.data() + 3, biasDevice(), sizeof(double), cudaMemcpyDeviceToDevice, stream_of(m_exec_conf)), "bias keep");
+    m_virial_dirty = true;
+}
+Scalar CollectiveVariable::keptBias() {
+    double b = 0;
+    cuda_check(cudaStreamSynchronize(stream_of(m_exec_conf)), "sync");
+    cuda_check(cudaMemcpy(&b, m_d_scalars.data() + 3, sizeof(double), cudaMemcpyDeviceToHost), "bias download");
     return (Scalar)b;
 }
 
@@ -266,8 +275,14 @@ void WellTemperedEnsemble::computeBiasForces(unsigned int) {
     metad_check(metad_wte_scale((float*)m_pdata->getNetForce().data(), (float*)m_pdata->getNetTorqueArray().data(),
                                 m_pdata->getNetVirial().data(), m_pdata->getNetVirialPitch(), m_pdata->getN(), biasDevice(),
                                 stream_of(m_exec_conf)), "metad_wte_scale");
-    const Scalar fac = Scalar(1.0) + biasHost();        // the same factor as the device side: bias incl. the umbrella increment
-    for (unsigned int i = 0; i < 6; ++i) m_pdata->setExternalVirial(i, fac * m_pdata->getExternalVirial(i));
+    // external virial of the other forces times the same factor (:180-184).  The factor lives on the device: it is read back
+    // only if there is something to scale (no external virial contributions: no host round trip in the step)
+    bool any = false;
+    for (unsigned int i = 0; i < 6; ++i) any = any || m_pdata->getExternalVirial(i) != Scalar(0.0);
+    if (any) {
+        const Scalar fac = Scalar(1.0) + biasHost();    // bias incl. the umbrella increment, like the device side
+        for (unsigned int i = 0; i < 6; ++i) m_pdata->setExternalVirial(i, fac * m_pdata->getExternalVirial(i));
+    }
 }
 std::vector<std::string> WellTemperedEnsemble::getProvidedLogQuantities() {
     auto l = CollectiveVariable::getProvidedLogQuantities();
@@ -338,11 +353,15 @@ Scalar AspectRatio::getCurrentValue(unsigned int) {
     else length2 = l[m_dir2];
     return length1 / length2;
 }
-// AspectRatio.cc:59-130
-void AspectRatio::computeBiasForces(unsigned int) {
+// AspectRatio.cc:59-130: the "bias force" of a box CV is an external virial, -bias ds/dL_a L_a.  The factor stays on the
+// device (it comes out of the grid kernel); the six numbers are evaluated when they are read.
+void AspectRatio::computeBiasForces(unsigned int) { keepBiasForVirial(); }
+void AspectRatio::updateExternalVirial() {
+    if (!m_virial_dirty) return;
+    m_virial_dirty = false;
     const BoxDim& box = m_pdata->getGlobalBox();
     const Scalar3 L = box.getL();
-    const Scalar bias = biasHost();
+    const Scalar bias = keptBias();
     Scalar dx(0.0), dy(0.0), dz(0.0);
     if (m_dir1 == 0 && m_dir2 == 1) { dx = Scalar(1.0) / L.y; dy = -L.x / L.y / L.y; }
     else if (m_dir1 == 0 && m_dir2 == 2) { dx = Scalar(1.0) / L.z; dz = -L.x / L.z / L.z; }
@@ -362,13 +381,16 @@ Density::Density(std::shared_ptr<SystemDefinition> sysdef, const std::string& su
     : CollectiveVariable(sysdef, "cv_density" + (suffix != "" ? "_" + suffix : "")) {}
 // Density.cc:20-27 (group = all particles in the shim)
 Scalar Density::getCurrentValue(unsigned int) { return (Scalar)m_pdata->getNGlobal() / (Scalar)m_pdata->getGlobalBox().getVolume(); }
-// Density.cc:29-54
-void Density::computeBiasForces(unsigned int) {
+// Density.cc:29-54 (evaluated lazily, like AspectRatio)
+void Density::computeBiasForces(unsigned int) { keepBiasForVirial(); }
+void Density::updateExternalVirial() {
+    if (!m_virial_dirty) return;
+    m_virial_dirty = false;
     const BoxDim& box = m_pdata->getGlobalBox();
     const Scalar V = (Scalar)box.getVolume();
     const Scalar3 L = box.getL();
     const Scalar fac = -(Scalar)m_pdata->getNGlobal() / (V * V);
-    const Scalar v = -biasHost() * fac * L.x * L.y * L.z;
+    const Scalar v = -keptBias() * fac * L.x * L.y * L.z;
     m_external_virial[0] = v; m_external_virial[1] = 0; m_external_virial[2] = 0;
     m_external_virial[3] = v; m_external_virial[4] = 0; m_external_virial[5] = v;
 }

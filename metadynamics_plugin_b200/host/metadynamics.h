@@ -59,7 +59,13 @@ class CollectiveVariable : public ForceCompute {
     Scalar biasHost();
 
     std::string m_cv_name;
-    DeviceArray<double> m_d_scalars;   // [0] bias factor from the integrator/host, [1] bias incl. umbrella, [2] CV value
+    DeviceArray<double> m_d_scalars;   // [0] bias factor from the integrator/host, [1] bias incl. umbrella, [2] CV value,
+                                       // [3] the factor of the last computeBiasForces (kept for a lazily evaluated external virial)
+    // host-scalar CVs: remember the factor of this computeBiasForces on the device; the external virial is evaluated from it
+    // when somebody reads it (updateExternalVirial), so the step itself has no device -> host round trip
+    void keepBiasForVirial();
+    Scalar keptBias();
+    bool m_virial_dirty = false;
     bool m_bias_with_umbrella = false;
 
   private:
@@ -137,6 +143,7 @@ class AspectRatio : public CollectiveVariable {
     AspectRatio(std::shared_ptr<SystemDefinition> sysdef, unsigned int dir1, unsigned int dir2);
     Scalar getCurrentValue(unsigned int timestep) override;
     bool canComputeDerivatives() override { return false; }
+    void updateExternalVirial() override;
 
   protected:
     void computeBiasForces(unsigned int timestep) override;
@@ -148,6 +155,7 @@ class Density : public CollectiveVariable {
     Density(std::shared_ptr<SystemDefinition> sysdef, const std::string& suffix);
     Scalar getCurrentValue(unsigned int timestep) override;
     bool canComputeDerivatives() override { return false; }
+    void updateExternalVirial() override;
 
   protected:
     void computeBiasForces(unsigned int timestep) override;

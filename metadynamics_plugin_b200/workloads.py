@@ -24,6 +24,19 @@ def _cell_order(pos, L, n):
     return np.argsort(key, kind="stable")
 
 
+def _morton_order(pos, L, n, coarse=4, seed=1):
+    """Space-filling-curve order on COARSE cells (coarse^3 mesh cells each), random inside a coarse cell: what an MD engine's
+    periodic SFC sort looks like some steps after the sort -- spatially local, but not sorted by mesh cell."""
+    rng = np.random.default_rng(seed)
+    shuffle = rng.permutation(pos.shape[0])
+    c = (np.floor((pos[shuffle].astype(np.float64) + L / 2.0) / L * n).astype(np.int64) % n) // coarse
+    key = np.zeros(pos.shape[0], dtype=np.int64)
+    for b in range(10):
+        for d in range(3):
+            key |= ((c[:, d] >> b) & 1) << (3 * b + d)
+    return shuffle[np.argsort(key, kind="stable")]
+
+
 def c1(seed=20260101):
     """test/test_mesh.py geometry: N=1000 jittered simple-cubic lattice, L=10, mesh 32^3, harmonic umbrella."""
     rng = np.random.default_rng(seed)
@@ -54,10 +67,13 @@ def c2(seed=20260102, N=262144):
 
 
 def random_mesh(N, nmesh, seed, sort=True, name="C3"):
+    """sort: True / "cell" = row-major mesh-cell order (headline), "sfc" = Morton order on 4^3-cell blocks, False = random."""
     rng = np.random.default_rng(seed)
     L = float(N) ** (1.0 / 3.0)
     pos = ((rng.random((N, 3)) - 0.5) * L).astype(np.float32)
-    if sort:
+    if sort == "sfc":
+        pos = pos[_morton_order(pos, L, nmesh)]
+    elif sort:
         pos = pos[_cell_order(pos, L, nmesh)]
     return dict(name=name, kind="mesh", postype=_postype(pos, np.zeros(N, np.int32)), L=L, mode=[1.0],
                 mesh=(nmesh, nmesh, nmesh), stride=100)
