@@ -42,6 +42,29 @@ inline cudaError_t launch_pdl(bool pdl, void (*kernel)(Exp...), dim3 grid, dim3 
 }
 #endif
 
+#ifdef __CUDACC__
+// the same with a thread-block cluster of `cluster_x` CTAs along x (distributed shared memory between them)
+template <class... Exp, class... Act>
+inline cudaError_t launch_cluster_pdl(bool pdl, unsigned cluster_x, void (*kernel)(Exp...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Act&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (cluster_x > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = cluster_x; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (pdl) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = attr; cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<Exp>(args)...);
+}
+#endif
+
 #define METAD_REQUIRE(cond, msg)                 \
     do {                                         \
         if (!(cond)) {                           \

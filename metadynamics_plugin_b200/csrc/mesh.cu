@@ -28,6 +28,7 @@
 // between them.  Integer halo addition makes the sharded density bitwise equal to the single-GPU one.
 #include "mesh_kernels.cuh"
 #include "mesh_fft_kernels.cuh"
+#include "mesh_fft_xy.cuh"
 #include "mesh_p2p.cuh"
 
 #include <cuda.h>            // CUtensorMap + cuTensorMapEncodeTiled (resolved through cudaGetDriverEntryPoint, no -lcuda)
@@ -78,6 +79,12 @@ struct metad_mesh {
     bool cache = true;
     bool tma_flush = true;          // knob 10: flush the spread tile with 3-D tensor-map reductions
     int spread_debug = 0;           // knob 12: timing experiments (wrong results)
+    // knob 15: x and y sweeps fused on whole z planes by thread-block clusters (mesh_fft_xy.cuh): three sweeps instead of five.
+    // 0 = never, 1 = where it was measured faster (default), 2 = wherever an instantiation exists.  Measured on B200
+    // (profiles/r02_notes.md): 128 x 128 planes (one CTA per plane) 0.0229 -> 0.0145 ms forward, 0.0244 -> 0.0148 ms inverse at C3;
+    // 256 x 256 planes (clusters of 2 / 4 / 8 CTAs over distributed shared memory) 0.084 -> 0.087..0.107 ms forward, 0.070 ->
+    // 0.089..0.111 ms inverse at C4: correct, but slower than the separate sweeps -- one or two CTAs per SM with long serial phases.
+    int fuse_xy = 1;
     // knob 13: epilogues of the fused z sweep -- arg-max of |f_k|^2 (q*_max / sq_max log quantities, computeQmax) and the
     // k-space virial sums (computeVirial) with the tabulated kernel derivative of metad_mesh_set_table
     bool extras = false;
@@ -350,11 +357,80 @@ int markp(metad_mesh* p, int i, cudaStream_t st) {
     return METAD_OK;
 }
 
+// fused x + y sweeps of one unsharded plan; inverse = false: density -> [z][y][kx] spectrum, true: spectrum -> real rows in place
+template <int LC, int LY, int C, int NT> int run_xy(metad_mesh* p, bool inverse, cudaStream_t st) {
+    using P = XYPlan<LC, LY, C, NT>;
+    float2* buf = reinterpret_cast<float2*>(p->d_buf);
+    const dim3 grid(C, p->g.nz);
+    if (inverse) {
+        int rc = set_smem(fft_xy_inv_kernel<LC, LY, C, NT>, P::smem_bytes); if (rc) return rc;
+        METAD_CUDA(launch_cluster_pdl(p->pdl, C, fft_xy_inv_kernel<LC, LY, C, NT>, grid, P::NT, P::smem_bytes, st, buf, p->d_twx, p->d_twy));
+        METAD_LAUNCH_CHECK();
+        return METAD_OK;
+    }
+    DensityIn in;
+    memset(&in, 0, sizeof in);
+    in.mesh = reinterpret_cast<const int2*>(p->d_mesh_i);
+    in.d_fx = p->d_fx;
+    in.d_sums = p->d_sums;
+    in.inv_cells = 1.0 / ((double)p->g.nx * (double)p->g.ny * (double)p->nzg);
+    in.lgy = p->g.lgy; in.nz = p->g.nz;
+    in.zero = reinterpret_cast<int4*>(p->d_mesh_i);
+    in.mesh64 = reinterpret_cast<const longlong2*>(p->d_mesh64);
+    in.zero64 = reinterpret_cast<int4*>(p->d_mesh64);
+    in.range_counter = p->d_counters + 6;
+    in.h_range = p->h_counters + 3;
+    if (p->wide) {
+        int rc = set_smem(fft_xy_fwd_kernel<LC, LY, C, NT, true>, P::smem_bytes); if (rc) return rc;
+        METAD_CUDA(launch_cluster_pdl(p->pdl, C, fft_xy_fwd_kernel<LC, LY, C, NT, true>, grid, P::NT, P::smem_bytes, st, in, p->d_twx, p->d_twy, buf));
+    } else {
+        int rc = set_smem(fft_xy_fwd_kernel<LC, LY, C, NT, false>, P::smem_bytes); if (rc) return rc;
+        METAD_CUDA(launch_cluster_pdl(p->pdl, C, fft_xy_fwd_kernel<LC, LY, C, NT, false>, grid, P::NT, P::smem_bytes, st, in, p->d_twx, p->d_twy, buf));
+    }
+    METAD_LAUNCH_CHECK();
+    return METAD_OK;
+}
+// plane shapes with a fused instantiation: (nx/2, ny) -> cluster size
+bool can_fuse_xy(const metad_mesh* p) {
+    if (!p->fuse_xy || p->g.slab || p->keep_rho) return false;
+    const unsigned lc = p->g.nx / 2, ly = p->g.ny;
+    if (lc == 64 && ly == 128) return true;
+    return p->fuse_xy >= 2 && ((lc == 128 && ly == 256) || (lc == 256 && ly == 512));
+}
+int dispatch_xy(metad_mesh* p, bool inverse, cudaStream_t st) {
+    const unsigned lc = p->g.nx / 2;
+    // cluster size / CTA size per plane shape (METAD_XY_VARIANT selects the alternatives for experiments)
+    static const int variant = getenv("METAD_XY_VARIANT") ? atoi(getenv("METAD_XY_VARIANT")) : 0;
+    if (lc == 128) {
+        if (variant == 1) return run_xy<128, 256, 4, 256>(p, inverse, st);
+        if (variant == 2) return run_xy<128, 256, 8, 256>(p, inverse, st);
+        if (variant == 3) return run_xy<128, 256, 4, 512>(p, inverse, st);
+        return run_xy<128, 256, 2, 512>(p, inverse, st);
+    }
+    if (lc == 64) {
+        if (variant == 1) return run_xy<64, 128, 2, 256>(p, inverse, st);
+        if (variant == 2) return run_xy<64, 128, 2, 128>(p, inverse, st);
+        return run_xy<64, 128, 1, 512>(p, inverse, st);
+    }
+    return run_xy<256, 512, 8, 512>(p, inverse, st);
+}
+
 int fft_pipeline(metad_mesh* p, unsigned N_global, double* d_cv, cudaStream_t st) {
     int rc = METAD_OK;
     float2* buf = reinterpret_cast<float2*>(p->d_buf);
     const unsigned nxh = p->g.nx / 2;
     if (p->keep_rho && !p->d_rho_keep) METAD_CUDA(cudaMalloc(&p->d_rho_keep, sizeof(float) * p->M()));
+    if (can_fuse_xy(p)) {       // three sweeps: xy forward, fused z, xy inverse (stage timers: the y slots stay empty)
+        rc = mark(p, 2, st); if (rc) return rc;
+        rc = dispatch_xy(p, false, st); if (rc) return rc;
+        rc = mark(p, 3, st); if (rc) return rc;
+        rc = mark(p, 4, st); if (rc) return rc;
+        METAD_DISPATCH_LEN(p->g.nz, (run_z<LL>(p, buf, nxh, 0, p->d_sums, N_global, d_cv, st))); if (rc) return rc;
+        rc = mark(p, 5, st); if (rc) return rc;
+        rc = mark(p, 6, st); if (rc) return rc;
+        rc = dispatch_xy(p, true, st); if (rc) return rc;
+        return mark(p, 7, st);
+    }
     rc = mark(p, 2, st); if (rc) return rc;
     METAD_DISPATCH_LEN(nxh, (run_x<LL>(p, false, nullptr, p->d_sums, nullptr, st))); if (rc) return rc;
     rc = mark(p, 3, st); if (rc) return rc;
@@ -627,7 +703,7 @@ metad_mesh::GraphKey make_key(metad_mesh* p, const void* postype, unsigned N, un
     k.postype = postype; k.N = N; k.N_global = N_global;
     for (int i = 0; i < 3; ++i) k.L[i] = box->L[i];
     k.d_cv = d_cv; k.stream = stream; k.kind = kind; k.keep_rho = p->keep_rho; k.keep_cells = p->keep_cells;
-    k.variant = (p->wide ? 1 : 0) | (p->cache ? 2 : 0) | (p->tma_flush ? 4 : 0) | (p->tma_gather ? 8 : 0) | (p->extras ? 16 : 0) | (p->use_table ? 32 : 0) |
+    k.variant = (p->fuse_xy << 6) | (p->wide ? 1 : 0) | (p->cache ? 2 : 0) | (p->tma_flush ? 4 : 0) | (p->tma_gather ? 8 : 0) | (p->extras ? 16 : 0) | (p->use_table ? 32 : 0) |
                 (int)(p->n_table << 8);
     return k;
 }
@@ -1364,6 +1440,7 @@ extern "C" int metad_mesh_set(metad_mesh* p, int key, long value) {
         case 11: p->tma_gather = value != 0; return METAD_OK;
         case 12: p->spread_debug = (int)value; return METAD_OK;
         case 13: p->extras = value != 0; return METAD_OK;
+        case 15: p->fuse_xy = (int)value; return METAD_OK;
         case 14: p->use_table = value != 0; return METAD_OK;
         default: set_error("metad_mesh_set: unknown key"); return METAD_ERR_INVALID;
     }

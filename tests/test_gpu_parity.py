@@ -336,6 +336,7 @@ def test_mesh_full_size_c3(gpu, oracle):
 FFT_LEN_CASES = [
     (32, 256, 16), (32, 16, 256), (512, 16, 16), (1024, 16, 16), (32, 512, 16), (32, 16, 512),
     (64, 128, 32), (256, 32, 128), (128, 64, 256),
+    (128, 128, 32), (256, 256, 16), (512, 512, 16),          # planes with a fused x+y instantiation (clusters of 1, 2, 8 CTAs)
 ]
 
 
@@ -366,6 +367,32 @@ def test_mesh_every_fft_length(gpu, oracle, dims):
     m32 = oracle.Mesh(*dims, modes, Lf, N, "f32")
     m32.assign(h_pt)
     assert np.array_equal(mesh.cells(), m32.cells())
+
+
+@pytest.mark.parametrize("dims", [(128, 128, 32), (256, 256, 32), (512, 512, 16)])
+def test_mesh_fused_xy_equals_separate_sweeps(gpu, dims):
+    """Knob 15: the x and y sweeps fused on whole z planes by thread-block clusters (distributed shared memory) perform the same
+    per-line arithmetic as the separate sweeps: CV, Re IFFT(G) and forces agree to rounding (here: bit for bit or a few ulps)."""
+    import torch
+    N = 200000
+    Lf = np.asarray(dims, float) * 0.9
+    pos, types = rand_pt(N, Lf, 2, 31)
+    d_pt = to_dev(gpu, pos, types)
+    box = gpu.Box.make(Lf)
+    bias = torch.tensor([0.9], dtype=torch.float64, device="cuda")
+    res = []
+    for fused in (2, 0):                                  # 2: every plane shape with a fused instantiation; 0: separate sweeps
+        mesh = gpu.Mesh(*dims, (1.0, -0.6))
+        mesh.set(15, fused)
+        cv = mesh.compute_cv(d_pt, N, box).cpu().item()
+        inv = np.asarray(mesh.inv(), dtype=np.float64)
+        f = mesh.forces(d_pt, N, box, bias).cpu().numpy()
+        cv2 = mesh.compute_cv(d_pt, N, box).cpu().item()          # the accumulator was cleared by the fused forward sweep
+        assert cv2 == cv
+        res.append((cv, inv, f))
+    assert res[0][0] == pytest.approx(res[1][0], rel=1e-9)
+    assert np.abs(res[0][1] - res[1][1]).max() <= 1e-6 * np.abs(res[1][1]).max()
+    assert np.abs(res[0][2] - res[1][2]).max() <= 1e-6 * np.abs(res[1][2]).max()
 
 
 def test_mesh_full_size_c4(gpu, oracle):
