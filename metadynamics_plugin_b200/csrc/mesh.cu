@@ -376,23 +376,16 @@ template <int LC, int LY, int C, int NT> int run_xy(metad_mesh* p, bool inverse,
     in.inv_cells = 1.0 / ((double)p->g.nx * (double)p->g.ny * (double)p->nzg);
     in.lgy = p->g.lgy; in.nz = p->g.nz;
     in.zero = reinterpret_cast<int4*>(p->d_mesh_i);
-    in.mesh64 = reinterpret_cast<const longlong2*>(p->d_mesh64);
-    in.zero64 = reinterpret_cast<int4*>(p->d_mesh64);
     in.range_counter = p->d_counters + 6;
     in.h_range = p->h_counters + 3;
-    if (p->wide) {
-        int rc = set_smem(fft_xy_fwd_kernel<LC, LY, C, NT, true>, P::smem_bytes); if (rc) return rc;
-        METAD_CUDA(launch_cluster_pdl(p->pdl, C, fft_xy_fwd_kernel<LC, LY, C, NT, true>, grid, P::NT, P::smem_bytes, st, in, p->d_twx, p->d_twy, buf));
-    } else {
-        int rc = set_smem(fft_xy_fwd_kernel<LC, LY, C, NT, false>, P::smem_bytes); if (rc) return rc;
-        METAD_CUDA(launch_cluster_pdl(p->pdl, C, fft_xy_fwd_kernel<LC, LY, C, NT, false>, grid, P::NT, P::smem_bytes, st, in, p->d_twx, p->d_twy, buf));
-    }
+    int rc = set_smem(fft_xy_fwd_kernel<LC, LY, C, NT>, P::smem_bytes); if (rc) return rc;
+    METAD_CUDA(launch_cluster_pdl(p->pdl, C, fft_xy_fwd_kernel<LC, LY, C, NT>, grid, P::NT, P::smem_bytes, st, in, p->d_twx, p->d_twy, buf));
     METAD_LAUNCH_CHECK();
     return METAD_OK;
 }
 // plane shapes with a fused instantiation: (nx/2, ny) -> cluster size
 bool can_fuse_xy(const metad_mesh* p) {
-    if (!p->fuse_xy || p->g.slab || p->keep_rho) return false;
+    if (!p->fuse_xy || p->g.slab || p->keep_rho || p->wide) return false;
     const unsigned lc = p->g.nx / 2, ly = p->g.ny;
     if (lc == 64 && ly == 128) return true;
     return p->fuse_xy >= 2 && ((lc == 128 && ly == 256) || (lc == 256 && ly == 512));
@@ -401,11 +394,11 @@ int dispatch_xy(metad_mesh* p, bool inverse, cudaStream_t st) {
     const unsigned lc = p->g.nx / 2;
     // cluster size / CTA size per plane shape (METAD_XY_VARIANT selects the alternatives for experiments)
     static const int variant = getenv("METAD_XY_VARIANT") ? atoi(getenv("METAD_XY_VARIANT")) : 0;
-    if (lc == 128) {
-        if (variant == 1) return run_xy<128, 256, 4, 256>(p, inverse, st);
+    if (lc == 128) {        // default: the fastest of the measured shapes (profiles/r02_notes.md)
+        if (variant == 1) return run_xy<128, 256, 2, 512>(p, inverse, st);
         if (variant == 2) return run_xy<128, 256, 8, 256>(p, inverse, st);
         if (variant == 3) return run_xy<128, 256, 4, 512>(p, inverse, st);
-        return run_xy<128, 256, 2, 512>(p, inverse, st);
+        return run_xy<128, 256, 4, 256>(p, inverse, st);
     }
     if (lc == 64) {
         if (variant == 1) return run_xy<64, 128, 2, 256>(p, inverse, st);

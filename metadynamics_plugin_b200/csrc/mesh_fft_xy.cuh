@@ -42,7 +42,8 @@ template <int LC, int LY, int C, int NT_ = 512> struct XYPlan {
 #ifdef __CUDACC__
 namespace cg = cooperative_groups;
 
-template <int LC, int LY, int C, int NT, bool WIDE>
+// (32-bit density only: a plan that accumulates in 64 bits takes the separate sweeps)
+template <int LC, int LY, int C, int NT>
 __global__ void __launch_bounds__(NT, (XYPlan<LC, LY, C, NT>::MINB))
 fft_xy_fwd_kernel(DensityIn in, const float2* __restrict__ g_twx /* 2 LC */, const float2* __restrict__ g_twy /* LY */, float2* __restrict__ out) {
     using P = XYPlan<LC, LY, C, NT>;
@@ -66,19 +67,12 @@ fft_xy_fwd_kernel(DensityIn in, const float2* __restrict__ g_twx /* 2 LC */, con
         const unsigned y0 = crank * P::ROWS + (it * P::GX + g) * kLines;          // first row (y) of this group's tile
         const size_t row0 = (size_t)z * LY + y0;
         int4 vin[kE / 2];
-        longlong2 win[WIDE ? kE : 1];
 #pragma unroll
         for (int q = 0; q < kE / 2; ++q) {
             const int idx = lt + q * nthr;
-            if (WIDE) {
-                const longlong2* src = in.mesh64 + (row0 + idx / (LC / 2)) * LC + 2 * (idx % (LC / 2));
-                win[(2 * q) % (WIDE ? kE : 1)] = __ldcs(src);
-                win[(2 * q + 1) % (WIDE ? kE : 1)] = __ldcs(src + 1);
-            } else {
-                vin[q] = __ldcs(reinterpret_cast<const int4*>(in.mesh + (row0 + idx / (LC / 2)) * LC) + idx % (LC / 2));
-            }
+            vin[q] = __ldcs(reinterpret_cast<const int4*>(in.mesh + (row0 + idx / (LC / 2)) * LC) + idx % (LC / 2));
         }
-        if (!WIDE && in.range_counter) {
+        if (in.range_counter) {
             int m = 0;
 #pragma unroll
             for (int q = 0; q < kE / 2; ++q) m = max(m, max(max(abs(vin[q].x), abs(vin[q].y)), max(abs(vin[q].z), abs(vin[q].w))));
@@ -88,14 +82,8 @@ fft_xy_fwd_kernel(DensityIn in, const float2* __restrict__ g_twx /* 2 LC */, con
         for (int q2 = 0; q2 < kE; ++q2) {
             const int idx = lt + (q2 >> 1) * nthr;
             const int w = idx / (LC / 2), l = 2 * (idx % (LC / 2)) + (q2 & 1);
-            float2 r;
-            if (WIDE) {
-                const longlong2 v64 = win[q2 % (WIDE ? kE : 1)];
-                r = make_float2(__ll2float_rn(v64.x) * inv_scale, __ll2float_rn(v64.y) * inv_scale);
-            } else {
-                const int2 v = (q2 & 1) ? make_int2(vin[q2 >> 1].z, vin[q2 >> 1].w) : make_int2(vin[q2 >> 1].x, vin[q2 >> 1].y);
-                r = density_to_float(v, inv_scale);
-            }
+            const int2 v = (q2 & 1) ? make_int2(vin[q2 >> 1].z, vin[q2 >> 1].w) : make_int2(vin[q2 >> 1].x, vin[q2 >> 1].y);
+            float2 r = density_to_float(v, inv_scale);
             r.x -= mean; r.y -= mean;
             tile[LayoutRow::addr(w, l, LC)] = r;
         }
@@ -104,9 +92,7 @@ fft_xy_fwd_kernel(DensityIn in, const float2* __restrict__ g_twx /* 2 LC */, con
 #pragma unroll
             for (int q = 0; q < kE / 2; ++q) {
                 const int idx = lt + q * nthr;
-                const size_t row = row0 + idx / (LC / 2);
-                if (WIDE) { int4* dst = in.zero64 + row * LC + 2 * (idx % (LC / 2)); dst[0] = z4; dst[1] = z4; }
-                else in.zero[row * (LC / 2) + idx % (LC / 2)] = z4;
+                in.zero[(row0 + idx / (LC / 2)) * (LC / 2) + idx % (LC / 2)] = z4;
             }
         }
         __syncthreads();
