@@ -360,10 +360,12 @@ fft_x_fwd_kernel(DensityIn in, const float2* __restrict__ g_tw /* length 2*LC */
         peer_signal(sync);                                   // phase 1: my share of every pencil is stored
         return;
     }
-    for (int idx = threadIdx.x; idx < kLines * LC; idx += nthr) {
-        const int ww = idx / LC, l = idx % LC;
+#pragma unroll
+    for (int q = 0; q < kE / 2; ++q) {          // 128-bit stores: two coefficients of one part
+        const int idx = threadIdx.x + q * nthr, ww = idx / (LC / 2), l = 2 * (idx % (LC / 2));
         const size_t dst = ((size_t)(l >> lg_part) * rows_total + (row0 + ww)) * part_len + (l & (part_len - 1));
-        out[dst] = tile[LayoutRow::addr(ww, l, LC)];
+        const float2 a = tile[LayoutRow::addr(ww, l, LC)], b = tile[LayoutRow::addr(ww, l + 1, LC)];
+        *reinterpret_cast<float4*>(out + dst) = make_float4(a.x, a.y, b.x, b.y);
     }
 }
 
@@ -388,10 +390,19 @@ fft_x_inv_kernel(float2* buf, const float2* __restrict__ g_tw, const float2* in,
         *d_cv = cv;
     }
     const unsigned part_len = 1u << lg_part;
-    for (int idx = threadIdx.x; idx < kLines * LC; idx += nthr) {
-        const int w = idx / LC, l = idx % LC;
+    // 128-bit loads (two coefficients of one part: parts are at least 16 wide), all issued before the first use
+    float4 vin[kE / 2];
+#pragma unroll
+    for (int q = 0; q < kE / 2; ++q) {
+        const int idx = threadIdx.x + q * nthr, w = idx / (LC / 2), l = 2 * (idx % (LC / 2));
         const size_t src = ((size_t)(l >> lg_part) * rows_total + (row0 + w)) * part_len + (l & (part_len - 1));
-        tile[LayoutRow::addr(w, l, LC)] = in[src];
+        vin[q] = *reinterpret_cast<const float4*>(in + src);
+    }
+#pragma unroll
+    for (int q = 0; q < kE / 2; ++q) {
+        const int idx = threadIdx.x + q * nthr, w = idx / (LC / 2), l = 2 * (idx % (LC / 2));
+        tile[LayoutRow::addr(w, l, LC)] = make_float2(vin[q].x, vin[q].y);
+        tile[LayoutRow::addr(w, l + 1, LC)] = make_float2(vin[q].z, vin[q].w);
     }
     __syncthreads();
     for (int idx = threadIdx.x; idx < kLines * (LC / 2 + 1); idx += nthr) {
@@ -403,9 +414,11 @@ fft_x_inv_kernel(float2* buf, const float2* __restrict__ g_tw, const float2* in,
     __syncthreads();
     const int w = threadIdx.x & (kLines - 1), t = threadIdx.x / kLines;
     line_fft<LC, +1, 2 * LC, LayoutRow>(tile, w, t, s_tw);
-    for (int idx = threadIdx.x; idx < kLines * LC; idx += nthr) {
-        const int ww = idx / LC, l = idx % LC;
-        buf[(row0 + ww) * LC + l] = tile[LayoutRow::addr(ww, l, LC)];
+#pragma unroll
+    for (int q = 0; q < kE / 2; ++q) {
+        const int idx = threadIdx.x + q * nthr, ww = idx / (LC / 2), l = 2 * (idx % (LC / 2));
+        const float2 a = tile[LayoutRow::addr(ww, l, LC)], b = tile[LayoutRow::addr(ww, l + 1, LC)];
+        *reinterpret_cast<float4*>(buf + (row0 + ww) * LC + l) = make_float4(a.x, a.y, b.x, b.y);
     }
 }
 
