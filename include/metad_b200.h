@@ -182,7 +182,13 @@ int metad_mesh_get(metad_mesh* p, int which, void* h_out);
  *        key 6 = order of the particles inside a tile: 1 (default) bank order, 0 layer order (mesh_kernels.cuh); results
  *                do not depend on it
  *        key 7 = programmatic dependent launch of the per-step kernels: 1 (default) on, 0 off
- *        key 8 = peer-memory mode: halo push and the barrier after it in one launch: 1 on, 0 (default, measured faster) off */
+ *        key 8 = peer-memory mode: halo push and the barrier after it in one launch: 1 on, 0 (default, measured faster) off
+ *        key 9..15 = kernel variants for measurements (particle cache, tensor-map flush / gather, debug, q_max / virial
+ *                epilogues (13), use_table (14), fused x+y sweeps (15)); see csrc/mesh.cu
+ *        key 16 = triclinic boxes (box->tilt != 0): 1 (default) in-cell offsets exactly as the reference computes them --
+ *                OrderParameterMesh.cc:571-573 / 806-808 take makeFraction(shift_cart + lo), which shears `lo` too, so every
+ *                offset carries a constant ((xz - yz xy) Lz + xy Ly) nx / (2 Lx) along x and yz Lz ny / (2 Ly) along y and
+ *                TSC weight beyond |x| = 3/2 is dropped; 0 = geometrically correct offsets (set before the first call) */
 int metad_mesh_set(metad_mesh* p, int key, long value);
 
 /* ------------------------------------------------------------------------------------------------

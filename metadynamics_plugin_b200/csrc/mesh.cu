@@ -85,6 +85,10 @@ struct metad_mesh {
     // 256 x 256 planes (clusters of 2 / 4 / 8 CTAs over distributed shared memory) 0.084 -> 0.087..0.107 ms forward, 0.070 ->
     // 0.089..0.111 ms inverse at C4: correct, but slower than the separate sweeps -- one or two CTAs per SM with long serial phases.
     int fuse_xy = 1;
+    // knob 16: triclinic boxes -- 1 (default): the in-cell offsets carry the constant the reference's own code gives them
+    // (Geom::tq in mesh_kernels.cuh: makeFraction(shift + lo) shears `lo` as well, OrderParameterMesh.cc:571-573); weight
+    // is then lost exactly where the reference loses it.  0: geometrically correct assignment (partition of unity).
+    bool tilt_literal = true;
     // knob 13: epilogues of the fused z sweep -- arg-max of |f_k|^2 (q*_max / sq_max log quantities, computeQmax) and the
     // k-space virial sums (computeVirial) with the tabulated kernel derivative of metad_mesh_set_table
     bool extras = false;
@@ -95,7 +99,8 @@ struct metad_mesh {
     double* d_vir_partials = nullptr;
     unsigned long long* d_amax_key = nullptr;
     double* d_extras_out = nullptr;
-    double box_L[3] = {0, 0, 0};
+    double box_L[3] = {0, 0, 0}, box_tilt[3] = {0, 0, 0};
+    double box_b[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};      // reciprocal lattice vectors (rows), without 2 pi
     unsigned extras_N_global = 0;
     bool tma_gather = true;         // knob 11: load the gather tile with one 3-D tensor-map copy when it does not wrap
     alignas(64) CUtensorMap tmap_mesh = {};     // integer mesh (incl. ghost planes), box = padded tile
@@ -133,7 +138,7 @@ struct metad_mesh {
     // CUDA-graph replay of the per-call kernel sequence (metad_mesh_set key 4): everything a call enqueues after the
     // (eager) tile-order decision is captured once per argument signature and replayed with one launch
     bool graph_mode = false;
-    struct GraphKey { const void* postype; unsigned N, N_global; double L[3]; const void* d_cv; cudaStream_t stream; int kind; bool keep_rho, keep_cells; int variant; };
+    struct GraphKey { const void* postype; unsigned N, N_global; double L[3], tilt[3]; const void* d_cv; cudaStream_t stream; int kind; bool keep_rho, keep_cells; int variant; };
     GraphKey gkey = {};
     int gwarm = 0;
     cudaGraphExec_t gexec = nullptr;
@@ -283,6 +288,8 @@ template <int L> int run_z(metad_mesh* p, float2* buf, unsigned row_len, unsigne
     cp.inv_n = (float)(1.0 / (double)N_global);
     cp.n_global = (double)N_global;
     cp.d_mode_sq = d_sums;
+    cp.dc_restore = (p->g.tri && (p->g.tq[0] != 0.f || p->g.tq[1] != 0.f)) ? 1 : 0;
+    cp.inv_cells = 1.0 / ((double)p->g.nx * (double)p->g.ny * (double)p->nzg);
     cp.partials = p->d_partials;
     cp.ticket = p->d_ticket;
     cp.n_blocks_plane0 = kx_off == 0 ? (ny / 2 + 1 + kLines / 2 - 1) / (kLines / 2) : 0;
@@ -298,7 +305,8 @@ template <int L> int run_z(metad_mesh* p, float2* buf, unsigned row_len, unsigne
     cp.n_table = p->n_table; cp.table_d = p->d_table_d;
     cp.k_min = (float)p->k_min; cp.k_max = (float)p->k_max;
     cp.delta_k = p->n_table >= 2 ? (float)((p->k_max - p->k_min) / (double)(p->n_table - 1)) : 1.0f;
-    for (int i = 0; i < 3; ++i) cp.bk[i] = (float)(2.0 * M_PI / p->box_L[i]);
+    for (int i = 0; i < 3; ++i)
+        for (int c = 0; c < 3; ++c) cp.bk[3 * i + c] = (float)(2.0 * M_PI * p->box_b[i][c]);
     cp.vir_partials = p->d_vir_partials; cp.amax_key = p->d_amax_key; cp.extras_out = p->d_extras_out;
     if (p->extras) {
         if (!p->d_vir_partials) {
@@ -454,14 +462,22 @@ int ensure_capacity(metad_mesh* p, unsigned N) {
     return METAD_OK;
 }
 
+// reciprocal lattice vectors b_i = (a_j x a_k) / V of the box (rows of `b`, without 2 pi), a_1 = (Lx, 0, 0), a_2 = (xy Ly, Ly, 0),
+// a_3 = (xz Lz, yz Lz, Lz)  (OrderParameterMesh.cc:362-369, 761-769)
+void reciprocal_vectors(const double* L, const double* tilt, double (&b)[3][3]) {
+    const double a1[3] = {L[0], 0.0, 0.0}, a2[3] = {tilt[0] * L[1], L[1], 0.0}, a3[3] = {tilt[1] * L[2], tilt[2] * L[2], L[2]};
+    const double V = L[0] * L[1] * L[2];
+    auto cross = [&](const double* u, const double* v, double* o) {
+        o[0] = (u[1] * v[2] - u[2] * v[1]) / V; o[1] = (u[2] * v[0] - u[0] * v[2]) / V; o[2] = (u[0] * v[1] - u[1] * v[0]) / V;
+    };
+    cross(a2, a3, b[0]); cross(a3, a1, b[1]); cross(a1, a2, b[2]);
+}
+
 int set_box(metad_mesh* p, const metad_box* box) {
-    if (box->tilt[0] != 0.0 || box->tilt[1] != 0.0 || box->tilt[2] != 0.0) {
-        set_error("cv.mesh: triclinic boxes are not supported by the sm_100a mesh path yet");
-        return METAD_ERR_UNSUPPORTED;
-    }
     for (int i = 0; i < 3; ++i) METAD_REQUIRE(box->L[i] > 0.0, "cv.mesh: box lengths must be positive");
-    geom_set_box(p->g, box->L);          // the box is the GLOBAL box
-    for (int i = 0; i < 3; ++i) p->box_L[i] = box->L[i];
+    geom_set_box(p->g, box->L, box->tilt, p->tilt_literal);          // the box is the GLOBAL box
+    for (int i = 0; i < 3; ++i) { p->box_L[i] = box->L[i]; p->box_tilt[i] = box->tilt[i]; }
+    reciprocal_vectors(box->L, box->tilt, p->box_b);
     return METAD_OK;
 }
 
@@ -559,6 +575,8 @@ int dispatch_spread(metad_mesh* p, int flags, const float* d_postype, const Spre
 #define METAD_SP(F) case F: return launch_spread<LGT, F>(p, d_postype, out, stream);
         METAD_SP(0) METAD_SP(1) METAD_SP(2) METAD_SP(3) METAD_SP(4) METAD_SP(5) METAD_SP(6) METAD_SP(7)
         METAD_SP(8) METAD_SP(9) METAD_SP(10) METAD_SP(11)
+        // triclinic boxes (kSpTri): row flush only
+        METAD_SP(16) METAD_SP(17) METAD_SP(18) METAD_SP(19) METAD_SP(20) METAD_SP(21) METAD_SP(22) METAD_SP(23)
 #undef METAD_SP
         default: set_error("spread: unknown kernel variant"); return METAD_ERR_INVALID;
     }
@@ -634,8 +652,9 @@ int enqueue_spread(metad_mesh* p, const float* d_postype, unsigned N, cudaStream
     out.cache4 = p->d_cache4;
     out.debug = p->spread_debug;
     int flags = (p->keep_cells ? kSpKeys : 0) | (p->cache ? kSpCache : 0);
+    if (g.tri) flags |= kSpTri;
     if (p->wide) flags |= kSpWide;
-    else if (p->tma_flush && !g.slab) {
+    else if (p->tma_flush && !g.slab && !g.tri) {
         rc = ensure_tmaps(p); if (rc) return rc;
         flags |= kSpTma;
         out.tmap = p->tmap_mesh;
@@ -694,9 +713,9 @@ metad_mesh::GraphKey make_key(metad_mesh* p, const void* postype, unsigned N, un
     metad_mesh::GraphKey k;
     memset(&k, 0, sizeof k);
     k.postype = postype; k.N = N; k.N_global = N_global;
-    for (int i = 0; i < 3; ++i) k.L[i] = box->L[i];
+    for (int i = 0; i < 3; ++i) { k.L[i] = box->L[i]; k.tilt[i] = box->tilt[i]; }
     k.d_cv = d_cv; k.stream = stream; k.kind = kind; k.keep_rho = p->keep_rho; k.keep_cells = p->keep_cells;
-    k.variant = (p->fuse_xy << 6) | (p->wide ? 1 : 0) | (p->cache ? 2 : 0) | (p->tma_flush ? 4 : 0) | (p->tma_gather ? 8 : 0) | (p->extras ? 16 : 0) | (p->use_table ? 32 : 0) |
+    k.variant = (p->tilt_literal ? (1 << 30) : 0) | (p->fuse_xy << 6) | (p->wide ? 1 : 0) | (p->cache ? 2 : 0) | (p->tma_flush ? 4 : 0) | (p->tma_gather ? 8 : 0) | (p->extras ? 16 : 0) | (p->use_table ? 32 : 0) |
                 (int)(p->n_table << 8);
     return k;
 }
@@ -710,9 +729,15 @@ int launch_gather(metad_mesh* p, const float* d_postype, const float* d_ghost, f
     // reciprocal lattice vectors of the (orthorhombic) box without 2 pi, times the mesh dimensions (:761-769, :852-854)
     ForceParams fp;
     memset(&fp, 0, sizeof fp);
-    fp.nb1[0] = (float)((double)g.nx / box->L[0]);
-    fp.nb2[1] = (float)((double)g.ny / box->L[1]);
-    fp.nb3[2] = (float)((double)g.nzg / box->L[2]);
+    {
+        double b[3][3];
+        reciprocal_vectors(box->L, box->tilt, b);
+        for (int c = 0; c < 3; ++c) {
+            fp.nb1[c] = (float)((double)g.nx * b[0][c]);
+            fp.nb2[c] = (float)((double)g.ny * b[1][c]);
+            fp.nb3[c] = (float)((double)g.nzg * b[2][c]);
+        }
+    }
     fp.two_over_n = 2.0 / (double)N_global;
     int rc = mark(p, 8, stream); if (rc) return rc;
     GatherIn gin;
@@ -727,7 +752,29 @@ int launch_gather(metad_mesh* p, const float* d_postype, const float* d_ghost, f
         gin.tmap = p->tmap_inv;
         gin.use_tmap = 1;
     }
-    if (g.lgT == 4) {
+    if (g.tri) {
+        // triclinic box: general TSC weights (mesh_gather_kernel<..., TRI>); one CTA shape per tile size
+        if (g.lgT == 4) {
+            const size_t sm = tile_smem_bytes<4>() + gather_stage_bytes(192, p->cache, p->ntypes);
+            if (p->cache) {
+                rc = set_smem(mesh_gather_kernel<4, 192, 3, true, true>, tile_smem_bytes<4>() + gather_stage_bytes(192, true, kSpreadModes)); if (rc) return rc;
+                METAD_CUDA(launch_pdl(p->pdl, mesh_gather_kernel<4, 192, 3, true, true>, num_tiles(g), 192, sm, stream, gin, p->d_tstart, g, p->d_buf, d_ghost, fp,
+                                      d_bias, (float4*)d_force, ps));
+            } else {
+                rc = set_smem(mesh_gather_kernel<4, 192, 3, false, true>, tile_smem_bytes<4>() + gather_stage_bytes(192, false, kSpreadModes)); if (rc) return rc;
+                METAD_CUDA(launch_pdl(p->pdl, mesh_gather_kernel<4, 192, 3, false, true>, num_tiles(g), 192, sm, stream, gin, p->d_tstart, g, p->d_buf, d_ghost, fp,
+                                      d_bias, (float4*)d_force, ps));
+            }
+        } else {
+            const size_t sm = tile_smem_bytes<3>() + gather_stage_bytes(kGatherThreads, p->cache, p->ntypes);
+            if (p->cache)
+                METAD_CUDA(launch_pdl(p->pdl, mesh_gather_kernel<3, kGatherThreads, 3, true, true>, num_tiles(g), kGatherThreads, sm, stream, gin, p->d_tstart, g, p->d_buf,
+                                      d_ghost, fp, d_bias, (float4*)d_force, ps));
+            else
+                METAD_CUDA(launch_pdl(p->pdl, mesh_gather_kernel<3, kGatherThreads, 3, false, true>, num_tiles(g), kGatherThreads, sm, stream, gin, p->d_tstart, g, p->d_buf,
+                                      d_ghost, fp, d_bias, (float4*)d_force, ps));
+        }
+    } else if (g.lgT == 4) {
         // CTA size / residency of the gather.  Measured on B200 (C4, ms per launch): 256 threads x 3 CTAs/SM (80 registers, the loop
         // state spills) 0.238; 256 x 2 0.210; 192 x 3 (96 registers, no spill) 0.201; 128 x 5 0.216; 128 x 4 0.212; 192 x 4 0.247.
         // METAD_GATHER_VARIANT selects the others for experiments.
@@ -1379,13 +1426,15 @@ extern "C" int metad_mesh_get(metad_mesh* p, int which, void* h_out) {
             // ties (flat index 0 comes first in the reference's scan)
             const double ng = (double)p->extras_N_global, f0 = sums[1] / ng;
             double a = (double)amp;
-            if (key == 0 || f0 * f0 >= a) { a = f0 * f0; flat = 0; }
+            // (literal triclinic offsets: the kernel restored f_0 itself, ConvParams::dc_restore, and it is no longer sum a / N)
+            const bool dc_in_kernel = p->g.tri && (p->g.tq[0] != 0.f || p->g.tq[1] != 0.f);
+            if (!dc_in_kernel && (key == 0 || f0 * f0 >= a)) { a = f0 * f0; flat = 0; }
             if (!(a > 0.0)) flat = 0;
             const unsigned nx = p->g.nx, ny = p->g.ny, nz = p->nzg;
             const unsigned kx = flat % nx, ky = (flat / nx) % ny, kz = flat / (nx * ny);
-            out[6] = a > 0.0 ? (double)miller(kx, nx) * 2.0 * M_PI / p->box_L[0] : 0.0;
-            out[7] = a > 0.0 ? (double)miller(ky, ny) * 2.0 * M_PI / p->box_L[1] : 0.0;
-            out[8] = a > 0.0 ? (double)miller(kz, nz) * 2.0 * M_PI / p->box_L[2] : 0.0;
+            const double m3[3] = {(double)miller(kx, nx), (double)miller(ky, ny), (double)miller(kz, nz)};
+            for (int c = 0; c < 3; ++c)
+                out[6 + c] = a > 0.0 ? 2.0 * M_PI * (m3[0] * p->box_b[0][c] + m3[1] * p->box_b[1][c] + m3[2] * p->box_b[2][c]) : 0.0;
             out[9] = a * ng;
             out[10] = (double)flat;
             out[11] = a;
@@ -1434,6 +1483,7 @@ extern "C" int metad_mesh_set(metad_mesh* p, int key, long value) {
         case 12: p->spread_debug = (int)value; return METAD_OK;
         case 13: p->extras = value != 0; return METAD_OK;
         case 15: p->fuse_xy = (int)value; return METAD_OK;
+        case 16: p->tilt_literal = value != 0; return METAD_OK;
         case 14: p->use_table = value != 0; return METAD_OK;
         default: set_error("metad_mesh_set: unknown key"); return METAD_ERR_INVALID;
     }

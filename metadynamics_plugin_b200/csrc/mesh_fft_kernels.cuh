@@ -30,7 +30,12 @@ struct ConvParams {
     unsigned kx_off;              // global kx of local column 0 (0 unless sharded)
     float inv_n;                  // 1 / N_global
     double n_global;
-    const double* d_mode_sq;      // device: sum_j a_j^2 of this step
+    const double* d_mode_sq;      // device: sum_j a_j^2 of this step; [1] = sum_j a_j
+    // Triclinic boxes with the reference's literal offsets (Geom::tq): the derivative weights of a particle no longer sum to
+    // zero, so the k = 0 mode of G matters for the forces.  The forward x sweep removed mean = fl(sum a / M) from every cell;
+    // dc_restore puts M * mean / N back into f_0 before the convolution (the reference convolves k = 0 like every other mode).
+    int dc_restore;
+    double inv_cells;             // 1 / M (global number of cells), the value the forward x sweep uses
     double* partials;             // per-block energy partial sums
     unsigned* ticket;
     unsigned n_blocks_plane0;     // plane0 blocks write partials[0 .. n_blocks_plane0)
@@ -47,7 +52,7 @@ struct ConvParams {
     unsigned n_table;
     const float* table_d;         // device: derivative table dK(k), n_table entries on [k_min, k_max]
     float k_min, k_max, delta_k;
-    float bk[3];                  // 2 pi / L per axis: k = Miller index * bk (orthorhombic box)
+    float bk[9];                  // 2 pi b_i (rows): k = mx b_1 + my b_2 + mz b_3 (diagonal 2 pi / L for an orthorhombic box)
     double* vir_partials;         // [blocks][6]
     unsigned long long* amax_key; // packed {|f|^2 bits, ~flat index}: atomicMax over the blocks
     double* extras_out;           // [6] virial sums (without the bias factor)
@@ -73,7 +78,9 @@ MHD void extra_add(ExtraAcc& a, const ConvParams& cp, float val, unsigned kx, un
     const unsigned long long key = ((unsigned long long)vb << 32) | (unsigned long long)(0xFFFFFFFFu - flat);
     if (key > a.key) a.key = key;
     if (cp.use_table && fk != 0) {
-        const float k0 = (float)miller(kx, cp.nx) * cp.bk[0], k1 = (float)miller(ky, cp.ny) * cp.bk[1], k2 = (float)miller(kz, cp.nz) * cp.bk[2];
+        const float mx = (float)miller(kx, cp.nx), my = (float)miller(ky, cp.ny), mz = (float)miller(kz, cp.nz);
+        const float k0 = mx * cp.bk[0] + my * cp.bk[3] + mz * cp.bk[6], k1 = mx * cp.bk[1] + my * cp.bk[4] + mz * cp.bk[7],
+                    k2 = mx * cp.bk[2] + my * cp.bk[5] + mz * cp.bk[8];
         const float knorm = sqrtf(k0 * k0 + k1 * k1 + k2 * k2);
         if (knorm >= cp.k_min && knorm < cp.k_max) {
             const float vf = (knorm - cp.k_min) / cp.delta_k;
@@ -105,7 +112,7 @@ MHD float2 conv_general(float2 F, float inv_n, float d, bool chi_k, double& e) {
 // pointwise convolution of the packed kx = 0 slot: z1 = Z(ky,kz), z2 = Z(-ky,-kz) (not yet conjugated).
 // A = (z1 + conj z2)/2 is the kx = 0 mode, B = (z1 - conj z2)/(2i) the kx = nx/2 mode; returns A' + i B'.
 MHD float2 conv_plane0(float2 z1, float2 z2raw, float inv_n, float d, unsigned ky, unsigned kz, unsigned ny,
-                       unsigned nz, bool counted, double& e) {
+                       unsigned nz, bool counted, double& e, float dc = 0.f /* added to f_0 (ky = kz = 0 only), see ConvParams::dc_restore */) {
     const float2 z2 = cconj(z2raw);
     const float2 A = make_float2(0.5f * (z1.x + z2.x), 0.5f * (z1.y + z2.y));
     const float2 Dm = make_float2(0.5f * (z1.x - z2.x), 0.5f * (z1.y - z2.y));
@@ -113,7 +120,7 @@ MHD float2 conv_plane0(float2 z1, float2 z2raw, float inv_n, float d, unsigned k
     // kx = 0: chi_k = [ky>=0][kz>=0], chi_{-k} = [-ky>=0][-kz>=0]
     const float chis = 0.5f * ((nonneg(ky, ny) && nonneg(kz, nz) ? 1.0f : 0.0f) +
                                (nonneg((ny - ky) % ny, ny) && nonneg((nz - kz) % nz, nz) ? 1.0f : 0.0f));
-    const float ar = A.x * inv_n, ai = A.y * inv_n;
+    const float ar = A.x * inv_n + ((ky == 0 && kz == 0) ? dc : 0.f), ai = A.y * inv_n;
     const float va = ar * ar + ai * ai;
     const float ga = va - d * chis;
     const float2 GA = make_float2(ar * ga, ai * ga);
@@ -609,6 +616,11 @@ __device__ __forceinline__ void z_plane0_body(float2* __restrict__ buf, const fl
     double e = 0.0;
     ExtraAcc xa;
     extra_init(xa);
+    float dc = 0.f;
+    if (cp.dc_restore) {
+        const float mean = (float)(cp.d_mode_sq[1] * cp.inv_cells);       // the value the forward x sweep subtracted from every cell
+        dc = (float)((double)mean / cp.inv_cells * (double)cp.inv_n);
+    }
     float2 outv[per_thread];
 #pragma unroll
     for (int it = 0; it < per_thread; ++it) {
@@ -623,12 +635,12 @@ __device__ __forceinline__ void z_plane0_body(float2* __restrict__ buf, const fl
         if (EXTRAS && counted) {
             // the kx = 0 mode A and the kx = nx/2 mode B of this (ky, kz), untangled as in conv_plane0
             const float2 z1 = tile[idx], z2 = cconj(tile[((L - kz) % L) * kLines + (ww ^ 1)]);
-            const float ar = 0.5f * (z1.x + z2.x) * cp.inv_n, ai = 0.5f * (z1.y + z2.y) * cp.inv_n;
+            const float ar = 0.5f * (z1.x + z2.x) * cp.inv_n + ((ky == 0 && kz == 0) ? dc : 0.f), ai = 0.5f * (z1.y + z2.y) * cp.inv_n;
             const float br = 0.5f * (z1.y - z2.y) * cp.inv_n, bi = -0.5f * (z1.x - z2.x) * cp.inv_n;
             extra_add(xa, cp, ar * ar + ai * ai, 0u, ky, kz, 1.0f);
             extra_add(xa, cp, br * br + bi * bi, cp.nx / 2, ky, kz, 1.0f);
         }
-        outv[it] = conv_plane0(tile[idx], tile[((L - kz) % L) * kLines + (ww ^ 1)], cp.inv_n, d, ky, kz, ny, L, counted, e);
+        outv[it] = conv_plane0(tile[idx], tile[((L - kz) % L) * kLines + (ww ^ 1)], cp.inv_n, d, ky, kz, ny, L, counted, e, dc);
     }
     __syncthreads();
 #pragma unroll

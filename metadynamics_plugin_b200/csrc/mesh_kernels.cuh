@@ -58,6 +58,18 @@ struct Geom {
     float hl_hi[3], hl_lo[3], c_hi[3], c_lo[3];
     float fn[3];                // (float) global mesh dimensions
     float rcpL[3];              // 1/L in single precision (HOOMD BoxDim::m_Linv)
+    // triclinic box (HOOMD tilt factors xy, xz, yz; BoxDim::makeFraction shears x and y before the division by L):
+    //   x' = x - (xz - yz xy) z - xy y,   y' = y - yz z,   z' = z
+    unsigned tri;               // 1: at least one tilt factor is non-zero
+    float t_xy, t_a, t_yz;      // single precision, rounded like a SINGLE_PRECISION BoxDim: xy, fl(xz - fl(yz xy)), yz
+    double d_xy, d_a, d_yz;     // fp64: xy, xz - yz xy, yz
+    // Reference behaviour in a triclinic box, restated literally: the in-cell offset is taken as
+    // makeFraction(shift_cart + lo) (OrderParameterMesh.cc:571-573, 806-808), and makeFraction applies its shear to the
+    // whole argument, lo included, so every offset carries the constant  -shear(lo)/L * n:
+    //   x: n_x ((xz - yz xy) Lz + xy Ly) / (2 Lx),   y: n_y yz Lz / (2 Ly),   z: 0     (in cells)
+    // The TSC weights are then evaluated at (offset + tq - tap) with their general, compactly supported form, exactly as the
+    // reference does (weight is lost where |.| > 3/2).  tq = 0 gives the geometrically correct assignment (knob 16).
+    float tq[3];
 };
 
 MHD void geom_set_dims(Geom& g, unsigned nx, unsigned ny, unsigned nz, unsigned lgT) {
@@ -69,8 +81,22 @@ MHD void geom_set_dims(Geom& g, unsigned nx, unsigned ny, unsigned nz, unsigned 
     g.lgtx = g.lgx - lgT; g.lgty = g.lgy - lgT; g.lgtz = g.lgz - lgT;
     g.ntx = 1u << g.lgtx; g.nty = 1u << g.lgty; g.ntz = 1u << g.lgtz;
 }
-// box: L[] in double (the GLOBAL box); n[] = global mesh dimensions
-inline void geom_set_box(Geom& g, const double* Ld) {
+// box: L[] in double (the GLOBAL box), tilt[] = xy, xz, yz (may be null); n[] = global mesh dimensions
+inline void geom_set_box(Geom& g, const double* Ld, const double* tilt = nullptr, bool literal_offset = true) {
+    {
+        const double xy = tilt ? tilt[0] : 0.0, xz = tilt ? tilt[1] : 0.0, yz = tilt ? tilt[2] : 0.0;
+        g.tri = (xy != 0.0 || xz != 0.0 || yz != 0.0) ? 1u : 0u;
+        g.d_xy = xy; g.d_yz = yz; g.d_a = xz - yz * xy;
+        g.t_xy = (float)xy; g.t_yz = (float)yz;
+        volatile float fxz = (float)xz, prod = g.t_yz * g.t_xy;      // two roundings, as in (m_xz - m_yz*m_xy) without contraction
+        volatile float ta = fxz - prod;
+        g.t_a = ta;
+        g.tq[0] = g.tq[1] = g.tq[2] = 0.f;
+        if (g.tri && literal_offset) {
+            g.tq[0] = (float)((double)g.nx * (g.d_a * Ld[2] + xy * Ld[1]) / (2.0 * Ld[0]));
+            g.tq[1] = (float)((double)g.ny * yz * Ld[2] / (2.0 * Ld[1]));
+        }
+    }
     const unsigned n[3] = {g.nx, g.ny, g.nzg};
     for (int i = 0; i < 3; ++i) {
         g.L[i] = (float)Ld[i];
@@ -176,8 +202,9 @@ MHD int cell_coord_ref(float x, float lo, float Linv, unsigned n) {
 // Hot form: same value for every input, no conversion-pipe instruction.
 // `raw` receives the index before the upper-edge wrap (n for a particle on the upper face): the in-cell offset is
 // measured from that cell, which is the periodic image of cell 0 the particle actually sits in.
-MHD int cell_coord(float x, int axis, const Geom& g, int& raw) {
-    const float f = f_mul(f_sub(x, g.lo[axis]), g.rcpL[axis]);
+// delta = the component of BoxDim::makeFraction's `delta` before the multiplication by 1/L (x - lo for an orthorhombic box)
+MHD int cell_coord_delta(float delta, int axis, const Geom& g, int& raw) {
+    const float f = f_mul(delta, g.rcpL[axis]);
     float r = f_mul(f, g.fn[axis]);
     const int n = (int)(axis == 0 ? g.nx : (axis == 1 ? g.ny : g.nzg));
 #ifdef __CUDA_ARCH__
@@ -192,6 +219,7 @@ MHD int cell_coord(float x, int axis, const Geom& g, int& raw) {
     if (i >= n) i = 0;
     return i;
 }
+MHD int cell_coord(float x, int axis, const Geom& g, int& raw) { return cell_coord_delta(f_sub(x, g.lo[axis]), axis, g, raw); }
 MHD int cell_coord(float x, int axis, const Geom& g) { int raw; return cell_coord(x, axis, g, raw); }
 
 // tile-major key: tile index * T^3 + local cell index (x fastest inside the tile)
@@ -254,6 +282,25 @@ MHD void tsc_deriv(float s, float (&w)[3]) {
     w[1] = -2.0f * s;
     w[2] = s + 0.5f;
 }
+// The same weights for an arbitrary offset (triclinic boxes: the reference's offsets carry a constant, Geom::tq), i.e.
+// assignTSC / assignTSCderiv as written: W(x) = 3/4 - x^2 (|x| <= 1/2), (3/2 - |x|)^2 / 2 (|x| <= 3/2), 0;
+// W'(x) = -2x, -(3/2 - |x|) sign(x), 0.  Taps i = -1, 0, +1 sit at x = s + 1, s, s - 1.
+MHD float tsc_w(float x) {
+    const float ax = fabsf(x), r = 1.5f - ax;
+    return ax <= 0.5f ? 0.75f - x * x : (ax <= 1.5f ? 0.5f * r * r : 0.f);
+}
+MHD float tsc_wd(float x) {
+    const float ax = fabsf(x), r = 1.5f - ax;
+    return ax <= 0.5f ? -2.0f * x : (ax <= 1.5f ? (x < 0.f ? r : -r) : 0.f);
+}
+template <bool GENERAL> MHD void tsc_any(float s, float (&w)[3]) {
+    if (GENERAL) { w[0] = tsc_w(s + 1.0f); w[1] = tsc_w(s); w[2] = tsc_w(s - 1.0f); }
+    else tsc(s, w);
+}
+template <bool GENERAL> MHD void tsc_deriv_any(float s, float (&w)[3]) {
+    if (GENERAL) { w[0] = tsc_wd(s + 1.0f); w[1] = tsc_wd(s); w[2] = tsc_wd(s - 1.0f); }
+    else tsc_deriv(s, w);
+}
 
 // ---------------------------------------------------------------------------------------------------
 // fixed point
@@ -298,8 +345,17 @@ struct Cell {
 };
 MHD Cell particle_cell(float4 p, const Geom& g) {
     Cell c;
-    c.ix = cell_coord(p.x, 0, g, c.rx);
-    c.iy = cell_coord(p.y, 1, g, c.ry);
+    if (g.tri) {
+        // BoxDim::makeFraction of a SINGLE_PRECISION build, operation by operation (no contraction):
+        //   delta = v - lo;  delta.x -= (xz - yz*xy)*v.z + xy*v.y;  delta.y -= yz*v.z;
+        const float dx = f_sub(f_sub(p.x, g.lo[0]), f_add(f_mul(g.t_a, p.z), f_mul(g.t_xy, p.y)));
+        const float dy = f_sub(f_sub(p.y, g.lo[1]), f_mul(g.t_yz, p.z));
+        c.ix = cell_coord_delta(dx, 0, g, c.rx);
+        c.iy = cell_coord_delta(dy, 1, g, c.ry);
+    } else {
+        c.ix = cell_coord(p.x, 0, g, c.rx);
+        c.iy = cell_coord(p.y, 1, g, c.ry);
+    }
     c.iz = cell_coord(p.z, 2, g, c.rz);
     c.owned = (unsigned)(c.iz - (int)g.z0) < g.nz;
     return c;
@@ -362,10 +418,13 @@ MHD void particle_rebase(Cell& c, float3& s, const Geom& g) {
 // offset then leaves [-1/2, 1/2] and the final rint() step moves cell and offset back together (the re-base above).
 // Agrees with particle_cell + particle_shift + particle_rebase (tests/cpu_emul/mesh_emul.cu compares the two on every
 // particle); 20 instead of 34 instructions per axis.
-MHD void axis_stencil(float x, int axis, const Geom& g, unsigned n, int& i, float& s) {
+// LOW: the coordinate is the unevaluated sum x + xl (a sheared coordinate of a triclinic box, |xl| <= ulp(x)/2).
+template <bool LOW = false>
+MHD void axis_stencil(float x, int axis, const Geom& g, unsigned n, int& i, float& s, float xl = 0.f) {
     const float hl = g.hl_hi[axis], ch = g.c_hi[axis];
     const float d = f_add(hl, x);
-    const float e = f_add(f_sub(x, f_sub(d, hl)), g.hl_lo[axis]);
+    float e = f_add(f_sub(x, f_sub(d, hl)), g.hl_lo[axis]);
+    if (LOW) e = f_add(e, xl);
     const float rh = f_mul(d, ch);
     const float rl = f_fma(d, ch, -rh);
     const float small = f_add(rl, f_fma(e, ch, f_mul(d, g.c_lo[axis])));
@@ -389,9 +448,24 @@ MHD void axis_stencil(float x, int axis, const Geom& g, unsigned n, int& i, floa
 // stencil base (global cell, z = global plane) and offsets of a particle; `owned` = the float-rule plane of the particle
 // belongs to this rank's slab (always true for an unsharded plan).  A slab keeps the base inside its planes (see
 // particle_rebase): the particle's taps must not reach beyond the one ghost layer.
+// TRI: triclinic box.  The sheared coordinates x' = x - (xz - yz xy) z - xy y and y' = y - yz z are evaluated in fp64 (two
+// fused multiply-adds; the products of single-precision positions with the tilt factors do not fit single precision) and
+// handed on as float pairs, so the offsets keep the < 1e-7 cell accuracy of the orthorhombic path.  A separate
+// instantiation: the orthorhombic kernels do not carry the fp64 instructions.
+template <bool TRI = false>
 MHD void particle_stencil(float4 p, const Geom& g, Cell& c, float3& s) {
-    axis_stencil(p.x, 0, g, g.nx, c.ix, s.x);
-    axis_stencil(p.y, 1, g, g.ny, c.iy, s.y);
+    if (TRI) {
+        const double xd = (double)p.x - (g.d_a * (double)p.z + g.d_xy * (double)p.y);
+        const double yd = (double)p.y - g.d_yz * (double)p.z;
+        const float xh = (float)xd, yh = (float)yd;
+        axis_stencil<true>(xh, 0, g, g.nx, c.ix, s.x, (float)(xd - (double)xh));
+        axis_stencil<true>(yh, 1, g, g.ny, c.iy, s.y, (float)(yd - (double)yh));
+        s.x += g.tq[0];          // the reference's constant (see Geom::tq); the weights take their general form from here on
+        s.y += g.tq[1];
+    } else {
+        axis_stencil(p.x, 0, g, g.nx, c.ix, s.x);
+        axis_stencil(p.y, 1, g, g.ny, c.iy, s.y);
+    }
     axis_stencil(p.z, 2, g, g.nzg, c.iz, s.z);
     c.owned = true;
     if (g.slab) {
@@ -406,10 +480,11 @@ MHD void particle_stencil(float4 p, const Geom& g, Cell& c, float3& s) {
     }
 }
 // separable weights: w[0..2] = Wx(tap -1,0,+1), w[3..5] = Wy, w[6..8] = amp * Wz
+template <bool TRI = false>
 MHD void spread_weights(float3 s, float amp, float (&w)[9]) {
     float wx[3], wy[3], wz[3];
-    tsc(s.x, wx);
-    tsc(s.y, wy);
+    tsc_any<TRI>(s.x, wx);
+    tsc_any<TRI>(s.y, wy);
     tsc(s.z, wz);
 #pragma unroll
     for (int i = 0; i < 3; ++i) { w[i] = wx[i]; w[3 + i] = wy[i]; w[6 + i] = amp * wz[i]; }
@@ -493,9 +568,10 @@ struct ForceParams {
 };
 
 struct GatherWeights { float wx[3], wy[3], wz[3], dx[3], dy[3], dz[3]; };
+template <bool TRI = false>
 MHD void gather_weights(float3 s, GatherWeights& w) {
-    tsc(s.x, w.wx); tsc(s.y, w.wy); tsc(s.z, w.wz);
-    tsc_deriv(s.x, w.dx); tsc_deriv(s.y, w.dy); tsc_deriv(s.z, w.dz);
+    tsc_any<TRI>(s.x, w.wx); tsc_any<TRI>(s.y, w.wy); tsc(s.z, w.wz);
+    tsc_deriv_any<TRI>(s.x, w.dx); tsc_deriv_any<TRI>(s.y, w.dy); tsc_deriv(s.z, w.dz);
 }
 // amp = a(type); scale = (2/N) * bias rounded to float
 MHD float4 force_from_sums(float Sx, float Sy, float Sz, float amp, const ForceParams& fp, float scale) {
@@ -821,6 +897,7 @@ constexpr int kSpKeys = 1;             // store the tile-major cell key of every
 constexpr int kSpCache = 2;            // write the particle cache {offsets, amplitude, code word, index} for the gather
 constexpr int kSpWide = 4;             // 64-bit accumulation: the density of a cell no longer shares 32 bits with the resolution
 constexpr int kSpTma = 8;              // flush interior tiles with one 3-D tensor-map reduction (cp.reduce.async.bulk.tensor)
+constexpr int kSpTri = 16;             // triclinic box: sheared coordinates (particle_stencil<true>); instantiated without kSpTma
 // Wide accumulation.  sm_100a has no native 64-bit shared-memory atomic add (atom.shared.add.u64 compiles to a
 // ATOMS.CAST.SPIN loop), so a tap v (|v| < 2^22) is split as v = hi * 2^12 + lo, 0 <= lo < 2^12, and the two parts are
 // added to two 32-bit tiles with the native ATOMS.ADD; a tile cell can take 2^20 taps (lo) / 2^21 taps (hi), i.e. about
@@ -856,6 +933,7 @@ mesh_spread_kernel(const float4* __restrict__ postype, const unsigned* __restric
                    const __grid_constant__ Geom g, const float* __restrict__ mode, int ntypes, const float* __restrict__ d_fx,
                    const __grid_constant__ SpreadOut out) {
     constexpr bool KEYS = FLAGS & kSpKeys, CACHE = FLAGS & kSpCache, WIDE = FLAGS & kSpWide, TMA = (FLAGS & kSpTma) && !WIDE;
+    constexpr bool TRI = FLAGS & kSpTri;
     constexpr int T = 1 << LGT, PX = T + 2 * kHaloX, PY = T + 2 * kHalo, PZ = PY, P3 = PX * PY * PZ;
     constexpr int TW = spread_tile_words<LGT>(FLAGS);
     extern __shared__ __align__(128) int tile[];      // P3 words (WIDE: the low parts, then P3 words of high parts)
@@ -919,7 +997,7 @@ mesh_spread_kernel(const float4* __restrict__ postype, const unsigned* __restric
             }
             Cell c;
             float3 sh;
-            particle_stencil(p, g, c, sh);
+            particle_stencil<TRI>(p, g, c, sh);
             unsigned lx = 0, ly = 0, lz = 0;
             const bool inside = c.owned && padded_coords(c, ox, oy, oz, g, PX, PY, PZ, lx, ly, lz);
             if (CACHE) out.cache4[j] = make_float4(sh.x, sh.y, sh.z, __uint_as_float(cache_code(lx, ly, lz, (unsigned)__float_as_int(p.w), inside, c.owned)));
@@ -927,7 +1005,7 @@ mesh_spread_kernel(const float4* __restrict__ postype, const unsigned* __restric
                 sq += (double)a * (double)a;
                 s1 += (double)a;
                 float w[9];
-                spread_weights(sh, a * scale, w);
+                spread_weights<TRI>(sh, a * scale, w);
                 if (inside && (out.debug & 2)) {
                 } else if (inside) {
                     // the flush skips the outermost y / z layers of the padded tile unless a particle has drifted that far
@@ -1079,13 +1157,14 @@ constexpr int kGatherStages = 4;       // staging buffers of the particle data (
 // slow path of a particle that drifted out of its padded tile: the 27 taps come from global memory.  Not inlined and
 // fed by value, so that the fast path keeps its weights in registers; recomputes cell and weights from the position.
 struct GatherDirectArgs { const float* inv; const float* ghost; const Geom* g; };
+template <bool TRI>
 __device__ __noinline__ float3 gather_direct(float4 p, GatherDirectArgs a) {
     const Geom g = *a.g;
     Cell c;
     float3 sh;
-    particle_stencil(p, g, c, sh);
+    particle_stencil<TRI>(p, g, c, sh);
     GatherWeights w;
-    gather_weights(sh, w);
+    gather_weights<TRI>(sh, w);
     const size_t plane = (size_t)g.nx * g.ny;
     float t27[27];
     for (int k = 0; k < 3; ++k)
@@ -1116,7 +1195,7 @@ struct GatherIn {
     alignas(64) CUtensorMap tmap;   // tensor map of Re IFFT(G) (dims nx, ny, nz; box = padded tile), inside the __grid_constant__ parameter
 };
 
-template <int LGT, int THREADS = kGatherThreads, int MINB = 3, bool CACHE = true>
+template <int LGT, int THREADS = kGatherThreads, int MINB = 3, bool CACHE = true, bool TRI = false>
 __global__ void __launch_bounds__(THREADS, MINB)
 mesh_gather_kernel(const __grid_constant__ GatherIn in, const unsigned* __restrict__ tstart, const __grid_constant__ Geom g,
                    const float* __restrict__ inv, const float* __restrict__ ghost /* slab mode: planes z0-1 and z0+nz of Re IFFT(G) */,
@@ -1209,13 +1288,13 @@ mesh_gather_kernel(const __grid_constant__ GatherIn in, const unsigned* __restri
                 float Sx, Sy, Sz;
                 if (code & kCacheInside) {
                     GatherWeights w;
-                    gather_weights(make_float3(q.x, q.y, q.z), w);
+                    gather_weights<TRI>(make_float3(q.x, q.y, q.z), w);
                     const unsigned lx = code & 31u, ly = (code >> 5) & 31u, lz = (code >> 10) & 31u;
                     gather_sums(ftile + ((lz - 1) * PY + (ly - 1)) * PX + (lx - 1), PX, PX * PY, w.wx, w.wy, w.wz, w.dx, w.dy, w.dz, Sx, Sy, Sz);
                 } else {
                     GatherDirectArgs da;
                     da.inv = inv; da.ghost = ghost; da.g = &g;
-                    const float3 S = gather_direct(__ldg(in.postype + n), da);
+                    const float3 S = gather_direct<TRI>(__ldg(in.postype + n), da);
                     Sx = S.x; Sy = S.y; Sz = S.z;
                 }
                 f = force_from_sums(Sx, Sy, Sz, s_mode[(code >> 15) & 1023u], fp, scale);
@@ -1254,19 +1333,19 @@ mesh_gather_kernel(const __grid_constant__ GatherIn in, const unsigned* __restri
             if (++buf == kGatherStages) buf = 0;
             Cell c;
             float3 sh;
-            particle_stencil(p, g, c, sh);
+            particle_stencil<TRI>(p, g, c, sh);
             float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
             if (c.owned) {
                 unsigned lx, ly, lz;
                 float Sx, Sy, Sz;
                 if (padded_coords(c, ox, oy, oz, g, PX, PY, PZ, lx, ly, lz)) {
                     GatherWeights w;
-                    gather_weights(sh, w);
+                    gather_weights<TRI>(sh, w);
                     gather_sums(ftile + ((lz - 1) * PY + (ly - 1)) * PX + (lx - 1), PX, PX * PY, w.wx, w.wy, w.wz, w.dx, w.dy, w.dz, Sx, Sy, Sz);
                 } else {
                     GatherDirectArgs da;
                     da.inv = inv; da.ghost = ghost; da.g = &g;
-                    const float3 S = gather_direct(p, da);
+                    const float3 S = gather_direct<TRI>(p, da);
                     Sx = S.x; Sy = S.y; Sz = S.z;
                 }
                 f = force_from_sums(Sx, Sy, Sz, s_mode[__float_as_int(p.w)], fp, scale);

@@ -153,6 +153,7 @@ template <class S> void wte_scale_c(float* f4, float* t4, float* vir, unsigned p
     }                                                                                                                 \
     double orc_mesh_mode_sq_##SFX(void* h) { return ((MeshCV<S>*)h)->mode_sq; }                                       \
     void orc_mesh_set_literal_copysignf_##SFX(void* h, int on) { ((MeshCV<S>*)h)->literal_copysignf = on != 0; }      \
+    void orc_mesh_set_literal_tilt_offset_##SFX(void* h, int on) { ((MeshCV<S>*)h)->literal_tilt_offset = on != 0; } \
     void orc_mesh_virial_##SFX(void* h, const double* table_d, unsigned n, double kmin, double kmax, int use_table,  \
                                double bias, double* out6) {                                                           \
         std::vector<S> t(table_d, table_d + n); S o[6];                                                               \

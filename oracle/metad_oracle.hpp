@@ -295,9 +295,18 @@ template <class S> struct MeshCV {
         V3<S> dims = v3<S>((S)nx, (S)ny, (S)nz);
         V3<S> c_cart = box.makeCoordinates(center / dims);
         V3<S> shift_cart = box.minImage(pos - c_cart);
+        // As written (:571-573, :806-808): makeFraction shears its whole argument, `lo` included, so in a triclinic box the
+        // offset carries the constant -shear(lo)/L (x: ((xz - yz xy) Lz + xy Ly)/(2 Lx), y: yz Lz/(2 Ly), times the mesh
+        // dimensions) and TSC weight is lost where |offset - tap| > 3/2.  Restated literally by default (pinned to the
+        // reference's own output, vectors t0-t2); literal_tilt_offset = false removes the constant.
         V3<S> shift_f = box.makeFraction(shift_cart + box.lo);
+        if (!literal_tilt_offset) {
+            shift_f.x += ((box.xz - box.yz * box.xy) * box.lo.z + box.xy * box.lo.y) * box.Linv.x;
+            shift_f.y += box.yz * box.lo.z * box.Linv.y;
+        }
         shift = shift_f * dims;
     }
+    bool literal_tilt_offset = true;
     static inline int wrap(int i, int n) { if (i == n) return 0; if (i < 0) return i + n; return i; }
 
     // assignParticles: OrderParameterMesh.cc:517-640

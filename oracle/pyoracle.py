@@ -64,6 +64,7 @@ def lib():
             g("orc_mesh_qmax").argtypes = [C.c_void_p, _dp]
             g("orc_mesh_virial").argtypes = [C.c_void_p, _dp, C.c_uint, C.c_double, C.c_double, C.c_int, C.c_double, _dp]
             g("orc_mesh_set_literal_copysignf").argtypes = [C.c_void_p, C.c_int]
+            g("orc_mesh_set_literal_tilt_offset").argtypes = [C.c_void_p, C.c_int]
             g("orc_lamellar_cv").restype = C.c_double
             g("orc_lamellar_cv").argtypes = [_fp, C.c_uint, C.c_uint, _dp, C.c_int, _ip, C.c_int, _dp, _dp]
             g("orc_lamellar_forces").argtypes = [_fp, C.c_uint, C.c_uint, _dp, C.c_int, _ip, C.c_int, _dp, C.c_double, _dp]
@@ -132,9 +133,10 @@ def make_postype(pos, types=None):
 class Mesh:
     """OrderParameterMesh oracle (CPU path)."""
 
-    def __init__(self, nx, ny, nz, mode, L, n_global, prec="f64", tilt=(0, 0, 0), literal_copysignf=True):
+    def __init__(self, nx, ny, nz, mode, L, n_global, prec="f64", tilt=(0, 0, 0), literal_copysignf=True, literal_tilt_offset=True):
         """literal_copysignf=False: evaluate |x| exactly in assignTSCderiv (what a SINGLE_PRECISION build does);
-        the double instance with this switch off is the tolerance target for forces (see metad_oracle.hpp)."""
+        the double instance with this switch off is the tolerance target for forces (see metad_oracle.hpp).
+        literal_tilt_offset=False: remove the constant the reference's in-cell offsets carry in a triclinic box."""
         self.prec = prec
         self.dims = (nx, ny, nz)
         self.M = nx * ny * nz
@@ -142,6 +144,7 @@ class Mesh:
         self._box = box6(L, tilt)
         self.h = _fn("orc_mesh_create", prec)(nx, ny, nz, _d(mode), len(mode), _d(self._box), n_global)
         _fn("orc_mesh_set_literal_copysignf", prec)(self.h, int(literal_copysignf))
+        _fn("orc_mesh_set_literal_tilt_offset", prec)(self.h, int(literal_tilt_offset))
 
     def __del__(self):
         try:

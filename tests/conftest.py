@@ -2,6 +2,7 @@ import os
 import subprocess
 import sys
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -40,3 +41,20 @@ def build_emul(name):
         subprocess.check_call([NVCC, "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler",
                                "-ffp-contract=off,-Wno-unknown-pragmas", "-o", exe, src])
     return exe
+
+
+def triclinic_case(N, L, tilt, ntypes, seed, faces=True):
+    """Particles inside a sheared box (HOOMD convention: r = lo + f L, x += xy y + xz z, y += yz z, all in float like a
+    single-precision trajectory), some of them a few ulps around cell faces of the fractional mesh."""
+    rng = np.random.default_rng(seed)
+    Lf = np.asarray(L, dtype=np.float64)
+    f = rng.random((N, 3))
+    if faces:
+        k = min(N // 4, 400)
+        f[:k] = np.round(f[:k] * 16) / 16 + rng.integers(-3, 4, (k, 3)) * 2.0 ** -24
+        f = np.clip(f, 2.0 ** -20, 1.0 - 2.0 ** -20)      # inside the box after the rounding to float (HOOMD wraps the rest)
+    v = (f - 0.5) * Lf
+    xy, xz, yz = tilt
+    v[:, 0] += xy * v[:, 1] + xz * v[:, 2]
+    v[:, 1] += yz * v[:, 2]
+    return v.astype(np.float32), rng.integers(0, ntypes, N).astype(np.int32)

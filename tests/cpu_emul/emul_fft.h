@@ -100,7 +100,7 @@ template <int L> double z_fused(float2* buf, unsigned nx, unsigned ny, float inv
         }
     return etot;
 }
-template <int L> double z_plane0(float2* buf, unsigned nx, unsigned ny, float inv_n, float d) {
+template <int L> double z_plane0(float2* buf, unsigned nx, unsigned ny, float inv_n, float d, float dc = 0.f) {
     auto tw = twiddles(L);
     std::vector<float2> tile(LayoutCol::size(L)), outv(LayoutCol::size(L));
     const unsigned nxh = nx / 2;
@@ -121,7 +121,7 @@ template <int L> double z_plane0(float2* buf, unsigned nx, unsigned ny, float in
             int ww = idx & (kLines - 1); unsigned kz = idx / kLines;
             unsigned kyp = b * (kLines / 2) + (ww >> 1), pky = (ny - kyp) % ny, ky = (ww & 1) ? pky : kyp;
             bool valid = kyp <= ny / 2, counted = valid && (!(ww & 1) || pky != kyp);
-            outv[idx] = conv_plane0(tile[idx], tile[((L - kz) % L) * kLines + (ww ^ 1)], inv_n, d, ky, kz, ny, L, counted, e);
+            outv[idx] = conv_plane0(tile[idx], tile[((L - kz) % L) * kLines + (ww ^ 1)], inv_n, d, ky, kz, ny, L, counted, e, dc);
         }
         tile = outv;
         emul_line_fft<L, +1, L, LayoutCol>(tile.data(), tw.data());

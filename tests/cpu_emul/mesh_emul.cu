@@ -31,7 +31,12 @@ int main(int argc, char** argv) {
     for (int i = 0; i < ntypes; ++i) { mode[i] = (float)atof(argv[12 + i]); amax = std::max(amax, std::fabs(mode[i])); }
     const char* fin = argv[12 + ntypes];
     const char* fout = argv[13 + ntypes];
-    geom_set_box(g, Ld);
+    // triclinic box: METAD_EMUL_TILT="xy,xz,yz" (the positions are then expected inside the sheared box)
+    double tilt[3] = {0.0, 0.0, 0.0};
+    if (const char* ts = getenv("METAD_EMUL_TILT")) sscanf(ts, "%lf,%lf,%lf", &tilt[0], &tilt[1], &tilt[2]);
+    // METAD_EMUL_TILT_LITERAL=0: geometrically correct offsets instead of the reference's (Geom::tq)
+    const bool literal = !(getenv("METAD_EMUL_TILT_LITERAL") && atoi(getenv("METAD_EMUL_TILT_LITERAL")) == 0);
+    geom_set_box(g, Ld, tilt, literal);
     FILE* f = fopen(fin, "rb");
     fseek(f, 0, SEEK_END); const long bytes = ftell(f); fseek(f, 0, SEEK_SET);
     const unsigned N = (unsigned)(bytes / 16);
@@ -75,9 +80,21 @@ int main(int argc, char** argv) {
         for (int d = 0; d < 3; ++d) {
             const float u = (hash32(i * 3u + d + 17u) >> 8) * (1.0f / 16777216.0f);
             float v = c[d] + (u - 0.5f) * 2.f * (float)(stale * Ld[d] / n3[d]);
-            if (v >= g.L[d] / 2.0f) v -= g.L[d];
-            if (v < -(g.L[d] / 2.0f)) v += g.L[d];
+            if (!g.tri) {
+                if (v >= g.L[d] / 2.0f) v -= g.L[d];
+                if (v < -(g.L[d] / 2.0f)) v += g.L[d];
+            }
             c[d] = v;
+        }
+        if (g.tri && stale > 0.0) {          // wrap the displaced position back into the sheared box (BoxDim::wrap, z first)
+            if (p.z >= g.L[2] / 2.0f) { p.z -= g.L[2]; p.y -= g.L[2] * (float)tilt[2]; p.x -= g.L[2] * (float)tilt[1]; }
+            else if (p.z < -(g.L[2] / 2.0f)) { p.z += g.L[2]; p.y += g.L[2] * (float)tilt[2]; p.x += g.L[2] * (float)tilt[1]; }
+            const float ys = p.y - (float)tilt[2] * p.z;
+            if (ys >= g.L[1] / 2.0f) { p.y -= g.L[1]; p.x -= g.L[1] * (float)tilt[0]; }
+            else if (ys < -(g.L[1] / 2.0f)) { p.y += g.L[1]; p.x += g.L[1] * (float)tilt[0]; }
+            const float xs = p.x - (float)g.d_a * p.z - (float)tilt[0] * p.y;
+            if (xs >= g.L[0] / 2.0f) p.x -= g.L[0];
+            else if (xs < -(g.L[0] / 2.0f)) p.x += g.L[0];
         }
         const Cell cc = particle_cell(p, g);
         keys[i] = key_of(cc.ix, cc.iy, cc.iz, g);
@@ -141,15 +158,33 @@ int main(int argc, char** argv) {
             cell_keys[n] = key_of(c.ix, c.iy, c.iz, g);
             sq += (double)a * (double)a; s1 += (double)a;
             float w[9];
-            float3 sh = particle_shift(p, c, g);
-            const float xyz[3] = {p.x, p.y, p.z};
-            const int cxyz[3] = {c.ix, c.iy, c.iz}, rxyz[3] = {c.rx, c.ry, c.rz};
-            for (int d = 0; d < 3; ++d)
-                shift_err = std::max(shift_err, (double)std::fabs(cell_shift(xyz[d], rxyz[d], d, g) - cell_shift_f64(xyz[d], cxyz[d], d, g)));
-            particle_rebase(c, sh, g);       // stencil base = the cell the accurate offset points to (see mesh_kernels.cuh)
+            float3 sh;
+            if (g.tri) {
+                // reference form of the stencil in a triclinic box: fractional coordinate (BoxDim::makeFraction) in fp64,
+                // cell = floor, offset from the cell centre
+                const double u[3] = {(double)p.x - (g.d_a * (double)p.z + g.d_xy * (double)p.y), (double)p.y - g.d_yz * (double)p.z, (double)p.z};
+                int ci[3]; float so[3];
+                const unsigned nn[3] = {g.nx, g.ny, g.nzg};
+                for (int d = 0; d < 3; ++d) {
+                    const double r = (u[d] - g.dlo[d]) * g.dscale[d];
+                    const double fl = std::floor(r);
+                    ci[d] = (int)(((long long)fl % (long long)nn[d] + nn[d]) % nn[d]);
+                    so[d] = (float)(r - fl - 0.5);
+                }
+                c.ix = ci[0]; c.iy = ci[1]; c.iz = ci[2];
+                sh = make_float3(so[0] + g.tq[0], so[1] + g.tq[1], so[2]);
+            } else {
+                sh = particle_shift(p, c, g);
+                const float xyz[3] = {p.x, p.y, p.z};
+                const int cxyz[3] = {c.ix, c.iy, c.iz}, rxyz[3] = {c.rx, c.ry, c.rz};
+                for (int d = 0; d < 3; ++d)
+                    shift_err = std::max(shift_err, (double)std::fabs(cell_shift(xyz[d], rxyz[d], d, g) - cell_shift_f64(xyz[d], cxyz[d], d, g)));
+                particle_rebase(c, sh, g);       // stencil base = the cell the accurate offset points to (see mesh_kernels.cuh)
+            }
             {   // the hot form used by the kernels must pick the same base (or the neighbour across a face it sits on) and the same offset
                 Cell ch; float3 sh2;
-                particle_stencil(p, g, ch, sh2);
+                if (g.tri) particle_stencil<true>(p, g, ch, sh2);
+                else particle_stencil<false>(p, g, ch, sh2);
                 const int dc[3] = {ch.ix - c.ix, ch.iy - c.iy, ch.iz - c.iz};
                 const float ds[3] = {sh2.x - sh.x, sh2.y - sh.y, sh2.z - sh.z};
                 const int nn[3] = {(int)g.nx, (int)g.ny, (int)g.nz};
@@ -160,7 +195,8 @@ int main(int argc, char** argv) {
                 }
                 c = ch; sh = sh2;
             }
-            spread_weights(sh, a * scale, w);
+            if (g.tri) spread_weights<true>(sh, a * scale, w);
+            else spread_weights<false>(sh, a * scale, w);
             unsigned lx, ly, lz;
             const bool inside = padded_coords(c, ox, oy, oz, g, PX, PY, PZ, lx, ly, lz);
             cache4[j] = make_float4(sh.x, sh.y, sh.z, a);
@@ -205,14 +241,23 @@ int main(int argc, char** argv) {
     double e = 0.0;
     DISPATCH(nxh, x_fwd<LL>(b2, g.ny * g.nz));
     DISPATCH(g.ny, (y_pass<LL, -1>(b2, nxh, g.nz)));
-    DISPATCH(g.nz, e += z_plane0<LL>(b2, g.nx, g.ny, inv_n, d));
+    // ConvParams::dc_restore: what the mean removal took out of f_0 goes back in before the convolution (literal triclinic offsets)
+    const float dc = (g.tri && (g.tq[0] != 0.f || g.tq[1] != 0.f)) ? (float)((double)mean * (double)M * (double)inv_n) : 0.f;
+    DISPATCH(g.nz, e += z_plane0<LL>(b2, g.nx, g.ny, inv_n, d, dc));
     DISPATCH(g.nz, e += z_fused<LL>(b2, g.nx, g.ny, inv_n, d));
     DISPATCH(g.ny, (y_pass<LL, +1>(b2, nxh, g.nz)));
     DISPATCH(nxh, x_inv<LL>(b2, g.ny * g.nz));
     const double cv = 0.5 * e;
     // ---- gather (mesh_gather_kernel)
     ForceParams fp; memset(&fp, 0, sizeof fp);
-    fp.nb1[0] = (float)((double)g.nx / Ld[0]); fp.nb2[1] = (float)((double)g.ny / Ld[1]); fp.nb3[2] = (float)((double)g.nz / Ld[2]);
+    {   // n_a b_a with the reciprocal lattice vectors b_a = (a_b x a_c) / V of the (sheared) box, as launch_gather (csrc/mesh.cu) sets them
+        const double a1[3] = {Ld[0], 0.0, 0.0}, a2[3] = {tilt[0] * Ld[1], Ld[1], 0.0}, a3[3] = {tilt[1] * Ld[2], tilt[2] * Ld[2], Ld[2]};
+        const double V = Ld[0] * Ld[1] * Ld[2];
+        auto cross = [&](const double* u, const double* v, double nn, float* o) {
+            o[0] = (float)(nn * (u[1] * v[2] - u[2] * v[1]) / V); o[1] = (float)(nn * (u[2] * v[0] - u[0] * v[2]) / V); o[2] = (float)(nn * (u[0] * v[1] - u[1] * v[0]) / V);
+        };
+        cross(a2, a3, (double)g.nx, fp.nb1); cross(a3, a1, (double)g.ny, fp.nb2); cross(a1, a2, (double)g.nz, fp.nb3);
+    }
     fp.two_over_n = 2.0 / (double)N_global;
     const float fscale = (float)(fp.two_over_n * bias);
     std::vector<float4> force(N);
@@ -234,9 +279,11 @@ int main(int argc, char** argv) {
             const float4 q = cache4[j];
             Cell c;
             float3 sh_g;
-            particle_stencil(p, g, c, sh_g);
+            if (g.tri) particle_stencil<true>(p, g, c, sh_g);
+            else particle_stencil<false>(p, g, c, sh_g);
             GatherWeights w;
-            gather_weights(make_float3(q.x, q.y, q.z), w);
+            if (g.tri) gather_weights<true>(make_float3(q.x, q.y, q.z), w);
+            else gather_weights<false>(make_float3(q.x, q.y, q.z), w);
             float Sx, Sy, Sz;
             if (code & kCacheInside) {
                 const unsigned lx = code & 31u, ly = (code >> 5) & 31u, lz = (code >> 10) & 31u;

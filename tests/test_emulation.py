@@ -9,7 +9,7 @@ import tempfile
 import numpy as np
 import pytest
 
-from conftest import build_emul
+from conftest import build_emul, triclinic_case
 
 
 def np_chi(dims):
@@ -57,14 +57,18 @@ def test_fft_sweeps_match_numpy(dims):
     assert np.abs(out - inv).max() < 2e-6 * np.abs(inv).max()
 
 
-def run_mesh(exe, pt, dims, L, n_global, bias, lgT, modes, stale=0.0):
+def run_mesh(exe, pt, dims, L, n_global, bias, lgT, modes, stale=0.0, tilt=None):
     nx, ny, nz = dims
     N = pt.shape[0]
+    env = dict(os.environ)
+    env.pop("METAD_EMUL_TILT", None)
+    if tilt is not None:
+        env["METAD_EMUL_TILT"] = ",".join(repr(float(t)) for t in tilt)
     with tempfile.TemporaryDirectory() as d:
         fin, fout = os.path.join(d, "in.bin"), os.path.join(d, "out.bin")
         pt.tofile(fin)
         subprocess.check_call([exe, str(nx), str(ny), str(nz)] + [repr(float(x)) for x in L] + [str(n_global), repr(bias), str(lgT),
-                              repr(float(stale)), str(len(modes))] + [repr(float(m)) for m in modes] + [fin, fout])
+                              repr(float(stale)), str(len(modes))] + [repr(float(m)) for m in modes] + [fin, fout], env=env)
         raw = np.fromfile(fout, dtype=np.uint8)
     M = nx * ny * nz
     cv, msq, shift_err, strays, scale, mismatch = raw[:48].view(np.float64)
@@ -118,6 +122,62 @@ def test_mesh_pipeline_matches_oracle(oracle, N, dims, L, lgT, modes, edge, stal
     assert np.abs(dinv).max() < 5e-6 * np.abs(m.inv_re - m.inv_re.mean()).max()
     assert np.abs(r["force"] - fo).max() < 1e-5 * np.abs(fo).max()  # north-star tolerance for forces
     assert np.all(r["force"][:, 3] == 0)
+
+
+@pytest.mark.parametrize("literal", [True, False])
+@pytest.mark.parametrize("N,dims,L,tilt,lgT,modes,stale", [
+    (3000, (32, 32, 32), (10.0, 10.0, 10.0), (0.2, -0.1, 0.15), 3, (1.0,), 0.0),
+    (5000, (32, 16, 64), (10.0, 7.3, 21.1), (-0.35, 0.4, 0.25), 3, (1.0, -1.0), 0.4),   # literal offset 12 cells: all weight lost
+    (5000, (64, 32, 32), (12.0, 9.0, 10.0), (0.5, 0.0, -0.3), 4, (1.0, -0.5, 2.0), 0.4),
+    (4000, (32, 32, 32), (11.0, 12.0, 13.0), (0.0, 0.3, 0.0), 3, (1.0,), 3.5),           # stale order: direct path
+    (4000, (32, 32, 32), (11.0, 12.0, 13.0), (0.02, -0.01, 0.03), 3, (1.0, -1.0), 0.4),  # small tilt: offsets below one cell
+])
+def test_mesh_pipeline_triclinic_matches_oracle(oracle, monkeypatch, N, dims, L, tilt, lgT, modes, stale, literal):
+    """Triclinic boxes (BoxDim::makeFraction shears x and y; forces come back through the reciprocal lattice vectors,
+    OrderParameterMesh.cc:543-573, 761-769, 836-850).  literal: with the constant the reference's in-cell offsets carry in
+    a sheared box (makeFraction(shift + lo), :571-573) -- the behaviour a user of the reference gets; otherwise the
+    geometrically correct assignment."""
+    exe = build_emul("mesh_emul")
+    monkeypatch.setenv("METAD_EMUL_TILT_LITERAL", "1" if literal else "0")
+    # With the literal offsets the weights are cut off at |x| = 3/2 and no longer sum to one, so the density is a
+    # DISCONTINUOUS function of the cell a particle on a cell face is given to (decided at 1e-16 in the double build):
+    # particles within ulps of faces are only meaningful for the continuous (corrected) assignment.
+    pos, types = triclinic_case(N, L, tilt, len(modes), N + lgT, faces=not literal)
+    pt = oracle.make_postype(pos, types)
+    bias = -0.6
+    r = run_mesh(exe, pt, dims, L, N, bias, lgT, modes, stale, tilt=tilt)
+    m = oracle.Mesh(*dims, modes, L, N, "f64", tilt=tilt, literal_copysignf=False, literal_tilt_offset=literal)
+    cvo = m.current_value(pt)
+    fo = m.forces(pt, bias)
+    m32 = oracle.Mesh(*dims, modes, L, N, "f32", tilt=tilt)
+    m32.assign(pt)
+    assert np.array_equal(r["cells"], m32.cells())                  # bit-exact against the single-precision build
+    # hot stencil vs its fp64 form; the literal offsets (up to 12 cells here) are added in single precision
+    assert r["shift_err"] < (1.5e-7 * max(1.0, 8.0 * max(abs(t) for t in tilt) * max(dims)) if literal else 1e-7)
+    assert (r["strays"] > 0) == (stale > 2.0)
+    # literal offsets of more than a cell drop most of the weight (3 % of it survives in the first case): the fixed-point
+    # resolution of a tap is then a larger fraction of the density, and the CV goes with its fourth power
+    lost = np.abs(r["rho"].sum()) < 0.5 * N * abs(np.mean(modes)) if literal else False
+    assert r["cv"] == pytest.approx(cvo, rel=3e-6 if lost else 1e-6)
+    assert np.abs(r["rho"] - m.mesh).max() < 2e-6 * max(1.0, np.abs(m.mesh).max())
+    assert np.abs(r["force"] - fo).max() <= 1e-5 * np.abs(fo).max()
+    assert np.all(r["force"][:, 3] == 0)
+
+
+def test_mesh_pipeline_matches_reference_vectors_triclinic():
+    """Vector t0 of the reference's own OrderParameterMesh.cc in a triclinic box (double build)."""
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_golden.npz"))
+    c = G["t0_cfg"]
+    dims, L, tilt, bias, modes = tuple(int(v) for v in c[:3]), tuple(c[3:6]), tuple(c[6:9]), float(c[9]), tuple(c[10:])
+    pt = G["t0_postype"]
+    r = run_mesh(build_emul("mesh_emul"), pt, dims, L, pt.shape[0], bias, 3, modes, 0.9, tilt=tilt)
+    ref_cv, ref_msq = G["t0_f64_cv"]
+    assert r["msq"] == ref_msq
+    rho = G["t0_f64_rho"]
+    assert np.abs(r["rho"] - rho).max() < 2e-6 * max(1.0, np.abs(rho).max())
+    assert r["cv"] == pytest.approx(ref_cv, rel=1e-6)
+    fr = G["t0_f64_force"]
+    assert np.abs(r["force"] - fr).max() < 2e-4 * np.abs(fr).max()
 
 
 @pytest.mark.parametrize("name", ["m0", "m1", "m2"])

@@ -48,6 +48,30 @@ def test_reference_test_mesh_scenario(api, oracle):
         mesh.cpp_force.getLogValue("no_such_quantity", 1)
 
 
+def test_mesh_cv_in_a_triclinic_box_through_the_api(api, oracle):
+    """cv.mesh in a box with tilt factors, through the script-level API: BoxDim carries the tilt to the plan
+    (OrderParameterMesh.cc:543, 761-769); the result is the reference's (literal in-cell offsets, see metad_b200.h key 16)."""
+    cv, integrate, hoomd = api
+    from conftest import triclinic_case
+    N, L, tilt = 4000, (11.0, 12.0, 13.0), (0.02, -0.01, 0.03)
+    pos, types = triclinic_case(N, L, tilt, 2, 17, faces=False)
+    hoomd.init.from_arrays(pos, types, ["A", "B"], L, tilt=tilt)
+    integrate.mode_standard(dt=0.001)
+    mesh = cv.mesh(nx=32, mode={'A': 1.0, 'B': -1.0})
+    cv0 = 0.01
+    mesh.set_params(umbrella='harmonic', cv0=cv0, kappa=50.0)
+    hoomd.run(1)
+    pt = oracle.make_postype(pos, types)
+    o = oracle.Mesh(32, 32, 32, [1.0, -1.0], L, N, "f64", tilt=tilt, literal_copysignf=False)
+    cvo = o.current_value(pt)
+    val = mesh.cpp_force.getLogValue("cv_mesh", 1)
+    assert val == pytest.approx(cvo, rel=2e-6)
+    bias = oracle.umbrella_bias("harmonic", cvo, 0.0, cv0=cv0, kappa=50.0)
+    f = mesh.get_forces()
+    fo = o.forces(pt, bias)
+    assert np.abs(f - fo).max() < 2e-5 * np.abs(fo).max()          # the umbrella's bias factor carries the CV's 1e-6
+
+
 def test_reference_test_2d_scenario(api, oracle, tmp_path):
     """reference test/test_2d.py: one particle, density + aspect-ratio CVs on a 20x30 grid, well-tempered, stride 1,
     grid dumped every step, box rescaled between two run(1) calls; a restart from bias.dat_1 must reproduce

@@ -672,6 +672,161 @@ def test_mesh_empty_and_tiny_inputs(gpu, oracle):
     assert mesh.compute_cv(empty, 5, box).cpu().item() == 0.0        # and back to empty: the accumulator was cleared
 
 
+# ------------------------------------------------------------------------------------------------ mesh CV in triclinic boxes
+def test_mesh_triclinic_against_reference_vector(gpu, oracle):
+    """Vector t0 (tests/golden/ref_golden.npz): the REFERENCE's own OrderParameterMesh.cc, double build, in a box with tilt
+    factors (0.2, -0.1, 0.15).  Its in-cell offsets carry a constant there (makeFraction(shift + lo) shears `lo` as well,
+    OrderParameterMesh.cc:571-573, 806-808: 0.67 cells along x, 1.33 along y) and TSC weight beyond |x| = 3/2 is dropped;
+    the device path reproduces that behaviour by default (knob 16)."""
+    import torch
+    G = _ref_gold()
+    c = G["t0_cfg"]
+    dims, L, tilt, bias, modes = tuple(int(v) for v in c[:3]), tuple(c[3:6]), tuple(c[6:9]), float(c[9]), tuple(c[10:])
+    pt = G["t0_postype"]
+    N = pt.shape[0]
+    d_pt = torch.from_numpy(pt).cuda()
+    box = gpu.Box.make(L, tilt)
+    mesh = gpu.Mesh(*dims, modes)
+    mesh.set(1, 1)
+    mesh.set(3, 1)
+    mesh.set(13, 1)                                                         # q_max epilogue (checked against the oracle below)
+    cv = mesh.compute_cv(d_pt, N, box).cpu().item()
+    ref_cv, ref_msq = G["t0_f64_cv"]
+    assert mesh.mode_sq() == ref_msq
+    rho = G["t0_f64_rho"]
+    assert np.abs(rho.sum()) < 0.9 * N                                      # the reference does lose weight here
+    assert np.abs(mesh.rho() - rho).max() < 2e-6 * max(1.0, np.abs(rho).max())
+    assert cv == pytest.approx(ref_cv, rel=1e-6)
+    f = mesh.forces(d_pt, N, box, torch.tensor([bias], dtype=torch.float64, device="cuda")).cpu().numpy()
+    fr = G["t0_f64_force"]
+    assert np.abs(f - fr).max() < 2e-4 * np.abs(fr).max()                   # copysignf in the reference's double build, see above
+    m = oracle.Mesh(*dims, modes, L, N, "f64", tilt=tilt, literal_copysignf=False)
+    m.current_value(pt)
+    fo = m.forces(pt, bias)
+    assert np.abs(f - fo).max() < 1e-5 * np.abs(fo).max()
+    m32 = oracle.Mesh(*dims, modes, L, N, "f32", tilt=tilt)
+    m32.assign(pt)
+    assert np.array_equal(mesh.cells(), m32.cells())                        # single-precision BoxDim::makeFraction, bit for bit
+    # computeQmax scans k = 0 as well, and with weight lost f_0 is no longer sum a / N: the kernel restores what the mean
+    # removal took out (ConvParams::dc_restore)
+    x, qo = mesh.extras(), m.qmax()
+    assert x["sq_max"] == pytest.approx(qo[3], rel=2e-6)
+    assert np.allclose(x["q_max"], qo[:3], rtol=1e-6, atol=1e-12) or np.allclose(x["q_max"], -qo[:3], rtol=1e-6, atol=1e-12)
+
+
+TRI_CASES = [
+    (3000, (32, 32, 32), (10.0, 10.0, 10.0), (0.2, -0.1, 0.15), (1.0,)),
+    (5000, (32, 16, 64), (10.0, 7.3, 21.1), (-0.35, 0.4, 0.25), (1.0, -1.0)),       # literal offset 12 cells: all weight lost
+    (40000, (64, 64, 64), (30.0, 28.0, 33.0), (0.02, -0.01, 0.03), (1.0, -1.0)),    # small tilt: offsets below one cell
+    (300000, (128, 64, 128), (70.0, 35.0, 70.0), (0.3, 0.1, -0.2), (1.0, -0.5)),    # 16^3 tiles
+]
+
+
+@pytest.mark.parametrize("literal", [True, False])
+@pytest.mark.parametrize("N,dims,L,tilt,modes", TRI_CASES)
+def test_mesh_triclinic_cv_forces_cells(gpu, oracle, N, dims, L, tilt, modes, literal):
+    """cv.mesh in a triclinic box against the oracle: with the reference's literal in-cell offsets (default) and with the
+    geometrically correct ones (knob 16 = 0; that assignment is continuous, so particles within ulps of cell faces are part
+    of the input)."""
+    import torch
+    from conftest import triclinic_case
+    pos, types = triclinic_case(N, L, tilt, len(modes), N % 1000 + 7, faces=not literal)
+    d_pt = to_dev(gpu, pos, types)
+    h_pt = host_pt(oracle, pos, types)
+    box = gpu.Box.make(L, tilt)
+    mesh = gpu.Mesh(*dims, modes)
+    mesh.set(16, 1 if literal else 0)
+    mesh.set(1, 1)
+    mesh.set(3, 1)
+    cv = mesh.compute_cv(d_pt, N, box).cpu().item()
+    m = oracle.Mesh(*dims, modes, L, N, "f64", tilt=tilt, literal_copysignf=False, literal_tilt_offset=literal)
+    cvo = m.current_value(h_pt)
+    m32 = oracle.Mesh(*dims, modes, L, N, "f32", tilt=tilt)
+    m32.assign(h_pt)
+    assert np.array_equal(mesh.cells(), m32.cells())
+    assert mesh.mode_sq() == m.mode_sq()
+    assert np.abs(mesh.rho() - m.mesh).max() < 2e-6 * max(1.0, np.abs(m.mesh).max())
+    # literal offsets of more than a cell drop most of the weight; the fixed-point resolution of a tap is then a larger
+    # fraction of the density and the CV goes with its fourth power (tests/test_emulation.py)
+    lost = literal and abs(m.mesh.sum()) < 0.5 * abs(np.asarray(modes)[types].sum())
+    assert cv == pytest.approx(cvo, rel=3e-6 if lost else 1e-6)
+    bias = torch.tensor([-0.6], dtype=torch.float64, device="cuda")
+    f = mesh.forces(d_pt, N, box, bias).cpu().numpy()
+    fo = m.forces(h_pt, -0.6)
+    assert np.abs(f - fo).max() <= 1e-5 * np.abs(fo).max()
+    assert np.all(f[:, 3] == 0)
+    cv2 = mesh.compute_cv(d_pt, N, box).cpu().item()
+    f2 = mesh.forces(d_pt, N, box, bias).cpu().numpy()
+    assert cv2 == cv and np.array_equal(f, f2)
+    st = mesh.stats()
+    assert st["rebuilds"] == 1 and st["drifted"] == 0 and st["outside_slab"] == 0
+    # without the particle cache (knob 9 = 0) the gather recomputes cell and offsets: same forces
+    nocache = gpu.Mesh(*dims, modes)
+    nocache.set(16, 1 if literal else 0)
+    nocache.set(9, 0)
+    assert nocache.compute_cv(d_pt, N, box).cpu().item() == pytest.approx(cv, rel=1e-7)
+    assert np.abs(nocache.forces(d_pt, N, box, bias).cpu().numpy() - f).max() <= 1e-6 * np.abs(f).max()
+
+
+def test_mesh_triclinic_stale_order_and_epilogues(gpu, oracle):
+    """Triclinic box: particles that drifted out of their padded tile (direct path of spread and gather), and the q_max /
+    virial epilogues with the reciprocal lattice vectors of the sheared box."""
+    import torch
+    from conftest import triclinic_case
+    N, dims, L, tilt, modes = 50000, (64, 64, 64), (40.0, 36.0, 44.0), (0.25, -0.15, 0.1), (1.0, -1.0)
+    pos, types = triclinic_case(N, L, tilt, 2, 5, faces=False)
+    box = gpu.Box.make(L, tilt)
+    bias = torch.tensor([0.9], dtype=torch.float64, device="cuda")
+    mesh = gpu.Mesh(*dims, modes)
+    mesh.set(16, 0)
+    mesh.set(0, 1000)
+    mesh.set(13, 1)
+    kt = np.linspace(0.2, 6.0, 64)
+    dK = -2.0 * (kt - 2.0) * np.exp(-(kt - 2.0) ** 2)
+    mesh.set_table(dK, 0.2, 6.0)
+    mesh.compute_cv(to_dev(gpu, pos, types), N, box)
+    # move every particle by up to 2.5 cells along z (a lattice direction that needs no re-wrapping in x and y for the
+    # particles that stay inside) and put it back into the box the way BoxDim::wrap does
+    rng = np.random.default_rng(3)
+    Lz, (xy, xz, yz) = L[2], tilt
+    p = pos.astype(np.float64)
+    dz = (rng.random(N) - 0.5) * 5.0 * Lz / dims[2]          # along the lattice vector a3 = (xz, yz, 1) Lz: only the z fraction changes
+    p[:, 2] += dz; p[:, 1] += yz * dz; p[:, 0] += xz * dz
+    up, dn = p[:, 2] >= Lz / 2, p[:, 2] < -Lz / 2
+    for sel, sgn in ((up, -1.0), (dn, 1.0)):
+        p[sel, 2] += sgn * Lz; p[sel, 1] += sgn * Lz * yz; p[sel, 0] += sgn * Lz * xz
+    pos2 = p.astype(np.float32)
+    # keep what is still strictly inside the box after the rounding to float (HOOMD would wrap the rest)
+    q = pos2.astype(np.float64)
+    fy = (q[:, 1] - yz * q[:, 2]) / L[1] + 0.5
+    fx = (q[:, 0] - (xz - yz * xy) * q[:, 2] - xy * q[:, 1]) / L[0] + 0.5
+    fz = q[:, 2] / Lz + 0.5
+    keep = np.all([(v > 1e-6) & (v < 1.0 - 1e-6) for v in (fx, fy, fz)], axis=0)
+    assert keep.sum() > 0.99 * N
+    pos2, types2 = pos2[keep], types[keep]
+    N2 = pos2.shape[0]
+    mesh2 = gpu.Mesh(*dims, modes)
+    mesh2.set(16, 0); mesh2.set(0, 1000); mesh2.set(13, 1); mesh2.set_table(dK, 0.2, 6.0)
+    d0 = to_dev(gpu, pos[keep], types2)
+    mesh2.compute_cv(d0, N2, box)                                            # tile order from the old positions
+    d_pt = to_dev(gpu, pos2, types2)
+    cv = mesh2.compute_cv(d_pt, N2, box).cpu().item()
+    f = mesh2.forces(d_pt, N2, box, bias).cpu().numpy()
+    st = mesh2.stats()
+    assert st["rebuilds"] == 1 and st["drifted"] > N2 // 256
+    h_pt = host_pt(oracle, pos2, types2)
+    m = oracle.Mesh(*dims, modes, L, N2, "f64", tilt=tilt, literal_copysignf=False, literal_tilt_offset=False)
+    assert cv == pytest.approx(m.current_value(h_pt), rel=1e-6)
+    fo = m.forces(h_pt, 0.9)
+    assert np.abs(f - fo).max() < 1e-5 * np.abs(fo).max()
+    x = mesh2.extras()
+    qo = m.qmax()
+    assert x["sq_max"] == pytest.approx(qo[3], rel=2e-6)
+    assert np.allclose(x["q_max"], qo[:3], rtol=1e-6, atol=1e-12) or np.allclose(x["q_max"], -qo[:3], rtol=1e-6, atol=1e-12)
+    vo = m.virial(dK, 0.2, 6.0, 0.9)
+    np.testing.assert_allclose(0.9 * x["virial"], vo, rtol=2e-5, atol=2e-6 * np.abs(vo).max())
+
+
 def test_mesh_rejects_unsupported(gpu):
     from metadynamics_plugin_b200._abi import MetadError
     with pytest.raises(MetadError, match="power of two"):
@@ -679,8 +834,6 @@ def test_mesh_rejects_unsupported(gpu):
     mesh = gpu.Mesh(32, 32, 32, [1.0])
     import torch
     pt = gpu.make_postype(np.zeros((4, 3), np.float32))
-    with pytest.raises(MetadError, match="triclinic"):
-        mesh.compute_cv(pt, 4, gpu.Box.make(5.0, (0.1, 0, 0)))
     with pytest.raises(MetadError, match="metad_mesh_cv"):
         mesh.forces(pt, 4, gpu.Box.make(5.0), torch.zeros(1, dtype=torch.float64, device="cuda"))
 

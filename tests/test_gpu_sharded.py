@@ -138,6 +138,60 @@ def test_mesh_slab_peer_memory_path(gpu, oracle, N, dims, L, P, modes):
     assert np.abs(f - fo).max() < 1e-5 * np.abs(fo).max()
 
 
+@pytest.mark.parametrize("N,dims,L,tilt,P,modes,literal", [
+    (20000, (64, 32, 32), (20.0, 11.0, 13.0), (0.03, -0.02, 0.04), 2, (1.0, -1.0), True),
+    (60000, (128, 32, 64), (40.0, 10.0, 20.0), (0.3, 0.2, -0.25), 4, (1.0, -1.0), False),
+])
+def test_mesh_slab_triclinic(gpu, oracle, N, dims, L, tilt, P, modes, literal):
+    """z slabs of a triclinic box (the shear leaves the z fraction alone, so the slab of a particle is still a function of
+    z): staged and peer-memory paths against the single plan and the oracle."""
+    import torch
+    from conftest import triclinic_case
+    ops, sharded = gpu
+    nx, ny, nz = dims
+    pos, types = triclinic_case(N, L, tilt, len(modes), N + P, faces=False)
+    owner = sharded.slab_of(pos[:, 2], L[2], nz, P)
+    box = ops.Box.make(L, tilt)
+    idx = [np.nonzero(owner == r)[0] for r in range(P)]
+    pts = [ops.make_postype(pos[i], types[i]) for i in idx]
+    bias = torch.tensor([0.9], dtype=torch.float64, device="cuda")
+
+    def make_ranks():
+        rr = [sharded.MeshSlabRank(nx, ny, nz, P, r, modes) for r in range(P)]
+        for r in rr:
+            r.set(16, 1 if literal else 0)
+        return rr
+
+    def collect(forces):
+        f = np.zeros((N, 4), np.float32)
+        for i, fr in zip(idx, forces):
+            f[i] = fr.cpu().numpy()
+        return f
+
+    ranks = make_ranks()
+    cvs, forces = sharded.mesh_slab_step_local(ranks, sharded.LocalComm(P), pts, N, box, bias)
+    cv, f = cvs[0].cpu().item(), collect(forces)
+    assert all(r.sums.cpu()[2].item() == 0 for r in ranks)        # no particle outside its slab
+    ranks2 = make_ranks()
+    sharded.connect_local(ranks2)
+    for _ in range(2):
+        cvs2, forces2 = sharded.mesh_slab_p2p_step_local(ranks2, pts, N, box, bias)
+    assert cvs2[0].cpu().item() == pytest.approx(cv, rel=1e-12)
+    assert np.abs(collect(forces2) - f).max() <= 1e-6 * np.abs(f).max()
+    single = ops.Mesh(nx, ny, nz, modes)
+    single.set(16, 1 if literal else 0)
+    d_all = ops.make_postype(pos, types)
+    cv1 = single.compute_cv(d_all, N, box).cpu().item()
+    f1 = single.forces(d_all, N, box, bias).cpu().numpy()
+    assert cv == pytest.approx(cv1, rel=2e-7)
+    assert np.abs(f - f1).max() < 2e-6 * np.abs(f1).max()
+    h_pt = oracle.make_postype(pos, types)
+    o = oracle.Mesh(nx, ny, nz, modes, L, N, "f64", tilt=tilt, literal_copysignf=False, literal_tilt_offset=literal)
+    assert cv == pytest.approx(o.current_value(h_pt), rel=1e-6)
+    fo = o.forces(h_pt, 0.9)
+    assert np.abs(f - fo).max() < 1e-5 * np.abs(fo).max()
+
+
 def test_mesh_slab_counts_misplaced_particles(gpu):
     import torch
     ops, sharded = gpu

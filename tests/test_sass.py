@@ -39,9 +39,21 @@ def test_tile_movement_uses_the_tma_engine(sass):
     spread = _body(sass, "void metad::mesh::mesh_spread_kernel<4, 10>")          # cache + tensor-map flush: the default at C4
     assert "UTMAREDG.3D.ADD" in spread and "UBLKRED" in spread                   # interior tiles / wrapped tiles
     assert spread.count("ATOMS.ADD") >= 27 and "ATOMS.CAST" not in spread        # native integer atomics, no CAS loop
-    gather = _body(sass, "void metad::mesh::mesh_gather_kernel<4, 192, 3, true>")
+    gather = _body(sass, "void metad::mesh::mesh_gather_kernel<4, 192, 3, true, false>")
     assert "UTMALDG.3D" in gather and "UBLKCP" in gather and "LDGSTS" in gather
     assert "FFMA2" in gather and "FFMA2" in spread                               # packed fp32 tap arithmetic
+
+
+def test_triclinic_variants_leave_the_orthorhombic_kernels_alone(sass):
+    """The sheared coordinates are evaluated in fp64 (particle_stencil<true>): those instructions live in separate
+    instantiations (kSpTri / TRI), the default kernels carry none of them inside their particle loops."""
+    ortho = _body(sass, "void metad::mesh::mesh_spread_kernel<4, 10>")
+    tri = _body(sass, "void metad::mesh::mesh_spread_kernel<4, 18>")             # cache + triclinic (row flush)
+    # (the orthorhombic kernel converts the mode coefficient once per particle for its fp64 sums, nothing else)
+    assert tri.count("F2F.F64.F32") >= ortho.count("F2F.F64.F32") + 3 and ortho.count("F2F.F64.F32") <= 1 and ortho.count("F2F.F32.F64") == 0
+    assert tri.count("ATOMS.ADD") >= 27 and "ATOMS.CAST" not in tri
+    gt = _body(sass, "void metad::mesh::mesh_gather_kernel<4, 192, 3, true, true>")
+    assert "UTMALDG.3D" in gt and "FFMA2" in gt
 
 
 def test_wide_spread_uses_split_32_bit_tiles_and_64_bit_reductions(sass):
