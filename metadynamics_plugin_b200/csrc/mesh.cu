@@ -29,6 +29,7 @@
 #include "mesh_kernels.cuh"
 #include "mesh_fft_kernels.cuh"
 #include "mesh_fft_xy.cuh"
+#include "mesh_general.cuh"
 #include "mesh_p2p.cuh"
 
 #include <cuda.h>            // CUtensorMap + cuTensorMapEncodeTiled (resolved through cudaGetDriverEntryPoint, no -lcuda)
@@ -147,6 +148,14 @@ struct metad_mesh {
     double* d_sums_global = nullptr;            // [4] sums over all ranks
     double* d_cv_partial = nullptr;
     unsigned* d_p2p_status = nullptr;
+    // general path (mesh_general.cuh): mesh sizes the tiled kernels do not take (not a power of two, or outside their range)
+    bool general = false;
+    float2* d_spec = nullptr;                   // complex mesh: density -> spectrum -> G -> IFFT(G)
+    int* d_cells = nullptr;                     // knob 3: reported cell of every particle, int[3 N]
+    unsigned cells_cap = 0;
+    double* d_gen_sums = nullptr;               // per-block partials of sum a^2, sum a
+    float2* d_gtw[3] = {nullptr, nullptr, nullptr};
+    meshgen::Radices grad[3] = {};
     // state
     bool have_cv = false;
     unsigned last_N = 0;
@@ -473,6 +482,24 @@ void reciprocal_vectors(const double* L, const double* tilt, double (&b)[3][3]) 
     cross(a2, a3, b[0]); cross(a3, a1, b[1]); cross(a1, a2, b[2]);
 }
 
+// n_a b_a of the force interpolation (ForceParams, mesh_kernels.cuh); an orthorhombic box keeps the plain quotients n / L
+void set_force_matrix(ForceParams& fp, const Geom& g, const metad_box* box) {
+    memset(fp.nb1, 0, sizeof fp.nb1); memset(fp.nb2, 0, sizeof fp.nb2); memset(fp.nb3, 0, sizeof fp.nb3);
+    if (box->tilt[0] == 0.0 && box->tilt[1] == 0.0 && box->tilt[2] == 0.0) {
+        fp.nb1[0] = (float)((double)g.nx / box->L[0]);
+        fp.nb2[1] = (float)((double)g.ny / box->L[1]);
+        fp.nb3[2] = (float)((double)g.nzg / box->L[2]);
+        return;
+    }
+    double b[3][3];
+    reciprocal_vectors(box->L, box->tilt, b);
+    for (int c = 0; c < 3; ++c) {
+        fp.nb1[c] = (float)((double)g.nx * b[0][c]);
+        fp.nb2[c] = (float)((double)g.ny * b[1][c]);
+        fp.nb3[c] = (float)((double)g.nzg * b[2][c]);
+    }
+}
+
 int set_box(metad_mesh* p, const metad_box* box) {
     for (int i = 0; i < 3; ++i) METAD_REQUIRE(box->L[i] > 0.0, "cv.mesh: box lengths must be positive");
     geom_set_box(p->g, box->L, box->tilt, p->tilt_literal);          // the box is the GLOBAL box
@@ -729,15 +756,7 @@ int launch_gather(metad_mesh* p, const float* d_postype, const float* d_ghost, f
     // reciprocal lattice vectors of the (orthorhombic) box without 2 pi, times the mesh dimensions (:761-769, :852-854)
     ForceParams fp;
     memset(&fp, 0, sizeof fp);
-    {
-        double b[3][3];
-        reciprocal_vectors(box->L, box->tilt, b);
-        for (int c = 0; c < 3; ++c) {
-            fp.nb1[c] = (float)((double)g.nx * b[0][c]);
-            fp.nb2[c] = (float)((double)g.ny * b[1][c]);
-            fp.nb3[c] = (float)((double)g.nzg * b[2][c]);
-        }
-    }
+    set_force_matrix(fp, g, box);
     fp.two_over_n = 2.0 / (double)N_global;
     int rc = mark(p, 8, stream); if (rc) return rc;
     GatherIn gin;
@@ -817,17 +836,184 @@ int launch_gather(metad_mesh* p, const float* d_postype, const float* d_ghost, f
     return mark(p, 9, stream);
 }
 
+// ---- general path (mesh_general.cuh) ------------------------------------------------------------------
+bool tiled_path_takes(unsigned nx, unsigned ny, unsigned nz) {
+    return is_pow2(nx) && is_pow2(ny) && is_pow2(nz) && nx >= 32 && nx <= 1024 && ny >= 16 && ny <= 512 && nz >= 16 && nz <= 512;
+}
+
+int general_create(metad_mesh** out, unsigned nx, unsigned ny, unsigned nz, int ntypes, const double* mode) {
+    using namespace meshgen;
+    if (nx < 1 || ny < 1 || nz < 1 || nx > kMaxLen || ny > kMaxLen || nz > kMaxLen) {
+        set_error("cv.mesh: supported mesh sizes are 1 <= nx, ny, nz <= 1024");
+        return METAD_ERR_UNSUPPORTED;
+    }
+    auto* p = new metad_mesh();
+    p->general = true;
+    geom_set_dims_general(p->g, nx, ny, nz);
+    p->n_ranks = 1; p->rank = 0; p->nzg = nz; p->kxl = 0;
+    p->ntypes = ntypes;
+    std::vector<float> m(ntypes);
+    p->amax = 0.f;
+    for (int i = 0; i < ntypes; ++i) { m[i] = (float)mode[i]; p->amax = fmaxf(p->amax, fabsf(m[i])); }
+    const size_t M = (size_t)nx * ny * nz;
+    p->n_partials = kMaxConvBlocks;
+    int rc = METAD_OK;
+    auto fail = [&](cudaError_t e, const char* what) { rc = cuda_fail(e, what, __FILE__, __LINE__); };
+    cudaError_t e;
+#define TRY(call) if (rc == METAD_OK && (e = (call)) != cudaSuccess) fail(e, #call)
+    TRY(cudaMalloc(&p->d_mode, sizeof(float) * ntypes));
+    TRY(cudaMemcpy(p->d_mode, m.data(), sizeof(float) * ntypes, cudaMemcpyHostToDevice));
+    TRY(cudaMalloc(&p->d_mesh64, sizeof(long long) * M));
+    TRY(cudaMemset(p->d_mesh64, 0, sizeof(long long) * M));
+    TRY(cudaMalloc(&p->d_spec, sizeof(float2) * M));
+    TRY(cudaMalloc(&p->d_sums, sizeof(double) * 4));
+    TRY(cudaMemset(p->d_sums, 0, sizeof(double) * 4));
+    TRY(cudaMalloc(&p->d_gen_sums, sizeof(double) * 2 * kMaxConvBlocks));
+    TRY(cudaMalloc(&p->d_partials, sizeof(double) * p->n_partials));
+    TRY(cudaMalloc(&p->d_ticket, sizeof(unsigned)));
+    TRY(cudaMemset(p->d_ticket, 0, sizeof(unsigned)));
+    TRY(cudaMallocHost(&p->h_counters, sizeof(unsigned) * 4));
+    TRY(cudaMallocHost(&p->h_mode, sizeof(unsigned) * 4));
+#undef TRY
+    if (rc == METAD_OK) {
+        memset(p->h_counters, 0, sizeof(unsigned) * 4);
+        memset(p->h_mode, 0, sizeof(unsigned) * 4);
+    }
+    const unsigned dims[3] = {nx, ny, nz};
+    for (int a = 0; a < 3 && rc == METAD_OK; ++a) {
+        p->grad[a] = factorize(dims[a]);
+        rc = upload_twiddles(&p->d_gtw[a], dims[a]);
+    }
+    if (rc != METAD_OK) { metad_mesh_destroy(p); return rc; }
+    *out = p;
+    return METAD_OK;
+}
+
+int general_fft(metad_mesh* p, int axis, float sign, cudaStream_t st) {
+    using namespace meshgen;
+    LineMap lm;
+    lm.nx = p->g.nx; lm.ny = p->g.ny; lm.nz = p->g.nz; lm.axis = axis;
+    const unsigned n = axis == 0 ? lm.nx : (axis == 1 ? lm.ny : lm.nz);
+    if (n == 1) return METAD_OK;                                    // a transform of length one is the identity
+    unsigned threads = (n + 31u) / 32u * 32u;
+    if (threads > (unsigned)kFftThreads) threads = kFftThreads;
+    gen_fft_kernel<<<line_count(lm), threads, sizeof(float2) * 3 * n, st>>>(p->d_spec, lm, p->grad[axis], p->d_gtw[axis], sign);
+    METAD_LAUNCH_CHECK();
+    return METAD_OK;
+}
+
+int general_cv(metad_mesh* p, const float* d_postype, unsigned N, unsigned N_global, double* d_cv, cudaStream_t st) {
+    using namespace meshgen;
+    const Geom& g = p->g;
+    const size_t M = p->M();
+    int rc = mark(p, 0, st); if (rc) return rc;
+    rc = mark(p, 1, st); if (rc) return rc;
+    if (p->keep_cells && p->cells_cap < N) {
+        cudaFree(p->d_cells); p->d_cells = nullptr; p->cells_cap = 0;
+        METAD_CUDA(cudaMalloc(&p->d_cells, sizeof(int) * 3 * (size_t)(N + N / 16 + 1024)));
+        p->cells_cap = N + N / 16 + 1024;
+    }
+    if (p->keep_rho && !p->d_rho_keep) METAD_CUDA(cudaMalloc(&p->d_rho_keep, sizeof(float) * M));
+    // fixed-point scale: one tap below 2^22; the 64-bit accumulators leave the cell totals alone
+    const float scale = fx_scale_for(p->amax, p->amax);
+    unsigned nb = (N + kParticleThreads - 1) / kParticleThreads;
+    if (nb > (unsigned)kMaxConvBlocks) nb = kMaxConvBlocks;
+    if (N > 0) {
+        int* cells = p->keep_cells ? p->d_cells : nullptr;
+        if (g.tri)
+            gen_spread_kernel<true><<<nb, kParticleThreads, 0, st>>>((const float4*)d_postype, N, g, p->d_mode, scale,
+                                                                    (unsigned long long*)p->d_mesh64, cells, p->d_gen_sums);
+        else
+            gen_spread_kernel<false><<<nb, kParticleThreads, 0, st>>>((const float4*)d_postype, N, g, p->d_mode, scale,
+                                                                     (unsigned long long*)p->d_mesh64, cells, p->d_gen_sums);
+        METAD_LAUNCH_CHECK();
+    }
+    gen_sums_kernel<<<1, 32, 0, st>>>(p->d_gen_sums, N > 0 ? nb : 0u, p->d_sums);
+    METAD_LAUNCH_CHECK();
+    unsigned cb = (unsigned)((M + kConvThreads - 1) / kConvThreads);
+    if (cb > (unsigned)kMaxConvBlocks) cb = kMaxConvBlocks;
+    const double inv_cells = 1.0 / (double)M;
+    gen_density_kernel<<<cb, kConvThreads, 0, st>>>(p->d_mesh64, p->d_spec, p->keep_rho ? p->d_rho_keep : nullptr, M, 1.0f / scale, p->d_sums, inv_cells);
+    METAD_LAUNCH_CHECK();
+    rc = mark(p, 2, st); if (rc) return rc;
+    rc = general_fft(p, 0, -1.f, st); if (rc) return rc;
+    rc = mark(p, 3, st); if (rc) return rc;
+    rc = general_fft(p, 1, -1.f, st); if (rc) return rc;
+    rc = mark(p, 4, st); if (rc) return rc;
+    rc = general_fft(p, 2, -1.f, st); if (rc) return rc;
+    fft::ConvParams cp;
+    memset(&cp, 0, sizeof cp);
+    cp.nx = g.nx; cp.ny = g.ny; cp.nz = g.nz;
+    cp.inv_n = (float)(1.0 / (double)N_global);
+    cp.n_global = (double)N_global;
+    cp.d_mode_sq = p->d_sums;
+    cp.dc_restore = (g.tri && (g.tq[0] != 0.f || g.tq[1] != 0.f)) ? 1 : 0;
+    cp.inv_cells = inv_cells;
+    cp.partials = p->d_partials;
+    cp.ticket = p->d_ticket;
+    cp.d_cv = d_cv;
+    cp.extras = p->extras ? 1 : 0;
+    cp.use_table = (p->use_table && p->d_table_d && p->n_table >= 2) ? 1 : 0;
+    cp.n_table = p->n_table; cp.table_d = p->d_table_d;
+    cp.k_min = (float)p->k_min; cp.k_max = (float)p->k_max;
+    cp.delta_k = p->n_table >= 2 ? (float)((p->k_max - p->k_min) / (double)(p->n_table - 1)) : 1.0f;
+    for (int i = 0; i < 3; ++i)
+        for (int c = 0; c < 3; ++c) cp.bk[3 * i + c] = (float)(2.0 * M_PI * p->box_b[i][c]);
+    if (p->extras) {
+        if (!p->d_vir_partials) {
+            METAD_CUDA(cudaMalloc(&p->d_vir_partials, sizeof(double) * 6 * p->n_partials));
+            METAD_CUDA(cudaMalloc(&p->d_amax_key, sizeof(unsigned long long)));
+            METAD_CUDA(cudaMalloc(&p->d_extras_out, sizeof(double) * 8));
+        }
+        METAD_CUDA(cudaMemsetAsync(p->d_amax_key, 0, sizeof(unsigned long long), st));
+        p->extras_N_global = N_global;
+    }
+    cp.vir_partials = p->d_vir_partials; cp.amax_key = p->d_amax_key; cp.extras_out = p->d_extras_out;
+    if (p->extras) gen_conv_kernel<true><<<cb, kConvThreads, 0, st>>>(p->d_spec, M, cp);
+    else gen_conv_kernel<false><<<cb, kConvThreads, 0, st>>>(p->d_spec, M, cp);
+    METAD_LAUNCH_CHECK();
+    rc = general_fft(p, 2, +1.f, st); if (rc) return rc;
+    rc = mark(p, 5, st); if (rc) return rc;
+    rc = general_fft(p, 1, +1.f, st); if (rc) return rc;
+    rc = mark(p, 6, st); if (rc) return rc;
+    rc = general_fft(p, 0, +1.f, st); if (rc) return rc;
+    return mark(p, 7, st);
+}
+
+int general_forces(metad_mesh* p, const float* d_postype, float* d_force, unsigned N, unsigned N_global, const metad_box* box,
+                   const double* d_bias, cudaStream_t st) {
+    using namespace meshgen;
+    const Geom& g = p->g;
+    ForceParams fp;
+    memset(&fp, 0, sizeof fp);
+    set_force_matrix(fp, g, box);
+    fp.two_over_n = 2.0 / (double)N_global;
+    int rc = mark(p, 8, st); if (rc) return rc;
+    unsigned nb = (N + kParticleThreads - 1) / kParticleThreads;
+    if (nb > 64u * (unsigned)device_sm_count()) nb = 64u * (unsigned)device_sm_count();
+    if (g.tri)
+        gen_gather_kernel<true><<<nb, kParticleThreads, 0, st>>>((const float4*)d_postype, N, g, p->d_mode, p->d_spec, fp, d_bias, (float4*)d_force);
+    else
+        gen_gather_kernel<false><<<nb, kParticleThreads, 0, st>>>((const float4*)d_postype, N, g, p->d_mode, p->d_spec, fp, d_bias, (float4*)d_force);
+    METAD_LAUNCH_CHECK();
+    return mark(p, 9, st);
+}
+
 int create_common(metad_mesh** out, unsigned nx, unsigned ny, unsigned nzg, unsigned n_ranks, unsigned rank, int ntypes,
                   const double* mode) {
     METAD_REQUIRE(out && mode, "metad_mesh_create: null argument");
     METAD_REQUIRE(ntypes > 0, "Number of modes unequal number of particle types.");
     if (ntypes > kSpreadModes) { set_error("cv.mesh: at most 1024 particle types"); return METAD_ERR_UNSUPPORTED; }
+    // one GPU: every mesh size works -- the tiled kernels for powers of two in their range, the general path otherwise
+    if (n_ranks == 1 && (!tiled_path_takes(nx, ny, nzg) || (getenv("METAD_MESH_GENERAL") && atoi(getenv("METAD_MESH_GENERAL")) == 1)))
+        return general_create(out, nx, ny, nzg, ntypes, mode);
+    // z slabs: like the reference under domain decomposition (OrderParameterMesh.cc:70-79), powers of two only
     if (!is_pow2(nx) || !is_pow2(ny) || !is_pow2(nzg)) {
-        set_error("cv.mesh: the number of mesh points along every direction must be a power of two");
+        set_error("cv.mesh: the number of mesh points along every direction must be a power of two when the mesh is sharded");
         return METAD_ERR_UNSUPPORTED;
     }
     if (nx < 32 || nx > 1024 || ny < 16 || ny > 512 || nzg < 16 || nzg > 512) {
-        set_error("cv.mesh: supported mesh sizes are 32 <= nx <= 1024, 16 <= ny,nz <= 512");
+        set_error("cv.mesh: sharded meshes need 32 <= nx <= 1024, 16 <= ny,nz <= 512");
         return METAD_ERR_UNSUPPORTED;
     }
     METAD_REQUIRE(n_ranks >= 1 && rank < n_ranks && is_pow2(n_ranks), "cv.mesh: the number of ranks must be a power of two");
@@ -935,6 +1121,8 @@ extern "C" int metad_mesh_destroy(metad_mesh* p) {
     cudaFree(p->d_mesh64); cudaFree(p->d_table_d); cudaFree(p->d_vir_partials); cudaFree(p->d_amax_key); cudaFree(p->d_extras_out);
     cudaFree(p->d_rho_keep); cudaFree(p->d_twx); cudaFree(p->d_twy); cudaFree(p->d_twz); cudaFree(p->d_sums);
     cudaFree(p->d_partials); cudaFree(p->d_ticket);
+    cudaFree(p->d_spec); cudaFree(p->d_cells); cudaFree(p->d_gen_sums);
+    for (auto& t : p->d_gtw) cudaFree(t);
     cudaFree(p->d_sums_global); cudaFree(p->d_cv_partial); cudaFree(p->d_p2p_status); cudaFree(p->d_epoch); cudaFree(p->d_sync);
     if (p->gexec) cudaGraphExecDestroy(p->gexec);
     if (p->capture_stream) cudaStreamDestroy(p->capture_stream);
@@ -955,6 +1143,12 @@ extern "C" int metad_mesh_cv(metad_mesh* p, const float* d_postype, unsigned N, 
     METAD_REQUIRE(N_global > 0, "metad_mesh_cv: N_global must be positive");
     int rc = set_box(p, box); if (rc) return rc;
     p->have_cv = false;
+    if (p->general) {
+        rc = general_cv(p, d_postype, N, N_global, d_cv, stream); if (rc) return rc;
+        p->have_cv = true;
+        p->last_N = N;
+        return METAD_OK;
+    }
     rc = prepare_order(p, d_postype, N, stream); if (rc) return rc;
     rc = run_captured(p, make_key(p, d_postype, N, N_global, box, d_cv, stream, 0), stream, [&](cudaStream_t st) -> int {
         int r = enqueue_spread(p, d_postype, N, st); if (r) return r;
@@ -977,6 +1171,7 @@ extern "C" int metad_mesh_forces(metad_mesh* p, const float* d_postype, float* d
     }
     if (N == 0) return METAD_OK;
     METAD_REQUIRE(d_postype && d_force, "metad_mesh_forces: null particle arrays");
+    if (p->general) return general_forces(p, d_postype, d_force, N, N_global, box, d_bias, stream);
     return launch_gather(p, d_postype, nullptr, d_force, N_global, box, d_bias, stream);
 }
 
@@ -1358,6 +1553,10 @@ extern "C" int metad_mesh_get(metad_mesh* p, int which, void* h_out) {
         case 0: {
             if (p->last_N == 0) return METAD_OK;
             if (!p->keep_cells) { set_error("metad_mesh_get: enable metad_mesh_set(p, 3, 1) before the spread to keep the cell indices"); return METAD_ERR_STATE; }
+            if (p->general) {
+                METAD_CUDA(cudaMemcpy(h_out, p->d_cells, sizeof(int) * 3 * (size_t)p->last_N, cudaMemcpyDeviceToHost));
+                return METAD_OK;
+            }
             std::vector<unsigned> keys(p->last_N);
             METAD_CUDA(cudaMemcpy(keys.data(), p->d_keys, sizeof(unsigned) * p->last_N, cudaMemcpyDeviceToHost));
             int* out = (int*)h_out;
@@ -1374,6 +1573,12 @@ extern "C" int metad_mesh_get(metad_mesh* p, int which, void* h_out) {
             return METAD_OK;
         case 2:
             if (!p->have_cv) { set_error("metad_mesh_get: no inverse mesh yet"); return METAD_ERR_STATE; }
+            if (p->general) {          // real part of the complex mesh
+                std::vector<float2> h(M);
+                METAD_CUDA(cudaMemcpy(h.data(), p->d_spec, sizeof(float2) * M, cudaMemcpyDeviceToHost));
+                for (size_t c = 0; c < M; ++c) ((float*)h_out)[c] = h[c].x;
+                return METAD_OK;
+            }
             METAD_CUDA(cudaMemcpy(h_out, p->d_buf, sizeof(float) * M, cudaMemcpyDeviceToHost));
             return METAD_OK;
         case 3:
@@ -1401,6 +1606,11 @@ extern "C" int metad_mesh_get(metad_mesh* p, int which, void* h_out) {
             // statistics, double[6]: rebuilds of the tile order so far; of the LAST spread: particles that took the direct
             // path, particles outside the slab, cells past half of the fixed-point range; fixed-point scale; calls since rebuild
             double* out = (double*)h_out;
+            if (p->general) {          // no tile order, no drift, no range to watch
+                out[0] = out[1] = out[2] = out[3] = out[5] = 0.0;
+                out[4] = (double)fx_scale_for(p->amax, p->amax);
+                return METAD_OK;
+            }
             unsigned c[8];
             float fx[2];
             METAD_CUDA(cudaMemcpy(c, p->d_counters, sizeof c, cudaMemcpyDeviceToHost));

@@ -419,7 +419,8 @@ MHD void particle_rebase(Cell& c, float3& s, const Geom& g) {
 // Agrees with particle_cell + particle_shift + particle_rebase (tests/cpu_emul/mesh_emul.cu compares the two on every
 // particle); 20 instead of 34 instructions per axis.
 // LOW: the coordinate is the unevaluated sum x + xl (a sheared coordinate of a triclinic box, |xl| <= ulp(x)/2).
-template <bool LOW = false>
+// POW2 = false: n is any positive number (general mesh path, mesh_general.cuh): the periodic wrap is a remainder.
+template <bool LOW = false, bool POW2 = true>
 MHD void axis_stencil(float x, int axis, const Geom& g, unsigned n, int& i, float& s, float xl = 0.f) {
     const float hl = g.hl_hi[axis], ch = g.c_hi[axis];
     const float d = f_add(hl, x);
@@ -433,7 +434,9 @@ MHD void axis_stencil(float x, int axis, const Geom& g, unsigned n, int& i, floa
     const float t = __fsub_rn(u, 8388608.f);
     const float sv = __fadd_rn(__fadd_rn(__fsub_rn(rh, t), -0.5f), small);
     const float ur = __fadd_rn(sv, kFxMagic);                             // 1.5 2^23 + rint(sv)
-    i = (int)((unsigned)(__float_as_int(u) + __float_as_int(ur) - (0x4B000000 + kFxMagicBits)) & (n - 1));
+    const int iv = __float_as_int(u) + __float_as_int(ur) - (0x4B000000 + kFxMagicBits);
+    if (POW2) i = (int)((unsigned)iv & (n - 1));
+    else { const int m = iv % (int)n; i = m < 0 ? m + (int)n : m; }
     s = __fsub_rn(sv, __fsub_rn(ur, kFxMagic));
 #else
     const float rc = rh > 0.f ? rh : 0.f;
@@ -441,7 +444,9 @@ MHD void axis_stencil(float x, int axis, const Geom& g, unsigned n, int& i, floa
     const float t = (float)i0;
     const float sv = f_add(f_add(f_sub(rh, t), -0.5f), small);
     const float ur = f_add(sv, kFxMagic);
-    i = (int)((unsigned)(i0 + (f2i_bits(ur) - kFxMagicBits)) & (n - 1));
+    const int iv = i0 + (f2i_bits(ur) - kFxMagicBits);
+    if (POW2) i = (int)((unsigned)iv & (n - 1));
+    else { const int m = iv % (int)n; i = m < 0 ? m + (int)n : m; }
     s = f_sub(sv, f_sub(ur, kFxMagic));
 #endif
 }
@@ -452,23 +457,23 @@ MHD void axis_stencil(float x, int axis, const Geom& g, unsigned n, int& i, floa
 // fused multiply-adds; the products of single-precision positions with the tilt factors do not fit single precision) and
 // handed on as float pairs, so the offsets keep the < 1e-7 cell accuracy of the orthorhombic path.  A separate
 // instantiation: the orthorhombic kernels do not carry the fp64 instructions.
-template <bool TRI = false>
+template <bool TRI = false, bool POW2 = true>
 MHD void particle_stencil(float4 p, const Geom& g, Cell& c, float3& s) {
     if (TRI) {
         const double xd = (double)p.x - (g.d_a * (double)p.z + g.d_xy * (double)p.y);
         const double yd = (double)p.y - g.d_yz * (double)p.z;
         const float xh = (float)xd, yh = (float)yd;
-        axis_stencil<true>(xh, 0, g, g.nx, c.ix, s.x, (float)(xd - (double)xh));
-        axis_stencil<true>(yh, 1, g, g.ny, c.iy, s.y, (float)(yd - (double)yh));
+        axis_stencil<true, POW2>(xh, 0, g, g.nx, c.ix, s.x, (float)(xd - (double)xh));
+        axis_stencil<true, POW2>(yh, 1, g, g.ny, c.iy, s.y, (float)(yd - (double)yh));
         s.x += g.tq[0];          // the reference's constant (see Geom::tq); the weights take their general form from here on
         s.y += g.tq[1];
     } else {
-        axis_stencil(p.x, 0, g, g.nx, c.ix, s.x);
-        axis_stencil(p.y, 1, g, g.ny, c.iy, s.y);
+        axis_stencil<false, POW2>(p.x, 0, g, g.nx, c.ix, s.x);
+        axis_stencil<false, POW2>(p.y, 1, g, g.ny, c.iy, s.y);
     }
-    axis_stencil(p.z, 2, g, g.nzg, c.iz, s.z);
+    axis_stencil<false, POW2>(p.z, 2, g, g.nzg, c.iz, s.z);
     c.owned = true;
-    if (g.slab) {
+    if (POW2 && g.slab) {
         const int izf = cell_coord(p.z, 2, g);
         c.owned = (unsigned)(izf - (int)g.z0) < g.nz;
         if (c.owned && (unsigned)(c.iz - (int)g.z0) >= g.nz) {

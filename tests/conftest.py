@@ -34,7 +34,7 @@ def build_emul(name):
     exe = os.path.join(out_dir, name)
     deps = [src, os.path.join(ROOT, "tests", "cpu_emul", "emul_fft.h")] + [
         os.path.join(ROOT, "metadynamics_plugin_b200", "csrc", f)
-        for f in ("mesh_fft.cuh", "mesh_fft_kernels.cuh", "mesh_kernels.cuh", "common.cuh")]
+        for f in ("mesh_fft.cuh", "mesh_fft_kernels.cuh", "mesh_kernels.cuh", "mesh_general.cuh", "common.cuh")]
     if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(d) for d in deps):
         if not os.path.exists(NVCC):
             pytest.skip("nvcc not available to build the CPU emulation harness")

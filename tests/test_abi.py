@@ -43,8 +43,13 @@ def test_no_cpu_fallback_error_is_loud():
     with pytest.raises(_abi.MetadError):
         _abi.check(rc)
     # argument validation happens before any CUDA call
-    rc = _abi.lib.metad_mesh_create(C.byref(h), 48, 32, 32, 1, mode.ctypes.data_as(C.POINTER(C.c_double)))
+    rc = _abi.lib.metad_mesh_create(C.byref(h), 2048, 32, 32, 1, mode.ctypes.data_as(C.POINTER(C.c_double)))
+    assert rc == -3 and "1024" in _abi.last_error()
+    rc = _abi.lib.metad_mesh_slab_create(C.byref(h), 96, 32, 32, 2, 0, 1, mode.ctypes.data_as(C.POINTER(C.c_double)))
     assert rc == -3 and "power of two" in _abi.last_error()
+    # a mesh that is not a power of two is a valid plan (general path): without a device its creation fails on the first CUDA call
+    rc = _abi.lib.metad_mesh_create(C.byref(h), 48, 32, 32, 1, mode.ctypes.data_as(C.POINTER(C.c_double)))
+    assert rc == -2 and "CUDA" in _abi.last_error()
 
 
 def test_product_package_does_not_import_the_oracle():

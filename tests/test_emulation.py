@@ -180,6 +180,76 @@ def test_mesh_pipeline_matches_reference_vectors_triclinic():
     assert np.abs(r["force"] - fr).max() < 2e-4 * np.abs(fr).max()
 
 
+# ---- general path (csrc/mesh_general.cuh): any mesh size
+@pytest.mark.parametrize("N,dims,L,modes,edge", [
+    (2000, (24, 20, 18), (11.0, 9.5, 8.0), (1.0,), True),              # 4.2.3 | 4.5 | 2.3.3
+    (3000, (48, 30, 36), (10.0, 7.3, 21.1), (1.0, -1.0), True),
+    (1500, (7, 11, 13), (6.0, 7.0, 8.0), (1.0, -0.5, 2.0), True),      # prime lengths: one radix-n stage
+    (1000, (32, 32, 32), (10.0, 10.0, 10.0), (1.0,), True),            # a power of two through the general path
+    (500, (3, 1, 2), (4.0, 5.0, 6.0), (1.0,), False),                  # taps alias onto the same cells
+    (3000, (100, 6, 45), (30.0, 4.0, 20.0), (1.0, -1.0), False),
+    (1000, (1021, 2, 3), (100.0, 3.0, 4.0), (1.0,), False),            # the longest prime line: one stage of 1021 terms per output
+    (5000, (16, 16, 16), (8.0, 8.0, 8.0), (1.0,), True),
+])
+def test_general_mesh_pipeline_matches_oracle(oracle, N, dims, L, modes, edge):
+    exe = build_emul("general_emul")
+    pos, types = mesh_case(N, dims, L, modes, edge, N + sum(dims))
+    pt = oracle.make_postype(pos, types)
+    bias = 0.7
+    r = run_mesh(exe, pt, dims, L, N, bias, 3, modes, 0.0)
+    m = oracle.Mesh(*dims, modes, L, N, "f64", literal_copysignf=False)
+    cvo = m.current_value(pt)
+    fo = m.forces(pt, bias)
+    m32 = oracle.Mesh(*dims, modes, L, N, "f32")
+    m32.assign(pt)
+    assert np.array_equal(r["cells"], m32.cells())                  # bit-exact against the single-precision build
+    assert r["msq"] == m.mode_sq()
+    assert r["cv"] == pytest.approx(cvo, rel=1e-6)
+    assert np.abs(r["rho"] - m.mesh).max() < 2e-6 * max(1.0, np.abs(m.mesh).max())
+    dinv = r["inv"] - m.inv_re
+    dinv -= dinv.mean()                                             # k = 0 stays out of the transforms (a constant in the inverse mesh)
+    assert np.abs(dinv).max() < 5e-6 * np.abs(m.inv_re - m.inv_re.mean()).max()
+    assert np.abs(r["force"] - fo).max() <= 1e-5 * np.abs(fo).max()
+    assert np.all(r["force"][:, 3] == 0)
+
+
+@pytest.mark.parametrize("name", ["t0", "t1", "t2"])
+def test_general_mesh_pipeline_matches_reference_vectors(name):
+    """Vectors t0-t2 of the reference's own OrderParameterMesh.cc: mesh sizes that are not powers of two (t1: 24 x 20 x 18,
+    orthorhombic; t2: 20 x 12 x 18, triclinic) and a triclinic power-of-two mesh (t0), double build."""
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_golden.npz"))
+    c = G[name + "_cfg"]
+    dims, L, tilt, bias, modes = tuple(int(v) for v in c[:3]), tuple(c[3:6]), tuple(c[6:9]), float(c[9]), tuple(c[10:])
+    pt = G[name + "_postype"]
+    r = run_mesh(build_emul("general_emul"), pt, dims, L, pt.shape[0], bias, 3, modes, 0.0, tilt=tilt)
+    ref_cv, ref_msq = G[name + "_f64_cv"]
+    assert r["msq"] == ref_msq
+    rho = G[name + "_f64_rho"]
+    assert np.abs(r["rho"] - rho).max() < 2e-6 * max(1.0, np.abs(rho).max())
+    assert r["cv"] == pytest.approx(ref_cv, rel=1e-6)
+    fr = G[name + "_f64_force"]
+    assert np.abs(r["force"] - fr).max() < 2e-4 * np.abs(fr).max()              # copysignf in the reference's double build
+
+
+@pytest.mark.parametrize("literal", [True, False])
+def test_general_mesh_pipeline_triclinic(oracle, monkeypatch, literal):
+    exe = build_emul("general_emul")
+    monkeypatch.setenv("METAD_EMUL_TILT_LITERAL", "1" if literal else "0")
+    N, dims, L, tilt, modes = 4000, (36, 20, 30), (11.0, 12.0, 13.0), (0.02, -0.01, 0.03), (1.0, -1.0)
+    pos, types = triclinic_case(N, L, tilt, len(modes), 77, faces=not literal)
+    pt = oracle.make_postype(pos, types)
+    r = run_mesh(exe, pt, dims, L, N, -0.6, 3, modes, 0.0, tilt=tilt)
+    m = oracle.Mesh(*dims, modes, L, N, "f64", tilt=tilt, literal_copysignf=False, literal_tilt_offset=literal)
+    cvo = m.current_value(pt)
+    fo = m.forces(pt, -0.6)
+    m32 = oracle.Mesh(*dims, modes, L, N, "f32", tilt=tilt)
+    m32.assign(pt)
+    assert np.array_equal(r["cells"], m32.cells())
+    assert r["cv"] == pytest.approx(cvo, rel=1e-6)
+    assert np.abs(r["rho"] - m.mesh).max() < 2e-6 * max(1.0, np.abs(m.mesh).max())
+    assert np.abs(r["force"] - fo).max() <= 1e-5 * np.abs(fo).max()
+
+
 @pytest.mark.parametrize("name", ["m0", "m1", "m2"])
 def test_mesh_pipeline_matches_reference_vectors(name):
     """The device code (CPU emulation) against outputs of the REFERENCE's own OrderParameterMesh.cc, double build

@@ -72,6 +72,29 @@ def test_mesh_cv_in_a_triclinic_box_through_the_api(api, oracle):
     assert np.abs(f - fo).max() < 2e-5 * np.abs(fo).max()          # the umbrella's bias factor carries the CV's 1e-6
 
 
+def test_mesh_cv_with_a_mesh_that_is_not_a_power_of_two_through_the_api(api, oracle):
+    """cv.mesh(nx=24, ny=20, nz=18): the reference takes any mesh size on one rank (OrderParameterMesh.cc:70-79)."""
+    cv, integrate, hoomd = api
+    N, L = 3000, (11.0, 9.5, 8.0)
+    rng = np.random.default_rng(5)
+    pos = ((rng.random((N, 3)) - 0.5) * np.asarray(L)).astype(np.float32)
+    types = rng.integers(0, 2, N).astype(np.int32)
+    hoomd.init.from_arrays(pos, types, ["A", "B"], L)
+    integrate.mode_standard(dt=0.001)
+    mesh = cv.mesh(nx=24, ny=20, nz=18, mode={'A': 1.0, 'B': -1.0})
+    cv0 = 0.01
+    mesh.set_params(umbrella='harmonic', cv0=cv0, kappa=50.0)
+    hoomd.run(1)
+    pt = oracle.make_postype(pos, types)
+    o = oracle.Mesh(24, 20, 18, [1.0, -1.0], L, N, "f64", literal_copysignf=False)
+    cvo = o.current_value(pt)
+    val = mesh.cpp_force.getLogValue("cv_mesh", 1)
+    assert val == pytest.approx(cvo, rel=2e-6)
+    f = mesh.get_forces()
+    fo = o.forces(pt, oracle.umbrella_bias("harmonic", cvo, 0.0, cv0=cv0, kappa=50.0))
+    assert np.abs(f - fo).max() < 2e-5 * np.abs(fo).max()
+
+
 def test_reference_test_2d_scenario(api, oracle, tmp_path):
     """reference test/test_2d.py: one particle, density + aspect-ratio CVs on a 20x30 grid, well-tempered, stride 1,
     grid dumped every step, box rescaled between two run(1) calls; a restart from bias.dat_1 must reproduce

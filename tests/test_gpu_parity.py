@@ -827,10 +827,143 @@ def test_mesh_triclinic_stale_order_and_epilogues(gpu, oracle):
     np.testing.assert_allclose(0.9 * x["virial"], vo, rtol=2e-5, atol=2e-6 * np.abs(vo).max())
 
 
+# ------------------------------------------------------------------------------------------------ mesh CV on any mesh size
+GENERAL_CASES = [
+    (2000, (24, 20, 18), (11.0, 9.5, 8.0), (1.0,), True),              # 4.2.3 | 4.5 | 2.3.3
+    (30000, (48, 30, 36), (10.0, 7.3, 21.1), (1.0, -1.0), True),
+    (1500, (7, 11, 13), (6.0, 7.0, 8.0), (1.0, -0.5, 2.0), True),      # prime lengths: one radix-n stage
+    (500, (3, 1, 2), (4.0, 5.0, 6.0), (1.0,), False),                  # taps alias onto the same cells
+    (200000, (96, 80, 100), (50.0, 40.0, 52.0), (1.0, -1.0), False),
+    (5000, (16, 16, 16), (8.0, 8.0, 8.0), (1.0,), True),               # a power of two below the tiled path's range
+    (1000, (1021, 2, 3), (100.0, 3.0, 4.0), (1.0,), False),            # the longest prime line
+]
+
+
+@pytest.mark.parametrize("N,dims,L,modes,edge", GENERAL_CASES)
+def test_mesh_general_path_any_mesh_size(gpu, oracle, N, dims, L, modes, edge):
+    """Mesh sizes that are not powers of two (or outside the tiled kernels' range) take the general path
+    (csrc/mesh_general.cuh); the reference accepts any size on one rank (OrderParameterMesh.cc:70-79)."""
+    import torch
+    Lf = np.asarray(L, float)
+    pos, types = rand_pt(N, Lf, len(modes), N % 1000 + 3)
+    if edge:
+        pos[0] = [np.float32(Lf[0]) / 2, 0, 0]
+        pos[1] = [-np.float32(Lf[0]) / 2, np.float32(Lf[1]) / 2, -np.float32(Lf[2]) / 2]
+        pos[2] = np.nextafter((Lf / 2).astype(np.float32), np.float32(0))
+    d_pt = to_dev(gpu, pos, types)
+    h_pt = host_pt(oracle, pos, types)
+    box = gpu.Box.make(Lf)
+    mesh = gpu.Mesh(*dims, modes)
+    mesh.set(1, 1)
+    mesh.set(3, 1)
+    cv = mesh.compute_cv(d_pt, N, box).cpu().item()
+    m = oracle.Mesh(*dims, modes, Lf, N, "f64", literal_copysignf=False)
+    cvo = m.current_value(h_pt)
+    m32 = oracle.Mesh(*dims, modes, Lf, N, "f32")
+    m32.assign(h_pt)
+    assert np.array_equal(mesh.cells(), m32.cells())
+    assert mesh.mode_sq() == m.mode_sq()
+    assert np.abs(mesh.rho() - m.mesh).max() < 2e-6 * max(1.0, np.abs(m.mesh).max())
+    assert cv == pytest.approx(cvo, rel=1e-6)
+    dinv = mesh.inv() - m.inv_re
+    dinv -= dinv.mean()
+    assert np.abs(dinv).max() < 5e-6 * np.abs(m.inv_re - m.inv_re.mean()).max()
+    bias = torch.tensor([0.61], dtype=torch.float64, device="cuda")
+    f = mesh.forces(d_pt, N, box, bias).cpu().numpy()
+    fo = m.forces(h_pt, 0.61)
+    assert np.abs(f - fo).max() <= 1e-5 * np.abs(fo).max()
+    assert np.all(f[:, 3] == 0)
+    # integer accumulation and fixed summation orders: a second evaluation, and a shuffled input, are bitwise identical
+    cv2 = mesh.compute_cv(d_pt, N, box).cpu().item()
+    f2 = mesh.forces(d_pt, N, box, bias).cpu().numpy()
+    assert cv2 == cv and np.array_equal(f, f2)
+    perm = np.random.default_rng(1).permutation(N)
+    d_sh = to_dev(gpu, pos[perm], types[perm])
+    rho1 = mesh.rho().copy()
+    mesh.compute_cv(d_sh, N, box)
+    assert np.array_equal(mesh.rho(), rho1)
+
+
+@pytest.mark.parametrize("name", ["t1", "t2"])
+def test_mesh_general_path_against_reference_vectors(gpu, oracle, name):
+    """Vectors t1 (24 x 20 x 18, orthorhombic) and t2 (20 x 12 x 18, triclinic) of the REFERENCE's own OrderParameterMesh.cc."""
+    import torch
+    G = _ref_gold()
+    c = G[name + "_cfg"]
+    dims, L, tilt, bias, modes = tuple(int(v) for v in c[:3]), tuple(c[3:6]), tuple(c[6:9]), float(c[9]), tuple(c[10:])
+    pt = G[name + "_postype"]
+    N = pt.shape[0]
+    d_pt = torch.from_numpy(pt).cuda()
+    box = gpu.Box.make(L, tilt)
+    mesh = gpu.Mesh(*dims, modes)
+    mesh.set(1, 1)
+    cv = mesh.compute_cv(d_pt, N, box).cpu().item()
+    ref_cv, ref_msq = G[name + "_f64_cv"]
+    assert mesh.mode_sq() == ref_msq
+    rho = G[name + "_f64_rho"]
+    assert np.abs(mesh.rho() - rho).max() < 2e-6 * max(1.0, np.abs(rho).max())
+    assert cv == pytest.approx(ref_cv, rel=1e-6)
+    f = mesh.forces(d_pt, N, box, torch.tensor([bias], dtype=torch.float64, device="cuda")).cpu().numpy()
+    fr = G[name + "_f64_force"]
+    assert np.abs(f - fr).max() < 2e-4 * np.abs(fr).max()                   # copysignf in the reference's double build
+    m = oracle.Mesh(*dims, modes, L, N, "f64", tilt=tilt, literal_copysignf=False)
+    m.current_value(pt)
+    fo = m.forces(pt, bias)
+    assert np.abs(f - fo).max() < 1e-5 * np.abs(fo).max()
+
+
+def test_mesh_general_path_equals_tiled_path(gpu, oracle, monkeypatch):
+    """A power-of-two mesh through both paths (METAD_MESH_GENERAL=1 forces the general one): same density bit for bit when
+    the fixed-point scales agree, CV and forces within the tolerances; q_max / virial epilogues of the general path against
+    the reference's vectors."""
+    import torch
+    N, dims, L, modes = 60000, (64, 32, 64), (30.0, 16.0, 31.0), (1.0, -1.0)
+    pos, types = rand_pt(N, L, 2, 21)
+    d_pt = to_dev(gpu, pos, types)
+    box = gpu.Box.make(L)
+    bias = torch.tensor([0.4], dtype=torch.float64, device="cuda")
+    tiled = gpu.Mesh(*dims, modes)
+    tiled.set(1, 1)
+    cv_t = tiled.compute_cv(d_pt, N, box).cpu().item()
+    f_t = tiled.forces(d_pt, N, box, bias).cpu().numpy()
+    monkeypatch.setenv("METAD_MESH_GENERAL", "1")
+    gen = gpu.Mesh(*dims, modes)
+    gen.set(1, 1)
+    cv_g = gen.compute_cv(d_pt, N, box).cpu().item()
+    f_g = gen.forces(d_pt, N, box, bias).cpu().numpy()
+    assert gen.stats()["rebuilds"] == 0 and tiled.stats()["rebuilds"] == 1          # it really was the other path
+    if gen.stats()["fx_scale"] == tiled.stats()["fx_scale"]:
+        assert np.array_equal(gen.rho(), tiled.rho())
+    assert cv_g == pytest.approx(cv_t, rel=5e-7)
+    assert np.abs(f_g - f_t).max() < 5e-6 * np.abs(f_t).max()
+    # epilogues of the general path (same checks as test_mesh_qmax_and_virial_against_reference_vectors)
+    G = _ref_gold()
+    c = G["m1_cfg"]
+    dims, L, bias_r, modes = tuple(int(v) for v in c[:3]), tuple(c[3:6]), float(c[6]), tuple(c[7:])
+    pt = G["m1_postype"]
+    kmin, kmax, n = G["virial_table"]
+    kt = np.linspace(kmin, kmax, int(n))
+    dK = -2.0 * (kt - 2.0) * np.exp(-(kt - 2.0) ** 2)
+    mesh = gpu.Mesh(*dims, modes)
+    mesh.set(13, 1)
+    mesh.set_table(dK, kmin, kmax)
+    cv = mesh.compute_cv(torch.from_numpy(pt).cuda(), pt.shape[0], gpu.Box.make(L)).cpu().item()
+    assert mesh.stats()["rebuilds"] == 0
+    assert cv == pytest.approx(G["m1_f64_cv"][0], rel=1e-6)
+    x = mesh.extras()
+    ref_q = G["m1_f64_qmax"]
+    assert x["sq_max"] == pytest.approx(ref_q[3], rel=2e-6)
+    assert np.allclose(x["q_max"], ref_q[:3], rtol=1e-6, atol=1e-12) or np.allclose(x["q_max"], -ref_q[:3], rtol=1e-6, atol=1e-12)
+    ref_v = G["m1_f64_virial"]
+    np.testing.assert_allclose(bias_r * x["virial"], ref_v, rtol=2e-5, atol=2e-6 * np.abs(ref_v).max())
+
+
 def test_mesh_rejects_unsupported(gpu):
     from metadynamics_plugin_b200._abi import MetadError
-    with pytest.raises(MetadError, match="power of two"):
-        gpu.Mesh(48, 32, 32, [1.0])
+    with pytest.raises(MetadError, match="1024"):
+        gpu.Mesh(2048, 32, 32, [1.0])
+    with pytest.raises(MetadError):
+        gpu.Mesh(0, 32, 32, [1.0])
     mesh = gpu.Mesh(32, 32, 32, [1.0])
     import torch
     pt = gpu.make_postype(np.zeros((4, 3), np.float32))

@@ -209,6 +209,8 @@ def test_slab_rejects_bad_decompositions(gpu):
         sharded.MeshSlabRank(64, 16, 16, 4, 0, [1.0])             # nx/2/P = 8 < 16
     with pytest.raises(MetadError):
         sharded.MeshSlabRank(128, 16, 16, 3, 0, [1.0])            # not a power of two
+    with pytest.raises(MetadError, match="power of two"):
+        sharded.MeshSlabRank(96, 32, 32, 2, 0, [1.0])             # like the reference under domain decomposition (OrderParameterMesh.cc:70-79)
 
 
 def test_lamellar_sharded_local(gpu, oracle):
