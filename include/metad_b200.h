@@ -28,7 +28,7 @@ enum {
     METAD_OK = 0,
     METAD_ERR_INVALID = -1,     /* bad argument */
     METAD_ERR_CUDA = -2,        /* CUDA runtime error (see metad_last_error) */
-    METAD_ERR_UNSUPPORTED = -3, /* valid in the reference, not implemented here (e.g. non power-of-two mesh) */
+    METAD_ERR_UNSUPPORTED = -3, /* valid in the reference, not implemented here (e.g. a mesh beyond 1024 points per direction) */
     METAD_ERR_STATE = -4        /* call order violated (e.g. forces before cv) */
 };
 
@@ -78,7 +78,10 @@ int metad_lamellar_forces(metad_lamellar* p, const float* d_postype, float* d_fo
  * ---------------------------------------------------------------------------------------------- */
 typedef struct metad_mesh metad_mesh;
 
-/* nx,ny,nz: mesh points (powers of two, 32 <= nx <= 1024, 16 <= ny,nz <= 512); mode: ntypes per-type coefficients. */
+/* nx,ny,nz: mesh points, 1 <= n <= 1024 each (the reference takes any size on one rank, OrderParameterMesh.cc:70-79);
+ * powers of two with 32 <= nx <= 1024, 16 <= ny,nz <= 512 run through the tiled kernels, every other size through the
+ * general path (csrc/mesh_general.cuh: same results, slower).  mode: ntypes per-type coefficients.  The box of every call
+ * may be triclinic (metad_box.tilt, key 16 of metad_mesh_set). */
 int metad_mesh_create(metad_mesh** out, unsigned nx, unsigned ny, unsigned nz, int ntypes, const double* mode);
 int metad_mesh_destroy(metad_mesh* p);
 
@@ -121,7 +124,8 @@ int metad_mesh_set_table(metad_mesh* p, const double* dK, unsigned n, double k_m
  *                               Re IFFT(G) to d_planes_out[0], [1] (to send to rank r-1 / r+1)
  *      -> neighbour exchange: d_ghost_inv[0] = last plane of rank r-1, d_ghost_inv[1] = first plane of rank r+1
  *   metad_mesh_slab_forces      interpolateForces for the local particles
- * Requirements: n_ranks a power of two, nz/n_ranks >= 8, nx/2/n_ranks >= 16.  `global_box` is the global box. */
+ * Requirements: nx, ny, nz powers of two (32 <= nx <= 1024, 16 <= ny,nz <= 512; the reference has the same rule under domain
+ * decomposition, OrderParameterMesh.cc:70-79), n_ranks a power of two, nz/n_ranks >= 8, nx/2/n_ranks >= 16.  `global_box` is the global box. */
 int metad_mesh_slab_create(metad_mesh** out, unsigned nx, unsigned ny, unsigned nz, unsigned n_ranks, unsigned rank, int ntypes,
                            const double* mode);
 int metad_mesh_slab_spread(metad_mesh* p, const float* d_postype, unsigned N_local, const metad_box* global_box, double* d_sums,
