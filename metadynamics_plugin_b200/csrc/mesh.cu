@@ -18,6 +18,12 @@
 // weights of the 27 taps sum to zero), so results are unchanged -- but without it the fp32 transforms carry a
 // DC term ~sqrt(N) times larger than every other mode and the force mesh loses several digits.
 //
+// Triclinic boxes: the same kernels with sheared coordinates in the stencil (instantiations kSpTri / TRI), forces through
+// the reciprocal lattice vectors; with the reference's literal in-cell offsets (knob 16, Geom::tq) the derivative weights
+// do not sum to zero and the k = 0 mode is put back before the convolution (ConvParams::dc_restore).
+// Mesh sizes the tiled kernels do not take (not a power of two, or outside 32 <= nx <= 1024, 16 <= ny, nz <= 512) run
+// through the general path (mesh_general.cuh; general_create / general_cv / general_forces below).
+//
 // z-slab sharding (metad_mesh_slab_*): rank r owns the planes [r nz/P, (r+1) nz/P) and the particles inside them
 // (reference: HOOMD domain decomposition + CommunicatorGrid ghost exchange + dfft, OrderParameterMesh.cc:263-315,
 // 659-746).  Per step: local spread (the integer mesh carries one ghost plane per side), halo exchange of the two
@@ -753,7 +759,7 @@ int launch_gather(metad_mesh* p, const float* d_postype, const float* d_ghost, f
     memset(&ps, 0, sizeof ps);
     if (sync) ps = *sync;
     const Geom& g = p->g;
-    // reciprocal lattice vectors of the (orthorhombic) box without 2 pi, times the mesh dimensions (:761-769, :852-854)
+    // reciprocal lattice vectors of the box without 2 pi, times the mesh dimensions (:761-769, :852-854)
     ForceParams fp;
     memset(&fp, 0, sizeof fp);
     set_force_matrix(fp, g, box);

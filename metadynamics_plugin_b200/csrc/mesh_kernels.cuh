@@ -45,7 +45,8 @@ constexpr int kHalo = 2;
 constexpr int kHaloX = 4;
 
 struct Geom {
-    unsigned nx, ny, nz;        // mesh points of the LOCAL mesh (powers of two); nz = planes of this z slab
+    unsigned nx, ny, nz;        // mesh points of the LOCAL mesh (powers of two on the tiled path; any size on the general path, which
+                                // uses only nx, ny, nz, nzg and the box members); nz = planes of this z slab
     unsigned lgx, lgy, lgz;     // log2 of the above
     unsigned nzg, z0;           // global number of z planes and first global plane of this slab (nzg = nz, z0 = 0 if unsharded)
     unsigned slab;              // 1: z is not periodic locally, the planes z0-1 and z0+nz belong to the neighbour ranks
