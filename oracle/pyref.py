@@ -205,3 +205,45 @@ def wte(net_force, net_torque, net_virial6N, external_energy, external_virial6, 
     rc = lib(prec).ref_wte(f.shape[0], _d(f), _d(t), _d(v), C.c_double(external_energy), _d(e), C.c_double(bias), C.byref(pe))
     assert rc == 0
     return dict(pe=pe.value, force=f, torque=t, virial=v, external_virial=e)
+
+
+class StepPlan:
+    """A CV object of the reference (OrderParameterMesh or LamellarOrderParameter) on a resident particle set; step(bias) runs
+    getCurrentValue + setBiasFactor + computeBiasForces for a new timestep -- the reference's own CPU implementation of the
+    hot path, what bench.py's `--impl reference` arm and `cpu_baseline` time when oracle/_ref is built."""
+
+    def __init__(self, kind, postype, L, mode, prec="f32", dims=None, lattice_vectors=None, tilt=(0, 0, 0)):
+        self.l = lib(prec)
+        self.l.ref_step_create_mesh.restype = C.c_void_p
+        self.l.ref_step_create_lamellar.restype = C.c_void_p
+        self.l.ref_step.argtypes = [C.c_void_p, C.c_double, _dp, _dp]
+        self.l.ref_step_force.argtypes = [C.c_void_p, C.c_uint, _dp]
+        self.l.ref_step_destroy.argtypes = [C.c_void_p]
+        mode = np.ascontiguousarray(mode, np.float64)
+        Lb, tb = _box(L, tilt)
+        pt = np.ascontiguousarray(postype, np.float32)
+        if kind == "mesh":
+            nx, ny, nz = dims
+            self.h = self.l.ref_step_create_mesh(nx, ny, nz, _d(mode), len(mode), _d(Lb), _d(tb), pt.ctypes.data_as(_fp), pt.shape[0])
+        else:
+            lv = np.ascontiguousarray(lattice_vectors, np.int32).reshape(-1, 3)
+            self.h = self.l.ref_step_create_lamellar(_d(mode), len(mode), lv.ctypes.data_as(_ip), lv.shape[0], _d(Lb), _d(tb),
+                                                     pt.ctypes.data_as(_fp), pt.shape[0])
+        if not self.h:
+            raise RuntimeError("the reference's CV object could not be created")
+
+    def step(self, bias):
+        cv, sec = C.c_double(), np.zeros(2)
+        if self.l.ref_step(self.h, float(bias), C.byref(cv), _d(sec)) != 0:
+            raise RuntimeError("ref_step failed")
+        return cv.value, float(sec[0]), float(sec[1])
+
+    def force(self, i):
+        out = np.zeros(4)
+        self.l.ref_step_force(self.h, int(i), _d(out))
+        return out
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.l.ref_step_destroy(self.h)
+            self.h = None

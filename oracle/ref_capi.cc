@@ -9,7 +9,9 @@
 #include <hoomd/extern/kiss_fftnd.h>
 #include <hoomd/extern/pybind/include/pybind11/pybind11.h>
 #include <hoomd/md/IntegratorTwoStep.h>
+#include <chrono>
 #include <cstdio>
+#include <memory>
 #include <string.h>
 #define private public
 #define protected public
@@ -74,9 +76,67 @@ template <class T, class U> void dump(const GPUArray<T>& a, U* out) {
 }
 }  // namespace
 
+namespace {
+// A CV object of the reference on a particle set that stays resident, as in a simulation: what bench.py times as the
+// reference's own CPU implementation of the step (getCurrentValue(t) + setBiasFactor + computeBiasForces(t), new timestep
+// every call so that the per-timestep cache of the CV never answers).
+struct RefStepPlan {
+    std::shared_ptr<SystemDefinition> sys;
+    std::unique_ptr<CollectiveVariable> cv;
+    unsigned t = 0;
+};
+}  // namespace
+
 extern "C" {
 
 int ref_scalar_bytes() { return (int)sizeof(Scalar); }
+
+void* ref_step_create_mesh(unsigned nx, unsigned ny, unsigned nz, const double* mode, unsigned ntypes, const double* L, const double* tilt,
+                           const float* postype, unsigned N) {
+    try {
+        auto* p = new RefStepPlan();
+        p->sys = make_system(postype, N, L, tilt, ntypes);
+        std::vector<Scalar> m(mode, mode + ntypes);
+        p->cv.reset(new OrderParameterMesh(p->sys, nx, ny, nz, m));
+        return p;
+    } catch (const std::exception& e) { fprintf(stderr, "ref_step_create_mesh: %s\n", e.what()); return nullptr; }
+}
+void* ref_step_create_lamellar(const double* mode, unsigned ntypes, const int* lattice, unsigned n_wave, const double* L, const double* tilt,
+                               const float* postype, unsigned N) {
+    try {
+        auto* p = new RefStepPlan();
+        p->sys = make_system(postype, N, L, tilt, ntypes);
+        std::vector<Scalar> m(mode, mode + ntypes);
+        std::vector<int3> lv(n_wave);
+        for (unsigned k = 0; k < n_wave; ++k) lv[k] = make_int3(lattice[3 * k], lattice[3 * k + 1], lattice[3 * k + 2]);
+        p->cv.reset(new LamellarOrderParameter(p->sys, m, lv, ""));
+        return p;
+    } catch (const std::exception& e) { fprintf(stderr, "ref_step_create_lamellar: %s\n", e.what()); return nullptr; }
+}
+// one step; seconds[0] = getCurrentValue, seconds[1] = computeBiasForces (wall clock)
+int ref_step(void* h, double bias, double* cv, double* seconds) {
+    try {
+        auto* p = (RefStepPlan*)h;
+        ++p->t;
+        const auto t0 = std::chrono::steady_clock::now();
+        *cv = (double)p->cv->getCurrentValue(p->t);
+        const auto t1 = std::chrono::steady_clock::now();
+        p->cv->setBiasFactor((Scalar)bias);
+        p->cv->computeBiasForces(p->t);
+        const auto t2 = std::chrono::steady_clock::now();
+        seconds[0] = std::chrono::duration<double>(t1 - t0).count();
+        seconds[1] = std::chrono::duration<double>(t2 - t1).count();
+        return 0;
+    } catch (const std::exception& e) { fprintf(stderr, "ref_step: %s\n", e.what()); return -1; }
+}
+// force of particle i after the last step (spot checks)
+int ref_step_force(void* h, unsigned i, double* out4) {
+    auto* p = (RefStepPlan*)h;
+    ArrayHandle<Scalar4> f(p->cv->getForceArray(), access_location::host, access_mode::read);
+    out4[0] = f.data[i].x; out4[1] = f.data[i].y; out4[2] = f.data[i].z; out4[3] = f.data[i].w;
+    return 0;
+}
+void ref_step_destroy(void* h) { delete (RefStepPlan*)h; }
 
 // OrderParameterMesh: getCurrentValue (assignParticles + updateMeshes + computeCV), then computeBiasForces with `bias`.
 // Outputs (double): cv, mode_sq, force[4N], rho[M] = Re(mesh), inv[M] = Re(inverse mesh), interp[M]
