@@ -961,7 +961,7 @@ def run_reference(args):
         return
     w = make_workload(args.workload)
     step, phases, kind, what = cpu_arm(w)
-    budget = 280.0                       # seconds for the whole arm: a full C4 step takes ~40 s in the reference's own code, 7.5 s in the port
+    budget = 200.0                       # seconds for the whole arm: a full C4 step takes ~40 s in the reference's own code, 7.5 s in the port
     t_start = time.perf_counter()
     done_w = 0
     for _ in range(args.warmup):
