@@ -281,9 +281,10 @@ TRI_CASES = [k[:-4] for k in GOLD.files if k.endswith("_cfg") and k.startswith("
 @pytest.mark.parametrize("name", TRI_CASES)
 @pytest.mark.parametrize("prec", ["f64", "f32"])
 def test_oracle_mesh_triclinic_and_general_sizes(oracle, name, prec):
-    """Triclinic boxes and mesh sizes that are not powers of two (the device path rejects both for now, SURVEY 8a rows
-    a3-a9 allow them): the oracle already reproduces the reference's own code -- density bit for bit, CV and forces to
-    rounding in the double build."""
+    """Triclinic boxes and mesh sizes that are not powers of two (on the device: the TRI instantiations of
+    the tiled kernels and csrc/mesh_general.cuh, tests/test_gpu_parity.py): the oracle reproduces the reference's own code --
+    density bit for bit, CV and forces to rounding in the double build -- including what the reference does to the in-cell
+    offsets in a sheared box (metad_oracle.hpp: literal_tilt_offset)."""
     c = GOLD[name + "_cfg"]
     dims, L, tilt, bias, modes = tuple(int(v) for v in c[:3]), tuple(c[3:6]), tuple(c[6:9]), float(c[9]), tuple(c[10:])
     pt = GOLD[name + "_postype"]
